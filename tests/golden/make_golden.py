@@ -1,0 +1,481 @@
+#!/usr/bin/env python3
+"""Generate the golden fixtures under tests/golden/ by RUNNING THE REFERENCE (test infrastructure only).
+
+Runs in the build container only (needs /root/reference); the GPU box never executes this file, it only
+reads the committed .npz fixtures.  Every array written here is an output of unmodified reference code
+(pyLabFEA v4.4.2 @ c488572) on seeded inputs:
+
+  response_<mat>.npz  Material.response (material.py:207-346) on (sig, epl, deps, CV) tuples that populate the
+                      elastic / split / 1-step / 50-sub-step / radial-correction branches; plus calc_seq
+                      (576-676), calc_yf (348-412), calc_fgrad (704-858), epl_dot (1009-1055), C_tan (1057-1086).
+  kmat_<case>.npz     Element.calc_Bmat / calc_Kel (model.py:365-370, 439-512) and Model.setupK (954-977):
+                      B matrices, Kel and the dense K (stored as COO of its non-zeros) for elastic and plastic
+                      element tangents.
+  solve_<case>.npz    Model.solve (model.py:979-1450) end-to-end: u, f, element sig/eps/epl, sgl/egl/epgl, niter.
+  svc_<name>.npz      a trained sklearn SVC (support vectors, dual coefs, intercept, gamma, scale_seq) plus
+                      calc_yf / calc_fgrad / ML_full_yf / response outputs of the reference on it.
+  barlat.npz          Material.calc_seq for Yld2004-18p (material.py:678-702).
+
+usage: python tests/golden/make_golden.py [response] [kmat] [solve] [svc] [barlat] [all]
+"""
+import os
+import sys
+import time
+import warnings
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, HERE)
+from ref_shim import import_reference  # noqa: E402
+
+FE = import_reference()
+warnings.filterwarnings('ignore')
+
+
+# ----------------------------------------------------------------------------------------------
+# materials
+# ----------------------------------------------------------------------------------------------
+def make_material(name):
+    m = FE.Material(name=name)
+    if name == 'j2':        # BASELINE config 2 / target
+        m.elasticity(E=200.e3, nu=0.3)
+        m.plasticity(sy=150., khard=500., sdim=6)
+    elif name == 'j2pp':    # perfectly plastic J2
+        m.elasticity(E=200.e3, nu=0.3)
+        m.plasticity(sy=150., khard=0., sdim=6)
+    elif name == 'hill':    # BASELINE config 3, reference tests/test_basic.py:130-133 uses sy=100
+        m.elasticity(E=200.e3, nu=0.3)
+        m.plasticity(sy=150., hill=[0.7, 1., 1.4, 1., 1.2, 0.8], khard=100., sdim=6)
+    elif name == 'hillrv':  # examples/train_hill.py:26-33 reference material of config 4
+        m.elasticity(E=200.e3, nu=0.3)
+        m.plasticity(sy=50., rv=[1.2, 1.0, 0.8, 1.0, 1.0, 1.0], sdim=6)
+    elif name == 'drucker':  # tension-compression asymmetry (never used in notebooks, cheap to pin)
+        m.elasticity(E=100.e3, nu=0.27)
+        m.plasticity(sy=120., hill=[1.2, 0.9, 1.1, 1.1, 0.9, 1.0], drucker=0.1, khard=300., sdim=6)
+    elif name == 'cubic':   # C11/C12/C44 elasticity + J2 hardening
+        m.elasticity(C11=170.e3, C12=124.e3, C44=75.e3)
+        m.plasticity(sy=200., khard=1000., sdim=6)
+    else:
+        raise ValueError(name)
+    return m
+
+
+def mat_params(m):
+    d = dict(E=m.E, nu=m.nu, C11=m.C11, C12=m.C12, C44=m.C44, CV=np.array(m.CV))
+    if m.sy is not None:
+        d.update(sy=m.sy, khard=m.khard, hill=np.array(m.hill, dtype=float),
+                 drucker=float(m.drucker), sdim=m.sdim)
+    return d
+
+
+def cv_plane_stress(m):
+    """Element.__init__ plane-stress CV (model.py:274-283)."""
+    hh = m.E / (1 - m.nu * m.nu)
+    C12 = m.nu * hh
+    C11 = hh
+    return np.array([[C11, C12, 0., 0., 0., 0.],
+                     [C12, C11, 0., 0., 0., 0.],
+                     [0., 0., 0., 0., 0., 0.],
+                     [0., 0., 0., 0., 0., 0.],
+                     [0., 0., 0., 0., 0., 0.],
+                     [0., 0., 0., 0., 0., m.C44]])
+
+
+def rand_dirs(rng, n, planar):
+    d = rng.standard_normal((n, 6))
+    if planar:
+        d[:, 2:5] = 0.
+    return d
+
+
+def make_tuples(m, rng, n, planar):
+    """Random (sig, epl, deps) states: SURVEY.md §8d recipe, extended with large increments so the
+    radial-correction branch (material.py:310-342) fires."""
+    sig = np.zeros((n, 6))
+    epl = np.zeros((n, 6))
+    deps = np.zeros((n, 6))
+    dirs = rand_dirs(rng, n, planar)
+    for i in range(n):
+        # plastic strain history: none / uniaxial-like / random deviatoric
+        c = i % 3
+        if c == 1:
+            epl[i] = rng.uniform(0., 0.02) * np.array([1., -.5, -.5, 0., 0., 0.])
+        elif c == 2:
+            e = rng.standard_normal(6) * 0.005
+            e[0:3] -= e[0:3].mean()
+            if planar:
+                e[3:5] = 0.
+            epl[i] = e
+        sflow = m.get_sflow(epl[i])
+        s = dirs[i]
+        seq = m.calc_seq(s)
+        # radius: mostly inside, many close to / on the yield surface
+        u = rng.uniform()
+        if u < 0.35:
+            r = rng.uniform(0., 0.9)
+        elif u < 0.7:
+            r = rng.uniform(0.9, 1.0)
+        else:
+            r = rng.uniform(0.996, 1.004)
+        sig[i] = s / seq * r * sflow
+        de = rng.standard_normal(6)
+        if planar:
+            de[3:5] = 0.
+        if i % 7 == 0:  # mostly radial loading direction (elastic strain direction of sig)
+            de = np.linalg.lstsq(m.CV, sig[i] + 1e-3 * de, rcond=None)[0]
+            if planar:
+                de[3:5] = 0.
+        mag = [5.e-4, 5.e-4, 2.e-3, 1.e-2, 1.e-4][i % 5]
+        deps[i] = de / FE.eps_eq(de) * mag
+    return sig, epl, deps
+
+
+def gen_response():
+    for name in ['j2', 'j2pp', 'hill', 'hillrv', 'drucker', 'cubic']:
+        m = make_material(name)
+        out = dict(mat_params(m))
+        t0 = time.time()
+        for planar, tag in [(False, 'pe'), (True, 'ps')]:
+            rng = np.random.default_rng(42 + planar)
+            n = 240
+            CV = cv_plane_stress(m) if planar else np.array(m.CV)
+            sig, epl, deps = make_tuples(m, rng, n, planar)
+            fy = np.zeros(n)
+            so = np.zeros((n, 6))
+            dp = np.zeros((n, 6))
+            ct = np.zeros((n, 6, 6))
+            ns = np.zeros(n, dtype=np.int32)
+            seq = np.zeros(n)
+            yf = np.zeros(n)
+            fg = np.zeros((n, 6))
+            ed = np.zeros((n, 6))
+            ctan = np.zeros((n, 6, 6))
+            for i in range(n):
+                m.msg['nsteps'] = -1
+                r = m.response(sig[i], epl[i], deps[i], CV)
+                fy[i], so[i], dp[i], ct[i] = r
+                ns[i] = m.msg['nsteps']
+                seq[i] = m.calc_seq(sig[i])
+                yf[i] = m.calc_yf(sig[i], epl=epl[i])
+                fg[i] = m.calc_fgrad(sig[i], epl=epl[i])
+                ed[i] = m.epl_dot(sig[i], epl[i], CV, deps[i])
+                ctan[i] = m.C_tan(sig[i], CV, epl=epl[i])
+            out.update({f'{tag}_CV': CV, f'{tag}_sig': sig, f'{tag}_epl': epl, f'{tag}_deps': deps,
+                        f'{tag}_fy': fy, f'{tag}_sig_out': so, f'{tag}_depl': dp, f'{tag}_ctan': ct,
+                        f'{tag}_nsteps': ns, f'{tag}_seq': seq, f'{tag}_yf': yf, f'{tag}_fgrad': fg,
+                        f'{tag}_epl_dot': ed, f'{tag}_C_tan': ctan})
+            el = np.sum((ns == 0) & (np.abs(ct - CV).max(axis=(1, 2)) == 0))
+            print(f'  {name}/{tag}: elastic {el}, 50-step {np.sum(ns == 49)}, other {n - el - np.sum(ns == 49)}')
+        np.savez_compressed(os.path.join(HERE, f'response_{name}.npz'), **out)
+        print(f'response_{name}.npz  {time.time() - t0:.1f}s')
+
+
+# ----------------------------------------------------------------------------------------------
+# Kel / setupK
+# ----------------------------------------------------------------------------------------------
+def dense_to_coo(K):
+    r, c = np.nonzero(K)
+    return r.astype(np.int32), c.astype(np.int32), K[r, c]
+
+
+def model_arrays(fe):
+    Nel = fe.Nel
+    d = dict(NX=fe.NnodeX - 1, NY=fe.NnodeY - 1, Ndof=fe.Ndof, planestress=int(fe.planestress),
+             lenx=fe.lenx, leny=fe.leny, thick=fe.thick,
+             nodes=np.array([el.nodes for el in fe.element], dtype=np.int32),
+             lx=np.array([el.Lelx for el in fe.element]), ly=np.array([el.Lely for el in fe.element]),
+             mat_id=np.array([fe.mat.index(el.Mat) for el in fe.element], dtype=np.int32),
+             CV=np.array([el.CV for el in fe.element]),
+             npos=np.array(fe.npos))
+    d['mat_E'] = np.array([m.E for m in fe.mat])
+    d['mat_nu'] = np.array([m.nu for m in fe.mat])
+    d['mat_CV'] = np.array([m.CV for m in fe.mat])
+    return d
+
+
+def kmat_case(name, fe, tangents=None):
+    """tangents: optional (Nel,6,6) replaces el.elstiff before calc_Kel (what Model.solve does at 1351-1354)."""
+    out = model_arrays(fe)
+    if tangents is not None:
+        for el, t in zip(fe.element, tangents):
+            el.elstiff = np.array(t)
+            el.calc_Kel()
+    out['elstiff'] = np.array([el.elstiff for el in fe.element])
+    out['Bmat'] = np.array([el.Bmat for el in fe.element[:min(fe.Nel, 64)]])   # (n,4,6,8)
+    out['Kel'] = np.array([el.Kel for el in fe.element])
+    K = fe.setupK()
+    r, c, v = dense_to_coo(K)
+    out['K_row'], out['K_col'], out['K_val'] = r, c, v
+    np.savez_compressed(os.path.join(HERE, f'kmat_{name}.npz'), **out)
+    print(f'kmat_{name}.npz Nel={fe.Nel} nnz={len(v)}')
+
+
+def cantilever(N=10):
+    """BASELINE config 1."""
+    mat = FE.Material()
+    mat.elasticity(E=200.e3, nu=0.3)
+    fe = FE.Model(dim=2, planestress=True)
+    fe.geom([10.], LY=1.)
+    fe.assign([mat])
+    fe.bcleft(0., 'disp', 'x')
+    fe.bcleft(0., 'disp', 'y')
+    fe.bcbot(0., 'force', 'y')
+    fe.bctop(0., 'force', 'y')
+    fe.bcright(-10., 'force', 'y')
+    fe.mesh(NX=N, NY=N)
+    return fe
+
+
+def laminate():
+    """tests/test_basic.py:84-101 (fem_v), 5 sections, plane stress."""
+    fe = FE.Model(dim=2, planestress=True)
+    fe.geom([2, 1, 2, 1, 2], LY=4.)
+    mat1 = FE.Material()
+    mat1.elasticity(E=100.e3, nu=0.35)
+    mat2 = FE.Material()
+    mat2.elasticity(E=300.e3, nu=0.3)
+    fe.assign([mat1, mat2, mat1, mat2, mat1])
+    fe.bcleft(0.)
+    fe.bcbot(0.)
+    fe.bcright(0., 'force')
+    fe.bctop(0.1 * fe.leny, 'disp')
+    fe.mesh(NX=16, NY=4)
+    return fe
+
+
+def uneven():
+    """two sections with different element widths (dx = 1.25 / 0.75), plane strain."""
+    fe = FE.Model(dim=2, planestress=False)
+    fe.geom([2.5, 1.5], LY=3.)
+    mat1 = make_material('j2')
+    mat2 = make_material('hill')
+    fe.assign([mat1, mat2])
+    fe.bcleft(0.)
+    fe.bcbot(0.)
+    fe.bcright(0., 'force')
+    fe.bctop(0.01 * fe.leny, 'disp')
+    fe.mesh(NX=4, NY=5)
+    return fe
+
+
+def inclusion(N=18, plastic=False, planestress=False, eps_tot=0.01):
+    """tests/test_basic.py:42-76 (elastic) / examples/inclusion.py:31-62 (plastic matrix)."""
+    n1 = int(N / 3)
+    el = np.ones((N, N))
+    el[n1:2 * n1, n1:2 * n1] = 2
+    mat1 = FE.Material(num=1)
+    mat1.elasticity(E=100.e3, nu=0.27)
+    if plastic:
+        mat1.plasticity(sy=150., khard=500., sdim=6)
+    mat2 = FE.Material(num=2)
+    mat2.elasticity(E=3.e3, nu=0.3)
+    fe = FE.Model(dim=2, planestress=planestress)
+    fe.geom(sect=2, LX=4., LY=4.)
+    fe.assign([mat1, mat2])
+    fe.bcbot(0.)
+    fe.bcright(0., 'force')
+    fe.bcleft(0., 'force')
+    fe.bctop(eps_tot * fe.leny, 'disp')
+    fe.mesh(elmts=el, NX=N, NY=N)
+    hh = [no in fe.nobot for no in fe.noleft]
+    noc = np.nonzero(hh)[0]
+    fe.bcnode(noc, 0., 'disp', 'x')
+    return fe
+
+
+def uniax(matname, N=4, planestress=False, eps=0.01):
+    mat = make_material(matname)
+    fe = FE.Model(dim=2, planestress=planestress)
+    fe.geom([4.], LY=4.)
+    fe.assign([mat])
+    fe.bcleft(0.)
+    fe.bcbot(0.)
+    fe.bcright(0., 'force')
+    fe.bctop(eps * fe.leny, 'disp')
+    fe.mesh(NX=N, NY=N)
+    return fe
+
+
+def plastic_tangents(fe, seed):
+    """Element tangents as Material.response returns them (sampled from the response fixtures' recipe)."""
+    rng = np.random.default_rng(seed)
+    T = []
+    for el in fe.element:
+        m = el.Mat
+        if m.sy is None:
+            T.append(np.array(el.CV))
+            continue
+        planar = fe.planestress
+        sig, epl, deps = make_tuples(m, rng, 1, planar)
+        r = m.response(sig[0], epl[0], deps[0] * 4., el.CV)
+        T.append(r[3])
+    return np.array(T)
+
+
+def gen_kmat():
+    kmat_case('cantilever10', cantilever(10))
+    kmat_case('laminate16x4', laminate())
+    kmat_case('inclusion18', inclusion(18))
+    fe = uneven()
+    kmat_case('uneven4x5_plastic', fe, plastic_tangents(fe, 7))
+    fe = uniax('hill', N=6, planestress=True)
+    kmat_case('hill6_ps_plastic', fe, plastic_tangents(fe, 8))
+    fe = inclusion(9, plastic=True)
+    kmat_case('inclusion9_plastic', fe, plastic_tangents(fe, 9))
+    fe = cantilever(1)
+    kmat_case('single', fe)
+
+
+# ----------------------------------------------------------------------------------------------
+# end-to-end solves
+# ----------------------------------------------------------------------------------------------
+def solve_case(name, fe, **kw):
+    t0 = time.time()
+    fe.solve(**kw)
+    fe.calc_global()
+    out = model_arrays(fe)
+    out.update(u=fe.u, f=fe.f,
+               sig=np.array([el.sig for el in fe.element]),
+               eps=np.array([el.eps for el in fe.element]),
+               epl=np.array([el.epl for el in fe.element]),
+               elstiff=np.array([el.elstiff for el in fe.element]),
+               sgl=fe.sgl, egl=fe.egl, epgl=fe.epgl, niter=np.array(fe.niter), nsteps=fe.nsteps,
+               co_nconv=np.array(fe.co_nconv),
+               glob_sig=fe.glob['sig'], glob_eps=fe.glob['eps'], glob_epl=fe.glob['epl'],
+               glob_bc=np.array([fe.glob[k] for k in ('ebc1', 'sbc1', 'ebc21', 'sbc21', 'ebc2', 'sbc2', 'ebc12', 'sbc12')]),
+               wall_s=time.time() - t0)
+    np.savez_compressed(os.path.join(HERE, f'solve_{name}.npz'), **out)
+    print(f'solve_{name}.npz  {time.time() - t0:.1f}s  nsteps={fe.nsteps} niter={fe.niter}')
+
+
+def gen_solve():
+    solve_case('cantilever10', cantilever(10))
+    solve_case('laminate16x4', laminate())
+    solve_case('inclusion18_elastic', inclusion(18))
+    solve_case('j2_4x4', uniax('j2', 4), min_step=20)
+    solve_case('hill_4x4_ps', uniax('hill', 4, planestress=True), min_step=10)
+    solve_case('j2_inclusion6', inclusion(6, plastic=True), min_step=8)
+
+
+# ----------------------------------------------------------------------------------------------
+# SVC
+# ----------------------------------------------------------------------------------------------
+def svc_arrays(m):
+    svm = m.svm_yf
+    return dict(sv=np.array(svm.support_vectors_), dual=np.array(svm.dual_coef_[0]),
+                rho=float(svm.intercept_[0]), gamma=float(m.gam_yf), scale_seq=float(m.scale_seq),
+                dev_only=int(bool(m.dev_only)), sy=float(m.sy), khard=float(m.khard),
+                E=m.E, nu=m.nu, CV=np.array(m.CV), sdim=m.sdim, Ndof=m.Ndof,
+                hill=np.array(m.hill, dtype=float), drucker=float(m.drucker))
+
+
+def gen_svc():
+    # (1) examples/train_hill.py:26-49 recipe (BASELINE config 4)
+    t0 = time.time()
+    mat_h = make_material('hillrv')
+    m = FE.Material('ML-Hill-p1', num=2)
+    m.train_SVC(C=2.0, gamma=1.0, mat_ref=mat_h, Nseq=25, Nlc=300, Fe=0.1, Ce=0.99, gridsearch=False)
+    print('trained: nsv =', len(m.svm_yf.support_vectors_), f'{time.time() - t0:.1f}s')
+    out = svc_arrays(m)
+    rng = np.random.default_rng(5)
+    n = 400
+    s = rng.standard_normal((n, 6))
+    seq = mat_h.calc_seq(s)
+    sig = s / seq[:, None] * (rng.uniform(0.05, 1.6, n) * m.sy)[:, None]
+    out['yf_sig'] = sig
+    out['yf'] = m.calc_yf(sig)                      # batched decision function (material.py:398-405)
+    fg = np.zeros((n, 6))
+    for i in range(n):
+        fg[i] = m.calc_fgrad(sig[i])
+    out['fgrad'] = fg
+    nf = 120
+    fyf = np.zeros(nf)
+    for i in range(nf):
+        fyf[i] = m.ML_full_yf(sig[i])
+    out['ML_full_yf'] = fyf
+    # response tuples
+    nr = 48
+    CVs = {'pe': np.array(m.CV), 'ps': cv_plane_stress(m)}
+    for tag, CV in CVs.items():
+        planar = tag == 'ps'
+        rs, re, rd = make_tuples(mat_h, np.random.default_rng(11 + planar), nr, planar)
+        # SVC material has no work hardening features -> perfectly plastic; keep epl small
+        fy = np.zeros(nr)
+        so = np.zeros((nr, 6))
+        dp = np.zeros((nr, 6))
+        ct = np.zeros((nr, 6, 6))
+        ns = np.zeros(nr, dtype=np.int32)
+        kh = np.zeros(nr)
+        t1 = time.time()
+        for i in range(nr):
+            m.khard = 0.
+            r = m.response(rs[i], re[i], rd[i], CV)
+            fy[i], so[i], dp[i], ct[i] = r
+            ns[i] = m.msg['nsteps']
+            kh[i] = m.khard
+        print(f'  svc response {tag}: {time.time() - t1:.1f}s')
+        out.update({f'{tag}_CV': CV, f'{tag}_sig': rs, f'{tag}_epl': re, f'{tag}_deps': rd, f'{tag}_fy': fy,
+                    f'{tag}_sig_out': so, f'{tag}_depl': dp, f'{tag}_ctan': ct, f'{tag}_nsteps': ns})
+    np.savez_compressed(os.path.join(HERE, 'svc_hill.npz'), **out)
+    print(f'svc_hill.npz {time.time() - t0:.1f}s')
+
+    # (2) tests/test_ml.py:170-201 (test_ml_shear): SVC in FE, 6x3 plane stress simple shear
+    t0 = time.time()
+    mat_h = FE.Material(name='Hill-shear')
+    mat_h.elasticity(E=200.e3, nu=0.3)
+    mat_h.plasticity(sy=150., hill=[1.4, 1., 0.7, 1.2, .8, 1.], sdim=6)
+    m = FE.Material('Hill-ML')
+    m.train_SVC(C=2, gamma=0.5, mat_ref=mat_h, Nseq=4, Nlc=300, Fe=0.7, Ce=0.95)
+    m.dev_only = False
+    out = svc_arrays(m)
+    fem = FE.Model(dim=2, planestress=True)
+    fem.geom([2], LY=2.)
+    fem.assign([m])
+    fem.bcbot(0., bctype='disp', bcdir='y')
+    fem.bcbot(0., bctype='disp', bcdir='x')
+    fem.bcleft(0., bctype='force')
+    fem.bcright(0., bctype='force')
+    fem.bctop(0.006 * fem.leny, bctype='disp', bcdir='x')
+    fem.bctop(0., bctype='disp', bcdir='y')
+    fem.mesh(NX=6, NY=3)
+    fem.solve()
+    fem.calc_global()
+    out.update(u=fem.u, f=fem.f, sig=np.array([el.sig for el in fem.element]),
+               eps=np.array([el.eps for el in fem.element]), epl=np.array([el.epl for el in fem.element]),
+               sgl=fem.sgl, egl=fem.egl, epgl=fem.epgl, niter=np.array(fem.niter), nsteps=fem.nsteps,
+               glob_sig=fem.glob['sig'])
+    np.savez_compressed(os.path.join(HERE, 'svc_shear.npz'), **out)
+    print(f'svc_shear.npz {time.time() - t0:.1f}s glob sig5={fem.glob["sig"][5]} (golden 77.53778881971623)')
+
+
+def gen_barlat():
+    # examples/train_goss_barlat.py:36-41
+    bp = None
+    src = open('/root/reference/examples/train_goss_barlat.py').read()
+    ns = {}
+    for line in src.splitlines():
+        if line.strip().startswith('bp ='):
+            i = src.index(line)
+            j = src.index(']', i)
+            exec(src[i:j + 1].strip(), {'np': np}, ns)
+            bp = ns['bp']
+            break
+    m = FE.Material('Goss-Barlat')
+    m.elasticity(E=151220., nu=0.3)
+    m.plasticity(sy=46.76, barlat=bp, barlat_exp=8, sdim=6)
+    rng = np.random.default_rng(3)
+    sig = rng.standard_normal((300, 6)) * 40.
+    sig[::5, 3:5] = 0.
+    seq = m.calc_seq(sig)
+    np.savez_compressed(os.path.join(HERE, 'barlat.npz'), bp=np.array(bp, dtype=float), barlat_exp=8.,
+                        Bar_m1=m.Bar_m1, Bar_m2=m.Bar_m2, sig=sig, seq=seq, sy=46.76, E=151220., nu=0.3)
+    print('barlat.npz', seq[:3])
+
+
+if __name__ == '__main__':
+    what = sys.argv[1:] or ['all']
+    if 'all' in what:
+        what = ['response', 'kmat', 'solve', 'svc', 'barlat']
+    for w in what:
+        print('==', w)
+        globals()['gen_' + w]()
