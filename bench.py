@@ -1,0 +1,395 @@
+#!/usr/bin/env python3
+"""bench.py -- headline benchmark of the hot path (BASELINE.json metric) on N B200s.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--mesh 1024]
+
+One "step" = one pass of the non-linear inner loop of Model.solve over one mesh: the batched return mapping
+(Material.response for every element) followed by the K integration + CSR assembly (Model.setupK) from the freshly
+computed tangents.  Workload (config.workload): 1024x1024 Q4 mesh, J2 plasticity (sy=150, khard=500, E=200e3,
+nu=0.3, plane strain), synthetic spatially correlated element states (seeded) that populate the elastic / 1-step /
+50-sub-step branches of the reference algorithm.  N>1 (torchrun): every rank owns its own mesh block of the same size
+(weak scaling, no data-path collective -- element updates and element rows are independent).
+
+`value`  : elements/s through (stress update + assembly), inputs resident in HBM, CUDA events, max over ranks.
+`e2e`    : same step through the C-ABI calls that take HOST buffers (plf_response_batch + plf_setupK_from_batch +
+           plf_get_csr), pinned host memory, H2D + D2H inside the timed region.
+`roofline`: return-mapping kernel(s): 540 B/update over the measured launch time vs MEASURED_PEAKS.json.
+`cpu_baseline`: the CPU oracle (port of the reference algorithm, oracle/plf_oracle.c) on a bounded sample.
+--impl reference: the same step on the host cores only (oracle port, all threads), bounded sample per step.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+E_MOD, NU, SY, KHARD = 200.e3, 0.3, 150., 500.
+BYTES_PER_UPDATE = 540.    # 144 B in + 4 B id + 392 B out
+BYTES_PER_ASSEMBLED = 592.  # 288 B tangent + 16 B connectivity-equivalent + 288 B CSR values
+
+
+def j2_material():
+    from pylabfea_b200 import _lib
+    m = _lib.PlfMaterial()
+    m.kind = _lib.MAT_HILL
+    m.E, m.nu = E_MOD, NU
+    hh = E_MOD / ((1. + NU) * (1. - 2. * NU))
+    C11, C12, C44 = (1. - NU) * hh, NU * hh, (0.5 - NU) * hh
+    CV = np.zeros((6, 6))
+    CV[0, 0] = CV[1, 1] = CV[2, 2] = C11
+    CV[0, 1] = CV[0, 2] = CV[1, 2] = CV[1, 0] = CV[2, 0] = CV[2, 1] = C12
+    CV[3, 3] = CV[4, 4] = CV[5, 5] = C44
+    m.CV[:] = list(CV.ravel())
+    m.C44 = C44
+    m.sy, m.khard = SY, KHARD
+    m.hill[:] = [1.] * 6
+    m.d[:] = [0.] * 3
+    return m, CV
+
+
+def synth_states(N, seed, correlated=True):
+    """Element states for an N x N mesh (element id = j*N + k).  Seeded, no file I/O.
+
+    correlated: a stress field as a loaded inclusion problem produces it -- uniaxial-y dominated stress whose level
+    (fraction of the flow stress) and direction vary smoothly in space (low-frequency Fourier modes), accumulated
+    plastic strain where the level is high, and a smooth strain increment of eps_eq ~ 5e-4 with
+    5 % element-wise noise.  Uncorrelated: the same marginals shuffled element-wise (worst case for divergence)."""
+    rng = np.random.default_rng(seed)
+    j, k = np.meshgrid(np.arange(N), np.arange(N), indexing='ij')
+    x, y = (j + .5) / N, (k + .5) / N
+
+    def smooth(nm=4):
+        f = np.zeros_like(x)
+        for _ in range(nm):
+            kx, ky = rng.integers(1, 4, 2)
+            f += rng.uniform(.3, 1.) * np.sin(2 * np.pi * (kx * x + rng.uniform())) * np.cos(2 * np.pi * (ky * y + rng.uniform()))
+        return f / nm
+    level = np.clip(0.53 + 1.9 * smooth(), 0.05, 1.0)            # seq / sflow before the increment (mix ~ 1/3 elastic, 12-15 % 50-sub-step as measured in reference solves)
+    peeq = np.where(level > 0.97, 0.01 * (1. + smooth()), 0.)      # yielded zones carry plastic strain
+    peeq = np.clip(peeq, 0., None)
+    ang = 0.35 * smooth()                                          # in-plane rotation of the principal axis
+    n = N * N
+    sig = np.zeros((n, 6))
+    c, s = np.cos(ang).ravel(), np.sin(ang).ravel()
+    s1 = np.ones(n)                                                # uniaxial unit stress along the rotated y axis
+    sig[:, 0] = s1 * s * s
+    sig[:, 1] = s1 * c * c
+    sig[:, 5] = s1 * s * c
+    sig[:, 2] = NU * 0.5 * (sig[:, 0] + sig[:, 1]) * (0.5 + 0.5 * smooth().ravel())   # partial plane-strain constraint
+    d01, d12, d20 = sig[:, 0] - sig[:, 1], sig[:, 1] - sig[:, 2], sig[:, 2] - sig[:, 0]
+    seq = np.sqrt(0.5 * (d01 ** 2 + d12 ** 2 + d20 ** 2 + 6 * sig[:, 5] ** 2))
+    sflow = SY + KHARD * peeq.ravel()
+    sig *= (level.ravel() * sflow / seq)[:, None]
+    epl = peeq.ravel()[:, None] * np.array([-.5, 1., -.5, 0., 0., 0.])[None, :]
+    deps = np.zeros((n, 6))
+    eyy = 5.e-4 * (1. + 0.4 * smooth().ravel())
+    deps[:, 1] = eyy
+    deps[:, 0] = -0.4 * eyy * (1. + 0.3 * smooth().ravel())
+    deps[:, 5] = 2.e-4 * smooth().ravel()
+    deps *= (1. + 0.05 * rng.standard_normal((n, 1)))
+    if not correlated:
+        p = rng.permutation(n)
+        sig, epl, deps = sig[p], epl[p], deps[p]
+    return np.ascontiguousarray(sig), np.ascontiguousarray(epl), np.ascontiguousarray(deps)
+
+
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = ('index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,'
+         'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, device):
+        self.device, self.rows, self.proc = device, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(['nvidia-smi', '-i', str(self.device), '--query-gpu=' + self.Q,
+                                          '--format=csv,noheader,nounits', '-lms', '100'],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(',')])
+
+    def stop(self):
+        if not self.proc:
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable']}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm = [float(r[1]) for r in self.rows if len(r) >= 9 and r[1].replace('.', '').isdigit()]
+        mx = [float(r[2]) for r in self.rows if len(r) >= 9 and r[2].replace('.', '').isdigit()]
+        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
+        reasons = set()
+        for r in self.rows:
+            if len(r) >= 9:
+                for nme, v in zip(names, r[5:9]):
+                    if v.lower().startswith('active'):
+                        reasons.add(nme)
+        return {'sm_mhz': float(np.median(sm)) if sm else None, 'sm_max_mhz': max(mx) if mx else None,
+                'reasons': sorted(reasons), 'samples': len(sm)}
+
+
+def oracle_step(orc, mats, CV, sig, epl, deps, B4, jacw, nthreads):
+    """The step on the host: oracle response for every sampled element, then Kel of each new tangent (the CPU side of
+    setupK; the O(1) adds of the assembly itself are not included, which favours the CPU)."""
+    if nthreads > 1:
+        out = orc.response_batch_threads(mats, None, sig, epl, deps, CV[None], nthreads)
+    else:
+        out = orc.response_batch(mats, None, sig, epl, deps, CV[None])
+    ct = out[3]
+    lib = orc.lib()
+    import ctypes as C
+    kel = np.zeros((8, 8))
+    B4c = np.ascontiguousarray(B4)
+    dp = C.POINTER(C.c_double)
+    for i in range(len(ct)):
+        lib.orc_kel(B4c.ctypes.data_as(dp), ct[i].ctypes.data_as(dp), C.c_double(jacw), kel.ctypes.data_as(dp))
+    return out
+
+
+def run_reference(args, rank, world):
+    """--impl reference: the reference algorithm on the host cores only (oracle port; the Python reference cannot
+    travel to the GPU box and cannot allocate its dense K at this size)."""
+    if rank != 0:
+        return
+    from oracle import oracle as orc
+    N = args.mesh
+    sample = args.cpu_sample
+    sig, epl, deps = synth_states(N, 1234)
+    idx = np.random.default_rng(7).choice(len(sig), sample, replace=False)
+    sig, epl, deps = sig[idx], epl[idx], deps[idx]
+    _, CV = j2_material()
+    mats = [orc.Mat(kind=orc.HILL, E=E_MOD, nu=NU, sy=SY, khard=KHARD)]
+    lx = 4. / N
+    B4 = orc.gauss_bmats(lx, lx, 0, CV, E_MOD, NU)
+    jacw = (lx * lx * 1.) * 4.
+    cores = os.cpu_count() or 1
+    for _ in range(args.warmup):
+        oracle_step(orc, mats, CV, sig[:2000], epl[:2000], deps[:2000], B4, jacw, cores)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        oracle_step(orc, mats, CV, sig, epl, deps, B4, jacw, cores)
+    dt = (time.perf_counter() - t0) / args.steps
+    val = sample / dt
+    unit = 'elements/s'
+    line = {'impl': 'reference', 'metric': METRIC, 'value': val, 'unit': unit, 'n_gpus': args.gpus, 'steps': args.steps,
+            'warmup': args.warmup, 'ms_per_step': dt * 1e3, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
+            'dtype': 'f64', 'data': 'synthetic', 'config': workload_config(N),
+            'cpu_baseline': {'value': val, 'unit': unit, 'cores': cores, 'kind': 'port',
+                             'sample': '%d elements sampled (seeded) from the %dx%d workload per step' % (sample, N, N)},
+            'e2e': {'value': val, 'unit': unit, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}, 'gpu_launches': 0}
+    print(json.dumps(line))
+
+
+METRIC = 'Gauss-point stress updates/sec + K-assembly elems/sec (one step = return mapping + setupK over the mesh)'
+
+
+def workload_config(N):
+    return {'workload': '%dx%d Q4 mesh, J2 plasticity (sy=150, khard=500, E=200e3, nu=0.3, plane strain), one inner pass '
+                        'of a load step: Material.response per element + Model.setupK into CSR' % (N, N),
+            'elements': N * N, 'state': 'synthetic correlated field, seed 1234', 'l2': 'inputs larger than L2 '
+            '(%.0f MB read+written per step)' % (N * N * (BYTES_PER_UPDATE + BYTES_PER_ASSEMBLED) / 1e6)}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=20)
+    ap.add_argument('--warmup', type=int, default=5)
+    ap.add_argument('--impl', default='ours')
+    ap.add_argument('--mesh', type=int, default=1024)
+    ap.add_argument('--cpu-sample', type=int, default=40000)
+    ap.add_argument('--no-e2e', action='store_true')
+    ap.add_argument('--no-cpu', action='store_true')
+    ap.add_argument('--compact', type=int, default=1)
+    args = ap.parse_args()
+
+    rank = int(os.environ.get('RANK', '0'))
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    local = int(os.environ.get('LOCAL_RANK', '0'))
+    if args.impl == 'reference':
+        run_reference(args, rank, world)
+        return
+
+    dist = None
+    if world > 1:
+        import torch
+        import torch.distributed as dist
+        torch.cuda.set_device(local)
+        dist.init_process_group('nccl', device_id=torch.device('cuda', local))
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+
+    def max_over_ranks(v):
+        if dist is None:
+            return v
+        import torch
+        t = torch.tensor([v], dtype=torch.float64, device='cuda')
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    from pylabfea_b200 import _lib
+    ctx = _lib.Context(local)
+    ctx.set_option('compact', args.compact)
+    N = args.mesh
+    Nel = N * N
+    mat, CV = j2_material()
+    ctx.set_materials([mat], planestress=False)
+    lx = 4. / N
+    ctx.mesh_structured(N, N, np.full(N, lx), lx, 1., np.zeros(Nel, np.int32))
+    sig, epl, deps = synth_states(N, 1234 + rank)
+    b = ctx.batch_create(Nel)
+    ctx.batch_upload(b, sig, epl, deps)
+    ctx.synchronize()
+
+    def step():
+        ctx.batch_run(b)
+        ctx.setupK_from_batch(b)
+
+    l0 = ctx.launch_count()
+    for _ in range(max(args.warmup, 3)):
+        step()
+    ctx.synchronize()
+    launches_per_step = (ctx.launch_count() - l0) / max(args.warmup, 3)
+
+    sampler = ClockSampler(local)
+    sampler.start()
+    K = args.steps
+    barrier()
+    ctx.synchronize()
+    t_wall0 = time.perf_counter()
+    l0 = ctx.launch_count()
+    ctx.event_record(0)
+    for i in range(K):
+        ctx.event_record(1 + 3 * i)
+        ctx.batch_run(b)
+        ctx.event_record(2 + 3 * i)
+        ctx.setupK_from_batch(b)
+        ctx.event_record(3 + 3 * i)
+    ctx.event_record(3 * K + 1)
+    ctx.synchronize()
+    barrier()
+    total_ms = ctx.event_elapsed(0, 3 * K + 1)
+    t_wall = time.perf_counter() - t_wall0
+    gpu_launches = ctx.launch_count() - l0
+    clocks = sampler.stop()
+    resp_ms = float(np.mean([ctx.event_elapsed(1 + 3 * i, 2 + 3 * i) for i in range(K)]))
+    asm_ms = float(np.mean([ctx.event_elapsed(2 + 3 * i, 3 + 3 * i) for i in range(K)]))
+    total_ms = max_over_ranks(total_ms)
+    resp_ms_max = max_over_ranks(resp_ms)
+    asm_ms_max = max_over_ranks(asm_ms)
+    ms_per_step = total_ms / K
+    value = world * Nel / (ms_per_step * 1e-3)
+
+    # branch census of the workload (one extra, untimed run)
+    ns = np.empty(Nel, dtype=np.int32)
+    ct0 = np.empty((Nel, 6, 6))
+    ctx.batch_download(b, ctan=ct0, nsteps=ns)
+    n50 = int(np.sum(ns == 49))
+    nel_elastic = int(np.sum(np.all(ct0.reshape(Nel, 36) == CV.ravel()[None, :], axis=1)))
+    del ct0
+
+    # ---- e2e through the host-buffer C-ABI calls -----------------------------------------------------------
+    e2e = None
+    if not args.no_e2e:
+        hs, he, hd = (_lib.pinned_empty((Nel, 6)) for _ in range(3))
+        hs[:], he[:], hd[:] = sig, epl, deps
+        o_fy = _lib.pinned_empty((Nel,))
+        o_sig = _lib.pinned_empty((Nel, 6))
+        o_dp = _lib.pinned_empty((Nel, 6))
+        o_ct = _lib.pinned_empty((Nel, 36))
+        o_ns = _lib.pinned_empty((Nel,), np.int32)
+        o_val = _lib.pinned_empty((ctx.nnz,))
+
+        def e2e_step():
+            ctx.batch_upload(b, hs, he, hd)
+            ctx.batch_run(b)
+            ctx.setupK_from_batch(b)
+            ctx.batch_download(b, fy=o_fy, sig_out=o_sig, depl=o_dp, ctan=o_ct, nsteps=o_ns)
+            ctx.get_csr_values(o_val)
+        for _ in range(2):
+            e2e_step()
+        ke = max(3, min(K, 10))
+        barrier()
+        t0 = time.perf_counter()
+        ctx.event_record(4000)
+        for _ in range(ke):
+            e2e_step()
+        ctx.event_record(4001)
+        ctx.synchronize()
+        barrier()
+        e2e_ms = max_over_ranks(max(ctx.event_elapsed(4000, 4001), (time.perf_counter() - t0) * 1e3)) / ke
+        h2d = Nel * (3 * 48 + 4)
+        d2h = Nel * (8 + 48 + 48 + 288 + 4) + ctx.nnz * 8
+        e2e = {'value': world * Nel / (e2e_ms * 1e-3), 'unit': 'elements/s', 'h2d_bytes_per_step': int(h2d),
+               'd2h_bytes_per_step': int(d2h), 'ms_per_step': e2e_ms,
+               'api': 'plf_batch_upload + plf_batch_run + plf_setupK_from_batch + plf_batch_download + plf_get_csr (pinned host buffers)'}
+
+    if rank != 0:
+        if dist is not None:
+            dist.destroy_process_group()
+        return
+
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, 'MEASURED_PEAKS.json')))
+    except Exception:
+        pass
+    peak = float(peaks.get('hbm_gbs', 6650.))
+    achieved = BYTES_PER_UPDATE * Nel / (resp_ms_max * 1e-3) / 1e9
+    asm_achieved = BYTES_PER_ASSEMBLED * Nel / (asm_ms_max * 1e-3) / 1e9
+    roofline = {'bound': 'hbm', 'kernel': 'response_hill_kernel (pass A + compacted pass B)' if args.compact else 'response_hill_kernel',
+                'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak,
+                'peak_source': 'MEASURED_PEAKS.json hbm_gbs (of measured)' if peaks else 'fallback 6650 GB/s (of fallback)',
+                'traffic': None, 'bytes_per_update': BYTES_PER_UPDATE, 'ms': resp_ms_max,
+                'assembly': {'kernel': 'assemble_rows_kernel', 'achieved': asm_achieved, 'frac': asm_achieved / peak,
+                             'bytes_per_element': BYTES_PER_ASSEMBLED, 'ms': asm_ms_max}}
+
+    cpu = None
+    if not args.no_cpu:
+        from oracle import oracle as orc
+        sample = args.cpu_sample
+        idx = np.random.default_rng(7).choice(Nel, sample, replace=False)
+        mats = [orc.Mat(kind=orc.HILL, E=E_MOD, nu=NU, sy=SY, khard=KHARD)]
+        B4 = orc.gauss_bmats(lx, lx, 0, CV, E_MOD, NU)
+        jacw = (lx * lx * 1.) * 4.
+        oracle_step(orc, mats, CV, sig[idx[:1000]], epl[idx[:1000]], deps[idx[:1000]], B4, jacw, 1)
+        t0 = time.perf_counter()
+        oracle_step(orc, mats, CV, sig[idx], epl[idx], deps[idx], B4, jacw, 1)
+        dt = time.perf_counter() - t0
+        cpu = {'value': sample / dt, 'unit': 'elements/s', 'cores': 1, 'kind': 'port',
+               'sample': '%d elements sampled (seeded) from the same %dx%d workload, oracle/plf_oracle.c, 1 thread, %.1f s'
+                         % (sample, N, N, dt)}
+
+    line = {'metric': METRIC, 'value': value, 'unit': 'elements/s', 'n_gpus': world, 'steps': K, 'warmup': max(args.warmup, 3),
+            'ms_per_step': ms_per_step, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f64',
+            'data': 'synthetic', 'config': workload_config(N),
+            'updates_per_s': world * Nel / (resp_ms_max * 1e-3), 'assembly_elems_per_s': world * Nel / (asm_ms_max * 1e-3),
+            'branch_mix': {'elastic': nel_elastic / Nel, 'substep50': n50 / Nel, 'plastic_1step': 1. - (nel_elastic + n50) / Nel},
+            'roofline': roofline, 'cpu_baseline': cpu, 'e2e': e2e, 'gpu_launches': int(gpu_launches),
+            'launches_per_step': launches_per_step, 'clocks': clocks, 'wall_s_timed_region': t_wall,
+            'device': ctx.device_info()['name']}
+    print(json.dumps(line))
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+if __name__ == '__main__':
+    main()

@@ -1,0 +1,195 @@
+/*
+ * plfb200.h -- C ABI of libplfb200.so: the B200 (sm_100a) implementation of pyLabFEA's per-element
+ * elastic-plastic stress update and global stiffness assembly.
+ *
+ * The reference (pyLabFEA v4.4.2, pure Python) has no FFI of its own; its boundary for this path is the Python
+ * class API.  Every entry point below names the reference call site it replaces (paths relative to
+ * /root/reference/src/pylabfea/).  INTEGRATION.md shows the ctypes binding a pyLabFEA maintainer would add.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; all floating point data is IEEE float64, indices are int32 (int64 counts).
+ *   - Voigt order (11,22,33,23,13,12) with engineering shear, 6x6 matrices row-major, as in the reference.
+ *   - host arrays are borrowed for the duration of the call; device buffers are owned by the context.
+ *   - every function returns PLF_OK (0) or a negative error code; plf_last_error() gives the message.
+ *     The Python wrapper maps PLF_EINVAL -> ValueError, PLF_ESTATE -> AttributeError (solve before mesh,
+ *     model.py:1025), PLF_EUNSUPPORTED -> NotImplementedError / ValueError as the reference raises them.
+ *   - one context = one CUDA device + one stream; calls on a context are serialised by the caller.
+ *   - there is NO CPU fallback: without a CUDA device plf_create() fails with PLF_ECUDA.
+ */
+#ifndef PLFB200_H
+#define PLFB200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PLF_OK 0
+#define PLF_EINVAL (-1)       /* bad argument (shape, id, NULL)                                  */
+#define PLF_ECUDA (-2)        /* CUDA runtime error or no device                                  */
+#define PLF_ESTATE (-3)       /* call order: mesh / materials / K not set up yet                  */
+#define PLF_EUNSUPPORTED (-4) /* feature the reference raises for (e.g. Tresca gradient)          */
+#define PLF_ENOCONV (-5)      /* linear solver did not reach the requested tolerance              */
+
+#define PLF_MAX_MATERIALS 16
+#define PLF_MAX_GEOM 16
+
+/* Material.response thresholds, named as in the reference */
+#define PLF_YF_TOLERANCE 5.e-3 /* basic.py:26 yf_tolerance                     */
+#define PLF_SPLIT_FY0 (-0.15)  /* material.py:260 elastic/plastic split         */
+#define PLF_MAXIT 50           /* material.py:207 maxit (sub-steps)             */
+#define PLF_DSTIFF_TOL 1.e-3   /* model.py:1348 Frobenius change of the tangent */
+
+typedef enum plf_mat_kind {
+    PLF_MAT_ELASTIC = 0, /* Material.sy is None                                                     */
+    PLF_MAT_HILL = 1,    /* sdim=6 Hill-6p equivalent stress; J2 is hill = 1 (material.py:653-661)  */
+    PLF_MAT_SVC = 2,     /* ML_yf: RBF support-vector yield function, sdim=6 (material.py:398-405)  */
+    PLF_MAT_BARLAT = 3   /* Yld2004-18p equivalent stress (material.py:678-702)                     */
+} plf_mat_kind;
+
+/* What Material.elasticity / Material.plasticity / train_SVC leave on a Material object
+ * (material.py:2401-2594, 1109-1278), flattened. */
+typedef struct plf_material {
+    int32_t kind;     /* plf_mat_kind */
+    int32_t nsv;      /* SVC: number of support vectors */
+    int32_t dev_only; /* SVC: features use the deviatoric stress (material.py:2337-2338) */
+    int32_t tresca;   /* only the ML_full_yf start value depends on it (material.py:470-473) */
+    int32_t lhs;      /* d[] holds LHS parameters (material.py:646-647, 829-830) instead of drucker*[1,1,1] */
+    int32_t pad_;
+    double E, nu;     /* isotropic constants; used for the plane-stress CV and B row (model.py:274-283, 498-501) */
+    double C44;       /* Material.C44 (plane-stress CV[5][5]) */
+    double CV[36];    /* Material.CV, the 3-d Voigt stiffness */
+    double sy, khard;
+    double hill[6];
+    double d[3];
+    double barlat_m1[36], barlat_m2[36], barlat_exp; /* Material.Bar_m1 / Bar_m2 / barlat_exp */
+    double svc_gamma, svc_rho, svc_scale_seq;        /* gam_yf, svm_yf.intercept_[0], scale_seq */
+    const double *svc_sv;   /* host, [nsv][6]: svm_yf.support_vectors_ */
+    const double *svc_dual; /* host, [nsv]:    svm_yf.dual_coef_[0]    */
+} plf_material;
+
+typedef struct plf_ctx plf_ctx;
+
+/* ---- context --------------------------------------------------------------------------------------------- */
+int plf_create(int device, plf_ctx **out);
+void plf_destroy(plf_ctx *ctx);
+const char *plf_last_error(const plf_ctx *ctx); /* ctx may be NULL: message of the last failed plf_create */
+const char *plf_version(void);
+size_t plf_sizeof_material(void); /* sizeof(plf_material), for binding self-checks */
+int plf_device_info(const plf_ctx *ctx, char *name, int name_len, int *sm_count, int *cc_major, int *cc_minor,
+                    int64_t *mem_bytes);
+/* CUDA-event timer on the context's stream (the stream every kernel of this library is launched on). */
+int plf_timer_start(plf_ctx *ctx);
+int plf_timer_stop(plf_ctx *ctx, float *ms); /* records, synchronises, returns elapsed ms */
+/* event pool for phase timing inside a step: record event `idx` (0..4095) on the stream; elapsed ms between two */
+int plf_event_record(plf_ctx *ctx, int idx);
+int plf_event_elapsed(plf_ctx *ctx, int idx0, int idx1, float *ms); /* synchronises on idx1 */
+int plf_synchronize(plf_ctx *ctx);
+int plf_flush_l2(plf_ctx *ctx);              /* overwrites a 256 MiB scratch buffer (L2 is 126 MB) */
+int64_t plf_launch_count(const plf_ctx *ctx); /* kernels launched by this context so far */
+/* page-locked host memory for callers that want asynchronous H2D/D2H copies of their numpy buffers */
+int plf_pinned_alloc(size_t bytes, void **out);
+int plf_pinned_free(void *p);
+/* tuning switches: "compact" (default 1) = two-pass return mapping, the 50-sub-step elements are compacted into a
+ * dense second launch instead of diverging inside the first one */
+int plf_set_option(plf_ctx *ctx, const char *key, int value);
+
+/* ---- materials ------------------------------------------------------------------------------------------- */
+/* Model.assign(mats) (model.py:554-577).  planestress selects Element.CV (model.py:270-304). */
+int plf_set_materials(plf_ctx *ctx, int nmat, const plf_material *mats, int planestress);
+/* Element.CV of material `id` as the kernels use it (6x6 row-major) */
+int plf_get_element_CV(const plf_ctx *ctx, int id, double *CV);
+
+/* ---- stateless batched constitutive calls on HOST arrays (H2D + kernel + D2H inside the call) ------------- */
+/* Material.response (material.py:207-346) for n independent elements.
+ * mat_id[n] may be NULL (all material 0).  Outputs: fy[n], sig_out[n][6], depl[n][6], ctan[n][36], nsteps[n]
+ * (= Material.msg['nsteps'], material.py:345).  Any output pointer may be NULL. */
+int plf_response_batch(plf_ctx *ctx, int64_t n, const int32_t *mat_id, const double *sig, const double *epl,
+                       const double *deps, double *fy, double *sig_out, double *depl, double *ctan, int32_t *nsteps);
+/* Material.calc_seq (576-676), calc_yf (348-412), calc_fgrad (704-858), ML_full_yf (414-516),
+ * epl_dot (1009-1055), C_tan (1057-1086) on (n,6) arrays, one material. */
+int plf_calc_seq_batch(plf_ctx *ctx, int mat, int64_t n, const double *sig, double *seq);
+int plf_calc_yf_batch(plf_ctx *ctx, int mat, int64_t n, const double *sig, const double *epl, double *yf);
+int plf_calc_fgrad_batch(plf_ctx *ctx, int mat, int64_t n, const double *sig, const double *epl, double *fgrad);
+int plf_ml_full_yf_batch(plf_ctx *ctx, int mat, int64_t n, const double *sig, const double *epl, const double *ld,
+                         double *yf);
+int plf_epl_dot_batch(plf_ctx *ctx, int mat, int64_t n, const double *sig, const double *epl, const double *deps,
+                      double *pdot);
+int plf_ctan_batch(plf_ctx *ctx, int mat, int64_t n, const double *sig, const double *epl, double *ctan);
+
+/* ---- device-resident batch (bench / pipelines that keep state in HBM) -------------------------------------- */
+typedef struct plf_batch plf_batch; /* n elements: mat_id, sig, epl, deps in; fy, sig_out, depl, ctan, nsteps out */
+int plf_batch_create(plf_ctx *ctx, int64_t n, plf_batch **out);
+void plf_batch_destroy(plf_ctx *ctx, plf_batch *b);
+int plf_batch_upload(plf_ctx *ctx, plf_batch *b, const int32_t *mat_id, const double *sig, const double *epl,
+                     const double *deps);
+int plf_batch_run(plf_ctx *ctx, plf_batch *b); /* asynchronous on the context stream */
+int plf_batch_download(plf_ctx *ctx, plf_batch *b, double *fy, double *sig_out, double *depl, double *ctan,
+                       int32_t *nsteps);
+
+/* ---- mesh, element stiffness, global stiffness -------------------------------------------------------------- */
+/* Model.mesh (model.py:758-952) for the structured Q4 mesh: NX x NY elements, element id = j*NY + k, node id =
+ * j*(NY+1) + k, element nodes [n1, n1+1, n1+NY+1, n1+NY+2] (932-949).  dx[NX]: element width per column
+ * (laminate sections may differ, 839), dy: element height, thick: Model.thick.  elem_mat[NX*NY]: material index
+ * per element (0-based).  Resets the element state (sig = eps = epl = 0, elstiff = CV) like the first
+ * Model.solve does (1214-1227). */
+int plf_mesh_structured(plf_ctx *ctx, int NX, int NY, const double *dx, double dy, double thick,
+                        const int32_t *elem_mat);
+int plf_mesh_sizes(const plf_ctx *ctx, int64_t *Nel, int64_t *Nnode, int64_t *Ndof, int64_t *nnz);
+/* Element.Bmat (model.py:439-512) of element e: 4 x (6x8) row-major */
+int plf_get_bmat(const plf_ctx *ctx, int64_t e, double *B4);
+/* Element.elstiff for all elements, (Nel,36).  set: NULL resets to Element.CV (model.py:1223). */
+int plf_set_tangent(plf_ctx *ctx, const double *elstiff);
+int plf_get_tangent(plf_ctx *ctx, double *elstiff);
+/* Element.calc_Kel (model.py:365-370) for all elements -> host (Nel,64) */
+int plf_get_kel(plf_ctx *ctx, double *Kel);
+/* Model.setupK (model.py:954-977): integrate B^T C B per element and assemble the global stiffness as CSR on the
+ * device.  Per entry the element contributions are summed in ascending element order (bit-exact with the
+ * reference's dense K). */
+int plf_setupK(plf_ctx *ctx);
+int plf_get_csr(plf_ctx *ctx, int32_t *rowptr, int32_t *col, double *val); /* sizes from plf_mesh_sizes */
+/* Same assembly, element tangents taken from the `ctan` output of a device-resident batch of Nel elements (the
+ * grad_stiff that Model.solve would store into Element.elstiff at model.py:1351) without a copy in between. */
+int plf_setupK_from_batch(plf_ctx *ctx, const plf_batch *b);
+
+/* ---- element state --------------------------------------------------------------------------------------------- */
+typedef enum plf_field {
+    PLF_SIG = 0, PLF_EPS = 1, PLF_EPL = 2,         /* Element.sig / eps / epl          (Nel,6) */
+    PLF_RES_SIG = 3, PLF_RES_DEPL = 4,             /* Element.res_sig / res_depl       (Nel,6) */
+    PLF_U = 5, PLF_DU = 6, PLF_F = 7,              /* Model.u / du / f                 (Ndof)  */
+    PLF_FYLD = 8,                                  /* f list of model.py:1345          (Nel)   */
+    PLF_NSTEPS = 9                                 /* msg['nsteps'] per element, int32 (Nel)   */
+} plf_field;
+int plf_get_field(plf_ctx *ctx, int field, void *host);
+int plf_set_field(plf_ctx *ctx, int field, const void *host);
+
+/* ---- one pass of the non-linear loop (model.py:1338-1361) on the device ---------------------------------------- */
+/* For every plastic element: deps = sum_g B_g du_e (387-398); response(sig, epl, deps, CV) (1342-1343);
+ * f = fyld / get_sflow(eps_eq(epl)) (1345); hh = |elstiff - grad_stiff|_F; if hh > 1e-3 replace the element tangent
+ * (average instead when nit >= 15) (1346-1355).  Outputs: change (any tangent replaced), conv (all f <= 5.0005e-3),
+ * max_hh, and counts of elements per branch {elastic, plastic 1 step, plastic 50 sub-steps, radial corrections}. */
+int plf_sweep(plf_ctx *ctx, int nit, int32_t *change, int32_t *conv, double *max_hh, int64_t counts[4]);
+/* state commit (model.py:1383-1392): u += du; f += K du; epl += res_depl; sig = res_sig (or += dsig / depl for
+ * elements that never went through response); eps = B u. */
+int plf_commit(plf_ctx *ctx);
+/* calc_global element part (model.py:1500-1511): volume-weighted means of sig, eps, epl -> 3 x 6 */
+int plf_reduce_global(plf_ctx *ctx, double *sig6, double *eps6, double *epl6);
+/* calc_scf (model.py:1036-1067) -> scaling factor of the load increment; sld = loading direction (1245-1258) */
+int plf_calc_scf(plf_ctx *ctx, const double *sld, double *scf);
+
+/* ---- linear solve (model.py:1028-1033, 1070-1206, 1291, 1335) -------------------------------------------------- */
+/* Solve K[ind][:,ind] du[ind] = df[ind] on the device with Jacobi-preconditioned CG.
+ *   fixed[Ndof]  : 1 where a displacement BC removed the dof from `ind`
+ *   du_bc[Ndof]  : prescribed du on fixed dofs (0 elsewhere)                      -- calc_BC's du
+ *   w[Ndof]      : sum of all BC values applied to a dof (what calc_BC multiplies K's columns with)
+ *   f_ext[Ndof]  : force-type BC contributions (1145-1151, 1173-1179, 1203-1205)
+ * df = f_ext - K w on the free dofs.  Result: Model.du on the device (PLF_DU).  rtol is on |r|/|b|. */
+int plf_solve_linear(plf_ctx *ctx, const uint8_t *fixed, const double *du_bc, const double *w, const double *f_ext,
+                     double rtol, int max_iter, int *iters, double *relres);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PLFB200_H */

@@ -1,0 +1,765 @@
+// model_kernels.cu -- device-resident load-step loop of Model.solve (model.py:979-1450):
+//   sweep   : per plastic element deps = B du, Material.response, convergence measure, tangent replacement
+//             (model.py:1338-1361), thread-per-element (Hill/J2) or warp-per-element (SVC)
+//   commit  : state update (1383-1392), calc_global element sums (1500-1511), calc_scf (1036-1067)
+//   solver  : CSR SpMV + Jacobi-preconditioned CG on the BC-reduced system (1028-1033, 1291, 1335)
+// All reductions are deterministic (fixed-order partial sums, last-block-done final pass).
+#include "plf_device.cuh"
+#include "plf_host.h"
+#include "model_kernels.h"
+
+namespace plf {
+
+__constant__ DevMat c_mat[PLF_MAX_MATERIALS];
+__constant__ GeomClass c_geom[PLF_MAX_GEOM];
+
+cudaError_t modelk_upload_materials(const DevMat *h, int n, cudaStream_t st)
+{
+    return cudaMemcpyToSymbolAsync(c_mat, h, sizeof(DevMat) * n, 0, cudaMemcpyHostToDevice, st);
+}
+cudaError_t modelk_upload_geom(const GeomClass *h, int n, cudaStream_t st)
+{
+    return cudaMemcpyToSymbolAsync(c_geom, h, sizeof(GeomClass) * n, 0, cudaMemcpyHostToDevice, st);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// helpers
+// ---------------------------------------------------------------------------------------------------------------
+// element strain from nodal values: sum_g B_g u_e = bsum u_e (Element.deps / eps_t, model.py:387-411)
+__device__ __forceinline__ void element_strain(const GeomClass &gc, int NY, int64_t e, const double *__restrict__ u, double *eps)
+{
+    const int64_t j = e / NY, k = e - j * NY;
+    const int64_t n1 = j * (NY + 1) + k, n3 = n1 + NY + 1;
+    double ue[8];
+    const double2 a0 = __ldg(reinterpret_cast<const double2 *>(u + 2 * n1));
+    const double2 a1 = __ldg(reinterpret_cast<const double2 *>(u + 2 * n1 + 2));
+    const double2 b0 = __ldg(reinterpret_cast<const double2 *>(u + 2 * n3));
+    const double2 b1 = __ldg(reinterpret_cast<const double2 *>(u + 2 * n3 + 2));
+    ue[0] = a0.x; ue[1] = a0.y; ue[2] = a1.x; ue[3] = a1.y; ue[4] = b0.x; ue[5] = b0.y; ue[6] = b1.x; ue[7] = b1.y;
+#pragma unroll
+    for (int r = 0; r < 6; r++) {
+        if (r == 3 || r == 4) { eps[r] = 0.; continue; }
+        double s = 0.;
+#pragma unroll
+        for (int c = 0; c < 8; c++) s += gc.bsum[r][c] * ue[c];
+        eps[r] = s;
+    }
+}
+
+__device__ __forceinline__ void atomic_max_nonneg(double *addr, double v)
+{
+    // v >= 0: IEEE bit patterns of non-negative doubles order like unsigned integers
+    atomicMax(reinterpret_cast<unsigned long long *>(addr), (unsigned long long)__double_as_longlong(v));
+}
+
+struct ElemStats {
+    bool active = false, changed = false, nonconv = false;
+    double hh = 0.;
+    int br = 0;
+};
+
+__device__ __forceinline__ void stats_atomics(const ElemStats &es, SweepStats *st)
+{
+    if (!es.active) return;
+    if (es.changed) atomicOr(&st->change, 1u);
+    if (es.nonconv) atomicAdd(&st->nonconv, 1u);
+    atomic_max_nonneg(&st->max_hh, es.hh);
+    atomicAdd(&st->counts[es.br & 3], 1ull);
+    if (es.br & 4) atomicAdd(&st->counts[3], 1ull);
+}
+
+// block-aggregated statistics: a handful of atomics per block instead of per element
+__device__ __forceinline__ void stats_block(const ElemStats &es, SweepStats *st)
+{
+    __shared__ double s_hh[32];
+    const int c_chg = __syncthreads_or(es.active && es.changed);
+    const int c_non = __syncthreads_count(es.active && es.nonconv);
+    const int c0 = __syncthreads_count(es.active && (es.br & 3) == 0);
+    const int c1 = __syncthreads_count(es.active && (es.br & 3) == 1);
+    const int c2 = __syncthreads_count(es.active && (es.br & 3) == 2);
+    const int c3 = __syncthreads_count(es.active && (es.br & 4));
+    double h = es.active ? es.hh : 0.;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) h = fmax(h, __shfl_xor_sync(0xffffffffu, h, o));
+    if ((threadIdx.x & 31) == 0) s_hh[threadIdx.x >> 5] = h;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int w = 1; w < (int)((blockDim.x + 31) >> 5); w++) h = fmax(h, s_hh[w]);
+        if (c_chg) atomicOr(&st->change, 1u);
+        if (c_non) atomicAdd(&st->nonconv, (unsigned)c_non);
+        if (h > 0.) atomic_max_nonneg(&st->max_hh, h);
+        if (c0) atomicAdd(&st->counts[0], (unsigned long long)c0);
+        if (c1) atomicAdd(&st->counts[1], (unsigned long long)c1);
+        if (c2) atomicAdd(&st->counts[2], (unsigned long long)c2);
+        if (c3) atomicAdd(&st->counts[3], (unsigned long long)c3);
+    }
+}
+
+// what Model.solve does with the result of one response call (model.py:1342-1357)
+__device__ __forceinline__ ElemStats sweep_finish(const DevMat &m, int64_t e, int nit, const double *sig_new, const double *depl,
+                                             const double *gs, double fyv, int ns, int br, const double *epl_old,
+                                             double *__restrict__ elstiff, double *__restrict__ res_sig,
+                                             double *__restrict__ res_depl, double *__restrict__ fyld,
+                                             int32_t *__restrict__ nsteps, unsigned char *__restrict__ has_res)
+{
+    ElemStats es;
+    es.active = true;
+    es.br = br;
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+        reinterpret_cast<double2 *>(res_sig + e * 6)[k] = make_double2(sig_new[2 * k], sig_new[2 * k + 1]);
+        reinterpret_cast<double2 *>(res_depl + e * 6)[k] = make_double2(depl[2 * k], depl[2 * k + 1]);
+    }
+    has_res[e] = 1;
+    nsteps[e] = ns;
+    const double f = fyv / (m.sy + eps_eq6(epl_old) * m.khard);   // 1345
+    fyld[e] = f;
+    double *C = elstiff + e * 36;
+    double old[36], hh = 0.;
+#pragma unroll
+    for (int k = 0; k < 18; k++) {
+        double2 v = reinterpret_cast<const double2 *>(C)[k];
+        old[2 * k] = v.x; old[2 * k + 1] = v.y;
+    }
+#pragma unroll
+    for (int i = 0; i < 6; i++)
+#pragma unroll
+        for (int j = 0; j < 6; j++) {
+            double d = old[6 * i + j] - gs[sym_idx(i, j)];
+            hh += d * d;
+        }
+    hh = sqrt(hh);   // Frobenius norm, 1346-1347
+    if (hh > PLF_DSTIFF_TOL) {
+#pragma unroll
+        for (int i = 0; i < 6; i++)
+#pragma unroll
+            for (int j = 0; j < 6; j += 2) {
+                double g0 = gs[sym_idx(i, j)], g1 = gs[sym_idx(i, j + 1)];
+                if (nit >= 15) { g0 = 0.5 * (g0 + old[6 * i + j]); g1 = 0.5 * (g1 + old[6 * i + j + 1]); }   // 1350-1353
+                reinterpret_cast<double2 *>(C)[(6 * i + j) >> 1] = make_double2(g0, g1);
+            }
+        es.changed = true;
+    }
+    es.nonconv = !(f <= PLF_YF_TOLERANCE * 1.0001);   // 1361
+    es.hh = hh;
+    return es;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// sweep, thread per element (Hill / J2).  GATHER: compacted second pass over the deferred elements.
+// ---------------------------------------------------------------------------------------------------------------
+template <int MODE, bool GATHER>
+__global__ void __launch_bounds__(128) sweep_hill_kernel(int64_t n, int NY, int nit, const int32_t *__restrict__ desc,
+                                                         const double *__restrict__ sig, const double *__restrict__ epl,
+                                                         const double *__restrict__ du, double *__restrict__ elstiff,
+                                                         double *__restrict__ res_sig, double *__restrict__ res_depl,
+                                                         double *__restrict__ fyld, int32_t *__restrict__ nsteps,
+                                                         unsigned char *__restrict__ has_res, const int32_t *__restrict__ index,
+                                                         int32_t *__restrict__ worklist, SweepStats *st)
+{
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    ElemStats es;
+    bool defer = false;
+    int64_t e = -1;
+    if (t < n) {
+        e = GATHER ? (int64_t)index[t] : t;
+        const int d = __ldg(desc + e);
+        const DevMat &m = c_mat[d & 0xffff];
+        if (m.kind == PLF_MAT_ELASTIC) {
+            fyld[e] = 0.;   // 1358-1359
+        } else if (m.kind == PLF_MAT_HILL) {
+            double s[6], ep[6], de[6], dp[6], gs[21], fyv;
+            int ns;
+#pragma unroll
+            for (int k = 0; k < 3; k++) {
+                double2 a = __ldg(reinterpret_cast<const double2 *>(sig + e * 6) + k);
+                double2 b = __ldg(reinterpret_cast<const double2 *>(epl + e * 6) + k);
+                s[2 * k] = a.x; s[2 * k + 1] = a.y; ep[2 * k] = b.x; ep[2 * k + 1] = b.y;
+            }
+            element_strain(c_geom[d >> 16], NY, e, du, de);
+            HillModel ym(m);
+            const int br = response_core<MODE>(ym, m, s, ep, de, dp, gs, fyv, ns);
+            if (br == -1) {
+                defer = true;
+            } else {
+                es = sweep_finish(m, e, nit, s, dp, gs, fyv, ns, br, ep, elstiff, res_sig, res_depl, fyld, nsteps, has_res);
+            }
+        }
+    }
+    if (MODE == 1) warp_append(defer, (int32_t)e, worklist, &st->work_count);
+    stats_block(es, st);
+}
+
+// sweep, warp per element, one SVC material (SV table in shared memory)
+__global__ void __launch_bounds__(256) sweep_svc_kernel(int64_t n, int NY, int nit, int mid, const int32_t *__restrict__ desc,
+                                                        const double *__restrict__ sig, const double *__restrict__ epl,
+                                                        const double *__restrict__ du, double *__restrict__ elstiff,
+                                                        double *__restrict__ res_sig, double *__restrict__ res_depl,
+                                                        double *__restrict__ fyld, int32_t *__restrict__ nsteps,
+                                                        unsigned char *__restrict__ has_res, SweepStats *st)
+{
+    extern __shared__ double smem[];
+    const DevMat &m = c_mat[mid];
+    const int np = m.nsv_pad;
+    for (int i = threadIdx.x; i < 6 * np; i += blockDim.x) smem[i] = m.sv[i];
+    for (int i = threadIdx.x; i < np; i += blockDim.x) smem[6 * np + i] = m.dual[i];
+    __syncthreads();
+    const int lane = threadIdx.x & 31;
+    SvcModel ym(m, smem, smem + 6 * np, lane);
+    for (;;) {
+        unsigned long long e0 = 0;
+        if (lane == 0) e0 = atomicAdd(&st->queue, 1ull);
+        const int64_t e = (int64_t)__shfl_sync(0xffffffffu, e0, 0);
+        if (e >= n) break;
+        const int d = __ldg(desc + e);
+        if ((d & 0xffff) != mid) continue;
+        double s[6], ep[6], de[6], dp[6], gs[21], fyv;
+        int ns;
+#pragma unroll
+        for (int k = 0; k < 6; k++) { s[k] = __ldg(sig + e * 6 + k); ep[k] = __ldg(epl + e * 6 + k); }
+        element_strain(c_geom[d >> 16], NY, e, du, de);
+        const int br = response_core<0>(ym, m, s, ep, de, dp, gs, fyv, ns);
+        if (lane == 0) {
+            ElemStats es = sweep_finish(m, e, nit, s, dp, gs, fyv, ns, br, ep, elstiff, res_sig, res_depl, fyld, nsteps, has_res);
+            stats_atomics(es, st);
+        }
+    }
+}
+
+cudaError_t modelk_init()
+{
+    return cudaFuncSetAttribute(sweep_svc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+}
+
+cudaError_t launch_sweep(const LaunchCtx &lc, const DevMat *hmats, int nmat, int64_t Nel, int NY, int nit, const int32_t *desc,
+                         const double *sig, const double *epl, const double *du, double *elstiff, double *res_sig,
+                         double *res_depl, double *fyld, int32_t *nsteps, unsigned char *has_res, int32_t *worklist,
+                         void *d_stats, void *h_stats, int compact, int64_t *launches)
+{
+    SweepStats *st = (SweepStats *)d_stats;
+    cudaError_t e = cudaMemsetAsync(st, 0, sizeof(SweepStats), lc.stream);
+    if (e != cudaSuccess) return e;
+    bool any_hill = false;
+    for (int i = 0; i < nmat; i++) any_hill |= (hmats[i].kind == PLF_MAT_HILL || hmats[i].kind == PLF_MAT_ELASTIC);
+    const unsigned grid = (unsigned)((Nel + 127) / 128);
+    if (any_hill) {
+        if (compact) {
+            sweep_hill_kernel<1, false><<<grid, 128, 0, lc.stream>>>(Nel, NY, nit, desc, sig, epl, du, elstiff, res_sig, res_depl,
+                                                                      fyld, nsteps, has_res, nullptr, worklist, st);
+            (*launches)++;
+            e = cudaMemcpyAsync(h_stats, st, sizeof(SweepStats), cudaMemcpyDeviceToHost, lc.stream);
+            if (e != cudaSuccess) return e;
+            e = cudaStreamSynchronize(lc.stream);
+            if (e != cudaSuccess) return e;
+            const unsigned nw = ((SweepStats *)h_stats)->work_count;
+            if (nw > 0) {
+                sweep_hill_kernel<0, true><<<(nw + 127) / 128, 128, 0, lc.stream>>>((int64_t)nw, NY, nit, desc, sig, epl, du, elstiff,
+                                                                                    res_sig, res_depl, fyld, nsteps, has_res,
+                                                                                    worklist, nullptr, st);
+                (*launches)++;
+            }
+        } else {
+            sweep_hill_kernel<0, false><<<grid, 128, 0, lc.stream>>>(Nel, NY, nit, desc, sig, epl, du, elstiff, res_sig, res_depl,
+                                                                      fyld, nsteps, has_res, nullptr, nullptr, st);
+            (*launches)++;
+        }
+    }
+    for (int i = 0; i < nmat; i++) {
+        if (hmats[i].kind != PLF_MAT_SVC) continue;
+        e = cudaMemsetAsync(&st->queue, 0, sizeof(unsigned long long), lc.stream);
+        if (e != cudaSuccess) return e;
+        int blocks = lc.sm_count * 2;
+        int64_t need = (Nel + 7) / 8;
+        if (blocks > need) blocks = (int)need;
+        sweep_svc_kernel<<<blocks, 256, sizeof(double) * 7 * (size_t)hmats[i].nsv_pad, lc.stream>>>(
+            Nel, NY, nit, i, desc, sig, epl, du, elstiff, res_sig, res_depl, fyld, nsteps, has_res, st);
+        (*launches)++;
+    }
+    e = cudaMemcpyAsync(h_stats, st, sizeof(SweepStats), cudaMemcpyDeviceToHost, lc.stream);
+    if (e != cudaSuccess) return e;
+    e = cudaStreamSynchronize(lc.stream);
+    if (e != cudaSuccess) return e;
+    return cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// commit (model.py:1383-1392): element part.  u += du and f += K du are done by the vector kernels below.
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) commit_elements_kernel(int64_t Nel, int NY, const int32_t *__restrict__ desc,
+                                                              const double *__restrict__ u_new, const double *__restrict__ du,
+                                                              const double *__restrict__ elstiff, double *__restrict__ sig,
+                                                              double *__restrict__ eps, double *__restrict__ epl,
+                                                              const double *__restrict__ res_sig,
+                                                              const double *__restrict__ res_depl,
+                                                              const unsigned char *__restrict__ has_res)
+{
+    const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= Nel) return;
+    const int d = desc[e];
+    const GeomClass &gc = c_geom[d >> 16];
+    const DevMat &m = c_mat[d & 0xffff];
+    double s[6], ep[6];
+#pragma unroll
+    for (int k = 0; k < 6; k++) { s[k] = sig[e * 6 + k]; ep[k] = epl[e * 6 + k]; }
+    if (has_res[e]) {   // 1389-1391
+#pragma unroll
+        for (int k = 0; k < 6; k++) { ep[k] += res_depl[e * 6 + k]; s[k] = res_sig[e * 6 + k]; }
+    } else {            // 1386-1388: el.epl += el.depl(); el.sig += el.dsig()
+        double de[6], ds[6], C[36];
+        element_strain(gc, NY, e, du, de);
+#pragma unroll
+        for (int k = 0; k < 36; k++) C[k] = elstiff[e * 36 + k];
+        if (m.kind == PLF_MAT_HILL) {
+            // Element.depl (model.py:424-437): Mat.epl_dot(sig, epl, CV, deps)
+            HillModel ym(m);
+            double cd[6], st[6], a[6], ca[6];
+            matvec6(m.CV, de, cd);
+#pragma unroll
+            for (int k = 0; k < 6; k++) st[k] = s[k] + cd[k];
+            const double sflow = m.sy + eps_eq6(ep) * m.khard;
+            if (ym.yf(st, sflow) > PLF_YF_TOLERANCE) {
+                ym.fgrad(s, a);
+                matvec6(m.CV, a, ca);
+                double hh = m.khard, acd = 0.;
+#pragma unroll
+                for (int k = 0; k < 6; k++) { hh += a[k] * ca[k]; acd += a[k] * cd[k]; }
+                const double lam = acd / hh;
+#pragma unroll
+                for (int k = 0; k < 6; k++) ep[k] += lam * a[k];
+            }
+        }
+        matvec6(C, de, ds);
+#pragma unroll
+        for (int k = 0; k < 6; k++) s[k] += ds[k];
+    }
+    double et[6];
+    element_strain(gc, NY, e, u_new, et);   // 1392
+#pragma unroll
+    for (int k = 0; k < 6; k++) { sig[e * 6 + k] = s[k]; epl[e * 6 + k] = ep[k]; eps[e * 6 + k] = et[k]; }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// deterministic reductions: per-block partials in fixed slots, summed in fixed order by the last block to finish
+// ---------------------------------------------------------------------------------------------------------------
+template <int NV>
+__device__ __forceinline__ void block_reduce_to_partials(double *v, double *partial, unsigned int *counter, double *out,
+                                                         int mode /*0 sum*/)
+{
+    __shared__ double sh[NV][32];
+    __shared__ bool is_last;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = (blockDim.x + 31) >> 5;
+#pragma unroll
+    for (int i = 0; i < NV; i++) {
+        double x = v[i];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
+        if (lane == 0) sh[i][warp] = x;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int i = 0; i < NV; i++) {
+            double x = 0.;
+            for (int w = 0; w < nwarp; w++) x += sh[i][w];
+            partial[(size_t)blockIdx.x * NV + i] = x;
+        }
+        __threadfence();
+        unsigned int done = atomicAdd(counter, 1u);
+        is_last = (done == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (!is_last) return;
+    __threadfence();
+    // last block: every thread sums a strided slice in ascending order, then a fixed tree over the threads
+#pragma unroll
+    for (int i = 0; i < NV; i++) {
+        double x = 0.;
+        for (unsigned int b = threadIdx.x; b < gridDim.x; b += blockDim.x) x += __ldcg(partial + (size_t)b * NV + i);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
+        if (lane == 0) sh[i][warp] = x;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int i = 0; i < NV; i++) {
+            double x = 0.;
+            for (int w = 0; w < nwarp; w++) x += sh[i][w];
+            out[i] = x;
+        }
+        *counter = 0;
+    }
+    (void)mode;
+}
+
+// calc_global element sums (model.py:1500-1507): sum_e Vel * {sig, eps, epl}
+__global__ void __launch_bounds__(256) global_sums_kernel(int64_t Nel, const int32_t *__restrict__ desc,
+                                                          const double *__restrict__ sig, const double *__restrict__ eps,
+                                                          const double *__restrict__ epl, double *partial,
+                                                          unsigned int *counter, double *out)
+{
+    double v[18];
+#pragma unroll
+    for (int i = 0; i < 18; i++) v[i] = 0.;
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < Nel; e += (int64_t)gridDim.x * blockDim.x) {
+        const double vel = c_geom[desc[e] >> 16].vel;
+#pragma unroll
+        for (int k = 0; k < 6; k++) {
+            v[k] += sig[e * 6 + k] * vel;
+            v[6 + k] += eps[e * 6 + k] * vel;
+            v[12 + k] += epl[e * 6 + k] * vel;
+        }
+    }
+    block_reduce_to_partials<18>(v, partial, counter, out, 0);
+}
+
+// calc_scf (model.py:1036-1067), pass 1: per element scaling candidate hh with multiplicity (0, 1 or 2)
+__global__ void __launch_bounds__(128) scf_elements_kernel(int64_t Nel, int NY, const int32_t *__restrict__ desc,
+                                                           const double *__restrict__ sig, const double *__restrict__ epl,
+                                                           const double *__restrict__ du, const double *__restrict__ elstiff,
+                                                           double *__restrict__ hval, unsigned char *__restrict__ mult)
+{
+    const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= Nel) return;
+    const int d = desc[e];
+    const DevMat &m = c_mat[d & 0xffff];
+    mult[e] = 0;
+    hval[e] = 0.;
+    if (m.kind == PLF_MAT_ELASTIC || m.kind == PLF_MAT_SVC) return;   // SVC elements: scf_svc_kernel
+    double de[6], ds[6], C[36], s[6], ep[6];
+    element_strain(c_geom[d >> 16], NY, e, du, de);
+#pragma unroll
+    for (int k = 0; k < 36; k++) C[k] = elstiff[e * 36 + k];
+    matvec6(C, de, ds);
+    HillModel ym(m);
+    const double sref = ym.seq(ds);   // Stress(el.dsig()).seq(el.Mat), 1040
+    if (!(sref > 0.1)) return;
+#pragma unroll
+    for (int k = 0; k < 6; k++) { s[k] = sig[e * 6 + k]; ep[k] = epl[e * 6 + k]; }
+    const double sflow = m.sy + eps_eq6(ep) * m.khard;
+    const double yf0 = ym.yf(s, sflow);
+    if (yf0 < PLF_SPLIT_FY0) {
+        hval[e] = fmin(1., -yf0 / sref);   // appended twice (1050 and 1054)
+        mult[e] = 2;
+    } else {
+        hval[e] = fmin(1., sqrt(1.5) * sflow / sref);
+        mult[e] = 1;
+    }
+}
+
+__global__ void __launch_bounds__(256) scf_svc_kernel(int64_t Nel, int NY, int mid, const int32_t *__restrict__ desc,
+                                                      const double *__restrict__ sig, const double *__restrict__ epl,
+                                                      const double *__restrict__ du, const double *__restrict__ elstiff,
+                                                      const double *__restrict__ sld, double *__restrict__ hval,
+                                                      unsigned char *__restrict__ mult)
+{
+    extern __shared__ double smem[];
+    const DevMat &m = c_mat[mid];
+    const int np = m.nsv_pad;
+    for (int i = threadIdx.x; i < 6 * np; i += blockDim.x) smem[i] = m.sv[i];
+    for (int i = threadIdx.x; i < np; i += blockDim.x) smem[6 * np + i] = m.dual[i];
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    SvcModel ym(m, smem, smem + 6 * np, lane);
+    double ld[6];
+#pragma unroll
+    for (int k = 0; k < 6; k++) ld[k] = sld[k];
+    for (int64_t e = (int64_t)blockIdx.x * 8 + warp; e < Nel; e += (int64_t)gridDim.x * 8) {
+        const int d = desc[e];
+        if ((d & 0xffff) != mid) continue;
+        double de[6], ds[6], C[36], s[6], ep[6];
+        element_strain(c_geom[d >> 16], NY, e, du, de);
+#pragma unroll
+        for (int k = 0; k < 36; k++) C[k] = elstiff[e * 36 + k];
+        matvec6(C, de, ds);
+        const double sref = ym.seq(ds);
+        double h = 0.;
+        unsigned char mu = 0;
+        if (sref > 0.1) {
+#pragma unroll
+            for (int k = 0; k < 6; k++) { s[k] = sig[e * 6 + k]; ep[k] = epl[e * 6 + k]; }
+            const double sflow = m.sy + eps_eq6(ep) * m.khard;
+            double yf0 = ym.yf(s, sflow);
+            if (yf0 < PLF_SPLIT_FY0) {
+                yf0 = ym.ml_full_yf(s, sflow, ld);   // 1045-1048
+                h = fmin(1., -yf0 / sref);
+                mu = 2;
+            } else {
+                h = fmin(1., sqrt(1.5) * sflow / sref);
+                mu = 1;
+            }
+        }
+        if (lane == 0) { hval[e] = h; mult[e] = mu; }
+    }
+}
+
+// pass 2/3: moments.  mode 0: {count, sum, min-as-negated-max}; mode 1: sum mult * (h - mean)^2
+__global__ void __launch_bounds__(256) scf_moments_kernel(int64_t Nel, const double *__restrict__ hval,
+                                                          const unsigned char *__restrict__ mult, double mean, int mode,
+                                                          double *partial, unsigned int *counter, double *out, double *minval)
+{
+    double v[2] = {0., 0.};
+    double mn = 2.;
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < Nel; e += (int64_t)gridDim.x * blockDim.x) {
+        const double mu = (double)mult[e];
+        if (mu == 0.) continue;
+        const double h = hval[e];
+        if (mode == 0) { v[0] += mu; v[1] += mu * h; mn = fmin(mn, h); }
+        else { double dlt = h - mean; v[0] += mu * dlt * dlt; }
+    }
+    if (mode == 0) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) mn = fmin(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+        // min over [0,1] values: atomicMin on the bit pattern of a non-negative double
+        if ((threadIdx.x & 31) == 0 && mn <= 1.)
+            atomicMin(reinterpret_cast<unsigned long long *>(minval), (unsigned long long)__double_as_longlong(fmax(mn, 0.)));
+    }
+    block_reduce_to_partials<2>(v, partial, counter, out, 0);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// vector kernels and CG
+// ---------------------------------------------------------------------------------------------------------------
+// y (op)= A x for the CSR stiffness, 8 lanes per row.  mode 0: y = A x ; 1: y += A x ; 2: y = rhs - A x
+// masked != nullptr: rows with masked[r] != 0 give y = 0 (mode 0/2).  dot != nullptr: partial sums of x . y.
+__global__ void __launch_bounds__(256) spmv_kernel(int64_t nrows, const int32_t *__restrict__ rowptr,
+                                                   const int32_t *__restrict__ col, const double *__restrict__ val,
+                                                   const double *__restrict__ x, const double *__restrict__ rhs,
+                                                   double *__restrict__ y, const unsigned char *__restrict__ masked, int mode,
+                                                   double *partial, unsigned int *counter, double *dot_out)
+{
+    const int sub = threadIdx.x & 7;
+    const int64_t r = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 3;
+    double s = 0., xy = 0.;
+    if (r < nrows) {
+        const int32_t b = rowptr[r], en = rowptr[r + 1];
+        for (int32_t i = b + sub; i < en; i += 8) s += __ldg(val + i) * __ldg(x + __ldg(col + i));
+    }
+    s += __shfl_xor_sync(0xffffffffu, s, 4);
+    s += __shfl_xor_sync(0xffffffffu, s, 2);
+    s += __shfl_xor_sync(0xffffffffu, s, 1);
+    if (r < nrows && sub == 0) {
+        double out;
+        const bool mk = masked && masked[r];
+        if (mode == 0) out = mk ? 0. : s;
+        else if (mode == 1) out = y[r] + s;
+        else out = mk ? 0. : rhs[r] - s;
+        y[r] = out;
+        if (partial) xy = x[r] * out;
+    }
+    if (partial) {
+        double v[1] = {xy};
+        block_reduce_to_partials<1>(v, partial, counter, dot_out, 0);
+    }
+}
+
+// CG scalars in device memory
+struct CgScalars {
+    double pq, rz, rz_new, rr, bb, alpha, beta;
+};
+
+// x += alpha p ; r -= alpha q ; z = r / diag ; partial sums of r.z and r.r   (alpha = rz / pq computed by every thread)
+__global__ void __launch_bounds__(256) cg_update_kernel(int64_t n, double *__restrict__ x, double *__restrict__ r,
+                                                        double *__restrict__ z, const double *__restrict__ p,
+                                                        const double *__restrict__ q, const double *__restrict__ diag,
+                                                        const unsigned char *__restrict__ fixed, CgScalars *sc, double *partial,
+                                                        unsigned int *counter)
+{
+    const double alpha = sc->rz / sc->pq;
+    double v[2] = {0., 0.};
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        if (fixed[i]) continue;
+        const double xi = x[i] + alpha * p[i];
+        const double ri = r[i] - alpha * q[i];
+        const double zi = ri / diag[i];
+        x[i] = xi; r[i] = ri; z[i] = zi;
+        v[0] += ri * zi;
+        v[1] += ri * ri;
+    }
+    block_reduce_to_partials<2>(v, partial, counter, &sc->rz_new, 0);   // writes rz_new, rr (adjacent)
+}
+
+// beta = rz_new / rz ; p = z + beta p ; then rz <- rz_new (thread 0 of block 0 after a grid-wide read is unsafe, so
+// the swap is done by the next spmv's prologue kernel: cg_swap_kernel)
+__global__ void __launch_bounds__(256) cg_p_kernel(int64_t n, double *__restrict__ p, const double *__restrict__ z,
+                                                   const CgScalars *sc)
+{
+    const double beta = sc->rz_new / sc->rz;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+        p[i] = z[i] + beta * p[i];
+}
+
+__global__ void cg_swap_kernel(CgScalars *sc) { sc->rz = sc->rz_new; }
+
+// init: r = b (masked), z = r / diag, p = z, x = 0 ; partial sums r.z and r.r
+__global__ void __launch_bounds__(256) cg_init_kernel(int64_t n, const double *__restrict__ b, double *__restrict__ x,
+                                                      double *__restrict__ r, double *__restrict__ z, double *__restrict__ p,
+                                                      const double *__restrict__ diag, const unsigned char *__restrict__ fixed,
+                                                      CgScalars *sc, double *partial, unsigned int *counter)
+{
+    double v[2] = {0., 0.};
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        double ri = fixed[i] ? 0. : b[i];
+        double zi = fixed[i] ? 0. : ri / diag[i];
+        x[i] = 0.; r[i] = ri; z[i] = zi; p[i] = zi;
+        v[0] += ri * zi;
+        v[1] += ri * ri;
+    }
+    block_reduce_to_partials<2>(v, partial, counter, &sc->rz_new, 0);
+}
+
+__global__ void __launch_bounds__(256) diag_kernel(int64_t nrows, const int32_t *__restrict__ rowptr,
+                                                   const int32_t *__restrict__ col, const double *__restrict__ val,
+                                                   double *__restrict__ diag)
+{
+    const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= nrows) return;
+    double d = 1.;
+    for (int32_t i = rowptr[r]; i < rowptr[r + 1]; i++)
+        if (col[i] == r) d = val[i];
+    diag[r] = (d != 0.) ? d : 1.;
+}
+
+// du = x on free dofs, du_bc on fixed dofs
+__global__ void __launch_bounds__(256) merge_du_kernel(int64_t n, const double *__restrict__ x, const double *__restrict__ du_bc,
+                                                       const unsigned char *__restrict__ fixed, double *__restrict__ du)
+{
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+        du[i] = fixed[i] ? du_bc[i] : x[i];
+}
+
+__global__ void __launch_bounds__(256) axpy_kernel(int64_t n, double a, const double *__restrict__ x, double *__restrict__ y)
+{
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) y[i] += a * x[i];
+}
+
+static inline unsigned vec_grid(int64_t n, int sm)
+{
+    int64_t g = (n + 255) / 256;
+    int64_t cap = (int64_t)sm * 8;
+    return (unsigned)std::max<int64_t>(1, std::min(g, cap));
+}
+
+cudaError_t launch_commit(const LaunchCtx &lc, int64_t Nel, int64_t Ndof, int NY, const int32_t *desc, double *u, const double *du,
+                          double *f, const int32_t *rowptr, const int32_t *col, const double *val, const double *elstiff,
+                          double *sig, double *eps, double *epl, const double *res_sig, const double *res_depl,
+                          const unsigned char *has_res, int64_t *launches)
+{
+    // u += du ; f += K du (1383-1384)
+    axpy_kernel<<<vec_grid(Ndof, lc.sm_count), 256, 0, lc.stream>>>(Ndof, 1., du, u);
+    spmv_kernel<<<(unsigned)((Ndof * 8 + 255) / 256), 256, 0, lc.stream>>>(Ndof, rowptr, col, val, du, nullptr, f, nullptr, 1, nullptr,
+                                                                          nullptr, nullptr);
+    commit_elements_kernel<<<(unsigned)((Nel + 127) / 128), 128, 0, lc.stream>>>(Nel, NY, desc, u, du, elstiff, sig, eps, epl, res_sig,
+                                                                                 res_depl, has_res);
+    *launches += 3;
+    return cudaGetLastError();
+}
+
+cudaError_t launch_global_sums(const LaunchCtx &lc, int64_t Nel, const int32_t *desc, const double *sig, const double *eps,
+                               const double *epl, double *partial, unsigned int *counter, double *out, int64_t *launches)
+{
+    unsigned grid = vec_grid(Nel, lc.sm_count);
+    global_sums_kernel<<<grid, 256, 0, lc.stream>>>(Nel, desc, sig, eps, epl, partial, counter, out);
+    (*launches)++;
+    return cudaGetLastError();
+}
+
+cudaError_t launch_scf(const LaunchCtx &lc, const DevMat *hmats, int nmat, int64_t Nel, int NY, const int32_t *desc, const double *sig,
+                       const double *epl, const double *du, const double *elstiff, const double *d_sld, double *hval,
+                       unsigned char *mult, double *partial, unsigned int *counter, double *d_out /*>= 4 doubles*/,
+                       double *h_out /*pinned*/, double *scf, int64_t *launches)
+{
+    scf_elements_kernel<<<(unsigned)((Nel + 127) / 128), 128, 0, lc.stream>>>(Nel, NY, desc, sig, epl, du, elstiff, hval, mult);
+    (*launches)++;
+    for (int i = 0; i < nmat; i++) {
+        if (hmats[i].kind != PLF_MAT_SVC) continue;
+        int blocks = lc.sm_count * 2;
+        int64_t need = (Nel + 7) / 8;
+        if (blocks > need) blocks = (int)need;
+        cudaFuncSetAttribute(scf_svc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        scf_svc_kernel<<<blocks, 256, sizeof(double) * 7 * (size_t)hmats[i].nsv_pad, lc.stream>>>(Nel, NY, i, desc, sig, epl, du, elstiff,
+                                                                                                  d_sld, hval, mult);
+        (*launches)++;
+    }
+    unsigned grid = vec_grid(Nel, lc.sm_count);
+    const double two = 2.;
+    cudaMemcpyAsync(d_out + 3, &two, sizeof(double), cudaMemcpyHostToDevice, lc.stream);   // min accumulator
+    scf_moments_kernel<<<grid, 256, 0, lc.stream>>>(Nel, hval, mult, 0., 0, partial, counter, d_out, d_out + 3);
+    (*launches)++;
+    cudaError_t e = cudaMemcpyAsync(h_out, d_out, 4 * sizeof(double), cudaMemcpyDeviceToHost, lc.stream);
+    if (e != cudaSuccess) return e;
+    if ((e = cudaStreamSynchronize(lc.stream)) != cudaSuccess) return e;
+    const double cnt = h_out[0], sum = h_out[1], mn = h_out[3];
+    if (cnt == 0.) { *scf = 1.; return cudaSuccess; }   // sc_list = [1.] (1056): std = 0 -> min = 1
+    const double mean = sum / cnt;
+    scf_moments_kernel<<<grid, 256, 0, lc.stream>>>(Nel, hval, mult, mean, 1, partial, counter, d_out, d_out + 3);
+    (*launches)++;
+    if ((e = cudaMemcpyAsync(h_out, d_out, sizeof(double), cudaMemcpyDeviceToHost, lc.stream)) != cudaSuccess) return e;
+    if ((e = cudaStreamSynchronize(lc.stream)) != cudaSuccess) return e;
+    const double sd = sqrt(h_out[0] / cnt);   // np.std (population)
+    double s = (sd < 0.1) ? mn : fmax(1.e-3, mean - sd);   // 1057-1062
+    if (s < 1.e-3) s = 1.e-3;                               // 1063-1066
+    *scf = s;
+    return cudaGetLastError();
+}
+
+// Jacobi-preconditioned CG on the masked operator.  b (rhs on free dofs) must already be in d_b.
+cudaError_t launch_cg(const LaunchCtx &lc, int64_t n, const int32_t *rowptr, const int32_t *col, const double *val,
+                      const unsigned char *fixed, const double *b, double *x, double *r, double *z, double *p, double *q,
+                      double *diag, double *partial, unsigned int *counter, void *d_sc, void *h_sc, double rtol, int max_iter,
+                      int check_every, int *iters, double *relres, int64_t *launches)
+{
+    CgScalars *sc = (CgScalars *)d_sc;
+    CgScalars *hs = (CgScalars *)h_sc;
+    const unsigned vg = vec_grid(n, lc.sm_count);
+    const unsigned sg = (unsigned)((n * 8 + 255) / 256);
+    cudaError_t e;
+    diag_kernel<<<(unsigned)((n + 255) / 256), 256, 0, lc.stream>>>(n, rowptr, col, val, diag);
+    cg_init_kernel<<<vg, 256, 0, lc.stream>>>(n, b, x, r, z, p, diag, fixed, sc, partial, counter);
+    cg_swap_kernel<<<1, 1, 0, lc.stream>>>(sc);
+    *launches += 3;
+    if ((e = cudaMemcpyAsync(hs, sc, sizeof(CgScalars), cudaMemcpyDeviceToHost, lc.stream)) != cudaSuccess) return e;
+    if ((e = cudaStreamSynchronize(lc.stream)) != cudaSuccess) return e;
+    const double bb = hs->rr;
+    *iters = 0;
+    *relres = 0.;
+    if (bb == 0.) return cudaSuccess;
+    const double target = rtol * rtol * bb;
+    int it = 0;
+    while (it < max_iter) {
+        int chunk = std::min(check_every, max_iter - it);
+        for (int c = 0; c < chunk; c++) {
+            spmv_kernel<<<sg, 256, 0, lc.stream>>>(n, rowptr, col, val, p, nullptr, q, fixed, 0, partial, counter, &sc->pq);
+            cg_update_kernel<<<vg, 256, 0, lc.stream>>>(n, x, r, z, p, q, diag, fixed, sc, partial, counter);
+            cg_p_kernel<<<vg, 256, 0, lc.stream>>>(n, p, z, sc);
+            cg_swap_kernel<<<1, 1, 0, lc.stream>>>(sc);
+        }
+        *launches += 4 * (int64_t)chunk;
+        it += chunk;
+        if ((e = cudaMemcpyAsync(hs, sc, sizeof(CgScalars), cudaMemcpyDeviceToHost, lc.stream)) != cudaSuccess) return e;
+        if ((e = cudaStreamSynchronize(lc.stream)) != cudaSuccess) return e;
+        *relres = sqrt(hs->rr / bb);
+        if (!(hs->rr > target)) break;   // also stops on NaN
+    }
+    *iters = it;
+    return cudaGetLastError();
+}
+
+cudaError_t launch_spmv(const LaunchCtx &lc, int64_t n, const int32_t *rowptr, const int32_t *col, const double *val, const double *x,
+                        const double *rhs, double *y, const unsigned char *masked, int mode, int64_t *launches)
+{
+    spmv_kernel<<<(unsigned)((n * 8 + 255) / 256), 256, 0, lc.stream>>>(n, rowptr, col, val, x, rhs, y, masked, mode, nullptr, nullptr,
+                                                                       nullptr);
+    (*launches)++;
+    return cudaGetLastError();
+}
+
+cudaError_t launch_merge_du(const LaunchCtx &lc, int64_t n, const double *x, const double *du_bc, const unsigned char *fixed, double *du,
+                            int64_t *launches)
+{
+    merge_du_kernel<<<vec_grid(n, lc.sm_count), 256, 0, lc.stream>>>(n, x, du_bc, fixed, du);
+    (*launches)++;
+    return cudaGetLastError();
+}
+
+}  // namespace plf

@@ -1,0 +1,47 @@
+// model_kernels.h -- launchers of model_kernels.cu
+#pragma once
+#include <algorithm>
+#include "plf_host.h"
+
+namespace plf {
+
+struct DevMat;
+
+// sweep statistics block in device scalars (mirrored to pinned host memory after every sweep)
+struct SweepStats {
+    unsigned int change;            // any tangent replaced (model.py:1355)
+    unsigned int nonconv;           // elements with f > yf_tolerance * 1.0001 (1361)
+    double max_hh;
+    unsigned long long counts[4];   // elastic, 1-step, 50-sub-step, radial corrections
+    unsigned int work_count;        // deferred (50-sub-step) elements of the compacted pass
+    unsigned int pad;
+    unsigned long long queue;       // SVC dynamic element queue
+};
+
+cudaError_t modelk_init();
+cudaError_t modelk_upload_materials(const DevMat *h, int n, cudaStream_t st);
+cudaError_t modelk_upload_geom(const GeomClass *h, int n, cudaStream_t st);
+cudaError_t launch_sweep(const LaunchCtx &lc, const DevMat *hmats, int nmat, int64_t Nel, int NY, int nit, const int32_t *desc,
+                         const double *sig, const double *epl, const double *du, double *elstiff, double *res_sig,
+                         double *res_depl, double *fyld, int32_t *nsteps, unsigned char *has_res, int32_t *worklist,
+                         void *d_stats, void *h_stats, int compact, int64_t *launches);
+cudaError_t launch_commit(const LaunchCtx &lc, int64_t Nel, int64_t Ndof, int NY, const int32_t *desc, double *u, const double *du,
+                          double *f, const int32_t *rowptr, const int32_t *col, const double *val, const double *elstiff,
+                          double *sig, double *eps, double *epl, const double *res_sig, const double *res_depl,
+                          const unsigned char *has_res, int64_t *launches);
+cudaError_t launch_global_sums(const LaunchCtx &lc, int64_t Nel, const int32_t *desc, const double *sig, const double *eps,
+                               const double *epl, double *partial, unsigned int *counter, double *out, int64_t *launches);
+cudaError_t launch_scf(const LaunchCtx &lc, const DevMat *hmats, int nmat, int64_t Nel, int NY, const int32_t *desc, const double *sig,
+                       const double *epl, const double *du, const double *elstiff, const double *d_sld, double *hval,
+                       unsigned char *mult, double *partial, unsigned int *counter, double *d_out, double *h_out, double *scf,
+                       int64_t *launches);
+cudaError_t launch_cg(const LaunchCtx &lc, int64_t n, const int32_t *rowptr, const int32_t *col, const double *val,
+                      const unsigned char *fixed, const double *b, double *x, double *r, double *z, double *p, double *q,
+                      double *diag, double *partial, unsigned int *counter, void *d_sc, void *h_sc, double rtol, int max_iter,
+                      int check_every, int *iters, double *relres, int64_t *launches);
+cudaError_t launch_spmv(const LaunchCtx &lc, int64_t n, const int32_t *rowptr, const int32_t *col, const double *val, const double *x,
+                        const double *rhs, double *y, const unsigned char *masked, int mode, int64_t *launches);
+cudaError_t launch_merge_du(const LaunchCtx &lc, int64_t n, const double *x, const double *du_bc, const unsigned char *fixed, double *du,
+                            int64_t *launches);
+
+}  // namespace plf

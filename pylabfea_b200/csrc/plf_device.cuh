@@ -1,0 +1,547 @@
+// plf_device.cuh -- device-side constitutive math shared by the sm_100a kernels.
+//
+// FP64 throughout.  One "yield model" policy per material family provides seq / yf / full_yf / fgrad; the
+// return-mapping core (response_core) is written once against that policy:
+//   HillModel : thread-per-element, analytic Hill-6p / J2 (+ Drucker / LHS term)   material.py:576-676, 816-858
+//   SvcModel  : warp-per-element, RBF support-vector decision function + gradient     material.py:398-405, 765-815
+//               with the table in shared memory and __shfl_xor reductions; ML_full_yf (414-516) incl. Brent.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "../../include/plfb200.h"
+
+namespace plf {
+
+struct DevMat {
+    int32_t kind, nsv, dev_only, tresca, lhs, nsv_pad;
+    double sy, khard;
+    double hill[6];
+    double d[3];     // I1 weights (calc_seq 645-650)
+    double d3[3];    // constant part of the gradient (calc_fgrad 829-832)
+    double CV[36];   // Element.CV (plane-strain or plane-stress variant)
+    double SV[36];   // compliance used by the radial-return correction (material.py:315-320)
+    double E, nu;
+    double gamma, rho, scale_seq, inv_scale_seq;
+    const double *sv;    // device, SoA [6][nsv_pad]
+    const double *dual;  // device, [nsv_pad] (zero padded)
+    double bar_m1[36], bar_m2[36], bar_exp;
+};
+
+// symmetric 6x6 packing: (i<=j) -> index
+__host__ __device__ constexpr int sym_idx(int i, int j)
+{
+    return (i <= j) ? (i * 6 - (i * (i - 1)) / 2 + (j - i)) : (j * 6 - (j * (j - 1)) / 2 + (i - j));
+}
+
+__device__ __forceinline__ double eps_eq6(const double *e)
+{
+    // basic.py:328-360
+    double a = e[0] * e[0] + e[1] * e[1] + e[2] * e[2];
+    double b = e[3] * e[3] + e[4] * e[4] + e[5] * e[5];
+    return sqrt(2. * (a + 0.5 * b) / 3.);
+}
+
+__device__ __forceinline__ void matvec6(const double *__restrict__ C, const double *v, double *o)
+{
+#pragma unroll
+    for (int i = 0; i < 6; i++) {
+        double s = 0.;
+#pragma unroll
+        for (int k = 0; k < 6; k++) s += C[6 * i + k] * v[k];
+        o[i] = s;
+    }
+}
+
+// eigenvalues of a symmetric 3x3 in Voigt order (11,22,33,23,13,12): cyclic Jacobi (Barlat, material.py:695-696)
+__device__ inline void sym3_eig(const double *v, double *w)
+{
+    double a00 = v[0], a11 = v[1], a22 = v[2], a12 = v[3], a02 = v[4], a01 = v[5];
+    for (int sweep = 0; sweep < 30; sweep++) {
+        double off = fabs(a01) + fabs(a02) + fabs(a12);
+        double dia = fabs(a00) + fabs(a11) + fabs(a22);
+        if (off <= 1e-300 || off <= 1e-18 * dia) break;
+        // rotate (0,1)
+        if (a01 != 0.) {
+            double th = (a11 - a00) / (2. * a01);
+            double t = copysign(1., th) / (fabs(th) + sqrt(th * th + 1.));
+            double c = rsqrt(t * t + 1.), s = t * c;
+            double n00 = a00 - t * a01, n11 = a11 + t * a01;
+            double n02 = c * a02 - s * a12, n12 = s * a02 + c * a12;
+            a00 = n00; a11 = n11; a02 = n02; a12 = n12; a01 = 0.;
+        }
+        if (a02 != 0.) {
+            double th = (a22 - a00) / (2. * a02);
+            double t = copysign(1., th) / (fabs(th) + sqrt(th * th + 1.));
+            double c = rsqrt(t * t + 1.), s = t * c;
+            double n00 = a00 - t * a02, n22 = a22 + t * a02;
+            double n01 = c * a01 - s * a12, n12 = s * a01 + c * a12;
+            a00 = n00; a22 = n22; a01 = n01; a12 = n12; a02 = 0.;
+        }
+        if (a12 != 0.) {
+            double th = (a22 - a11) / (2. * a12);
+            double t = copysign(1., th) / (fabs(th) + sqrt(th * th + 1.));
+            double c = rsqrt(t * t + 1.), s = t * c;
+            double n11 = a11 - t * a12, n22 = a22 + t * a12;
+            double n01 = c * a01 - s * a02, n02 = s * a01 + c * a02;
+            a11 = n11; a22 = n22; a01 = n01; a02 = n02; a12 = 0.;
+        }
+    }
+    w[0] = a00; w[1] = a11; w[2] = a22;
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// Hill-6p / J2 equivalent stress (material.py:650-673) and its gradient (826-845)
+// ------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ double hill_seq(const DevMat &m, const double *s)
+{
+    double I1 = (s[0] * m.d[0] + s[1] * m.d[1] + s[2] * m.d[2]) / 3.;
+    double d01 = s[0] - s[1], d12 = s[1] - s[2], d20 = s[2] - s[0];
+    double I2 = m.hill[0] * (d01 * d01) + m.hill[1] * (d12 * d12) + m.hill[2] * (d20 * d20) +
+                6. * m.hill[3] * (s[3] * s[3]) + 6. * m.hill[4] * (s[4] * s[4]) + 6. * m.hill[5] * (s[5] * s[5]);
+    return sqrt(0.5 * I2) + I1;
+}
+
+__device__ __forceinline__ double j2_seq(const double *s)
+{
+    // calc_seq for an elastic material: h = 1, d = 0 (material.py:640-643)
+    double d01 = s[0] - s[1], d12 = s[1] - s[2], d20 = s[2] - s[0];
+    double I2 = d01 * d01 + d12 * d12 + d20 * d20 + 6. * (s[3] * s[3]) + 6. * (s[4] * s[4]) + 6. * (s[5] * s[5]);
+    return sqrt(0.5 * I2);
+}
+
+__device__ inline double barlat_seq(const DevMat &m, const double *sv)
+{
+    // material.py:678-702
+    double p = (sv[0] + sv[1] + sv[2]) / 3.;
+    double sd[6] = {sv[0] - p, sv[1] - p, sv[2] - p, sv[3], sv[4], sv[5]};
+    double st1[6], st2[6], p1[3], p2[3];
+    matvec6(m.bar_m1, sd, st1);
+    matvec6(m.bar_m2, sd, st2);
+    sym3_eig(st1, p1);
+    sym3_eig(st2, p2);
+    double s = 0.;
+#pragma unroll
+    for (int i = 0; i < 3; i++)
+#pragma unroll
+        for (int j = 0; j < 3; j++) s += pow(fabs(p1[i] - p2[j]), m.bar_exp);
+    return pow(0.25 * s, 1. / m.bar_exp);
+}
+
+__device__ __forceinline__ void hill_fgrad(const DevMat &m, const double *s, double seq, double *a)
+{
+    double p = (s[0] + s[1] + s[2]) / 3.;
+    double s0 = s[0] - p, s1 = s[1] - p, s2 = s[2] - p;
+    double h0 = m.hill[0], h1 = m.hill[1], h2 = m.hill[2];
+    double i2 = 1. / (2. * seq), i1 = 1. / seq;
+    a[0] = ((h0 + h2) * s0 - h0 * s1 - h2 * s2) * i2 + m.d3[0];
+    a[1] = ((h1 + h0) * s1 - h0 * s0 - h1 * s2) * i2 + m.d3[1];
+    a[2] = ((h2 + h1) * s2 - h2 * s0 - h1 * s1) * i2 + m.d3[2];
+    a[3] = 3. * m.hill[3] * s[3] * i1;
+    a[4] = 3. * m.hill[4] * s[4] * i1;
+    a[5] = 3. * m.hill[5] * s[5] * i1;
+}
+
+struct HillModel {
+    static constexpr bool is_ml = false;
+    const DevMat &m;
+    __device__ explicit HillModel(const DevMat &mm) : m(mm) {}
+    __device__ __forceinline__ double khard() const { return m.khard; }
+    __device__ __forceinline__ double seq(const double *s) const
+    {
+        return m.kind == PLF_MAT_ELASTIC ? j2_seq(s) : hill_seq(m, s);
+    }
+    __device__ __forceinline__ double yf(const double *s, double sflow) const { return seq(s) - sflow; }
+    __device__ __forceinline__ double full_yf(const double *s, double sflow) const { return seq(s) - sflow; }
+    __device__ __forceinline__ void fgrad(const double *s, double *a) const { hill_fgrad(m, s, hill_seq(m, s), a); }
+};
+
+// ------------------------------------------------------------------------------------------------------------
+// RBF support-vector yield function, one warp per element.  All lanes hold the same element state; the sum over
+// support vectors is strided over lanes and combined with __shfl_xor (every lane ends with the full sum).
+// Shared-memory table: sv[6][nsv_pad] (SoA: lane-consecutive, conflict free) + dual[nsv_pad] (zero padded).
+// ------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ double warp_sum(double v)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// warp-aggregated append to a work list: one atomic per warp.  Must be called by all 32 lanes.
+__device__ __forceinline__ void warp_append(bool pred, int32_t item, int32_t *list, unsigned int *count)
+{
+    const unsigned m = __ballot_sync(0xffffffffu, pred);
+    if (m == 0) return;
+    const int lane = threadIdx.x & 31;
+    const int leader = __ffs(m) - 1;
+    unsigned base = 0;
+    if (lane == leader) base = atomicAdd(count, (unsigned)__popc(m));
+    base = __shfl_sync(0xffffffffu, base, leader);
+    if (pred) list[base + __popc(m & ((1u << lane) - 1u))] = item;
+}
+
+struct SvcModel {
+    static constexpr bool is_ml = true;
+    const DevMat &m;
+    const double *s_sv;    // shared, [6][nsv_pad]
+    const double *s_dual;  // shared, [nsv_pad]
+    int lane;
+    __device__ SvcModel(const DevMat &mm, const double *sv, const double *dual, int l)
+        : m(mm), s_sv(sv), s_dual(dual), lane(l) {}
+    // material.py:812-814: without work-hardening features every gradient call resets khard to 0
+    __device__ __forceinline__ double khard() const { return 0.; }
+    __device__ __forceinline__ double seq(const double *s) const { return hill_seq(m, s); }
+
+    __device__ __forceinline__ void features(const double *s, double *x) const
+    {
+        // create_scaled_input, sdim = 6 (material.py:2336-2340)
+        double p = m.dev_only ? (s[0] + s[1] + s[2]) / 3. : 0.;
+        x[0] = (s[0] - p) / m.scale_seq; x[1] = (s[1] - p) / m.scale_seq; x[2] = (s[2] - p) / m.scale_seq;
+        x[3] = s[3] / m.scale_seq; x[4] = s[4] / m.scale_seq; x[5] = s[5] / m.scale_seq;
+    }
+    // decision_function (material.py:405): sum_i dual_i exp(-gamma |x - sv_i|^2) + rho
+    __device__ __forceinline__ double decision_x(const double *x) const
+    {
+        const int np = m.nsv_pad;
+        double f = 0.;
+        for (int i = lane; i < np; i += 32) {
+            double r = 0.;
+#pragma unroll
+            for (int k = 0; k < 6; k++) {
+                double t = x[k] - s_sv[k * np + i];
+                r = fma(t, t, r);
+            }
+            f = fma(s_dual[i], exp(-m.gamma * r), f);
+        }
+        return warp_sum(f) + m.rho;
+    }
+    __device__ __forceinline__ double yf(const double *s, double /*sflow*/) const
+    {
+        double x[6];
+        features(s, x);
+        return decision_x(x);
+    }
+    // gradient of the decision function w.r.t. stress (material.py:768-778, 802-807)
+    __device__ __forceinline__ void fgrad(const double *s, double *a) const
+    {
+        const int np = m.nsv_pad;
+        double x[6], g[6] = {0., 0., 0., 0., 0., 0.};
+        features(s, x);
+        for (int i = lane; i < np; i += 32) {
+            double hv[6], r = 0.;
+#pragma unroll
+            for (int k = 0; k < 6; k++) {
+                hv[k] = x[k] - s_sv[k * np + i];
+                r = fma(hv[k], hv[k], r);
+            }
+            double w = s_dual[i] * exp(-m.gamma * r) * (-2. * m.gamma);
+#pragma unroll
+            for (int k = 0; k < 6; k++) g[k] = fma(w, hv[k], g[k]);
+        }
+#pragma unroll
+        for (int k = 0; k < 6; k++) a[k] = warp_sum(g[k]) / m.scale_seq;
+    }
+
+    // find_yloc_scalar (material.py:547-574)
+    __device__ __forceinline__ double yloc(double xs, const double *xu) const
+    {
+        double x[6];
+#pragma unroll
+        for (int k = 0; k < 6; k++) x[k] = xs * xu[k];
+        return decision_x(x);
+    }
+
+    // ML_full_yf (material.py:414-516).  ld == nullptr: loading direction = sig / seq.
+    __device__ double ml_full_yf(const double *sig, double sflow, const double *ld) const
+    {
+        double seq = hill_seq(m, sig);
+        if (seq < 0.01 && ld == nullptr) return seq - 0.85 * sflow;
+        double su[6];
+        if (ld == nullptr) {
+#pragma unroll
+            for (int k = 0; k < 6; k++) su[k] = sig[k] / seq;
+        } else {
+            double hh = 0.;
+#pragma unroll
+            for (int k = 0; k < 6; k++) hh += ld[k] * ld[k];
+            hh = sqrt(hh);
+            if (hh < 1.e-3) {
+#pragma unroll
+                for (int k = 0; k < 6; k++) su[k] = 0.;
+                su[0] = sqrt(1.5);
+            } else {
+#pragma unroll
+                for (int k = 0; k < 6; k++) su[k] = ld[k] * sqrt(1.5) / hh;
+            }
+        }
+        // features of the unit stress: x(xs * su) = xs * x(su) is NOT used (division by scale_seq after the
+        // product, as the reference does): keep xs*su then scale.
+        double x0 = sflow;
+        if (su[0] * su[1] < -1.e-5) x0 *= (m.tresca ? 0.4 : 0.5);
+        double x1 = x0;
+        auto f = [&](double xs) {
+            double s[6];
+#pragma unroll
+            for (int k = 0; k < 6; k++) s[k] = xs * su[k];
+            return yf(s, sflow);
+        };
+        while (f(x0) >= 0. && x0 > 0.01) x0 *= 0.98;
+        while (f(x1) < 0. && x1 < 5. * sflow) x1 *= 1.02;
+        double f0 = f(x0), f1 = f(x1);
+        if (f0 * f1 > 0.) return seq - 0.85 * sflow;
+        // scipy.optimize.root_scalar(method='brentq', xtol=1e-5): rtol = 4 eps, maxiter = 100
+        const double xtol = 1.e-5, rtol = 4. * 2.220446049250313e-16;
+        double xpre = x0, xcur = x1, xblk = 0., fpre = f0, fcur = f1, fblk = 0., spre = 0., scur = 0.;
+        double xs = 0.;
+        bool conv = false;
+        if (fpre == 0.) { xs = xpre; conv = true; }
+        else if (fcur == 0.) { xs = xcur; conv = true; }
+        else {
+            for (int it = 0; it < 100; it++) {
+                if (fpre != 0. && fcur != 0. && (signbit(fpre) != signbit(fcur))) {
+                    xblk = xpre; fblk = fpre;
+                    spre = scur = xcur - xpre;
+                }
+                if (fabs(fblk) < fabs(fcur)) {
+                    xpre = xcur; xcur = xblk; xblk = xpre;
+                    fpre = fcur; fcur = fblk; fblk = fpre;
+                }
+                double delta = (xtol + rtol * fabs(xcur)) / 2.;
+                double sbis = (xblk - xcur) / 2.;
+                if (fcur == 0. || fabs(sbis) < delta) { xs = xcur; conv = true; break; }
+                if (fabs(spre) > delta && fabs(fcur) < fabs(fpre)) {
+                    double stry;
+                    if (xpre == xblk) {
+                        stry = -fcur * (xcur - xpre) / (fcur - fpre);
+                    } else {
+                        double dpre = (fpre - fcur) / (xpre - xcur);
+                        double dblk = (fblk - fcur) / (xblk - xcur);
+                        stry = -fcur * (fblk * dblk - fpre * dpre) / (dblk * dpre * (fblk - fpre));
+                    }
+                    if (2. * fabs(stry) < fmin(fabs(spre), 3. * fabs(sbis) - delta)) { spre = scur; scur = stry; }
+                    else { spre = sbis; scur = sbis; }
+                } else {
+                    spre = sbis; scur = sbis;
+                }
+                xpre = xcur; fpre = fcur;
+                if (fabs(scur) > delta) xcur += scur;
+                else xcur += (sbis > 0. ? delta : -delta);
+                fcur = f(xcur);
+            }
+            if (!conv) xs = xcur;
+        }
+        if (conv && xs < 4. * sflow) return seq - xs * hill_seq(m, su);
+        return seq - 0.85 * sflow;
+    }
+    __device__ __forceinline__ double full_yf(const double *s, double sflow) const { return ml_full_yf(s, sflow, nullptr); }
+};
+
+// ------------------------------------------------------------------------------------------------------------
+// radial-return correction helpers (material.py:310-342)
+// ------------------------------------------------------------------------------------------------------------
+// minimum-norm least-squares solution of the 3x6 system of material.py:328-332 (np.linalg.lstsq, rcond=None):
+// x = A^T (A A^T)^+ b, pseudo-inverse from the Jacobi eigen-decomposition of the 3x3 Gram matrix.
+static __device__ __noinline__ void lstsq_3x6(const double *d /*deps_r*/, const double *b /*dsig[0:3]*/, double *x)
+{
+    const double A[3][6] = {{d[0], 0., 0., 0., d[2], d[1]}, {0., d[1], 0., d[2], 0., d[0]}, {0., 0., d[2], d[1], d[0], 0.}};
+    double G[3][3], V[3][3] = {{1., 0., 0.}, {0., 1., 0.}, {0., 0., 1.}};
+    for (int i = 0; i < 3; i++)
+        for (int j = 0; j < 3; j++) {
+            double s = 0.;
+            for (int k = 0; k < 6; k++) s += A[i][k] * A[j][k];
+            G[i][j] = s;
+        }
+    for (int sweep = 0; sweep < 60; sweep++) {
+        double off = fabs(G[0][1]) + fabs(G[0][2]) + fabs(G[1][2]);
+        double dia = fabs(G[0][0]) + fabs(G[1][1]) + fabs(G[2][2]);
+        if (off <= 1e-300 || off <= 1e-20 * dia) break;
+        for (int p = 0; p < 2; p++)
+            for (int q = p + 1; q < 3; q++) {
+                if (G[p][q] == 0.) continue;
+                double theta = (G[q][q] - G[p][p]) / (2. * G[p][q]);
+                double t = copysign(1., theta) / (fabs(theta) + sqrt(theta * theta + 1.));
+                double c = 1. / sqrt(t * t + 1.), s = t * c;
+                for (int k = 0; k < 3; k++) {
+                    double gkp = G[k][p], gkq = G[k][q];
+                    G[k][p] = c * gkp - s * gkq; G[k][q] = s * gkp + c * gkq;
+                }
+                for (int k = 0; k < 3; k++) {
+                    double gpk = G[p][k], gqk = G[q][k];
+                    G[p][k] = c * gpk - s * gqk; G[q][k] = s * gpk + c * gqk;
+                }
+                for (int k = 0; k < 3; k++) {
+                    double vkp = V[k][p], vkq = V[k][q];
+                    V[k][p] = c * vkp - s * vkq; V[k][q] = s * vkp + c * vkq;
+                }
+            }
+    }
+    double lmax = fmax(G[0][0], fmax(G[1][1], G[2][2]));
+    double smax = lmax > 0. ? sqrt(lmax) : 0.;
+    double cut = 2.220446049250313e-16 * 6. * smax;
+    double y[3] = {0., 0., 0.};
+    for (int e = 0; e < 3; e++) {
+        double lam = G[e][e];
+        double sv = lam > 0. ? sqrt(lam) : 0.;
+        if (sv <= cut || sv == 0.) continue;
+        double vb = V[0][e] * b[0] + V[1][e] * b[1] + V[2][e] * b[2];
+        for (int i = 0; i < 3; i++) y[i] += V[i][e] * vb / lam;
+    }
+    for (int k = 0; k < 6; k++) x[k] = A[0][k] * y[0] + A[1][k] * y[1] + A[2][k] * y[2];
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// Material.response (material.py:207-346) for one element.
+//
+// The tangent of a sub-step is Ct = CV - ca ca^T / hh (C_tan, 1083-1085), so the stress update is
+// sig += CV deps_r - ca (ca . deps_r) / hh, and the returned average tangent is
+//   grad_stiff = CV (1 - st_scal) [split only] + (nsteps CV - W) st_scal / nsteps,  W = sum_steps (ca ca^T / hh + Ct_corr)
+// with W symmetric (21 registers instead of two 6x6 matrices).
+//
+// branch codes (for the sweep statistics): 0 elastic, 1 plastic single step, 2 plastic 50 sub-steps; bit 2 set when
+// at least one radial-return correction fired.
+// MODE 0: everything; MODE 1: return -1 instead of running the 50-sub-step loop (deferred to the compacted pass);
+// ------------------------------------------------------------------------------------------------------------
+template <int MODE, class Model>
+__device__ __forceinline__ int response_core(const Model &ym, const DevMat &m, double *sig /*in/out*/, const double *epl,
+                                             const double *deps, double *depl /*out*/, double *gs /*out, 21 sym*/,
+                                             double &fy_out, int &nsteps_out)
+{
+    const double *CV = m.CV;
+    const double sflow0 = m.sy + eps_eq6(epl) * ym.khard();   // get_sflow(epl) with the khard in effect
+    const double toler = PLF_YF_TOLERANCE * (m.sy + eps_eq6(epl) * m.khard);   // 243 (uses Material.khard as set)
+    double dsig[6], st[6];
+#pragma unroll
+    for (int k = 0; k < 6; k++) depl[k] = 0.;
+    matvec6(CV, deps, dsig);   // 244
+#pragma unroll
+    for (int k = 0; k < 6; k++) st[k] = sig[k] + dsig[k];
+    double fy1 = ym.full_yf(st, sflow0);   // 249-252
+    nsteps_out = 0;
+    if (fy1 < toler) {   // 253-256 purely elastic
+#pragma unroll
+        for (int k = 0; k < 6; k++) sig[k] = st[k];
+#pragma unroll
+        for (int i = 0; i < 6; i++)
+#pragma unroll
+            for (int j = i; j < 6; j++) gs[sym_idx(i, j)] = CV[6 * i + j];
+        fy_out = fy1;
+        return 0;
+    }
+    double st_scal = 1.;
+    double deps_r[6];
+    bool split = false;
+    double fy0 = ym.yf(sig, sflow0);   // 259
+    if (fy0 < PLF_SPLIT_FY0) {         // 260-270
+        split = true;
+        // ML: distance to the yield surface, called without epl (263-265): sflow = sy
+        if (Model::is_ml) fy0 = ym.full_yf(sig, m.sy);
+        st_scal += fy0 / ym.seq(dsig);
+        double del[6], t[6];
+#pragma unroll
+        for (int k = 0; k < 6; k++) del[k] = deps[k] * (1. - st_scal);
+        matvec6(CV, del, t);
+#pragma unroll
+        for (int k = 0; k < 6; k++) {
+            sig[k] += t[k];
+            deps_r[k] = deps[k] - del[k];
+        }
+    } else {
+#pragma unroll
+        for (int k = 0; k < 6; k++) deps_r[k] = deps[k];
+    }
+
+    // one plastic (sub-)step; returns fy at its end.  W accumulates ca ca^T / hh (+ correction block).
+    double W[21];
+#pragma unroll
+    for (int k = 0; k < 21; k++) W[k] = 0.;
+    double ddepl[6];
+    bool corrected = false;
+    const double kh = ym.khard();
+
+    auto plastic_step = [&](double *s, const double *dr, bool commit) -> double {
+        double cd[6], a[6], ca[6], eplt[6];
+        matvec6(CV, dr, cd);
+#pragma unroll
+        for (int k = 0; k < 6; k++) st[k] = s[k] + cd[k];
+        double yfun = ym.yf(st, sflow0);   // epl_dot 1031
+        ym.fgrad(s, a);                    // calc_fgrad (shared by epl_dot 1050 and C_tan 1082)
+        matvec6(CV, a, ca);
+        double hh = kh, acd = 0., cadr = 0.;
+#pragma unroll
+        for (int k = 0; k < 6; k++) {
+            hh += a[k] * ca[k];
+            acd += a[k] * cd[k];
+            cadr += ca[k] * dr[k];
+        }
+        double ihh = 1. / hh;
+        double lam = (yfun <= PLF_YF_TOLERANCE) ? 0. : acd * ihh;   // 1041-1054
+        double q = cadr * ihh;
+#pragma unroll
+        for (int k = 0; k < 6; k++) {
+            ddepl[k] = lam * a[k];
+            eplt[k] = epl[k] + depl[k] + ddepl[k];
+            st[k] = s[k] + (cd[k] - ca[k] * q);   // sig + t_stiff @ deps_r
+        }
+        double sfl = m.sy + eps_eq6(eplt) * ym.khard();
+        double fy = ym.full_yf(st, sfl);
+        if (!commit) return fy;
+#pragma unroll
+        for (int k = 0; k < 6; k++) s[k] = st[k];
+        if (fy > toler) {
+            // 310-342: scale the stress back radially, balance with plastic strain, correct the tangent
+            corrected = true;
+            double sq = ym.seq(s);
+            double ex[6], t[6];
+#pragma unroll
+            for (int k = 0; k < 6; k++) {
+                ex[k] = s[k] * fy / sq;
+                s[k] -= ex[k];
+            }
+            matvec6(m.SV, ex, t);
+#pragma unroll
+            for (int k = 0; k < 6; k++) {
+                ddepl[k] += t[k];
+                eplt[k] = epl[k] + depl[k] + ddepl[k];
+            }
+            double x[6];
+            lstsq_3x6(dr, ex, x);
+            W[sym_idx(0, 0)] += x[0]; W[sym_idx(0, 1)] += x[5]; W[sym_idx(0, 2)] += x[4];
+            W[sym_idx(1, 1)] += x[1]; W[sym_idx(1, 2)] += x[3]; W[sym_idx(2, 2)] += x[2];
+            sfl = m.sy + eps_eq6(eplt) * ym.khard();
+            fy = ym.full_yf(s, sfl);
+        }
+#pragma unroll
+        for (int i = 0; i < 6; i++)
+#pragma unroll
+            for (int j = i; j < 6; j++) W[sym_idx(i, j)] += ca[i] * ca[j] * ihh;
+#pragma unroll
+        for (int k = 0; k < 6; k++) depl[k] += ddepl[k];
+        return fy;
+    };
+
+    // trial step with the full remaining increment (277-285)
+    fy1 = plastic_step(sig, deps_r, false);
+    int nsteps = 1;
+    if (fy1 > toler) {   // 288-293
+        if (MODE == 1) return -1;
+        nsteps = PLF_MAXIT;
+#pragma unroll
+        for (int k = 0; k < 6; k++) deps_r[k] /= (double)PLF_MAXIT;
+    }
+    for (int it = 0; it < nsteps; it++) fy1 = plastic_step(sig, deps_r, true);   // 295-344
+
+    const double f1 = split ? (1. - st_scal) : 0.;
+    const double f2 = st_scal / (double)nsteps;
+#pragma unroll
+    for (int i = 0; i < 6; i++)
+#pragma unroll
+        for (int j = i; j < 6; j++) {
+            double c = CV[6 * i + j];
+            gs[sym_idx(i, j)] = c * f1 + ((double)nsteps * c - W[sym_idx(i, j)]) * f2;
+        }
+    fy_out = fy1;
+    nsteps_out = nsteps - 1;   // msg['nsteps'] = niter (345)
+    return (nsteps == 1 ? 1 : 2) | (corrected ? 4 : 0);
+}
+
+}  // namespace plf

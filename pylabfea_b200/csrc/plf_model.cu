@@ -1,0 +1,456 @@
+// plf_model.cu -- C-ABI entry points for the device-resident model: mesh, element tangents, Kel, setupK -> CSR,
+// the sweep / commit / calc_global / calc_scf steps of Model.solve, and the CG solve of the BC-reduced system.
+// Host code only (compiled with -ffp-contract=off): the B matrices are computed here with the reference's
+// operation order so they are bit-identical to Element.calc_Bmat (model.py:439-512).
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "model_kernels.h"
+#include "plf_device.cuh"
+#include "plf_host.h"
+#include "plf_model.h"
+
+using namespace plf;
+
+#define CK(call)                                                                                        \
+    do {                                                                                                \
+        cudaError_t e_ = (call);                                                                        \
+        if (e_ != cudaSuccess)                                                                          \
+            return fail(ctx, PLF_ECUDA, std::string(#call) + ": " + cudaGetErrorString(e_));            \
+    } while (0)
+
+template <class T>
+static int dalloc(plf_ctx *ctx, T **p, size_t n)
+{
+    if (*p) { cudaFree(*p); *p = nullptr; }
+    if (n == 0) return PLF_OK;
+    CK(cudaMalloc((void **)p, n * sizeof(T)));
+    return PLF_OK;
+}
+
+void model_free(plf_ctx *c)
+{
+    cudaFree(c->d_desc); cudaFree(c->d_elstiff); cudaFree(c->d_sig); cudaFree(c->d_eps); cudaFree(c->d_epl);
+    cudaFree(c->d_res_sig); cudaFree(c->d_res_depl); cudaFree(c->d_fyld); cudaFree(c->d_nsteps); cudaFree(c->d_branch);
+    cudaFree(c->d_has_res); cudaFree(c->d_u); cudaFree(c->d_du); cudaFree(c->d_f); cudaFree(c->d_rowptr); cudaFree(c->d_col);
+    cudaFree(c->d_val); cudaFree(c->d_worklist); cudaFree(c->d_r); cudaFree(c->d_z); cudaFree(c->d_p); cudaFree(c->d_q);
+    cudaFree(c->d_b); cudaFree(c->d_diag); cudaFree(c->d_w); cudaFree(c->d_fixed); cudaFree(c->d_partial);
+    c->d_desc = nullptr; c->d_elstiff = c->d_sig = c->d_eps = c->d_epl = c->d_res_sig = c->d_res_depl = c->d_fyld = nullptr;
+    c->d_nsteps = c->d_branch = nullptr; c->d_has_res = nullptr; c->d_u = c->d_du = c->d_f = nullptr;
+    c->d_rowptr = c->d_col = nullptr; c->d_val = nullptr; c->d_worklist = nullptr;
+    c->d_r = c->d_z = c->d_p = c->d_q = c->d_b = c->d_diag = c->d_w = nullptr; c->d_fixed = nullptr; c->d_partial = nullptr;
+    c->mesh_ready = c->K_ready = false;
+}
+
+cudaError_t model_upload_materials(plf_ctx *ctx)
+{
+    cudaError_t e = modelk_init();
+    if (e != cudaSuccess) return e;
+    return modelk_upload_materials(ctx->hmats, ctx->nmat, ctx->stream);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// geometry classes: Element.__init__ (model.py:316-348) + calc_Bmat (439-512)
+// ---------------------------------------------------------------------------------------------------------------
+static void make_geom(const DevMat &m, int planestress, double lx, double ly, double thick, GeomClass &g, double B4[4][48])
+{
+    memset(&g, 0, sizeof g);
+    const double cpos = std::sqrt(1. / 3.);
+    g.vel = lx * ly * thick;          // 316
+    g.jacw = (g.vel * 4.) * 1.;       // 322, 340, 370: Jac * wght
+    for (int i = 0; i < 4; i++) {
+        const double sx = ((i / 2) % 2) ? -1. : 1.;   // (-1) ** int(i / 2)
+        const double sy = (i % 2) ? -1. : 1.;         // (-1) ** i
+        const double x = 0.5 * (1. + sx * cpos) * lx;
+        const double y = 0.5 * (1. + sy * cpos) * ly;
+        const double xi1 = 2. * x / lx - 1.;
+        const double xi2 = 2. * y / ly - 1.;
+        const double hxm = 0.125 * (1. - xi1) / ly;
+        const double hym = 0.125 * (1. - xi2) / lx;
+        const double hxp = 0.125 * (1. + xi1) / ly;
+        const double hyp = 0.125 * (1. + xi2) / lx;
+        const double p[4] = {-hym, -hyp, hym, hyp};
+        const double q[4] = {-hxm, hxm, -hxp, hxp};
+        double *B = B4[i];
+        memset(B, 0, 48 * sizeof(double));
+        for (int l = 0; l < 4; l++) {
+            g.p[i][l] = p[l];
+            g.q[i][l] = q[l];
+            B[0 * 8 + 2 * l] = p[l];
+            B[1 * 8 + 2 * l + 1] = q[l];
+            B[5 * 8 + 2 * l] = q[l];
+            B[5 * 8 + 2 * l + 1] = p[l];
+        }
+        if (planestress) {
+            // hh = CV @ B (numpy matmul = ascending-k fma chain); B[2,:] = -nu*(hh[0,:]+hh[1,:])/E   (498-501)
+            for (int j = 0; j < 8; j++) {
+                double h0 = 0., h1 = 0.;
+                for (int k = 0; k < 6; k++) {
+                    h0 = std::fma(m.CV[k], B[8 * k + j], h0);
+                    h1 = std::fma(m.CV[6 + k], B[8 * k + j], h1);
+                }
+                const double v = -m.nu * (h0 + h1) / m.E;
+                g.r[i][j] = v;
+                B[2 * 8 + j] = v;
+            }
+        }
+    }
+    // centroid operator: sum_g wght * B_g, accumulated in Gauss point order like Element.deps (395-398)
+    for (int r = 0; r < 6; r++)
+        for (int c = 0; c < 8; c++) {
+            double s = 0.;
+            for (int i = 0; i < 4; i++) s += B4[i][8 * r + c];
+            g.bsum[r][c] = s;
+        }
+}
+
+extern "C" int plf_mesh_structured(plf_ctx *ctx, int NX, int NY, const double *dx, double dy, double thick, const int32_t *elem_mat)
+{
+    if (!ctx) return PLF_EINVAL;
+    if (ctx->nmat == 0) return fail(ctx, PLF_ESTATE, "plf_mesh_structured: call plf_set_materials first (Model.assign before Model.mesh)");
+    if (NX < 1 || NY < 1 || !dx || !elem_mat || !(dy > 0.) || !(thick > 0.))
+        return fail(ctx, PLF_EINVAL, "plf_mesh_structured: bad arguments");
+    const int64_t Nel = (int64_t)NX * NY, Nnode = (int64_t)(NX + 1) * (NY + 1), Ndof = 2 * Nnode;
+    const int64_t nnz = 4ll * (3ll * NX + 1) * (3ll * NY + 1);
+    if (nnz > 2147483647ll) return fail(ctx, PLF_EUNSUPPORTED, "plf_mesh_structured: CSR index exceeds int32");
+    CK(cudaSetDevice(ctx->device));
+    model_free(ctx);
+    ctx->NX = NX; ctx->NY = NY; ctx->Nel = Nel; ctx->Nnode = Nnode; ctx->Ndof = Ndof; ctx->nnz = nnz;
+    ctx->dy = dy; ctx->thick = thick;
+    ctx->dx.assign(dx, dx + NX);
+    // geometry classes: unique (dx, material if plane stress)
+    ctx->ngeom = 0;
+    ctx->h_desc.resize((size_t)Nel);
+    struct Key { double dx; int mat; };
+    std::vector<Key> keys;
+    double vol = 0.;
+    for (int j = 0; j < NX; j++) {
+        if (!(dx[j] > 0.)) return fail(ctx, PLF_EINVAL, "plf_mesh_structured: dx must be positive");
+        for (int k = 0; k < NY; k++) {
+            const int64_t e = (int64_t)j * NY + k;
+            const int mid = elem_mat[e];
+            if (mid < 0 || mid >= ctx->nmat) return fail(ctx, PLF_EINVAL, "plf_mesh_structured: material index out of range");
+            const int kmat = ctx->planestress ? mid : 0;
+            int cls = -1;
+            for (size_t c = 0; c < keys.size(); c++)
+                if (keys[c].dx == dx[j] && keys[c].mat == kmat) { cls = (int)c; break; }
+            if (cls < 0) {
+                if ((int)keys.size() >= PLF_MAX_GEOM)
+                    return fail(ctx, PLF_EUNSUPPORTED, "plf_mesh_structured: more than " + std::to_string(PLF_MAX_GEOM) +
+                                                           " distinct element geometries");
+                cls = (int)keys.size();
+                keys.push_back({dx[j], kmat});
+                make_geom(ctx->hmats[kmat], ctx->planestress, dx[j], dy, thick, ctx->geom[cls], ctx->geom_B[cls]);
+            }
+            ctx->h_desc[(size_t)e] = (cls << 16) | mid;
+            vol += ctx->geom[cls].vel;
+        }
+    }
+    ctx->ngeom = (int)keys.size();
+    ctx->volume = vol;
+    int rc;
+    const size_t E = (size_t)Nel, D = (size_t)Ndof;
+    if ((rc = dalloc(ctx, &ctx->d_desc, E)) || (rc = dalloc(ctx, &ctx->d_elstiff, 36 * E)) || (rc = dalloc(ctx, &ctx->d_sig, 6 * E)) ||
+        (rc = dalloc(ctx, &ctx->d_eps, 6 * E)) || (rc = dalloc(ctx, &ctx->d_epl, 6 * E)) || (rc = dalloc(ctx, &ctx->d_res_sig, 6 * E)) ||
+        (rc = dalloc(ctx, &ctx->d_res_depl, 6 * E)) || (rc = dalloc(ctx, &ctx->d_fyld, E)) || (rc = dalloc(ctx, &ctx->d_nsteps, E)) ||
+        (rc = dalloc(ctx, &ctx->d_has_res, E)) || (rc = dalloc(ctx, &ctx->d_worklist, E)) || (rc = dalloc(ctx, &ctx->d_u, D)) ||
+        (rc = dalloc(ctx, &ctx->d_du, D)) || (rc = dalloc(ctx, &ctx->d_f, D)) || (rc = dalloc(ctx, &ctx->d_rowptr, D + 1)) ||
+        (rc = dalloc(ctx, &ctx->d_col, (size_t)nnz)) || (rc = dalloc(ctx, &ctx->d_val, (size_t)nnz)))
+        return rc;
+    CK(cudaMemcpyAsync(ctx->d_desc, ctx->h_desc.data(), E * sizeof(int32_t), cudaMemcpyHostToDevice, ctx->stream));
+    CK(assembly_upload_geom(ctx->geom, ctx->ngeom, ctx->stream));
+    CK(modelk_upload_geom(ctx->geom, ctx->ngeom, ctx->stream));
+    LaunchCtx lc{ctx->stream, ctx->sm_count};
+    CK(launch_csr_pattern(lc, NX, NY, ctx->d_rowptr, ctx->d_col, &ctx->launches));
+    // first Model.solve (model.py:1214-1227): zero state, elstiff = CV
+    CK(cudaMemsetAsync(ctx->d_sig, 0, 6 * E * sizeof(double), ctx->stream));
+    CK(cudaMemsetAsync(ctx->d_eps, 0, 6 * E * sizeof(double), ctx->stream));
+    CK(cudaMemsetAsync(ctx->d_epl, 0, 6 * E * sizeof(double), ctx->stream));
+    CK(cudaMemsetAsync(ctx->d_res_sig, 0, 6 * E * sizeof(double), ctx->stream));
+    CK(cudaMemsetAsync(ctx->d_res_depl, 0, 6 * E * sizeof(double), ctx->stream));
+    CK(cudaMemsetAsync(ctx->d_fyld, 0, E * sizeof(double), ctx->stream));
+    CK(cudaMemsetAsync(ctx->d_nsteps, 0, E * sizeof(int32_t), ctx->stream));
+    CK(cudaMemsetAsync(ctx->d_has_res, 0, E, ctx->stream));
+    CK(cudaMemsetAsync(ctx->d_u, 0, D * sizeof(double), ctx->stream));
+    CK(cudaMemsetAsync(ctx->d_du, 0, D * sizeof(double), ctx->stream));
+    CK(cudaMemsetAsync(ctx->d_f, 0, D * sizeof(double), ctx->stream));
+    ctx->mesh_ready = true;
+    ctx->K_ready = false;
+    rc = plf_set_tangent(ctx, nullptr);
+    if (rc != PLF_OK) return rc;
+    CK(cudaStreamSynchronize(ctx->stream));
+    return PLF_OK;
+}
+
+#define NEED_MESH(name) \
+    if (!ctx) return PLF_EINVAL; \
+    if (!ctx->mesh_ready) return fail(ctx, PLF_ESTATE, std::string(name) + ": attributes for mesh not set (call plf_mesh_structured)")
+
+extern "C" int plf_mesh_sizes(const plf_ctx *ctx, int64_t *Nel, int64_t *Nnode, int64_t *Ndof, int64_t *nnz)
+{
+    if (!ctx || !ctx->mesh_ready) return PLF_ESTATE;
+    if (Nel) *Nel = ctx->Nel;
+    if (Nnode) *Nnode = ctx->Nnode;
+    if (Ndof) *Ndof = ctx->Ndof;
+    if (nnz) *nnz = ctx->nnz;
+    return PLF_OK;
+}
+
+extern "C" int plf_get_bmat(const plf_ctx *ctx, int64_t e, double *B4)
+{
+    if (!ctx || !ctx->mesh_ready || !B4 || e < 0 || e >= ctx->Nel) return PLF_EINVAL;
+    memcpy(B4, ctx->geom_B[ctx->h_desc[(size_t)e] >> 16], 4 * 48 * sizeof(double));
+    return PLF_OK;
+}
+
+extern "C" int plf_set_tangent(plf_ctx *ctx, const double *elstiff)
+{
+    NEED_MESH("plf_set_tangent");
+    CK(cudaSetDevice(ctx->device));
+    const size_t E = (size_t)ctx->Nel;
+    if (elstiff) {
+        CK(cudaMemcpyAsync(ctx->d_elstiff, elstiff, 36 * E * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    } else {
+        std::vector<double> h(36 * E);
+        for (size_t e = 0; e < E; e++) memcpy(&h[36 * e], ctx->hmats[ctx->h_desc[e] & 0xffff].CV, 36 * sizeof(double));
+        CK(cudaMemcpyAsync(ctx->d_elstiff, h.data(), 36 * E * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    }
+    CK(cudaStreamSynchronize(ctx->stream));
+    ctx->K_ready = false;
+    return PLF_OK;
+}
+
+extern "C" int plf_get_tangent(plf_ctx *ctx, double *elstiff)
+{
+    NEED_MESH("plf_get_tangent");
+    if (!elstiff) return PLF_EINVAL;
+    CK(cudaMemcpyAsync(elstiff, ctx->d_elstiff, 36 * (size_t)ctx->Nel * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return PLF_OK;
+}
+
+extern "C" int plf_get_kel(plf_ctx *ctx, double *Kel)
+{
+    NEED_MESH("plf_get_kel");
+    if (!Kel) return PLF_EINVAL;
+    CK(cudaSetDevice(ctx->device));
+    double *d = nullptr;
+    CK(cudaMalloc((void **)&d, 64 * (size_t)ctx->Nel * sizeof(double)));
+    LaunchCtx lc{ctx->stream, ctx->sm_count};
+    cudaError_t e = launch_kel(lc, ctx->Nel, ctx->planestress, ctx->d_desc, ctx->d_elstiff, d, &ctx->launches);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(Kel, d, 64 * (size_t)ctx->Nel * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    cudaFree(d);
+    CK(e);
+    return PLF_OK;
+}
+
+extern "C" int plf_setupK(plf_ctx *ctx)
+{
+    NEED_MESH("plf_setupK");
+    LaunchCtx lc{ctx->stream, ctx->sm_count};
+    CK(launch_assemble(lc, ctx->NX, ctx->NY, ctx->planestress, ctx->d_desc, ctx->d_elstiff, ctx->d_rowptr, ctx->d_val, &ctx->launches));
+    ctx->K_ready = true;
+    return PLF_OK;
+}
+
+extern "C" int plf_setupK_from_batch(plf_ctx *ctx, const plf_batch *b)
+{
+    NEED_MESH("plf_setupK_from_batch");
+    if (!b || b->n != ctx->Nel) return fail(ctx, PLF_EINVAL, "plf_setupK_from_batch: batch must hold exactly Nel elements");
+    LaunchCtx lc{ctx->stream, ctx->sm_count};
+    CK(launch_assemble(lc, ctx->NX, ctx->NY, ctx->planestress, ctx->d_desc, b->ctan, ctx->d_rowptr, ctx->d_val, &ctx->launches));
+    ctx->K_ready = true;
+    return PLF_OK;
+}
+
+extern "C" int plf_get_csr(plf_ctx *ctx, int32_t *rowptr, int32_t *col, double *val)
+{
+    NEED_MESH("plf_get_csr");
+    if (val && !ctx->K_ready) return fail(ctx, PLF_ESTATE, "plf_get_csr: call plf_setupK first");
+    if (rowptr) CK(cudaMemcpyAsync(rowptr, ctx->d_rowptr, ((size_t)ctx->Ndof + 1) * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
+    if (col) CK(cudaMemcpyAsync(col, ctx->d_col, (size_t)ctx->nnz * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
+    if (val) CK(cudaMemcpyAsync(val, ctx->d_val, (size_t)ctx->nnz * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return PLF_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// fields
+// ---------------------------------------------------------------------------------------------------------------
+static int field_ptr(plf_ctx *ctx, int field, void **p, size_t *bytes)
+{
+    const size_t E = (size_t)ctx->Nel, D = (size_t)ctx->Ndof;
+    switch (field) {
+    case PLF_SIG: *p = ctx->d_sig; *bytes = 6 * E * 8; break;
+    case PLF_EPS: *p = ctx->d_eps; *bytes = 6 * E * 8; break;
+    case PLF_EPL: *p = ctx->d_epl; *bytes = 6 * E * 8; break;
+    case PLF_RES_SIG: *p = ctx->d_res_sig; *bytes = 6 * E * 8; break;
+    case PLF_RES_DEPL: *p = ctx->d_res_depl; *bytes = 6 * E * 8; break;
+    case PLF_U: *p = ctx->d_u; *bytes = D * 8; break;
+    case PLF_DU: *p = ctx->d_du; *bytes = D * 8; break;
+    case PLF_F: *p = ctx->d_f; *bytes = D * 8; break;
+    case PLF_FYLD: *p = ctx->d_fyld; *bytes = E * 8; break;
+    case PLF_NSTEPS: *p = ctx->d_nsteps; *bytes = E * 4; break;
+    default: return fail(ctx, PLF_EINVAL, "unknown field id");
+    }
+    return PLF_OK;
+}
+
+extern "C" int plf_get_field(plf_ctx *ctx, int field, void *host)
+{
+    NEED_MESH("plf_get_field");
+    if (!host) return PLF_EINVAL;
+    void *p; size_t bytes;
+    int rc = field_ptr(ctx, field, &p, &bytes);
+    if (rc != PLF_OK) return rc;
+    CK(cudaMemcpyAsync(host, p, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return PLF_OK;
+}
+
+extern "C" int plf_set_field(plf_ctx *ctx, int field, const void *host)
+{
+    NEED_MESH("plf_set_field");
+    if (!host) return PLF_EINVAL;
+    void *p; size_t bytes;
+    int rc = field_ptr(ctx, field, &p, &bytes);
+    if (rc != PLF_OK) return rc;
+    CK(cudaMemcpyAsync(p, host, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    if (field == PLF_RES_SIG) CK(cudaMemsetAsync(ctx->d_has_res, 1, (size_t)ctx->Nel, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return PLF_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// non-linear loop pieces
+// ---------------------------------------------------------------------------------------------------------------
+static int ensure_partials(plf_ctx *ctx)
+{
+    const int need = ctx->sm_count * 8 * 18 + 64;
+    const int64_t spmv_blocks = (ctx->Ndof * 8 + 255) / 256 + 1;
+    const int64_t want = std::max<int64_t>(need, spmv_blocks * 2);
+    if (ctx->d_partial && ctx->n_partial >= want) return PLF_OK;
+    int rc = dalloc(ctx, &ctx->d_partial, (size_t)want);
+    if (rc != PLF_OK) return rc;
+    ctx->n_partial = (int)want;
+    return PLF_OK;
+}
+
+// layout of the 4 KB scalar scratch: [0,256) SweepStats | [256,512) CgScalars | [512,516) reduction counter |
+// [576,1024) small vectors (sld, global sums, scf moments)
+static inline unsigned int *counter_ptr(plf_ctx *ctx) { return (unsigned int *)(ctx->d_scalars + 512); }
+
+extern "C" int plf_sweep(plf_ctx *ctx, int nit, int32_t *change, int32_t *conv, double *max_hh, int64_t counts[4])
+{
+    NEED_MESH("plf_sweep");
+    LaunchCtx lc{ctx->stream, ctx->sm_count};
+    CK(launch_sweep(lc, ctx->hmats, ctx->nmat, ctx->Nel, ctx->NY, nit, ctx->d_desc, ctx->d_sig, ctx->d_epl, ctx->d_du, ctx->d_elstiff,
+                    ctx->d_res_sig, ctx->d_res_depl, ctx->d_fyld, ctx->d_nsteps, ctx->d_has_res, ctx->d_worklist, ctx->d_scalars,
+                    ctx->h_scalars, ctx->compact, &ctx->launches));
+    const SweepStats *st = (const SweepStats *)ctx->h_scalars;
+    if (change) *change = st->change ? 1 : 0;
+    if (conv) *conv = st->nonconv == 0 ? 1 : 0;
+    if (max_hh) *max_hh = st->max_hh;
+    if (counts) for (int i = 0; i < 4; i++) counts[i] = (int64_t)st->counts[i];
+    if (st->change) ctx->K_ready = false;
+    return PLF_OK;
+}
+
+extern "C" int plf_commit(plf_ctx *ctx)
+{
+    NEED_MESH("plf_commit");
+    if (!ctx->K_ready) return fail(ctx, PLF_ESTATE, "plf_commit: the stiffness the increment was solved with is not assembled");
+    LaunchCtx lc{ctx->stream, ctx->sm_count};
+    CK(launch_commit(lc, ctx->Nel, ctx->Ndof, ctx->NY, ctx->d_desc, ctx->d_u, ctx->d_du, ctx->d_f, ctx->d_rowptr, ctx->d_col, ctx->d_val,
+                     ctx->d_elstiff, ctx->d_sig, ctx->d_eps, ctx->d_epl, ctx->d_res_sig, ctx->d_res_depl, ctx->d_has_res,
+                     &ctx->launches));
+    return PLF_OK;
+}
+
+extern "C" int plf_reduce_global(plf_ctx *ctx, double *sig6, double *eps6, double *epl6)
+{
+    NEED_MESH("plf_reduce_global");
+    int rc = ensure_partials(ctx);
+    if (rc != PLF_OK) return rc;
+    LaunchCtx lc{ctx->stream, ctx->sm_count};
+    double *d_out = (double *)(ctx->d_scalars + 576);
+    CK(launch_global_sums(lc, ctx->Nel, ctx->d_desc, ctx->d_sig, ctx->d_eps, ctx->d_epl, ctx->d_partial, counter_ptr(ctx), d_out,
+                          &ctx->launches));
+    double *h = (double *)(ctx->h_scalars + 576);
+    CK(cudaMemcpyAsync(h, d_out, 18 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    // model.py:1508-1511: divide by the model volume lenx*leny*thick
+    double lenx = 0.;
+    for (double v : ctx->dx) lenx += v;
+    const double Vm = lenx * (ctx->dy * ctx->NY) * ctx->thick;
+    for (int k = 0; k < 6; k++) {
+        if (sig6) sig6[k] = h[k] / Vm;
+        if (eps6) eps6[k] = h[6 + k] / Vm;
+        if (epl6) epl6[k] = h[12 + k] / Vm;
+    }
+    return PLF_OK;
+}
+
+extern "C" int plf_calc_scf(plf_ctx *ctx, const double *sld, double *scf)
+{
+    NEED_MESH("plf_calc_scf");
+    if (!sld || !scf) return PLF_EINVAL;
+    int rc = ensure_partials(ctx);
+    if (rc != PLF_OK) return rc;
+    LaunchCtx lc{ctx->stream, ctx->sm_count};
+    double *d_sld = (double *)(ctx->d_scalars + 576);
+    double *d_out = (double *)(ctx->d_scalars + 640);
+    CK(cudaMemcpyAsync(d_sld, sld, 6 * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    // hval / mult reuse the fyld array and the worklist bytes (both are rewritten by the next sweep)
+    CK(launch_scf(lc, ctx->hmats, ctx->nmat, ctx->Nel, ctx->NY, ctx->d_desc, ctx->d_sig, ctx->d_epl, ctx->d_du, ctx->d_elstiff, d_sld,
+                  ctx->d_fyld, (unsigned char *)ctx->d_worklist, ctx->d_partial, counter_ptr(ctx), d_out,
+                  (double *)(ctx->h_scalars + 640), scf, &ctx->launches));
+    return PLF_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// linear solve
+// ---------------------------------------------------------------------------------------------------------------
+extern "C" int plf_solve_linear(plf_ctx *ctx, const uint8_t *fixed, const double *du_bc, const double *w, const double *f_ext,
+                                double rtol, int max_iter, int *iters, double *relres)
+{
+    NEED_MESH("plf_solve_linear");
+    if (!fixed || !du_bc || !w || !f_ext) return fail(ctx, PLF_EINVAL, "plf_solve_linear: NULL argument");
+    if (!ctx->K_ready) return fail(ctx, PLF_ESTATE, "plf_solve_linear: call plf_setupK first");
+    CK(cudaSetDevice(ctx->device));
+    const size_t D = (size_t)ctx->Ndof;
+    int rc;
+    if (!ctx->d_r) {
+        if ((rc = dalloc(ctx, &ctx->d_r, D)) || (rc = dalloc(ctx, &ctx->d_z, D)) || (rc = dalloc(ctx, &ctx->d_p, D)) ||
+            (rc = dalloc(ctx, &ctx->d_q, D)) || (rc = dalloc(ctx, &ctx->d_b, D)) || (rc = dalloc(ctx, &ctx->d_diag, D)) ||
+            (rc = dalloc(ctx, &ctx->d_w, D)) || (rc = dalloc(ctx, &ctx->d_fixed, D)))
+            return rc;
+    }
+    if ((rc = ensure_partials(ctx)) != PLF_OK) return rc;
+    LaunchCtx lc{ctx->stream, ctx->sm_count};
+    CK(cudaMemcpyAsync(ctx->d_fixed, fixed, D, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->d_w, w, D * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->d_q, f_ext, D * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->d_z, du_bc, D * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    // b = f_ext - K w on the free dofs (calc_BC, model.py:1099-1205)
+    CK(launch_spmv(lc, ctx->Ndof, ctx->d_rowptr, ctx->d_col, ctx->d_val, ctx->d_w, ctx->d_q, ctx->d_b, ctx->d_fixed, 2, &ctx->launches));
+    // du_bc is parked in d_w while CG runs (d_w is free after the rhs is built)
+    CK(cudaMemcpyAsync(ctx->d_w, ctx->d_z, D * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
+    int it = 0;
+    double rr = 0.;
+    double *x = ctx->d_du;   // CG iterate lives in du; fixed dofs are merged at the end
+    CK(launch_cg(lc, ctx->Ndof, ctx->d_rowptr, ctx->d_col, ctx->d_val, ctx->d_fixed, ctx->d_b, x, ctx->d_r, ctx->d_z, ctx->d_p, ctx->d_q,
+                 ctx->d_diag, ctx->d_partial, counter_ptr(ctx), ctx->d_scalars + 256, ctx->h_scalars + 256, rtol, max_iter, 50, &it, &rr,
+                 &ctx->launches));
+    CK(launch_merge_du(lc, ctx->Ndof, x, ctx->d_w, ctx->d_fixed, ctx->d_du, &ctx->launches));
+    CK(cudaStreamSynchronize(ctx->stream));
+    if (iters) *iters = it;
+    if (relres) *relres = rr;
+    if (!(rr <= rtol) && it >= max_iter)
+        return fail(ctx, PLF_ENOCONV, "plf_solve_linear: CG stopped at max_iter with relative residual " + std::to_string(rr));
+    return PLF_OK;
+}

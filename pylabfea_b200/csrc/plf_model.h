@@ -1,0 +1,75 @@
+// plf_model.h -- the context object behind the C-ABI handle and the device-resident model state.
+#pragma once
+#include <string>
+#include <vector>
+
+#include "plf_device.cuh"
+#include "plf_host.h"
+
+// device buffers of one batch of independent stress updates (AoS records, see DESIGN.md "data layout")
+struct plf_batch {
+    int64_t n = 0, cap = 0;
+    int32_t *mat_id = nullptr;
+    double *sig = nullptr, *epl = nullptr, *deps = nullptr;                       // in:  (n,6) each
+    double *fy = nullptr, *sig_out = nullptr, *depl = nullptr, *ctan = nullptr;   // out: (n), (n,6), (n,6), (n,36)
+    int32_t *nsteps = nullptr;
+    int32_t *worklist = nullptr;   // compaction list of 50-sub-step elements
+};
+
+struct plf_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    std::vector<cudaEvent_t> ev_pool;
+    std::string err;
+    int sm_count = 0, cc_major = 0, cc_minor = 0;
+    int64_t mem_bytes = 0;
+    char dev_name[128] = {0};
+    int64_t launches = 0;
+    unsigned char *d_flush = nullptr;
+    int flush_val = 0;
+    unsigned char *d_scalars = nullptr;   // 4 KB of device scratch scalars (counters, reductions)
+    unsigned char *h_scalars = nullptr;   // pinned mirror
+    int compact = 1;                      // two-pass (compacted) return mapping
+
+    // materials
+    int nmat = 0, planestress = 0;
+    plf::DevMat hmats[PLF_MAX_MATERIALS];
+    std::vector<plf_material> mats;
+    double *d_sv[PLF_MAX_MATERIALS] = {nullptr};
+    double *d_dual[PLF_MAX_MATERIALS] = {nullptr};
+    plf_batch scratch;
+
+    // mesh (Model.mesh, model.py:758-952)
+    bool mesh_ready = false, K_ready = false;
+    int NX = 0, NY = 0;
+    int64_t Nel = 0, Nnode = 0, Ndof = 0, nnz = 0;
+    double dy = 0., thick = 0.;
+    std::vector<double> dx;
+    std::vector<int32_t> h_desc;   // (geometry class << 16) | material id, per element
+    int ngeom = 0;
+    plf::GeomClass geom[PLF_MAX_GEOM];
+    double geom_B[PLF_MAX_GEOM][4][48];   // full B matrices per class (plf_get_bmat)
+    double volume = 0.;
+
+    int32_t *d_desc = nullptr;
+    double *d_elstiff = nullptr;                                                  // Element.elstiff (Nel,36)
+    double *d_sig = nullptr, *d_eps = nullptr, *d_epl = nullptr;                  // Element.sig/eps/epl (Nel,6)
+    double *d_res_sig = nullptr, *d_res_depl = nullptr;                           // Element.res_sig/res_depl
+    double *d_fyld = nullptr;                                                     // f list (model.py:1345)
+    int32_t *d_nsteps = nullptr, *d_branch = nullptr;
+    unsigned char *d_has_res = nullptr;                                           // el.res_sig is not None
+    double *d_u = nullptr, *d_du = nullptr, *d_f = nullptr;                       // Model.u/du/f (Ndof)
+    int32_t *d_rowptr = nullptr, *d_col = nullptr;
+    double *d_val = nullptr;                                                      // CSR(K)
+    int32_t *d_worklist = nullptr;
+    // solver work vectors
+    double *d_r = nullptr, *d_z = nullptr, *d_p = nullptr, *d_q = nullptr, *d_b = nullptr, *d_diag = nullptr, *d_w = nullptr;
+    unsigned char *d_fixed = nullptr;
+    double *d_partial = nullptr;   // block partial sums
+    int n_partial = 0;
+};
+
+int fail(plf_ctx *c, int code, const std::string &msg);
+void model_free(plf_ctx *ctx);
+cudaError_t model_upload_materials(plf_ctx *ctx);

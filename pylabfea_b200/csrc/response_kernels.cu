@@ -1,0 +1,402 @@
+// response_kernels.cu -- K1/K2: batched Material.response (material.py:207-346) and the batched user-facing
+// constitutive calls (calc_seq / calc_yf / calc_fgrad / ML_full_yf / epl_dot / C_tan) for sm_100a.
+//
+// K1 (Hill-6p / J2): one thread per element.  The 6-component sig / epl / deps records are AoS in HBM (48 B per
+//    element); a block stages its 128 records through shared memory with 128-bit loads so that every HBM
+//    transaction is a fully used 128 B line, and stages the 36-double tangent the same way on the way out.
+// K2 (SVC): one warp per element, support-vector table resident in shared memory (SoA), dynamic element queue.
+#include "plf_device.cuh"
+#include "plf_host.h"
+
+namespace plf {
+
+__constant__ DevMat c_mat[PLF_MAX_MATERIALS];
+
+cudaError_t response_upload_materials(const DevMat *h, int n, cudaStream_t st)
+{
+    return cudaMemcpyToSymbolAsync(c_mat, h, sizeof(DevMat) * n, 0, cudaMemcpyHostToDevice, st);
+}
+
+constexpr int RB = 128;       // threads (= elements) per block, K1
+constexpr int CT_STRIDE = 37; // padded shared-memory stride of one tangent record (odd -> conflict free)
+
+__device__ __forceinline__ void expand_sym(const double *gs, double *out, int stride1)
+{
+#pragma unroll
+    for (int i = 0; i < 6; i++)
+#pragma unroll
+        for (int j = 0; j < 6; j++) out[(6 * i + j) * stride1] = gs[sym_idx(i, j)];
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// K1: thread-per-element return mapping with shared-memory staged AoS I/O.
+//   index == nullptr : elements [0, n) in order (coalesced staging)
+//   index != nullptr : compacted pass over the elements listed in index[0..n) (gathered I/O)
+//   MODE 1           : 50-sub-step elements are appended to worklist instead of being processed
+// ------------------------------------------------------------------------------------------------------------
+template <int MODE, bool GATHER>
+__global__ void __launch_bounds__(RB) response_hill_kernel(int64_t n, const int32_t *__restrict__ mat_id,
+                                                           const double *__restrict__ sig, const double *__restrict__ epl,
+                                                           const double *__restrict__ deps, double *__restrict__ fy,
+                                                           double *__restrict__ sig_out, double *__restrict__ depl_out,
+                                                           double *__restrict__ ctan, int32_t *__restrict__ nsteps,
+                                                           const int32_t *__restrict__ index, int32_t *__restrict__ worklist,
+                                                           unsigned int *__restrict__ work_count)
+{
+    extern __shared__ double smem[];
+    double *s_sig = smem;               // RB*6
+    double *s_epl = smem + RB * 6;      // RB*6
+    double *s_dep = smem + 2 * RB * 6;  // RB*6
+    double *s_ct = smem + 3 * RB * 6;   // RB*CT_STRIDE
+    __shared__ unsigned char s_done[RB];
+
+    const int tid = threadIdx.x;
+    const int64_t base = (int64_t)blockIdx.x * RB;
+    const int cnt = (int)min((int64_t)RB, n - base);
+
+    double s[6], ep[6], de[6];
+    int64_t e = -1;
+    if (!GATHER) {
+        // coalesced 128-bit loads: cnt*3 double2 per array
+        const double2 *g0 = reinterpret_cast<const double2 *>(sig + base * 6);
+        const double2 *g1 = reinterpret_cast<const double2 *>(epl + base * 6);
+        const double2 *g2 = reinterpret_cast<const double2 *>(deps + base * 6);
+        for (int i = tid; i < cnt * 3; i += RB) {
+            reinterpret_cast<double2 *>(s_sig)[i] = __ldg(g0 + i);
+            reinterpret_cast<double2 *>(s_epl)[i] = __ldg(g1 + i);
+            reinterpret_cast<double2 *>(s_dep)[i] = __ldg(g2 + i);
+        }
+        __syncthreads();
+        if (tid < cnt) {
+            e = base + tid;
+#pragma unroll
+            for (int k = 0; k < 3; k++) {
+                double2 a = reinterpret_cast<double2 *>(s_sig)[3 * tid + k];
+                double2 b = reinterpret_cast<double2 *>(s_epl)[3 * tid + k];
+                double2 c = reinterpret_cast<double2 *>(s_dep)[3 * tid + k];
+                s[2 * k] = a.x; s[2 * k + 1] = a.y;
+                ep[2 * k] = b.x; ep[2 * k + 1] = b.y;
+                de[2 * k] = c.x; de[2 * k + 1] = c.y;
+            }
+        }
+    } else {
+        if (tid < cnt) {
+            e = index[base + tid];
+#pragma unroll
+            for (int k = 0; k < 3; k++) {
+                double2 a = __ldg(reinterpret_cast<const double2 *>(sig + e * 6) + k);
+                double2 b = __ldg(reinterpret_cast<const double2 *>(epl + e * 6) + k);
+                double2 c = __ldg(reinterpret_cast<const double2 *>(deps + e * 6) + k);
+                s[2 * k] = a.x; s[2 * k + 1] = a.y;
+                ep[2 * k] = b.x; ep[2 * k + 1] = b.y;
+                de[2 * k] = c.x; de[2 * k + 1] = c.y;
+            }
+        }
+    }
+
+    bool done = false, defer = false;
+    if (e >= 0) {
+        const int mid = mat_id ? mat_id[e] : 0;
+        const DevMat &m = c_mat[mid];
+        double dp[6], gs[21], fyv = 0.;
+        int ns = 0, br = 0;
+        if (m.kind == PLF_MAT_ELASTIC) {
+            // Model.solve never calls response for elastic materials (model.py:1341); elastic update for completeness
+            double t[6];
+            matvec6(m.CV, de, t);
+#pragma unroll
+            for (int k = 0; k < 6; k++) { s[k] += t[k]; dp[k] = 0.; }
+#pragma unroll
+            for (int i = 0; i < 6; i++)
+#pragma unroll
+                for (int j = i; j < 6; j++) gs[sym_idx(i, j)] = m.CV[6 * i + j];
+        } else if (m.kind == PLF_MAT_HILL) {
+            HillModel ym(m);
+            br = response_core<MODE>(ym, m, s, ep, de, dp, gs, fyv, ns);
+        } else {
+            br = -2;   // not this kernel's material family
+        }
+        if (br == -1) {
+            defer = true;
+        } else if (br != -2) {
+            done = true;
+            if (fy) fy[e] = fyv;
+            if (nsteps) nsteps[e] = ns;
+            if (!GATHER) {
+#pragma unroll
+                for (int k = 0; k < 6; k++) { s_sig[6 * tid + k] = s[k]; s_epl[6 * tid + k] = dp[k]; }
+                expand_sym(gs, s_ct + CT_STRIDE * tid, 1);
+            } else {
+                if (sig_out)
+#pragma unroll
+                    for (int k = 0; k < 6; k++) sig_out[e * 6 + k] = s[k];
+                if (depl_out)
+#pragma unroll
+                    for (int k = 0; k < 6; k++) depl_out[e * 6 + k] = dp[k];
+                if (ctan) expand_sym(gs, ctan + e * 36, 1);
+            }
+        }
+    }
+    if (MODE == 1) warp_append(defer, (int32_t)e, worklist, work_count);
+    if (!GATHER) {
+        s_done[tid] = done;
+        __syncthreads();
+        // coalesced 128-bit stores of the staged records (skipping deferred / foreign elements)
+        for (int i = tid; i < cnt * 3; i += RB) {
+            int el = i / 3;
+            if (!s_done[el]) continue;
+            if (sig_out) reinterpret_cast<double2 *>(sig_out + base * 6)[i] = reinterpret_cast<double2 *>(s_sig)[i];
+            if (depl_out) reinterpret_cast<double2 *>(depl_out + base * 6)[i] = reinterpret_cast<double2 *>(s_epl)[i];
+        }
+        if (ctan) {
+            double2 *g = reinterpret_cast<double2 *>(ctan + base * 36);
+            for (int i = tid; i < cnt * 18; i += RB) {
+                int el = i / 18, k2 = i - el * 18;
+                if (!s_done[el]) continue;
+                const double *p = s_ct + CT_STRIDE * el + 2 * k2;
+                g[i] = make_double2(p[0], p[1]);
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// K2: warp-per-element return mapping for one SVC material, SV table in shared memory.
+// ------------------------------------------------------------------------------------------------------------
+constexpr int SVC_WARPS = 8;
+
+__device__ __forceinline__ void svc_load_table(const DevMat &m, double *s_tab)
+{
+    const int np = m.nsv_pad;
+    for (int i = threadIdx.x; i < 6 * np; i += blockDim.x) s_tab[i] = m.sv[i];
+    for (int i = threadIdx.x; i < np; i += blockDim.x) s_tab[6 * np + i] = m.dual[i];
+    __syncthreads();
+}
+
+__global__ void __launch_bounds__(SVC_WARPS * 32) response_svc_kernel(int64_t n, int mid, const int32_t *__restrict__ mat_id,
+                                                                      const double *__restrict__ sig, const double *__restrict__ epl,
+                                                                      const double *__restrict__ deps, double *__restrict__ fy,
+                                                                      double *__restrict__ sig_out, double *__restrict__ depl_out,
+                                                                      double *__restrict__ ctan, int32_t *__restrict__ nsteps,
+                                                                      unsigned long long *__restrict__ queue)
+{
+    extern __shared__ double smem[];
+    const DevMat &m = c_mat[mid];
+    svc_load_table(m, smem);
+    const int lane = threadIdx.x & 31;
+    SvcModel ym(m, smem, smem + 6 * m.nsv_pad, lane);
+    for (;;) {
+        unsigned long long e0 = 0;
+        if (lane == 0) e0 = atomicAdd(queue, 1ull);
+        const int64_t e = (int64_t)__shfl_sync(0xffffffffu, e0, 0);
+        if (e >= n) break;
+        if (mat_id && mat_id[e] != mid) continue;
+        double s[6], ep[6], de[6], dp[6], gs[21], fyv;
+        int ns;
+#pragma unroll
+        for (int k = 0; k < 6; k++) {
+            s[k] = __ldg(sig + e * 6 + k);
+            ep[k] = __ldg(epl + e * 6 + k);
+            de[k] = __ldg(deps + e * 6 + k);
+        }
+        response_core<0>(ym, m, s, ep, de, dp, gs, fyv, ns);
+        if (lane == 0) {
+            if (fy) fy[e] = fyv;
+            if (nsteps) nsteps[e] = ns;
+            if (sig_out)
+#pragma unroll
+                for (int k = 0; k < 6; k++) sig_out[e * 6 + k] = s[k];
+            if (depl_out)
+#pragma unroll
+                for (int k = 0; k < 6; k++) depl_out[e * 6 + k] = dp[k];
+            if (ctan) expand_sym(gs, ctan + e * 36, 1);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// batched user-facing calls.  op: 0 calc_seq, 1 calc_yf, 2 calc_fgrad, 3 epl_dot, 4 C_tan
+// ------------------------------------------------------------------------------------------------------------
+enum { OP_SEQ = 0, OP_YF = 1, OP_FGRAD = 2, OP_EPLDOT = 3, OP_CTAN = 4, OP_MLFULL = 5 };
+
+template <class Model>
+__device__ __forceinline__ void prim_eval(const Model &ym, const DevMat &m, int op, const double *s, const double *ep,
+                                          const double *de, const double *ld, double *out, bool writer, int64_t e)
+{
+    if (op == OP_SEQ) {
+        double v = (m.kind == PLF_MAT_BARLAT) ? barlat_seq(m, s) : ym.seq(s);
+        if (writer) out[e] = v;
+    } else if (op == OP_YF) {
+        double sflow = m.sy + eps_eq6(ep) * m.khard;
+        double v = (m.kind == PLF_MAT_BARLAT) ? barlat_seq(m, s) - sflow : ym.yf(s, sflow);
+        if (writer) out[e] = v;
+    } else if (op == OP_MLFULL) {
+        double sflow = m.sy + eps_eq6(ep) * m.khard;
+        double v = ym.full_yf(s, sflow);
+        if (writer) out[e] = v;
+    } else if (op == OP_FGRAD) {
+        double a[6];
+        ym.fgrad(s, a);
+        if (writer)
+#pragma unroll
+            for (int k = 0; k < 6; k++) out[e * 6 + k] = a[k];
+    } else {
+        // epl_dot (material.py:1009-1055) / C_tan (1057-1086) with Cel = Element.CV
+        double a[6], ca[6], cd[6], st[6];
+        matvec6(m.CV, de, cd);
+#pragma unroll
+        for (int k = 0; k < 6; k++) st[k] = s[k] + cd[k];
+        double sflow = m.sy + eps_eq6(ep) * m.khard;
+        double yfun = (op == OP_EPLDOT) ? ym.yf(st, sflow) : 1.;
+        ym.fgrad(s, a);
+        matvec6(m.CV, a, ca);
+        double hh = ym.khard(), acd = 0.;
+#pragma unroll
+        for (int k = 0; k < 6; k++) { hh += a[k] * ca[k]; acd += a[k] * cd[k]; }
+        if (!writer) return;
+        if (op == OP_EPLDOT) {
+            double lam = (yfun <= PLF_YF_TOLERANCE) ? 0. : acd / hh;
+#pragma unroll
+            for (int k = 0; k < 6; k++) out[e * 6 + k] = lam * a[k];
+        } else {
+#pragma unroll
+            for (int i = 0; i < 6; i++)
+#pragma unroll
+                for (int j = 0; j < 6; j++) out[e * 36 + 6 * i + j] = m.CV[6 * i + j] - ca[i] * ca[j] / hh;
+        }
+    }
+}
+
+__global__ void __launch_bounds__(128) prim_hill_kernel(int op, int mid, int64_t n, const double *__restrict__ sig,
+                                                        const double *__restrict__ epl, const double *__restrict__ deps,
+                                                        double *__restrict__ out)
+{
+    const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= n) return;
+    const DevMat &m = c_mat[mid];
+    double s[6], ep[6] = {0, 0, 0, 0, 0, 0}, de[6] = {0, 0, 0, 0, 0, 0};
+#pragma unroll
+    for (int k = 0; k < 6; k++) {
+        s[k] = sig[e * 6 + k];
+        if (epl) ep[k] = epl[e * 6 + k];
+        if (deps) de[k] = deps[e * 6 + k];
+    }
+    HillModel ym(m);
+    prim_eval(ym, m, op, s, ep, de, nullptr, out, true, e);
+}
+
+__global__ void __launch_bounds__(SVC_WARPS * 32) prim_svc_kernel(int op, int mid, int64_t n, const double *__restrict__ sig,
+                                                                  const double *__restrict__ epl, const double *__restrict__ deps,
+                                                                  const double *__restrict__ ld, double *__restrict__ out)
+{
+    extern __shared__ double smem[];
+    const DevMat &m = c_mat[mid];
+    svc_load_table(m, smem);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    SvcModel ym(m, smem, smem + 6 * m.nsv_pad, lane);
+    for (int64_t e = (int64_t)blockIdx.x * SVC_WARPS + warp; e < n; e += (int64_t)gridDim.x * SVC_WARPS) {
+        double s[6], ep[6] = {0, 0, 0, 0, 0, 0}, de[6] = {0, 0, 0, 0, 0, 0};
+#pragma unroll
+        for (int k = 0; k < 6; k++) {
+            s[k] = sig[e * 6 + k];
+            if (epl) ep[k] = epl[e * 6 + k];
+            if (deps) de[k] = deps[e * 6 + k];
+        }
+        if (op == OP_MLFULL) {
+            double ldv[6];
+            if (ld)
+#pragma unroll
+                for (int k = 0; k < 6; k++) ldv[k] = ld[k];
+            double sflow = m.sy + eps_eq6(ep) * m.khard;
+            double v = ym.ml_full_yf(s, sflow, ld ? ldv : nullptr);
+            if (lane == 0) out[e] = v;
+        } else {
+            prim_eval(ym, m, op, s, ep, de, nullptr, out, lane == 0, e);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// host launchers
+// ------------------------------------------------------------------------------------------------------------
+static size_t k1_smem() { return sizeof(double) * (3 * RB * 6 + RB * CT_STRIDE); }
+static size_t svc_smem(const DevMat &m) { return sizeof(double) * 7 * (size_t)m.nsv_pad; }
+
+cudaError_t response_init()
+{
+    cudaError_t e;
+    e = cudaFuncSetAttribute(response_hill_kernel<0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)k1_smem());
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(response_hill_kernel<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)k1_smem());
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(response_hill_kernel<0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)k1_smem());
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(response_svc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e != cudaSuccess) return e;
+    return cudaFuncSetAttribute(prim_svc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+}
+
+// Launches the return mapping over n elements (device pointers).  scratch: worklist[n] int32 + 2 counters.
+cudaError_t launch_response(const LaunchCtx &lc, const DevMat *hmats, int nmat, int64_t n, const int32_t *mat_id,
+                            const double *sig, const double *epl, const double *deps, double *fy, double *sig_out,
+                            double *depl, double *ctan, int32_t *nsteps, int32_t *worklist, unsigned int *work_count,
+                            unsigned long long *queue, int compact, int64_t *launches)
+{
+    if (n <= 0) return cudaSuccess;
+    bool any_hill = false;
+    for (int i = 0; i < nmat; i++)
+        if (hmats[i].kind == PLF_MAT_HILL || hmats[i].kind == PLF_MAT_ELASTIC) any_hill = true;
+    const unsigned grid = (unsigned)((n + RB - 1) / RB);
+    if (any_hill) {
+        if (compact && worklist) {
+            cudaMemsetAsync(work_count, 0, sizeof(unsigned int), lc.stream);
+            response_hill_kernel<1, false><<<grid, RB, k1_smem(), lc.stream>>>(n, mat_id, sig, epl, deps, fy, sig_out, depl,
+                                                                                ctan, nsteps, nullptr, worklist, work_count);
+            (*launches)++;
+            unsigned int nw = 0;
+            cudaError_t e = cudaMemcpyAsync(&nw, work_count, sizeof nw, cudaMemcpyDeviceToHost, lc.stream);
+            if (e != cudaSuccess) return e;
+            e = cudaStreamSynchronize(lc.stream);
+            if (e != cudaSuccess) return e;
+            if (nw > 0) {
+                response_hill_kernel<0, true><<<(nw + RB - 1) / RB, RB, k1_smem(), lc.stream>>>(
+                    (int64_t)nw, mat_id, sig, epl, deps, fy, sig_out, depl, ctan, nsteps, worklist, nullptr, nullptr);
+                (*launches)++;
+            }
+        } else {
+            response_hill_kernel<0, false><<<grid, RB, k1_smem(), lc.stream>>>(n, mat_id, sig, epl, deps, fy, sig_out, depl,
+                                                                                ctan, nsteps, nullptr, nullptr, nullptr);
+            (*launches)++;
+        }
+    }
+    for (int i = 0; i < nmat; i++) {
+        if (hmats[i].kind != PLF_MAT_SVC) continue;
+        cudaMemsetAsync(queue, 0, sizeof(unsigned long long), lc.stream);
+        int blocks = lc.sm_count * 2;
+        int64_t need = (n + SVC_WARPS - 1) / SVC_WARPS;
+        if (blocks > need) blocks = (int)need;
+        response_svc_kernel<<<blocks, SVC_WARPS * 32, svc_smem(hmats[i]), lc.stream>>>(n, i, nmat > 1 ? mat_id : nullptr, sig,
+                                                                                       epl, deps, fy, sig_out, depl, ctan,
+                                                                                       nsteps, queue);
+        (*launches)++;
+    }
+    return cudaGetLastError();
+}
+
+cudaError_t launch_prim(const LaunchCtx &lc, const DevMat *hmats, int op, int mid, int64_t n, const double *sig,
+                        const double *epl, const double *deps, const double *ld, double *out, int64_t *launches)
+{
+    if (n <= 0) return cudaSuccess;
+    if (hmats[mid].kind == PLF_MAT_SVC) {
+        int blocks = lc.sm_count * 2;
+        int64_t need = (n + SVC_WARPS - 1) / SVC_WARPS;
+        if (blocks > need) blocks = (int)need;
+        prim_svc_kernel<<<blocks, SVC_WARPS * 32, svc_smem(hmats[mid]), lc.stream>>>(op, mid, n, sig, epl, deps, ld, out);
+    } else {
+        prim_hill_kernel<<<(unsigned)((n + 127) / 128), 128, 0, lc.stream>>>(op, mid, n, sig, epl, deps, out);
+    }
+    (*launches)++;
+    return cudaGetLastError();
+}
+
+}  // namespace plf

@@ -1,0 +1,219 @@
+"""GPU parity tests (run on the B200 box with -m gpu): the CUDA path, called through the C-ABI, against
+ (a) the golden fixtures produced by the unmodified reference and (b) the CPU oracle on fresh seeded inputs.
+
+Tolerances: CSR(K), Kel, B: bit-exact (np.array_equal).  Material.response: 1e-6 relative (BASELINE.json
+north_star); measured agreement is ~1e-12 for the analytic models."""
+import numpy as np
+import pytest
+
+from helpers import plf_material_from_golden, elastic_material, relmax
+
+pytestmark = pytest.mark.gpu
+
+RESP_MATS = ['j2', 'j2pp', 'hill', 'hillrv', 'drucker', 'cubic']
+TOL = 1e-6
+
+
+@pytest.fixture(scope='module')
+def ctx():
+    from pylabfea_b200 import _lib
+    c = _lib.Context(0)
+    yield c
+    c.close()
+
+
+def check_response(out, g, tag, sy, tol=TOL):
+    fy, so, dp, ct, ns = out
+    assert np.array_equal(ns, g[tag + '_nsteps'])
+    assert np.max(np.abs(fy - g[tag + '_fy'])) / sy < tol
+    for i in range(len(fy)):
+        assert relmax(so[i], g[tag + '_sig_out'][i]) < tol, i
+        assert np.max(np.abs(dp[i] - g[tag + '_depl'][i])) < tol * max(np.max(np.abs(g[tag + '_depl'][i])), 1e-4), i
+        assert relmax(ct[i], g[tag + '_ctan'][i]) < tol, i
+
+
+@pytest.mark.parametrize('compact', [0, 1])
+@pytest.mark.parametrize('tag', ['pe', 'ps'])
+@pytest.mark.parametrize('name', RESP_MATS)
+def test_response_vs_reference_golden(ctx, golden, name, tag, compact):
+    g = golden('response_' + name)
+    ctx.set_option('compact', compact)
+    ctx.set_materials([plf_material_from_golden(g)], planestress=(tag == 'ps'))
+    assert np.array_equal(ctx.element_CV(0), g[tag + '_CV'])
+    out = ctx.response_batch(g[tag + '_sig'], g[tag + '_epl'], g[tag + '_deps'])
+    check_response(out, g, tag, float(g['sy']))
+    ctx.set_option('compact', 1)
+
+
+@pytest.mark.parametrize('tag', ['pe', 'ps'])
+@pytest.mark.parametrize('name', RESP_MATS)
+def test_primitives_vs_reference_golden(ctx, golden, name, tag):
+    g = golden('response_' + name)
+    ctx.set_materials([plf_material_from_golden(g)], planestress=(tag == 'ps'))
+    sig, epl, deps = g[tag + '_sig'], g[tag + '_epl'], g[tag + '_deps']
+    assert relmax(ctx.calc_seq(0, sig), g[tag + '_seq']) < 1e-12
+    assert relmax(ctx.calc_yf(0, sig, epl), g[tag + '_yf']) < 1e-11
+    assert relmax(ctx.calc_fgrad(0, sig, epl), g[tag + '_fgrad']) < 1e-11
+    assert relmax(ctx.epl_dot(0, sig, epl, deps), g[tag + '_epl_dot']) < 1e-10
+    assert relmax(ctx.C_tan(0, sig, epl), g[tag + '_C_tan']) < 1e-11
+
+
+def test_response_mixed_materials_vs_oracle(ctx, golden):
+    """Several materials in one batch, ragged size, fresh random states: CUDA vs the CPU oracle."""
+    from oracle import oracle as orc
+    gs = [golden('response_' + n) for n in ('j2', 'hill', 'drucker')]
+    ctx.set_materials([plf_material_from_golden(g) for g in gs], planestress=False)
+    rng = np.random.default_rng(123)
+    n = 4099   # not a multiple of the block size
+    mid = rng.integers(0, 3, n).astype(np.int32)
+    sig = np.zeros((n, 6)); epl = np.zeros((n, 6)); deps = np.zeros((n, 6))
+    for k, g in enumerate(gs):
+        idx = np.nonzero(mid == k)[0]
+        src = rng.integers(0, len(g['pe_sig']), len(idx))
+        sig[idx] = g['pe_sig'][src] * rng.uniform(0.9, 1.02, (len(idx), 1))
+        epl[idx] = g['pe_epl'][src]
+        deps[idx] = g['pe_deps'][rng.integers(0, len(g['pe_sig']), len(idx))] * rng.uniform(0.2, 1.5, (len(idx), 1))
+    mats = [orc.Mat.from_golden(g) for g in gs]
+    CVs = np.array([g['pe_CV'] for g in gs])
+    ref = orc.response_batch(mats, mid, sig, epl, deps, CVs)
+    for compact in (0, 1):
+        ctx.set_option('compact', compact)
+        fy, so, dp, ct, ns = ctx.response_batch(sig, epl, deps, mat_id=mid)
+        assert np.array_equal(ns, ref[4])
+        assert np.max(np.abs(fy - ref[0])) < TOL * 150
+        assert relmax(so, ref[1]) < TOL and relmax(ct, ref[3]) < TOL
+        assert np.max(np.abs(dp - ref[2])) < TOL * np.max(np.abs(ref[2]))
+    ctx.set_option('compact', 1)
+
+
+def test_response_edge_cases(ctx, golden):
+    g = golden('response_j2')
+    ctx.set_materials([plf_material_from_golden(g)], planestress=False)
+    # empty batch
+    out = ctx.response_batch(np.zeros((0, 6)), np.zeros((0, 6)), np.zeros((0, 6)))
+    assert out[0].shape == (0,) and out[3].shape == (0, 6, 6)
+    # single element, zero increment from zero stress: purely elastic, tangent = CV
+    fy, so, dp, ct, ns = ctx.response_batch(np.zeros((1, 6)), np.zeros((1, 6)), np.zeros((1, 6)))
+    assert np.array_equal(ct[0], g['pe_CV']) and np.all(so == 0) and np.all(dp == 0) and ns[0] == 0
+    assert fy[0] == -float(g['sy'])
+    # shape errors raise ValueError like material.py:236-239
+    with pytest.raises(ValueError):
+        ctx.response_batch(np.zeros((2, 6)), np.zeros((3, 6)), np.zeros((2, 6)))
+    # material id out of range is rejected by the mesh call, not silently used
+    with pytest.raises(ValueError):
+        ctx.mesh_structured(2, 2, [1., 1.], 1., 1., np.full(4, 7))
+
+
+def test_svc_vs_reference_golden(ctx, golden):
+    g = golden('svc_hill')
+    ctx.set_materials([plf_material_from_golden(g)], planestress=False)
+    yf = ctx.calc_yf(0, g['yf_sig'])
+    assert np.max(np.abs(yf - g['yf'])) < 1e-10          # warp-tree sum vs libsvm's sequential sum
+    fg = ctx.calc_fgrad(0, g['yf_sig'])
+    assert relmax(fg, g['fgrad']) < 1e-10
+    n = len(g['ML_full_yf'])
+    fyf = ctx.ml_full_yf(0, g['yf_sig'][:n])
+    assert np.max(np.abs(fyf - g['ML_full_yf'])) < TOL * float(g['sy'])
+
+
+@pytest.mark.parametrize('tag', ['pe', 'ps'])
+def test_svc_response_vs_reference_golden(ctx, golden, tag):
+    g = golden('svc_hill')
+    ctx.set_materials([plf_material_from_golden(g)], planestress=(tag == 'ps'))
+    out = ctx.response_batch(g[tag + '_sig'], g[tag + '_epl'], g[tag + '_deps'])
+    check_response(out, g, tag, float(g['sy']), tol=2e-6)
+
+
+def test_barlat_seq_vs_reference_golden(ctx, golden):
+    from pylabfea_b200 import _lib
+    g = golden('barlat')
+    m = _lib.PlfMaterial()
+    m.kind = _lib.MAT_BARLAT
+    m.E, m.nu, m.sy = float(g['E']), float(g['nu']), float(g['sy'])
+    m.hill[:] = [1.] * 6
+    m.barlat_m1[:] = list(g['Bar_m1'].ravel())
+    m.barlat_m2[:] = list(g['Bar_m2'].ravel())
+    m.barlat_exp = float(g['barlat_exp'])
+    CV = np.eye(6)
+    m.CV[:] = list(CV.ravel())
+    ctx.set_materials([m], planestress=False)
+    assert relmax(ctx.calc_seq(0, g['sig']), g['seq']) < 1e-11
+    with pytest.raises(ValueError):      # material.py:822-823: no analytical gradient for Barlat
+        ctx.calc_fgrad(0, g['sig'])
+
+
+# ------------------------------------------------------------------------------------------------------------
+# K path: bit-exact
+# ------------------------------------------------------------------------------------------------------------
+KCASES = ['cantilever10', 'laminate16x4', 'inclusion18', 'uneven4x5_plastic', 'hill6_ps_plastic',
+          'inclusion9_plastic', 'single']
+
+
+def setup_mesh_from_golden(ctx, g):
+    from pylabfea_b200 import _lib
+    nm = len(g['mat_E'])
+    mats = []
+    for i in range(nm):
+        mats.append(elastic_material(g['mat_E'][i], g['mat_nu'][i], g['mat_CV'][i]))
+    ps = int(g['planestress'])
+    ctx.set_materials(mats, planestress=ps)
+    NX, NY = int(g['NX']), int(g['NY'])
+    dx = g['lx'].reshape(NX, NY)[:, 0]
+    ctx.mesh_structured(NX, NY, dx, float(g['ly'][0]), float(g['thick']), g['mat_id'])
+    return NX, NY
+
+
+@pytest.mark.parametrize('case', KCASES)
+def test_K_bit_exact_vs_reference_golden(ctx, golden, case):
+    g = golden('kmat_' + case)
+    NX, NY = setup_mesh_from_golden(ctx, g)
+    for e in range(len(g['Bmat'])):
+        assert np.array_equal(ctx.get_bmat(e), g['Bmat'][e]), 'B must be bit-exact'
+    ctx.set_tangent(g['elstiff'])
+    assert np.array_equal(ctx.get_kel(), g['Kel']), 'Kel must be bit-exact'
+    ctx.setupK()
+    rowptr, col, val = ctx.get_csr()
+    Ndof = int(g['Ndof'])
+    assert ctx.Ndof == Ndof and rowptr[-1] == ctx.nnz == 4 * (3 * NX + 1) * (3 * NY + 1)
+    # CSR well-formed: sorted, unique columns per row
+    for r in range(Ndof):
+        c = col[rowptr[r]:rowptr[r + 1]]
+        assert np.all(np.diff(c) > 0)
+    K = np.zeros((Ndof, Ndof))
+    rows = np.repeat(np.arange(Ndof), np.diff(rowptr))
+    K[rows, col] = val
+    Kref = np.zeros((Ndof, Ndof))
+    Kref[g['K_row'], g['K_col']] = g['K_val']
+    assert np.array_equal(K, Kref), 'assembled K must be bit-exact (max diff %g)' % np.max(np.abs(K - Kref))
+
+
+def test_K_large_mesh_vs_oracle(ctx, golden):
+    """256x256 (BASELINE config 2 size) with random plastic tangents: CSR values bit-exact vs the oracle's
+    ascending-element assembly; plus size-independent properties (symmetry to rounding, zero row sums)."""
+    from oracle import oracle as orc
+    g = golden('response_j2')
+    N = 256
+    ctx.set_materials([plf_material_from_golden(g)], planestress=False)
+    ctx.mesh_structured(N, N, np.full(N, 4. / N), 4. / N, 1., np.zeros(N * N, np.int32))
+    rng = np.random.default_rng(5)
+    T = g['pe_ctan'][rng.integers(0, len(g['pe_ctan']), N * N)]
+    ctx.set_tangent(T)
+    ctx.setupK()
+    rowptr, col, val = ctx.get_csr()
+    CV = g['pe_CV']
+    B4 = orc.gauss_bmats(4. / N, 4. / N, 0, CV, float(g['E']), float(g['nu']))
+    assert np.array_equal(ctx.get_bmat(0), B4)
+    jacw = ((4. / N) * (4. / N) * 1.) * 4.
+    idx = rng.integers(0, N * N, 200)
+    kel_gpu = ctx.get_kel()
+    for e in idx:
+        assert np.array_equal(kel_gpu[e], orc.kel(B4, T[e], jacw))
+    j, k = np.divmod(np.arange(N * N), N)
+    n1 = j * (N + 1) + k
+    nodes = np.stack([n1, n1 + 1, n1 + N + 1, n1 + N + 2], axis=1).astype(np.int32)
+    ref = orc.setupK_csr(nodes, kel_gpu, rowptr, col)
+    assert np.array_equal(val, ref)
+    # rigid translation is in the null space of K: row sums over the x (and y) columns vanish to rounding
+    rows = np.repeat(np.arange(ctx.Ndof), np.diff(rowptr))
+    sx = np.bincount(rows, weights=val * (col % 2 == 0), minlength=ctx.Ndof)
+    assert np.max(np.abs(sx)) < 1e-9 * np.max(np.abs(val))
