@@ -4,6 +4,7 @@
 //   commit  : state update (1383-1392), calc_global element sums (1500-1511), calc_scf (1036-1067)
 //   solver  : CSR SpMV + Jacobi-preconditioned CG on the BC-reduced system (1028-1033, 1291, 1335)
 // All reductions are deterministic (fixed-order partial sums, last-block-done final pass).
+#include "hill_fast.cuh"
 #include "plf_device.cuh"
 #include "plf_host.h"
 #include "model_kernels.h"
@@ -157,37 +158,55 @@ __global__ void __launch_bounds__(128) sweep_hill_kernel(int64_t n, int NY, int 
                                                          unsigned char *__restrict__ has_res, const int32_t *__restrict__ index,
                                                          int32_t *__restrict__ worklist, SweepStats *st)
 {
-    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    ElemStats es;
-    bool defer = false;
-    int64_t e = -1;
-    if (t < n) {
-        e = GATHER ? (int64_t)index[t] : t;
-        const int d = __ldg(desc + e);
-        const DevMat &m = c_mat[d & 0xffff];
-        if (m.kind == PLF_MAT_ELASTIC) {
-            fyld[e] = 0.;   // 1358-1359
-        } else if (m.kind == PLF_MAT_HILL) {
-            double s[6], ep[6], de[6], dp[6], gs[21], fyv;
-            int ns;
+    // MODE 1 / !GATHER: pass A over all elements; MODE 0 / GATHER: persistent pass B over the work list (length read
+    // from device memory: no host round trip between the passes); MODE 0 / !GATHER: unsplit response_core.
+    const int64_t total = GATHER ? (int64_t)st->work_count : n;
+    const int64_t stride = GATHER ? (int64_t)gridDim.x * blockDim.x : total + blockDim.x;
+    for (int64_t t0 = (int64_t)blockIdx.x * blockDim.x; t0 < total; t0 += stride) {
+        const int64_t t = t0 + threadIdx.x;
+        ElemStats es;
+        bool defer = false;
+        int64_t e = -1;
+        if (t < total) {
+            e = GATHER ? (int64_t)index[t] : t;
+            const int d = __ldg(desc + e);
+            const DevMat &m = c_mat[d & 0xffff];
+            if (m.kind == PLF_MAT_ELASTIC) {
+                fyld[e] = 0.;   // 1358-1359
+            } else if (m.kind == PLF_MAT_HILL) {
+                double s[6], ep[6], de[6], dp[6], gs[21], fyv;
+                int ns = 0, br;
 #pragma unroll
-            for (int k = 0; k < 3; k++) {
-                double2 a = __ldg(reinterpret_cast<const double2 *>(sig + e * 6) + k);
-                double2 b = __ldg(reinterpret_cast<const double2 *>(epl + e * 6) + k);
-                s[2 * k] = a.x; s[2 * k + 1] = a.y; ep[2 * k] = b.x; ep[2 * k + 1] = b.y;
-            }
-            element_strain(c_geom[d >> 16], NY, e, du, de);
-            HillModel ym(m);
-            const int br = response_core<MODE>(ym, m, s, ep, de, dp, gs, fyv, ns);
-            if (br == -1) {
-                defer = true;
-            } else {
-                es = sweep_finish(m, e, nit, s, dp, gs, fyv, ns, br, ep, elstiff, res_sig, res_depl, fyld, nsteps, has_res);
+                for (int k = 0; k < 3; k++) {
+                    double2 a = __ldg(reinterpret_cast<const double2 *>(sig + e * 6) + k);
+                    double2 b = __ldg(reinterpret_cast<const double2 *>(epl + e * 6) + k);
+                    s[2 * k] = a.x; s[2 * k + 1] = a.y; ep[2 * k] = b.x; ep[2 * k + 1] = b.y;
+                }
+                element_strain(c_geom[d >> 16], NY, e, du, de);
+                if (MODE == 1) {
+                    double ca[6], tc, tw;
+                    br = hill_passA(m, s, ep, de, dp, ca, tc, tw, fyv);
+#pragma unroll
+                    for (int i = 0; i < 6; i++)
+#pragma unroll
+                        for (int j = i; j < 6; j++) gs[sym_idx(i, j)] = m.CV[6 * i + j] * tc - (ca[i] * tw) * ca[j];
+                } else if (GATHER) {
+                    br = hill_passB(m, s, ep, de, dp, gs, fyv);
+                    ns = PLF_MAXIT - 1;
+                } else {
+                    HillModel ym(m);
+                    br = response_core<0>(ym, m, s, ep, de, dp, gs, fyv, ns);
+                }
+                if (br == -1) {
+                    defer = true;
+                } else {
+                    es = sweep_finish(m, e, nit, s, dp, gs, fyv, ns, br, ep, elstiff, res_sig, res_depl, fyld, nsteps, has_res);
+                }
             }
         }
+        if (MODE == 1) warp_append(defer, (int32_t)e, worklist, &st->work_count);
+        stats_block(es, st);
     }
-    if (MODE == 1) warp_append(defer, (int32_t)e, worklist, &st->work_count);
-    stats_block(es, st);
 }
 
 // sweep, warp per element, one SVC material (SV table in shared memory)
@@ -246,18 +265,10 @@ cudaError_t launch_sweep(const LaunchCtx &lc, const DevMat *hmats, int nmat, int
         if (compact) {
             sweep_hill_kernel<1, false><<<grid, 128, 0, lc.stream>>>(Nel, NY, nit, desc, sig, epl, du, elstiff, res_sig, res_depl,
                                                                       fyld, nsteps, has_res, nullptr, worklist, st);
-            (*launches)++;
-            e = cudaMemcpyAsync(h_stats, st, sizeof(SweepStats), cudaMemcpyDeviceToHost, lc.stream);
-            if (e != cudaSuccess) return e;
-            e = cudaStreamSynchronize(lc.stream);
-            if (e != cudaSuccess) return e;
-            const unsigned nw = ((SweepStats *)h_stats)->work_count;
-            if (nw > 0) {
-                sweep_hill_kernel<0, true><<<(nw + 127) / 128, 128, 0, lc.stream>>>((int64_t)nw, NY, nit, desc, sig, epl, du, elstiff,
-                                                                                    res_sig, res_depl, fyld, nsteps, has_res,
-                                                                                    worklist, nullptr, st);
-                (*launches)++;
-            }
+            const unsigned bgrid = (unsigned)std::min<int64_t>((int64_t)lc.sm_count * 8, (int64_t)grid);
+            sweep_hill_kernel<0, true><<<bgrid, 128, 0, lc.stream>>>(0, NY, nit, desc, sig, epl, du, elstiff, res_sig, res_depl, fyld,
+                                                                      nsteps, has_res, worklist, nullptr, st);
+            *launches += 2;
         } else {
             sweep_hill_kernel<0, false><<<grid, 128, 0, lc.stream>>>(Nel, NY, nit, desc, sig, epl, du, elstiff, res_sig, res_depl,
                                                                       fyld, nsteps, has_res, nullptr, nullptr, st);

@@ -244,6 +244,11 @@ extern "C" int plf_set_materials(plf_ctx *ctx, int nmat, const plf_material *mat
         }
         element_CV(m, planestress, d.CV);
         compliance(d.CV, d.SV);
+        d.cv_block = 1;
+        for (int r = 0; r < 6; r++)
+            for (int c = 0; c < 6; c++)
+                if (!((r < 3 && c < 3) || r == c) && d.CV[6 * r + c] != 0.) d.cv_block = 0;
+        d.has_d = (d.d[0] != 0. || d.d[1] != 0. || d.d[2] != 0.) ? 1 : 0;
         memcpy(d.bar_m1, m.barlat_m1, sizeof d.bar_m1);
         memcpy(d.bar_m2, m.barlat_m2, sizeof d.bar_m2);
         d.bar_exp = m.barlat_exp;

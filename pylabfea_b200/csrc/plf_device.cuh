@@ -14,6 +14,8 @@ namespace plf {
 
 struct DevMat {
     int32_t kind, nsv, dev_only, tresca, lhs, nsv_pad;
+    int32_t cv_block;   // CV = [3x3 normal block | diagonal shear] (cv_mul, hill_fast.cuh)
+    int32_t has_d;      // any Drucker / LHS weight non-zero
     double sy, khard;
     double hill[6];
     double d[3];     // I1 weights (calc_seq 645-650)

@@ -5,6 +5,9 @@
 //    element); a block stages its 128 records through shared memory with 128-bit loads so that every HBM
 //    transaction is a fully used 128 B line, and stages the 36-double tangent the same way on the way out.
 // K2 (SVC): one warp per element, support-vector table resident in shared memory (SoA), dynamic element queue.
+#include <algorithm>
+
+#include "hill_fast.cuh"
 #include "plf_device.cuh"
 #include "plf_host.h"
 
@@ -29,135 +32,203 @@ __device__ __forceinline__ void expand_sym(const double *gs, double *out, int st
 }
 
 // ------------------------------------------------------------------------------------------------------------
-// K1: thread-per-element return mapping with shared-memory staged AoS I/O.
-//   index == nullptr : elements [0, n) in order (coalesced staging)
-//   index != nullptr : compacted pass over the elements listed in index[0..n) (gathered I/O)
-//   MODE 1           : 50-sub-step elements are appended to worklist instead of being processed
+// K1: thread-per-element return mapping.
+//   response_passA_kernel  : staged AoS I/O; elastic + single-step elements finish, 50-sub-step elements are
+//                            appended (warp-aggregated) to the work list
+//   response_passB_kernel  : persistent; runs the 50 sub-steps for the listed elements (gathered I/O); reads the
+//                            list length from device memory, so no host round trip sits between A and B
+//   response_generic_kernel: the unsplit reference formulation (response_core), "compact = 0"
 // ------------------------------------------------------------------------------------------------------------
-template <int MODE, bool GATHER>
-__global__ void __launch_bounds__(RB) response_hill_kernel(int64_t n, const int32_t *__restrict__ mat_id,
-                                                           const double *__restrict__ sig, const double *__restrict__ epl,
-                                                           const double *__restrict__ deps, double *__restrict__ fy,
-                                                           double *__restrict__ sig_out, double *__restrict__ depl_out,
-                                                           double *__restrict__ ctan, int32_t *__restrict__ nsteps,
-                                                           const int32_t *__restrict__ index, int32_t *__restrict__ worklist,
-                                                           unsigned int *__restrict__ work_count)
+__device__ __forceinline__ void stage_in(const double *__restrict__ sig, const double *__restrict__ epl,
+                                         const double *__restrict__ deps, int64_t base, int cnt, double *s_sig, double *s_epl,
+                                         double *s_dep, double *s, double *ep, double *de)
+{
+    const int tid = threadIdx.x;
+    // coalesced 128-bit loads: cnt*3 double2 per array
+    const double2 *g0 = reinterpret_cast<const double2 *>(sig + base * 6);
+    const double2 *g1 = reinterpret_cast<const double2 *>(epl + base * 6);
+    const double2 *g2 = reinterpret_cast<const double2 *>(deps + base * 6);
+    for (int i = tid; i < cnt * 3; i += RB) {
+        reinterpret_cast<double2 *>(s_sig)[i] = __ldg(g0 + i);
+        reinterpret_cast<double2 *>(s_epl)[i] = __ldg(g1 + i);
+        reinterpret_cast<double2 *>(s_dep)[i] = __ldg(g2 + i);
+    }
+    __syncthreads();
+    if (tid < cnt) {
+#pragma unroll
+        for (int k = 0; k < 3; k++) {
+            double2 a = reinterpret_cast<double2 *>(s_sig)[3 * tid + k];
+            double2 b = reinterpret_cast<double2 *>(s_epl)[3 * tid + k];
+            double2 c = reinterpret_cast<double2 *>(s_dep)[3 * tid + k];
+            s[2 * k] = a.x; s[2 * k + 1] = a.y;
+            ep[2 * k] = b.x; ep[2 * k + 1] = b.y;
+            de[2 * k] = c.x; de[2 * k + 1] = c.y;
+        }
+    }
+}
+
+__device__ __forceinline__ void stage_out(int64_t base, int cnt, const double *s_sig, const double *s_epl, const double *s_ct,
+                                          const unsigned char *s_done, double *__restrict__ sig_out,
+                                          double *__restrict__ depl_out, double *__restrict__ ctan)
+{
+    const int tid = threadIdx.x;
+    // coalesced 128-bit stores of the staged records (skipping deferred / foreign elements)
+    for (int i = tid; i < cnt * 3; i += RB) {
+        int el = i / 3;
+        if (!s_done[el]) continue;
+        if (sig_out) reinterpret_cast<double2 *>(sig_out + base * 6)[i] = reinterpret_cast<const double2 *>(s_sig)[i];
+        if (depl_out) reinterpret_cast<double2 *>(depl_out + base * 6)[i] = reinterpret_cast<const double2 *>(s_epl)[i];
+    }
+    if (ctan) {
+        double2 *g = reinterpret_cast<double2 *>(ctan + base * 36);
+        for (int i = tid; i < cnt * 18; i += RB) {
+            int el = i / 18, k2 = i - el * 18;
+            if (!s_done[el]) continue;
+            const double *p = s_ct + CT_STRIDE * el + 2 * k2;
+            g[i] = make_double2(p[0], p[1]);
+        }
+    }
+}
+
+__global__ void __launch_bounds__(RB) response_passA_kernel(int64_t n, const int32_t *__restrict__ mat_id,
+                                                            const double *__restrict__ sig, const double *__restrict__ epl,
+                                                            const double *__restrict__ deps, double *__restrict__ fy,
+                                                            double *__restrict__ sig_out, double *__restrict__ depl_out,
+                                                            double *__restrict__ ctan, int32_t *__restrict__ nsteps,
+                                                            int32_t *__restrict__ worklist, unsigned int *__restrict__ work_count)
 {
     extern __shared__ double smem[];
-    double *s_sig = smem;               // RB*6
-    double *s_epl = smem + RB * 6;      // RB*6
-    double *s_dep = smem + 2 * RB * 6;  // RB*6
-    double *s_ct = smem + 3 * RB * 6;   // RB*CT_STRIDE
+    double *s_sig = smem, *s_epl = smem + RB * 6, *s_dep = smem + 2 * RB * 6, *s_ct = smem + 3 * RB * 6;
     __shared__ unsigned char s_done[RB];
-
     const int tid = threadIdx.x;
     const int64_t base = (int64_t)blockIdx.x * RB;
     const int cnt = (int)min((int64_t)RB, n - base);
-
     double s[6], ep[6], de[6];
-    int64_t e = -1;
-    if (!GATHER) {
-        // coalesced 128-bit loads: cnt*3 double2 per array
-        const double2 *g0 = reinterpret_cast<const double2 *>(sig + base * 6);
-        const double2 *g1 = reinterpret_cast<const double2 *>(epl + base * 6);
-        const double2 *g2 = reinterpret_cast<const double2 *>(deps + base * 6);
-        for (int i = tid; i < cnt * 3; i += RB) {
-            reinterpret_cast<double2 *>(s_sig)[i] = __ldg(g0 + i);
-            reinterpret_cast<double2 *>(s_epl)[i] = __ldg(g1 + i);
-            reinterpret_cast<double2 *>(s_dep)[i] = __ldg(g2 + i);
-        }
-        __syncthreads();
-        if (tid < cnt) {
-            e = base + tid;
+    stage_in(sig, epl, deps, base, cnt, s_sig, s_epl, s_dep, s, ep, de);
+    bool done = false, defer = false;
+    const int64_t e = base + tid;
+    if (tid < cnt) {
+        const DevMat &m = c_mat[mat_id ? mat_id[e] : 0];
+        if (m.kind == PLF_MAT_ELASTIC || m.kind == PLF_MAT_HILL) {
+            double dp[6], ca[6], tc = 1., tw = 0., fyv = 0.;
+            int br = 0;
+            if (m.kind == PLF_MAT_ELASTIC) {
+                // Model.solve never calls response for elastic materials (model.py:1341); elastic update for completeness
+                double t[6];
+                cv_mul(m, de, t);
 #pragma unroll
-            for (int k = 0; k < 3; k++) {
-                double2 a = reinterpret_cast<double2 *>(s_sig)[3 * tid + k];
-                double2 b = reinterpret_cast<double2 *>(s_epl)[3 * tid + k];
-                double2 c = reinterpret_cast<double2 *>(s_dep)[3 * tid + k];
-                s[2 * k] = a.x; s[2 * k + 1] = a.y;
-                ep[2 * k] = b.x; ep[2 * k + 1] = b.y;
-                de[2 * k] = c.x; de[2 * k + 1] = c.y;
+                for (int k = 0; k < 6; k++) { s[k] += t[k]; dp[k] = 0.; ca[k] = 0.; }
+            } else {
+                br = hill_passA(m, s, ep, de, dp, ca, tc, tw, fyv);
             }
-        }
-    } else {
-        if (tid < cnt) {
-            e = index[base + tid];
+            if (br < 0) {
+                defer = true;
+            } else {
+                done = true;
+                if (fy) fy[e] = fyv;
+                if (nsteps) nsteps[e] = 0;
 #pragma unroll
-            for (int k = 0; k < 3; k++) {
-                double2 a = __ldg(reinterpret_cast<const double2 *>(sig + e * 6) + k);
-                double2 b = __ldg(reinterpret_cast<const double2 *>(epl + e * 6) + k);
-                double2 c = __ldg(reinterpret_cast<const double2 *>(deps + e * 6) + k);
-                s[2 * k] = a.x; s[2 * k + 1] = a.y;
-                ep[2 * k] = b.x; ep[2 * k + 1] = b.y;
-                de[2 * k] = c.x; de[2 * k + 1] = c.y;
+                for (int k = 0; k < 6; k++) { s_sig[6 * tid + k] = s[k]; s_epl[6 * tid + k] = dp[k]; }
+                double *o = s_ct + CT_STRIDE * tid;
+#pragma unroll
+                for (int i = 0; i < 6; i++) {
+                    const double wi = ca[i] * tw;
+#pragma unroll
+                    for (int j = 0; j < 6; j++) o[6 * i + j] = m.CV[6 * i + j] * tc - wi * ca[j];
+                }
             }
         }
     }
+    warp_append(defer, (int32_t)e, worklist, work_count);
+    s_done[tid] = done;
+    __syncthreads();
+    stage_out(base, cnt, s_sig, s_epl, s_ct, s_done, sig_out, depl_out, ctan);
+}
 
-    bool done = false, defer = false;
-    if (e >= 0) {
-        const int mid = mat_id ? mat_id[e] : 0;
-        const DevMat &m = c_mat[mid];
-        double dp[6], gs[21], fyv = 0.;
-        int ns = 0, br = 0;
-        if (m.kind == PLF_MAT_ELASTIC) {
-            // Model.solve never calls response for elastic materials (model.py:1341); elastic update for completeness
-            double t[6];
-            matvec6(m.CV, de, t);
+__global__ void __launch_bounds__(RB) response_passB_kernel(const int32_t *__restrict__ mat_id, const double *__restrict__ sig,
+                                                            const double *__restrict__ epl, const double *__restrict__ deps,
+                                                            double *__restrict__ fy, double *__restrict__ sig_out,
+                                                            double *__restrict__ depl_out, double *__restrict__ ctan,
+                                                            int32_t *__restrict__ nsteps, const int32_t *__restrict__ worklist,
+                                                            const unsigned int *__restrict__ work_count)
+{
+    const unsigned int n = *work_count;
+    for (unsigned int t = blockIdx.x * RB + threadIdx.x; t < n; t += gridDim.x * RB) {
+        const int64_t e = worklist[t];
+        const DevMat &m = c_mat[mat_id ? mat_id[e] : 0];
+        double s[6], ep[6], de[6], dp[6], gs[21], fyv;
 #pragma unroll
-            for (int k = 0; k < 6; k++) { s[k] += t[k]; dp[k] = 0.; }
+        for (int k = 0; k < 3; k++) {
+            double2 a = __ldg(reinterpret_cast<const double2 *>(sig + e * 6) + k);
+            double2 b = __ldg(reinterpret_cast<const double2 *>(epl + e * 6) + k);
+            double2 c = __ldg(reinterpret_cast<const double2 *>(deps + e * 6) + k);
+            s[2 * k] = a.x; s[2 * k + 1] = a.y;
+            ep[2 * k] = b.x; ep[2 * k + 1] = b.y;
+            de[2 * k] = c.x; de[2 * k + 1] = c.y;
+        }
+        hill_passB(m, s, ep, de, dp, gs, fyv);
+        if (fy) fy[e] = fyv;
+        if (nsteps) nsteps[e] = PLF_MAXIT - 1;
+        if (sig_out)
+#pragma unroll
+            for (int k = 0; k < 3; k++) reinterpret_cast<double2 *>(sig_out + e * 6)[k] = make_double2(s[2 * k], s[2 * k + 1]);
+        if (depl_out)
+#pragma unroll
+            for (int k = 0; k < 3; k++) reinterpret_cast<double2 *>(depl_out + e * 6)[k] = make_double2(dp[2 * k], dp[2 * k + 1]);
+        if (ctan)
 #pragma unroll
             for (int i = 0; i < 6; i++)
 #pragma unroll
-                for (int j = i; j < 6; j++) gs[sym_idx(i, j)] = m.CV[6 * i + j];
-        } else if (m.kind == PLF_MAT_HILL) {
-            HillModel ym(m);
-            br = response_core<MODE>(ym, m, s, ep, de, dp, gs, fyv, ns);
-        } else {
-            br = -2;   // not this kernel's material family
-        }
-        if (br == -1) {
-            defer = true;
-        } else if (br != -2) {
+                for (int j = 0; j < 6; j += 2)
+                    reinterpret_cast<double2 *>(ctan + e * 36)[(6 * i + j) >> 1] = make_double2(gs[sym_idx(i, j)], gs[sym_idx(i, j + 1)]);
+    }
+}
+
+__global__ void __launch_bounds__(RB) response_generic_kernel(int64_t n, const int32_t *__restrict__ mat_id,
+                                                              const double *__restrict__ sig, const double *__restrict__ epl,
+                                                              const double *__restrict__ deps, double *__restrict__ fy,
+                                                              double *__restrict__ sig_out, double *__restrict__ depl_out,
+                                                              double *__restrict__ ctan, int32_t *__restrict__ nsteps)
+{
+    extern __shared__ double smem[];
+    double *s_sig = smem, *s_epl = smem + RB * 6, *s_dep = smem + 2 * RB * 6, *s_ct = smem + 3 * RB * 6;
+    __shared__ unsigned char s_done[RB];
+    const int tid = threadIdx.x;
+    const int64_t base = (int64_t)blockIdx.x * RB;
+    const int cnt = (int)min((int64_t)RB, n - base);
+    double s[6], ep[6], de[6];
+    stage_in(sig, epl, deps, base, cnt, s_sig, s_epl, s_dep, s, ep, de);
+    bool done = false;
+    const int64_t e = base + tid;
+    if (tid < cnt) {
+        const DevMat &m = c_mat[mat_id ? mat_id[e] : 0];
+        if (m.kind == PLF_MAT_ELASTIC || m.kind == PLF_MAT_HILL) {
+            double dp[6], gs[21], fyv = 0.;
+            int ns = 0;
+            if (m.kind == PLF_MAT_ELASTIC) {
+                double t[6];
+                matvec6(m.CV, de, t);
+#pragma unroll
+                for (int k = 0; k < 6; k++) { s[k] += t[k]; dp[k] = 0.; }
+#pragma unroll
+                for (int i = 0; i < 6; i++)
+#pragma unroll
+                    for (int j = i; j < 6; j++) gs[sym_idx(i, j)] = m.CV[6 * i + j];
+            } else {
+                HillModel ym(m);
+                response_core<0>(ym, m, s, ep, de, dp, gs, fyv, ns);
+            }
             done = true;
             if (fy) fy[e] = fyv;
             if (nsteps) nsteps[e] = ns;
-            if (!GATHER) {
 #pragma unroll
-                for (int k = 0; k < 6; k++) { s_sig[6 * tid + k] = s[k]; s_epl[6 * tid + k] = dp[k]; }
-                expand_sym(gs, s_ct + CT_STRIDE * tid, 1);
-            } else {
-                if (sig_out)
-#pragma unroll
-                    for (int k = 0; k < 6; k++) sig_out[e * 6 + k] = s[k];
-                if (depl_out)
-#pragma unroll
-                    for (int k = 0; k < 6; k++) depl_out[e * 6 + k] = dp[k];
-                if (ctan) expand_sym(gs, ctan + e * 36, 1);
-            }
+            for (int k = 0; k < 6; k++) { s_sig[6 * tid + k] = s[k]; s_epl[6 * tid + k] = dp[k]; }
+            expand_sym(gs, s_ct + CT_STRIDE * tid, 1);
         }
     }
-    if (MODE == 1) warp_append(defer, (int32_t)e, worklist, work_count);
-    if (!GATHER) {
-        s_done[tid] = done;
-        __syncthreads();
-        // coalesced 128-bit stores of the staged records (skipping deferred / foreign elements)
-        for (int i = tid; i < cnt * 3; i += RB) {
-            int el = i / 3;
-            if (!s_done[el]) continue;
-            if (sig_out) reinterpret_cast<double2 *>(sig_out + base * 6)[i] = reinterpret_cast<double2 *>(s_sig)[i];
-            if (depl_out) reinterpret_cast<double2 *>(depl_out + base * 6)[i] = reinterpret_cast<double2 *>(s_epl)[i];
-        }
-        if (ctan) {
-            double2 *g = reinterpret_cast<double2 *>(ctan + base * 36);
-            for (int i = tid; i < cnt * 18; i += RB) {
-                int el = i / 18, k2 = i - el * 18;
-                if (!s_done[el]) continue;
-                const double *p = s_ct + CT_STRIDE * el + 2 * k2;
-                g[i] = make_double2(p[0], p[1]);
-            }
-        }
-    }
+    s_done[tid] = done;
+    __syncthreads();
+    stage_out(base, cnt, s_sig, s_epl, s_ct, s_done, sig_out, depl_out, ctan);
 }
 
 // ------------------------------------------------------------------------------------------------------------
@@ -325,11 +396,9 @@ static size_t svc_smem(const DevMat &m) { return sizeof(double) * 7 * (size_t)m.
 cudaError_t response_init()
 {
     cudaError_t e;
-    e = cudaFuncSetAttribute(response_hill_kernel<0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)k1_smem());
+    e = cudaFuncSetAttribute(response_passA_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)k1_smem());
     if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(response_hill_kernel<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)k1_smem());
-    if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(response_hill_kernel<0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)k1_smem());
+    e = cudaFuncSetAttribute(response_generic_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)k1_smem());
     if (e != cudaSuccess) return e;
     e = cudaFuncSetAttribute(response_svc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e != cudaSuccess) return e;
@@ -350,22 +419,14 @@ cudaError_t launch_response(const LaunchCtx &lc, const DevMat *hmats, int nmat, 
     if (any_hill) {
         if (compact && worklist) {
             cudaMemsetAsync(work_count, 0, sizeof(unsigned int), lc.stream);
-            response_hill_kernel<1, false><<<grid, RB, k1_smem(), lc.stream>>>(n, mat_id, sig, epl, deps, fy, sig_out, depl,
-                                                                                ctan, nsteps, nullptr, worklist, work_count);
-            (*launches)++;
-            unsigned int nw = 0;
-            cudaError_t e = cudaMemcpyAsync(&nw, work_count, sizeof nw, cudaMemcpyDeviceToHost, lc.stream);
-            if (e != cudaSuccess) return e;
-            e = cudaStreamSynchronize(lc.stream);
-            if (e != cudaSuccess) return e;
-            if (nw > 0) {
-                response_hill_kernel<0, true><<<(nw + RB - 1) / RB, RB, k1_smem(), lc.stream>>>(
-                    (int64_t)nw, mat_id, sig, epl, deps, fy, sig_out, depl, ctan, nsteps, worklist, nullptr, nullptr);
-                (*launches)++;
-            }
+            response_passA_kernel<<<grid, RB, k1_smem(), lc.stream>>>(n, mat_id, sig, epl, deps, fy, sig_out, depl, ctan, nsteps,
+                                                                      worklist, work_count);
+            int64_t bgrid = std::min<int64_t>((int64_t)lc.sm_count * 8, (int64_t)grid);
+            response_passB_kernel<<<(unsigned)bgrid, RB, 0, lc.stream>>>(mat_id, sig, epl, deps, fy, sig_out, depl, ctan, nsteps,
+                                                                         worklist, work_count);
+            *launches += 2;
         } else {
-            response_hill_kernel<0, false><<<grid, RB, k1_smem(), lc.stream>>>(n, mat_id, sig, epl, deps, fy, sig_out, depl,
-                                                                                ctan, nsteps, nullptr, nullptr, nullptr);
+            response_generic_kernel<<<grid, RB, k1_smem(), lc.stream>>>(n, mat_id, sig, epl, deps, fy, sig_out, depl, ctan, nsteps);
             (*launches)++;
         }
     }
