@@ -356,7 +356,8 @@ extern "C" int plf_sweep(plf_ctx *ctx, int nit, int32_t *change, int32_t *conv, 
     if (conv) *conv = st->nonconv == 0 ? 1 : 0;
     if (max_hh) *max_hh = st->max_hh;
     if (counts) for (int i = 0; i < 4; i++) counts[i] = (int64_t)st->counts[i];
-    if (st->change) ctx->K_ready = false;
+    // K_ready stays set: the CSR memory still holds the stiffness the current increment was solved with, which is
+    // what plf_commit must use for f += K du (model.py:1384 uses the K assembled before the last sweep).
     return PLF_OK;
 }
 

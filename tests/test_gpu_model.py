@@ -1,0 +1,270 @@
+"""GPU parity of the device-resident Model.solve against end-to-end solutions of the unmodified reference
+(tests/golden/solve_*.npz, svc_shear.npz) and against the reference's own known-answer tests
+(/root/reference/tests/test_basic.py, test_ml.py -- golden scalars quoted with their line numbers).
+
+Tolerances: linear models: u within 1e-9 relative (the reference solves with dense LU, this path with CG);
+plastic models: stress / plastic strain / PEEQ within 1e-6 relative (BASELINE.json north_star), same number of
+increments and of inner passes."""
+import numpy as np
+import pytest
+
+import pylabfea_b200 as FE
+from helpers import relmax
+
+pytestmark = pytest.mark.gpu
+
+
+def make_material(name):
+    m = FE.Material(name=name)
+    if name == 'j2':
+        m.elasticity(E=200.e3, nu=0.3)
+        m.plasticity(sy=150., khard=500., sdim=6)
+    elif name == 'hill':
+        m.elasticity(E=200.e3, nu=0.3)
+        m.plasticity(sy=150., hill=[0.7, 1., 1.4, 1., 1.2, 0.8], khard=100., sdim=6)
+    return m
+
+
+def cantilever(N=10):
+    mat = FE.Material()
+    mat.elasticity(E=200.e3, nu=0.3)
+    fe = FE.Model(dim=2, planestress=True)
+    fe.geom([10.], LY=1.)
+    fe.assign([mat])
+    fe.bcleft(0., 'disp', 'x')
+    fe.bcleft(0., 'disp', 'y')
+    fe.bcbot(0., 'force', 'y')
+    fe.bctop(0., 'force', 'y')
+    fe.bcright(-10., 'force', 'y')
+    fe.mesh(NX=N, NY=N)
+    return fe
+
+
+def laminate():
+    fe = FE.Model(dim=2, planestress=True)
+    fe.geom([2, 1, 2, 1, 2], LY=4.)
+    mat1 = FE.Material()
+    mat1.elasticity(E=100.e3, nu=0.35)
+    mat2 = FE.Material()
+    mat2.elasticity(E=300.e3, nu=0.3)
+    fe.assign([mat1, mat2, mat1, mat2, mat1])
+    fe.bcleft(0.)
+    fe.bcbot(0.)
+    fe.bcright(0., 'force')
+    fe.bctop(0.1 * fe.leny, 'disp')
+    fe.mesh(NX=16, NY=4)
+    return fe, mat1, mat2
+
+
+def inclusion(N=18, plastic=False, eps_tot=0.01):
+    n1 = int(N / 3)
+    el = np.ones((N, N))
+    el[n1:2 * n1, n1:2 * n1] = 2
+    mat1 = FE.Material(num=1)
+    mat1.elasticity(E=100.e3, nu=0.27)
+    if plastic:
+        mat1.plasticity(sy=150., khard=500., sdim=6)
+    mat2 = FE.Material(num=2)
+    mat2.elasticity(E=3.e3, nu=0.3)
+    fe = FE.Model(dim=2, planestress=False)
+    fe.geom(sect=2, LX=4., LY=4.)
+    fe.assign([mat1, mat2])
+    fe.bcbot(0.)
+    fe.bcright(0., 'force')
+    fe.bcleft(0., 'force')
+    fe.bctop(eps_tot * fe.leny, 'disp')
+    fe.mesh(elmts=el, NX=N, NY=N)
+    hh = [no in fe.nobot for no in fe.noleft]
+    noc = np.nonzero(hh)[0]
+    fe.bcnode(noc, 0., 'disp', 'x')
+    return fe
+
+
+def uniax(matname, N=4, planestress=False, eps=0.01):
+    mat = make_material(matname)
+    fe = FE.Model(dim=2, planestress=planestress)
+    fe.geom([4.], LY=4.)
+    fe.assign([mat])
+    fe.bcleft(0.)
+    fe.bcbot(0.)
+    fe.bcright(0., 'force')
+    fe.bctop(eps * fe.leny, 'disp')
+    fe.mesh(NX=N, NY=N)
+    return fe
+
+
+def compare_solution(fe, g, tol_u, tol_state):
+    assert np.array_equal(fe.npos, g['npos'])
+    assert relmax(fe.u, g['u']) < tol_u
+    assert np.max(np.abs(fe.f - g['f'])) < tol_u * max(np.max(np.abs(g['f'])), np.max(np.abs(g['sig'])))
+    sig = np.array([el.sig for el in fe.element])
+    assert relmax(sig, g['sig']) < tol_state
+    assert relmax(fe.element[0].eps, g['eps'][0]) < tol_state
+    assert relmax(np.array([el.eps for el in fe.element]), g['eps']) < tol_state
+    epl = np.array([el.epl for el in fe.element])
+    assert np.max(np.abs(epl - g['epl'])) <= tol_state * max(np.max(np.abs(g['epl'])), 1e-12)
+    assert fe.sgl.shape == g['sgl'].shape
+    assert relmax(fe.sgl, g['sgl']) < tol_state and relmax(fe.egl, g['egl']) < tol_state
+    assert np.max(np.abs(fe.epgl - g['epgl'])) <= tol_state * max(np.max(np.abs(g['epgl'])), 1e-12)
+    bc = np.array([fe.glob[k] for k in ('ebc1', 'sbc1', 'ebc21', 'sbc21', 'ebc2', 'sbc2', 'ebc12', 'sbc12')])
+    assert np.max(np.abs(bc - g['glob_bc'])) < tol_state * np.max(np.abs(g['glob_bc']))
+
+
+def test_linear_cantilever_config1(golden):
+    """BASELINE config 1: 10x10 linear-elastic cantilever: setupK bit-exact, u from CG vs the reference's dense LU."""
+    g = golden('solve_cantilever10')
+    fe = cantilever(10)
+    K = fe.setupK()
+    gk = golden('kmat_cantilever10')
+    Kref = np.zeros((fe.Ndof, fe.Ndof))
+    Kref[gk['K_row'], gk['K_col']] = gk['K_val']
+    assert np.array_equal(K.toarray(), Kref)
+    fe.solve()
+    assert fe.nsteps == 1 and fe.niter == [-1]
+    compare_solution(fe, g, 1e-9, 1e-9)
+    assert abs(fe.u[2 * fe.noright[-1] + 1] - (-0.14455)) < 1e-4   # tip deflection
+
+
+def test_linear_laminate_voigt_average(golden):
+    """/root/reference/tests/test_basic.py:12-16 (test_model): effective stiffness = Voigt average."""
+    g = golden('solve_laminate16x4')
+    fe, mat1, mat2 = laminate()
+    fe.solve()
+    fe.calc_global()
+    compare_solution(fe, g, 1e-9, 1e-9)
+    mod_stiff = fe.glob['sig'][1] / fe.glob['eps'][1]
+    voigt_stiff = 6. / 8. * mat1.E + 2. / 8. * mat2.E
+    assert abs(voigt_stiff - mod_stiff) < 1e-5
+
+
+def test_linear_inclusion_bcnode(golden):
+    """/root/reference/tests/test_basic.py:42-80 (test_bcnode): 18x18 plane strain, two materials, corner pin."""
+    g = golden('solve_inclusion18_elastic')
+    fe = inclusion(18)
+    fe.solve()
+    compare_solution(fe, g, 1e-9, 1e-9)
+    NY = 18
+    assert abs(fe.u[684] + 9.730777232237817e-3) < 1e-5
+    assert abs(fe.element[0].sig[5] - 2.2990816342732256) < 1e-5
+    assert abs(fe.element[5 * NY + 7].sig[0] - 45.68020736256676) < 1e-5
+    assert abs(fe.element[6 * NY + 7].sig[1] - 69.16252458086865) < 1e-5
+
+
+@pytest.mark.parametrize('compact', [1, 0])
+def test_plastic_j2_uniaxial(golden, compact):
+    """4x4 plane strain, J2 with hardening, 20 increments: same increments, same inner passes, state to 1e-6."""
+    g = golden('solve_j2_4x4')
+    fe = uniax('j2', 4)
+    fe._dev().set_option('compact', compact)
+    fe.solve(min_step=20)
+    assert fe.nsteps == int(g['nsteps'])
+    assert list(fe.niter) == list(g['niter'])
+    assert list(fe.co_nconv) == list(g['co_nconv'])
+    compare_solution(fe, g, 1e-6, 1e-6)
+    assert relmax(np.array([el.elstiff for el in fe.element]), g['elstiff']) < 1e-6
+
+
+def test_plastic_hill_plane_stress(golden):
+    g = golden('solve_hill_4x4_ps')
+    fe = uniax('hill', 4, planestress=True)
+    fe.solve(min_step=10)
+    assert fe.nsteps == int(g['nsteps']) and list(fe.niter) == list(g['niter'])
+    compare_solution(fe, g, 1e-6, 1e-6)
+
+
+def test_plastic_inclusion_nonuniform(golden):
+    """6x6 inclusion (examples/inclusion.py pattern), J2 matrix + soft elastic inclusion: non-uniform field, inner
+    loop hits its 16-pass cap in several increments."""
+    g = golden('solve_j2_inclusion6')
+    fe = inclusion(6, plastic=True)
+    fe.solve(min_step=8)
+    assert fe.nsteps == int(g['nsteps']) and list(fe.niter) == list(g['niter'])
+    compare_solution(fe, g, 1e-6, 1e-6)
+
+
+def test_calc_properties_workhard_golden():
+    """/root/reference/tests/test_basic.py:28-33 (test_workhard): J2 sdim=6, sy=150, khard=2000, eps=0.1."""
+    mat3 = FE.Material()
+    mat3.elasticity(E=300.e3, nu=0.3)
+    mat3.plasticity(sy=150., khard=2000.)
+    mat3.calc_properties(eps=0.1, sigeps=True)
+    assert abs(mat3.propJ2['stx']['seq'][-1] - 347.68211920529546) < 1e-5
+    assert abs(mat3.propJ2['sty']['peeq'][-1] - 0.09883666666666659) < 1e-5
+    assert abs(mat3.sigeps['et2']['sig'][-1][0] - 307.1334214002634) < 1e-5
+    assert abs(mat3.sigeps['ect']['sig'][-1][0] + 192.15895530336059) < 1e-5
+
+
+def test_calc_properties_hill6p_golden():
+    """/root/reference/tests/test_basic.py:35-40 (test_hill_6p)."""
+    mat4 = FE.Material()
+    mat4.elasticity(E=200.e3, nu=0.3)
+    mat4.plasticity(sy=100., hill=[0.7, 1., 1.4, 1., 1.2, 0.8], khard=100., sdim=6)
+    mat4.calc_properties(eps=0.05, sigeps=True)
+    assert abs(mat4.propJ2['stx']['peeq'][-1] - 0.05039661) < 1e-5
+    assert abs(mat4.propJ2['sty']['seq'][-1] - 114.28035811) < 1e-5
+    assert abs(mat4.sigeps['et2']['sig'][-1][1] - 102.534840) < 1e-5
+    assert abs(mat4.sigeps['ect']['sig'][-1][0] + 54.6031702) < 1e-5
+
+
+def test_material_elastic_constants():
+    """/root/reference/tests/test_basic.py:6-10 (test_material)."""
+    mat1 = FE.Material()
+    mat1.elasticity(E=100.e3, nu=0.35)
+    assert abs(mat1.C11 - 160493.8271604938) < 1e-5
+    assert abs(mat1.C12 - 86419.75308641973) < 1e-5
+    assert abs(mat1.C44 - 37037.03703703704) < 1e-5
+
+
+def test_svc_simple_shear_in_fe(golden):
+    """/root/reference/tests/test_ml.py:170-201 (test_ml_shear): SVC yield function inside the FE loop, 6x3 plane
+    stress simple shear.  The SVC is the one the reference trained (fixture svc_shear.npz)."""
+    g = golden('svc_shear')
+    m = FE.Material('Hill-ML')
+    m.elasticity(CV=g['CV'])
+    m.plasticity(sy=float(g['sy']), sdim=6)
+    m.set_svc(g['sv'], g['dual'], float(g['rho']), float(g['gamma']), scale_seq=float(g['scale_seq']), dev_only=False)
+    fem = FE.Model(dim=2, planestress=True)
+    fem.geom([2], LY=2.)
+    fem.assign([m])
+    fem.bcbot(0., bctype='disp', bcdir='y')
+    fem.bcbot(0., bctype='disp', bcdir='x')
+    fem.bcleft(0., bctype='force')
+    fem.bcright(0., bctype='force')
+    fem.bctop(0.006 * fem.leny, bctype='disp', bcdir='x')
+    fem.bctop(0., bctype='disp', bcdir='y')
+    fem.mesh(NX=6, NY=3)
+    fem.solve()
+    fem.calc_global()
+    # the reference test's own tolerances (test_ml.py:199-201)
+    assert abs(fem.glob['sig'][5] - 77.53778881971623) < 6e-4
+    assert abs(fem.element[3].epl[5] - 0.003942707316047761) < 1e-7
+    assert abs(fem.element[3].sig[1] - 43.9060552472426) < 5e-3
+    # and the full state of the reference run in this container
+    assert fem.nsteps == int(g['nsteps']) and list(fem.niter) == list(g['niter'])
+    assert relmax(np.array([el.sig for el in fem.element]), g['sig']) < 1e-5
+    assert relmax(fem.u, g['u']) < 1e-5
+
+
+def test_solve_before_mesh_raises():
+    fe = FE.Model(dim=2)
+    with pytest.raises(AttributeError):      # model.py:1024-1025
+        fe.solve()
+    with pytest.raises(TypeError):           # model.py:644
+        fe.bcright(0., 'spring')
+    with pytest.raises(ValueError):          # model.py:609-610
+        fe.bcleft(1., 'force')
+
+
+def test_resolve_continues_from_previous_state():
+    """Model.solve is re-entrant (model.py:1235-1239): a second solve with new BCs continues from u, bcr_mem/bct_mem."""
+    fe = uniax('j2', 4, eps=0.002)
+    fe.solve(min_step=4)
+    u1 = fe.u.copy()
+    fe.bctop(0.004 * fe.leny, 'disp')
+    fe.solve(min_step=4)
+    ref = uniax('j2', 4, eps=0.004)
+    ref.solve(min_step=8)
+    assert np.max(np.abs(fe.u)) > np.max(np.abs(u1))
+    assert abs(fe.glob['eps'][1] - 0.004) < 1e-9
+    # path dependence is weak for proportional loading: the two histories end at the same stress to ~1e-3
+    assert relmax(fe.glob['sig'], ref.glob['sig']) < 5e-3
