@@ -566,7 +566,8 @@ __global__ void __launch_bounds__(256) spmv_kernel(int64_t nrows, const int32_t 
 
 // CG scalars in device memory
 struct CgScalars {
-    double pq, rz, rz_new, rr, bb, alpha, beta;
+    double pq, rz, rz_new, rr;
+    double target, active, iters;   // target = (rtol |b|)^2: once rr <= target the iteration freezes; iters counts real steps
 };
 
 // x += alpha p ; r -= alpha q ; z = r / diag ; partial sums of r.z and r.r   (alpha = rz / pq computed by every thread)
@@ -576,7 +577,8 @@ __global__ void __launch_bounds__(256) cg_update_kernel(int64_t n, double *__res
                                                         const unsigned char *__restrict__ fixed, CgScalars *sc, double *partial,
                                                         unsigned int *counter)
 {
-    const double alpha = sc->rz / sc->pq;
+    // converged (or exactly solved: small systems reach r = 0 in a few steps) -> no further update, no 0/0
+    const double alpha = (sc->rr <= sc->target || sc->pq == 0.) ? 0. : sc->rz / sc->pq;
     double v[2] = {0., 0.};
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
         if (fixed[i]) continue;
@@ -595,12 +597,17 @@ __global__ void __launch_bounds__(256) cg_update_kernel(int64_t n, double *__res
 __global__ void __launch_bounds__(256) cg_p_kernel(int64_t n, double *__restrict__ p, const double *__restrict__ z,
                                                    const CgScalars *sc)
 {
-    const double beta = sc->rz_new / sc->rz;
+    const double beta = (sc->rr <= sc->target || sc->rz == 0.) ? 0. : sc->rz_new / sc->rz;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
         p[i] = z[i] + beta * p[i];
 }
 
-__global__ void cg_swap_kernel(CgScalars *sc) { sc->rz = sc->rz_new; }
+__global__ void cg_swap_kernel(CgScalars *sc)
+{
+    if (sc->active != 0.) sc->iters += 1.;            // the step just finished was a real one
+    sc->active = (sc->rr > sc->target) ? 1. : 0.;     // NaN -> inactive as well
+    sc->rz = sc->rz_new;
+}
 
 // init: r = b (masked), z = r / diag, p = z, x = 0 ; partial sums r.z and r.r
 __global__ void __launch_bounds__(256) cg_init_kernel(int64_t n, const double *__restrict__ b, double *__restrict__ x,
@@ -736,6 +743,8 @@ cudaError_t launch_cg(const LaunchCtx &lc, int64_t n, const int32_t *rowptr, con
     *relres = 0.;
     if (bb == 0.) return cudaSuccess;
     const double target = rtol * rtol * bb;
+    const double init[3] = {target, 1., 0.};   // target, active, iters
+    if ((e = cudaMemcpyAsync(&sc->target, init, sizeof init, cudaMemcpyHostToDevice, lc.stream)) != cudaSuccess) return e;
     int it = 0;
     while (it < max_iter) {
         int chunk = std::min(check_every, max_iter - it);
@@ -752,7 +761,7 @@ cudaError_t launch_cg(const LaunchCtx &lc, int64_t n, const int32_t *rowptr, con
         *relres = sqrt(hs->rr / bb);
         if (!(hs->rr > target)) break;   // also stops on NaN
     }
-    *iters = it;
+    *iters = (int)hs->iters;
     return cudaGetLastError();
 }
 

@@ -451,7 +451,8 @@ extern "C" int plf_solve_linear(plf_ctx *ctx, const uint8_t *fixed, const double
     CK(cudaStreamSynchronize(ctx->stream));
     if (iters) *iters = it;
     if (relres) *relres = rr;
-    if (!(rr <= rtol) && it >= max_iter)
-        return fail(ctx, PLF_ENOCONV, "plf_solve_linear: CG stopped at max_iter with relative residual " + std::to_string(rr));
+    if (!(rr <= rtol))   // also catches NaN (break-down on an indefinite tangent)
+        return fail(ctx, PLF_ENOCONV, "plf_solve_linear: CG stopped after " + std::to_string(it) +
+                                          " iterations with relative residual " + std::to_string(rr));
     return PLF_OK;
 }
