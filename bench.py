@@ -217,6 +217,8 @@ def main():
     ap.add_argument('--no-e2e', action='store_true')
     ap.add_argument('--no-cpu', action='store_true')
     ap.add_argument('--compact', type=int, default=1)
+    ap.add_argument('--passb-wsmem', type=int, default=2)
+    ap.add_argument('--assembly-tiled', type=int, default=2)
     args = ap.parse_args()
 
     rank = int(os.environ.get('RANK', '0'))
@@ -248,6 +250,8 @@ def main():
     from pylabfea_b200 import _lib
     ctx = _lib.Context(local)
     ctx.set_option('compact', args.compact)
+    ctx.set_option('passb_wsmem', args.passb_wsmem)
+    ctx.set_option('assembly_tiled', args.assembly_tiled)
     N = args.mesh
     Nel = N * N
     mat, CV = j2_material()

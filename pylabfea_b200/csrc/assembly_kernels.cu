@@ -142,10 +142,188 @@ __global__ void __launch_bounds__(128) assemble_rows_kernel(int NX, int NY, cons
 #pragma unroll
         for (int sk = 0; sk < 3; sk++) {
             if (k + sk - 1 < 0 || k + sk - 1 > NY) continue;
-            val[pos] = acc[3 * sj + sk][0];
-            val[pos + 1] = acc[3 * sj + sk][1];
+            // entries come in (ux, uy) pairs and row starts are even: one 128-bit store per pair
+            *reinterpret_cast<double2 *>(val + pos) = make_double2(acc[3 * sj + sk][0], acc[3 * sj + sk][1]);
             pos += 2;
         }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Row-per-thread with staged stores (production).  Same loads and arithmetic as assemble_rows_kernel; a block owns
+// 64 consecutive nodes of one node column, whose 128 CSR rows form one contiguous run of values.  The rows are
+// collected in shared memory (128-bit, conflict-free) and written back with fully coalesced 128-bit stores, so L2
+// receives whole 32 B sectors instead of two partial writes per sector.
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int SN = 64;   // nodes per block
+
+template <bool PS>
+__global__ void __launch_bounds__(2 * SN) assemble_rows_staged_kernel(int NX, int NY, const int32_t *__restrict__ elem_desc,
+                                                                      const double *__restrict__ elstiff,
+                                                                      const int32_t *__restrict__ rowptr, double *__restrict__ val)
+{
+    __shared__ double2 s_out[SN * 2 * 9];
+    const int tid = threadIdx.x;
+    const int NnY = NY + 1;
+    const int j = blockIdx.y, k0 = blockIdx.x * SN;
+    const int c = tid & 1, k = k0 + (tid >> 1);
+    const bool active = k <= NY;
+    const int kmax = min(k0 + SN - 1, NY);
+    const int64_t r_first = 2 * ((int64_t)j * NnY + k0);
+    const int64_t r_last = 2 * ((int64_t)j * NnY + kmax) + 1;
+    const int32_t begin = __ldg(rowptr + r_first), end = __ldg(rowptr + r_last + 1);
+
+    if (active) {
+        double acc[9][2];
+#pragma unroll
+        for (int s = 0; s < 9; s++) acc[s][0] = acc[s][1] = 0.;
+#pragma unroll
+        for (int ddj = 0; ddj < 2; ddj++) {
+#pragma unroll
+            for (int ddk = 0; ddk < 2; ddk++) {
+                const int ej = j - 1 + ddj, ek = k - 1 + ddk;   // ascending element index e = ej*NY + ek
+                if (ej < 0 || ej >= NX || ek < 0 || ek >= NY) continue;
+                const int64_t e = (int64_t)ej * NY + ek;
+                const int cls = __ldg(elem_desc + e) >> 16;
+                const int a = 2 * (1 - ddj) + (1 - ddk);
+                double kel[8];
+                kel_row<PS>(c_geom[cls], elstiff + e * 36, a, c, kel);
+#pragma unroll
+                for (int m = 0; m < 4; m++) {
+                    const int sj = ddj + (m >> 1), sk = ddk + (m & 1);
+                    acc[3 * sj + sk][0] = acc[3 * sj + sk][0] + kel[2 * m];
+                    acc[3 * sj + sk][1] = acc[3 * sj + sk][1] + kel[2 * m + 1];
+                }
+            }
+        }
+        const int64_t r = 2 * ((int64_t)j * NnY + k) + c;
+        int pos2 = (__ldg(rowptr + r) - begin) >> 1;
+#pragma unroll
+        for (int sj = 0; sj < 3; sj++) {
+            if (j + sj - 1 < 0 || j + sj - 1 > NX) continue;
+#pragma unroll
+            for (int sk = 0; sk < 3; sk++) {
+                if (k + sk - 1 < 0 || k + sk - 1 > NY) continue;
+                s_out[pos2++] = make_double2(acc[3 * sj + sk][0], acc[3 * sj + sk][1]);
+            }
+        }
+    }
+    __syncthreads();
+    const int n2 = (end - begin) >> 1;
+    double2 *dst = reinterpret_cast<double2 *>(val + begin);
+    for (int i = tid; i < n2; i += 2 * SN) dst[i] = s_out[i];
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Tiled variant (experimental, slower: kept for the record, see profiles/).  The row-per-thread kernel above reads the 288 B AoS tangents and writes its 144 B rows
+// with a stride between lanes, so every warp-level access touches 16-36 cache lines and the L1 wavefront rate
+// (one 128 B line per cycle per SM) becomes the limit (ncu: long_scoreboard + lg_throttle, 42 % of the HBM roofline).
+// Here a block of 256 threads owns a tile of 4 node columns x 32 node rows:
+//   1. the 5 x 33 element tangents around the tile are loaded with coalesced 128-bit loads (each element column of
+//      the tile is one contiguous run in memory) into shared memory, record stride 37 doubles (conflict-free),
+//   2. every thread computes its CSR row exactly as above, reading the tangents from shared memory,
+//   3. the rows are staged in shared memory in CSR order (one contiguous run per node column) and written with
+//      coalesced 128-bit stores.
+// Arithmetic and summation order are unchanged -> CSR(K) stays bit-identical to the reference.
+// ---------------------------------------------------------------------------------------------------------------
+static int g_tiled = 2;   // 0: row per thread, direct stores; 1: shared-memory tile; 2: row per thread, staged stores
+constexpr int TJ = 4, TK = 32;                 // node tile
+constexpr int TEJ = TJ + 1, TEK = TK + 1;      // element tile (one halo column / row on the low side)
+constexpr int ESTRIDE = 37;
+
+template <bool PS>
+__global__ void __launch_bounds__(TJ * TK * 2) assemble_tile_kernel(int NX, int NY, const int32_t *__restrict__ elem_desc,
+                                                                    const double *__restrict__ elstiff,
+                                                                    const int32_t *__restrict__ rowptr, double *__restrict__ val)
+{
+    extern __shared__ double smem[];                       // TEJ*TEK*ESTRIDE doubles, reused for the output staging
+    __shared__ int s_cls[TEJ * TEK];
+    const int tid = threadIdx.x;
+    const int NnY = NY + 1;
+    const int j0 = blockIdx.x * TJ, k0 = blockIdx.y * TK;
+
+    // 1. coalesced load of the element tile
+    for (int cj = 0; cj < TEJ; cj++) {
+        const int ej = j0 - 1 + cj;
+        if (ej < 0 || ej >= NX) continue;
+        const int ek_lo = max(k0 - 1, 0), ek_hi = min(k0 + TK - 1, NY - 1);
+        const int nel = ek_hi - ek_lo + 1;
+        if (nel <= 0) continue;
+        const int64_t e0 = (int64_t)ej * NY + ek_lo;
+        const double2 *src = reinterpret_cast<const double2 *>(elstiff + e0 * 36);
+        const int lbase = cj * TEK + (ek_lo - (k0 - 1));
+        for (int i = tid; i < nel * 18; i += TJ * TK * 2) {
+            const double2 v = __ldg(src + i);
+            const int el = i / 18, w = i - el * 18;
+            double *dst = smem + (lbase + el) * ESTRIDE + 2 * w;
+            dst[0] = v.x;
+            dst[1] = v.y;
+        }
+        for (int i = tid; i < nel; i += TJ * TK * 2) s_cls[lbase + i] = __ldg(elem_desc + e0 + i) >> 16;
+    }
+    __syncthreads();
+
+    // 2. one CSR row per thread
+    const int c = tid & 1, kk = (tid >> 1) & (TK - 1), jj = tid >> 6;
+    const int j = j0 + jj, k = k0 + kk;
+    const bool active = (j <= NX) && (k <= NY);
+    double acc[9][2];
+#pragma unroll
+    for (int s = 0; s < 9; s++) acc[s][0] = acc[s][1] = 0.;
+    if (active) {
+#pragma unroll
+        for (int ddj = 0; ddj < 2; ddj++) {
+#pragma unroll
+            for (int ddk = 0; ddk < 2; ddk++) {
+                const int ej = j - 1 + ddj, ek = k - 1 + ddk;   // ascending element index e = ej*NY + ek
+                if (ej < 0 || ej >= NX || ek < 0 || ek >= NY) continue;
+                const int le = (jj + ddj) * TEK + (kk + ddk);
+                const int a = 2 * (1 - ddj) + (1 - ddk);
+                double kel[8];
+                kel_row<PS>(c_geom[s_cls[le]], smem + le * ESTRIDE, a, c, kel);
+#pragma unroll
+                for (int m = 0; m < 4; m++) {
+                    const int sj = ddj + (m >> 1), sk = ddk + (m & 1);
+                    acc[3 * sj + sk][0] = acc[3 * sj + sk][0] + kel[2 * m];
+                    acc[3 * sj + sk][1] = acc[3 * sj + sk][1] + kel[2 * m + 1];
+                }
+            }
+        }
+    }
+    __syncthreads();   // all reads of the tangent tile are done: reuse the memory for the rows
+
+    // 3. stage the rows in CSR order (per node column: rows 2*(j*NnY + k0) ... are one contiguous run) and store
+    const bool col_ok = (j <= NX);
+    const int kmax = min(k0 + TK - 1, NY);                 // last node row of this tile
+    int32_t col_begin = 0, col_end = 0;
+    if (col_ok) {
+        const int64_t r_first = 2 * ((int64_t)j * NnY + k0);
+        const int64_t r_last = 2 * ((int64_t)j * NnY + kmax) + 1;
+        col_begin = rowptr[r_first];
+        col_end = rowptr[r_last + 1];
+    }
+    double *s_out = smem + jj * (TK * 2 * 18);             // <= 64 rows x 18 entries per node column
+    if (active) {
+        const int64_t r = 2 * ((int64_t)j * NnY + k) + c;
+        int pos = rowptr[r] - col_begin;
+#pragma unroll
+        for (int sj = 0; sj < 3; sj++) {
+            if (j + sj - 1 < 0 || j + sj - 1 > NX) continue;
+#pragma unroll
+            for (int sk = 0; sk < 3; sk++) {
+                if (k + sk - 1 < 0 || k + sk - 1 > NY) continue;
+                s_out[pos] = acc[3 * sj + sk][0];
+                s_out[pos + 1] = acc[3 * sj + sk][1];
+                pos += 2;
+            }
+        }
+    }
+    __syncthreads();
+    if (col_ok) {
+        const int n2 = (col_end - col_begin) >> 1;          // entries come in (ux, uy) pairs; col_begin is even
+        double2 *dst = reinterpret_cast<double2 *>(val + col_begin);
+        const double2 *src = reinterpret_cast<const double2 *>(s_out);
+        for (int i = tid & 63; i < n2; i += 64) dst[i] = src[i];
     }
 }
 
@@ -176,15 +354,38 @@ cudaError_t launch_csr_pattern(const LaunchCtx &lc, int NX, int NY, int32_t *row
 cudaError_t launch_assemble(const LaunchCtx &lc, int NX, int NY, int planestress, const int32_t *elem_desc,
                             const double *elstiff, const int32_t *rowptr, double *val, int64_t *launches)
 {
-    const int64_t Ndof = 2ll * (NX + 1) * (NY + 1);
-    const unsigned grid = (unsigned)((Ndof + 127) / 128);
-    if (planestress)
-        assemble_rows_kernel<true><<<grid, 128, 0, lc.stream>>>(NX, NY, elem_desc, elstiff, rowptr, val);
-    else
-        assemble_rows_kernel<false><<<grid, 128, 0, lc.stream>>>(NX, NY, elem_desc, elstiff, rowptr, val);
+    if (g_tiled == 2) {
+        const dim3 grid((NY + 1 + SN - 1) / SN, NX + 1);
+        if (planestress)
+            assemble_rows_staged_kernel<true><<<grid, 2 * SN, 0, lc.stream>>>(NX, NY, elem_desc, elstiff, rowptr, val);
+        else
+            assemble_rows_staged_kernel<false><<<grid, 2 * SN, 0, lc.stream>>>(NX, NY, elem_desc, elstiff, rowptr, val);
+    } else if (g_tiled == 1) {
+        static bool attr_set = false;
+        const int smem = TEJ * TEK * ESTRIDE * (int)sizeof(double);
+        if (!attr_set) {
+            cudaFuncSetAttribute(assemble_tile_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+            cudaFuncSetAttribute(assemble_tile_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+            attr_set = true;
+        }
+        const dim3 grid((NX + 1 + TJ - 1) / TJ, (NY + 1 + TK - 1) / TK);
+        if (planestress)
+            assemble_tile_kernel<true><<<grid, TJ * TK * 2, smem, lc.stream>>>(NX, NY, elem_desc, elstiff, rowptr, val);
+        else
+            assemble_tile_kernel<false><<<grid, TJ * TK * 2, smem, lc.stream>>>(NX, NY, elem_desc, elstiff, rowptr, val);
+    } else {
+        const int64_t Ndof = 2ll * (NX + 1) * (NY + 1);
+        const unsigned grid = (unsigned)((Ndof + 127) / 128);
+        if (planestress)
+            assemble_rows_kernel<true><<<grid, 128, 0, lc.stream>>>(NX, NY, elem_desc, elstiff, rowptr, val);
+        else
+            assemble_rows_kernel<false><<<grid, 128, 0, lc.stream>>>(NX, NY, elem_desc, elstiff, rowptr, val);
+    }
     (*launches)++;
     return cudaGetLastError();
 }
+
+void assembly_set_tiled(int on) { g_tiled = on; }
 
 cudaError_t launch_kel(const LaunchCtx &lc, int64_t Nel, int planestress, const int32_t *elem_desc, const double *elstiff,
                        double *Kel, int64_t *launches)

@@ -93,7 +93,7 @@ __device__ __forceinline__ void hill_seq_inv(const DevMat &m, const double *s, d
 }
 __device__ __forceinline__ void hill_grad(const DevMat &m, const double *s, double iseq, double *a)
 {
-    const double p = (s[0] + s[1] + s[2]) / 3.;
+    const double p = (s[0] + s[1] + s[2]) * (1. / 3.);   // multiplication instead of the IEEE division routine
     const double s0 = s[0] - p, s1 = s[1] - p, s2 = s[2] - p;
     const double h0 = m.hill[0], h1 = m.hill[1], h2 = m.hill[2];
     const double i2 = 0.5 * iseq;
@@ -112,9 +112,34 @@ __device__ __forceinline__ bool hill_fy_gt(const DevMat &m, double seq, const do
     if (lhs <= 0.) return false;
     const double a = eplt[0] * eplt[0] + eplt[1] * eplt[1] + eplt[2] * eplt[2];
     const double b = eplt[3] * eplt[3] + eplt[4] * eplt[4] + eplt[5] * eplt[5];
-    const double e2 = 2. * (a + 0.5 * b) / 3.;
+    const double e2 = (2. / 3.) * (a + 0.5 * b);
     return lhs * lhs > m.khard * m.khard * e2;
 }
+
+// gradient of the quadratic form q = hill_q: q(s + c) = q(s) + s . hill_qgrad(c) + q(c)
+__device__ __forceinline__ void hill_qgrad(const DevMat &m, const double *c, double *g)
+{
+    const double d01 = c[0] - c[1], d12 = c[1] - c[2], d20 = c[2] - c[0];
+    g[0] = m.hill[0] * d01 - m.hill[2] * d20;
+    g[1] = m.hill[1] * d12 - m.hill[0] * d01;
+    g[2] = m.hill[2] * d20 - m.hill[1] * d12;
+    g[3] = 6. * m.hill[3] * c[3];
+    g[4] = 6. * m.hill[4] * c[4];
+    g[5] = 6. * m.hill[5] * c[5];
+}
+
+// accumulator of the symmetric tangent sum: 21 registers, or 21 shared-memory words per thread (stride = block size)
+struct WRegs {
+    double w[21];
+    __device__ __forceinline__ double get(int k) const { return w[k]; }
+    __device__ __forceinline__ void set(int k, double v) { w[k] = v; }
+};
+struct WShared {
+    double *p;
+    int stride;
+    __device__ __forceinline__ double get(int k) const { return p[k * stride]; }
+    __device__ __forceinline__ void set(int k, double v) { p[k * stride] = v; }
+};
 
 struct HillStep {
     double sflow0, toler;   // get_sflow(epl), yf_tolerance * get_sflow(epl)   (material.py:243)
@@ -216,48 +241,72 @@ __device__ __forceinline__ int hill_passA(const DevMat &m, double *s, const doub
     return 1;
 }
 
-// Pass B: the 50 sub-steps for an element that pass A deferred.  gs: symmetric 21.  Returns branch code 2 (| 4 when a
-// radial-return correction fired).
-__device__ __forceinline__ int hill_passB(const DevMat &m, double *s, const double *ep, const double *de, double *depl, double *gs,
-                                          double &fy)
+// Pass B: the 50 sub-steps for an element that pass A deferred.
+//   epd : in = epl at the start of the step, out = epl + depl (the caller recovers depl = epd - epl; keeping only the
+//         running sum live saves 12 registers in the loop)
+//   W   : accumulator policy (WRegs / WShared) for sum_k ca ca^T / hh (+ correction blocks)
+//   gs  : out, symmetric 21.
+// Returns branch code 2 (| 4 when a radial-return correction fired).
+template <class WAcc>
+__device__ __forceinline__ int hill_passB(const DevMat &m, double *s, double *epd, const double *de, WAcc &W, double *gs, double &fy)
 {
     HillStep P;
-    hill_prelude(m, s, ep, de, P, fy);   // cannot be elastic: pass A deferred this element
+    hill_prelude(m, s, epd, de, P, fy);   // cannot be elastic: pass A deferred this element
     const double inv = 1. / (double)PLF_MAXIT;
 #pragma unroll
-    for (int k = 0; k < 6; k++) {
-        P.dr[k] = P.dr[k] / (double)PLF_MAXIT;   // 290
-        depl[k] = 0.;
-    }
+    for (int k = 0; k < 6; k++) P.dr[k] = P.dr[k] / (double)PLF_MAXIT;   // 290
     cv_mul(m, P.dr, P.cdr);
-    double W[21];
 #pragma unroll
-    for (int k = 0; k < 21; k++) W[k] = 0.;
+    for (int k = 0; k < 21; k++) W.set(k, 0.);
+    // q(s + cdr) = q(s) + s . gq + qc: the sub-step's elastic-trial yield check without re-evaluating the form
+    double gq[6];
+    hill_qgrad(m, P.cdr, gq);
+    const double qc = hill_q(m, P.cdr);
     double seq, iseq;
     hill_seq_inv(m, s, seq, iseq);
     bool corrected = false;
     const double ythr = P.sflow0 + PLF_YF_TOLERANCE;
+    const double ythr2 = ythr * ythr;
 #pragma unroll 1
     for (int it = 0; it < PLF_MAXIT; it++) {
-        double st[6], a[6], ca[6], dd[6], eplt[6];
+        double a[6], ca[6], dd[6];
+        bool yplus;
+        if (m.has_d) {
+            double st[6];
 #pragma unroll
-        for (int k = 0; k < 6; k++) st[k] = s[k] + P.cdr[k];
-        const bool yplus = hill_seq_gt(m, st, ythr);
+            for (int k = 0; k < 6; k++) st[k] = s[k] + P.cdr[k];
+            yplus = hill_seq_gt(m, st, ythr);
+        } else {
+            double qst = seq * seq + qc;   // seq^2 = q(s) when there is no hydrostatic term
+#pragma unroll
+            for (int k = 0; k < 6; k++) qst = fma(s[k], gq[k], qst);
+            yplus = qst > ythr2;
+        }
         hill_grad(m, s, iseq, a);
         cv_mul(m, a, ca);
-        double hh = m.khard, acd = 0., cadr = 0.;
+        double hh = m.khard, acd = 0.;
 #pragma unroll
-        for (int k = 0; k < 6; k++) { hh += a[k] * ca[k]; acd += a[k] * P.cdr[k]; cadr += ca[k] * P.dr[k]; }
+        for (int k = 0; k < 6; k++) { hh = fma(a[k], ca[k], hh); acd = fma(a[k], P.cdr[k], acd); }
+        // (CV a) . deps_r == a . (CV deps_r) for a symmetric CV: the second dot product (and deps_r itself) is only
+        // needed for a non-symmetric user-supplied stiffness
+        double cadr = acd;
+        if (!m.cv_sym) {
+            cadr = 0.;
+#pragma unroll
+            for (int k = 0; k < 6; k++) cadr = fma(ca[k], P.dr[k], cadr);
+        }
         const double ihh = fast_rcp(hh);
         const double lam = yplus ? acd * ihh : 0.;
         const double q = cadr * ihh;
 #pragma unroll
         for (int k = 0; k < 6; k++) {
             dd[k] = lam * a[k];
-            eplt[k] = ep[k] + depl[k] + dd[k];
             s[k] += P.cdr[k] - ca[k] * q;
         }
         hill_seq_inv(m, s, seq, iseq);
+        double eplt[6];
+#pragma unroll
+        for (int k = 0; k < 6; k++) eplt[k] = epd[k] + dd[k];
         if (hill_fy_gt(m, seq, eplt, P.toler)) {
             // radial-return correction (310-342), rare: exact arithmetic path
             corrected = true;
@@ -270,25 +319,26 @@ __device__ __forceinline__ int hill_passB(const DevMat &m, double *s, const doub
             }
             matvec6(m.SV, ex, t);
 #pragma unroll
-            for (int k = 0; k < 6; k++) dd[k] += t[k];
+            for (int k = 0; k < 6; k++) eplt[k] += t[k];
             lstsq_3x6(P.dr, ex, x);
-            W[sym_idx(0, 0)] += x[0]; W[sym_idx(0, 1)] += x[5]; W[sym_idx(0, 2)] += x[4];
-            W[sym_idx(1, 1)] += x[1]; W[sym_idx(1, 2)] += x[3]; W[sym_idx(2, 2)] += x[2];
+            W.set(sym_idx(0, 0), W.get(sym_idx(0, 0)) + x[0]);
+            W.set(sym_idx(0, 1), W.get(sym_idx(0, 1)) + x[5]);
+            W.set(sym_idx(0, 2), W.get(sym_idx(0, 2)) + x[4]);
+            W.set(sym_idx(1, 1), W.get(sym_idx(1, 1)) + x[1]);
+            W.set(sym_idx(1, 2), W.get(sym_idx(1, 2)) + x[3]);
+            W.set(sym_idx(2, 2), W.get(sym_idx(2, 2)) + x[2]);
             hill_seq_inv(m, s, seq, iseq);
         }
 #pragma unroll
         for (int i = 0; i < 6; i++) {
             const double ci = ca[i] * ihh;
 #pragma unroll
-            for (int j = i; j < 6; j++) W[sym_idx(i, j)] = fma(ci, ca[j], W[sym_idx(i, j)]);
+            for (int j = i; j < 6; j++) W.set(sym_idx(i, j), fma(ci, ca[j], W.get(sym_idx(i, j))));
         }
 #pragma unroll
-        for (int k = 0; k < 6; k++) depl[k] += dd[k];
+        for (int k = 0; k < 6; k++) epd[k] = eplt[k];
     }
-    double eplt[6];
-#pragma unroll
-    for (int k = 0; k < 6; k++) eplt[k] = ep[k] + depl[k];
-    fy = seq - (m.sy + (m.khard != 0. ? eps_eq6(eplt) * m.khard : 0.));
+    fy = seq - (m.sy + (m.khard != 0. ? eps_eq6(epd) * m.khard : 0.));
     const double f1 = P.split ? (1. - P.st_scal) : 0.;
     const double f2 = P.st_scal * inv;
 #pragma unroll
@@ -296,7 +346,7 @@ __device__ __forceinline__ int hill_passB(const DevMat &m, double *s, const doub
 #pragma unroll
         for (int j = i; j < 6; j++) {
             const double c = m.CV[6 * i + j];
-            gs[sym_idx(i, j)] = c * f1 + ((double)PLF_MAXIT * c - W[sym_idx(i, j)]) * f2;
+            gs[sym_idx(i, j)] = c * f1 + ((double)PLF_MAXIT * c - W.get(sym_idx(i, j))) * f2;
         }
     return 2 | (corrected ? 4 : 0);
 }

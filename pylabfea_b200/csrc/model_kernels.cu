@@ -191,7 +191,13 @@ __global__ void __launch_bounds__(128) sweep_hill_kernel(int64_t n, int NY, int 
 #pragma unroll
                         for (int j = i; j < 6; j++) gs[sym_idx(i, j)] = m.CV[6 * i + j] * tc - (ca[i] * tw) * ca[j];
                 } else if (GATHER) {
-                    br = hill_passB(m, s, ep, de, dp, gs, fyv);
+                    double epd[6];
+#pragma unroll
+                    for (int k = 0; k < 6; k++) epd[k] = ep[k];
+                    WRegs W;
+                    br = hill_passB(m, s, epd, de, W, gs, fyv);
+#pragma unroll
+                    for (int k = 0; k < 6; k++) dp[k] = epd[k] - ep[k];
                     ns = PLF_MAXIT - 1;
                 } else {
                     HillModel ym(m);

@@ -249,6 +249,10 @@ extern "C" int plf_set_materials(plf_ctx *ctx, int nmat, const plf_material *mat
             for (int c = 0; c < 6; c++)
                 if (!((r < 3 && c < 3) || r == c) && d.CV[6 * r + c] != 0.) d.cv_block = 0;
         d.has_d = (d.d[0] != 0. || d.d[1] != 0. || d.d[2] != 0.) ? 1 : 0;
+        d.cv_sym = 1;
+        for (int r = 0; r < 6; r++)
+            for (int c = r + 1; c < 6; c++)
+                if (d.CV[6 * r + c] != d.CV[6 * c + r]) d.cv_sym = 0;
         memcpy(d.bar_m1, m.barlat_m1, sizeof d.bar_m1);
         memcpy(d.bar_m2, m.barlat_m2, sizeof d.bar_m2);
         d.bar_exp = m.barlat_exp;
@@ -347,7 +351,7 @@ extern "C" int plf_batch_run(plf_ctx *ctx, plf_batch *b)
 {
     if (!ctx || !b) return PLF_EINVAL;
     if (ctx->nmat == 0) return fail(ctx, PLF_ESTATE, "plf_batch_run: no materials set");
-    LaunchCtx lc{ctx->stream, ctx->sm_count};
+    LaunchCtx lc{ctx->stream, ctx->sm_count, ctx->passb_wsmem};
     CK(launch_response(lc, ctx->hmats, ctx->nmat, b->n, b->mat_id, b->sig, b->epl, b->deps, b->fy, b->sig_out, b->depl,
                        b->ctan, b->nsteps, b->worklist, (unsigned int *)ctx->d_scalars,
                        (unsigned long long *)(ctx->d_scalars + 8), ctx->compact, &ctx->launches));
@@ -372,6 +376,8 @@ extern "C" int plf_set_option(plf_ctx *ctx, const char *key, int value)
 {
     if (!ctx || !key) return PLF_EINVAL;
     if (!strcmp(key, "compact")) { ctx->compact = value; return PLF_OK; }
+    if (!strcmp(key, "assembly_tiled")) { assembly_set_tiled(value); return PLF_OK; }
+    if (!strcmp(key, "passb_wsmem")) { ctx->passb_wsmem = value; return PLF_OK; }
     return fail(ctx, PLF_EINVAL, std::string("plf_set_option: unknown key ") + key);
 }
 

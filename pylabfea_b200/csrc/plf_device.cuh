@@ -16,6 +16,8 @@ struct DevMat {
     int32_t kind, nsv, dev_only, tresca, lhs, nsv_pad;
     int32_t cv_block;   // CV = [3x3 normal block | diagonal shear] (cv_mul, hill_fast.cuh)
     int32_t has_d;      // any Drucker / LHS weight non-zero
+    int32_t cv_sym;     // CV is exactly symmetric: (CV a) . deps == a . (CV deps)
+    int32_t pad2_;
     double sy, khard;
     double hill[6];
     double d[3];     // I1 weights (calc_seq 645-650)

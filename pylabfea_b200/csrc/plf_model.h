@@ -31,6 +31,7 @@ struct plf_ctx {
     unsigned char *d_scalars = nullptr;   // 4 KB of device scratch scalars (counters, reductions)
     unsigned char *h_scalars = nullptr;   // pinned mirror
     int compact = 1;                      // two-pass (compacted) return mapping
+    int passb_wsmem = 2;                  // pass B variant: 0 regs/2 blocks per SM, 1 smem accumulator/4, 2 regs/3 (fastest measured)
 
     // materials
     int nmat = 0, planestress = 0;

@@ -90,7 +90,10 @@ __device__ __forceinline__ void stage_out(int64_t base, int cnt, const double *s
     }
 }
 
-__global__ void __launch_bounds__(RB) response_passA_kernel(int64_t n, const int32_t *__restrict__ mat_id,
+// SINGLE: the batch uses one material -> c_mat[0] is addressed with immediate constant-bank operands (no registers
+// hold material parameters, no indexed constant loads)
+template <bool SINGLE>
+__global__ void __launch_bounds__(RB, 4) response_passA_kernel(int64_t n, const int32_t *__restrict__ mat_id,
                                                             const double *__restrict__ sig, const double *__restrict__ epl,
                                                             const double *__restrict__ deps, double *__restrict__ fy,
                                                             double *__restrict__ sig_out, double *__restrict__ depl_out,
@@ -108,7 +111,7 @@ __global__ void __launch_bounds__(RB) response_passA_kernel(int64_t n, const int
     bool done = false, defer = false;
     const int64_t e = base + tid;
     if (tid < cnt) {
-        const DevMat &m = c_mat[mat_id ? mat_id[e] : 0];
+        const DevMat &m = c_mat[SINGLE ? 0 : mat_id[e]];
         if (m.kind == PLF_MAT_ELASTIC || m.kind == PLF_MAT_HILL) {
             double dp[6], ca[6], tc = 1., tw = 0., fyv = 0.;
             int br = 0;
@@ -145,17 +148,21 @@ __global__ void __launch_bounds__(RB) response_passA_kernel(int64_t n, const int
     stage_out(base, cnt, s_sig, s_epl, s_ct, s_done, sig_out, depl_out, ctan);
 }
 
-__global__ void __launch_bounds__(RB) response_passB_kernel(const int32_t *__restrict__ mat_id, const double *__restrict__ sig,
+// WSMEM: the 21-entry tangent accumulator lives in shared memory ([k][thread], conflict free) instead of registers,
+// which lets 4 blocks (16 warps) share an SM instead of 2.
+template <bool WSMEM, int MINB, bool SINGLE>
+__global__ void __launch_bounds__(RB, MINB) response_passB_kernel(const int32_t *__restrict__ mat_id, const double *__restrict__ sig,
                                                             const double *__restrict__ epl, const double *__restrict__ deps,
                                                             double *__restrict__ fy, double *__restrict__ sig_out,
                                                             double *__restrict__ depl_out, double *__restrict__ ctan,
                                                             int32_t *__restrict__ nsteps, const int32_t *__restrict__ worklist,
                                                             const unsigned int *__restrict__ work_count)
 {
+    __shared__ double s_W[WSMEM ? 21 * RB : 1];
     const unsigned int n = *work_count;
     for (unsigned int t = blockIdx.x * RB + threadIdx.x; t < n; t += gridDim.x * RB) {
         const int64_t e = worklist[t];
-        const DevMat &m = c_mat[mat_id ? mat_id[e] : 0];
+        const DevMat &m = c_mat[SINGLE ? 0 : mat_id[e]];
         double s[6], ep[6], de[6], dp[6], gs[21], fyv;
 #pragma unroll
         for (int k = 0; k < 3; k++) {
@@ -166,7 +173,20 @@ __global__ void __launch_bounds__(RB) response_passB_kernel(const int32_t *__res
             ep[2 * k] = b.x; ep[2 * k + 1] = b.y;
             de[2 * k] = c.x; de[2 * k + 1] = c.y;
         }
-        hill_passB(m, s, ep, de, dp, gs, fyv);
+        if (WSMEM) {
+            WShared W{s_W + threadIdx.x, RB};
+            hill_passB(m, s, ep, de, W, gs, fyv);
+        } else {
+            WRegs W;
+            hill_passB(m, s, ep, de, W, gs, fyv);
+        }
+        // ep now holds epl + depl; the increment is recovered against the (L2-resident) input record
+#pragma unroll
+        for (int k = 0; k < 3; k++) {
+            double2 b = __ldcg(reinterpret_cast<const double2 *>(epl + e * 6) + k);   // a real re-load, not a live register
+            dp[2 * k] = ep[2 * k] - b.x;
+            dp[2 * k + 1] = ep[2 * k + 1] - b.y;
+        }
         if (fy) fy[e] = fyv;
         if (nsteps) nsteps[e] = PLF_MAXIT - 1;
         if (sig_out)
@@ -396,7 +416,9 @@ static size_t svc_smem(const DevMat &m) { return sizeof(double) * 7 * (size_t)m.
 cudaError_t response_init()
 {
     cudaError_t e;
-    e = cudaFuncSetAttribute(response_passA_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)k1_smem());
+    e = cudaFuncSetAttribute(response_passA_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)k1_smem());
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(response_passA_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)k1_smem());
     if (e != cudaSuccess) return e;
     e = cudaFuncSetAttribute(response_generic_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)k1_smem());
     if (e != cudaSuccess) return e;
@@ -419,11 +441,28 @@ cudaError_t launch_response(const LaunchCtx &lc, const DevMat *hmats, int nmat, 
     if (any_hill) {
         if (compact && worklist) {
             cudaMemsetAsync(work_count, 0, sizeof(unsigned int), lc.stream);
-            response_passA_kernel<<<grid, RB, k1_smem(), lc.stream>>>(n, mat_id, sig, epl, deps, fy, sig_out, depl, ctan, nsteps,
-                                                                      worklist, work_count);
+            const bool single = (nmat == 1);
+            if (single)
+                response_passA_kernel<true><<<grid, RB, k1_smem(), lc.stream>>>(n, mat_id, sig, epl, deps, fy, sig_out, depl, ctan,
+                                                                                nsteps, worklist, work_count);
+            else
+                response_passA_kernel<false><<<grid, RB, k1_smem(), lc.stream>>>(n, mat_id, sig, epl, deps, fy, sig_out, depl, ctan,
+                                                                                 nsteps, worklist, work_count);
             int64_t bgrid = std::min<int64_t>((int64_t)lc.sm_count * 8, (int64_t)grid);
-            response_passB_kernel<<<(unsigned)bgrid, RB, 0, lc.stream>>>(mat_id, sig, epl, deps, fy, sig_out, depl, ctan, nsteps,
-                                                                         worklist, work_count);
+#define PASSB(W, M, S)                                                                                                     \
+    response_passB_kernel<W, M, S><<<(unsigned)bgrid, RB, 0, lc.stream>>>(mat_id, sig, epl, deps, fy, sig_out, depl, ctan, \
+                                                                          nsteps, worklist, work_count)
+            // variant: 0 = accumulator in registers, 2 blocks per SM; 1 = shared memory, 4 blocks; 2 = registers, 3 blocks
+            if (single) {
+                switch (lc.passb_wsmem) {
+                case 1: PASSB(true, 4, true); break;
+                case 2: PASSB(false, 3, true); break;
+                default: PASSB(false, 2, true); break;
+                }
+            } else {
+                PASSB(false, 2, false);
+            }
+#undef PASSB
             *launches += 2;
         } else {
             response_generic_kernel<<<grid, RB, k1_smem(), lc.stream>>>(n, mat_id, sig, epl, deps, fy, sig_out, depl, ctan, nsteps);

@@ -163,9 +163,11 @@ def setup_mesh_from_golden(ctx, g):
     return NX, NY
 
 
+@pytest.mark.parametrize('tiled', [2, 1, 0])
 @pytest.mark.parametrize('case', KCASES)
-def test_K_bit_exact_vs_reference_golden(ctx, golden, case):
+def test_K_bit_exact_vs_reference_golden(ctx, golden, case, tiled):
     g = golden('kmat_' + case)
+    ctx.set_option('assembly_tiled', tiled)
     NX, NY = setup_mesh_from_golden(ctx, g)
     for e in range(len(g['Bmat'])):
         assert np.array_equal(ctx.get_bmat(e), g['Bmat'][e]), 'B must be bit-exact'
@@ -185,6 +187,28 @@ def test_K_bit_exact_vs_reference_golden(ctx, golden, case):
     Kref = np.zeros((Ndof, Ndof))
     Kref[g['K_row'], g['K_col']] = g['K_val']
     assert np.array_equal(K, Kref), 'assembled K must be bit-exact (max diff %g)' % np.max(np.abs(K - Kref))
+    ctx.set_option('assembly_tiled', 2)
+
+
+@pytest.mark.parametrize('shape', [(256, 256), (37, 95), (130, 3), (1, 70)])
+def test_K_tiled_equals_direct_on_ragged_meshes(ctx, golden, shape):
+    """Tile-boundary cases (mesh sizes that are not multiples of the 4 x 32 node tile, one-element-wide meshes,
+    plane stress): the tiled assembly must reproduce the row-per-thread kernel bit for bit."""
+    g = golden('response_hill')
+    NX, NY = shape
+    rng = np.random.default_rng(NX * 1000 + NY)
+    for ps in (0, 1):
+        ctx.set_materials([plf_material_from_golden(g)], planestress=ps)
+        ctx.mesh_structured(NX, NY, rng.choice([0.5, 1.0, 1.5], NX), 0.7, 1.3, np.zeros(NX * NY, np.int32))
+        tag = 'ps' if ps else 'pe'
+        ctx.set_tangent(g[tag + '_ctan'][rng.integers(0, len(g[tag + '_ctan']), NX * NY)])
+        vals = []
+        for tiled in (0, 1, 2):
+            ctx.set_option('assembly_tiled', tiled)
+            ctx.setupK()
+            vals.append(ctx.get_csr()[2])
+        assert np.array_equal(vals[0], vals[1]) and np.array_equal(vals[0], vals[2])
+    ctx.set_option('assembly_tiled', 2)
 
 
 def test_K_large_mesh_vs_oracle(ctx, golden):
