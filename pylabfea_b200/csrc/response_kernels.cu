@@ -92,22 +92,74 @@ __device__ __forceinline__ void stage_out(int64_t base, int cnt, const double *s
 
 // SINGLE: the batch uses one material -> c_mat[0] is addressed with immediate constant-bank operands (no registers
 // hold material parameters, no indexed constant loads)
+__device__ __forceinline__ void cp_async16(void *smem_dst, const void *gmem_src)
+{
+    const unsigned s = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(s), "l"(gmem_src));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N)); }
+
+// Persistent, software-pipelined pass A: while a block computes and writes tile t, the 3 x 6 KB input records of its
+// next tile are already in flight (cp.async into the second shared-memory buffer), so HBM reads overlap the math and
+// the write-back instead of being exposed at the top of every block (ncu of the non-pipelined version:
+// long_scoreboard on the staging loads dominated, 39 % DRAM throughput).
 template <bool SINGLE>
-__global__ void __launch_bounds__(RB, 4) response_passA_kernel(int64_t n, const int32_t *__restrict__ mat_id,
+__global__ void __launch_bounds__(RB, 3) response_passA_kernel(int64_t n, const int32_t *__restrict__ mat_id,
                                                             const double *__restrict__ sig, const double *__restrict__ epl,
                                                             const double *__restrict__ deps, double *__restrict__ fy,
                                                             double *__restrict__ sig_out, double *__restrict__ depl_out,
                                                             double *__restrict__ ctan, int32_t *__restrict__ nsteps,
                                                             int32_t *__restrict__ worklist, unsigned int *__restrict__ work_count)
 {
-    extern __shared__ double smem[];
-    double *s_sig = smem, *s_epl = smem + RB * 6, *s_dep = smem + 2 * RB * 6, *s_ct = smem + 3 * RB * 6;
+    extern __shared__ double smem[];   // [2][3][RB*6] input buffers + [RB*CT_STRIDE] tangent staging
+    double *s_ct = smem + 2 * 3 * RB * 6;
     __shared__ unsigned char s_done[RB];
     const int tid = threadIdx.x;
-    const int64_t base = (int64_t)blockIdx.x * RB;
+    const int64_t ntiles = (n + RB - 1) / RB;
+
+    auto prefetch = [&](int64_t tile, int buf) {
+        const int64_t b0 = tile * RB;
+        const int c = (int)min((int64_t)RB, n - b0);
+        double *d = smem + buf * (3 * RB * 6);
+        const double2 *g0 = reinterpret_cast<const double2 *>(sig + b0 * 6);
+        const double2 *g1 = reinterpret_cast<const double2 *>(epl + b0 * 6);
+        const double2 *g2 = reinterpret_cast<const double2 *>(deps + b0 * 6);
+        for (int i = tid; i < c * 3; i += RB) {
+            cp_async16(reinterpret_cast<double2 *>(d) + i, g0 + i);
+            cp_async16(reinterpret_cast<double2 *>(d + RB * 6) + i, g1 + i);
+            cp_async16(reinterpret_cast<double2 *>(d + 2 * RB * 6) + i, g2 + i);
+        }
+        cp_async_commit();
+    };
+
+    int buf = 0;
+    if ((int64_t)blockIdx.x < ntiles) prefetch(blockIdx.x, 0);
+    for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, buf ^= 1) {
+    const int64_t nxt = tile + gridDim.x;
+    if (nxt < ntiles) {
+        prefetch(nxt, buf ^ 1);
+        cp_async_wait<1>();   // everything but the newest group (the next tile) has landed
+    } else {
+        cp_async_wait<0>();
+    }
+    __syncthreads();
+    double *s_sig = smem + buf * (3 * RB * 6), *s_epl = s_sig + RB * 6, *s_dep = s_sig + 2 * RB * 6;
+    const int64_t base = tile * RB;
     const int cnt = (int)min((int64_t)RB, n - base);
     double s[6], ep[6], de[6];
-    stage_in(sig, epl, deps, base, cnt, s_sig, s_epl, s_dep, s, ep, de);
+    if (tid < cnt) {
+#pragma unroll
+        for (int k = 0; k < 3; k++) {
+            double2 a = reinterpret_cast<double2 *>(s_sig)[3 * tid + k];
+            double2 b = reinterpret_cast<double2 *>(s_epl)[3 * tid + k];
+            double2 c = reinterpret_cast<double2 *>(s_dep)[3 * tid + k];
+            s[2 * k] = a.x; s[2 * k + 1] = a.y;
+            ep[2 * k] = b.x; ep[2 * k + 1] = b.y;
+            de[2 * k] = c.x; de[2 * k + 1] = c.y;
+        }
+    }
     bool done = false, defer = false;
     const int64_t e = base + tid;
     if (tid < cnt) {
@@ -146,6 +198,8 @@ __global__ void __launch_bounds__(RB, 4) response_passA_kernel(int64_t n, const 
     s_done[tid] = done;
     __syncthreads();
     stage_out(base, cnt, s_sig, s_epl, s_ct, s_done, sig_out, depl_out, ctan);
+    __syncthreads();   // staging buffers are free again (the next prefetch overwrites this input buffer)
+    }
 }
 
 // WSMEM: the 21-entry tangent accumulator lives in shared memory ([k][thread], conflict free) instead of registers,
@@ -411,14 +465,15 @@ __global__ void __launch_bounds__(SVC_WARPS * 32) prim_svc_kernel(int op, int mi
 // host launchers
 // ------------------------------------------------------------------------------------------------------------
 static size_t k1_smem() { return sizeof(double) * (3 * RB * 6 + RB * CT_STRIDE); }
+static size_t k1a_smem() { return sizeof(double) * (2 * 3 * RB * 6 + RB * CT_STRIDE); }   // double-buffered inputs
 static size_t svc_smem(const DevMat &m) { return sizeof(double) * 7 * (size_t)m.nsv_pad; }
 
 cudaError_t response_init()
 {
     cudaError_t e;
-    e = cudaFuncSetAttribute(response_passA_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)k1_smem());
+    e = cudaFuncSetAttribute(response_passA_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)k1a_smem());
     if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(response_passA_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)k1_smem());
+    e = cudaFuncSetAttribute(response_passA_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)k1a_smem());
     if (e != cudaSuccess) return e;
     e = cudaFuncSetAttribute(response_generic_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)k1_smem());
     if (e != cudaSuccess) return e;
@@ -442,12 +497,14 @@ cudaError_t launch_response(const LaunchCtx &lc, const DevMat *hmats, int nmat, 
         if (compact && worklist) {
             cudaMemsetAsync(work_count, 0, sizeof(unsigned int), lc.stream);
             const bool single = (nmat == 1);
+            // persistent: 3 blocks per SM, each walking tiles with a double-buffered cp.async prefetch
+            const unsigned agrid = (unsigned)std::min<int64_t>((int64_t)lc.sm_count * 3, (int64_t)grid);
             if (single)
-                response_passA_kernel<true><<<grid, RB, k1_smem(), lc.stream>>>(n, mat_id, sig, epl, deps, fy, sig_out, depl, ctan,
-                                                                                nsteps, worklist, work_count);
+                response_passA_kernel<true><<<agrid, RB, k1a_smem(), lc.stream>>>(n, mat_id, sig, epl, deps, fy, sig_out, depl, ctan,
+                                                                                  nsteps, worklist, work_count);
             else
-                response_passA_kernel<false><<<grid, RB, k1_smem(), lc.stream>>>(n, mat_id, sig, epl, deps, fy, sig_out, depl, ctan,
-                                                                                 nsteps, worklist, work_count);
+                response_passA_kernel<false><<<agrid, RB, k1a_smem(), lc.stream>>>(n, mat_id, sig, epl, deps, fy, sig_out, depl,
+                                                                                   ctan, nsteps, worklist, work_count);
             int64_t bgrid = std::min<int64_t>((int64_t)lc.sm_count * 8, (int64_t)grid);
 #define PASSB(W, M, S)                                                                                                     \
     response_passB_kernel<W, M, S><<<(unsigned)bgrid, RB, 0, lc.stream>>>(mat_id, sig, epl, deps, fy, sig_out, depl, ctan, \
