@@ -147,19 +147,14 @@ class ClockSampler:
 def oracle_step(orc, mats, CV, sig, epl, deps, B4, jacw, nthreads):
     """The step on the host: oracle response for every sampled element, then Kel of each new tangent (the CPU side of
     setupK; the O(1) adds of the assembly itself are not included, which favours the CPU)."""
-    if nthreads > 1:
-        out = orc.response_batch_threads(mats, None, sig, epl, deps, CV[None], nthreads)
-    else:
-        out = orc.response_batch(mats, None, sig, epl, deps, CV[None])
-    ct = out[3]
-    lib = orc.lib()
-    import ctypes as C
-    kel = np.zeros((8, 8))
-    B4c = np.ascontiguousarray(B4)
-    dp = C.POINTER(C.c_double)
-    for i in range(len(ct)):
-        lib.orc_kel(B4c.ctypes.data_as(dp), ct[i].ctypes.data_as(dp), C.c_double(jacw), kel.ctypes.data_as(dp))
-    return out
+    return orc.step_batch(mats, sig, epl, deps, CV[None], B4, jacw, nthreads)
+
+
+def host_cores():
+    try:
+        return len(os.sched_getaffinity(0))
+    except AttributeError:
+        return os.cpu_count() or 1
 
 
 def run_reference(args, rank, world):
@@ -178,7 +173,7 @@ def run_reference(args, rank, world):
     lx = 4. / N
     B4 = orc.gauss_bmats(lx, lx, 0, CV, E_MOD, NU)
     jacw = (lx * lx * 1.) * 4.
-    cores = os.cpu_count() or 1
+    cores = host_cores()
     for _ in range(args.warmup):
         oracle_step(orc, mats, CV, sig[:2000], epl[:2000], deps[:2000], B4, jacw, cores)
     t0 = time.perf_counter()
@@ -206,8 +201,54 @@ def workload_config(N):
             '(%.0f MB read+written per step)' % (N * N * (BYTES_PER_UPDATE + BYTES_PER_ASSEMBLED) / 1e6)}
 
 
+def shard_plan(N, rank, world):
+    """Weak scaling: every rank owns its own N x N mesh block (independent elements and element rows, SURVEY.md 8e:
+    no data-path collective).  The block's synthetic state is seeded per rank."""
+    return {'rank': rank, 'world': world, 'mesh': N, 'elements': N * N, 'seed': 1234 + rank}
+
+
+class RankGroup:
+    """torch.distributed plumbing for the bench: barrier + MAX/SUM of a scalar over the ranks.  NCCL on GPUs
+    (device tensors), gloo for the CPU self-test.  With one rank it is a no-op and torch is never imported."""
+
+    def __init__(self, world, local, backend='nccl'):
+        self.world, self.dist, self.dev = world, None, 'cpu'
+        if world > 1:
+            import torch
+            import torch.distributed as dist
+            self.torch, self.dist = torch, dist
+            if backend == 'nccl':
+                torch.cuda.set_device(local)
+                self.dev = 'cuda'
+                dist.init_process_group('nccl', device_id=torch.device('cuda', local))
+            else:
+                dist.init_process_group(backend)
+
+    def barrier(self):
+        if self.dist is not None:
+            self.dist.barrier()
+
+    def _reduce(self, v, op):
+        if self.dist is None:
+            return v
+        t = self.torch.tensor([v], dtype=self.torch.float64, device=self.dev)
+        self.dist.all_reduce(t, op=op)
+        return float(t.item())
+
+    def max_over_ranks(self, v):
+        return self._reduce(v, self.dist.ReduceOp.MAX if self.dist else None)
+
+    def sum_over_ranks(self, v):
+        return self._reduce(v, self.dist.ReduceOp.SUM if self.dist else None)
+
+    def close(self):
+        if self.dist is not None:
+            self.dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
+    ap.add_argument('--dist-selftest', action='store_true')
     ap.add_argument('--gpus', type=int, default=1)
     ap.add_argument('--steps', type=int, default=200)
     ap.add_argument('--warmup', type=int, default=5)
@@ -228,24 +269,20 @@ def main():
         run_reference(args, rank, world)
         return
 
-    dist = None
-    if world > 1:
-        import torch
-        import torch.distributed as dist
-        torch.cuda.set_device(local)
-        dist.init_process_group('nccl', device_id=torch.device('cuda', local))
-
-    def barrier():
-        if dist is not None:
-            dist.barrier()
-
-    def max_over_ranks(v):
-        if dist is None:
-            return v
-        import torch
-        t = torch.tensor([v], dtype=torch.float64, device='cuda')
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item())
+    plan = shard_plan(args.mesh, rank, world)
+    group = RankGroup(world, local, backend='gloo' if args.dist_selftest else 'nccl')
+    barrier, max_over_ranks = group.barrier, group.max_over_ranks
+    if args.dist_selftest:
+        # CPU-only check of the multi-rank plumbing (tests/test_dist_gloo.py): every rank plans its block, the ranks
+        # meet at a barrier and reduce a per-rank time with MAX and the element count with SUM.
+        barrier()
+        t = max_over_ranks(float(rank + 1))
+        total = group.sum_over_ranks(float(plan['elements']))
+        if rank == 0:
+            print(json.dumps({'selftest': True, 'world': world, 'max_time': t, 'total_elements': total,
+                              'seed_rank0': plan['seed'], 'scaling': 'weak'}))
+        group.close()
+        return
 
     from pylabfea_b200 import _lib
     ctx = _lib.Context(local)
@@ -258,7 +295,7 @@ def main():
     ctx.set_materials([mat], planestress=False)
     lx = 4. / N
     ctx.mesh_structured(N, N, np.full(N, lx), lx, 1., np.zeros(Nel, np.int32))
-    sig, epl, deps = synth_states(N, 1234 + rank)
+    sig, epl, deps = synth_states(N, plan['seed'])
     b = ctx.batch_create(Nel)
     ctx.batch_upload(b, sig, epl, deps)
     ctx.synchronize()
@@ -355,8 +392,7 @@ def main():
                'api': 'plf_batch_upload + plf_batch_run + plf_setupK_from_batch + plf_batch_download + plf_get_csr (pinned host buffers)'}
 
     if rank != 0:
-        if dist is not None:
-            dist.destroy_process_group()
+        group.close()
         return
 
     peaks = {}
@@ -365,14 +401,35 @@ def main():
     except Exception:
         pass
     peak = float(peaks.get('hbm_gbs', 6650.))
+
+    def ncu_traffic(*kernels):
+        """DRAM bytes per launch from the committed ncu capture (profiles/traffic.json, scripts/summarize_ncu.py);
+        only valid for the mesh size the capture was taken at (1024 x 1024)."""
+        try:
+            tj = json.load(open(os.path.join(ROOT, 'profiles', 'traffic.json')))
+            tot = 0.
+            for kname in kernels:
+                hit = [v for k, v in tj.items() if k.split('<')[0].endswith(kname)]
+                if not hit:
+                    return None
+                tot += hit[0]['dram_bytes_per_launch']
+            return tot if N == 1024 else None
+        except Exception:
+            return None
     achieved = BYTES_PER_UPDATE * Nel / (resp_ms_max * 1e-3) / 1e9
     asm_achieved = BYTES_PER_ASSEMBLED * Nel / (asm_ms_max * 1e-3) / 1e9
-    roofline = {'bound': 'hbm', 'kernel': 'response_hill_kernel (pass A + compacted pass B)' if args.compact else 'response_hill_kernel',
+    asm_kernel = {0: 'assemble_rows_kernel', 1: 'assemble_tile_kernel', 2: 'assemble_rows_staged_kernel'}[args.assembly_tiled]
+    roofline = {'bound': 'hbm',
+                'kernel': 'response_passA_kernel + response_passB_kernel (return mapping, compacted 50-sub-step pass)'
+                if args.compact else 'response_generic_kernel',
                 'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak,
                 'peak_source': 'MEASURED_PEAKS.json hbm_gbs (of measured)' if peaks else 'fallback 6650 GB/s (of fallback)',
-                'traffic': None, 'bytes_per_update': BYTES_PER_UPDATE, 'ms': resp_ms_max,
-                'assembly': {'kernel': 'assemble_rows_kernel', 'achieved': asm_achieved, 'frac': asm_achieved / peak,
-                             'bytes_per_element': BYTES_PER_ASSEMBLED, 'ms': asm_ms_max}}
+                'algorithmic_bytes': BYTES_PER_UPDATE * Nel,
+                'traffic': ncu_traffic('response_passA_kernel', 'response_passB_kernel') if args.compact else None,
+                'bytes_per_update': BYTES_PER_UPDATE, 'ms': resp_ms_max,
+                'assembly': {'kernel': asm_kernel, 'achieved': asm_achieved, 'frac': asm_achieved / peak,
+                             'bytes_per_element': BYTES_PER_ASSEMBLED, 'algorithmic_bytes': BYTES_PER_ASSEMBLED * Nel,
+                             'traffic': ncu_traffic(asm_kernel), 'ms': asm_ms_max}}
 
     cpu = None
     if not args.no_cpu:
@@ -399,8 +456,7 @@ def main():
             'launches_per_step': launches_per_step, 'clocks': clocks, 'wall_s_timed_region': t_wall,
             'device': ctx.device_info()['name']}
     print(json.dumps(line))
-    if dist is not None:
-        dist.destroy_process_group()
+    group.close()
 
 
 if __name__ == '__main__':

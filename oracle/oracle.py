@@ -134,6 +134,41 @@ def response_batch_threads(mats, mat_id, sig, epl, deps, CVs, nthreads):
     return tuple(np.concatenate([r[k] for r in res]) for k in range(5))
 
 
+def step_batch(mats, sig, epl, deps, CVs, B4, jacw, nthreads=1):
+    """bench.py's CPU step: Material.response for every element + Kel of the new tangent, sharded over host threads
+    (one C call per shard; ctypes releases the GIL).  Returns (fy, sig, depl, ctan, nsteps)."""
+    from concurrent.futures import ThreadPoolExecutor
+    L = lib()
+    L.orc_step_batch.restype = C.c_double
+    sig, epl, deps = _a(sig), _a(epl), _a(deps)
+    n = len(sig)
+    arr = (OrcMat * len(mats))(*[m.c for m in mats])
+    CVs = _a(CVs).reshape(len(mats), 36)
+    B4 = _a(B4)
+    mid = np.zeros(n, dtype=np.int32)
+    fy = np.zeros(n)
+    so = np.zeros((n, 6))
+    dp = np.zeros((n, 6))
+    ct = np.zeros((n, 36))
+    ns = np.zeros(n, dtype=np.int32)
+    cuts = np.linspace(0, n, max(1, nthreads) * 4 + 1).astype(int)
+
+    def run(ab):
+        a, b = ab
+        if b <= a:
+            return 0.
+        return L.orc_step_batch(arr, C.c_int64(b - a), _p(mid[a:b]), _p(sig[a:b]), _p(epl[a:b]), _p(deps[a:b]), _p(CVs),
+                                _p(B4), C.c_double(jacw), _p(fy[a:b]), _p(so[a:b]), _p(dp[a:b]), _p(ct[a:b]), _p(ns[a:b]), None)
+    parts = list(zip(cuts[:-1], cuts[1:]))
+    if nthreads > 1:
+        with ThreadPoolExecutor(nthreads) as ex:
+            list(ex.map(run, parts))
+    else:
+        for p in parts:
+            run(p)
+    return fy, so, dp, ct.reshape(n, 6, 6), ns
+
+
 def calc_seq(mat, sig):
     sig = _a(sig).reshape(-1, 6)
     out = np.zeros(len(sig))

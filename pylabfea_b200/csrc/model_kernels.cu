@@ -358,8 +358,9 @@ __global__ void __launch_bounds__(128) commit_elements_kernel(int64_t Nel, int N
 // ---------------------------------------------------------------------------------------------------------------
 // deterministic reductions: per-block partials in fixed slots, summed in fixed order by the last block to finish
 // ---------------------------------------------------------------------------------------------------------------
+// Returns true in exactly one thread of the grid (thread 0 of the last block) after it has written out[0..NV).
 template <int NV>
-__device__ __forceinline__ void block_reduce_to_partials(double *v, double *partial, unsigned int *counter, double *out,
+__device__ __forceinline__ bool block_reduce_to_partials(double *v, double *partial, unsigned int *counter, double *out,
                                                          int mode /*0 sum*/)
 {
     __shared__ double sh[NV][32];
@@ -385,7 +386,7 @@ __device__ __forceinline__ void block_reduce_to_partials(double *v, double *part
         is_last = (done == gridDim.x - 1);
     }
     __syncthreads();
-    if (!is_last) return;
+    if (!is_last) return false;
     __threadfence();
     // last block: every thread sums a strided slice in ascending order, then a fixed tree over the threads
 #pragma unroll
@@ -405,8 +406,10 @@ __device__ __forceinline__ void block_reduce_to_partials(double *v, double *part
             out[i] = x;
         }
         *counter = 0;
+        return true;
     }
     (void)mode;
+    return false;
 }
 
 // calc_global element sums (model.py:1500-1507): sum_e Vel * {sig, eps, epl}
@@ -545,24 +548,29 @@ __global__ void __launch_bounds__(256) spmv_kernel(int64_t nrows, const int32_t 
                                                    double *__restrict__ y, const unsigned char *__restrict__ masked, int mode,
                                                    double *partial, unsigned int *counter, double *dot_out)
 {
+    // grid-stride over groups of 32 rows per block (8 lanes per row): a capped grid keeps the number of partial sums
+    // (and of atomics in the final reduction) small for the launch-bound CG loop
     const int sub = threadIdx.x & 7;
-    const int64_t r = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 3;
-    double s = 0., xy = 0.;
-    if (r < nrows) {
-        const int32_t b = rowptr[r], en = rowptr[r + 1];
-        for (int32_t i = b + sub; i < en; i += 8) s += __ldg(val + i) * __ldg(x + __ldg(col + i));
-    }
-    s += __shfl_xor_sync(0xffffffffu, s, 4);
-    s += __shfl_xor_sync(0xffffffffu, s, 2);
-    s += __shfl_xor_sync(0xffffffffu, s, 1);
-    if (r < nrows && sub == 0) {
-        double out;
-        const bool mk = masked && masked[r];
-        if (mode == 0) out = mk ? 0. : s;
-        else if (mode == 1) out = y[r] + s;
-        else out = mk ? 0. : rhs[r] - s;
-        y[r] = out;
-        if (partial) xy = x[r] * out;
+    double xy = 0.;
+    for (int64_t r0 = (int64_t)blockIdx.x * 32; r0 < nrows; r0 += (int64_t)gridDim.x * 32) {
+        const int64_t r = r0 + (threadIdx.x >> 3);
+        double s = 0.;
+        if (r < nrows) {
+            const int32_t b = rowptr[r], en = rowptr[r + 1];
+            for (int32_t i = b + sub; i < en; i += 8) s += __ldg(val + i) * __ldg(x + __ldg(col + i));
+        }
+        s += __shfl_xor_sync(0xffffffffu, s, 4);
+        s += __shfl_xor_sync(0xffffffffu, s, 2);
+        s += __shfl_xor_sync(0xffffffffu, s, 1);
+        if (r < nrows && sub == 0) {
+            double out;
+            const bool mk = masked && masked[r];
+            if (mode == 0) out = mk ? 0. : s;
+            else if (mode == 1) out = y[r] + s;
+            else out = mk ? 0. : rhs[r] - s;
+            y[r] = out;
+            if (partial) xy += x[r] * out;
+        }
     }
     if (partial) {
         double v[1] = {xy};
@@ -570,13 +578,15 @@ __global__ void __launch_bounds__(256) spmv_kernel(int64_t nrows, const int32_t 
     }
 }
 
-// CG scalars in device memory
+// CG scalars in device memory.  rz is double-buffered by iteration parity so that no kernel has to swap it:
+// step with parity P reads rz[P] (r.z before the step) and writes rz[1-P].
 struct CgScalars {
-    double pq, rz, rz_new, rr;
-    double target, active, iters;   // target = (rtol |b|)^2: once rr <= target the iteration freezes; iters counts real steps
+    double pq, rz[2], tmp[2], rr;
+    double target, iters;   // target = (rtol |b|)^2: once rr <= target the iteration freezes; iters counts real steps
 };
 
-// x += alpha p ; r -= alpha q ; z = r / diag ; partial sums of r.z and r.r   (alpha = rz / pq computed by every thread)
+// x += alpha p ; r -= alpha q ; z = r / diag ; r.z and r.r   (alpha = rz / pq computed by every thread)
+template <int P>
 __global__ void __launch_bounds__(256) cg_update_kernel(int64_t n, double *__restrict__ x, double *__restrict__ r,
                                                         double *__restrict__ z, const double *__restrict__ p,
                                                         const double *__restrict__ q, const double *__restrict__ diag,
@@ -584,7 +594,8 @@ __global__ void __launch_bounds__(256) cg_update_kernel(int64_t n, double *__res
                                                         unsigned int *counter)
 {
     // converged (or exactly solved: small systems reach r = 0 in a few steps) -> no further update, no 0/0
-    const double alpha = (sc->rr <= sc->target || sc->pq == 0.) ? 0. : sc->rz / sc->pq;
+    const bool live = sc->rr > sc->target && sc->pq != 0.;
+    const double alpha = live ? sc->rz[P] / sc->pq : 0.;
     double v[2] = {0., 0.};
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
         if (fixed[i]) continue;
@@ -595,31 +606,28 @@ __global__ void __launch_bounds__(256) cg_update_kernel(int64_t n, double *__res
         v[0] += ri * zi;
         v[1] += ri * ri;
     }
-    block_reduce_to_partials<2>(v, partial, counter, &sc->rz_new, 0);   // writes rz_new, rr (adjacent)
+    if (block_reduce_to_partials<2>(v, partial, counter, sc->tmp, 0)) {
+        // the one finalising thread: publish r.z for the next step, r.r, and count the step if it was a real one
+        sc->rz[1 - P] = sc->tmp[0];
+        if (live) { sc->rr = sc->tmp[1]; sc->iters += 1.; }
+    }
 }
 
-// beta = rz_new / rz ; p = z + beta p ; then rz <- rz_new (thread 0 of block 0 after a grid-wide read is unsafe, so
-// the swap is done by the next spmv's prologue kernel: cg_swap_kernel)
+// beta = rz_new / rz_old ; p = z + beta p
+template <int P>
 __global__ void __launch_bounds__(256) cg_p_kernel(int64_t n, double *__restrict__ p, const double *__restrict__ z,
                                                    const CgScalars *sc)
 {
-    const double beta = (sc->rr <= sc->target || sc->rz == 0.) ? 0. : sc->rz_new / sc->rz;
+    const double beta = (sc->rr <= sc->target || sc->rz[P] == 0.) ? 0. : sc->rz[1 - P] / sc->rz[P];
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
         p[i] = z[i] + beta * p[i];
 }
 
-__global__ void cg_swap_kernel(CgScalars *sc)
-{
-    if (sc->active != 0.) sc->iters += 1.;            // the step just finished was a real one
-    sc->active = (sc->rr > sc->target) ? 1. : 0.;     // NaN -> inactive as well
-    sc->rz = sc->rz_new;
-}
-
-// init: r = b (masked), z = r / diag, p = z, x = 0 ; partial sums r.z and r.r
+// init: r = b (masked), z = r / diag, p = z, x = 0 ; r.z -> rz[0], r.r -> rr ; target = rtol^2 r.r ; iters = 0
 __global__ void __launch_bounds__(256) cg_init_kernel(int64_t n, const double *__restrict__ b, double *__restrict__ x,
                                                       double *__restrict__ r, double *__restrict__ z, double *__restrict__ p,
                                                       const double *__restrict__ diag, const unsigned char *__restrict__ fixed,
-                                                      CgScalars *sc, double *partial, unsigned int *counter)
+                                                      CgScalars *sc, double rtol, double *partial, unsigned int *counter)
 {
     double v[2] = {0., 0.};
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
@@ -629,7 +637,14 @@ __global__ void __launch_bounds__(256) cg_init_kernel(int64_t n, const double *_
         v[0] += ri * zi;
         v[1] += ri * ri;
     }
-    block_reduce_to_partials<2>(v, partial, counter, &sc->rz_new, 0);
+    if (block_reduce_to_partials<2>(v, partial, counter, sc->tmp, 0)) {
+        sc->rz[0] = sc->tmp[0];
+        sc->rz[1] = 0.;
+        sc->rr = sc->tmp[1];
+        sc->target = rtol * rtol * sc->tmp[1];
+        sc->iters = 0.;
+        sc->pq = 0.;
+    }
 }
 
 __global__ void __launch_bounds__(256) diag_kernel(int64_t nrows, const int32_t *__restrict__ rowptr,
@@ -657,6 +672,12 @@ __global__ void __launch_bounds__(256) axpy_kernel(int64_t n, double a, const do
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) y[i] += a * x[i];
 }
 
+static inline unsigned spmv_grid(int64_t nrows, int sm)
+{
+    const int64_t g = (nrows + 31) / 32;   // 32 rows per block and pass
+    return (unsigned)std::max<int64_t>(1, std::min<int64_t>(g, (int64_t)sm * 8));
+}
+
 static inline unsigned vec_grid(int64_t n, int sm)
 {
     int64_t g = (n + 255) / 256;
@@ -671,7 +692,7 @@ cudaError_t launch_commit(const LaunchCtx &lc, int64_t Nel, int64_t Ndof, int NY
 {
     // u += du ; f += K du (1383-1384)
     axpy_kernel<<<vec_grid(Ndof, lc.sm_count), 256, 0, lc.stream>>>(Ndof, 1., du, u);
-    spmv_kernel<<<(unsigned)((Ndof * 8 + 255) / 256), 256, 0, lc.stream>>>(Ndof, rowptr, col, val, du, nullptr, f, nullptr, 1, nullptr,
+    spmv_kernel<<<spmv_grid(Ndof, lc.sm_count), 256, 0, lc.stream>>>(Ndof, rowptr, col, val, du, nullptr, f, nullptr, 1, nullptr,
                                                                           nullptr, nullptr);
     commit_elements_kernel<<<(unsigned)((Nel + 127) / 128), 128, 0, lc.stream>>>(Nel, NY, desc, u, du, elstiff, sig, eps, epl, res_sig,
                                                                                  res_depl, has_res);
@@ -728,6 +749,20 @@ cudaError_t launch_scf(const LaunchCtx &lc, const DevMat *hmats, int nmat, int64
 }
 
 // Jacobi-preconditioned CG on the masked operator.  b (rhs on free dofs) must already be in d_b.
+// One iteration = 3 launches (SpMV + p.q, update + r.z + r.r, direction); all scalars stay on the device.  A chunk of
+// `check_every` iterations is captured once into a CUDA graph (launch-bound loop: the kernels of a 10^5-dof system
+// run for a few microseconds each) and replayed; the host only reads the residual after every chunk.  Iterations
+// after convergence inside a chunk are frozen on the device (alpha = beta = 0), so the result does not depend on
+// the chunk length.
+struct CgGraphCache {
+    cudaGraphExec_t exec = nullptr;
+    int64_t n = 0;
+    const void *key[6] = {nullptr};
+    int chunk = 0;
+    cudaStream_t stream = nullptr;
+};
+static CgGraphCache g_cg;
+
 cudaError_t launch_cg(const LaunchCtx &lc, int64_t n, const int32_t *rowptr, const int32_t *col, const double *val,
                       const unsigned char *fixed, const double *b, double *x, double *r, double *z, double *p, double *q,
                       double *diag, double *partial, unsigned int *counter, void *d_sc, void *h_sc, double rtol, int max_iter,
@@ -736,32 +771,50 @@ cudaError_t launch_cg(const LaunchCtx &lc, int64_t n, const int32_t *rowptr, con
     CgScalars *sc = (CgScalars *)d_sc;
     CgScalars *hs = (CgScalars *)h_sc;
     const unsigned vg = vec_grid(n, lc.sm_count);
-    const unsigned sg = (unsigned)((n * 8 + 255) / 256);
+    const unsigned sg = spmv_grid(n, lc.sm_count);
     cudaError_t e;
+    check_every = std::max(2, check_every & ~1);   // even: the rz ping-pong returns to parity 0 at chunk end
     diag_kernel<<<(unsigned)((n + 255) / 256), 256, 0, lc.stream>>>(n, rowptr, col, val, diag);
-    cg_init_kernel<<<vg, 256, 0, lc.stream>>>(n, b, x, r, z, p, diag, fixed, sc, partial, counter);
-    cg_swap_kernel<<<1, 1, 0, lc.stream>>>(sc);
-    *launches += 3;
+    cg_init_kernel<<<vg, 256, 0, lc.stream>>>(n, b, x, r, z, p, diag, fixed, sc, rtol, partial, counter);
+    *launches += 2;
     if ((e = cudaMemcpyAsync(hs, sc, sizeof(CgScalars), cudaMemcpyDeviceToHost, lc.stream)) != cudaSuccess) return e;
     if ((e = cudaStreamSynchronize(lc.stream)) != cudaSuccess) return e;
     const double bb = hs->rr;
     *iters = 0;
     *relres = 0.;
     if (bb == 0.) return cudaSuccess;
-    const double target = rtol * rtol * bb;
-    const double init[3] = {target, 1., 0.};   // target, active, iters
-    if ((e = cudaMemcpyAsync(&sc->target, init, sizeof init, cudaMemcpyHostToDevice, lc.stream)) != cudaSuccess) return e;
+    const double target = hs->target;
+
+    auto enqueue_chunk = [&]() {
+        for (int c = 0; c < check_every; c += 2) {
+            spmv_kernel<<<sg, 256, 0, lc.stream>>>(n, rowptr, col, val, p, nullptr, q, fixed, 0, partial, counter, &sc->pq);
+            cg_update_kernel<0><<<vg, 256, 0, lc.stream>>>(n, x, r, z, p, q, diag, fixed, sc, partial, counter);
+            cg_p_kernel<0><<<vg, 256, 0, lc.stream>>>(n, p, z, sc);
+            spmv_kernel<<<sg, 256, 0, lc.stream>>>(n, rowptr, col, val, p, nullptr, q, fixed, 0, partial, counter, &sc->pq);
+            cg_update_kernel<1><<<vg, 256, 0, lc.stream>>>(n, x, r, z, p, q, diag, fixed, sc, partial, counter);
+            cg_p_kernel<1><<<vg, 256, 0, lc.stream>>>(n, p, z, sc);
+        }
+    };
+    const void *key[6] = {rowptr, val, x, fixed, d_sc, partial};
+    bool cached = g_cg.exec && g_cg.n == n && g_cg.chunk == check_every && g_cg.stream == lc.stream;
+    for (int i = 0; i < 6 && cached; i++) cached = (g_cg.key[i] == key[i]);
+    if (!cached) {
+        if (g_cg.exec) { cudaGraphExecDestroy(g_cg.exec); g_cg.exec = nullptr; }
+        cudaGraph_t graph = nullptr;
+        if ((e = cudaStreamBeginCapture(lc.stream, cudaStreamCaptureModeThreadLocal)) != cudaSuccess) return e;
+        enqueue_chunk();
+        if ((e = cudaStreamEndCapture(lc.stream, &graph)) != cudaSuccess) return e;
+        e = cudaGraphInstantiate(&g_cg.exec, graph, 0);
+        cudaGraphDestroy(graph);
+        if (e != cudaSuccess) { g_cg.exec = nullptr; return e; }
+        g_cg.n = n; g_cg.chunk = check_every; g_cg.stream = lc.stream;
+        for (int i = 0; i < 6; i++) g_cg.key[i] = key[i];
+    }
     int it = 0;
     while (it < max_iter) {
-        int chunk = std::min(check_every, max_iter - it);
-        for (int c = 0; c < chunk; c++) {
-            spmv_kernel<<<sg, 256, 0, lc.stream>>>(n, rowptr, col, val, p, nullptr, q, fixed, 0, partial, counter, &sc->pq);
-            cg_update_kernel<<<vg, 256, 0, lc.stream>>>(n, x, r, z, p, q, diag, fixed, sc, partial, counter);
-            cg_p_kernel<<<vg, 256, 0, lc.stream>>>(n, p, z, sc);
-            cg_swap_kernel<<<1, 1, 0, lc.stream>>>(sc);
-        }
-        *launches += 4 * (int64_t)chunk;
-        it += chunk;
+        if ((e = cudaGraphLaunch(g_cg.exec, lc.stream)) != cudaSuccess) return e;
+        *launches += 3 * (int64_t)check_every;
+        it += check_every;
         if ((e = cudaMemcpyAsync(hs, sc, sizeof(CgScalars), cudaMemcpyDeviceToHost, lc.stream)) != cudaSuccess) return e;
         if ((e = cudaStreamSynchronize(lc.stream)) != cudaSuccess) return e;
         *relres = sqrt(hs->rr / bb);
@@ -771,10 +824,16 @@ cudaError_t launch_cg(const LaunchCtx &lc, int64_t n, const int32_t *rowptr, con
     return cudaGetLastError();
 }
 
+void cg_graph_reset()
+{
+    if (g_cg.exec) cudaGraphExecDestroy(g_cg.exec);
+    g_cg = CgGraphCache();
+}
+
 cudaError_t launch_spmv(const LaunchCtx &lc, int64_t n, const int32_t *rowptr, const int32_t *col, const double *val, const double *x,
                         const double *rhs, double *y, const unsigned char *masked, int mode, int64_t *launches)
 {
-    spmv_kernel<<<(unsigned)((n * 8 + 255) / 256), 256, 0, lc.stream>>>(n, rowptr, col, val, x, rhs, y, masked, mode, nullptr, nullptr,
+    spmv_kernel<<<spmv_grid(n, lc.sm_count), 256, 0, lc.stream>>>(n, rowptr, col, val, x, rhs, y, masked, mode, nullptr, nullptr,
                                                                        nullptr);
     (*launches)++;
     return cudaGetLastError();

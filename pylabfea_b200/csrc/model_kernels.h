@@ -41,6 +41,7 @@ cudaError_t launch_cg(const LaunchCtx &lc, int64_t n, const int32_t *rowptr, con
                       int check_every, int *iters, double *relres, int64_t *launches);
 cudaError_t launch_spmv(const LaunchCtx &lc, int64_t n, const int32_t *rowptr, const int32_t *col, const double *val, const double *x,
                         const double *rhs, double *y, const unsigned char *masked, int mode, int64_t *launches);
+void cg_graph_reset();   // drops the cached CUDA graph of the CG iteration chunk (call before freeing its buffers)
 cudaError_t launch_merge_du(const LaunchCtx &lc, int64_t n, const double *x, const double *du_bc, const unsigned char *fixed, double *du,
                             int64_t *launches);
 

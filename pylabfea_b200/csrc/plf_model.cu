@@ -33,6 +33,7 @@ static int dalloc(plf_ctx *ctx, T **p, size_t n)
 
 void model_free(plf_ctx *c)
 {
+    cg_graph_reset();
     cudaFree(c->d_desc); cudaFree(c->d_elstiff); cudaFree(c->d_sig); cudaFree(c->d_eps); cudaFree(c->d_epl);
     cudaFree(c->d_res_sig); cudaFree(c->d_res_depl); cudaFree(c->d_fyld); cudaFree(c->d_nsteps); cudaFree(c->d_branch);
     cudaFree(c->d_has_res); cudaFree(c->d_u); cudaFree(c->d_du); cudaFree(c->d_f); cudaFree(c->d_rowptr); cudaFree(c->d_col);
