@@ -247,7 +247,60 @@ __device__ __forceinline__ int hill_passA(const DevMat &m, double *s, const doub
 //   W   : accumulator policy (WRegs / WShared) for sum_k ca ca^T / hh (+ correction blocks)
 //   gs  : out, symmetric 21.
 // Returns branch code 2 (| 4 when a radial-return correction fired).
-template <class WAcc>
+// Fast modes of the sub-step loop, chosen on the host for single-material batches (the flags are compile-time, so the
+// uniform branches and the dead general-case code disappear from the loop):
+//   FM 0 : general (any CV, Drucker / LHS terms)
+//   FM 1 : block-structured symmetric CV, no hydrostatic term            (DevMat.cv_block && cv_sym && !has_d)
+//   FM 2 : FM 1 and all Hill parameters equal 1 (J2): q = 1.5 |dev s|^2 + 3 |shear|^2, a = 1.5 dev(s) / seq
+template <int FM>
+__device__ __forceinline__ void cv_mul_t(const DevMat &m, const double *v, double *o)
+{
+    if (FM > 0) {
+        const double *C = m.CV;
+        o[0] = C[0] * v[0] + C[1] * v[1] + C[2] * v[2];
+        o[1] = C[6] * v[0] + C[7] * v[1] + C[8] * v[2];
+        o[2] = C[12] * v[0] + C[13] * v[1] + C[14] * v[2];
+        o[3] = C[21] * v[3];
+        o[4] = C[28] * v[4];
+        o[5] = C[35] * v[5];
+    } else {
+        cv_mul(m, v, o);
+    }
+}
+// seq(s), 1/seq(s) and the gradient direction for the NEXT sub-step share the deviator
+template <int FM>
+__device__ __forceinline__ void seq_inv_t(const DevMat &m, const double *s, double &seq, double &iseq)
+{
+    if (FM == 2) {
+        const double p = (s[0] + s[1] + s[2]) * (1. / 3.);
+        const double s0 = s[0] - p, s1 = s[1] - p, s2 = s[2] - p;
+        const double q = 1.5 * (s0 * s0 + s1 * s1 + s2 * s2) + 3. * (s[3] * s[3] + s[4] * s[4] + s[5] * s[5]);
+        const double rs = q > 0. ? fast_rsqrt(q) : 1. / 0.;
+        seq = q > 0. ? q * rs : 0.;
+        iseq = rs;
+    } else if (FM == 1) {
+        const double q = hill_q(m, s);
+        const double rs = q > 0. ? fast_rsqrt(q) : 1. / 0.;
+        seq = q > 0. ? q * rs : 0.;
+        iseq = rs;
+    } else {
+        hill_seq_inv(m, s, seq, iseq);
+    }
+}
+template <int FM>
+__device__ __forceinline__ void grad_t(const DevMat &m, const double *s, double iseq, double *a)
+{
+    if (FM == 2) {
+        const double p = (s[0] + s[1] + s[2]) * (1. / 3.);
+        const double c15 = 1.5 * iseq, c3 = 3. * iseq;
+        a[0] = (s[0] - p) * c15; a[1] = (s[1] - p) * c15; a[2] = (s[2] - p) * c15;
+        a[3] = s[3] * c3; a[4] = s[4] * c3; a[5] = s[5] * c3;
+    } else {
+        hill_grad(m, s, iseq, a);
+    }
+}
+
+template <int FM, class WAcc>
 __device__ __forceinline__ int hill_passB(const DevMat &m, double *s, double *epd, const double *de, WAcc &W, double *gs, double &fy)
 {
     HillStep P;
@@ -255,7 +308,7 @@ __device__ __forceinline__ int hill_passB(const DevMat &m, double *s, double *ep
     const double inv = 1. / (double)PLF_MAXIT;
 #pragma unroll
     for (int k = 0; k < 6; k++) P.dr[k] = P.dr[k] / (double)PLF_MAXIT;   // 290
-    cv_mul(m, P.dr, P.cdr);
+    cv_mul_t<FM>(m, P.dr, P.cdr);
 #pragma unroll
     for (int k = 0; k < 21; k++) W.set(k, 0.);
     // q(s + cdr) = q(s) + s . gq + qc: the sub-step's elastic-trial yield check without re-evaluating the form
@@ -263,7 +316,7 @@ __device__ __forceinline__ int hill_passB(const DevMat &m, double *s, double *ep
     hill_qgrad(m, P.cdr, gq);
     const double qc = hill_q(m, P.cdr);
     double seq, iseq;
-    hill_seq_inv(m, s, seq, iseq);
+    seq_inv_t<FM>(m, s, seq, iseq);
     bool corrected = false;
     const double ythr = P.sflow0 + PLF_YF_TOLERANCE;
     const double ythr2 = ythr * ythr;
@@ -271,7 +324,7 @@ __device__ __forceinline__ int hill_passB(const DevMat &m, double *s, double *ep
     for (int it = 0; it < PLF_MAXIT; it++) {
         double a[6], ca[6], dd[6];
         bool yplus;
-        if (m.has_d) {
+        if (FM == 0 && m.has_d) {
             double st[6];
 #pragma unroll
             for (int k = 0; k < 6; k++) st[k] = s[k] + P.cdr[k];
@@ -282,15 +335,15 @@ __device__ __forceinline__ int hill_passB(const DevMat &m, double *s, double *ep
             for (int k = 0; k < 6; k++) qst = fma(s[k], gq[k], qst);
             yplus = qst > ythr2;
         }
-        hill_grad(m, s, iseq, a);
-        cv_mul(m, a, ca);
+        grad_t<FM>(m, s, iseq, a);
+        cv_mul_t<FM>(m, a, ca);
         double hh = m.khard, acd = 0.;
 #pragma unroll
         for (int k = 0; k < 6; k++) { hh = fma(a[k], ca[k], hh); acd = fma(a[k], P.cdr[k], acd); }
         // (CV a) . deps_r == a . (CV deps_r) for a symmetric CV: the second dot product (and deps_r itself) is only
         // needed for a non-symmetric user-supplied stiffness
         double cadr = acd;
-        if (!m.cv_sym) {
+        if (FM == 0 && !m.cv_sym) {
             cadr = 0.;
 #pragma unroll
             for (int k = 0; k < 6; k++) cadr = fma(ca[k], P.dr[k], cadr);
@@ -303,7 +356,7 @@ __device__ __forceinline__ int hill_passB(const DevMat &m, double *s, double *ep
             dd[k] = lam * a[k];
             s[k] += P.cdr[k] - ca[k] * q;
         }
-        hill_seq_inv(m, s, seq, iseq);
+        seq_inv_t<FM>(m, s, seq, iseq);
         double eplt[6];
 #pragma unroll
         for (int k = 0; k < 6; k++) eplt[k] = epd[k] + dd[k];
@@ -327,7 +380,7 @@ __device__ __forceinline__ int hill_passB(const DevMat &m, double *s, double *ep
             W.set(sym_idx(1, 1), W.get(sym_idx(1, 1)) + x[1]);
             W.set(sym_idx(1, 2), W.get(sym_idx(1, 2)) + x[3]);
             W.set(sym_idx(2, 2), W.get(sym_idx(2, 2)) + x[2]);
-            hill_seq_inv(m, s, seq, iseq);
+            seq_inv_t<FM>(m, s, seq, iseq);
         }
 #pragma unroll
         for (int i = 0; i < 6; i++) {

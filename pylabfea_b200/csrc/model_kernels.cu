@@ -195,7 +195,7 @@ __global__ void __launch_bounds__(128) sweep_hill_kernel(int64_t n, int NY, int 
 #pragma unroll
                     for (int k = 0; k < 6; k++) epd[k] = ep[k];
                     WRegs W;
-                    br = hill_passB(m, s, epd, de, W, gs, fyv);
+                    br = hill_passB<0>(m, s, epd, de, W, gs, fyv);
 #pragma unroll
                     for (int k = 0; k < 6; k++) dp[k] = epd[k] - ep[k];
                     ns = PLF_MAXIT - 1;

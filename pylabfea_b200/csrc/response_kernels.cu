@@ -204,7 +204,7 @@ __global__ void __launch_bounds__(RB, 3) response_passA_kernel(int64_t n, const 
 
 // WSMEM: the 21-entry tangent accumulator lives in shared memory ([k][thread], conflict free) instead of registers,
 // which lets 4 blocks (16 warps) share an SM instead of 2.
-template <bool WSMEM, int MINB, bool SINGLE>
+template <bool WSMEM, int MINB, bool SINGLE, int FM>
 __global__ void __launch_bounds__(RB, MINB) response_passB_kernel(const int32_t *__restrict__ mat_id, const double *__restrict__ sig,
                                                             const double *__restrict__ epl, const double *__restrict__ deps,
                                                             double *__restrict__ fy, double *__restrict__ sig_out,
@@ -229,10 +229,10 @@ __global__ void __launch_bounds__(RB, MINB) response_passB_kernel(const int32_t 
         }
         if (WSMEM) {
             WShared W{s_W + threadIdx.x, RB};
-            hill_passB(m, s, ep, de, W, gs, fyv);
+            hill_passB<FM>(m, s, ep, de, W, gs, fyv);
         } else {
             WRegs W;
-            hill_passB(m, s, ep, de, W, gs, fyv);
+            hill_passB<FM>(m, s, ep, de, W, gs, fyv);
         }
         // ep now holds epl + depl; the increment is recovered against the (L2-resident) input record
 #pragma unroll
@@ -506,18 +506,26 @@ cudaError_t launch_response(const LaunchCtx &lc, const DevMat *hmats, int nmat, 
                 response_passA_kernel<false><<<agrid, RB, k1a_smem(), lc.stream>>>(n, mat_id, sig, epl, deps, fy, sig_out, depl,
                                                                                    ctan, nsteps, worklist, work_count);
             int64_t bgrid = std::min<int64_t>((int64_t)lc.sm_count * 8, (int64_t)grid);
-#define PASSB(W, M, S)                                                                                                     \
-    response_passB_kernel<W, M, S><<<(unsigned)bgrid, RB, 0, lc.stream>>>(mat_id, sig, epl, deps, fy, sig_out, depl, ctan, \
-                                                                          nsteps, worklist, work_count)
+#define PASSB(W, M, S, F)                                                                                                     \
+    response_passB_kernel<W, M, S, F><<<(unsigned)bgrid, RB, 0, lc.stream>>>(mat_id, sig, epl, deps, fy, sig_out, depl, ctan, \
+                                                                             nsteps, worklist, work_count)
             // variant: 0 = accumulator in registers, 2 blocks per SM; 1 = shared memory, 4 blocks; 2 = registers, 3 blocks
-            if (single) {
-                switch (lc.passb_wsmem) {
-                case 1: PASSB(true, 4, true); break;
-                case 2: PASSB(false, 3, true); break;
-                default: PASSB(false, 2, true); break;
-                }
+            // fast mode (hill_fast.cuh): 1 = block-structured symmetric CV without hydrostatic term, 2 = additionally J2
+            int fm = 0;
+            if (single && hmats[0].cv_block && hmats[0].cv_sym && !hmats[0].has_d) {
+                fm = 2;
+                for (int k = 0; k < 6; k++) if (hmats[0].hill[k] != 1.) fm = 1;
+            }
+            if (single && lc.passb_wsmem == 1) {
+                PASSB(true, 4, true, 0);
+            } else if (single && lc.passb_wsmem == 0) {
+                PASSB(false, 2, true, 0);
+            } else if (single) {
+                if (fm == 2) PASSB(false, 3, true, 2);
+                else if (fm == 1) PASSB(false, 3, true, 1);
+                else PASSB(false, 3, true, 0);
             } else {
-                PASSB(false, 2, false);
+                PASSB(false, 2, false, 0);
             }
 #undef PASSB
             *launches += 2;
