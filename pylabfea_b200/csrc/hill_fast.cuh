@@ -148,20 +148,38 @@ struct HillStep {
     bool split;
 };
 
+// fast-mode helpers (defined below, see "Fast modes")
+template <int FM> __device__ __forceinline__ void cv_mul_t(const DevMat &m, const double *v, double *o);
+template <int FM> __device__ __forceinline__ void seq_inv_t(const DevMat &m, const double *s, double &seq, double &iseq);
+template <int FM> __device__ __forceinline__ void grad_t(const DevMat &m, const double *s, double iseq, double *a);
+template <int FM>
+__device__ __forceinline__ bool seq_gt_t(const DevMat &m, const double *s, double thr)
+{
+    if (FM == 0) return hill_seq_gt(m, s, thr);
+    if (FM == 2) {
+        const double p = (s[0] + s[1] + s[2]) * (1. / 3.);
+        const double s0 = s[0] - p, s1 = s[1] - p, s2 = s[2] - p;
+        const double q = 1.5 * (s0 * s0 + s1 * s1 + s2 * s2) + 3. * (s[3] * s[3] + s[4] * s[4] + s[5] * s[5]);
+        return thr < 0. || q > thr * thr;
+    }
+    return thr < 0. || hill_q(m, s) > thr * thr;
+}
+
 // Elastic predictor and elastic/plastic split (material.py:243-274).  Returns true when the step is purely elastic
 // (s updated, fy set).  Otherwise s is the stress at the start of the plastic part and P describes that part.
+template <int FM>
 __device__ __forceinline__ bool hill_prelude(const DevMat &m, double *s, const double *ep, const double *de, HillStep &P, double &fy)
 {
     P.sflow0 = m.sy + (m.khard != 0. ? eps_eq6(ep) * m.khard : 0.);
     P.toler = PLF_YF_TOLERANCE * P.sflow0;
     double cd[6], st[6];
-    cv_mul(m, de, cd);
+    cv_mul_t<FM>(m, de, cd);
 #pragma unroll
     for (int k = 0; k < 6; k++) st[k] = s[k] + cd[k];
-    if (!hill_seq_gt(m, st, P.sflow0 + P.toler) ) {
+    if (!seq_gt_t<FM>(m, st, P.sflow0 + P.toler) ) {
         // fy1 < toler would be the exact test; seq == sflow0 + toler to the last bit is treated as elastic too
         double seq, iseq;
-        hill_seq_inv(m, st, seq, iseq);
+        seq_inv_t<FM>(m, st, seq, iseq);
         fy = seq - P.sflow0;
         if (fy < P.toler) {
 #pragma unroll
@@ -172,12 +190,12 @@ __device__ __forceinline__ bool hill_prelude(const DevMat &m, double *s, const d
     P.st_scal = 1.;
     P.split = false;
     double seq0, iseq0;
-    hill_seq_inv(m, s, seq0, iseq0);
+    seq_inv_t<FM>(m, s, seq0, iseq0);
     const double fy0 = seq0 - P.sflow0;   // 259
     if (fy0 < PLF_SPLIT_FY0) {            // 260-270
         P.split = true;
         double seqd, iseqd;
-        hill_seq_inv(m, cd, seqd, iseqd);
+        seq_inv_t<FM>(m, cd, seqd, iseqd);
         P.st_scal += fy0 / seqd;
         const double c = 1. - P.st_scal;
 #pragma unroll
@@ -188,10 +206,10 @@ __device__ __forceinline__ bool hill_prelude(const DevMat &m, double *s, const d
         double cdel[6], del[6];
 #pragma unroll
         for (int k = 0; k < 6; k++) del[k] = de[k] * c;
-        cv_mul(m, del, cdel);
+        cv_mul_t<FM>(m, del, cdel);
 #pragma unroll
         for (int k = 0; k < 6; k++) s[k] += cdel[k];
-        cv_mul(m, P.dr, P.cdr);
+        cv_mul_t<FM>(m, P.dr, P.cdr);
     } else {
 #pragma unroll
         for (int k = 0; k < 6; k++) { P.dr[k] = de[k]; P.cdr[k] = cd[k]; }
@@ -201,6 +219,7 @@ __device__ __forceinline__ bool hill_prelude(const DevMat &m, double *s, const d
 
 // Pass A.  Returns 0 (elastic), 1 (plastic, single step) or -1 (needs the 50-sub-step loop: deferred).
 // Tangent is returned in factored form: ct_ij = CV_ij * tc - ca_i ca_j * tw   (elastic: tc = 1, tw = 0).
+template <int FM>
 __device__ __forceinline__ int hill_passA(const DevMat &m, double *s, const double *ep, const double *de, double *dp, double *ca,
                                           double &tc, double &tw, double &fy)
 {
@@ -208,18 +227,24 @@ __device__ __forceinline__ int hill_passA(const DevMat &m, double *s, const doub
 #pragma unroll
     for (int k = 0; k < 6; k++) { dp[k] = 0.; ca[k] = 0.; }
     tc = 1.; tw = 0.;
-    if (hill_prelude(m, s, ep, de, P, fy)) return 0;
+    if (hill_prelude<FM>(m, s, ep, de, P, fy)) return 0;
     // trial step with the full remaining increment (277-285) == the only step when nsteps = 1 (295-308)
     double st[6], a[6], seq, iseq;
 #pragma unroll
     for (int k = 0; k < 6; k++) st[k] = s[k] + P.cdr[k];
-    const bool yplus = hill_seq_gt(m, st, P.sflow0 + PLF_YF_TOLERANCE);   // epl_dot 1031-1041
-    hill_seq_inv(m, s, seq, iseq);
-    hill_grad(m, s, iseq, a);
-    cv_mul(m, a, ca);
+    const bool yplus = seq_gt_t<FM>(m, st, P.sflow0 + PLF_YF_TOLERANCE);   // epl_dot 1031-1041
+    seq_inv_t<FM>(m, s, seq, iseq);
+    grad_t<FM>(m, s, iseq, a);
+    cv_mul_t<FM>(m, a, ca);
     double hh = m.khard, acd = 0., cadr = 0.;
 #pragma unroll
-    for (int k = 0; k < 6; k++) { hh += a[k] * ca[k]; acd += a[k] * P.cdr[k]; cadr += ca[k] * P.dr[k]; }
+    for (int k = 0; k < 6; k++) { hh += a[k] * ca[k]; acd += a[k] * P.cdr[k]; }
+    cadr = acd;   // symmetric CV (see hill_passB)
+    if (FM == 0 && !m.cv_sym) {
+        cadr = 0.;
+#pragma unroll
+        for (int k = 0; k < 6; k++) cadr += ca[k] * P.dr[k];
+    }
     const double ihh = fast_rcp(hh);
     const double lam = yplus ? acd * ihh : 0.;
     const double q = cadr * ihh;
@@ -230,7 +255,7 @@ __device__ __forceinline__ int hill_passA(const DevMat &m, double *s, const doub
         eplt[k] = ep[k] + dp[k];
         st[k] = s[k] + (P.cdr[k] - ca[k] * q);
     }
-    hill_seq_inv(m, st, seq, iseq);
+    seq_inv_t<FM>(m, st, seq, iseq);
     fy = seq - (m.sy + (m.khard != 0. ? eps_eq6(eplt) * m.khard : 0.));
     if (fy > P.toler) return -1;   // 288-291: subdivide
 #pragma unroll
@@ -304,7 +329,7 @@ template <int FM, class WAcc>
 __device__ __forceinline__ int hill_passB(const DevMat &m, double *s, double *epd, const double *de, WAcc &W, double *gs, double &fy)
 {
     HillStep P;
-    hill_prelude(m, s, epd, de, P, fy);   // cannot be elastic: pass A deferred this element
+    hill_prelude<FM>(m, s, epd, de, P, fy);   // cannot be elastic: pass A deferred this element
     const double inv = 1. / (double)PLF_MAXIT;
 #pragma unroll
     for (int k = 0; k < 6; k++) P.dr[k] = P.dr[k] / (double)PLF_MAXIT;   // 290

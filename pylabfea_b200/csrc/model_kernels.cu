@@ -185,7 +185,7 @@ __global__ void __launch_bounds__(128) sweep_hill_kernel(int64_t n, int NY, int 
                 element_strain(c_geom[d >> 16], NY, e, du, de);
                 if (MODE == 1) {
                     double ca[6], tc, tw;
-                    br = hill_passA(m, s, ep, de, dp, ca, tc, tw, fyv);
+                    br = hill_passA<0>(m, s, ep, de, dp, ca, tc, tw, fyv);
 #pragma unroll
                     for (int i = 0; i < 6; i++)
 #pragma unroll

@@ -105,7 +105,7 @@ __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_gr
 // next tile are already in flight (cp.async into the second shared-memory buffer), so HBM reads overlap the math and
 // the write-back instead of being exposed at the top of every block (ncu of the non-pipelined version:
 // long_scoreboard on the staging loads dominated, 39 % DRAM throughput).
-template <bool SINGLE>
+template <bool SINGLE, int FM>
 __global__ void __launch_bounds__(RB, 3) response_passA_kernel(int64_t n, const int32_t *__restrict__ mat_id,
                                                             const double *__restrict__ sig, const double *__restrict__ epl,
                                                             const double *__restrict__ deps, double *__restrict__ fy,
@@ -174,7 +174,7 @@ __global__ void __launch_bounds__(RB, 3) response_passA_kernel(int64_t n, const 
 #pragma unroll
                 for (int k = 0; k < 6; k++) { s[k] += t[k]; dp[k] = 0.; ca[k] = 0.; }
             } else {
-                br = hill_passA(m, s, ep, de, dp, ca, tc, tw, fyv);
+                br = hill_passA<FM>(m, s, ep, de, dp, ca, tc, tw, fyv);
             }
             if (br < 0) {
                 defer = true;
@@ -471,9 +471,13 @@ static size_t svc_smem(const DevMat &m) { return sizeof(double) * 7 * (size_t)m.
 cudaError_t response_init()
 {
     cudaError_t e;
-    e = cudaFuncSetAttribute(response_passA_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)k1a_smem());
+    e = cudaFuncSetAttribute(response_passA_kernel<true, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)k1a_smem());
     if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(response_passA_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)k1a_smem());
+    e = cudaFuncSetAttribute(response_passA_kernel<true, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)k1a_smem());
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(response_passA_kernel<true, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)k1a_smem());
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(response_passA_kernel<false, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)k1a_smem());
     if (e != cudaSuccess) return e;
     e = cudaFuncSetAttribute(response_generic_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)k1_smem());
     if (e != cudaSuccess) return e;
@@ -499,23 +503,26 @@ cudaError_t launch_response(const LaunchCtx &lc, const DevMat *hmats, int nmat, 
             const bool single = (nmat == 1);
             // persistent: 3 blocks per SM, each walking tiles with a double-buffered cp.async prefetch
             const unsigned agrid = (unsigned)std::min<int64_t>((int64_t)lc.sm_count * 3, (int64_t)grid);
-            if (single)
-                response_passA_kernel<true><<<agrid, RB, k1a_smem(), lc.stream>>>(n, mat_id, sig, epl, deps, fy, sig_out, depl, ctan,
-                                                                                  nsteps, worklist, work_count);
-            else
-                response_passA_kernel<false><<<agrid, RB, k1a_smem(), lc.stream>>>(n, mat_id, sig, epl, deps, fy, sig_out, depl,
-                                                                                   ctan, nsteps, worklist, work_count);
+            // fast mode (hill_fast.cuh): 1 = block-structured symmetric CV without hydrostatic term, 2 = additionally J2
+            int fm = 0;
+            if (single && hmats[0].kind == PLF_MAT_HILL && hmats[0].cv_block && hmats[0].cv_sym && !hmats[0].has_d) {
+                fm = 2;
+                for (int k = 0; k < 6; k++) if (hmats[0].hill[k] != 1.) fm = 1;
+            }
+            if (lc.passb_wsmem != 2) fm = 0;   // the A/B variants 0 and 1 keep the general code path
+#define PASSA(S, F)                                                                                                         \
+    response_passA_kernel<S, F><<<agrid, RB, k1a_smem(), lc.stream>>>(n, mat_id, sig, epl, deps, fy, sig_out, depl, ctan, \
+                                                                      nsteps, worklist, work_count)
+            if (!single) PASSA(false, 0);
+            else if (fm == 2) PASSA(true, 2);
+            else if (fm == 1) PASSA(true, 1);
+            else PASSA(true, 0);
+#undef PASSA
             int64_t bgrid = std::min<int64_t>((int64_t)lc.sm_count * 8, (int64_t)grid);
 #define PASSB(W, M, S, F)                                                                                                     \
     response_passB_kernel<W, M, S, F><<<(unsigned)bgrid, RB, 0, lc.stream>>>(mat_id, sig, epl, deps, fy, sig_out, depl, ctan, \
                                                                              nsteps, worklist, work_count)
             // variant: 0 = accumulator in registers, 2 blocks per SM; 1 = shared memory, 4 blocks; 2 = registers, 3 blocks
-            // fast mode (hill_fast.cuh): 1 = block-structured symmetric CV without hydrostatic term, 2 = additionally J2
-            int fm = 0;
-            if (single && hmats[0].cv_block && hmats[0].cv_sym && !hmats[0].has_d) {
-                fm = 2;
-                for (int k = 0; k < 6; k++) if (hmats[0].hill[k] != 1.) fm = 1;
-            }
             if (single && lc.passb_wsmem == 1) {
                 PASSB(true, 4, true, 0);
             } else if (single && lc.passb_wsmem == 0) {
