@@ -54,7 +54,7 @@ def j2_material():
     return m, CV
 
 
-def synth_states(N, seed, correlated=True):
+def synth_states(N, seed, correlated=True, sy=SY, khard=KHARD, deps_scale=1.):
     """Element states for an N x N mesh (element id = j*N + k).  Seeded, no file I/O.
 
     correlated: a stress field as a loaded inclusion problem produces it -- uniaxial-y dominated stress whose level
@@ -85,7 +85,7 @@ def synth_states(N, seed, correlated=True):
     sig[:, 2] = NU * 0.5 * (sig[:, 0] + sig[:, 1]) * (0.5 + 0.5 * smooth().ravel())   # partial plane-strain constraint
     d01, d12, d20 = sig[:, 0] - sig[:, 1], sig[:, 1] - sig[:, 2], sig[:, 2] - sig[:, 0]
     seq = np.sqrt(0.5 * (d01 ** 2 + d12 ** 2 + d20 ** 2 + 6 * sig[:, 5] ** 2))
-    sflow = SY + KHARD * peeq.ravel()
+    sflow = sy + khard * peeq.ravel()
     sig *= (level.ravel() * sflow / seq)[:, None]
     epl = peeq.ravel()[:, None] * np.array([-.5, 1., -.5, 0., 0., 0.])[None, :]
     deps = np.zeros((n, 6))
@@ -93,7 +93,7 @@ def synth_states(N, seed, correlated=True):
     deps[:, 1] = eyy
     deps[:, 0] = -0.4 * eyy * (1. + 0.3 * smooth().ravel())
     deps[:, 5] = 2.e-4 * smooth().ravel()
-    deps *= (1. + 0.05 * rng.standard_normal((n, 1)))
+    deps *= deps_scale * (1. + 0.05 * rng.standard_normal((n, 1)))
     if not correlated:
         p = rng.permutation(n)
         sig, epl, deps = sig[p], epl[p], deps[p]
