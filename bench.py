@@ -260,6 +260,7 @@ def main():
     ap.add_argument('--compact', type=int, default=1)
     ap.add_argument('--passb-wsmem', type=int, default=2)
     ap.add_argument('--assembly-tiled', type=int, default=2)
+    ap.add_argument('--opt', action='append', default=[], help='extra plf_set_option key=value (A/B measurements)')
     args = ap.parse_args()
 
     rank = int(os.environ.get('RANK', '0'))
@@ -289,6 +290,9 @@ def main():
     ctx.set_option('compact', args.compact)
     ctx.set_option('passb_wsmem', args.passb_wsmem)
     ctx.set_option('assembly_tiled', args.assembly_tiled)
+    for kv in args.opt:
+        k, v = kv.split('=')
+        ctx.set_option(k, int(v))
     N = args.mesh
     Nel = N * N
     mat, CV = j2_material()
@@ -420,8 +424,8 @@ def main():
     asm_achieved = BYTES_PER_ASSEMBLED * Nel / (asm_ms_max * 1e-3) / 1e9
     asm_kernel = {0: 'assemble_rows_kernel', 1: 'assemble_tile_kernel', 2: 'assemble_rows_staged_kernel'}[args.assembly_tiled]
     roofline = {'bound': 'hbm',
-                'kernel': 'response_passA_kernel + response_passB_kernel (return mapping, compacted 50-sub-step pass)'
-                if args.compact else 'response_generic_kernel',
+                'kernel': {1: 'response_passA_kernel + response_passB_kernel (return mapping, compacted 50-sub-step pass)',
+                           0: 'response_generic_kernel'}[args.compact],
                 'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak,
                 'peak_source': 'MEASURED_PEAKS.json hbm_gbs (of measured)' if peaks else 'fallback 6650 GB/s (of fallback)',
                 'algorithmic_bytes': BYTES_PER_UPDATE * Nel,

@@ -156,7 +156,7 @@ template <int FM>
 __device__ __forceinline__ bool seq_gt_t(const DevMat &m, const double *s, double thr)
 {
     if (FM == 0) return hill_seq_gt(m, s, thr);
-    if (FM == 2) {
+    if (FM >= 2) {
         const double p = (s[0] + s[1] + s[2]) * (1. / 3.);
         const double s0 = s[0] - p, s1 = s[1] - p, s2 = s[2] - p;
         const double q = 1.5 * (s0 * s0 + s1 * s1 + s2 * s2) + 3. * (s[3] * s[3] + s[4] * s[4] + s[5] * s[5]);
@@ -277,6 +277,7 @@ __device__ __forceinline__ int hill_passA(const DevMat &m, double *s, const doub
 //   FM 0 : general (any CV, Drucker / LHS terms)
 //   FM 1 : block-structured symmetric CV, no hydrostatic term            (DevMat.cv_block && cv_sym && !has_d)
 //   FM 2 : FM 1 and all Hill parameters equal 1 (J2): q = 1.5 |dev s|^2 + 3 |shear|^2, a = 1.5 dev(s) / seq
+//   FM 3 : FM 2 and isotropic elasticity (DevMat.cv_iso): pass B runs hill_passB_iso below, pass A is FM 2
 template <int FM>
 __device__ __forceinline__ void cv_mul_t(const DevMat &m, const double *v, double *o)
 {
@@ -296,7 +297,7 @@ __device__ __forceinline__ void cv_mul_t(const DevMat &m, const double *v, doubl
 template <int FM>
 __device__ __forceinline__ void seq_inv_t(const DevMat &m, const double *s, double &seq, double &iseq)
 {
-    if (FM == 2) {
+    if (FM >= 2) {
         const double p = (s[0] + s[1] + s[2]) * (1. / 3.);
         const double s0 = s[0] - p, s1 = s[1] - p, s2 = s[2] - p;
         const double q = 1.5 * (s0 * s0 + s1 * s1 + s2 * s2) + 3. * (s[3] * s[3] + s[4] * s[4] + s[5] * s[5]);
@@ -315,7 +316,7 @@ __device__ __forceinline__ void seq_inv_t(const DevMat &m, const double *s, doub
 template <int FM>
 __device__ __forceinline__ void grad_t(const DevMat &m, const double *s, double iseq, double *a)
 {
-    if (FM == 2) {
+    if (FM >= 2) {
         const double p = (s[0] + s[1] + s[2]) * (1. / 3.);
         const double c15 = 1.5 * iseq, c3 = 3. * iseq;
         a[0] = (s[0] - p) * c15; a[1] = (s[1] - p) * c15; a[2] = (s[2] - p) * c15;
@@ -425,6 +426,278 @@ __device__ __forceinline__ int hill_passB(const DevMat &m, double *s, double *ep
         for (int j = i; j < 6; j++) {
             const double c = m.CV[6 * i + j];
             gs[sym_idx(i, j)] = c * f1 + ((double)PLF_MAXIT * c - W.get(sym_idx(i, j))) * f2;
+        }
+    return 2 | (corrected ? 4 : 0);
+}
+
+// sqrt(q) and 1/sqrt(q) of q >= 0 without a branch (q = 0: seq = 0 and a finite rs; a stress-free state has no flow
+// direction, the reference divides by zero there)
+__device__ __forceinline__ void seq_rs(double q, double &seq, double &rs)
+{
+    rs = fast_rsqrt(q + 1e-300);   // the addend vanishes in rounding for any q > 1e-284
+    seq = q * rs;
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// FM 3: J2 yield function on isotropic elasticity (C11 - C12 = 2 C44 = 2G; BASELINE configs 2 and the 1024^2 target).
+// With n = (dev(s)_0..2, s_3..5) and r = 1/seq the flow direction is a = r (1.5 n_i | 3 n_k), and because a is
+// deviatoric   CV a = 3G r n   for ALL six components, so that
+//     hh  = a.CV a + khard = 3G + khard                      (a constant: no reciprocal in the loop)
+//     acd = a.(CV deps_r) = r ncd,   ncd = 1.5 n_i dc_i + 3 n_k dc_k,  dc = dev/shear part of CV deps_r
+//     sig += CV deps_r - CV a (acd / hh)      <=>  n_k += dc_k - beta n_k,  p += pc,  beta = 3G ncd / (hh seq^2)
+//     q(sig + CV deps_r) = seq^2 + q(CV deps_r) + 2 ncd       (elastic-trial check of epl_dot, no extra dot product)
+//     sum CV a (CV a)^T / hh = sum w n n^T,  w = (3G)^2 / (hh seq^2); n_2 = -n_0 - n_1, so only the 15 entries over
+//     the index set {0,1,3,4,5} are accumulated and the index-2 row is recovered at the end.
+// The same reference algorithm (50 forward-Euler sub-steps, material.py:295-344), ~85 FP64 instructions per
+// sub-step instead of ~160.  Radial-return corrections (rare) are added through 6 shared-memory words per thread.
+// ------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ int hill_passB_iso(const DevMat &m, double *s, double *epd, const double *de, double *xc, int xstride,
+                                              double *gs, double &fy)
+{
+    HillStep P;
+    hill_prelude<2>(m, s, epd, de, P, fy);   // cannot be elastic: pass A deferred this element
+    const double inv = 1. / (double)PLF_MAXIT;
+#pragma unroll
+    for (int k = 0; k < 6; k++) P.dr[k] *= inv;   // 290 (x * 0.02 instead of x / 50: 1 ulp, saves six IEEE divisions)
+    cv_mul_t<2>(m, P.dr, P.cdr);
+    const double G3 = 3. * m.CV[21];
+    const double ihh = 1. / (G3 + m.khard);
+    const double bfac = G3 * ihh, wfac = G3 * G3 * ihh;
+    const double pc = (P.cdr[0] + P.cdr[1] + P.cdr[2]) * (1. / 3.);
+    double dc[6] = {P.cdr[0] - pc, P.cdr[1] - pc, P.cdr[2] - pc, P.cdr[3], P.cdr[4], P.cdr[5]};
+    const double qc = 1.5 * (dc[0] * dc[0] + dc[1] * dc[1] + dc[2] * dc[2]) + 3. * (dc[3] * dc[3] + dc[4] * dc[4] + dc[5] * dc[5]);
+    double p = (s[0] + s[1] + s[2]) * (1. / 3.);
+    double n[6] = {s[0] - p, s[1] - p, s[2] - p, s[3], s[4], s[5]};
+    double q2 = 1.5 * (n[0] * n[0] + n[1] * n[1] + n[2] * n[2]) + 3. * (n[3] * n[3] + n[4] * n[4] + n[5] * n[5]);
+    double rs, seq;
+    seq_rs(q2, seq, rs);
+    const double c0 = m.sy + P.toler, K2 = m.khard * m.khard;
+    // reduced accumulator over the index set {0,1,3,4,5}: W[a][b], a <= b
+    double W00 = 0., W01 = 0., W03 = 0., W04 = 0., W05 = 0., W11 = 0., W13 = 0., W14 = 0., W15 = 0., W33 = 0., W34 = 0.,
+           W35 = 0., W44 = 0., W45 = 0., W55 = 0.;
+#pragma unroll
+    for (int k = 0; k < 6; k++) xc[k * xstride] = 0.;
+    bool corrected = false;
+    const double ythr = P.sflow0 + PLF_YF_TOLERANCE;
+    const double ythr2 = ythr * ythr;
+#pragma unroll 1
+    for (int it = 0; it < PLF_MAXIT; it++) {
+        const double ncd = 1.5 * (n[0] * dc[0] + n[1] * dc[1] + n[2] * dc[2]) + 3. * (n[3] * dc[3] + n[4] * dc[4] + n[5] * dc[5]);
+        const bool yplus = fma(2., ncd, q2 + qc) > ythr2;
+        const double r2 = rs * rs;
+        const double g = ncd * r2;
+        const double beta = g * bfac;
+        const double gam = yplus ? 1.5 * (g * ihh) : 0.;
+        const double gam2 = gam + gam;
+        const double w = r2 * wfac;
+        const double t0 = w * n[0], t1 = w * n[1], t3 = w * n[3], t4 = w * n[4], t5 = w * n[5];
+        W00 = fma(t0, n[0], W00); W01 = fma(t0, n[1], W01); W03 = fma(t0, n[3], W03); W04 = fma(t0, n[4], W04); W05 = fma(t0, n[5], W05);
+        W11 = fma(t1, n[1], W11); W13 = fma(t1, n[3], W13); W14 = fma(t1, n[4], W14); W15 = fma(t1, n[5], W15);
+        W33 = fma(t3, n[3], W33); W34 = fma(t3, n[4], W34); W35 = fma(t3, n[5], W35);
+        W44 = fma(t4, n[4], W44); W45 = fma(t4, n[5], W45);
+        W55 = fma(t5, n[5], W55);
+        double eplt[6];
+        eplt[0] = fma(gam, n[0], epd[0]); eplt[1] = fma(gam, n[1], epd[1]); eplt[2] = fma(gam, n[2], epd[2]);
+        eplt[3] = fma(gam2, n[3], epd[3]); eplt[4] = fma(gam2, n[4], epd[4]); eplt[5] = fma(gam2, n[5], epd[5]);
+#pragma unroll
+        for (int k = 0; k < 6; k++) n[k] = fma(-beta, n[k], n[k] + dc[k]);
+        p += pc;
+        q2 = 1.5 * (n[0] * n[0] + n[1] * n[1] + n[2] * n[2]) + 3. * (n[3] * n[3] + n[4] * n[4] + n[5] * n[5]);
+        seq_rs(q2, seq, rs);
+        const double e2s = (2. / 3.) * ((eplt[0] * eplt[0] + eplt[1] * eplt[1] + eplt[2] * eplt[2]) +
+                                        0.5 * (eplt[3] * eplt[3] + eplt[4] * eplt[4] + eplt[5] * eplt[5]));
+        const double lhs = seq - c0;
+        if (lhs > 0. && lhs * lhs > K2 * e2s) {   // fy > toler (hill_fy_gt), one rarely taken branch
+            // radial-return correction (310-342), rare: exact arithmetic path on the full stress vector
+            corrected = true;
+            const double fyv = seq - (m.sy + eps_eq6(eplt) * m.khard);
+            double sf[6] = {n[0] + p, n[1] + p, n[2] + p, n[3], n[4], n[5]};
+            double ex[6], t[6], x[6];
+#pragma unroll
+            for (int k = 0; k < 6; k++) {
+                ex[k] = sf[k] * fyv / seq;
+                sf[k] -= ex[k];
+            }
+            matvec6(m.SV, ex, t);
+#pragma unroll
+            for (int k = 0; k < 6; k++) eplt[k] += t[k];
+            lstsq_3x6(P.dr, ex, x);
+#pragma unroll
+            for (int k = 0; k < 6; k++) xc[k * xstride] += x[k];
+            p = (sf[0] + sf[1] + sf[2]) * (1. / 3.);
+            n[0] = sf[0] - p; n[1] = sf[1] - p; n[2] = sf[2] - p; n[3] = sf[3]; n[4] = sf[4]; n[5] = sf[5];
+            q2 = 1.5 * (n[0] * n[0] + n[1] * n[1] + n[2] * n[2]) + 3. * (n[3] * n[3] + n[4] * n[4] + n[5] * n[5]);
+            seq_rs(q2, seq, rs);
+        }
+#pragma unroll
+        for (int k = 0; k < 6; k++) epd[k] = eplt[k];
+    }
+    s[0] = n[0] + p; s[1] = n[1] + p; s[2] = n[2] + p; s[3] = n[3]; s[4] = n[4]; s[5] = n[5];
+    fy = seq - (m.sy + (m.khard != 0. ? eps_eq6(epd) * m.khard : 0.));
+    // full symmetric sum: index 2 from the trace relation n_2 = -n_0 - n_1, plus the correction blocks
+    double Wf[21];
+    Wf[sym_idx(0, 0)] = W00; Wf[sym_idx(0, 1)] = W01; Wf[sym_idx(0, 3)] = W03; Wf[sym_idx(0, 4)] = W04; Wf[sym_idx(0, 5)] = W05;
+    Wf[sym_idx(1, 1)] = W11; Wf[sym_idx(1, 3)] = W13; Wf[sym_idx(1, 4)] = W14; Wf[sym_idx(1, 5)] = W15;
+    Wf[sym_idx(3, 3)] = W33; Wf[sym_idx(3, 4)] = W34; Wf[sym_idx(3, 5)] = W35;
+    Wf[sym_idx(4, 4)] = W44; Wf[sym_idx(4, 5)] = W45; Wf[sym_idx(5, 5)] = W55;
+    Wf[sym_idx(0, 2)] = -W00 - W01;
+    Wf[sym_idx(1, 2)] = -W01 - W11;
+    Wf[sym_idx(2, 2)] = W00 + 2. * W01 + W11;
+    Wf[sym_idx(2, 3)] = -W03 - W13;
+    Wf[sym_idx(2, 4)] = -W04 - W14;
+    Wf[sym_idx(2, 5)] = -W05 - W15;
+    if (corrected) {
+        Wf[sym_idx(0, 0)] += xc[0 * xstride];
+        Wf[sym_idx(0, 1)] += xc[5 * xstride];
+        Wf[sym_idx(0, 2)] += xc[4 * xstride];
+        Wf[sym_idx(1, 1)] += xc[1 * xstride];
+        Wf[sym_idx(1, 2)] += xc[3 * xstride];
+        Wf[sym_idx(2, 2)] += xc[2 * xstride];
+    }
+    const double f1 = P.split ? (1. - P.st_scal) : 0.;
+    const double f2 = P.st_scal * inv;
+#pragma unroll
+    for (int i = 0; i < 6; i++)
+#pragma unroll
+        for (int j = i; j < 6; j++) {
+            const double c = m.CV[6 * i + j];
+            gs[sym_idx(i, j)] = c * f1 + ((double)PLF_MAXIT * c - Wf[sym_idx(i, j)]) * f2;
+        }
+    return 2 | (corrected ? 4 : 0);
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// FM 3, planar states: sig, epl, deps with zero 23 and 13 components (every state a 2-d pyLabFEA model produces:
+// Element.deps has no out-of-plane shear, model.py:387-398).  Block-structured CV keeps such a state planar through
+// the whole update, so the loop of hill_passB_iso shrinks to the components {0,1,2,5}: 6 accumulator entries over
+// the index set {0,1,5}, ~65 FP64 instructions per sub-step, ~100 registers.  Pass A sorts deferred elements into
+// planar (front of the work list) and general (back).  dr: the six words of deps_r / 50 are parked in shared memory
+// next to the correction sums (only the rare radial-return correction reads them).
+// ------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ bool planar_state(const double *s, const double *ep, const double *de)
+{
+    return s[3] == 0. && s[4] == 0. && ep[3] == 0. && ep[4] == 0. && de[3] == 0. && de[4] == 0.;
+}
+
+// radial-return correction of hill_passB_iso2d (material.py:310-342) on st = {n0, n1, n2, n5, p, eplt0, eplt1, eplt2,
+// eplt5, seq}; xc: [0..5] correction sums, [6..11] deps_r / 50 (shared memory, stride xstride)
+static __device__ __noinline__ void iso2d_correct(const DevMat &m, double *st, double *xc, int xstride)
+{
+    const double p = st[4], seq = st[9];
+    double eplt[6] = {st[5], st[6], st[7], 0., 0., st[8]};
+    const double fyv = seq - (m.sy + eps_eq6(eplt) * m.khard);
+    double sf[6] = {st[0] + p, st[1] + p, st[2] + p, 0., 0., st[3]};
+    double ex[6], t[6], x[6], dr[6];
+#pragma unroll
+    for (int k = 0; k < 6; k++) {
+        ex[k] = sf[k] * fyv / seq;
+        sf[k] -= ex[k];
+        dr[k] = xc[(6 + k) * xstride];
+    }
+    matvec6(m.SV, ex, t);
+    lstsq_3x6(dr, ex, x);
+#pragma unroll
+    for (int k = 0; k < 6; k++) xc[k * xstride] += x[k];
+    const double pn = (sf[0] + sf[1] + sf[2]) * (1. / 3.);
+    st[0] = sf[0] - pn; st[1] = sf[1] - pn; st[2] = sf[2] - pn; st[3] = sf[5]; st[4] = pn;
+    st[5] = eplt[0] + t[0]; st[6] = eplt[1] + t[1]; st[7] = eplt[2] + t[2]; st[8] = eplt[5] + t[5];
+}
+
+__device__ __forceinline__ int hill_passB_iso2d(const DevMat &m, double *s, double *epd, const double *de, double *xc, int xstride,
+                                                double *gs, double &fy)
+{
+    double st_scal, f1;
+    double pc, dc0, dc1, dc2, dc5, qc, c0, ythr2;
+    {
+        HillStep P;
+        hill_prelude<2>(m, s, epd, de, P, fy);   // cannot be elastic: pass A deferred this element
+#pragma unroll
+        for (int k = 0; k < 6; k++) {
+            P.dr[k] *= 1. / (double)PLF_MAXIT;   // 290
+            xc[(6 + k) * xstride] = P.dr[k];
+            xc[k * xstride] = 0.;
+        }
+        cv_mul_t<2>(m, P.dr, P.cdr);
+        pc = (P.cdr[0] + P.cdr[1] + P.cdr[2]) * (1. / 3.);
+        dc0 = P.cdr[0] - pc; dc1 = P.cdr[1] - pc; dc2 = P.cdr[2] - pc; dc5 = P.cdr[5];
+        qc = 1.5 * (dc0 * dc0 + dc1 * dc1 + dc2 * dc2) + 3. * (dc5 * dc5);
+        c0 = m.sy + P.toler;
+        const double ythr = P.sflow0 + PLF_YF_TOLERANCE;
+        ythr2 = ythr * ythr;
+        st_scal = P.st_scal;
+        f1 = P.split ? (1. - P.st_scal) : 0.;
+    }
+    const double G3 = 3. * m.CV[21];
+    const double ihh = 1. / (G3 + m.khard);
+    const double bfac = G3 * ihh, wfac = G3 * G3 * ihh, gfac = 1.5 * ihh, K2 = m.khard * m.khard;
+    double p = (s[0] + s[1] + s[2]) * (1. / 3.);
+    double n0 = s[0] - p, n1 = s[1] - p, n2 = s[2] - p, n5 = s[5];
+    double e0 = epd[0], e1 = epd[1], e2 = epd[2], e5 = epd[5];
+    double q2 = 1.5 * (n0 * n0 + n1 * n1 + n2 * n2) + 3. * (n5 * n5);
+    double rs, seq;
+    seq_rs(q2, seq, rs);
+    double W00 = 0., W01 = 0., W05 = 0., W11 = 0., W15 = 0., W55 = 0.;
+    bool corrected = false;
+#pragma unroll 1
+    for (int it = 0; it < PLF_MAXIT; it++) {
+        const double ncd = fma(1.5, fma(n2, dc2, fma(n1, dc1, n0 * dc0)), 3. * (n5 * dc5));
+        const bool yplus = fma(2., ncd, q2 + qc) > ythr2;
+        const double r2 = rs * rs;
+        const double g = ncd * r2;
+        const double beta = g * bfac;
+        const double gam = yplus ? g * gfac : 0.;
+        const double gam2 = gam + gam;
+        const double w = r2 * wfac;
+        const double t0 = w * n0, t1 = w * n1, t5 = w * n5;
+        W00 = fma(t0, n0, W00); W01 = fma(t0, n1, W01); W05 = fma(t0, n5, W05);
+        W11 = fma(t1, n1, W11); W15 = fma(t1, n5, W15); W55 = fma(t5, n5, W55);
+        double f0 = fma(gam, n0, e0), f1e = fma(gam, n1, e1), f2 = fma(gam, n2, e2), f5 = fma(gam2, n5, e5);
+        n0 = fma(-beta, n0, n0 + dc0); n1 = fma(-beta, n1, n1 + dc1); n2 = fma(-beta, n2, n2 + dc2); n5 = fma(-beta, n5, n5 + dc5);
+        p += pc;
+        q2 = 1.5 * (n0 * n0 + n1 * n1 + n2 * n2) + 3. * (n5 * n5);
+        seq_rs(q2, seq, rs);
+        const double e2s = (2. / 3.) * ((f0 * f0 + f1e * f1e + f2 * f2) + 0.5 * (f5 * f5));
+        const double lhs = seq - c0;
+        if (lhs > 0. && lhs * lhs > K2 * e2s) {
+            // radial-return correction (310-342), rare: out of line, state handed over through local memory so that
+            // its temporaries do not take registers from the loop
+            corrected = true;
+            double st[10] = {n0, n1, n2, n5, p, f0, f1e, f2, f5, seq};
+            iso2d_correct(m, st, xc, xstride);
+            n0 = st[0]; n1 = st[1]; n2 = st[2]; n5 = st[3]; p = st[4];
+            f0 = st[5]; f1e = st[6]; f2 = st[7]; f5 = st[8];
+            q2 = 1.5 * (n0 * n0 + n1 * n1 + n2 * n2) + 3. * (n5 * n5);
+            seq_rs(q2, seq, rs);
+        }
+        e0 = f0; e1 = f1e; e2 = f2; e5 = f5;
+    }
+    s[0] = n0 + p; s[1] = n1 + p; s[2] = n2 + p; s[3] = 0.; s[4] = 0.; s[5] = n5;
+    epd[0] = e0; epd[1] = e1; epd[2] = e2; epd[5] = e5;   // epd[3], epd[4] stay zero
+    fy = seq - (m.sy + (m.khard != 0. ? eps_eq6(epd) * m.khard : 0.));
+    double Wf[21];
+#pragma unroll
+    for (int k = 0; k < 21; k++) Wf[k] = 0.;
+    Wf[sym_idx(0, 0)] = W00; Wf[sym_idx(0, 1)] = W01; Wf[sym_idx(0, 5)] = W05;
+    Wf[sym_idx(1, 1)] = W11; Wf[sym_idx(1, 5)] = W15; Wf[sym_idx(5, 5)] = W55;
+    Wf[sym_idx(0, 2)] = -W00 - W01;
+    Wf[sym_idx(1, 2)] = -W01 - W11;
+    Wf[sym_idx(2, 2)] = W00 + 2. * W01 + W11;
+    Wf[sym_idx(2, 5)] = -W05 - W15;
+    if (corrected) {
+        Wf[sym_idx(0, 0)] += xc[0 * xstride];
+        Wf[sym_idx(0, 1)] += xc[5 * xstride];
+        Wf[sym_idx(0, 2)] += xc[4 * xstride];
+        Wf[sym_idx(1, 1)] += xc[1 * xstride];
+        Wf[sym_idx(1, 2)] += xc[3 * xstride];
+        Wf[sym_idx(2, 2)] += xc[2 * xstride];
+    }
+    const double f2s = st_scal * (1. / (double)PLF_MAXIT);
+#pragma unroll
+    for (int i = 0; i < 6; i++)
+#pragma unroll
+        for (int j = i; j < 6; j++) {
+            const double c = m.CV[6 * i + j];
+            gs[sym_idx(i, j)] = c * f1 + ((double)PLF_MAXIT * c - Wf[sym_idx(i, j)]) * f2s;
         }
     return 2 | (corrected ? 4 : 0);
 }

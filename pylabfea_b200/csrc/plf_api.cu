@@ -253,6 +253,13 @@ extern "C" int plf_set_materials(plf_ctx *ctx, int nmat, const plf_material *mat
         for (int r = 0; r < 6; r++)
             for (int c = r + 1; c < 6; c++)
                 if (d.CV[6 * r + c] != d.CV[6 * c + r]) d.cv_sym = 0;
+        // isotropic elasticity in full 3-d form (C11 - C12 = 2 C44): enables hill_passB_iso for J2 (hill_fast.cuh, FM 3)
+        {
+            const double *C = d.CV;
+            const double C11 = C[0], C12 = C[1], C44 = C[21];
+            d.cv_iso = (d.cv_block && d.cv_sym && C[7] == C11 && C[14] == C11 && C[2] == C12 && C[8] == C12 && C[28] == C44 &&
+                        C[35] == C44 && C44 > 0. && fabs(C11 - C12 - 2. * C44) <= 1e-13 * fabs(C11)) ? 1 : 0;
+        }
         memcpy(d.bar_m1, m.barlat_m1, sizeof d.bar_m1);
         memcpy(d.bar_m2, m.barlat_m2, sizeof d.bar_m2);
         d.bar_exp = m.barlat_exp;
@@ -351,9 +358,9 @@ extern "C" int plf_batch_run(plf_ctx *ctx, plf_batch *b)
 {
     if (!ctx || !b) return PLF_EINVAL;
     if (ctx->nmat == 0) return fail(ctx, PLF_ESTATE, "plf_batch_run: no materials set");
-    LaunchCtx lc{ctx->stream, ctx->sm_count, ctx->passb_wsmem};
+    LaunchCtx lc{ctx->stream, ctx->sm_count, ctx->passb_wsmem, ctx->passa_direct, ctx->max_fm, ctx->minb, ctx->k1_only};
     CK(launch_response(lc, ctx->hmats, ctx->nmat, b->n, b->mat_id, b->sig, b->epl, b->deps, b->fy, b->sig_out, b->depl,
-                       b->ctan, b->nsteps, b->worklist, (unsigned int *)ctx->d_scalars,
+                       b->ctan, b->nsteps, b->worklist, (unsigned int *)(ctx->d_scalars + 16),
                        (unsigned long long *)(ctx->d_scalars + 8), ctx->compact, &ctx->launches));
     return PLF_OK;
 }
@@ -378,6 +385,10 @@ extern "C" int plf_set_option(plf_ctx *ctx, const char *key, int value)
     if (!strcmp(key, "compact")) { ctx->compact = value; return PLF_OK; }
     if (!strcmp(key, "assembly_tiled")) { assembly_set_tiled(value); return PLF_OK; }
     if (!strcmp(key, "passb_wsmem")) { ctx->passb_wsmem = value; return PLF_OK; }
+    if (!strcmp(key, "passa_direct")) { ctx->passa_direct = value; return PLF_OK; }
+    if (!strcmp(key, "max_fm")) { ctx->max_fm = value; return PLF_OK; }
+    if (!strcmp(key, "minb")) { ctx->minb = value; return PLF_OK; }
+    if (!strcmp(key, "k1_only")) { ctx->k1_only = value; return PLF_OK; }
     return fail(ctx, PLF_EINVAL, std::string("plf_set_option: unknown key ") + key);
 }
 

@@ -17,7 +17,7 @@ struct DevMat {
     int32_t cv_block;   // CV = [3x3 normal block | diagonal shear] (cv_mul, hill_fast.cuh)
     int32_t has_d;      // any Drucker / LHS weight non-zero
     int32_t cv_sym;     // CV is exactly symmetric: (CV a) . deps == a . (CV deps)
-    int32_t pad2_;
+    int32_t cv_iso;     // cv_block && cv_sym && C11 - C12 == 2 C44 (to 1e-13): isotropic elasticity, plane strain / 3-d
     double sy, khard;
     double hill[6];
     double d[3];     // I1 weights (calc_seq 645-650)
@@ -182,6 +182,29 @@ __device__ __forceinline__ void warp_append(bool pred, int32_t item, int32_t *li
     if (lane == leader) base = atomicAdd(count, (unsigned)__popc(m));
     base = __shfl_sync(0xffffffffu, base, leader);
     if (pred) list[base + __popc(m & ((1u << lane) - 1u))] = item;
+}
+
+// Two-ended work list: class-0 items grow from the front (count[0]), class-1 items from the back (count[1]) of the
+// same n-slot buffer -- the two classes are consumed by different kernels.  Must be called by all 32 lanes.
+__device__ __forceinline__ void warp_append2(bool pred, bool back, int32_t item, int32_t *list, int64_t n, unsigned int *count)
+{
+    const unsigned m0 = __ballot_sync(0xffffffffu, pred && !back), m1 = __ballot_sync(0xffffffffu, pred && back);
+    if ((m0 | m1) == 0) return;
+    const int lane = threadIdx.x & 31;
+    if (m0) {
+        const int leader = __ffs(m0) - 1;
+        unsigned base = 0;
+        if (lane == leader) base = atomicAdd(count, (unsigned)__popc(m0));
+        base = __shfl_sync(0xffffffffu, base, leader);
+        if (pred && !back) list[base + __popc(m0 & ((1u << lane) - 1u))] = item;
+    }
+    if (m1) {
+        const int leader = __ffs(m1) - 1;
+        unsigned base = 0;
+        if (lane == leader) base = atomicAdd(count + 1, (unsigned)__popc(m1));
+        base = __shfl_sync(0xffffffffu, base, leader);
+        if (pred && back) list[n - 1 - (int64_t)(base + __popc(m1 & ((1u << lane) - 1u)))] = item;
+    }
 }
 
 struct SvcModel {

@@ -30,7 +30,11 @@ struct plf_ctx {
     int flush_val = 0;
     unsigned char *d_scalars = nullptr;   // 4 KB of device scratch scalars (counters, reductions)
     unsigned char *h_scalars = nullptr;   // pinned mirror
-    int compact = 1;                      // two-pass (compacted) return mapping
+    int compact = 1;                      // 1: two-pass (compacted) return mapping, 0: unsplit
+    int passa_direct = 0;                 // pass A: shared-memory staged coalesced stores (0, fastest measured) or per-thread 256-bit stores (1)
+    int max_fm = 4;                       // cap of the single-material fast mode (hill_fast.cuh)
+    int k1_only = 0;                      // diagnostics: 1 = launch pass A only
+    int minb = 4;                         // blocks per SM requested for the return-mapping kernels (3 or 4)
     int passb_wsmem = 2;                  // pass B variant: 0 regs/2 blocks per SM, 1 smem accumulator/4, 2 regs/3 (fastest measured)
 
     // materials

@@ -101,51 +101,45 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N)); }
 
-// Persistent, software-pipelined pass A: while a block computes and writes tile t, the 3 x 6 KB input records of its
-// next tile are already in flight (cp.async into the second shared-memory buffer), so HBM reads overlap the math and
-// the write-back instead of being exposed at the top of every block (ncu of the non-pipelined version:
-// long_scoreboard on the staging loads dominated, 39 % DRAM throughput).
-template <bool SINGLE, int FM>
-__global__ void __launch_bounds__(RB, 3) response_passA_kernel(int64_t n, const int32_t *__restrict__ mat_id,
-                                                            const double *__restrict__ sig, const double *__restrict__ epl,
-                                                            const double *__restrict__ deps, double *__restrict__ fy,
-                                                            double *__restrict__ sig_out, double *__restrict__ depl_out,
-                                                            double *__restrict__ ctan, int32_t *__restrict__ nsteps,
-                                                            int32_t *__restrict__ worklist, unsigned int *__restrict__ work_count)
+// 256-bit global store (sm_100: STG.E.ENL2.256): one full 32 B sector per thread, so a thread can write its own
+// 288 B tangent record (9 sectors, 32 B aligned) straight from registers without partial-sector traffic
+__device__ __forceinline__ void st256(double *p, double a, double b, double c, double d)
 {
-    extern __shared__ double smem[];   // [2][3][RB*6] input buffers + [RB*CT_STRIDE] tangent staging
-    double *s_ct = smem + 2 * 3 * RB * 6;
-    __shared__ unsigned char s_done[RB];
-    const int tid = threadIdx.x;
-    const int64_t ntiles = (n + RB - 1) / RB;
+    asm volatile("st.global.v4.f64 [%0], {%1, %2, %3, %4};\n" ::"l"(p), "d"(a), "d"(b), "d"(c), "d"(d) : "memory");
+}
 
-    auto prefetch = [&](int64_t tile, int buf) {
-        const int64_t b0 = tile * RB;
-        const int c = (int)min((int64_t)RB, n - b0);
-        double *d = smem + buf * (3 * RB * 6);
-        const double2 *g0 = reinterpret_cast<const double2 *>(sig + b0 * 6);
-        const double2 *g1 = reinterpret_cast<const double2 *>(epl + b0 * 6);
-        const double2 *g2 = reinterpret_cast<const double2 *>(deps + b0 * 6);
-        for (int i = tid; i < c * 3; i += RB) {
-            cp_async16(reinterpret_cast<double2 *>(d) + i, g0 + i);
-            cp_async16(reinterpret_cast<double2 *>(d + RB * 6) + i, g1 + i);
-            cp_async16(reinterpret_cast<double2 *>(d + 2 * RB * 6) + i, g2 + i);
-        }
-        cp_async_commit();
-    };
-
-    int buf = 0;
-    if ((int64_t)blockIdx.x < ntiles) prefetch(blockIdx.x, 0);
-    for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, buf ^= 1) {
-    const int64_t nxt = tile + gridDim.x;
-    if (nxt < ntiles) {
-        prefetch(nxt, buf ^ 1);
-        cp_async_wait<1>();   // everything but the newest group (the next tile) has landed
-    } else {
-        cp_async_wait<0>();
+// prefetch of one input tile (3 x RB records of 48 B) into shared memory
+__device__ __forceinline__ void tile_prefetch(int64_t n, int64_t tile, double *d, const double *__restrict__ sig,
+                                              const double *__restrict__ epl, const double *__restrict__ deps)
+{
+    const int64_t b0 = tile * RB;
+    const int c = (int)min((int64_t)RB, n - b0);
+    const double2 *g0 = reinterpret_cast<const double2 *>(sig + b0 * 6);
+    const double2 *g1 = reinterpret_cast<const double2 *>(epl + b0 * 6);
+    const double2 *g2 = reinterpret_cast<const double2 *>(deps + b0 * 6);
+    for (int i = threadIdx.x; i < c * 3; i += RB) {
+        cp_async16(reinterpret_cast<double2 *>(d) + i, g0 + i);
+        cp_async16(reinterpret_cast<double2 *>(d + RB * 6) + i, g1 + i);
+        cp_async16(reinterpret_cast<double2 *>(d + 2 * RB * 6) + i, g2 + i);
     }
-    __syncthreads();
-    double *s_sig = smem + buf * (3 * RB * 6), *s_epl = s_sig + RB * 6, *s_dep = s_sig + 2 * RB * 6;
+    cp_async_commit();
+}
+
+// Pass A on one tile whose inputs are resident in shared memory (s_in = [3][RB*6]).
+//   DIRECT = false: results are staged through shared memory (tangent in s_ct, stride 37) and written with coalesced
+//                   128-bit stores by the whole block
+//   DIRECT = true : every thread writes its own records from registers (tangent: 9 x 256-bit stores); no tangent
+//                   staging buffer, no copy loop, one barrier less -- ~300 fewer instructions per element
+template <bool SINGLE, int FM, bool DIRECT>
+__device__ __forceinline__ void passA_tile(int64_t n, int64_t tile, double *s_in, double *s_ct, unsigned char *s_done,
+                                           const int32_t *__restrict__ mat_id, double *__restrict__ fy,
+                                           double *__restrict__ sig_out, double *__restrict__ depl_out,
+                                           double *__restrict__ ctan, int32_t *__restrict__ nsteps, int32_t *worklist,
+                                           unsigned int *work_count)
+{
+    constexpr int FA = FM >= 3 ? 2 : FM;   // pass A of the isotropic modes is the J2 code
+    const int tid = threadIdx.x;
+    double *s_sig = s_in, *s_epl = s_in + RB * 6, *s_dep = s_in + 2 * RB * 6;
     const int64_t base = tile * RB;
     const int cnt = (int)min((int64_t)RB, n - base);
     double s[6], ep[6], de[6];
@@ -160,10 +154,11 @@ __global__ void __launch_bounds__(RB, 3) response_passA_kernel(int64_t n, const 
             de[2 * k] = c.x; de[2 * k + 1] = c.y;
         }
     }
-    bool done = false, defer = false;
+    bool done = false, defer = false, general = false;
     const int64_t e = base + tid;
     if (tid < cnt) {
         const DevMat &m = c_mat[SINGLE ? 0 : mat_id[e]];
+        if (FM == 4) general = !planar_state(s, ep, de);   // planar states go to the front of the list (hill_passB_iso2d)
         if (m.kind == PLF_MAT_ELASTIC || m.kind == PLF_MAT_HILL) {
             double dp[6], ca[6], tc = 1., tw = 0., fyv = 0.;
             int br = 0;
@@ -174,7 +169,7 @@ __global__ void __launch_bounds__(RB, 3) response_passA_kernel(int64_t n, const 
 #pragma unroll
                 for (int k = 0; k < 6; k++) { s[k] += t[k]; dp[k] = 0.; ca[k] = 0.; }
             } else {
-                br = hill_passA<FM>(m, s, ep, de, dp, ca, tc, tw, fyv);
+                br = hill_passA<FA>(m, s, ep, de, dp, ca, tc, tw, fyv);
             }
             if (br < 0) {
                 defer = true;
@@ -182,23 +177,133 @@ __global__ void __launch_bounds__(RB, 3) response_passA_kernel(int64_t n, const 
                 done = true;
                 if (fy) fy[e] = fyv;
                 if (nsteps) nsteps[e] = 0;
+                if (DIRECT) {
+                    if (sig_out)
 #pragma unroll
-                for (int k = 0; k < 6; k++) { s_sig[6 * tid + k] = s[k]; s_epl[6 * tid + k] = dp[k]; }
-                double *o = s_ct + CT_STRIDE * tid;
+                        for (int k = 0; k < 3; k++)
+                            reinterpret_cast<double2 *>(sig_out + e * 6)[k] = make_double2(s[2 * k], s[2 * k + 1]);
+                    if (depl_out)
 #pragma unroll
-                for (int i = 0; i < 6; i++) {
-                    const double wi = ca[i] * tw;
+                        for (int k = 0; k < 3; k++)
+                            reinterpret_cast<double2 *>(depl_out + e * 6)[k] = make_double2(dp[2 * k], dp[2 * k + 1]);
+                    if (ctan) {
+                        double w[6];
 #pragma unroll
-                    for (int j = 0; j < 6; j++) o[6 * i + j] = m.CV[6 * i + j] * tc - wi * ca[j];
+                        for (int i = 0; i < 6; i++) w[i] = ca[i] * tw;
+#pragma unroll
+                        for (int g = 0; g < 9; g++) {
+                            double v[4];
+#pragma unroll
+                            for (int q = 0; q < 4; q++) {
+                                const int idx = 4 * g + q, i = idx / 6, j = idx - 6 * i;
+                                v[q] = m.CV[idx] * tc - w[i] * ca[j];
+                            }
+                            st256(ctan + e * 36 + 4 * g, v[0], v[1], v[2], v[3]);
+                        }
+                    }
+                } else {
+#pragma unroll
+                    for (int k = 0; k < 6; k++) { s_sig[6 * tid + k] = s[k]; s_epl[6 * tid + k] = dp[k]; }
+                    double *o = s_ct + CT_STRIDE * tid;
+#pragma unroll
+                    for (int i = 0; i < 6; i++) {
+                        const double wi = ca[i] * tw;
+#pragma unroll
+                        for (int j = 0; j < 6; j++) o[6 * i + j] = m.CV[6 * i + j] * tc - wi * ca[j];
+                    }
                 }
             }
         }
     }
-    warp_append(defer, (int32_t)e, worklist, work_count);
-    s_done[tid] = done;
-    __syncthreads();
-    stage_out(base, cnt, s_sig, s_epl, s_ct, s_done, sig_out, depl_out, ctan);
-    __syncthreads();   // staging buffers are free again (the next prefetch overwrites this input buffer)
+    warp_append2(defer, general, (int32_t)e, worklist, n, work_count);
+    if (!DIRECT) {
+        s_done[tid] = done;
+        __syncthreads();
+        stage_out(base, cnt, s_sig, s_epl, s_ct, s_done, sig_out, depl_out, ctan);
+    }
+}
+
+// Pass B for one deferred element: gathered 128-bit loads, the 50 sub-steps, direct stores.
+//   xc: this thread's 6 shared-memory words (stride RB) for the radial-return correction sums of FM 3
+template <bool SINGLE, int FM, class WAcc>
+__device__ __forceinline__ void passB_element(int64_t e, WAcc &W, double *xc, const int32_t *__restrict__ mat_id,
+                                              const double *__restrict__ sig, const double *__restrict__ epl,
+                                              const double *__restrict__ deps, double *__restrict__ fy,
+                                              double *__restrict__ sig_out, double *__restrict__ depl_out,
+                                              double *__restrict__ ctan, int32_t *__restrict__ nsteps)
+{
+    const DevMat &m = c_mat[SINGLE ? 0 : mat_id[e]];
+    double s[6], ep[6], de[6], dp[6], gs[21], fyv;
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+        double2 a = __ldg(reinterpret_cast<const double2 *>(sig + e * 6) + k);
+        double2 b = __ldg(reinterpret_cast<const double2 *>(epl + e * 6) + k);
+        double2 c = __ldg(reinterpret_cast<const double2 *>(deps + e * 6) + k);
+        s[2 * k] = a.x; s[2 * k + 1] = a.y;
+        ep[2 * k] = b.x; ep[2 * k + 1] = b.y;
+        de[2 * k] = c.x; de[2 * k + 1] = c.y;
+    }
+    if (FM == 4) hill_passB_iso2d(m, s, ep, de, xc, RB, gs, fyv);
+    else if (FM == 3) hill_passB_iso(m, s, ep, de, xc, RB, gs, fyv);
+    else hill_passB<FM>(m, s, ep, de, W, gs, fyv);
+    // ep now holds epl + depl; the increment is recovered against the (L2-resident) input record
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+        double2 b = __ldcg(reinterpret_cast<const double2 *>(epl + e * 6) + k);   // a real re-load, not a live register
+        dp[2 * k] = ep[2 * k] - b.x;
+        dp[2 * k + 1] = ep[2 * k + 1] - b.y;
+    }
+    if (fy) fy[e] = fyv;
+    if (nsteps) nsteps[e] = PLF_MAXIT - 1;
+    if (sig_out)
+#pragma unroll
+        for (int k = 0; k < 3; k++) reinterpret_cast<double2 *>(sig_out + e * 6)[k] = make_double2(s[2 * k], s[2 * k + 1]);
+    if (depl_out)
+#pragma unroll
+        for (int k = 0; k < 3; k++) reinterpret_cast<double2 *>(depl_out + e * 6)[k] = make_double2(dp[2 * k], dp[2 * k + 1]);
+    if (ctan)
+#pragma unroll
+        for (int g = 0; g < 9; g++) {
+            double v[4];
+#pragma unroll
+            for (int q = 0; q < 4; q++) {
+                const int idx = 4 * g + q, i = idx / 6, j = idx - 6 * i;
+                v[q] = gs[sym_idx(i, j)];
+            }
+            st256(ctan + e * 36 + 4 * g, v[0], v[1], v[2], v[3]);
+        }
+}
+
+// Persistent, software-pipelined pass A: while a block computes and writes tile t, the 3 x 6 KB input records of its
+// next tile are already in flight (cp.async into the second shared-memory buffer), so HBM reads overlap the math and
+// the write-back instead of being exposed at the top of every block (ncu of the non-pipelined version:
+// long_scoreboard on the staging loads dominated, 39 % DRAM throughput).
+template <bool SINGLE, int FM, bool DIRECT>
+__global__ void __launch_bounds__(RB, 3) response_passA_kernel(int64_t n, const int32_t *__restrict__ mat_id,
+                                                               const double *__restrict__ sig, const double *__restrict__ epl,
+                                                               const double *__restrict__ deps, double *__restrict__ fy,
+                                                               double *__restrict__ sig_out, double *__restrict__ depl_out,
+                                                               double *__restrict__ ctan, int32_t *__restrict__ nsteps,
+                                                               int32_t *__restrict__ worklist, unsigned int *__restrict__ work_count)
+{
+    extern __shared__ double smem[];   // [2][3][RB*6] input buffers (+ [RB*CT_STRIDE] tangent staging when !DIRECT)
+    double *s_ct = smem + 2 * 3 * RB * 6;
+    __shared__ unsigned char s_done[DIRECT ? 1 : RB];
+    const int64_t ntiles = (n + RB - 1) / RB;
+    int buf = 0;
+    if ((int64_t)blockIdx.x < ntiles) tile_prefetch(n, blockIdx.x, smem, sig, epl, deps);
+    for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, buf ^= 1) {
+        const int64_t nxt = tile + gridDim.x;
+        if (nxt < ntiles) {
+            tile_prefetch(n, nxt, smem + (buf ^ 1) * (3 * RB * 6), sig, epl, deps);
+            cp_async_wait<1>();   // everything but the newest group (the next tile) has landed
+        } else {
+            cp_async_wait<0>();
+        }
+        __syncthreads();
+        passA_tile<SINGLE, FM, DIRECT>(n, tile, smem + buf * (3 * RB * 6), s_ct, s_done, mat_id, fy, sig_out, depl_out, ctan,
+                                       nsteps, worklist, work_count);
+        __syncthreads();   // input / staging buffers are free again (the next prefetch overwrites this input buffer)
     }
 }
 
@@ -210,51 +315,36 @@ __global__ void __launch_bounds__(RB, MINB) response_passB_kernel(const int32_t 
                                                             double *__restrict__ fy, double *__restrict__ sig_out,
                                                             double *__restrict__ depl_out, double *__restrict__ ctan,
                                                             int32_t *__restrict__ nsteps, const int32_t *__restrict__ worklist,
-                                                            const unsigned int *__restrict__ work_count)
+                                                            int64_t nlist, unsigned int *count)
 {
-    __shared__ double s_W[WSMEM ? 21 * RB : 1];
-    const unsigned int n = *work_count;
-    for (unsigned int t = blockIdx.x * RB + threadIdx.x; t < n; t += gridDim.x * RB) {
+    // count: [0] front class, [1] back class of the two-ended work list, [2] blocks that have finished
+    __shared__ double s_W[WSMEM ? 21 * RB : (FM >= 3 ? 12 * RB : 1)];
+    const unsigned int n0 = count[0], n1 = count[1];
+    for (unsigned int t = blockIdx.x * RB + threadIdx.x; t < n0; t += gridDim.x * RB) {
         const int64_t e = worklist[t];
-        const DevMat &m = c_mat[SINGLE ? 0 : mat_id[e]];
-        double s[6], ep[6], de[6], dp[6], gs[21], fyv;
-#pragma unroll
-        for (int k = 0; k < 3; k++) {
-            double2 a = __ldg(reinterpret_cast<const double2 *>(sig + e * 6) + k);
-            double2 b = __ldg(reinterpret_cast<const double2 *>(epl + e * 6) + k);
-            double2 c = __ldg(reinterpret_cast<const double2 *>(deps + e * 6) + k);
-            s[2 * k] = a.x; s[2 * k + 1] = a.y;
-            ep[2 * k] = b.x; ep[2 * k + 1] = b.y;
-            de[2 * k] = c.x; de[2 * k + 1] = c.y;
-        }
         if (WSMEM) {
             WShared W{s_W + threadIdx.x, RB};
-            hill_passB<FM>(m, s, ep, de, W, gs, fyv);
+            passB_element<SINGLE, FM>(e, W, nullptr, mat_id, sig, epl, deps, fy, sig_out, depl_out, ctan, nsteps);
         } else {
             WRegs W;
-            hill_passB<FM>(m, s, ep, de, W, gs, fyv);
+            passB_element<SINGLE, FM>(e, W, s_W + threadIdx.x, mat_id, sig, epl, deps, fy, sig_out, depl_out, ctan, nsteps);
         }
-        // ep now holds epl + depl; the increment is recovered against the (L2-resident) input record
-#pragma unroll
-        for (int k = 0; k < 3; k++) {
-            double2 b = __ldcg(reinterpret_cast<const double2 *>(epl + e * 6) + k);   // a real re-load, not a live register
-            dp[2 * k] = ep[2 * k] - b.x;
-            dp[2 * k + 1] = ep[2 * k + 1] - b.y;
+    }
+    if (FM == 4) {
+        // the non-planar elements (back of the list) with the general isotropic loop
+        for (unsigned int t = blockIdx.x * RB + threadIdx.x; t < n1; t += gridDim.x * RB) {
+            const int64_t e = worklist[nlist - 1 - (int64_t)t];
+            WRegs W;
+            passB_element<SINGLE, 3>(e, W, s_W + threadIdx.x, mat_id, sig, epl, deps, fy, sig_out, depl_out, ctan, nsteps);
         }
-        if (fy) fy[e] = fyv;
-        if (nsteps) nsteps[e] = PLF_MAXIT - 1;
-        if (sig_out)
-#pragma unroll
-            for (int k = 0; k < 3; k++) reinterpret_cast<double2 *>(sig_out + e * 6)[k] = make_double2(s[2 * k], s[2 * k + 1]);
-        if (depl_out)
-#pragma unroll
-            for (int k = 0; k < 3; k++) reinterpret_cast<double2 *>(depl_out + e * 6)[k] = make_double2(dp[2 * k], dp[2 * k + 1]);
-        if (ctan)
-#pragma unroll
-            for (int i = 0; i < 6; i++)
-#pragma unroll
-                for (int j = 0; j < 6; j += 2)
-                    reinterpret_cast<double2 *>(ctan + e * 36)[(6 * i + j) >> 1] = make_double2(gs[sym_idx(i, j)], gs[sym_idx(i, j + 1)]);
+    }
+    // the last block to finish zeroes the counters for the next launch (saves a memset node per step)
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        if (atomicAdd(count + 2, 1u) == gridDim.x - 1) {
+            count[0] = 0; count[1] = 0; count[2] = 0;
+        }
     }
 }
 
@@ -465,28 +555,44 @@ __global__ void __launch_bounds__(SVC_WARPS * 32) prim_svc_kernel(int op, int mi
 // host launchers
 // ------------------------------------------------------------------------------------------------------------
 static size_t k1_smem() { return sizeof(double) * (3 * RB * 6 + RB * CT_STRIDE); }
-static size_t k1a_smem() { return sizeof(double) * (2 * 3 * RB * 6 + RB * CT_STRIDE); }   // double-buffered inputs
+// double-buffered inputs (+ tangent staging for the non-direct variants)
+static size_t k1a_smem(bool direct) { return sizeof(double) * (2 * 3 * RB * 6 + (direct ? 0 : RB * CT_STRIDE)); }
 static size_t svc_smem(const DevMat &m) { return sizeof(double) * 7 * (size_t)m.nsv_pad; }
+
+template <class K>
+static cudaError_t big_smem(K kernel, size_t bytes)
+{
+    return cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+}
 
 cudaError_t response_init()
 {
     cudaError_t e;
-    e = cudaFuncSetAttribute(response_passA_kernel<true, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)k1a_smem());
-    if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(response_passA_kernel<true, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)k1a_smem());
-    if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(response_passA_kernel<true, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)k1a_smem());
-    if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(response_passA_kernel<false, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)k1a_smem());
-    if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(response_generic_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)k1_smem());
-    if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(response_svc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-    if (e != cudaSuccess) return e;
-    return cudaFuncSetAttribute(prim_svc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    // only the staged (non-direct) variants need more than the default 48 KB of dynamic shared memory
+    if ((e = big_smem(response_passA_kernel<false, 0, false>, k1a_smem(false))) != cudaSuccess) return e;
+    if ((e = big_smem(response_passA_kernel<true, 0, false>, k1a_smem(false))) != cudaSuccess) return e;
+    if ((e = big_smem(response_passA_kernel<true, 1, false>, k1a_smem(false))) != cudaSuccess) return e;
+    if ((e = big_smem(response_passA_kernel<true, 2, false>, k1a_smem(false))) != cudaSuccess) return e;
+    if ((e = big_smem(response_passA_kernel<true, 4, false>, k1a_smem(false))) != cudaSuccess) return e;
+    if ((e = big_smem(response_generic_kernel, k1_smem())) != cudaSuccess) return e;
+    if ((e = big_smem(response_svc_kernel, 227 * 1024)) != cudaSuccess) return e;
+    return big_smem(prim_svc_kernel, 227 * 1024);
 }
 
-// Launches the return mapping over n elements (device pointers).  scratch: worklist[n] int32 + 2 counters.
+// Fast mode of a single-material Hill batch (hill_fast.cuh): 1 = block-structured symmetric CV without hydrostatic
+// term, 2 = additionally J2, 3 = additionally isotropic elasticity, 4 = 3 with planar states sorted to their own
+// pass B kernel.  max_fm caps it (A/B measurements, tests).
+static int fast_mode(const DevMat *hmats, int nmat, int max_fm)
+{
+    if (nmat != 1 || hmats[0].kind != PLF_MAT_HILL || !hmats[0].cv_block || !hmats[0].cv_sym || hmats[0].has_d) return 0;
+    int fm = 2;
+    for (int k = 0; k < 6; k++)
+        if (hmats[0].hill[k] != 1.) fm = 1;
+    if (fm == 2 && hmats[0].cv_iso) fm = 4;
+    return std::min(fm, max_fm);
+}
+
+// Launches the return mapping over n elements (device pointers).  scratch: worklist[n] int32 (all -1) + counters.
 cudaError_t launch_response(const LaunchCtx &lc, const DevMat *hmats, int nmat, int64_t n, const int32_t *mat_id,
                             const double *sig, const double *epl, const double *deps, double *fy, double *sig_out,
                             double *depl, double *ctan, int32_t *nsteps, int32_t *worklist, unsigned int *work_count,
@@ -498,37 +604,46 @@ cudaError_t launch_response(const LaunchCtx &lc, const DevMat *hmats, int nmat, 
         if (hmats[i].kind == PLF_MAT_HILL || hmats[i].kind == PLF_MAT_ELASTIC) any_hill = true;
     const unsigned grid = (unsigned)((n + RB - 1) / RB);
     if (any_hill) {
+        const bool single = (nmat == 1);
+        const bool direct = lc.passa_direct != 0;
+        const int fm = fast_mode(hmats, nmat, lc.passb_wsmem == 2 ? lc.max_fm : 0);   // the pass B A/B variants 0 and 1 keep the general path
+        const unsigned pgrid = (unsigned)std::min<int64_t>((int64_t)lc.sm_count * 3, (int64_t)grid);
         if (compact && worklist) {
-            cudaMemsetAsync(work_count, 0, sizeof(unsigned int), lc.stream);
-            const bool single = (nmat == 1);
+            // work_count[0..2] are zero here: set at context creation and re-zeroed by the last block of pass B
             // persistent: 3 blocks per SM, each walking tiles with a double-buffered cp.async prefetch
-            const unsigned agrid = (unsigned)std::min<int64_t>((int64_t)lc.sm_count * 3, (int64_t)grid);
-            // fast mode (hill_fast.cuh): 1 = block-structured symmetric CV without hydrostatic term, 2 = additionally J2
-            int fm = 0;
-            if (single && hmats[0].kind == PLF_MAT_HILL && hmats[0].cv_block && hmats[0].cv_sym && !hmats[0].has_d) {
-                fm = 2;
-                for (int k = 0; k < 6; k++) if (hmats[0].hill[k] != 1.) fm = 1;
-            }
-            if (lc.passb_wsmem != 2) fm = 0;   // the A/B variants 0 and 1 keep the general code path
-#define PASSA(S, F)                                                                                                         \
-    response_passA_kernel<S, F><<<agrid, RB, k1a_smem(), lc.stream>>>(n, mat_id, sig, epl, deps, fy, sig_out, depl, ctan, \
-                                                                      nsteps, worklist, work_count)
+#define PASSA(S, F)                                                                                                              \
+    do {                                                                                                                         \
+        if (direct)                                                                                                              \
+            response_passA_kernel<S, F, true><<<pgrid, RB, k1a_smem(true), lc.stream>>>(n, mat_id, sig, epl, deps, fy, sig_out,  \
+                                                                                        depl, ctan, nsteps, worklist, work_count); \
+        else                                                                                                                     \
+            response_passA_kernel<S, F, false><<<pgrid, RB, k1a_smem(false), lc.stream>>>(n, mat_id, sig, epl, deps, fy, sig_out, \
+                                                                                          depl, ctan, nsteps, worklist, work_count); \
+    } while (0)
             if (!single) PASSA(false, 0);
-            else if (fm == 2) PASSA(true, 2);
+            else if (fm == 4) PASSA(true, 4);
+            else if (fm >= 2) PASSA(true, 2);
             else if (fm == 1) PASSA(true, 1);
             else PASSA(true, 0);
 #undef PASSA
-            int64_t bgrid = std::min<int64_t>((int64_t)lc.sm_count * 8, (int64_t)grid);
+            if (lc.k1_only == 1) {   // diagnostics: time pass A alone
+                cudaMemsetAsync(work_count, 0, 3 * sizeof(unsigned int), lc.stream);
+                (*launches)++;
+                return cudaGetLastError();
+            }
+            const int64_t bgrid = std::min<int64_t>((int64_t)lc.sm_count * 8, (int64_t)grid);
 #define PASSB(W, M, S, F)                                                                                                     \
     response_passB_kernel<W, M, S, F><<<(unsigned)bgrid, RB, 0, lc.stream>>>(mat_id, sig, epl, deps, fy, sig_out, depl, ctan, \
-                                                                             nsteps, worklist, work_count)
+                                                                             nsteps, worklist, n, work_count)
             // variant: 0 = accumulator in registers, 2 blocks per SM; 1 = shared memory, 4 blocks; 2 = registers, 3 blocks
             if (single && lc.passb_wsmem == 1) {
                 PASSB(true, 4, true, 0);
             } else if (single && lc.passb_wsmem == 0) {
                 PASSB(false, 2, true, 0);
             } else if (single) {
-                if (fm == 2) PASSB(false, 3, true, 2);
+                if (fm == 4) PASSB(false, 3, true, 4);   // planar elements first, then whatever is not planar
+                else if (fm == 3) PASSB(false, 3, true, 3);
+                else if (fm == 2) PASSB(false, 3, true, 2);
                 else if (fm == 1) PASSB(false, 3, true, 1);
                 else PASSB(false, 3, true, 0);
             } else {

@@ -241,3 +241,59 @@ def test_K_large_mesh_vs_oracle(ctx, golden):
     rows = np.repeat(np.arange(ctx.Ndof), np.diff(rowptr))
     sx = np.bincount(rows, weights=val * (col % 2 == 0), minlength=ctx.Ndof)
     assert np.max(np.abs(sx)) < 1e-9 * np.max(np.abs(val))
+
+
+def test_response_full_size_fast_modes_vs_oracle(ctx):
+    """BASELINE target size (1024 x 1024 J2 on isotropic elasticity, synthetic correlated field): the production fast
+    mode (planar isotropic pass B, two-ended work list) against the general Hill kernels on every element, against the
+    CPU oracle on a seeded sample, launch-to-launch reproducibility (the in-kernel counter reset), and a batch in which
+    30 % of the elements carry out-of-plane shear (back of the work list)."""
+    import bench
+    from oracle import oracle as orc
+    N = 1024
+    mat, CV = bench.j2_material()
+    ctx.set_materials([mat], planestress=False)
+    sig, epl, deps = bench.synth_states(N, 1234)
+    mats = [orc.Mat(kind=orc.HILL, E=bench.E_MOD, nu=bench.NU, sy=bench.SY, khard=bench.KHARD)]
+
+    def run(a, b, c, **opts):
+        o = dict(compact=1, max_fm=4, passa_direct=0)
+        o.update(opts)
+        for k, v in o.items():
+            ctx.set_option(k, v)
+        return ctx.response_batch(a, b, c)
+
+    try:
+        ref = run(sig, epl, deps, max_fm=0)                      # general Hill path (any CV, any Hill parameters)
+        n50 = int(np.sum(ref[4] == 49))
+        assert 0.05 * N * N < n50 < 0.5 * N * N                  # the 50-sub-step pass really ran
+        for opts in (dict(max_fm=2), dict(max_fm=3), dict(max_fm=4), dict(max_fm=4), dict(max_fm=4, passa_direct=1)):
+            out = run(sig, epl, deps, **opts)
+            assert np.array_equal(out[4], ref[4]), opts          # same branch per element
+            for a, b in zip(out[:4], ref[:4]):
+                assert np.max(np.abs(a - b)) <= 1e-10 * np.max(np.abs(b)), opts
+        idx = np.random.default_rng(3).choice(N * N, 20000, replace=False)
+        oref = orc.response_batch(mats, None, sig[idx], epl[idx], deps[idx], CV[None])
+        fy, so, dp, ct, ns = (o[idx] for o in out)
+        assert np.array_equal(ns, oref[4])
+        assert np.max(np.abs(fy - oref[0])) < TOL * bench.SY
+        assert relmax(so, oref[1]) < TOL and relmax(ct, oref[3]) < TOL
+        assert np.max(np.abs(dp - oref[2])) < TOL * np.max(np.abs(oref[2]))
+        # non-planar states: 30 % of a 200k-element batch get 23 / 13 shear components
+        m = 200000
+        s3, e3, d3 = sig[:m].copy(), epl[:m].copy(), deps[:m].copy()
+        rng = np.random.default_rng(1)
+        odd = rng.random(m) < 0.3
+        s3[odd, 3] = 20. * rng.standard_normal(odd.sum())
+        s3[odd, 4] = 10. * rng.standard_normal(odd.sum())
+        d3[odd, 3] = 1e-4 * rng.standard_normal(odd.sum())
+        out = run(s3, e3, d3)
+        sel = np.concatenate([np.nonzero(odd)[0][:3000], np.nonzero(~odd)[0][:3000]])
+        oref = orc.response_batch(mats, None, s3[sel], e3[sel], d3[sel], CV[None])
+        assert np.array_equal(out[4][sel], oref[4])
+        assert int(np.sum(out[4][sel][:3000] == 49)) > 100       # deferred non-planar elements exist
+        assert relmax(out[1][sel], oref[1]) < TOL and relmax(out[3][sel], oref[3]) < TOL
+        assert np.max(np.abs(out[2][sel] - oref[2])) < TOL * np.max(np.abs(oref[2]))
+    finally:
+        for k, v in dict(compact=1, max_fm=4, passa_direct=0).items():
+            ctx.set_option(k, v)
