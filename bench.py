@@ -422,7 +422,7 @@ def main():
             return None
     achieved = BYTES_PER_UPDATE * Nel / (resp_ms_max * 1e-3) / 1e9
     asm_achieved = BYTES_PER_ASSEMBLED * Nel / (asm_ms_max * 1e-3) / 1e9
-    asm_kernel = {0: 'assemble_rows_kernel', 1: 'assemble_tile_kernel', 2: 'assemble_rows_staged_kernel'}[args.assembly_tiled]
+    asm_kernel = {0: 'assemble_rows_kernel', 2: 'assemble_rows_staged_kernel'}[args.assembly_tiled]
     roofline = {'bound': 'hbm',
                 'kernel': {1: 'response_passA_kernel + response_passB_kernel (return mapping, compacted 50-sub-step pass)',
                            0: 'response_generic_kernel'}[args.compact],

@@ -22,6 +22,23 @@ cudaError_t assembly_upload_geom(const GeomClass *h, int n, cudaStream_t st)
     return cudaMemcpyToSymbolAsync(c_geom, h, sizeof(GeomClass) * n, 0, cudaMemcpyHostToDevice, st);
 }
 
+// First CSR entry of a row of the structured mesh, in closed form (row 2n+c has the dofs of all nodes within +-1 in
+// (j,k), ascending): the kernels compute row starts instead of loading rowptr (a dependent load at the top and at
+// the bottom of every thread was 17 % of the assembly kernel's stall samples).
+__device__ __forceinline__ int64_t csr_row_start(int NX, int NY, int64_t row)
+{
+    const int NnY = NY + 1;
+    const int64_t colw = 4ll * (3 * NY + 1);   // entries per unit of "x neighbours" in one node column
+    const int64_t n = row >> 1;
+    const int c = (int)(row & 1);
+    const int j = (int)(n / NnY), k = (int)(n - (int64_t)j * NnY);
+    if (j > NX) return colw * (3ll * (NX + 1) - 2);   // row == Ndof: total number of non-zeros
+    const int nxc = 1 + (j > 0) + (j < NX), nyc = 1 + (k > 0) + (k < NY);
+    const int64_t pj = (j == 0) ? 0 : 3ll * j - 1;
+    const int64_t pk = (k == 0) ? 0 : 3ll * k - 1;
+    return colw * pj + 4ll * nxc * pk + (int64_t)c * 2 * nxc * nyc;
+}
+
 // CSR pattern of the structured mesh: row 2n+c has the dofs of all nodes within +-1 in (j,k), ascending.
 __global__ void csr_pattern_kernel(int NX, int NY, int32_t *__restrict__ rowptr, int32_t *__restrict__ col)
 {
@@ -61,14 +78,51 @@ __global__ void csr_pattern_kernel(int NX, int NY, int32_t *__restrict__ rowptr,
 }
 
 // One row (dof `c` of local node `a`) of the element stiffness: kel[8].
+// The row needs 8 (plane strain) or 12 (plane stress) of the 36 tangent entries; they are fetched with 128-bit loads
+// (entry pairs [6c, 6c+1], [6c+4, 6c+5], [30, 31], [34, 35]: all 16 B aligned in the 288 B record).  With scalar
+// loads the kernel was bound by L1 wavefronts (every warp-level load touches 16 different records), not by HBM.
+template <bool PS>
+struct CRow {   // the tangent entries one Kel row needs
+    double c10, c11, c12, c15, c50, c51, c52, c55, c20, c21, c22, c25;
+};
+
+template <bool PS>
+__device__ __forceinline__ CRow<PS> load_crow(const double *__restrict__ C, int c)
+{
+    CRow<PS> r;
+    const double2 ra = __ldg(reinterpret_cast<const double2 *>(C + 6 * c));       // ux rows use C row 0, uy rows use C row 1
+    const double2 rb = __ldg(reinterpret_cast<const double2 *>(C + 6 * c + 4));
+    const double2 r5a = __ldg(reinterpret_cast<const double2 *>(C + 30));
+    const double2 r5b = __ldg(reinterpret_cast<const double2 *>(C + 34));
+    r.c10 = ra.x; r.c11 = ra.y; r.c15 = rb.y;
+    r.c50 = r5a.x; r.c51 = r5a.y; r.c55 = r5b.y;
+    r.c12 = r.c52 = r.c20 = r.c21 = r.c22 = r.c25 = 0.;
+    if (PS) {
+        r.c12 = __ldg(C + 6 * c + 2);
+        r.c52 = __ldg(C + 32);
+        const double2 r2a = __ldg(reinterpret_cast<const double2 *>(C + 12));
+        const double2 r2b = __ldg(reinterpret_cast<const double2 *>(C + 14));
+        const double2 r2c = __ldg(reinterpret_cast<const double2 *>(C + 16));
+        r.c20 = r2a.x; r.c21 = r2a.y; r.c22 = r2b.x; r.c25 = r2c.y;
+    }
+    return r;
+}
+
+template <bool PS>
+__device__ __forceinline__ void kel_row_from(const GeomClass &gc, const CRow<PS> &R, int a, int c, double *kel);
+
 template <bool PS>
 __device__ __forceinline__ void kel_row(const GeomClass &gc, const double *__restrict__ C, int a, int c, double *kel)
 {
-    const int row1 = c;   // ux rows use C row 0, uy rows use C row 1
-    const double c10 = C[6 * row1 + 0], c11 = C[6 * row1 + 1], c12 = C[6 * row1 + 2], c15 = C[6 * row1 + 5];
-    const double c50 = C[30], c51 = C[31], c52 = C[32], c55 = C[35];
-    double c20 = 0., c21 = 0., c22 = 0., c25 = 0.;
-    if (PS) { c20 = C[12]; c21 = C[13]; c22 = C[14]; c25 = C[17]; }
+    const CRow<PS> R = load_crow<PS>(C, c);
+    kel_row_from<PS>(gc, R, a, c, kel);
+}
+
+template <bool PS>
+__device__ __forceinline__ void kel_row_from(const GeomClass &gc, const CRow<PS> &R, int a, int c, double *kel)
+{
+    const double c10 = R.c10, c11 = R.c11, c12 = R.c12, c15 = R.c15, c50 = R.c50, c51 = R.c51, c52 = R.c52, c55 = R.c55;
+    const double c20 = R.c20, c21 = R.c21, c22 = R.c22, c25 = R.c25;
     double ksum[8];
 #pragma unroll
     for (int g = 0; g < 4; g++) {
@@ -157,10 +211,14 @@ __global__ void __launch_bounds__(128) assemble_rows_kernel(int NX, int NY, cons
 // ---------------------------------------------------------------------------------------------------------------
 constexpr int SN = 64;   // nodes per block
 
-template <bool PS>
-__global__ void __launch_bounds__(2 * SN) assemble_rows_staged_kernel(int NX, int NY, const int32_t *__restrict__ elem_desc,
-                                                                      const double *__restrict__ elstiff,
-                                                                      const int32_t *__restrict__ rowptr, double *__restrict__ val)
+// UNIFORM: the mesh has a single geometry class -> no descriptor loads.  MINB: blocks per SM asked of the register
+// allocator (5 measured faster than 6, which spills).  All four elements' operands are requested before the first one is used (indices clamped into the mesh,
+// so the loads are unconditional; contributions of elements outside the mesh are skipped): four independent memory
+// round trips per thread instead of four dependent ones.
+template <bool PS, bool UNIFORM, int MINB>
+__global__ void __launch_bounds__(2 * SN, MINB) assemble_rows_staged_kernel(int NX, int NY, const int32_t *__restrict__ elem_desc,
+                                                                            const double *__restrict__ elstiff,
+                                                                            double *__restrict__ val)
 {
     __shared__ double2 s_out[SN * 2 * 9];
     const int tid = threadIdx.x;
@@ -171,33 +229,38 @@ __global__ void __launch_bounds__(2 * SN) assemble_rows_staged_kernel(int NX, in
     const int kmax = min(k0 + SN - 1, NY);
     const int64_t r_first = 2 * ((int64_t)j * NnY + k0);
     const int64_t r_last = 2 * ((int64_t)j * NnY + kmax) + 1;
-    const int32_t begin = __ldg(rowptr + r_first), end = __ldg(rowptr + r_last + 1);
+    const int64_t begin = csr_row_start(NX, NY, r_first), end = csr_row_start(NX, NY, r_last + 1);
 
     if (active) {
         double acc[9][2];
 #pragma unroll
         for (int s = 0; s < 9; s++) acc[s][0] = acc[s][1] = 0.;
+        CRow<PS> R[4];
+        int cls[4];
 #pragma unroll
-        for (int ddj = 0; ddj < 2; ddj++) {
+        for (int q = 0; q < 4; q++) {
+            const int ej = min(max(j - 1 + (q >> 1), 0), NX - 1), ek = min(max(k - 1 + (q & 1), 0), NY - 1);
+            const int64_t e = (int64_t)ej * NY + ek;
+            cls[q] = UNIFORM ? 0 : (__ldg(elem_desc + e) >> 16);
+            R[q] = load_crow<PS>(elstiff + e * 36, c);
+        }
 #pragma unroll
-            for (int ddk = 0; ddk < 2; ddk++) {
-                const int ej = j - 1 + ddj, ek = k - 1 + ddk;   // ascending element index e = ej*NY + ek
-                if (ej < 0 || ej >= NX || ek < 0 || ek >= NY) continue;
-                const int64_t e = (int64_t)ej * NY + ek;
-                const int cls = __ldg(elem_desc + e) >> 16;
-                const int a = 2 * (1 - ddj) + (1 - ddk);
-                double kel[8];
-                kel_row<PS>(c_geom[cls], elstiff + e * 36, a, c, kel);
+        for (int q = 0; q < 4; q++) {
+            const int ddj = q >> 1, ddk = q & 1;
+            const int ej = j - 1 + ddj, ek = k - 1 + ddk;   // ascending element index e = ej*NY + ek
+            if (ej < 0 || ej >= NX || ek < 0 || ek >= NY) continue;
+            const int a = 2 * (1 - ddj) + (1 - ddk);
+            double kel[8];
+            kel_row_from<PS>(c_geom[cls[q]], R[q], a, c, kel);
 #pragma unroll
-                for (int m = 0; m < 4; m++) {
-                    const int sj = ddj + (m >> 1), sk = ddk + (m & 1);
-                    acc[3 * sj + sk][0] = acc[3 * sj + sk][0] + kel[2 * m];
-                    acc[3 * sj + sk][1] = acc[3 * sj + sk][1] + kel[2 * m + 1];
-                }
+            for (int m = 0; m < 4; m++) {
+                const int sj = ddj + (m >> 1), sk = ddk + (m & 1);
+                acc[3 * sj + sk][0] = acc[3 * sj + sk][0] + kel[2 * m];
+                acc[3 * sj + sk][1] = acc[3 * sj + sk][1] + kel[2 * m + 1];
             }
         }
         const int64_t r = 2 * ((int64_t)j * NnY + k) + c;
-        int pos2 = (__ldg(rowptr + r) - begin) >> 1;
+        int pos2 = (int)((csr_row_start(NX, NY, r) - begin) >> 1);
 #pragma unroll
         for (int sj = 0; sj < 3; sj++) {
             if (j + sj - 1 < 0 || j + sj - 1 > NX) continue;
@@ -209,123 +272,14 @@ __global__ void __launch_bounds__(2 * SN) assemble_rows_staged_kernel(int NX, in
         }
     }
     __syncthreads();
-    const int n2 = (end - begin) >> 1;
+    const int n2 = (int)((end - begin) >> 1);
     double2 *dst = reinterpret_cast<double2 *>(val + begin);
     for (int i = tid; i < n2; i += 2 * SN) dst[i] = s_out[i];
 }
 
-// ---------------------------------------------------------------------------------------------------------------
-// Tiled variant (experimental, slower: kept for the record, see profiles/).  The row-per-thread kernel above reads the 288 B AoS tangents and writes its 144 B rows
-// with a stride between lanes, so every warp-level access touches 16-36 cache lines and the L1 wavefront rate
-// (one 128 B line per cycle per SM) becomes the limit (ncu: long_scoreboard + lg_throttle, 42 % of the HBM roofline).
-// Here a block of 256 threads owns a tile of 4 node columns x 32 node rows:
-//   1. the 5 x 33 element tangents around the tile are loaded with coalesced 128-bit loads (each element column of
-//      the tile is one contiguous run in memory) into shared memory, record stride 37 doubles (conflict-free),
-//   2. every thread computes its CSR row exactly as above, reading the tangents from shared memory,
-//   3. the rows are staged in shared memory in CSR order (one contiguous run per node column) and written with
-//      coalesced 128-bit stores.
-// Arithmetic and summation order are unchanged -> CSR(K) stays bit-identical to the reference.
-// ---------------------------------------------------------------------------------------------------------------
-static int g_tiled = 2;   // 0: row per thread, direct stores; 1: shared-memory tile; 2: row per thread, staged stores
-constexpr int TJ = 4, TK = 32;                 // node tile
-constexpr int TEJ = TJ + 1, TEK = TK + 1;      // element tile (one halo column / row on the low side)
-constexpr int ESTRIDE = 37;
-
-template <bool PS>
-__global__ void __launch_bounds__(TJ * TK * 2) assemble_tile_kernel(int NX, int NY, const int32_t *__restrict__ elem_desc,
-                                                                    const double *__restrict__ elstiff,
-                                                                    const int32_t *__restrict__ rowptr, double *__restrict__ val)
-{
-    extern __shared__ double smem[];                       // TEJ*TEK*ESTRIDE doubles, reused for the output staging
-    __shared__ int s_cls[TEJ * TEK];
-    const int tid = threadIdx.x;
-    const int NnY = NY + 1;
-    const int j0 = blockIdx.x * TJ, k0 = blockIdx.y * TK;
-
-    // 1. coalesced load of the element tile
-    for (int cj = 0; cj < TEJ; cj++) {
-        const int ej = j0 - 1 + cj;
-        if (ej < 0 || ej >= NX) continue;
-        const int ek_lo = max(k0 - 1, 0), ek_hi = min(k0 + TK - 1, NY - 1);
-        const int nel = ek_hi - ek_lo + 1;
-        if (nel <= 0) continue;
-        const int64_t e0 = (int64_t)ej * NY + ek_lo;
-        const double2 *src = reinterpret_cast<const double2 *>(elstiff + e0 * 36);
-        const int lbase = cj * TEK + (ek_lo - (k0 - 1));
-        for (int i = tid; i < nel * 18; i += TJ * TK * 2) {
-            const double2 v = __ldg(src + i);
-            const int el = i / 18, w = i - el * 18;
-            double *dst = smem + (lbase + el) * ESTRIDE + 2 * w;
-            dst[0] = v.x;
-            dst[1] = v.y;
-        }
-        for (int i = tid; i < nel; i += TJ * TK * 2) s_cls[lbase + i] = __ldg(elem_desc + e0 + i) >> 16;
-    }
-    __syncthreads();
-
-    // 2. one CSR row per thread
-    const int c = tid & 1, kk = (tid >> 1) & (TK - 1), jj = tid >> 6;
-    const int j = j0 + jj, k = k0 + kk;
-    const bool active = (j <= NX) && (k <= NY);
-    double acc[9][2];
-#pragma unroll
-    for (int s = 0; s < 9; s++) acc[s][0] = acc[s][1] = 0.;
-    if (active) {
-#pragma unroll
-        for (int ddj = 0; ddj < 2; ddj++) {
-#pragma unroll
-            for (int ddk = 0; ddk < 2; ddk++) {
-                const int ej = j - 1 + ddj, ek = k - 1 + ddk;   // ascending element index e = ej*NY + ek
-                if (ej < 0 || ej >= NX || ek < 0 || ek >= NY) continue;
-                const int le = (jj + ddj) * TEK + (kk + ddk);
-                const int a = 2 * (1 - ddj) + (1 - ddk);
-                double kel[8];
-                kel_row<PS>(c_geom[s_cls[le]], smem + le * ESTRIDE, a, c, kel);
-#pragma unroll
-                for (int m = 0; m < 4; m++) {
-                    const int sj = ddj + (m >> 1), sk = ddk + (m & 1);
-                    acc[3 * sj + sk][0] = acc[3 * sj + sk][0] + kel[2 * m];
-                    acc[3 * sj + sk][1] = acc[3 * sj + sk][1] + kel[2 * m + 1];
-                }
-            }
-        }
-    }
-    __syncthreads();   // all reads of the tangent tile are done: reuse the memory for the rows
-
-    // 3. stage the rows in CSR order (per node column: rows 2*(j*NnY + k0) ... are one contiguous run) and store
-    const bool col_ok = (j <= NX);
-    const int kmax = min(k0 + TK - 1, NY);                 // last node row of this tile
-    int32_t col_begin = 0, col_end = 0;
-    if (col_ok) {
-        const int64_t r_first = 2 * ((int64_t)j * NnY + k0);
-        const int64_t r_last = 2 * ((int64_t)j * NnY + kmax) + 1;
-        col_begin = rowptr[r_first];
-        col_end = rowptr[r_last + 1];
-    }
-    double *s_out = smem + jj * (TK * 2 * 18);             // <= 64 rows x 18 entries per node column
-    if (active) {
-        const int64_t r = 2 * ((int64_t)j * NnY + k) + c;
-        int pos = rowptr[r] - col_begin;
-#pragma unroll
-        for (int sj = 0; sj < 3; sj++) {
-            if (j + sj - 1 < 0 || j + sj - 1 > NX) continue;
-#pragma unroll
-            for (int sk = 0; sk < 3; sk++) {
-                if (k + sk - 1 < 0 || k + sk - 1 > NY) continue;
-                s_out[pos] = acc[3 * sj + sk][0];
-                s_out[pos + 1] = acc[3 * sj + sk][1];
-                pos += 2;
-            }
-        }
-    }
-    __syncthreads();
-    if (col_ok) {
-        const int n2 = (col_end - col_begin) >> 1;          // entries come in (ux, uy) pairs; col_begin is even
-        double2 *dst = reinterpret_cast<double2 *>(val + col_begin);
-        const double2 *src = reinterpret_cast<const double2 *>(s_out);
-        for (int i = tid & 63; i < n2; i += 64) dst[i] = src[i];
-    }
-}
+static int g_tiled = 2;   // 0: row per thread, direct stores; 2: row per thread, staged stores (production)
+// (a shared-memory tiled variant -- coalesced tile loads of the tangents, 3 barriers -- measured 0.27 ms against
+//  0.15 ms for the staged row kernel at 1024^2 and was removed)
 
 // Element.Kel for every element (plf_get_kel): thread per (element, row).
 template <bool PS>
@@ -351,28 +305,16 @@ cudaError_t launch_csr_pattern(const LaunchCtx &lc, int NX, int NY, int32_t *row
     return cudaGetLastError();
 }
 
-cudaError_t launch_assemble(const LaunchCtx &lc, int NX, int NY, int planestress, const int32_t *elem_desc,
+cudaError_t launch_assemble(const LaunchCtx &lc, int NX, int NY, int planestress, int ngeom, const int32_t *elem_desc,
                             const double *elstiff, const int32_t *rowptr, double *val, int64_t *launches)
 {
-    if (g_tiled == 2) {
+    if (g_tiled != 0) {
         const dim3 grid((NY + 1 + SN - 1) / SN, NX + 1);
-        if (planestress)
-            assemble_rows_staged_kernel<true><<<grid, 2 * SN, 0, lc.stream>>>(NX, NY, elem_desc, elstiff, rowptr, val);
-        else
-            assemble_rows_staged_kernel<false><<<grid, 2 * SN, 0, lc.stream>>>(NX, NY, elem_desc, elstiff, rowptr, val);
-    } else if (g_tiled == 1) {
-        static bool attr_set = false;
-        const int smem = TEJ * TEK * ESTRIDE * (int)sizeof(double);
-        if (!attr_set) {
-            cudaFuncSetAttribute(assemble_tile_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-            cudaFuncSetAttribute(assemble_tile_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-            attr_set = true;
-        }
-        const dim3 grid((NX + 1 + TJ - 1) / TJ, (NY + 1 + TK - 1) / TK);
-        if (planestress)
-            assemble_tile_kernel<true><<<grid, TJ * TK * 2, smem, lc.stream>>>(NX, NY, elem_desc, elstiff, rowptr, val);
-        else
-            assemble_tile_kernel<false><<<grid, TJ * TK * 2, smem, lc.stream>>>(NX, NY, elem_desc, elstiff, rowptr, val);
+#define ASM(PS, U, M) assemble_rows_staged_kernel<PS, U, M><<<grid, 2 * SN, 0, lc.stream>>>(NX, NY, elem_desc, elstiff, val)
+        const bool uni = (ngeom == 1);
+        if (planestress) { if (uni) ASM(true, true, 4); else ASM(true, false, 4); }
+        else { if (uni) ASM(false, true, 5); else ASM(false, false, 5); }
+#undef ASM
     } else {
         const int64_t Ndof = 2ll * (NX + 1) * (NY + 1);
         const unsigned grid = (unsigned)((Ndof + 127) / 128);

@@ -44,7 +44,7 @@ cudaError_t launch_prim(const LaunchCtx &lc, const DevMat *hmats, int op, int mi
 cudaError_t assembly_upload_geom(const GeomClass *h, int n, cudaStream_t st);
 void assembly_set_tiled(int on);   // 1 (default): shared-memory tiled assembly; 0: row-per-thread direct variant
 cudaError_t launch_csr_pattern(const LaunchCtx &lc, int NX, int NY, int32_t *rowptr, int32_t *col, int64_t *launches);
-cudaError_t launch_assemble(const LaunchCtx &lc, int NX, int NY, int planestress, const int32_t *elem_desc,
+cudaError_t launch_assemble(const LaunchCtx &lc, int NX, int NY, int planestress, int ngeom, const int32_t *elem_desc,
                             const double *elstiff, const int32_t *rowptr, double *val, int64_t *launches);
 cudaError_t launch_kel(const LaunchCtx &lc, int64_t Nel, int planestress, const int32_t *elem_desc, const double *elstiff,
                        double *Kel, int64_t *launches);

@@ -253,7 +253,7 @@ extern "C" int plf_setupK(plf_ctx *ctx)
 {
     NEED_MESH("plf_setupK");
     LaunchCtx lc{ctx->stream, ctx->sm_count};
-    CK(launch_assemble(lc, ctx->NX, ctx->NY, ctx->planestress, ctx->d_desc, ctx->d_elstiff, ctx->d_rowptr, ctx->d_val, &ctx->launches));
+    CK(launch_assemble(lc, ctx->NX, ctx->NY, ctx->planestress, ctx->ngeom, ctx->d_desc, ctx->d_elstiff, ctx->d_rowptr, ctx->d_val, &ctx->launches));
     ctx->K_ready = true;
     return PLF_OK;
 }
@@ -263,7 +263,7 @@ extern "C" int plf_setupK_from_batch(plf_ctx *ctx, const plf_batch *b)
     NEED_MESH("plf_setupK_from_batch");
     if (!b || b->n != ctx->Nel) return fail(ctx, PLF_EINVAL, "plf_setupK_from_batch: batch must hold exactly Nel elements");
     LaunchCtx lc{ctx->stream, ctx->sm_count};
-    CK(launch_assemble(lc, ctx->NX, ctx->NY, ctx->planestress, ctx->d_desc, b->ctan, ctx->d_rowptr, ctx->d_val, &ctx->launches));
+    CK(launch_assemble(lc, ctx->NX, ctx->NY, ctx->planestress, ctx->ngeom, ctx->d_desc, b->ctan, ctx->d_rowptr, ctx->d_val, &ctx->launches));
     ctx->K_ready = true;
     return PLF_OK;
 }

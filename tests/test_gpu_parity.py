@@ -163,7 +163,7 @@ def setup_mesh_from_golden(ctx, g):
     return NX, NY
 
 
-@pytest.mark.parametrize('tiled', [2, 1, 0])
+@pytest.mark.parametrize('tiled', [2, 0])
 @pytest.mark.parametrize('case', KCASES)
 def test_K_bit_exact_vs_reference_golden(ctx, golden, case, tiled):
     g = golden('kmat_' + case)
@@ -193,7 +193,7 @@ def test_K_bit_exact_vs_reference_golden(ctx, golden, case, tiled):
 @pytest.mark.parametrize('shape', [(256, 256), (37, 95), (130, 3), (1, 70)])
 def test_K_tiled_equals_direct_on_ragged_meshes(ctx, golden, shape):
     """Tile-boundary cases (mesh sizes that are not multiples of the 4 x 32 node tile, one-element-wide meshes,
-    plane stress): the tiled assembly must reproduce the row-per-thread kernel bit for bit."""
+    plane stress): the staged assembly must reproduce the direct row-per-thread kernel bit for bit."""
     g = golden('response_hill')
     NX, NY = shape
     rng = np.random.default_rng(NX * 1000 + NY)
@@ -203,11 +203,11 @@ def test_K_tiled_equals_direct_on_ragged_meshes(ctx, golden, shape):
         tag = 'ps' if ps else 'pe'
         ctx.set_tangent(g[tag + '_ctan'][rng.integers(0, len(g[tag + '_ctan']), NX * NY)])
         vals = []
-        for tiled in (0, 1, 2):
+        for tiled in (0, 2):
             ctx.set_option('assembly_tiled', tiled)
             ctx.setupK()
             vals.append(ctx.get_csr()[2])
-        assert np.array_equal(vals[0], vals[1]) and np.array_equal(vals[0], vals[2])
+        assert np.array_equal(vals[0], vals[1])
     ctx.set_option('assembly_tiled', 2)
 
 
