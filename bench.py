@@ -11,8 +11,8 @@ nu=0.3, plane strain), synthetic spatially correlated element states (seeded) th
 (weak scaling, no data-path collective -- element updates and element rows are independent).
 
 `value`  : elements/s through (stress update + assembly), inputs resident in HBM, CUDA events, max over ranks.
-`e2e`    : same step through the C-ABI calls that take HOST buffers (plf_response_batch + plf_setupK_from_batch +
-           plf_get_csr), pinned host memory, H2D + D2H inside the timed region.
+`e2e`    : same step through the C-ABI call that takes HOST buffers (plf_step_host: states in, response results and
+           CSR(K) values out), pinned host memory, H2D + D2H inside the timed region.
 `roofline`: return-mapping kernel(s): 540 B/update over the measured launch time vs MEASURED_PEAKS.json.
 `cpu_baseline`: the CPU oracle (port of the reference algorithm, oracle/plf_oracle.c) on a bounded sample.
 --impl reference: the same step on the host cores only (oracle port, all threads), bounded sample per step.
@@ -372,11 +372,9 @@ def main():
         o_val = _lib.pinned_empty((ctx.nnz,))
 
         def e2e_step():
-            ctx.batch_upload(b, hs, he, hd)
-            ctx.batch_run(b)
-            ctx.setupK_from_batch(b)
-            ctx.batch_download(b, fy=o_fy, sig_out=o_sig, depl=o_dp, ctan=o_ct, nsteps=o_ns)
-            ctx.get_csr_values(o_val)
+            # one call, host buffers in and out: upload, return mapping + assembly and download pipelined over
+            # chunks of element columns (three streams, PCIe busy in both directions)
+            ctx.step_host(b, hs, he, hd, fy=o_fy, sig_out=o_sig, depl=o_dp, ctan=o_ct, nsteps=o_ns, kval=o_val)
         for _ in range(2):
             e2e_step()
         ke = max(3, min(K, 10))
@@ -389,11 +387,11 @@ def main():
         ctx.synchronize()
         barrier()
         e2e_ms = max_over_ranks(max(ctx.event_elapsed(4000, 4001), (time.perf_counter() - t0) * 1e3)) / ke
-        h2d = Nel * (3 * 48 + 4)
+        h2d = Nel * 3 * 48
         d2h = Nel * (8 + 48 + 48 + 288 + 4) + ctx.nnz * 8
         e2e = {'value': world * Nel / (e2e_ms * 1e-3), 'unit': 'elements/s', 'h2d_bytes_per_step': int(h2d),
                'd2h_bytes_per_step': int(d2h), 'ms_per_step': e2e_ms,
-               'api': 'plf_batch_upload + plf_batch_run + plf_setupK_from_batch + plf_batch_download + plf_get_csr (pinned host buffers)'}
+               'api': 'plf_step_host: (Nel,6) sig/epl/deps in; fy, sig, depl, grad_stiff, nsteps and the CSR(K) values out (pinned host buffers, chunked three-stream pipeline)'}
 
     if rank != 0:
         group.close()

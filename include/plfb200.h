@@ -153,6 +153,13 @@ int plf_get_csr(plf_ctx *ctx, int32_t *rowptr, int32_t *col, double *val); /* si
 /* Same assembly, element tangents taken from the `ctan` output of a device-resident batch of Nel elements (the
  * grad_stiff that Model.solve would store into Element.elstiff at model.py:1351) without a copy in between. */
 int plf_setupK_from_batch(plf_ctx *ctx, const plf_batch *b);
+/* One inner pass of Model.solve's non-linear loop with HOST buffers (model.py:1338-1361 followed by setupK, 954-977):
+ * (Nel,6) element states in; Material.response results (fy, sig, depl, grad_stiff, nsteps) and the nnz CSR values of
+ * the K assembled from the new tangents out.  Upload, update + assembly and download are pipelined over chunks of
+ * element columns on three streams (full-duplex PCIe); pass pinned buffers (plf_pinned_alloc).  Output pointers may
+ * be NULL.  Single-material meshes; `b` must hold Nel elements. */
+int plf_step_host(plf_ctx *ctx, plf_batch *b, const double *sig, const double *epl, const double *deps, double *fy,
+                  double *sig_out, double *depl, double *ctan, int32_t *nsteps, double *kval);
 
 /* ---- element state --------------------------------------------------------------------------------------------- */
 typedef enum plf_field {

@@ -301,6 +301,11 @@ class Context:
     def setupK_from_batch(self, b):
         self._ck(self.L.plf_setupK_from_batch(self.h, b))
 
+    def step_host(self, b, sig, epl, deps, fy=None, sig_out=None, depl=None, ctan=None, nsteps=None, kval=None):
+        """plf_step_host: Material.response for every mesh element + setupK, host buffers in and out, pipelined."""
+        self._ck(self.L.plf_step_host(self.h, b, _ptr(sig), _ptr(epl), _ptr(deps), _ptr(fy), _ptr(sig_out), _ptr(depl),
+                                      _ptr(ctan), _ptr(nsteps), _ptr(kval)))
+
     def get_csr_values(self, out):
         self._ck(self.L.plf_get_csr(self.h, None, None, _ptr(out)))
         return out

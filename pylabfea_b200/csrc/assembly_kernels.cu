@@ -216,14 +216,15 @@ constexpr int SN = 64;   // nodes per block
 // so the loads are unconditional; contributions of elements outside the mesh are skipped): four independent memory
 // round trips per thread instead of four dependent ones.
 template <bool PS, bool UNIFORM, int MINB>
-__global__ void __launch_bounds__(2 * SN, MINB) assemble_rows_staged_kernel(int NX, int NY, const int32_t *__restrict__ elem_desc,
+__global__ void __launch_bounds__(2 * SN, MINB) assemble_rows_staged_kernel(int NX, int NY, int j_first,
+                                                                            const int32_t *__restrict__ elem_desc,
                                                                             const double *__restrict__ elstiff,
                                                                             double *__restrict__ val)
 {
     __shared__ double2 s_out[SN * 2 * 9];
     const int tid = threadIdx.x;
     const int NnY = NY + 1;
-    const int j = blockIdx.y, k0 = blockIdx.x * SN;
+    const int j = j_first + blockIdx.y, k0 = blockIdx.x * SN;   // node column j (a launch covers columns j_first ...)
     const int c = tid & 1, k = k0 + (tid >> 1);
     const bool active = k <= NY;
     const int kmax = min(k0 + SN - 1, NY);
@@ -305,12 +306,35 @@ cudaError_t launch_csr_pattern(const LaunchCtx &lc, int NX, int NY, int32_t *row
     return cudaGetLastError();
 }
 
+// first CSR entry of node column j (host side of csr_row_start)
+int64_t csr_column_start(int NX, int NY, int j)
+{
+    const int64_t colw = 4ll * (3 * NY + 1);
+    if (j > NX) return colw * (3ll * (NX + 1) - 2);
+    return colw * ((j == 0) ? 0 : 3ll * j - 1);
+}
+
+// node columns [j_first, j_last) only (plf_step_host assembles a column range as soon as its elements are updated)
+cudaError_t launch_assemble_columns(const LaunchCtx &lc, int NX, int NY, int planestress, int ngeom, int j_first, int j_last,
+                                    const int32_t *elem_desc, const double *elstiff, double *val, int64_t *launches)
+{
+    if (j_last <= j_first) return cudaSuccess;
+    const dim3 grid((NY + 1 + SN - 1) / SN, j_last - j_first);
+#define ASM(PS, U, M) assemble_rows_staged_kernel<PS, U, M><<<grid, 2 * SN, 0, lc.stream>>>(NX, NY, j_first, elem_desc, elstiff, val)
+    const bool uni = (ngeom == 1);
+    if (planestress) { if (uni) ASM(true, true, 4); else ASM(true, false, 4); }
+    else { if (uni) ASM(false, true, 5); else ASM(false, false, 5); }
+#undef ASM
+    (*launches)++;
+    return cudaGetLastError();
+}
+
 cudaError_t launch_assemble(const LaunchCtx &lc, int NX, int NY, int planestress, int ngeom, const int32_t *elem_desc,
                             const double *elstiff, const int32_t *rowptr, double *val, int64_t *launches)
 {
     if (g_tiled != 0) {
         const dim3 grid((NY + 1 + SN - 1) / SN, NX + 1);
-#define ASM(PS, U, M) assemble_rows_staged_kernel<PS, U, M><<<grid, 2 * SN, 0, lc.stream>>>(NX, NY, elem_desc, elstiff, val)
+#define ASM(PS, U, M) assemble_rows_staged_kernel<PS, U, M><<<grid, 2 * SN, 0, lc.stream>>>(NX, NY, 0, elem_desc, elstiff, val)
         const bool uni = (ngeom == 1);
         if (planestress) { if (uni) ASM(true, true, 4); else ASM(true, false, 4); }
         else { if (uni) ASM(false, true, 5); else ASM(false, false, 5); }

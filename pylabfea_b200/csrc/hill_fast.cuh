@@ -430,6 +430,15 @@ __device__ __forceinline__ int hill_passB(const DevMat &m, double *s, double *ep
     return 2 | (corrected ? 4 : 0);
 }
 
+// sqrt through the fast reciprocal square root (x >= 0; ~1 ulp)
+__device__ __forceinline__ double fast_sqrt(double x) { return x * fast_rsqrt(x + 1e-300); }
+__device__ __forceinline__ double eps_eq6_fast(const double *e)
+{
+    const double a = e[0] * e[0] + e[1] * e[1] + e[2] * e[2];
+    const double b = e[3] * e[3] + e[4] * e[4] + e[5] * e[5];
+    return fast_sqrt((2. / 3.) * (a + 0.5 * b));
+}
+
 // sqrt(q) and 1/sqrt(q) of q >= 0 without a branch (q = 0: seq = 0 and a finite rs; a stress-free state has no flow
 // direction, the reference divides by zero there)
 __device__ __forceinline__ void seq_rs(double q, double &seq, double &rs)
@@ -451,17 +460,111 @@ __device__ __forceinline__ void seq_rs(double q, double &seq, double &rs)
 // The same reference algorithm (50 forward-Euler sub-steps, material.py:295-344), ~85 FP64 instructions per
 // sub-step instead of ~160.  Radial-return corrections (rare) are added through 6 shared-memory words per thread.
 // ------------------------------------------------------------------------------------------------------------
+// Elastic predictor and elastic/plastic split for the isotropic J2 modes: hill_prelude<2> with
+//   * CV (c deps) = c (CV deps): the split re-uses CV deps instead of two more matrix products,
+//   * the ratio fy0 / seq(CV deps) through the reciprocal square root that seq comes from,
+//   * sqrt of eps_eq through fast_rsqrt (no IEEE sqrt / division sequences on the path).
+__device__ __forceinline__ bool iso_prelude(const DevMat &m, double *s, const double *ep, const double *de, HillStep &P, double &fy)
+{
+    P.sflow0 = m.sy + (m.khard != 0. ? eps_eq6_fast(ep) * m.khard : 0.);
+    P.toler = PLF_YF_TOLERANCE * P.sflow0;
+    double cd[6], st[6];
+    cv_mul_t<2>(m, de, cd);
+#pragma unroll
+    for (int k = 0; k < 6; k++) st[k] = s[k] + cd[k];
+    if (!seq_gt_t<2>(m, st, P.sflow0 + P.toler)) {
+        double seq, iseq;
+        seq_inv_t<2>(m, st, seq, iseq);
+        fy = seq - P.sflow0;
+        if (fy < P.toler) {
+#pragma unroll
+            for (int k = 0; k < 6; k++) s[k] = st[k];
+            return true;
+        }
+    }
+    P.st_scal = 1.;
+    P.split = false;
+    double seq0, iseq0;
+    seq_inv_t<2>(m, s, seq0, iseq0);
+    const double fy0 = seq0 - P.sflow0;   // 259
+    if (fy0 < PLF_SPLIT_FY0) {            // 260-270
+        P.split = true;
+        double seqd, iseqd;
+        seq_inv_t<2>(m, cd, seqd, iseqd);
+        P.st_scal += fy0 * iseqd;
+        const double c = 1. - P.st_scal;
+#pragma unroll
+        for (int k = 0; k < 6; k++) {
+            s[k] = fma(c, cd[k], s[k]);
+            P.dr[k] = de[k] - de[k] * c;
+            P.cdr[k] = cd[k] - cd[k] * c;
+        }
+    } else {
+#pragma unroll
+        for (int k = 0; k < 6; k++) { P.dr[k] = de[k]; P.cdr[k] = cd[k]; }
+    }
+    return false;
+}
+
+// Pass A for the isotropic J2 modes (same contract as hill_passA): the trial step written with the identities of
+// hill_passB_iso -- CV a = 3G r n, hh = 3G + khard -- so that no gradient, no matrix product and no reciprocal is
+// evaluated; roughly half the FP64 instructions of hill_passA<2>.
+__device__ __forceinline__ int iso_passA(const DevMat &m, double *s, const double *ep, const double *de, double *dp, double *ca,
+                                         double &tc, double &tw, double &fy)
+{
+    HillStep P;
+#pragma unroll
+    for (int k = 0; k < 6; k++) { dp[k] = 0.; ca[k] = 0.; }
+    tc = 1.; tw = 0.;
+    if (iso_prelude(m, s, ep, de, P, fy)) return 0;
+    const double G3 = 3. * m.CV[21];
+    const double ihh = m.iso_ihh;
+    const double pc = (P.cdr[0] + P.cdr[1] + P.cdr[2]) * (1. / 3.);
+    const double dc[6] = {P.cdr[0] - pc, P.cdr[1] - pc, P.cdr[2] - pc, P.cdr[3], P.cdr[4], P.cdr[5]};
+    const double qc = 1.5 * (dc[0] * dc[0] + dc[1] * dc[1] + dc[2] * dc[2]) + 3. * (dc[3] * dc[3] + dc[4] * dc[4] + dc[5] * dc[5]);
+    const double p = (s[0] + s[1] + s[2]) * (1. / 3.);
+    const double n[6] = {s[0] - p, s[1] - p, s[2] - p, s[3], s[4], s[5]};
+    const double q2 = 1.5 * (n[0] * n[0] + n[1] * n[1] + n[2] * n[2]) + 3. * (n[3] * n[3] + n[4] * n[4] + n[5] * n[5]);
+    double seq, rs;
+    seq_rs(q2, seq, rs);
+    const double ncd = 1.5 * (n[0] * dc[0] + n[1] * dc[1] + n[2] * dc[2]) + 3. * (n[3] * dc[3] + n[4] * dc[4] + n[5] * dc[5]);
+    const double ythr = P.sflow0 + PLF_YF_TOLERANCE;
+    const bool yplus = fma(2., ncd, q2 + qc) > ythr * ythr;   // epl_dot 1031-1041 on the elastic trial stress
+    const double g = ncd * (rs * rs);
+    const double beta = g * (G3 * ihh);
+    const double gam = yplus ? g * (1.5 * ihh) : 0.;
+    double eplt[6], nt[6];
+#pragma unroll
+    for (int k = 0; k < 6; k++) {
+        dp[k] = (k < 3 ? gam : gam + gam) * n[k];
+        eplt[k] = ep[k] + dp[k];
+        nt[k] = fma(-beta, n[k], n[k] + dc[k]);
+    }
+    const double q2t = 1.5 * (nt[0] * nt[0] + nt[1] * nt[1] + nt[2] * nt[2]) + 3. * (nt[3] * nt[3] + nt[4] * nt[4] + nt[5] * nt[5]);
+    fy = fast_sqrt(q2t) - (m.sy + (m.khard != 0. ? eps_eq6_fast(eplt) * m.khard : 0.));
+    if (fy > P.toler) return -1;   // 288-291: subdivide
+    const double pt = p + pc;
+    s[0] = nt[0] + pt; s[1] = nt[1] + pt; s[2] = nt[2] + pt; s[3] = nt[3]; s[4] = nt[4]; s[5] = nt[5];
+    const double cf = G3 * rs;
+#pragma unroll
+    for (int k = 0; k < 6; k++) ca[k] = cf * n[k];
+    // grad_stiff = CV (1 - st_scal) [split] + (CV - ca ca^T / hh) st_scal   (269, 343 with nsteps = 1)
+    tc = (P.split ? (1. - P.st_scal) : 0.) + P.st_scal;
+    tw = ihh * P.st_scal;
+    return 1;
+}
+
 __device__ __forceinline__ int hill_passB_iso(const DevMat &m, double *s, double *epd, const double *de, double *xc, int xstride,
                                               double *gs, double &fy)
 {
     HillStep P;
-    hill_prelude<2>(m, s, epd, de, P, fy);   // cannot be elastic: pass A deferred this element
+    iso_prelude(m, s, epd, de, P, fy);   // cannot be elastic: pass A deferred this element
     const double inv = 1. / (double)PLF_MAXIT;
 #pragma unroll
     for (int k = 0; k < 6; k++) P.dr[k] *= inv;   // 290 (x * 0.02 instead of x / 50: 1 ulp, saves six IEEE divisions)
     cv_mul_t<2>(m, P.dr, P.cdr);
     const double G3 = 3. * m.CV[21];
-    const double ihh = 1. / (G3 + m.khard);
+    const double ihh = m.iso_ihh;
     const double bfac = G3 * ihh, wfac = G3 * G3 * ihh;
     const double pc = (P.cdr[0] + P.cdr[1] + P.cdr[2]) * (1. / 3.);
     double dc[6] = {P.cdr[0] - pc, P.cdr[1] - pc, P.cdr[2] - pc, P.cdr[3], P.cdr[4], P.cdr[5]};
@@ -610,7 +713,7 @@ __device__ __forceinline__ int hill_passB_iso2d(const DevMat &m, double *s, doub
     double pc, dc0, dc1, dc2, dc5, qc, c0, ythr2;
     {
         HillStep P;
-        hill_prelude<2>(m, s, epd, de, P, fy);   // cannot be elastic: pass A deferred this element
+        iso_prelude(m, s, epd, de, P, fy);   // cannot be elastic: pass A deferred this element
 #pragma unroll
         for (int k = 0; k < 6; k++) {
             P.dr[k] *= 1. / (double)PLF_MAXIT;   // 290
@@ -628,7 +731,7 @@ __device__ __forceinline__ int hill_passB_iso2d(const DevMat &m, double *s, doub
         f1 = P.split ? (1. - P.st_scal) : 0.;
     }
     const double G3 = 3. * m.CV[21];
-    const double ihh = 1. / (G3 + m.khard);
+    const double ihh = m.iso_ihh;
     const double bfac = G3 * ihh, wfac = G3 * G3 * ihh, gfac = 1.5 * ihh, K2 = m.khard * m.khard;
     double p = (s[0] + s[1] + s[2]) * (1. / 3.);
     double n0 = s[0] - p, n1 = s[1] - p, n2 = s[2] - p, n5 = s[5];

@@ -53,6 +53,19 @@ __device__ __forceinline__ void atomic_max_nonneg(double *addr, double v)
     atomicMax(reinterpret_cast<unsigned long long *>(addr), (unsigned long long)__double_as_longlong(v));
 }
 
+// analytic yield models that share the thread-per-element kernels: Hill-6p / J2 (HillModel) and Yld2004-18p (BarlatModel)
+template <class F>
+__device__ __forceinline__ void with_model(const DevMat &m, F f)
+{
+    if (m.kind == PLF_MAT_BARLAT) {
+        BarlatModel ym(m);
+        f(ym);
+    } else {
+        HillModel ym(m);
+        f(ym);
+    }
+}
+
 struct ElemStats {
     bool active = false, changed = false, nonconv = false;
     double hh = 0.;
@@ -215,6 +228,34 @@ __global__ void __launch_bounds__(128) sweep_hill_kernel(int64_t n, int NY, int 
     }
 }
 
+// sweep, thread per element, Yld2004-18p elements (unsplit response_core; FP64-bound: two 3x3 eigen-decompositions per
+// yield-function / gradient evaluation)
+__global__ void __launch_bounds__(128) sweep_barlat_kernel(int64_t n, int NY, int nit, const int32_t *__restrict__ desc,
+                                                           const double *__restrict__ sig, const double *__restrict__ epl,
+                                                           const double *__restrict__ du, double *__restrict__ elstiff,
+                                                           double *__restrict__ res_sig, double *__restrict__ res_depl,
+                                                           double *__restrict__ fyld, int32_t *__restrict__ nsteps,
+                                                           unsigned char *__restrict__ has_res, SweepStats *st)
+{
+    const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    ElemStats es;
+    if (e < n) {
+        const int d = __ldg(desc + e);
+        const DevMat &m = c_mat[d & 0xffff];
+        if (m.kind == PLF_MAT_BARLAT) {
+            double s[6], ep[6], de[6], dp[6], gs[21], fyv;
+            int ns = 0;
+#pragma unroll
+            for (int k = 0; k < 6; k++) { s[k] = __ldg(sig + e * 6 + k); ep[k] = __ldg(epl + e * 6 + k); }
+            element_strain(c_geom[d >> 16], NY, e, du, de);
+            BarlatModel ym(m);
+            const int br = response_core<0>(ym, m, s, ep, de, dp, gs, fyv, ns);
+            es = sweep_finish(m, e, nit, s, dp, gs, fyv, ns, br, ep, elstiff, res_sig, res_depl, fyld, nsteps, has_res);
+        }
+    }
+    stats_block(es, st);
+}
+
 // sweep, warp per element, one SVC material (SV table in shared memory)
 __global__ void __launch_bounds__(256) sweep_svc_kernel(int64_t n, int NY, int nit, int mid, const int32_t *__restrict__ desc,
                                                         const double *__restrict__ sig, const double *__restrict__ epl,
@@ -281,6 +322,13 @@ cudaError_t launch_sweep(const LaunchCtx &lc, const DevMat *hmats, int nmat, int
             (*launches)++;
         }
     }
+    bool any_barlat = false;
+    for (int i = 0; i < nmat; i++) any_barlat |= (hmats[i].kind == PLF_MAT_BARLAT);
+    if (any_barlat) {
+        sweep_barlat_kernel<<<grid, 128, 0, lc.stream>>>(Nel, NY, nit, desc, sig, epl, du, elstiff, res_sig, res_depl, fyld, nsteps,
+                                                         has_res, st);
+        (*launches)++;
+    }
     for (int i = 0; i < nmat; i++) {
         if (hmats[i].kind != PLF_MAT_SVC) continue;
         e = cudaMemsetAsync(&st->queue, 0, sizeof(unsigned long long), lc.stream);
@@ -326,24 +374,25 @@ __global__ void __launch_bounds__(128) commit_elements_kernel(int64_t Nel, int N
         element_strain(gc, NY, e, du, de);
 #pragma unroll
         for (int k = 0; k < 36; k++) C[k] = elstiff[e * 36 + k];
-        if (m.kind == PLF_MAT_HILL) {
+        if (m.kind == PLF_MAT_HILL || m.kind == PLF_MAT_BARLAT) {
             // Element.depl (model.py:424-437): Mat.epl_dot(sig, epl, CV, deps)
-            HillModel ym(m);
-            double cd[6], st[6], a[6], ca[6];
-            matvec6(m.CV, de, cd);
+            with_model(m, [&](const auto &ym) {
+                double cd[6], st[6], a[6], ca[6];
+                matvec6(m.CV, de, cd);
 #pragma unroll
-            for (int k = 0; k < 6; k++) st[k] = s[k] + cd[k];
-            const double sflow = m.sy + eps_eq6(ep) * m.khard;
-            if (ym.yf(st, sflow) > PLF_YF_TOLERANCE) {
-                ym.fgrad(s, a);
-                matvec6(m.CV, a, ca);
-                double hh = m.khard, acd = 0.;
+                for (int k = 0; k < 6; k++) st[k] = s[k] + cd[k];
+                const double sflow = m.sy + eps_eq6(ep) * m.khard;
+                if (ym.yf(st, sflow) > PLF_YF_TOLERANCE) {
+                    ym.fgrad(s, a);
+                    matvec6(m.CV, a, ca);
+                    double hh = m.khard, acd = 0.;
 #pragma unroll
-                for (int k = 0; k < 6; k++) { hh += a[k] * ca[k]; acd += a[k] * cd[k]; }
-                const double lam = acd / hh;
+                    for (int k = 0; k < 6; k++) { hh += a[k] * ca[k]; acd += a[k] * cd[k]; }
+                    const double lam = acd / hh;
 #pragma unroll
-                for (int k = 0; k < 6; k++) ep[k] += lam * a[k];
-            }
+                    for (int k = 0; k < 6; k++) ep[k] += lam * a[k];
+                }
+            });
         }
         matvec6(C, de, ds);
 #pragma unroll
@@ -451,20 +500,21 @@ __global__ void __launch_bounds__(128) scf_elements_kernel(int64_t Nel, int NY, 
 #pragma unroll
     for (int k = 0; k < 36; k++) C[k] = elstiff[e * 36 + k];
     matvec6(C, de, ds);
-    HillModel ym(m);
-    const double sref = ym.seq(ds);   // Stress(el.dsig()).seq(el.Mat), 1040
-    if (!(sref > 0.1)) return;
+    with_model(m, [&](const auto &ym) {
+        const double sref = ym.seq(ds);   // Stress(el.dsig()).seq(el.Mat), 1040
+        if (!(sref > 0.1)) return;
 #pragma unroll
-    for (int k = 0; k < 6; k++) { s[k] = sig[e * 6 + k]; ep[k] = epl[e * 6 + k]; }
-    const double sflow = m.sy + eps_eq6(ep) * m.khard;
-    const double yf0 = ym.yf(s, sflow);
-    if (yf0 < PLF_SPLIT_FY0) {
-        hval[e] = fmin(1., -yf0 / sref);   // appended twice (1050 and 1054)
-        mult[e] = 2;
-    } else {
-        hval[e] = fmin(1., sqrt(1.5) * sflow / sref);
-        mult[e] = 1;
-    }
+        for (int k = 0; k < 6; k++) { s[k] = sig[e * 6 + k]; ep[k] = epl[e * 6 + k]; }
+        const double sflow = m.sy + eps_eq6(ep) * m.khard;
+        const double yf0 = ym.yf(s, sflow);
+        if (yf0 < PLF_SPLIT_FY0) {
+            hval[e] = fmin(1., -yf0 / sref);   // appended twice (1050 and 1054)
+            mult[e] = 2;
+        } else {
+            hval[e] = fmin(1., sqrt(1.5) * sflow / sref);
+            mult[e] = 1;
+        }
+    });
 }
 
 __global__ void __launch_bounds__(256) scf_svc_kernel(int64_t Nel, int NY, int mid, const int32_t *__restrict__ desc,

@@ -101,6 +101,9 @@ extern "C" void plf_destroy(plf_ctx *ctx)
     cudaEventDestroy(ctx->ev0);
     cudaEventDestroy(ctx->ev1);
     for (cudaEvent_t ev : ctx->ev_pool) if (ev) cudaEventDestroy(ev);
+    for (cudaEvent_t ev : ctx->ev_step) if (ev) cudaEventDestroy(ev);
+    if (ctx->s_in) cudaStreamDestroy(ctx->s_in);
+    if (ctx->s_out) cudaStreamDestroy(ctx->s_out);
     cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
@@ -259,6 +262,7 @@ extern "C" int plf_set_materials(plf_ctx *ctx, int nmat, const plf_material *mat
             const double C11 = C[0], C12 = C[1], C44 = C[21];
             d.cv_iso = (d.cv_block && d.cv_sym && C[7] == C11 && C[14] == C11 && C[2] == C12 && C[8] == C12 && C[28] == C44 &&
                         C[35] == C44 && C44 > 0. && fabs(C11 - C12 - 2. * C44) <= 1e-13 * fabs(C11)) ? 1 : 0;
+            d.iso_ihh = 1. / (3. * C44 + d.khard);
         }
         memcpy(d.bar_m1, m.barlat_m1, sizeof d.bar_m1);
         memcpy(d.bar_m2, m.barlat_m2, sizeof d.bar_m2);
@@ -414,9 +418,10 @@ static int prim_call(plf_ctx *ctx, int op, int mat, int64_t n, const double *sig
     if (!ctx || n < 0 || !sig || !out) return fail(ctx, PLF_EINVAL, "batched constitutive call: bad arguments");
     if (mat < 0 || mat >= ctx->nmat) return fail(ctx, PLF_EINVAL, "batched constitutive call: material id out of range");
     const DevMat &m = ctx->hmats[mat];
-    if ((op == OP_FGRAD || op == OP_EPLDOT || op == OP_CTAN) && (m.kind == PLF_MAT_BARLAT || m.tresca))
-        // material.py:822-825: the reference raises ValueError for these
-        return fail(ctx, PLF_EUNSUPPORTED, "calc_fgrad: analytical gradient for Barlat / Tresca not implemented");
+    if ((op == OP_FGRAD || op == OP_EPLDOT || op == OP_CTAN) && m.tresca)
+        // material.py:824-825: the reference raises ValueError for Tresca.  (It also raises for Barlat, 822-823; the
+        // Barlat gradient is implemented here -- barlat_seq_grad -- because BASELINE config 5 needs the return mapping.)
+        return fail(ctx, PLF_EUNSUPPORTED, "calc_fgrad: analytical gradient for Tresca not implemented");
     if (n == 0) return PLF_OK;
     CK(cudaSetDevice(ctx->device));
     int rc = batch_reserve(ctx, ctx->scratch, n);

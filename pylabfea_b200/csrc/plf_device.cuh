@@ -25,6 +25,7 @@ struct DevMat {
     double CV[36];   // Element.CV (plane-strain or plane-stress variant)
     double SV[36];   // compliance used by the radial-return correction (material.py:315-320)
     double E, nu;
+    double iso_ihh;   // 1 / (3 C44 + khard): the constant hardening denominator of the isotropic J2 modes
     double gamma, rho, scale_seq, inv_scale_seq;
     const double *sv;    // device, SoA [6][nsv_pad]
     const double *dual;  // device, [nsv_pad] (zero padded)
@@ -131,6 +132,88 @@ __device__ inline double barlat_seq(const DevMat &m, const double *sv)
     return pow(0.25 * s, 1. / m.bar_exp);
 }
 
+// eigenvalues w[e] and orthonormal eigenvectors V[i][e] of a symmetric 3x3 given in Voigt order: cyclic Jacobi
+__device__ inline void sym3_eigv(const double *v, double *w, double V[3][3])
+{
+    double A[3][3] = {{v[0], v[5], v[4]}, {v[5], v[1], v[3]}, {v[4], v[3], v[2]}};
+    for (int i = 0; i < 3; i++)
+        for (int j = 0; j < 3; j++) V[i][j] = (i == j) ? 1. : 0.;
+    for (int sweep = 0; sweep < 30; sweep++) {
+        const double off = fabs(A[0][1]) + fabs(A[0][2]) + fabs(A[1][2]);
+        const double dia = fabs(A[0][0]) + fabs(A[1][1]) + fabs(A[2][2]);
+        if (off <= 1e-300 || off <= 1e-18 * dia) break;
+        for (int p = 0; p < 2; p++)
+            for (int q = p + 1; q < 3; q++) {
+                if (A[p][q] == 0.) continue;
+                const double th = (A[q][q] - A[p][p]) / (2. * A[p][q]);
+                const double t = copysign(1., th) / (fabs(th) + sqrt(th * th + 1.));
+                const double c = rsqrt(t * t + 1.), sn = t * c;
+                const int r = 3 - p - q;
+                const double apq = A[p][q], arp = A[r][p], arq = A[r][q];
+                A[p][p] -= t * apq;
+                A[q][q] += t * apq;
+                A[p][q] = A[q][p] = 0.;
+                A[r][p] = A[p][r] = c * arp - sn * arq;
+                A[r][q] = A[q][r] = sn * arp + c * arq;
+                for (int k = 0; k < 3; k++) {
+                    const double vp = V[k][p], vq = V[k][q];
+                    V[k][p] = c * vp - sn * vq;
+                    V[k][q] = sn * vp + c * vq;
+                }
+            }
+    }
+    w[0] = A[0][0]; w[1] = A[1][1]; w[2] = A[2][2];
+}
+
+// Gradient of the Yld2004-18p equivalent stress (material.py:678-702) with respect to the Voigt stress.  The reference
+// has no analytic gradient for Barlat (calc_fgrad raises, material.py:822-823); this is the chain rule through
+//   seq = (phi / 4)^(1/a),  phi = sum_ij |S'_i - S''_j|^a,  S' / S'' = eigenvalues of L' dev(sig) / L'' dev(sig),
+// with d(lambda_e) / d(Voigt k) = (v1^2, v2^2, v3^2, 2 v2 v3, 2 v1 v3, 2 v1 v2) of eigenvector e (phi is a symmetric
+// function of the eigenvalues, so any orthonormal eigenbasis gives the gradient, also for repeated eigenvalues).
+// Returns seq.
+__device__ inline double barlat_seq_grad(const DevMat &m, const double *sv, double *g)
+{
+    const double p = (sv[0] + sv[1] + sv[2]) / 3.;
+    const double sd[6] = {sv[0] - p, sv[1] - p, sv[2] - p, sv[3], sv[4], sv[5]};
+    double st1[6], st2[6], p1[3], p2[3], V1[3][3], V2[3][3];
+    matvec6(m.bar_m1, sd, st1);
+    matvec6(m.bar_m2, sd, st2);
+    sym3_eigv(st1, p1, V1);
+    sym3_eigv(st2, p2, V2);
+    const double a = m.bar_exp;
+    double phi = 0., g1[3] = {0., 0., 0.}, g2[3] = {0., 0., 0.};
+    for (int i = 0; i < 3; i++)
+        for (int j = 0; j < 3; j++) {
+            const double d = p1[i] - p2[j], ad = fabs(d);
+            const double pw = pow(ad, a - 1.);
+            phi += pw * ad;
+            const double sg = copysign(pw, d);   // |d|^(a-1) sign(d)
+            g1[i] += sg;
+            g2[j] -= sg;
+        }
+    const double seq = pow(0.25 * phi, 1. / a);
+    double E1[6] = {0., 0., 0., 0., 0., 0.}, E2[6] = {0., 0., 0., 0., 0., 0.};
+    for (int e = 0; e < 3; e++) {
+        const double x = V1[0][e], y = V1[1][e], z = V1[2][e];
+        E1[0] += g1[e] * x * x; E1[1] += g1[e] * y * y; E1[2] += g1[e] * z * z;
+        E1[3] += g1[e] * 2. * y * z; E1[4] += g1[e] * 2. * x * z; E1[5] += g1[e] * 2. * x * y;
+        const double x2 = V2[0][e], y2 = V2[1][e], z2 = V2[2][e];
+        E2[0] += g2[e] * x2 * x2; E2[1] += g2[e] * y2 * y2; E2[2] += g2[e] * z2 * z2;
+        E2[3] += g2[e] * 2. * y2 * z2; E2[4] += g2[e] * 2. * x2 * z2; E2[5] += g2[e] * 2. * x2 * y2;
+    }
+    double h[6];
+    for (int k = 0; k < 6; k++) {
+        double t = 0.;
+        for (int r = 0; r < 6; r++) t += m.bar_m1[6 * r + k] * E1[r] + m.bar_m2[6 * r + k] * E2[r];   // L'^T E1 + L''^T E2
+        h[k] = t;
+    }
+    const double hm = (h[0] + h[1] + h[2]) / 3.;
+    const double f = seq / phi;   // d seq / d phi = seq / (a phi); the factor a of d|d|^a cancels it
+    g[0] = f * (h[0] - hm); g[1] = f * (h[1] - hm); g[2] = f * (h[2] - hm);
+    g[3] = f * h[3]; g[4] = f * h[4]; g[5] = f * h[5];
+    return seq;
+}
+
 __device__ __forceinline__ void hill_fgrad(const DevMat &m, const double *s, double seq, double *a)
 {
     double p = (s[0] + s[1] + s[2]) / 3.;
@@ -157,6 +240,19 @@ struct HillModel {
     __device__ __forceinline__ double yf(const double *s, double sflow) const { return seq(s) - sflow; }
     __device__ __forceinline__ double full_yf(const double *s, double sflow) const { return seq(s) - sflow; }
     __device__ __forceinline__ void fgrad(const double *s, double *a) const { hill_fgrad(m, s, hill_seq(m, s), a); }
+};
+
+// Yld2004-18p yield model (thread per element): equivalent stress of the reference, analytic gradient from the chain
+// rule (the reference raises in calc_fgrad for Barlat, so its return mapping cannot run; BASELINE config 5 asks for it)
+struct BarlatModel {
+    static constexpr bool is_ml = false;
+    const DevMat &m;
+    __device__ explicit BarlatModel(const DevMat &mm) : m(mm) {}
+    __device__ __forceinline__ double khard() const { return m.khard; }
+    __device__ __forceinline__ double seq(const double *s) const { return barlat_seq(m, s); }
+    __device__ __forceinline__ double yf(const double *s, double sflow) const { return barlat_seq(m, s) - sflow; }
+    __device__ __forceinline__ double full_yf(const double *s, double sflow) const { return barlat_seq(m, s) - sflow; }
+    __device__ __forceinline__ void fgrad(const double *s, double *a) const { barlat_seq_grad(m, s, a); }
 };
 
 // ------------------------------------------------------------------------------------------------------------

@@ -46,6 +46,9 @@ void assembly_set_tiled(int on);   // 1 (default): shared-memory tiled assembly;
 cudaError_t launch_csr_pattern(const LaunchCtx &lc, int NX, int NY, int32_t *rowptr, int32_t *col, int64_t *launches);
 cudaError_t launch_assemble(const LaunchCtx &lc, int NX, int NY, int planestress, int ngeom, const int32_t *elem_desc,
                             const double *elstiff, const int32_t *rowptr, double *val, int64_t *launches);
+int64_t csr_column_start(int NX, int NY, int j);
+cudaError_t launch_assemble_columns(const LaunchCtx &lc, int NX, int NY, int planestress, int ngeom, int j_first, int j_last,
+                                    const int32_t *elem_desc, const double *elstiff, double *val, int64_t *launches);
 cudaError_t launch_kel(const LaunchCtx &lc, int64_t Nel, int planestress, const int32_t *elem_desc, const double *elstiff,
                        double *Kel, int64_t *launches);
 

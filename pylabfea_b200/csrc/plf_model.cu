@@ -268,6 +268,74 @@ extern "C" int plf_setupK_from_batch(plf_ctx *ctx, const plf_batch *b)
     return PLF_OK;
 }
 
+// One inner pass of the load-step loop with HOST buffers (model.py:1338-1361 + setupK): element states in, response
+// results and CSR(K) values out.  The mesh is cut into chunks of element columns; chunk c is uploaded on one copy
+// stream while chunk c-1 is updated and its node columns are assembled on the compute stream and chunk c-2 drains
+// to the host on a second copy stream, so that the PCIe link is busy in both directions for the whole call
+// (host buffers should be pinned, plf_host_alloc).  Any output pointer may be NULL.
+extern "C" int plf_step_host(plf_ctx *ctx, plf_batch *b, const double *sig, const double *epl, const double *deps, double *fy,
+                             double *sig_out, double *depl, double *ctan, int32_t *nsteps, double *kval)
+{
+    NEED_MESH("plf_step_host");
+    if (!b || b->n != ctx->Nel || !sig || !epl || !deps)
+        return fail(ctx, PLF_EINVAL, "plf_step_host: batch must hold exactly Nel elements; sig, epl, deps are required");
+    if (ctx->nmat == 0) return fail(ctx, PLF_ESTATE, "plf_step_host: no materials set");
+    CK(cudaSetDevice(ctx->device));
+    if (!ctx->s_in) {
+        CK(cudaStreamCreateWithFlags(&ctx->s_in, cudaStreamNonBlocking));
+        CK(cudaStreamCreateWithFlags(&ctx->s_out, cudaStreamNonBlocking));
+    }
+    const int NX = ctx->NX, NY = ctx->NY;
+    const int nchunk = std::max(1, std::min(NX, 8));
+    while ((int)ctx->ev_step.size() < 2 * nchunk + 1) {
+        cudaEvent_t e;
+        CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        ctx->ev_step.push_back(e);
+    }
+    // everything queued earlier on the compute stream (previous steps reading / writing the batch) comes first
+    CK(cudaEventRecord(ctx->ev_step[2 * nchunk], ctx->stream));
+    CK(cudaStreamWaitEvent(ctx->s_in, ctx->ev_step[2 * nchunk], 0));
+    CK(cudaStreamWaitEvent(ctx->s_out, ctx->ev_step[2 * nchunk], 0));
+    CK(cudaMemsetAsync(b->mat_id, 0, (size_t)b->n * sizeof(int32_t), ctx->stream));
+    if (ctx->nmat > 1)   // material ids of the mesh elements (descriptor low half)
+        return fail(ctx, PLF_EUNSUPPORTED, "plf_step_host: single-material meshes only (use plf_sweep for mixed meshes)");
+    LaunchCtx lc{ctx->stream, ctx->sm_count, ctx->passb_wsmem, ctx->passa_direct, ctx->max_fm, ctx->minb, ctx->k1_only};
+    for (int c = 0; c < nchunk; c++) {
+        const int ja = (int)((int64_t)NX * c / nchunk), jb = (int)((int64_t)NX * (c + 1) / nchunk);   // element columns
+        const int64_t e0 = (int64_t)ja * NY, ne = (int64_t)(jb - ja) * NY;
+        const size_t o6 = 6 * (size_t)e0, n6 = 6 * (size_t)ne * sizeof(double);
+        CK(cudaMemcpyAsync(b->sig + o6, sig + o6, n6, cudaMemcpyHostToDevice, ctx->s_in));
+        CK(cudaMemcpyAsync(b->epl + o6, epl + o6, n6, cudaMemcpyHostToDevice, ctx->s_in));
+        CK(cudaMemcpyAsync(b->deps + o6, deps + o6, n6, cudaMemcpyHostToDevice, ctx->s_in));
+        CK(cudaEventRecord(ctx->ev_step[2 * c], ctx->s_in));
+        CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_step[2 * c], 0));
+        CK(launch_response(lc, ctx->hmats, ctx->nmat, ne, b->mat_id + e0, b->sig + o6, b->epl + o6, b->deps + o6, b->fy + e0,
+                           b->sig_out + o6, b->depl + o6, b->ctan + 36 * (size_t)e0, b->nsteps + e0, b->worklist + e0,
+                           (unsigned int *)(ctx->d_scalars + 16), (unsigned long long *)(ctx->d_scalars + 8), ctx->compact,
+                           &ctx->launches));
+        // node columns whose elements are all updated now: ja .. jb-1 (column jb needs the next chunk), plus NX at the end
+        const int na = ja, nb = (c == nchunk - 1) ? NX + 1 : jb;
+        CK(launch_assemble_columns(lc, NX, NY, ctx->planestress, ctx->ngeom, na, nb, ctx->d_desc, b->ctan, ctx->d_val,
+                                   &ctx->launches));
+        CK(cudaEventRecord(ctx->ev_step[2 * c + 1], ctx->stream));
+        CK(cudaStreamWaitEvent(ctx->s_out, ctx->ev_step[2 * c + 1], 0));
+        if (fy) CK(cudaMemcpyAsync(fy + e0, b->fy + e0, (size_t)ne * sizeof(double), cudaMemcpyDeviceToHost, ctx->s_out));
+        if (nsteps) CK(cudaMemcpyAsync(nsteps + e0, b->nsteps + e0, (size_t)ne * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->s_out));
+        if (sig_out) CK(cudaMemcpyAsync(sig_out + o6, b->sig_out + o6, n6, cudaMemcpyDeviceToHost, ctx->s_out));
+        if (depl) CK(cudaMemcpyAsync(depl + o6, b->depl + o6, n6, cudaMemcpyDeviceToHost, ctx->s_out));
+        if (ctan) CK(cudaMemcpyAsync(ctan + 36 * (size_t)e0, b->ctan + 36 * (size_t)e0, 36 * (size_t)ne * sizeof(double),
+                                     cudaMemcpyDeviceToHost, ctx->s_out));
+        if (kval) {
+            const int64_t v0 = csr_column_start(NX, NY, na), v1 = csr_column_start(NX, NY, nb);
+            CK(cudaMemcpyAsync(kval + v0, ctx->d_val + v0, (size_t)(v1 - v0) * sizeof(double), cudaMemcpyDeviceToHost, ctx->s_out));
+        }
+    }
+    ctx->K_ready = true;
+    CK(cudaStreamSynchronize(ctx->s_out));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return PLF_OK;
+}
+
 extern "C" int plf_get_csr(plf_ctx *ctx, int32_t *rowptr, int32_t *col, double *val)
 {
     NEED_MESH("plf_get_csr");

@@ -20,6 +20,8 @@ struct plf_ctx {
     int device = 0;
     cudaStream_t stream = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    cudaStream_t s_in = nullptr, s_out = nullptr;            // copy streams of plf_step_host (created on first use)
+    std::vector<cudaEvent_t> ev_step;                        // per-chunk events of plf_step_host
     std::vector<cudaEvent_t> ev_pool;
     std::string err;
     int sm_count = 0, cc_major = 0, cc_minor = 0;

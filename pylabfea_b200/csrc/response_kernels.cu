@@ -137,7 +137,7 @@ __device__ __forceinline__ void passA_tile(int64_t n, int64_t tile, double *s_in
                                            double *__restrict__ ctan, int32_t *__restrict__ nsteps, int32_t *worklist,
                                            unsigned int *work_count)
 {
-    constexpr int FA = FM >= 3 ? 2 : FM;   // pass A of the isotropic modes is the J2 code
+    constexpr int FA = FM >= 3 ? 2 : FM;   // (the isotropic modes use iso_passA)
     const int tid = threadIdx.x;
     double *s_sig = s_in, *s_epl = s_in + RB * 6, *s_dep = s_in + 2 * RB * 6;
     const int64_t base = tile * RB;
@@ -169,7 +169,13 @@ __device__ __forceinline__ void passA_tile(int64_t n, int64_t tile, double *s_in
 #pragma unroll
                 for (int k = 0; k < 6; k++) { s[k] += t[k]; dp[k] = 0.; ca[k] = 0.; }
             } else {
-                br = hill_passA<FA>(m, s, ep, de, dp, ca, tc, tw, fyv);
+                if (FM == 5) {   // diagnostics only (k1_only = 2): no constitutive math, same data movement
+                    br = 1;
+#pragma unroll
+                    for (int k = 0; k < 6; k++) { dp[k] = ep[k]; ca[k] = de[k]; }
+                    fyv = s[0];
+                } else
+                br = (FM >= 3) ? iso_passA(m, s, ep, de, dp, ca, tc, tw, fyv) : hill_passA<FA>(m, s, ep, de, dp, ca, tc, tw, fyv);
             }
             if (br < 0) {
                 defer = true;
@@ -459,11 +465,11 @@ __device__ __forceinline__ void prim_eval(const Model &ym, const DevMat &m, int 
                                           const double *de, const double *ld, double *out, bool writer, int64_t e)
 {
     if (op == OP_SEQ) {
-        double v = (m.kind == PLF_MAT_BARLAT) ? barlat_seq(m, s) : ym.seq(s);
+        double v = ym.seq(s);
         if (writer) out[e] = v;
     } else if (op == OP_YF) {
         double sflow = m.sy + eps_eq6(ep) * m.khard;
-        double v = (m.kind == PLF_MAT_BARLAT) ? barlat_seq(m, s) - sflow : ym.yf(s, sflow);
+        double v = ym.yf(s, sflow);
         if (writer) out[e] = v;
     } else if (op == OP_MLFULL) {
         double sflow = m.sy + eps_eq6(ep) * m.khard;
@@ -520,6 +526,57 @@ __global__ void __launch_bounds__(128) prim_hill_kernel(int op, int mid, int64_t
     prim_eval(ym, m, op, s, ep, de, nullptr, out, true, e);
 }
 
+// Barlat Yld2004-18p: thread per element (two 3x3 eigen-decompositions per yield-function / gradient evaluation;
+// FP64-bound, not tuned: BASELINE config 5 only)
+__global__ void __launch_bounds__(128) prim_barlat_kernel(int op, int mid, int64_t n, const double *__restrict__ sig,
+                                                          const double *__restrict__ epl, const double *__restrict__ deps,
+                                                          double *__restrict__ out)
+{
+    const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= n) return;
+    const DevMat &m = c_mat[mid];
+    double s[6], ep[6] = {0, 0, 0, 0, 0, 0}, de[6] = {0, 0, 0, 0, 0, 0};
+#pragma unroll
+    for (int k = 0; k < 6; k++) {
+        s[k] = sig[e * 6 + k];
+        if (epl) ep[k] = epl[e * 6 + k];
+        if (deps) de[k] = deps[e * 6 + k];
+    }
+    BarlatModel ym(m);
+    prim_eval(ym, m, op, s, ep, de, nullptr, out, true, e);
+}
+
+__global__ void __launch_bounds__(128) response_barlat_kernel(int64_t n, int mid, const int32_t *__restrict__ mat_id,
+                                                              const double *__restrict__ sig, const double *__restrict__ epl,
+                                                              const double *__restrict__ deps, double *__restrict__ fy,
+                                                              double *__restrict__ sig_out, double *__restrict__ depl_out,
+                                                              double *__restrict__ ctan, int32_t *__restrict__ nsteps)
+{
+    const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= n) return;
+    if (mat_id && mat_id[e] != mid) return;
+    const DevMat &m = c_mat[mid];
+    double s[6], ep[6], de[6], dp[6], gs[21], fyv;
+    int ns;
+#pragma unroll
+    for (int k = 0; k < 6; k++) {
+        s[k] = __ldg(sig + e * 6 + k);
+        ep[k] = __ldg(epl + e * 6 + k);
+        de[k] = __ldg(deps + e * 6 + k);
+    }
+    BarlatModel ym(m);
+    response_core<0>(ym, m, s, ep, de, dp, gs, fyv, ns);
+    if (fy) fy[e] = fyv;
+    if (nsteps) nsteps[e] = ns;
+    if (sig_out)
+#pragma unroll
+        for (int k = 0; k < 6; k++) sig_out[e * 6 + k] = s[k];
+    if (depl_out)
+#pragma unroll
+        for (int k = 0; k < 6; k++) depl_out[e * 6 + k] = dp[k];
+    if (ctan) expand_sym(gs, ctan + e * 36, 1);
+}
+
 __global__ void __launch_bounds__(SVC_WARPS * 32) prim_svc_kernel(int op, int mid, int64_t n, const double *__restrict__ sig,
                                                                   const double *__restrict__ epl, const double *__restrict__ deps,
                                                                   const double *__restrict__ ld, double *__restrict__ out)
@@ -573,7 +630,9 @@ cudaError_t response_init()
     if ((e = big_smem(response_passA_kernel<true, 0, false>, k1a_smem(false))) != cudaSuccess) return e;
     if ((e = big_smem(response_passA_kernel<true, 1, false>, k1a_smem(false))) != cudaSuccess) return e;
     if ((e = big_smem(response_passA_kernel<true, 2, false>, k1a_smem(false))) != cudaSuccess) return e;
+    if ((e = big_smem(response_passA_kernel<true, 3, false>, k1a_smem(false))) != cudaSuccess) return e;
     if ((e = big_smem(response_passA_kernel<true, 4, false>, k1a_smem(false))) != cudaSuccess) return e;
+    if ((e = big_smem(response_passA_kernel<true, 5, false>, k1a_smem(false))) != cudaSuccess) return e;
     if ((e = big_smem(response_generic_kernel, k1_smem())) != cudaSuccess) return e;
     if ((e = big_smem(response_svc_kernel, 227 * 1024)) != cudaSuccess) return e;
     return big_smem(prim_svc_kernel, 227 * 1024);
@@ -620,13 +679,15 @@ cudaError_t launch_response(const LaunchCtx &lc, const DevMat *hmats, int nmat, 
             response_passA_kernel<S, F, false><<<pgrid, RB, k1a_smem(false), lc.stream>>>(n, mat_id, sig, epl, deps, fy, sig_out, \
                                                                                           depl, ctan, nsteps, worklist, work_count); \
     } while (0)
-            if (!single) PASSA(false, 0);
+            if (lc.k1_only == 2) PASSA(true, 5);
+            else if (!single) PASSA(false, 0);
             else if (fm == 4) PASSA(true, 4);
-            else if (fm >= 2) PASSA(true, 2);
+            else if (fm == 3) PASSA(true, 3);
+            else if (fm == 2) PASSA(true, 2);
             else if (fm == 1) PASSA(true, 1);
             else PASSA(true, 0);
 #undef PASSA
-            if (lc.k1_only == 1) {   // diagnostics: time pass A alone
+            if (lc.k1_only) {   // diagnostics: time pass A alone (2: without the constitutive math)
                 cudaMemsetAsync(work_count, 0, 3 * sizeof(unsigned int), lc.stream);
                 (*launches)++;
                 return cudaGetLastError();
@@ -657,6 +718,12 @@ cudaError_t launch_response(const LaunchCtx &lc, const DevMat *hmats, int nmat, 
         }
     }
     for (int i = 0; i < nmat; i++) {
+        if (hmats[i].kind != PLF_MAT_BARLAT) continue;
+        response_barlat_kernel<<<grid, RB, 0, lc.stream>>>(n, i, nmat > 1 ? mat_id : nullptr, sig, epl, deps, fy, sig_out, depl,
+                                                           ctan, nsteps);
+        (*launches)++;
+    }
+    for (int i = 0; i < nmat; i++) {
         if (hmats[i].kind != PLF_MAT_SVC) continue;
         cudaMemsetAsync(queue, 0, sizeof(unsigned long long), lc.stream);
         int blocks = lc.sm_count * 2;
@@ -679,6 +746,8 @@ cudaError_t launch_prim(const LaunchCtx &lc, const DevMat *hmats, int op, int mi
         int64_t need = (n + SVC_WARPS - 1) / SVC_WARPS;
         if (blocks > need) blocks = (int)need;
         prim_svc_kernel<<<blocks, SVC_WARPS * 32, svc_smem(hmats[mid]), lc.stream>>>(op, mid, n, sig, epl, deps, ld, out);
+    } else if (hmats[mid].kind == PLF_MAT_BARLAT) {
+        prim_barlat_kernel<<<(unsigned)((n + 127) / 128), 128, 0, lc.stream>>>(op, mid, n, sig, epl, deps, out);
     } else {
         prim_hill_kernel<<<(unsigned)((n + 127) / 128), 128, 0, lc.stream>>>(op, mid, n, sig, epl, deps, out);
     }

@@ -340,8 +340,10 @@ class Material(object):
         return float(out[0])
 
     def calc_fgrad(self, sig, epl=None, seq=None, ana=False, **_ignored):
-        """Gradient of the yield function w.r.t. stress (material.py:704-858).  Raises ValueError for Barlat / Tresca
-        like the reference (822-825)."""
+        """Gradient of the yield function w.r.t. stress (material.py:704-858).  Raises ValueError for Tresca like the
+        reference (824-825).  Deviation: the reference also raises for Barlat (822-823) and therefore cannot run a
+        Barlat return mapping at all; here the Yld2004-18p gradient is implemented analytically on the device
+        (barlat_seq_grad, chain rule through the two eigen-decompositions), which is what BASELINE config 5 needs."""
         a, single = self._as_rows(sig, 'calc_fgrad')
         if epl is not None and np.shape(epl) != np.shape(sig):
             raise ValueError('Parameter sig and epl must have the same shape.')
@@ -349,6 +351,8 @@ class Material(object):
         if self.ML_yf:
             self.khard = 0.
             self.msg['gradient'] = 'gradient to ML_yf'
+        elif self.barlat:
+            self.msg['gradient'] = 'analytical, Barlat Yld2004-18p, full stress'
         else:
             self.msg['gradient'] = 'analytical, 6-parameter Hill, full stress'
         return out[0] if single else out

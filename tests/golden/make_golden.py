@@ -15,8 +15,12 @@ reads the committed .npz fixtures.  Every array written here is an output of unm
   svc_<name>.npz      a trained sklearn SVC (support vectors, dual coefs, intercept, gamma, scale_seq) plus
                       calc_yf / calc_fgrad / ML_full_yf / response outputs of the reference on it.
   barlat.npz          Material.calc_seq for Yld2004-18p (material.py:678-702).
+  barlat_response.npz Material.response / epl_dot / C_tan of the reference for Yld2004-18p materials.  The reference
+                      has no Barlat gradient (calc_fgrad raises, material.py:822-823), so a test-only subclass
+                      supplies it as 4th-order central differences of the reference's OWN calc_seq; everything else
+                      (return mapping, sub-stepping, tangent) is unmodified reference code (Barlat plan).
 
-usage: python tests/golden/make_golden.py [response] [kmat] [solve] [svc] [barlat] [all]
+usage: python tests/golden/make_golden.py [response] [kmat] [solve] [svc] [barlat] [barlat_response] [all]
 """
 import os
 import sys
@@ -472,10 +476,103 @@ def gen_barlat():
     print('barlat.npz', seq[:3])
 
 
+def barlat_material(khard=0.):
+    # examples/train_goss_barlat.py:36-41
+    bp = None
+    src = open('/root/reference/examples/train_goss_barlat.py').read()
+    ns = {}
+    for line in src.splitlines():
+        if line.strip().startswith('bp ='):
+            i = src.index(line)
+            j = src.index(']', i)
+            exec(src[i:j + 1].strip(), {'np': np}, ns)
+            bp = ns['bp']
+            break
+
+    class BarlatFD(FE.Material):
+        """Reference Material whose (missing) Barlat gradient is the numerical derivative of its own calc_seq."""
+
+        def calc_fgrad(self, sig, epl=None, **kw):
+            if not self.barlat:
+                return super().calc_fgrad(sig, epl=epl, **kw)
+            sig = np.asarray(sig, dtype=float)
+            if sig.ndim == 2:
+                return np.array([self.calc_fgrad(s) for s in sig])
+            seq0 = self.calc_seq(sig)
+            h = 1.e-3 * max(seq0, 1.e-3)
+            g = np.zeros(6)
+            for k in range(6):
+                f = []
+                for off in (1., -1., 2., -2.):
+                    x = sig.copy()
+                    x[k] += off * h
+                    f.append(self.calc_seq(x))
+                g[k] = (8. * (f[0] - f[1]) - (f[2] - f[3])) / (12. * h)
+            return g
+
+    m = BarlatFD('Goss-Barlat')
+    m.elasticity(E=151220., nu=0.3)
+    m.plasticity(sy=46.76, khard=khard, barlat=bp, barlat_exp=8, sdim=6)
+    return m, bp
+
+
+def gen_barlat_response():
+    out = {}
+    t0 = time.time()
+    for khard, kt in [(0., 'pp'), (300., 'kh')]:
+        m, bp = barlat_material(khard)
+        out.update(bp=np.array(bp, dtype=float), barlat_exp=8., Bar_m1=m.Bar_m1, Bar_m2=m.Bar_m2, sy=46.76, E=151220.,
+                   nu=0.3)
+        out[kt + '_khard'] = khard
+        for planar, tag in [(False, 'pe'), (True, 'ps')]:
+            rng = np.random.default_rng(7 + planar + int(khard))
+            n = 60
+            CV = cv_plane_stress(m) if planar else np.array(m.CV)
+            sig, epl, deps = make_tuples(m, rng, n, planar)
+            fy = np.zeros(n); so = np.zeros((n, 6)); dp = np.zeros((n, 6)); ct = np.zeros((n, 6, 6))
+            ns = np.zeros(n, dtype=np.int32); fg = np.zeros((n, 6)); ed = np.zeros((n, 6)); ctan = np.zeros((n, 6, 6))
+            seq = np.zeros(n)
+            for i in range(n):
+                m.msg['nsteps'] = -1
+                fy[i], so[i], dp[i], ct[i] = m.response(sig[i], epl[i], deps[i], CV)
+                ns[i] = m.msg['nsteps']
+                seq[i] = m.calc_seq(sig[i])
+                fg[i] = m.calc_fgrad(sig[i], epl=epl[i])
+                ed[i] = m.epl_dot(sig[i], epl[i], CV, deps[i])
+                ctan[i] = m.C_tan(sig[i], CV, epl=epl[i])
+            t = kt + '_' + tag
+            out.update({f'{t}_CV': CV, f'{t}_sig': sig, f'{t}_epl': epl, f'{t}_deps': deps, f'{t}_fy': fy,
+                        f'{t}_sig_out': so, f'{t}_depl': dp, f'{t}_ctan': ct, f'{t}_nsteps': ns, f'{t}_seq': seq,
+                        f'{t}_fgrad': fg, f'{t}_epl_dot': ed, f'{t}_C_tan': ctan})
+            el = np.sum((ns == 0) & (np.abs(ct - CV).max(axis=(1, 2)) == 0))
+            print(f'  barlat {t}: elastic {el}, 50-step {np.sum(ns == 49)}, other {n - el - np.sum(ns == 49)}, {time.time() - t0:.0f}s')
+    np.savez_compressed(os.path.join(HERE, 'barlat_response.npz'), **out)
+    print('barlat_response.npz')
+
+
+def gen_barlat_solve():
+    """Model.solve of the reference on a 3x3 plane-strain mesh with the FD-gradient Barlat material (hardening 300):
+    uniaxial-y displacement control, 6 increments."""
+    mat, bp = barlat_material(300.)
+    fe = FE.Model(dim=2, planestress=False)
+    fe.geom([4.], LY=4.)
+    fe.assign([mat])
+    fe.bcleft(0.)
+    fe.bcbot(0.)
+    fe.bcright(0., 'force')
+    fe.bctop(0.002 * fe.leny, 'disp')
+    fe.mesh(NX=3, NY=3)
+    solve_case('barlat_3x3', fe, min_step=6)
+    d = dict(np.load(os.path.join(HERE, 'solve_barlat_3x3.npz')))
+    d.update(bp=np.array(bp, dtype=float), Bar_m1=mat.Bar_m1, Bar_m2=mat.Bar_m2, barlat_exp=8., sy=46.76, khard=300.,
+             E=151220., nu=0.3)
+    np.savez_compressed(os.path.join(HERE, 'solve_barlat_3x3.npz'), **d)
+
+
 if __name__ == '__main__':
     what = sys.argv[1:] or ['all']
     if 'all' in what:
-        what = ['response', 'kmat', 'solve', 'svc', 'barlat']
+        what = ['response', 'kmat', 'solve', 'svc', 'barlat', 'barlat_response']
     for w in what:
         print('==', w)
         globals()['gen_' + w]()

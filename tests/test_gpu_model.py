@@ -307,3 +307,27 @@ def test_resolve_continues_from_previous_state():
     # stress depends on the increment sizes of the forward-Euler integration (a property of the reference algorithm)
     assert abs(fe.glob['sig'][1] - ref.glob['sig'][1]) < 2e-3 * ref.glob['sig'][1]
     assert relmax(fe.glob['sig'], ref.glob['sig']) < 3e-2
+
+
+def test_plastic_barlat_uniaxial(golden):
+    """3x3 plane strain, Yld2004-18p with hardening (BASELINE config 5 material, examples/train_goss_barlat.py:36-41),
+    6 increments.  The reference cannot run a Barlat return mapping (no gradient, material.py:822-823); the fixture is
+    the unmodified reference Model.solve with the numerical derivative of its own calc_seq as gradient
+    (tests/golden/make_golden.py gen_barlat_solve).  Same increments, same inner passes, state to 1e-6."""
+    g = golden('solve_barlat_3x3')
+    mat = FE.Material(name='Goss-Barlat')
+    mat.elasticity(E=float(g['E']), nu=float(g['nu']))
+    mat.plasticity(sy=float(g['sy']), khard=float(g['khard']), barlat=list(g['bp']), barlat_exp=int(g['barlat_exp']), sdim=6)
+    fe = FE.Model(dim=2, planestress=False)
+    fe.geom([4.], LY=4.)
+    fe.assign([mat])
+    fe.bcleft(0.)
+    fe.bcbot(0.)
+    fe.bcright(0., 'force')
+    fe.bctop(0.002 * fe.leny, 'disp')
+    fe.mesh(NX=3, NY=3)
+    fe.solve(min_step=6)
+    assert fe.nsteps == int(g['nsteps'])
+    assert list(fe.niter) == list(g['niter'])
+    compare_solution(fe, g, 1e-6, 1e-6)
+    assert relmax(np.array([el.elstiff for el in fe.element]), g['elstiff']) < 1e-6

@@ -124,22 +124,46 @@ def test_svc_response_vs_reference_golden(ctx, golden, tag):
     check_response(out, g, tag, float(g['sy']), tol=2e-6)
 
 
-def test_barlat_seq_vs_reference_golden(ctx, golden):
+def barlat_plf_material(g, khard=0.):
     from pylabfea_b200 import _lib
-    g = golden('barlat')
     m = _lib.PlfMaterial()
     m.kind = _lib.MAT_BARLAT
-    m.E, m.nu, m.sy = float(g['E']), float(g['nu']), float(g['sy'])
+    m.E, m.nu, m.sy, m.khard = float(g['E']), float(g['nu']), float(g['sy']), float(khard)
     m.hill[:] = [1.] * 6
     m.barlat_m1[:] = list(g['Bar_m1'].ravel())
     m.barlat_m2[:] = list(g['Bar_m2'].ravel())
     m.barlat_exp = float(g['barlat_exp'])
-    CV = np.eye(6)
-    m.CV[:] = list(CV.ravel())
+    return m
+
+
+def test_barlat_seq_vs_reference_golden(ctx, golden):
+    g = golden('barlat')
+    m = barlat_plf_material(g)
+    m.CV[:] = list(np.eye(6).ravel())
     ctx.set_materials([m], planestress=False)
     assert relmax(ctx.calc_seq(0, g['sig']), g['seq']) < 1e-11
-    with pytest.raises(ValueError):      # material.py:822-823: no analytical gradient for Barlat
-        ctx.calc_fgrad(0, g['sig'])
+
+
+@pytest.mark.parametrize('kt', ['pp', 'kh'])
+@pytest.mark.parametrize('tag', ['pe', 'ps'])
+def test_barlat_gradient_and_response_vs_reference_golden(ctx, golden, kt, tag):
+    """Yld2004-18p: analytic device gradient (barlat_seq_grad) and return mapping against the reference return mapping
+    driven by the numerical derivative of the reference's own calc_seq (the reference has no Barlat gradient,
+    material.py:822-823; fixture: tests/golden/make_golden.py BarlatFD).  1e-6 relative as BASELINE.json asks."""
+    g = golden('barlat_response')
+    t = kt + '_' + tag
+    m = barlat_plf_material(g, float(g[kt + '_khard']))
+    m.CV[:] = list(np.ascontiguousarray(g[kt + '_pe_CV']).ravel())
+    m.C44 = float(g[kt + '_pe_CV'][3, 3])
+    ctx.set_materials([m], planestress=(tag == 'ps'))
+    assert np.array_equal(ctx.element_CV(0), g[t + '_CV'])
+    sig, epl, deps = g[t + '_sig'], g[t + '_epl'], g[t + '_deps']
+    assert relmax(ctx.calc_seq(0, sig), g[t + '_seq']) < 1e-11
+    assert relmax(ctx.calc_fgrad(0, sig, epl), g[t + '_fgrad']) < 1e-7      # analytic vs 4th-order differences
+    assert relmax(ctx.epl_dot(0, sig, epl, deps), g[t + '_epl_dot']) < 1e-6
+    assert relmax(ctx.C_tan(0, sig, epl), g[t + '_C_tan']) < 1e-6
+    out = ctx.response_batch(sig, epl, deps)
+    check_response(out, g, t, float(g['sy']))
 
 
 # ------------------------------------------------------------------------------------------------------------
@@ -297,3 +321,34 @@ def test_response_full_size_fast_modes_vs_oracle(ctx):
     finally:
         for k, v in dict(compact=1, max_fm=4, passa_direct=0).items():
             ctx.set_option(k, v)
+
+
+@pytest.mark.parametrize('shape', [(40, 24), (3, 70), (1, 5)])
+def test_step_host_pipelined_equals_unpipelined(ctx, shape):
+    """plf_step_host (chunked upload / update + column-range assembly / download on three streams) returns exactly
+    what the single-stream sequence batch_upload + batch_run + setupK_from_batch + batch_download + get_csr returns."""
+    import bench
+    NX, NY = shape
+    mat, CV = bench.j2_material()
+    ctx.set_materials([mat], planestress=False)
+    ctx.mesh_structured(NX, NY, np.full(NX, 4. / NX), 4. / NY, 1., np.zeros(NX * NY, np.int32))
+    n = NX * NY
+    s0, e0, d0 = bench.synth_states(max(NX, NY), 77)
+    sig, epl, deps = s0[:n].copy(), e0[:n].copy(), d0[:n].copy()
+    b = ctx.batch_create(n)
+    ctx.batch_upload(b, sig, epl, deps)
+    ctx.batch_run(b)
+    ctx.setupK_from_batch(b)
+    ref = [np.empty(n), np.empty((n, 6)), np.empty((n, 6)), np.empty((n, 6, 6)), np.empty(n, np.int32)]
+    ctx.batch_download(b, fy=ref[0], sig_out=ref[1], depl=ref[2], ctan=ref[3], nsteps=ref[4])
+    kref = ctx.get_csr_values(np.empty(ctx.nnz))
+    out = [np.full(n, np.nan), np.full((n, 6), np.nan), np.full((n, 6), np.nan), np.full((n, 6, 6), np.nan),
+           np.full(n, -7, np.int32)]
+    kval = np.full(ctx.nnz, np.nan)
+    for _ in range(2):   # twice: the second call re-uses streams / events and meets a used batch
+        ctx.step_host(b, sig, epl, deps, fy=out[0], sig_out=out[1], depl=out[2], ctan=out[3], nsteps=out[4], kval=kval)
+        for a, r in zip(out, ref):
+            assert np.array_equal(a, r)
+        assert np.array_equal(kval, kref)
+    ctx.step_host(b, sig, epl, deps)   # all outputs optional
+    ctx.batch_destroy(b)
