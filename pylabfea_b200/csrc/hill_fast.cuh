@@ -277,7 +277,9 @@ __device__ __forceinline__ int hill_passA(const DevMat &m, double *s, const doub
 //   FM 0 : general (any CV, Drucker / LHS terms)
 //   FM 1 : block-structured symmetric CV, no hydrostatic term            (DevMat.cv_block && cv_sym && !has_d)
 //   FM 2 : FM 1 and all Hill parameters equal 1 (J2): q = 1.5 |dev s|^2 + 3 |shear|^2, a = 1.5 dev(s) / seq
-//   FM 3 : FM 2 and isotropic elasticity (DevMat.cv_iso): pass B runs hill_passB_iso below, pass A is FM 2
+//   FM 3 : FM 2 and isotropic elasticity (DevMat.cv_iso): iso_passA / hill_passB_iso below
+//   FM 4 : FM 3 with planar states sorted to hill_passB_iso2d (the non-planar rest runs the FM 3 loop)
+//   FM 6 : FM 1 and isotropic elasticity, planar states sorted to hill_passB_hilliso2d (rest: the FM 1 loop)
 template <int FM>
 __device__ __forceinline__ void cv_mul_t(const DevMat &m, const double *v, double *o)
 {
@@ -460,21 +462,22 @@ __device__ __forceinline__ void seq_rs(double q, double &seq, double &rs)
 // The same reference algorithm (50 forward-Euler sub-steps, material.py:295-344), ~85 FP64 instructions per
 // sub-step instead of ~160.  Radial-return corrections (rare) are added through 6 shared-memory words per thread.
 // ------------------------------------------------------------------------------------------------------------
-// Elastic predictor and elastic/plastic split for the isotropic J2 modes: hill_prelude<2> with
+// Elastic predictor and elastic/plastic split for the isotropic modes (QF 2: J2, QF 1: Hill-6p form): hill_prelude with
 //   * CV (c deps) = c (CV deps): the split re-uses CV deps instead of two more matrix products,
 //   * the ratio fy0 / seq(CV deps) through the reciprocal square root that seq comes from,
 //   * sqrt of eps_eq through fast_rsqrt (no IEEE sqrt / division sequences on the path).
+template <int QF = 2>
 __device__ __forceinline__ bool iso_prelude(const DevMat &m, double *s, const double *ep, const double *de, HillStep &P, double &fy)
 {
     P.sflow0 = m.sy + (m.khard != 0. ? eps_eq6_fast(ep) * m.khard : 0.);
     P.toler = PLF_YF_TOLERANCE * P.sflow0;
     double cd[6], st[6];
-    cv_mul_t<2>(m, de, cd);
+    cv_mul_t<QF>(m, de, cd);
 #pragma unroll
     for (int k = 0; k < 6; k++) st[k] = s[k] + cd[k];
-    if (!seq_gt_t<2>(m, st, P.sflow0 + P.toler)) {
+    if (!seq_gt_t<QF>(m, st, P.sflow0 + P.toler)) {
         double seq, iseq;
-        seq_inv_t<2>(m, st, seq, iseq);
+        seq_inv_t<QF>(m, st, seq, iseq);
         fy = seq - P.sflow0;
         if (fy < P.toler) {
 #pragma unroll
@@ -485,12 +488,12 @@ __device__ __forceinline__ bool iso_prelude(const DevMat &m, double *s, const do
     P.st_scal = 1.;
     P.split = false;
     double seq0, iseq0;
-    seq_inv_t<2>(m, s, seq0, iseq0);
+    seq_inv_t<QF>(m, s, seq0, iseq0);
     const double fy0 = seq0 - P.sflow0;   // 259
     if (fy0 < PLF_SPLIT_FY0) {            // 260-270
         P.split = true;
         double seqd, iseqd;
-        seq_inv_t<2>(m, cd, seqd, iseqd);
+        seq_inv_t<QF>(m, cd, seqd, iseqd);
         P.st_scal += fy0 * iseqd;
         const double c = 1. - P.st_scal;
 #pragma unroll
@@ -775,6 +778,181 @@ __device__ __forceinline__ int hill_passB_iso2d(const DevMat &m, double *s, doub
         e0 = f0; e1 = f1e; e2 = f2; e5 = f5;
     }
     s[0] = n0 + p; s[1] = n1 + p; s[2] = n2 + p; s[3] = 0.; s[4] = 0.; s[5] = n5;
+    epd[0] = e0; epd[1] = e1; epd[2] = e2; epd[5] = e5;   // epd[3], epd[4] stay zero
+    fy = seq - (m.sy + (m.khard != 0. ? eps_eq6(epd) * m.khard : 0.));
+    double Wf[21];
+#pragma unroll
+    for (int k = 0; k < 21; k++) Wf[k] = 0.;
+    Wf[sym_idx(0, 0)] = W00; Wf[sym_idx(0, 1)] = W01; Wf[sym_idx(0, 5)] = W05;
+    Wf[sym_idx(1, 1)] = W11; Wf[sym_idx(1, 5)] = W15; Wf[sym_idx(5, 5)] = W55;
+    Wf[sym_idx(0, 2)] = -W00 - W01;
+    Wf[sym_idx(1, 2)] = -W01 - W11;
+    Wf[sym_idx(2, 2)] = W00 + 2. * W01 + W11;
+    Wf[sym_idx(2, 5)] = -W05 - W15;
+    if (corrected) {
+        Wf[sym_idx(0, 0)] += xc[0 * xstride];
+        Wf[sym_idx(0, 1)] += xc[5 * xstride];
+        Wf[sym_idx(0, 2)] += xc[4 * xstride];
+        Wf[sym_idx(1, 1)] += xc[1 * xstride];
+        Wf[sym_idx(1, 2)] += xc[3 * xstride];
+        Wf[sym_idx(2, 2)] += xc[2 * xstride];
+    }
+    const double f2s = st_scal * (1. / (double)PLF_MAXIT);
+#pragma unroll
+    for (int i = 0; i < 6; i++)
+#pragma unroll
+        for (int j = i; j < 6; j++) {
+            const double c = m.CV[6 * i + j];
+            gs[sym_idx(i, j)] = c * f1 + ((double)PLF_MAXIT * c - Wf[sym_idx(i, j)]) * f2s;
+        }
+    return 2 | (corrected ? 4 : 0);
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// FM 6: Hill-6p yield function (no Drucker / LHS term) on isotropic elasticity (BASELINE config 3), planar states
+// sorted to their own loop like FM 4.  With g = grad q(s) (hill_qgrad: q is the quadratic form, seq = sqrt(q)) the
+// flow direction is a = g / (2 seq); g is deviatoric in its normal part, so
+//     CV a = G ghat / seq,   ghat = (g_0, g_1, g_2, g_3/2, g_4/2, g_5/2)
+//     hh   = a.CV a + khard = (G / (2 q)) (Gam + kap q),   Gam = g.ghat,  kap = 2 khard / G
+//     sig += CV deps_r - CV a (a.CV deps_r / hh)   <=>   s += cdr - beta ghat,   beta = (g.cdr) D,  D = 1 / (Gam + kap q)
+//     depl = gam g,  gam = beta / (2G)  (when the elastic trial stress is outside the yield surface)
+//     CV a (CV a)^T / hh = 2G D ghat ghat^T;  q(s + cdr) = q(s) + g.cdr + q(cdr)
+// so a sub-step needs one reciprocal for the update and one reciprocal square root for the yield check, and the
+// accumulated tangent sum lives on the index set {0,1,5} (ghat_2 = -ghat_0 - ghat_1).  ~80 FP64 instructions per
+// sub-step against ~170 of the general loop.
+// ------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ int hilliso_passA(const DevMat &m, double *s, const double *ep, const double *de, double *dp, double *ca,
+                                             double &tc, double &tw, double &fy)
+{
+    HillStep P;
+#pragma unroll
+    for (int k = 0; k < 6; k++) { dp[k] = 0.; ca[k] = 0.; }
+    tc = 1.; tw = 0.;
+    if (iso_prelude<1>(m, s, ep, de, P, fy)) return 0;
+    const double G = m.CV[21];
+    double g[6], gh[6];
+    hill_qgrad(m, s, g);
+    gh[0] = g[0]; gh[1] = g[1]; gh[2] = g[2]; gh[3] = 0.5 * g[3]; gh[4] = 0.5 * g[4]; gh[5] = 0.5 * g[5];
+    const double q = hill_q(m, s), qc = hill_q(m, P.cdr);
+    double Gam = 0., gcd = 0.;
+#pragma unroll
+    for (int k = 0; k < 6; k++) { Gam = fma(g[k], gh[k], Gam); gcd = fma(g[k], P.cdr[k], gcd); }
+    const double D = fast_rcp(fma(2. * m.khard / G, q, Gam));
+    const double beta = gcd * D;
+    const double ythr = P.sflow0 + PLF_YF_TOLERANCE;
+    const bool yplus = (q + gcd) + qc > ythr * ythr;   // epl_dot 1031-1041 on the elastic trial stress
+    const double gam = yplus ? beta * (0.5 / G) : 0.;
+    double eplt[6], st[6];
+#pragma unroll
+    for (int k = 0; k < 6; k++) {
+        dp[k] = gam * g[k];
+        eplt[k] = ep[k] + dp[k];
+        st[k] = fma(-beta, gh[k], s[k] + P.cdr[k]);
+    }
+    fy = fast_sqrt(hill_q(m, st)) - (m.sy + (m.khard != 0. ? eps_eq6_fast(eplt) * m.khard : 0.));
+    if (fy > P.toler) return -1;   // 288-291: subdivide
+#pragma unroll
+    for (int k = 0; k < 6; k++) { s[k] = st[k]; ca[k] = gh[k]; }
+    // grad_stiff = CV (1 - st_scal) [split] + (CV - 2G D ghat ghat^T) st_scal   (269, 343 with nsteps = 1)
+    tc = (P.split ? (1. - P.st_scal) : 0.) + P.st_scal;
+    tw = 2. * G * D * P.st_scal;
+    return 1;
+}
+
+// radial-return correction of the planar Hill loop (material.py:310-342) on st = {s0, s1, s2, s5, eplt0, eplt1, eplt2,
+// eplt5, seq}; xc as in iso2d_correct
+static __device__ __noinline__ void hilliso2d_correct(const DevMat &m, double *st, double *xc, int xstride)
+{
+    const double seq = st[8];
+    double eplt[6] = {st[4], st[5], st[6], 0., 0., st[7]};
+    const double fyv = seq - (m.sy + eps_eq6(eplt) * m.khard);
+    double sf[6] = {st[0], st[1], st[2], 0., 0., st[3]};
+    double ex[6], t[6], x[6], dr[6];
+#pragma unroll
+    for (int k = 0; k < 6; k++) {
+        ex[k] = sf[k] * fyv / seq;
+        sf[k] -= ex[k];
+        dr[k] = xc[(6 + k) * xstride];
+    }
+    matvec6(m.SV, ex, t);
+    lstsq_3x6(dr, ex, x);
+#pragma unroll
+    for (int k = 0; k < 6; k++) xc[k * xstride] += x[k];
+    st[0] = sf[0]; st[1] = sf[1]; st[2] = sf[2]; st[3] = sf[5];
+    st[4] = eplt[0] + t[0]; st[5] = eplt[1] + t[1]; st[6] = eplt[2] + t[2]; st[7] = eplt[5] + t[5];
+}
+
+__device__ __forceinline__ int hill_passB_hilliso2d(const DevMat &m, double *s, double *epd, const double *de, double *xc, int xstride,
+                                                    double *gs, double &fy)
+{
+    double st_scal, f1;
+    double c0k, c1k, c2k, c5k, qc, c0, ythr2;   // CV deps_r / 50 on {0,1,2,5}
+    {
+        HillStep P;
+        iso_prelude<1>(m, s, epd, de, P, fy);   // cannot be elastic: pass A deferred this element
+#pragma unroll
+        for (int k = 0; k < 6; k++) {
+            P.dr[k] *= 1. / (double)PLF_MAXIT;   // 290
+            xc[(6 + k) * xstride] = P.dr[k];
+            xc[k * xstride] = 0.;
+        }
+        cv_mul_t<1>(m, P.dr, P.cdr);
+        c0k = P.cdr[0]; c1k = P.cdr[1]; c2k = P.cdr[2]; c5k = P.cdr[5];
+        qc = hill_q(m, P.cdr);
+        c0 = m.sy + P.toler;
+        const double ythr = P.sflow0 + PLF_YF_TOLERANCE;
+        ythr2 = ythr * ythr;
+        st_scal = P.st_scal;
+        f1 = P.split ? (1. - P.st_scal) : 0.;
+    }
+    const double G = m.CV[21];
+    const double kap = 2. * m.khard / G, G2 = 2. * G, iG2 = 0.5 / G, K2 = m.khard * m.khard;
+    const double h0 = m.hill[0], h1 = m.hill[1], h2 = m.hill[2], h5x6 = 6. * m.hill[5];
+    double s0 = s[0], s1 = s[1], s2 = s[2], s5 = s[5];
+    double e0 = epd[0], e1 = epd[1], e2 = epd[2], e5 = epd[5];
+    // g = grad q(s), q = q(s): evaluated at the end of a sub-step for the yield check and re-used by the next one
+    double u0 = h0 * (s0 - s1), u1 = h1 * (s1 - s2), u2 = h2 * (s2 - s0);
+    double g0 = u0 - u2, g1 = u1 - u0, g2 = u2 - u1, g5 = h5x6 * s5;
+    double q = 0.5 * (u0 * (s0 - s1) + u1 * (s1 - s2) + u2 * (s2 - s0) + g5 * s5);
+    double W00 = 0., W01 = 0., W05 = 0., W11 = 0., W15 = 0., W55 = 0.;
+    double seq = 0.;
+    bool corrected = false;
+#pragma unroll 1
+    for (int it = 0; it < PLF_MAXIT; it++) {
+        const double gh5 = 0.5 * g5;
+        const double Gam = fma(g5, gh5, fma(g2, g2, fma(g1, g1, g0 * g0)));
+        const double gcd = fma(g5, c5k, fma(g2, c2k, fma(g1, c1k, g0 * c0k)));
+        const bool yplus = (q + gcd) + qc > ythr2;
+        const double D = fast_rcp(fma(kap, q, Gam));
+        const double beta = gcd * D;
+        const double gam = yplus ? beta * iG2 : 0.;
+        const double w = G2 * D;
+        const double t0 = w * g0, t1 = w * g1, t5 = w * gh5;
+        W00 = fma(t0, g0, W00); W01 = fma(t0, g1, W01); W05 = fma(t0, gh5, W05);
+        W11 = fma(t1, g1, W11); W15 = fma(t1, gh5, W15); W55 = fma(t5, gh5, W55);
+        double f0 = fma(gam, g0, e0), f1e = fma(gam, g1, e1), f2 = fma(gam, g2, e2), f5 = fma(gam, g5, e5);
+        s0 = fma(-beta, g0, s0 + c0k); s1 = fma(-beta, g1, s1 + c1k); s2 = fma(-beta, g2, s2 + c2k); s5 = fma(-beta, gh5, s5 + c5k);
+        const double d01 = s0 - s1, d12 = s1 - s2, d20 = s2 - s0;
+        u0 = h0 * d01; u1 = h1 * d12; u2 = h2 * d20;
+        g0 = u0 - u2; g1 = u1 - u0; g2 = u2 - u1; g5 = h5x6 * s5;
+        q = 0.5 * fma(g5, s5, fma(u2, d20, fma(u1, d12, u0 * d01)));
+        seq = fast_sqrt(q);
+        const double e2s = (2. / 3.) * ((f0 * f0 + f1e * f1e + f2 * f2) + 0.5 * (f5 * f5));
+        const double lhs = seq - c0;
+        if (lhs > 0. && lhs * lhs > K2 * e2s) {
+            corrected = true;
+            double st[9] = {s0, s1, s2, s5, f0, f1e, f2, f5, seq};
+            hilliso2d_correct(m, st, xc, xstride);
+            s0 = st[0]; s1 = st[1]; s2 = st[2]; s5 = st[3];
+            f0 = st[4]; f1e = st[5]; f2 = st[6]; f5 = st[7];
+            u0 = h0 * (s0 - s1); u1 = h1 * (s1 - s2); u2 = h2 * (s2 - s0);
+            g0 = u0 - u2; g1 = u1 - u0; g2 = u2 - u1; g5 = h5x6 * s5;
+            q = 0.5 * (u0 * (s0 - s1) + u1 * (s1 - s2) + u2 * (s2 - s0) + g5 * s5);
+            seq = fast_sqrt(q);
+        }
+        e0 = f0; e1 = f1e; e2 = f2; e5 = f5;
+    }
+    s[0] = s0; s[1] = s1; s[2] = s2; s[3] = 0.; s[4] = 0.; s[5] = s5;
     epd[0] = e0; epd[1] = e1; epd[2] = e2; epd[5] = e5;   // epd[3], epd[4] stay zero
     fy = seq - (m.sy + (m.khard != 0. ? eps_eq6(epd) * m.khard : 0.));
     double Wf[21];

@@ -137,7 +137,7 @@ __device__ __forceinline__ void passA_tile(int64_t n, int64_t tile, double *s_in
                                            double *__restrict__ ctan, int32_t *__restrict__ nsteps, int32_t *worklist,
                                            unsigned int *work_count)
 {
-    constexpr int FA = FM >= 3 ? 2 : FM;   // (the isotropic modes use iso_passA)
+    constexpr int FA = FM == 6 ? 1 : (FM >= 3 ? 2 : FM);   // (the isotropic modes use iso_passA / hilliso_passA)
     const int tid = threadIdx.x;
     double *s_sig = s_in, *s_epl = s_in + RB * 6, *s_dep = s_in + 2 * RB * 6;
     const int64_t base = tile * RB;
@@ -158,7 +158,7 @@ __device__ __forceinline__ void passA_tile(int64_t n, int64_t tile, double *s_in
     const int64_t e = base + tid;
     if (tid < cnt) {
         const DevMat &m = c_mat[SINGLE ? 0 : mat_id[e]];
-        if (FM == 4) general = !planar_state(s, ep, de);   // planar states go to the front of the list (hill_passB_iso2d)
+        if (FM == 4 || FM == 6) general = !planar_state(s, ep, de);   // planar states go to the front of the list
         if (m.kind == PLF_MAT_ELASTIC || m.kind == PLF_MAT_HILL) {
             double dp[6], ca[6], tc = 1., tw = 0., fyv = 0.;
             int br = 0;
@@ -175,7 +175,8 @@ __device__ __forceinline__ void passA_tile(int64_t n, int64_t tile, double *s_in
                     for (int k = 0; k < 6; k++) { dp[k] = ep[k]; ca[k] = de[k]; }
                     fyv = s[0];
                 } else
-                br = (FM >= 3) ? iso_passA(m, s, ep, de, dp, ca, tc, tw, fyv) : hill_passA<FA>(m, s, ep, de, dp, ca, tc, tw, fyv);
+                br = (FM == 6) ? hilliso_passA(m, s, ep, de, dp, ca, tc, tw, fyv)
+                   : (FM >= 3) ? iso_passA(m, s, ep, de, dp, ca, tc, tw, fyv) : hill_passA<FA>(m, s, ep, de, dp, ca, tc, tw, fyv);
             }
             if (br < 0) {
                 defer = true;
@@ -249,7 +250,8 @@ __device__ __forceinline__ void passB_element(int64_t e, WAcc &W, double *xc, co
         ep[2 * k] = b.x; ep[2 * k + 1] = b.y;
         de[2 * k] = c.x; de[2 * k + 1] = c.y;
     }
-    if (FM == 4) hill_passB_iso2d(m, s, ep, de, xc, RB, gs, fyv);
+    if (FM == 6) hill_passB_hilliso2d(m, s, ep, de, xc, RB, gs, fyv);
+    else if (FM == 4) hill_passB_iso2d(m, s, ep, de, xc, RB, gs, fyv);
     else if (FM == 3) hill_passB_iso(m, s, ep, de, xc, RB, gs, fyv);
     else hill_passB<FM>(m, s, ep, de, W, gs, fyv);
     // ep now holds epl + depl; the increment is recovered against the (L2-resident) input record
@@ -336,12 +338,13 @@ __global__ void __launch_bounds__(RB, MINB) response_passB_kernel(const int32_t 
             passB_element<SINGLE, FM>(e, W, s_W + threadIdx.x, mat_id, sig, epl, deps, fy, sig_out, depl_out, ctan, nsteps);
         }
     }
-    if (FM == 4) {
-        // the non-planar elements (back of the list) with the general isotropic loop
+    if (FM == 4 || FM == 6) {
+        // the non-planar elements (back of the list) with the general loop of the material class
         for (unsigned int t = blockIdx.x * RB + threadIdx.x; t < n1; t += gridDim.x * RB) {
             const int64_t e = worklist[nlist - 1 - (int64_t)t];
             WRegs W;
-            passB_element<SINGLE, 3>(e, W, s_W + threadIdx.x, mat_id, sig, epl, deps, fy, sig_out, depl_out, ctan, nsteps);
+            passB_element<SINGLE, (FM == 4 ? 3 : 1)>(e, W, s_W + threadIdx.x, mat_id, sig, epl, deps, fy, sig_out, depl_out, ctan,
+                                                     nsteps);
         }
     }
     // the last block to finish zeroes the counters for the next launch (saves a memset node per step)
@@ -633,6 +636,7 @@ cudaError_t response_init()
     if ((e = big_smem(response_passA_kernel<true, 3, false>, k1a_smem(false))) != cudaSuccess) return e;
     if ((e = big_smem(response_passA_kernel<true, 4, false>, k1a_smem(false))) != cudaSuccess) return e;
     if ((e = big_smem(response_passA_kernel<true, 5, false>, k1a_smem(false))) != cudaSuccess) return e;
+    if ((e = big_smem(response_passA_kernel<true, 6, false>, k1a_smem(false))) != cudaSuccess) return e;
     if ((e = big_smem(response_generic_kernel, k1_smem())) != cudaSuccess) return e;
     if ((e = big_smem(response_svc_kernel, 227 * 1024)) != cudaSuccess) return e;
     return big_smem(prim_svc_kernel, 227 * 1024);
@@ -640,7 +644,7 @@ cudaError_t response_init()
 
 // Fast mode of a single-material Hill batch (hill_fast.cuh): 1 = block-structured symmetric CV without hydrostatic
 // term, 2 = additionally J2, 3 = additionally isotropic elasticity, 4 = 3 with planar states sorted to their own
-// pass B kernel.  max_fm caps it (A/B measurements, tests).
+// loop, 6 = Hill on isotropic elasticity with its planar loop.  max_fm caps it (A/B measurements, tests).
 static int fast_mode(const DevMat *hmats, int nmat, int max_fm)
 {
     if (nmat != 1 || hmats[0].kind != PLF_MAT_HILL || !hmats[0].cv_block || !hmats[0].cv_sym || hmats[0].has_d) return 0;
@@ -648,6 +652,7 @@ static int fast_mode(const DevMat *hmats, int nmat, int max_fm)
     for (int k = 0; k < 6; k++)
         if (hmats[0].hill[k] != 1.) fm = 1;
     if (fm == 2 && hmats[0].cv_iso) fm = 4;
+    if (fm == 1 && hmats[0].cv_iso && max_fm >= 4) return 6;   // Hill on isotropic elasticity: its own planar mode
     return std::min(fm, max_fm);
 }
 
@@ -681,6 +686,7 @@ cudaError_t launch_response(const LaunchCtx &lc, const DevMat *hmats, int nmat, 
     } while (0)
             if (lc.k1_only == 2) PASSA(true, 5);
             else if (!single) PASSA(false, 0);
+            else if (fm == 6) PASSA(true, 6);
             else if (fm == 4) PASSA(true, 4);
             else if (fm == 3) PASSA(true, 3);
             else if (fm == 2) PASSA(true, 2);
@@ -702,7 +708,8 @@ cudaError_t launch_response(const LaunchCtx &lc, const DevMat *hmats, int nmat, 
             } else if (single && lc.passb_wsmem == 0) {
                 PASSB(false, 2, true, 0);
             } else if (single) {
-                if (fm == 4) PASSB(false, 3, true, 4);   // planar elements first, then whatever is not planar
+                if (fm == 6) PASSB(false, 3, true, 6);
+                else if (fm == 4) PASSB(false, 3, true, 4);   // planar elements first, then whatever is not planar
                 else if (fm == 3) PASSB(false, 3, true, 3);
                 else if (fm == 2) PASSB(false, 3, true, 2);
                 else if (fm == 1) PASSB(false, 3, true, 1);

@@ -1,11 +1,12 @@
 #!/usr/bin/env python3
 """Kernel throughput on the other BASELINE.json configurations (bench.py measures the headline 1024 x 1024 J2 case):
 
-    python scripts/config_bench.py j2_256 | hill_512 | svc_512 [n_elements_for_svc]
+    python scripts/config_bench.py j2_256 | hill_512 | svc_512 | barlat_2048 [n_elements]
 
 config 2: 256 x 256 J2; config 3: 512 x 512 Hill (sy=150, hill=[0.7,1,1.4,1,1.2,0.8], khard=100); config 4: 512 x 512
 with the RBF-SVC yield function of examples/train_hill.py (1 585 support vectors, the model the reference trained in
-the build container: tests/golden/svc_hill.npz).  Inputs resident in HBM, CUDA events, L2 flushed between repetitions
+the build container: tests/golden/svc_hill.npz); config 5: 2048 x 2048 Barlat Yld2004-18p (examples/train_goss_barlat.py
+parameters, a = 8; one GPU's share or a sample of it).  Inputs resident in HBM, CUDA events, L2 flushed between repetitions
 for the small meshes.  Prints one JSON line per config."""
 import json
 import os
@@ -43,6 +44,15 @@ def run(name, n_override=None):
         mat = m._descriptor()
         sig, epl, deps = bench.synth_states(N, 1234, sy=float(g['sy']), khard=0., deps_scale=1. / 3.)
         reps = 2
+    elif name == 'barlat_2048':
+        N = 2048
+        g = dict(np.load(os.path.join(os.path.dirname(__file__), '..', 'tests', 'golden', 'barlat_response.npz')))
+        m = FE.Material('Goss-Barlat')
+        m.elasticity(E=float(g['E']), nu=float(g['nu']))
+        m.plasticity(sy=float(g['sy']), khard=0., barlat=list(g['bp']), barlat_exp=int(g['barlat_exp']), sdim=6)
+        mat = m._descriptor()
+        sig, epl, deps = bench.synth_states(N, 1234, sy=float(g['sy']), khard=0., deps_scale=1. / 3.)
+        reps = 3
     else:
         raise SystemExit('unknown config ' + name)
     n = N * N if n_override is None else int(n_override)

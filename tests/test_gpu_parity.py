@@ -352,3 +352,37 @@ def test_step_host_pipelined_equals_unpipelined(ctx, shape):
         assert np.array_equal(kval, kref)
     ctx.step_host(b, sig, epl, deps)   # all outputs optional
     ctx.batch_destroy(b)
+
+
+def test_response_hill_isotropic_planar_mode_vs_oracle(ctx):
+    """BASELINE config 3 (512 x 512, Hill-6p with isotropic hardening on isotropic elasticity, synthetic planar field):
+    the Hill fast mode (hilliso_passA + planar 50-sub-step loop) against the general Hill kernels on every element and
+    against the CPU oracle on a seeded sample."""
+    import bench
+    from oracle import oracle as orc
+    N = 512
+    hill = [0.7, 1., 1.4, 1., 1.2, 0.8]
+    mat, CV = bench.j2_material()
+    mat.hill[:] = hill
+    mat.khard = 100.
+    ctx.set_materials([mat], planestress=False)
+    sig, epl, deps = bench.synth_states(N, 4321, khard=100.)
+    try:
+        ctx.set_option('max_fm', 0)
+        ref = ctx.response_batch(sig, epl, deps)
+        ctx.set_option('max_fm', 4)
+        out = ctx.response_batch(sig, epl, deps)
+        n50 = int(np.sum(ref[4] == 49))
+        assert n50 > 0.03 * N * N
+        assert np.array_equal(out[4], ref[4])
+        for a, b in zip(out[:4], ref[:4]):
+            assert np.max(np.abs(a - b)) <= 1e-10 * np.max(np.abs(b))
+        idx = np.random.default_rng(5).choice(N * N, 20000, replace=False)
+        mats = [orc.Mat(kind=orc.HILL, E=bench.E_MOD, nu=bench.NU, sy=bench.SY, khard=100., hill=hill)]
+        oref = orc.response_batch(mats, None, sig[idx], epl[idx], deps[idx], CV[None])
+        assert np.array_equal(out[4][idx], oref[4])
+        assert np.max(np.abs(out[0][idx] - oref[0])) < TOL * bench.SY
+        assert relmax(out[1][idx], oref[1]) < TOL and relmax(out[3][idx], oref[3]) < TOL
+        assert np.max(np.abs(out[2][idx] - oref[2])) < TOL * np.max(np.abs(oref[2]))
+    finally:
+        ctx.set_option('max_fm', 4)
