@@ -22,6 +22,7 @@ COMMON = ['-gencode', 'arch=compute_100a,code=sm_100a', '-O3', '-lineinfo', '-st
 UNITS = {
     'response_kernels.cu': [],
     'model_kernels.cu': [],
+    'mg_kernels.cu': [],
     'assembly_kernels.cu': ['-fmad=false'],
     'plf_api.cu': [],
     'plf_model.cu': [],

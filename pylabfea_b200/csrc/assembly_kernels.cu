@@ -10,6 +10,7 @@
 // independent, so nothing is computed twice across threads), and accumulates into the <= 18 entries of its row
 // held in registers.  Every CSR value is written exactly once and no Kel ever touches HBM:
 //   HBM traffic = 288 B tangent read + 4 B descriptor per element, 8 B per non-zero written (= 288 B per element).
+#include "csr_stencil.cuh"
 #include "plf_device.cuh"
 #include "plf_host.h"
 
@@ -22,22 +23,8 @@ cudaError_t assembly_upload_geom(const GeomClass *h, int n, cudaStream_t st)
     return cudaMemcpyToSymbolAsync(c_geom, h, sizeof(GeomClass) * n, 0, cudaMemcpyHostToDevice, st);
 }
 
-// First CSR entry of a row of the structured mesh, in closed form (row 2n+c has the dofs of all nodes within +-1 in
-// (j,k), ascending): the kernels compute row starts instead of loading rowptr (a dependent load at the top and at
-// the bottom of every thread was 17 % of the assembly kernel's stall samples).
-__device__ __forceinline__ int64_t csr_row_start(int NX, int NY, int64_t row)
-{
-    const int NnY = NY + 1;
-    const int64_t colw = 4ll * (3 * NY + 1);   // entries per unit of "x neighbours" in one node column
-    const int64_t n = row >> 1;
-    const int c = (int)(row & 1);
-    const int j = (int)(n / NnY), k = (int)(n - (int64_t)j * NnY);
-    if (j > NX) return colw * (3ll * (NX + 1) - 2);   // row == Ndof: total number of non-zeros
-    const int nxc = 1 + (j > 0) + (j < NX), nyc = 1 + (k > 0) + (k < NY);
-    const int64_t pj = (j == 0) ? 0 : 3ll * j - 1;
-    const int64_t pk = (k == 0) ? 0 : 3ll * k - 1;
-    return colw * pj + 4ll * nxc * pk + (int64_t)c * 2 * nxc * nyc;
-}
+// Row starts come in closed form (csr_stencil.cuh) instead of rowptr loads: a dependent load at the top and at the
+// bottom of every thread was 17 % of the assembly kernel's stall samples.
 
 // CSR pattern of the structured mesh: row 2n+c has the dofs of all nodes within +-1 in (j,k), ascending.
 __global__ void csr_pattern_kernel(int NX, int NY, int32_t *__restrict__ rowptr, int32_t *__restrict__ col)

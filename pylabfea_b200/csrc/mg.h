@@ -1,0 +1,30 @@
+// mg.h -- geometric multigrid preconditioner of the on-device CG solve (mg_kernels.cu)
+#pragma once
+#include <vector>
+#include "plf_host.h"
+
+namespace plf {
+
+struct MgLevel {
+    int NX = 0, NY = 0;
+    int64_t ndof = 0, nnz = 0;
+    double *val = nullptr;            // level matrix in the closed-form CSR layout (level 0: the model's K, not owned)
+    unsigned char *mask = nullptr;    // 1 = Dirichlet dof (level 0: the solver's mask, not owned)
+    double *dinv = nullptr;           // 1 / diag, 0 on masked rows
+    double *x = nullptr, *b = nullptr, *r = nullptr, *t = nullptr;   // level 0: x and b are the caller's z and r
+};
+
+struct MgHierarchy {
+    std::vector<MgLevel> lv;
+    int nu = 2;                // pre- and post-smoothing sweeps (even)
+    int coarse_sweeps = 40;    // damped Jacobi sweeps on the coarsest level
+    double omega = 0.7;
+    int levels() const { return (int)lv.size(); }
+};
+
+cudaError_t mg_build(MgHierarchy &H, int NX, int NY);
+void mg_free(MgHierarchy &H);
+cudaError_t mg_setup(const LaunchCtx &lc, MgHierarchy &H, const double *val_fine, const unsigned char *mask_fine, int64_t *launches);
+cudaError_t mg_vcycle(const LaunchCtx &lc, MgHierarchy &H, const double *r_fine, double *z_fine, int64_t *launches);
+
+}  // namespace plf

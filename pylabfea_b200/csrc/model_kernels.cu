@@ -8,6 +8,7 @@
 #include "plf_device.cuh"
 #include "plf_host.h"
 #include "model_kernels.h"
+#include "mg.h"
 
 namespace plf {
 
@@ -636,7 +637,9 @@ struct CgScalars {
 };
 
 // x += alpha p ; r -= alpha q ; z = r / diag ; r.z and r.r   (alpha = rz / pq computed by every thread)
-template <int P>
+// MG: the preconditioner is the multigrid V-cycle (mg_kernels.cu), applied between this kernel and cg_rz_kernel:
+// z and r.z are not touched here.
+template <int P, bool MG>
 __global__ void __launch_bounds__(256) cg_update_kernel(int64_t n, double *__restrict__ x, double *__restrict__ r,
                                                         double *__restrict__ z, const double *__restrict__ p,
                                                         const double *__restrict__ q, const double *__restrict__ diag,
@@ -651,16 +654,31 @@ __global__ void __launch_bounds__(256) cg_update_kernel(int64_t n, double *__res
         if (fixed[i]) continue;
         const double xi = x[i] + alpha * p[i];
         const double ri = r[i] - alpha * q[i];
-        const double zi = ri / diag[i];
-        x[i] = xi; r[i] = ri; z[i] = zi;
-        v[0] += ri * zi;
+        x[i] = xi; r[i] = ri;
+        if (!MG) {
+            const double zi = ri / diag[i];
+            z[i] = zi;
+            v[0] += ri * zi;
+        }
         v[1] += ri * ri;
     }
     if (block_reduce_to_partials<2>(v, partial, counter, sc->tmp, 0)) {
         // the one finalising thread: publish r.z for the next step, r.r, and count the step if it was a real one
-        sc->rz[1 - P] = sc->tmp[0];
+        if (!MG) sc->rz[1 - P] = sc->tmp[0];
         if (live) { sc->rr = sc->tmp[1]; sc->iters += 1.; }
     }
+}
+
+// r.z after the V-cycle -> rz[SLOT]
+template <int SLOT>
+__global__ void __launch_bounds__(256) cg_rz_kernel(int64_t n, const double *__restrict__ r, const double *__restrict__ z,
+                                                    const unsigned char *__restrict__ fixed, CgScalars *sc, double *partial,
+                                                    unsigned int *counter)
+{
+    double v[1] = {0.};
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+        if (!fixed[i]) v[0] += r[i] * z[i];
+    if (block_reduce_to_partials<1>(v, partial, counter, sc->tmp, 0)) sc->rz[SLOT] = sc->tmp[0];
 }
 
 // beta = rz_new / rz_old ; p = z + beta p
@@ -810,13 +828,14 @@ struct CgGraphCache {
     const void *key[6] = {nullptr};
     int chunk = 0;
     cudaStream_t stream = nullptr;
+    int64_t launches_per_chunk = 0;
 };
 static CgGraphCache g_cg;
 
 cudaError_t launch_cg(const LaunchCtx &lc, int64_t n, const int32_t *rowptr, const int32_t *col, const double *val,
                       const unsigned char *fixed, const double *b, double *x, double *r, double *z, double *p, double *q,
                       double *diag, double *partial, unsigned int *counter, void *d_sc, void *h_sc, double rtol, int max_iter,
-                      int check_every, int *iters, double *relres, int64_t *launches)
+                      int check_every, int *iters, double *relres, int64_t *launches, MgHierarchy *mg)
 {
     CgScalars *sc = (CgScalars *)d_sc;
     CgScalars *hs = (CgScalars *)h_sc;
@@ -827,6 +846,14 @@ cudaError_t launch_cg(const LaunchCtx &lc, int64_t n, const int32_t *rowptr, con
     diag_kernel<<<(unsigned)((n + 255) / 256), 256, 0, lc.stream>>>(n, rowptr, col, val, diag);
     cg_init_kernel<<<vg, 256, 0, lc.stream>>>(n, b, x, r, z, p, diag, fixed, sc, rtol, partial, counter);
     *launches += 2;
+    if (mg) {
+        // z = V(r), r.z, p = z with the multigrid preconditioner (the Jacobi z / p / r.z of cg_init_kernel are replaced)
+        if ((e = mg_setup(lc, *mg, val, fixed, launches)) != cudaSuccess) return e;
+        if ((e = mg_vcycle(lc, *mg, r, z, launches)) != cudaSuccess) return e;
+        cg_rz_kernel<0><<<vg, 256, 0, lc.stream>>>(n, r, z, fixed, sc, partial, counter);
+        (*launches)++;
+        if ((e = cudaMemcpyAsync(p, z, (size_t)n * sizeof(double), cudaMemcpyDeviceToDevice, lc.stream)) != cudaSuccess) return e;
+    }
     if ((e = cudaMemcpyAsync(hs, sc, sizeof(CgScalars), cudaMemcpyDeviceToHost, lc.stream)) != cudaSuccess) return e;
     if ((e = cudaStreamSynchronize(lc.stream)) != cudaSuccess) return e;
     const double bb = hs->rr;
@@ -835,17 +862,33 @@ cudaError_t launch_cg(const LaunchCtx &lc, int64_t n, const int32_t *rowptr, con
     if (bb == 0.) return cudaSuccess;
     const double target = hs->target;
 
+    int64_t chunk_launches = 0;
     auto enqueue_chunk = [&]() {
         for (int c = 0; c < check_every; c += 2) {
             spmv_kernel<<<sg, 256, 0, lc.stream>>>(n, rowptr, col, val, p, nullptr, q, fixed, 0, partial, counter, &sc->pq);
-            cg_update_kernel<0><<<vg, 256, 0, lc.stream>>>(n, x, r, z, p, q, diag, fixed, sc, partial, counter);
+            if (mg) {
+                cg_update_kernel<0, true><<<vg, 256, 0, lc.stream>>>(n, x, r, z, p, q, diag, fixed, sc, partial, counter);
+                mg_vcycle(lc, *mg, r, z, &chunk_launches);
+                cg_rz_kernel<1><<<vg, 256, 0, lc.stream>>>(n, r, z, fixed, sc, partial, counter);
+                chunk_launches++;
+            } else {
+                cg_update_kernel<0, false><<<vg, 256, 0, lc.stream>>>(n, x, r, z, p, q, diag, fixed, sc, partial, counter);
+            }
             cg_p_kernel<0><<<vg, 256, 0, lc.stream>>>(n, p, z, sc);
             spmv_kernel<<<sg, 256, 0, lc.stream>>>(n, rowptr, col, val, p, nullptr, q, fixed, 0, partial, counter, &sc->pq);
-            cg_update_kernel<1><<<vg, 256, 0, lc.stream>>>(n, x, r, z, p, q, diag, fixed, sc, partial, counter);
+            if (mg) {
+                cg_update_kernel<1, true><<<vg, 256, 0, lc.stream>>>(n, x, r, z, p, q, diag, fixed, sc, partial, counter);
+                mg_vcycle(lc, *mg, r, z, &chunk_launches);
+                cg_rz_kernel<0><<<vg, 256, 0, lc.stream>>>(n, r, z, fixed, sc, partial, counter);
+                chunk_launches++;
+            } else {
+                cg_update_kernel<1, false><<<vg, 256, 0, lc.stream>>>(n, x, r, z, p, q, diag, fixed, sc, partial, counter);
+            }
             cg_p_kernel<1><<<vg, 256, 0, lc.stream>>>(n, p, z, sc);
+            chunk_launches += 6;
         }
     };
-    const void *key[6] = {rowptr, val, x, fixed, d_sc, partial};
+    const void *key[6] = {rowptr, val, x, fixed, d_sc, mg ? (const void *)mg : (const void *)partial};
     bool cached = g_cg.exec && g_cg.n == n && g_cg.chunk == check_every && g_cg.stream == lc.stream;
     for (int i = 0; i < 6 && cached; i++) cached = (g_cg.key[i] == key[i]);
     if (!cached) {
@@ -857,13 +900,13 @@ cudaError_t launch_cg(const LaunchCtx &lc, int64_t n, const int32_t *rowptr, con
         e = cudaGraphInstantiate(&g_cg.exec, graph, 0);
         cudaGraphDestroy(graph);
         if (e != cudaSuccess) { g_cg.exec = nullptr; return e; }
-        g_cg.n = n; g_cg.chunk = check_every; g_cg.stream = lc.stream;
+        g_cg.n = n; g_cg.chunk = check_every; g_cg.stream = lc.stream; g_cg.launches_per_chunk = chunk_launches;
         for (int i = 0; i < 6; i++) g_cg.key[i] = key[i];
     }
     int it = 0;
     while (it < max_iter) {
         if ((e = cudaGraphLaunch(g_cg.exec, lc.stream)) != cudaSuccess) return e;
-        *launches += 3 * (int64_t)check_every;
+        *launches += g_cg.launches_per_chunk;
         it += check_every;
         if ((e = cudaMemcpyAsync(hs, sc, sizeof(CgScalars), cudaMemcpyDeviceToHost, lc.stream)) != cudaSuccess) return e;
         if ((e = cudaStreamSynchronize(lc.stream)) != cudaSuccess) return e;

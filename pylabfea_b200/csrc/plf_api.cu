@@ -393,6 +393,7 @@ extern "C" int plf_set_option(plf_ctx *ctx, const char *key, int value)
     if (!strcmp(key, "max_fm")) { ctx->max_fm = value; return PLF_OK; }
     if (!strcmp(key, "minb")) { ctx->minb = value; return PLF_OK; }
     if (!strcmp(key, "k1_only")) { ctx->k1_only = value; return PLF_OK; }
+    if (!strcmp(key, "solver_mg")) { ctx->solver_mg = value; return PLF_OK; }
     return fail(ctx, PLF_EINVAL, std::string("plf_set_option: unknown key ") + key);
 }
 

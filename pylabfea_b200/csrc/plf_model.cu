@@ -9,6 +9,7 @@
 #include <vector>
 
 #include "model_kernels.h"
+#include "mg.h"
 #include "plf_device.cuh"
 #include "plf_host.h"
 #include "plf_model.h"
@@ -34,6 +35,7 @@ static int dalloc(plf_ctx *ctx, T **p, size_t n)
 void model_free(plf_ctx *c)
 {
     cg_graph_reset();
+    if (c->mg) { mg_free(*c->mg); delete c->mg; c->mg = nullptr; }
     cudaFree(c->d_desc); cudaFree(c->d_elstiff); cudaFree(c->d_sig); cudaFree(c->d_eps); cudaFree(c->d_epl);
     cudaFree(c->d_res_sig); cudaFree(c->d_res_depl); cudaFree(c->d_fyld); cudaFree(c->d_nsteps); cudaFree(c->d_branch);
     cudaFree(c->d_has_res); cudaFree(c->d_u); cudaFree(c->d_du); cudaFree(c->d_f); cudaFree(c->d_rowptr); cudaFree(c->d_col);
@@ -178,6 +180,8 @@ extern "C" int plf_mesh_structured(plf_ctx *ctx, int NX, int NY, const double *d
     CK(cudaMemsetAsync(ctx->d_u, 0, D * sizeof(double), ctx->stream));
     CK(cudaMemsetAsync(ctx->d_du, 0, D * sizeof(double), ctx->stream));
     CK(cudaMemsetAsync(ctx->d_f, 0, D * sizeof(double), ctx->stream));
+    ctx->mg = new MgHierarchy();
+    CK(mg_build(*ctx->mg, NX, NY));
     ctx->mesh_ready = true;
     ctx->K_ready = false;
     rc = plf_set_tangent(ctx, nullptr);
@@ -513,9 +517,11 @@ extern "C" int plf_solve_linear(plf_ctx *ctx, const uint8_t *fixed, const double
     int it = 0;
     double rr = 0.;
     double *x = ctx->d_du;   // CG iterate lives in du; fixed dofs are merged at the end
+    // multigrid V-cycle preconditioner when the mesh coarsens at least once (mesh-independent iteration counts), else Jacobi
+    const bool use_mg = ctx->solver_mg && ctx->mg && ctx->mg->levels() >= 2;
     CK(launch_cg(lc, ctx->Ndof, ctx->d_rowptr, ctx->d_col, ctx->d_val, ctx->d_fixed, ctx->d_b, x, ctx->d_r, ctx->d_z, ctx->d_p, ctx->d_q,
-                 ctx->d_diag, ctx->d_partial, counter_ptr(ctx), ctx->d_scalars + 256, ctx->h_scalars + 256, rtol, max_iter, 50, &it, &rr,
-                 &ctx->launches));
+                 ctx->d_diag, ctx->d_partial, counter_ptr(ctx), ctx->d_scalars + 256, ctx->h_scalars + 256, rtol, max_iter,
+                 use_mg ? 4 : 50, &it, &rr, &ctx->launches, use_mg ? ctx->mg : nullptr));
     CK(launch_merge_du(lc, ctx->Ndof, x, ctx->d_w, ctx->d_fixed, ctx->d_du, &ctx->launches));
     CK(cudaStreamSynchronize(ctx->stream));
     if (iters) *iters = it;

@@ -7,6 +7,8 @@
 #include "plf_host.h"
 
 // device buffers of one batch of independent stress updates (AoS records, see DESIGN.md "data layout")
+namespace plf { struct MgHierarchy; }
+
 struct plf_batch {
     int64_t n = 0, cap = 0;
     int32_t *mat_id = nullptr;
@@ -73,6 +75,8 @@ struct plf_ctx {
     // solver work vectors
     double *d_r = nullptr, *d_z = nullptr, *d_p = nullptr, *d_q = nullptr, *d_b = nullptr, *d_diag = nullptr, *d_w = nullptr;
     unsigned char *d_fixed = nullptr;
+    plf::MgHierarchy *mg = nullptr;   // multigrid preconditioner of plf_solve_linear (built with the mesh)
+    int solver_mg = 1;                // 1: V-cycle preconditioner when the mesh coarsens at least once, 0: Jacobi
     double *d_partial = nullptr;   // block partial sums
     int n_partial = 0;
 };

@@ -37,6 +37,7 @@ def main():
     fe.mesh(elmts=el, NX=N, NY=N)
     fe.bcnode(0, 0., 'disp', 'x')
     fe.solver_rtol = float(os.environ.get('PLF_RTOL', '1e-10'))
+    fe._dev().set_option('solver_mg', int(os.environ.get('PLF_MG', '1')))   # 0: Jacobi-preconditioned CG
     t1 = time.time()
     fe.solve(min_step=min_step)
     t2 = time.time()
