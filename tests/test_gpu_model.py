@@ -339,7 +339,7 @@ def test_multigrid_and_jacobi_cg_agree_and_mg_is_mesh_independent():
     stays O(10) while Jacobi needs hundreds."""
     runs = {}
     for mg in (1, 0):
-        fe = inclusion(30, plastic=True, eps_tot=0.004)
+        fe = inclusion(32, plastic=True, eps_tot=0.004)
         fe._dev().set_option('solver_mg', mg)
         fe.solver_rtol = 1.e-12
         fe.solve(min_step=4)
