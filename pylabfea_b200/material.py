@@ -195,6 +195,56 @@ class Material(object):
         self.Ndof = 6
         self.khard = 0.   # material.py:812-814: the SVC gradient resets khard when there are no hardening features
 
+    @classmethod
+    def from_MLparam(cls, file, path='', sy=None, name=None):
+        """Load a trained ML flow rule from the CSV (+ optional JSON metadata) that export_MLparam writes
+        (material.py:2133-2273; the reference's own from_MLparam, 2688-2703, is unimplemented).  `file` is the trunk
+        of the file name, as in export_MLparam: the CSV is path + file + '-svm.csv'.
+
+        CSV layout (8 numbers per line, flattened): [0] nsv, [1] Ndof, [2:5] C11 C12 C44, [5] intercept (rho), [6] gamma,
+        [7] epc, [8] scale_seq, [9] scale_wh, [10:16] C22 C33 C13 C23 C55 C66 (or -1), [16] -1 when dev_only, [17] Nset,
+        [18:18+Nset] scale_text, [29:29+nsv] dual coefficients, then the (nsv, Ndof) support vectors.
+        The yield strength is not part of the format; sy defaults to scale_seq (what train_SVC uses for scaling when no
+        microstructure data is attached, material.py:1160-1161)."""
+        import json
+        import os
+        trunk = os.path.join(path, file)
+        props = np.loadtxt(trunk + '-svm.csv', delimiter=',').ravel()
+        nsv, ndof = int(round(props[0])), int(round(props[1]))
+        if ndof != 6:
+            raise NotImplementedError('from_MLparam: only sdim = 6 models without work-hardening / texture features '
+                                      '(Ndof = 6) are supported on the device path, file has Ndof = %d' % ndof)
+        if nsv < 1 or len(props) < 29 + nsv * (ndof + 1):
+            raise ValueError('from_MLparam: file %s-svm.csv is truncated' % trunk)
+        meta = None
+        if os.path.exists(trunk + '-svm_meta.json'):
+            with open(trunk + '-svm_meta.json') as fp:
+                meta = json.load(fp)
+        m = cls(name=name or (os.path.basename(file)))
+        if props[10] > 0.:
+            CV = np.zeros((6, 6))
+            CV[0, 0], CV[1, 1], CV[2, 2] = props[2], props[10], props[11]
+            CV[0, 1] = CV[1, 0] = props[3]
+            CV[0, 2] = CV[2, 0] = props[12]
+            CV[1, 2] = CV[2, 1] = props[13]
+            CV[3, 3], CV[4, 4], CV[5, 5] = props[4], props[14], props[15]
+            iso = (props[10] == props[2] and props[11] == props[2] and props[12] == props[3] and props[13] == props[3]
+                   and props[14] == props[4] and props[15] == props[4])
+            if iso:
+                m.elasticity(C11=props[2], C12=props[3], C44=props[4])
+            else:
+                m.elasticity(CV=CV)
+        else:
+            m.elasticity(C11=props[2], C12=props[3], C44=props[4])
+        scale_seq = float(props[8])
+        m.plasticity(sy=float(scale_seq if sy is None else sy), sdim=6)
+        dual = props[29:29 + nsv]
+        sv = props[29 + nsv:29 + nsv + nsv * ndof].reshape(nsv, ndof)
+        m.set_svc(sv, dual, float(props[5]), float(props[6]), scale_seq=scale_seq, dev_only=(props[16] < 0.))
+        m.epc, m.scale_wh = float(props[7]), float(props[9])
+        m.meta = meta
+        return m
+
     def from_sklearn(self, svc, scale_seq=None, dev_only=False):
         """Adopt a fitted sklearn.svm.SVC(kernel='rbf') (binary) as yield function."""
         self.svm_yf = svc

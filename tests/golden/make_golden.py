@@ -569,10 +569,36 @@ def gen_barlat_solve():
     np.savez_compressed(os.path.join(HERE, 'solve_barlat_3x3.npz'), **d)
 
 
+def gen_mlparam():
+    """export_MLparam wire format (material.py:2133-2273): CSV (8 numbers per line: header block, dual coefficients,
+    support vectors) + JSON metadata, written by the reference for a freshly trained SVC; plus reference calc_yf values
+    so that a loader can be checked end to end."""
+    t0 = time.time()
+    mat_h = FE.Material(name='Hill-shear')
+    mat_h.elasticity(E=200.e3, nu=0.3)
+    mat_h.plasticity(sy=150., hill=[1.4, 1., 0.7, 1.2, .8, 1.], sdim=6)
+    m = FE.Material('Hill-ML')
+    m.train_SVC(C=2, gamma=0.5, mat_ref=mat_h, Nseq=4, Nlc=300, Fe=0.7, Ce=0.95)
+    cwd = os.getcwd()
+    os.chdir(HERE)
+    try:
+        m.export_MLparam(sname='tests/golden/make_golden.py', source='Hill-shear reference material', file='mlparam_hill',
+                         path='./', descr=['sy', 'hill'], param=[150., [1.4, 1., 0.7, 1.2, .8, 1.]])
+    finally:
+        os.chdir(cwd)
+    rng = np.random.default_rng(9)
+    s = rng.standard_normal((200, 6))
+    sig = s / mat_h.calc_seq(s)[:, None] * (rng.uniform(0.05, 1.6, 200) * m.sy)[:, None]
+    out = svc_arrays(m)
+    out.update(yf_sig=sig, yf=m.calc_yf(sig), C11=m.C11, C12=m.C12, C44=m.C44)
+    np.savez_compressed(os.path.join(HERE, 'mlparam_hill.npz'), **out)
+    print(f'mlparam_hill-svm.csv / -svm_meta.json / mlparam_hill.npz  nsv={len(out["dual"])}  {time.time() - t0:.1f}s')
+
+
 if __name__ == '__main__':
     what = sys.argv[1:] or ['all']
     if 'all' in what:
-        what = ['response', 'kmat', 'solve', 'svc', 'barlat', 'barlat_response']
+        what = ['response', 'kmat', 'solve', 'svc', 'barlat', 'barlat_response', 'barlat_solve', 'mlparam']
     for w in what:
         print('==', w)
         globals()['gen_' + w]()

@@ -351,3 +351,14 @@ def test_multigrid_and_jacobi_cg_agree_and_mg_is_mesh_independent():
     its_mg = np.array([s[0] for s in a.solver_stats])
     its_j = np.array([s[0] for s in b.solver_stats])
     assert its_mg.max() <= 60 and its_j.mean() > 4 * its_mg.mean()
+
+
+def test_from_MLparam_yield_function_matches_reference(golden):
+    """A model exported by the reference (export_MLparam) and loaded with Material.from_MLparam evaluates the same
+    yield function as the reference material it came from (calc_yf on 200 stresses)."""
+    import os
+    g = golden('mlparam_hill')
+    here = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden')
+    m = FE.Material.from_MLparam('mlparam_hill', path=here + os.sep)
+    yf = m.calc_yf(g['yf_sig'])
+    assert np.max(np.abs(yf - g['yf'])) < 1e-10

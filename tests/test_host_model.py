@@ -102,3 +102,20 @@ def test_bc_argument_errors():
         fe.bcright(1., 'disp', 'z')
     with pytest.raises(ValueError):
         FE.Model(dim=3)
+
+
+def test_from_MLparam_parses_the_reference_export(golden):
+    """Loader for the export_MLparam wire format (material.py:2133-2273) against a file written by the reference
+    (tests/golden/mlparam_hill-svm.csv / -svm_meta.json, make_golden.py gen_mlparam): host-side parsing only."""
+    import os
+    import numpy as np
+    import pylabfea_b200 as FE
+    g = golden('mlparam_hill')
+    here = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden')
+    m = FE.Material.from_MLparam('mlparam_hill', path=here + os.sep)
+    sv, dc, rho = m._svc
+    assert np.array_equal(sv, g['sv']) and np.array_equal(dc, g['dual'])
+    assert rho == float(g['rho']) and m.gam_yf == float(g['gamma']) and m.scale_seq == float(g['scale_seq'])
+    assert m.sy == float(g['sy']) and m.dev_only == bool(g['dev_only']) and m.ML_yf
+    assert np.allclose(m.CV, g['CV'], rtol=1e-15, atol=0.)
+    assert m.meta['Data']['Class'] == 'SVC_parameters' and m.meta['Model']['Creator'] == 'pylabfea'
