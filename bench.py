@@ -258,7 +258,6 @@ def main():
     ap.add_argument('--no-e2e', action='store_true')
     ap.add_argument('--no-cpu', action='store_true')
     ap.add_argument('--compact', type=int, default=1)
-    ap.add_argument('--passb-wsmem', type=int, default=2)
     ap.add_argument('--assembly-tiled', type=int, default=2)
     ap.add_argument('--opt', action='append', default=[], help='extra plf_set_option key=value (A/B measurements)')
     args = ap.parse_args()
@@ -288,7 +287,6 @@ def main():
     from pylabfea_b200 import _lib
     ctx = _lib.Context(local)
     ctx.set_option('compact', args.compact)
-    ctx.set_option('passb_wsmem', args.passb_wsmem)
     ctx.set_option('assembly_tiled', args.assembly_tiled)
     for kv in args.opt:
         k, v = kv.split('=')

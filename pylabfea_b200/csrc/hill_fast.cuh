@@ -128,17 +128,11 @@ __device__ __forceinline__ void hill_qgrad(const DevMat &m, const double *c, dou
     g[5] = 6. * m.hill[5] * c[5];
 }
 
-// accumulator of the symmetric tangent sum: 21 registers, or 21 shared-memory words per thread (stride = block size)
+// accumulator of the symmetric tangent sum: 21 registers
 struct WRegs {
     double w[21];
     __device__ __forceinline__ double get(int k) const { return w[k]; }
     __device__ __forceinline__ void set(int k, double v) { w[k] = v; }
-};
-struct WShared {
-    double *p;
-    int stride;
-    __device__ __forceinline__ double get(int k) const { return p[k * stride]; }
-    __device__ __forceinline__ void set(int k, double v) { p[k * stride] = v; }
 };
 
 struct HillStep {
@@ -269,7 +263,7 @@ __device__ __forceinline__ int hill_passA(const DevMat &m, double *s, const doub
 // Pass B: the 50 sub-steps for an element that pass A deferred.
 //   epd : in = epl at the start of the step, out = epl + depl (the caller recovers depl = epd - epl; keeping only the
 //         running sum live saves 12 registers in the loop)
-//   W   : accumulator policy (WRegs / WShared) for sum_k ca ca^T / hh (+ correction blocks)
+//   W   : accumulator (WRegs) for sum_k ca ca^T / hh (+ correction blocks)
 //   gs  : out, symmetric 21.
 // Returns branch code 2 (| 4 when a radial-return correction fired).
 // Fast modes of the sub-step loop, chosen on the host for single-material batches (the flags are compile-time, so the

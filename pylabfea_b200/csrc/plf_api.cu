@@ -362,7 +362,7 @@ extern "C" int plf_batch_run(plf_ctx *ctx, plf_batch *b)
 {
     if (!ctx || !b) return PLF_EINVAL;
     if (ctx->nmat == 0) return fail(ctx, PLF_ESTATE, "plf_batch_run: no materials set");
-    LaunchCtx lc{ctx->stream, ctx->sm_count, ctx->passb_wsmem, ctx->passa_direct, ctx->max_fm, ctx->minb, ctx->k1_only};
+    LaunchCtx lc{ctx->stream, ctx->sm_count, ctx->passa_direct, ctx->max_fm, ctx->k1_only};
     CK(launch_response(lc, ctx->hmats, ctx->nmat, b->n, b->mat_id, b->sig, b->epl, b->deps, b->fy, b->sig_out, b->depl,
                        b->ctan, b->nsteps, b->worklist, (unsigned int *)(ctx->d_scalars + 16),
                        (unsigned long long *)(ctx->d_scalars + 8), ctx->compact, &ctx->launches));
@@ -388,10 +388,8 @@ extern "C" int plf_set_option(plf_ctx *ctx, const char *key, int value)
     if (!ctx || !key) return PLF_EINVAL;
     if (!strcmp(key, "compact")) { ctx->compact = value; return PLF_OK; }
     if (!strcmp(key, "assembly_tiled")) { assembly_set_tiled(value); return PLF_OK; }
-    if (!strcmp(key, "passb_wsmem")) { ctx->passb_wsmem = value; return PLF_OK; }
     if (!strcmp(key, "passa_direct")) { ctx->passa_direct = value; return PLF_OK; }
     if (!strcmp(key, "max_fm")) { ctx->max_fm = value; return PLF_OK; }
-    if (!strcmp(key, "minb")) { ctx->minb = value; return PLF_OK; }
     if (!strcmp(key, "k1_only")) { ctx->k1_only = value; return PLF_OK; }
     if (!strcmp(key, "solver_mg")) { ctx->solver_mg = value; return PLF_OK; }
     return fail(ctx, PLF_EINVAL, std::string("plf_set_option: unknown key ") + key);

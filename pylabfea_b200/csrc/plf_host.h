@@ -23,10 +23,8 @@ struct GeomClass {
 struct LaunchCtx {
     cudaStream_t stream;
     int sm_count;
-    int passb_wsmem = 2;   // pass B variant (see launch_response)
     int passa_direct = 0;  // 1: pass A writes its records straight from registers (256-bit stores) instead of staging them
     int max_fm = 4;        // cap of the single-material fast mode (hill_fast.cuh)
-    int minb = 4;          // blocks per SM requested for the planar pass B kernel (3..6)
     int k1_only = 0;       // diagnostics: 1 = launch pass A only
 };
 

@@ -38,8 +38,6 @@ struct plf_ctx {
     int passa_direct = 0;                 // pass A: shared-memory staged coalesced stores (0, fastest measured) or per-thread 256-bit stores (1)
     int max_fm = 4;                       // cap of the single-material fast mode (hill_fast.cuh)
     int k1_only = 0;                      // diagnostics: 1 = launch pass A only
-    int minb = 4;                         // blocks per SM requested for the return-mapping kernels (3 or 4)
-    int passb_wsmem = 2;                  // pass B variant: 0 regs/2 blocks per SM, 1 smem accumulator/4, 2 regs/3 (fastest measured)
 
     // materials
     int nmat = 0, planestress = 0;

@@ -315,9 +315,9 @@ __global__ void __launch_bounds__(RB, 3) response_passA_kernel(int64_t n, const 
     }
 }
 
-// WSMEM: the 21-entry tangent accumulator lives in shared memory ([k][thread], conflict free) instead of registers,
-// which lets 4 blocks (16 warps) share an SM instead of 2.
-template <bool WSMEM, int MINB, bool SINGLE, int FM>
+// Pass B: persistent kernel over the two-ended work list.  (Variants that kept the 21-entry tangent accumulator in
+// shared memory for 4 blocks per SM, or ran at 2 blocks per SM without register cap, measured slower and were removed.)
+template <int MINB, bool SINGLE, int FM>
 __global__ void __launch_bounds__(RB, MINB) response_passB_kernel(const int32_t *__restrict__ mat_id, const double *__restrict__ sig,
                                                             const double *__restrict__ epl, const double *__restrict__ deps,
                                                             double *__restrict__ fy, double *__restrict__ sig_out,
@@ -326,24 +326,19 @@ __global__ void __launch_bounds__(RB, MINB) response_passB_kernel(const int32_t 
                                                             int64_t nlist, unsigned int *count)
 {
     // count: [0] front class, [1] back class of the two-ended work list, [2] blocks that have finished
-    __shared__ double s_W[WSMEM ? 21 * RB : (FM >= 3 ? 12 * RB : 1)];
+    __shared__ double s_xc[FM >= 3 ? 12 * RB : 1];   // radial-return correction sums + deps_r / 50 of the isotropic modes
     const unsigned int n0 = count[0], n1 = count[1];
     for (unsigned int t = blockIdx.x * RB + threadIdx.x; t < n0; t += gridDim.x * RB) {
         const int64_t e = worklist[t];
-        if (WSMEM) {
-            WShared W{s_W + threadIdx.x, RB};
-            passB_element<SINGLE, FM>(e, W, nullptr, mat_id, sig, epl, deps, fy, sig_out, depl_out, ctan, nsteps);
-        } else {
-            WRegs W;
-            passB_element<SINGLE, FM>(e, W, s_W + threadIdx.x, mat_id, sig, epl, deps, fy, sig_out, depl_out, ctan, nsteps);
-        }
+        WRegs W;
+        passB_element<SINGLE, FM>(e, W, s_xc + threadIdx.x, mat_id, sig, epl, deps, fy, sig_out, depl_out, ctan, nsteps);
     }
     if (FM == 4 || FM == 6) {
         // the non-planar elements (back of the list) with the general loop of the material class
         for (unsigned int t = blockIdx.x * RB + threadIdx.x; t < n1; t += gridDim.x * RB) {
             const int64_t e = worklist[nlist - 1 - (int64_t)t];
             WRegs W;
-            passB_element<SINGLE, (FM == 4 ? 3 : 1)>(e, W, s_W + threadIdx.x, mat_id, sig, epl, deps, fy, sig_out, depl_out, ctan,
+            passB_element<SINGLE, (FM == 4 ? 3 : 1)>(e, W, s_xc + threadIdx.x, mat_id, sig, epl, deps, fy, sig_out, depl_out, ctan,
                                                      nsteps);
         }
     }
@@ -670,7 +665,7 @@ cudaError_t launch_response(const LaunchCtx &lc, const DevMat *hmats, int nmat, 
     if (any_hill) {
         const bool single = (nmat == 1);
         const bool direct = lc.passa_direct != 0;
-        const int fm = fast_mode(hmats, nmat, lc.passb_wsmem == 2 ? lc.max_fm : 0);   // the pass B A/B variants 0 and 1 keep the general path
+        const int fm = fast_mode(hmats, nmat, lc.max_fm);
         const unsigned pgrid = (unsigned)std::min<int64_t>((int64_t)lc.sm_count * 3, (int64_t)grid);
         if (compact && worklist) {
             // work_count[0..2] are zero here: set at context creation and re-zeroed by the last block of pass B
@@ -699,23 +694,18 @@ cudaError_t launch_response(const LaunchCtx &lc, const DevMat *hmats, int nmat, 
                 return cudaGetLastError();
             }
             const int64_t bgrid = std::min<int64_t>((int64_t)lc.sm_count * 8, (int64_t)grid);
-#define PASSB(W, M, S, F)                                                                                                     \
-    response_passB_kernel<W, M, S, F><<<(unsigned)bgrid, RB, 0, lc.stream>>>(mat_id, sig, epl, deps, fy, sig_out, depl, ctan, \
-                                                                             nsteps, worklist, n, work_count)
-            // variant: 0 = accumulator in registers, 2 blocks per SM; 1 = shared memory, 4 blocks; 2 = registers, 3 blocks
-            if (single && lc.passb_wsmem == 1) {
-                PASSB(true, 4, true, 0);
-            } else if (single && lc.passb_wsmem == 0) {
-                PASSB(false, 2, true, 0);
-            } else if (single) {
-                if (fm == 6) PASSB(false, 3, true, 6);
-                else if (fm == 4) PASSB(false, 3, true, 4);   // planar elements first, then whatever is not planar
-                else if (fm == 3) PASSB(false, 3, true, 3);
-                else if (fm == 2) PASSB(false, 3, true, 2);
-                else if (fm == 1) PASSB(false, 3, true, 1);
-                else PASSB(false, 3, true, 0);
+#define PASSB(M, S, F)                                                                                                     \
+    response_passB_kernel<M, S, F><<<(unsigned)bgrid, RB, 0, lc.stream>>>(mat_id, sig, epl, deps, fy, sig_out, depl, ctan, \
+                                                                          nsteps, worklist, n, work_count)
+            if (single) {
+                if (fm == 6) PASSB(3, true, 6);
+                else if (fm == 4) PASSB(3, true, 4);   // planar elements first, then whatever is not planar
+                else if (fm == 3) PASSB(3, true, 3);
+                else if (fm == 2) PASSB(3, true, 2);
+                else if (fm == 1) PASSB(3, true, 1);
+                else PASSB(3, true, 0);
             } else {
-                PASSB(false, 2, false, 0);
+                PASSB(2, false, 0);
             }
 #undef PASSB
             *launches += 2;

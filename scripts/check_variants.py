@@ -9,7 +9,7 @@ ctx = _lib.Context(0)
 mat, CV = bench.j2_material()
 ctx.set_materials([mat], planestress=False)
 def run(sig, epl, deps, **opts):
-    base = dict(compact=1, passa_direct=0, max_fm=2, minb=4)
+    base = dict(compact=1, passa_direct=0, max_fm=2)
     base.update(opts)
     for k, v in base.items():
         ctx.set_option(k, v)

@@ -1,3 +1,4 @@
+// nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o scripts/bin/dfma_lat scripts/dfma_lat.cu
 // Microbenchmark: FP64 FMA dependent-issue latency and per-SM throughput on this GPU as a function of resident warps
 // and independent chains per thread (decides whether the 50-sub-step loop wants occupancy or ILP).
 #include <cstdio>

@@ -1,3 +1,4 @@
+// nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o scripts/bin/membw scripts/membw.cu
 // Microbenchmark: HBM bandwidth of this GPU for read-only, write-only, copy and the return mapping's own mix
 // (144 B read + 392 B written per element), 128-bit accesses, grid-stride, buffers far larger than L2.
 #include <cstdio>
@@ -50,6 +51,5 @@ int main()
         const size_t np = n / 49;
         t = timeit([&] { k_mix<<<g, 256>>>(a, b, np); });   printf("blocks/SM %2d mix 144r:392w %.0f GB/s (read+write)\n", bps, np * (18 + 49) * 16 / t / 1e6);
     }
-    t_done:
     return 0;
 }
