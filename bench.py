@@ -7,8 +7,10 @@ One "step" = one pass of the non-linear inner loop of Model.solve over one mesh:
 (Material.response for every element) followed by the K integration + CSR assembly (Model.setupK) from the freshly
 computed tangents.  Workload (config.workload): 1024x1024 Q4 mesh, J2 plasticity (sy=150, khard=500, E=200e3,
 nu=0.3, plane strain), synthetic spatially correlated element states (seeded) that populate the elastic / 1-step /
-50-sub-step branches of the reference algorithm.  N>1 (torchrun): every rank owns its own mesh block of the same size
-(weak scaling, no data-path collective -- element updates and element rows are independent).
+50-sub-step branches of the reference algorithm.  N>1 (torchrun): ONE mesh of N*1024 x 1024 elements cut into strips of
+1024 element columns, one strip per rank; a rank with a left neighbour recomputes that neighbour's last element column
+(halo), so the K rows of its node columns are complete without communication (pylabfea_b200/shard.py; weak scaling,
+no data-path collective -- element updates and element rows are independent).
 
 `value`  : elements/s through (stress update + assembly), inputs resident in HBM, CUDA events, max over ranks.
 `e2e`    : same step through the C-ABI call that takes HOST buffers (plf_step_host: states in, response results and
@@ -202,9 +204,13 @@ def workload_config(N):
 
 
 def shard_plan(N, rank, world):
-    """Weak scaling: every rank owns its own N x N mesh block (independent elements and element rows, SURVEY.md 8e:
-    no data-path collective).  The block's synthetic state is seeded per rank."""
-    return {'rank': rank, 'world': world, 'mesh': N, 'elements': N * N, 'seed': 1234 + rank}
+    """Weak scaling: the global mesh has world*N x N elements; every rank owns a strip of N element columns (N*N
+    elements) and, when it has a left neighbour, additionally computes that neighbour's last column (halo) so that its
+    K rows need no communication.  The strip's synthetic state is seeded per rank."""
+    from pylabfea_b200.shard import strip_shard
+    s = strip_shard(world * N, rank, world)
+    return {'rank': rank, 'world': world, 'mesh': N, 'elements': N * N, 'seed': 1234 + rank, 'halo': s['halo'],
+            'nx_local': s['nx_local'], 'elem_cols_global': s['elem_cols_global']}
 
 
 class RankGroup:
@@ -292,12 +298,16 @@ def main():
         k, v = kv.split('=')
         ctx.set_option(k, int(v))
     N = args.mesh
-    Nel = N * N
+    NXl = plan['nx_local']                 # N owned element columns (+ 1 halo column on ranks with a left neighbour)
+    Nel = NXl * N                          # elements this rank processes per step
+    owned = N * N                          # elements this rank contributes to `value`
     mat, CV = j2_material()
     ctx.set_materials([mat], planestress=False)
     lx = 4. / N
-    ctx.mesh_structured(N, N, np.full(N, lx), lx, 1., np.zeros(Nel, np.int32))
+    ctx.mesh_structured(NXl, N, np.full(NXl, lx), lx, 1., np.zeros(Nel, np.int32))
     sig, epl, deps = synth_states(N, plan['seed'])
+    if plan['halo']:                       # halo column: any state will do for the timing, re-use the first column's
+        sig, epl, deps = (np.ascontiguousarray(np.concatenate([a[:N], a])) for a in (sig, epl, deps))
     b = ctx.batch_create(Nel)
     ctx.batch_upload(b, sig, epl, deps)
     ctx.synchronize()
@@ -347,7 +357,7 @@ def main():
     resp_ms_max = max_over_ranks(resp_ms)
     asm_ms_max = max_over_ranks(asm_ms)
     ms_per_step = total_ms / K
-    value = world * Nel / (ms_per_step * 1e-3)
+    value = world * owned / (ms_per_step * 1e-3)
 
     # branch census of the workload (one extra, untimed run)
     ns = np.empty(Nel, dtype=np.int32)
@@ -355,6 +365,10 @@ def main():
     ctx.batch_download(b, ctan=ct0, nsteps=ns)
     n50 = int(np.sum(ns == 49))
     nel_elastic = int(np.sum(np.all(ct0.reshape(Nel, 36) == CV.ravel()[None, :], axis=1)))
+    if world > 1:
+        workload_extra = {'partition': 'strips of %d element columns of one %dx%d mesh, 1 halo column on ranks > 0' % (N, world * N, N)}
+    else:
+        workload_extra = {}
     del ct0
 
     # ---- e2e through the host-buffer C-ABI calls -----------------------------------------------------------
@@ -387,7 +401,7 @@ def main():
         e2e_ms = max_over_ranks(max(ctx.event_elapsed(4000, 4001), (time.perf_counter() - t0) * 1e3)) / ke
         h2d = Nel * 3 * 48
         d2h = Nel * (8 + 48 + 48 + 288 + 4) + ctx.nnz * 8
-        e2e = {'value': world * Nel / (e2e_ms * 1e-3), 'unit': 'elements/s', 'h2d_bytes_per_step': int(h2d),
+        e2e = {'value': world * owned / (e2e_ms * 1e-3), 'unit': 'elements/s', 'h2d_bytes_per_step': int(h2d),
                'd2h_bytes_per_step': int(d2h), 'ms_per_step': e2e_ms,
                'api': 'plf_step_host: (Nel,6) sig/epl/deps in; fy, sig, depl, grad_stiff, nsteps and the CSR(K) values out (pinned host buffers, chunked three-stream pipeline)'}
 
@@ -449,8 +463,8 @@ def main():
 
     line = {'metric': METRIC, 'value': value, 'unit': 'elements/s', 'n_gpus': world, 'steps': K, 'warmup': max(args.warmup, 3),
             'ms_per_step': ms_per_step, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f64',
-            'data': 'synthetic', 'config': workload_config(N),
-            'updates_per_s': world * Nel / (resp_ms_max * 1e-3), 'assembly_elems_per_s': world * Nel / (asm_ms_max * 1e-3),
+            'data': 'synthetic', 'config': dict(workload_config(N), **workload_extra),
+            'updates_per_s': world * owned / (resp_ms_max * 1e-3), 'assembly_elems_per_s': world * owned / (asm_ms_max * 1e-3),
             'branch_mix': {'elastic': nel_elastic / Nel, 'substep50': n50 / Nel, 'plastic_1step': 1. - (nel_elastic + n50) / Nel},
             'roofline': roofline, 'cpu_baseline': cpu, 'e2e': e2e, 'gpu_launches': int(gpu_launches),
             'launches_per_step': launches_per_step, 'clocks': clocks, 'wall_s_timed_region': t_wall,

@@ -45,3 +45,24 @@ def test_shard_plan_is_per_rank():
     import bench
     p0, p1 = bench.shard_plan(128, 0, 2), bench.shard_plan(128, 1, 2)
     assert p0['elements'] == p1['elements'] == 128 * 128 and p0['seed'] != p1['seed']
+
+
+def test_strip_shards_partition_the_mesh_exactly():
+    """Host logic of the strip partition (pylabfea_b200/shard.py): owned element and node columns of all ranks tile the
+    global mesh exactly once, ranks > 0 carry one halo element column, local element ids are contiguous runs."""
+    sys.path.insert(0, ROOT)
+    from pylabfea_b200.shard import strip_shard, local_element_ids
+    for NX, NY, world in ((1024, 1024, 8), (37, 5, 4), (8, 3, 8), (10, 2, 3)):
+        elem_cols, node_cols = [], []
+        for r in range(world):
+            s = strip_shard(NX, r, world)
+            a, b = s['elem_cols_global']
+            elem_cols += list(range(a, b))
+            node_cols += s['owned_node_cols_global']
+            assert s['halo'] == (1 if r > 0 else 0) and s['nx_local'] == b - a + s['halo']
+            ids = local_element_ids(s, NY)
+            assert ids == list(range(s['first_col_global'] * NY, b * NY))
+            assert s['owned_node_cols_local'][0] == s['halo']     # the halo's left node column is never owned
+        assert elem_cols == list(range(NX)) and node_cols == list(range(NX + 1))
+    with pytest.raises(ValueError):
+        strip_shard(4, 0, 5)

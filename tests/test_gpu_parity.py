@@ -386,3 +386,43 @@ def test_response_hill_isotropic_planar_mode_vs_oracle(ctx):
         assert np.max(np.abs(out[2][idx] - oref[2])) < TOL * np.max(np.abs(oref[2]))
     finally:
         ctx.set_option('max_fm', 4)
+
+
+@pytest.mark.parametrize('world', [2, 3])
+def test_strip_sharded_K_rows_equal_global_K(ctx, golden, world):
+    """a rank that owns a strip of element columns of ONE mesh and recomputes its left neighbour's last column
+    (halo) assembles the rows of its node columns bit-identically to the single-GPU assembly of the whole mesh -- no
+    communication, same ascending-element summation order.  Ranks are played one after the other on one GPU."""
+    from pylabfea_b200.shard import strip_shard, local_element_ids
+    g = golden('response_j2')
+    NX, NY = 26, 9
+    dx = np.array([0.1, 0.25, 0.15, 0.3])[np.arange(NX) % 4]   # non-uniform columns: four geometry classes
+    ctx.set_materials([plf_material_from_golden(g)], planestress=False)
+    rng = np.random.default_rng(17)
+    T = g['pe_ctan'][rng.integers(0, len(g['pe_ctan']), NX * NY)]
+    ctx.mesh_structured(NX, NY, dx, 0.2, 1., np.zeros(NX * NY, np.int32))
+    ctx.set_tangent(T)
+    ctx.setupK()
+    rp_g, col_g, val_g = ctx.get_csr()
+    seen = 0
+    for r in range(world):
+        s = strip_shard(NX, r, world)
+        first, nxl = s['first_col_global'], s['nx_local']
+        ids = np.array(local_element_ids(s, NY))
+        ctx.mesh_structured(nxl, NY, dx[first:first + nxl], 0.2, 1., np.zeros(nxl * NY, np.int32))
+        ctx.set_tangent(T[ids])
+        ctx.setupK()
+        rp, col, val = ctx.get_csr()
+        for jg, jl in zip(s['owned_node_cols_global'], s['owned_node_cols_local']):
+            for k in range(NY + 1):
+                for c in range(2):
+                    rg, rl = 2 * (jg * (NY + 1) + k) + c, 2 * (jl * (NY + 1) + k) + c
+                    vg, vl = val_g[rp_g[rg]:rp_g[rg + 1]], val[rp[rl]:rp[rl + 1]]
+                    if jg == 0 or jg == NX or (jl > 0 and jl < nxl):
+                        assert np.array_equal(vg, vl), (r, jg, k, c)
+                    else:
+                        raise AssertionError('owned node column on a local boundary that is not a global boundary')
+                    # column indices agree up to the shift of the node numbering
+                    assert np.array_equal(col_g[rp_g[rg]:rp_g[rg + 1]] - 2 * first * (NY + 1), col[rp[rl]:rp[rl + 1]])
+                    seen += 1
+    assert seen == 2 * (NX + 1) * (NY + 1)
