@@ -404,6 +404,23 @@ def main():
         e2e = {'value': world * owned / (e2e_ms * 1e-3), 'unit': 'elements/s', 'h2d_bytes_per_step': int(h2d),
                'd2h_bytes_per_step': int(d2h), 'ms_per_step': e2e_ms,
                'api': 'plf_step_host: (Nel,6) sig/epl/deps in; fy, sig, depl, grad_stiff, nsteps and the CSR(K) values out (pinned host buffers, chunked three-stream pipeline)'}
+        # informational second figure (NOT the headline): the same call when the consumer of the tangents and of K is
+        # the on-device solver, as in Model.solve -- grad_stiff and CSR(K) stay in HBM, only fy / sig / depl / nsteps
+        # return to the host
+        def lean_step():
+            ctx.step_host(b, hs, he, hd, fy=o_fy, sig_out=o_sig, depl=o_dp, nsteps=o_ns)
+        for _ in range(2):
+            lean_step()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(ke):
+            lean_step()
+        ctx.synchronize()
+        barrier()
+        lean_ms = max_over_ranks((time.perf_counter() - t0) * 1e3) / ke
+        e2e['device_resident_tangents_and_K'] = {'value': world * owned / (lean_ms * 1e-3), 'ms_per_step': lean_ms,
+                                                  'd2h_bytes_per_step': int(Nel * (8 + 48 + 48 + 4)),
+                                                  'note': 'informational: grad_stiff and CSR(K) not copied back (on-device solve)'}
 
     if rank != 0:
         group.close()

@@ -17,7 +17,7 @@ struct MgLevel {
 struct MgHierarchy {
     std::vector<MgLevel> lv;
     int nu = 2;                // pre- and post-smoothing sweeps (even)
-    int coarse_sweeps = 40;    // damped Jacobi sweeps on the coarsest level
+    int coarse_sweeps = 10;    // damped Jacobi sweeps on the coarsest level (40 measured 15 % slower per solve, 4 % fewer iterations)
     double omega = 0.7;
     int levels() const { return (int)lv.size(); }
 };

@@ -392,6 +392,14 @@ extern "C" int plf_set_option(plf_ctx *ctx, const char *key, int value)
     if (!strcmp(key, "max_fm")) { ctx->max_fm = value; return PLF_OK; }
     if (!strcmp(key, "k1_only")) { ctx->k1_only = value; return PLF_OK; }
     if (!strcmp(key, "solver_mg")) { ctx->solver_mg = value; return PLF_OK; }
+    if (!strcmp(key, "mg_nu") || !strcmp(key, "mg_coarse_sweeps") || !strcmp(key, "mg_omega_permille")) {
+        // multigrid tuning knobs (take effect at the next plf_mesh_structured / solve; the CG graph is rebuilt)
+        if (!strcmp(key, "mg_nu")) ctx->mg_nu = value & ~1;
+        else if (!strcmp(key, "mg_coarse_sweeps")) ctx->mg_coarse_sweeps = value;
+        else ctx->mg_omega = value * 1e-3;
+        model_apply_mg_options(ctx);
+        return PLF_OK;
+    }
     return fail(ctx, PLF_EINVAL, std::string("plf_set_option: unknown key ") + key);
 }
 

@@ -32,6 +32,15 @@ static int dalloc(plf_ctx *ctx, T **p, size_t n)
     return PLF_OK;
 }
 
+void model_apply_mg_options(plf_ctx *ctx)
+{
+    if (!ctx->mg) return;
+    ctx->mg->nu = std::max(2, ctx->mg_nu);
+    ctx->mg->coarse_sweeps = std::max(1, ctx->mg_coarse_sweeps);
+    ctx->mg->omega = ctx->mg_omega;
+    cg_graph_reset();   // the captured V-cycle has the old sweep counts baked in
+}
+
 void model_free(plf_ctx *c)
 {
     cg_graph_reset();
@@ -182,6 +191,7 @@ extern "C" int plf_mesh_structured(plf_ctx *ctx, int NX, int NY, const double *d
     CK(cudaMemsetAsync(ctx->d_f, 0, D * sizeof(double), ctx->stream));
     ctx->mg = new MgHierarchy();
     CK(mg_build(*ctx->mg, NX, NY));
+    model_apply_mg_options(ctx);
     ctx->mesh_ready = true;
     ctx->K_ready = false;
     rc = plf_set_tangent(ctx, nullptr);

@@ -75,6 +75,8 @@ struct plf_ctx {
     unsigned char *d_fixed = nullptr;
     plf::MgHierarchy *mg = nullptr;   // multigrid preconditioner of plf_solve_linear (built with the mesh)
     int solver_mg = 1;                // 1: V-cycle preconditioner when the mesh coarsens at least once, 0: Jacobi
+    int mg_nu = 2, mg_coarse_sweeps = 10;   // smoothing sweeps per level (even) / on the coarsest level
+    double mg_omega = 0.7;            // Jacobi damping
     double *d_partial = nullptr;   // block partial sums
     int n_partial = 0;
 };
@@ -82,3 +84,5 @@ struct plf_ctx {
 int fail(plf_ctx *c, int code, const std::string &msg);
 void model_free(plf_ctx *ctx);
 cudaError_t model_upload_materials(plf_ctx *ctx);
+
+void model_apply_mg_options(plf_ctx *ctx);   // copies mg_nu / mg_coarse_sweeps / mg_omega into the hierarchy

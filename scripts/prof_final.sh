@@ -8,3 +8,4 @@ timeout 600 ncu --set full --clock-control none --import-source on -k regex:'res
 timeout 600 python bench.py --steps 200 --warmup 5 > gpurun_out/${TAG}_bench.json 2> gpurun_out/${TAG}_bench.err
 timeout 600 python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/${TAG}_bench_reference.json 2>> gpurun_out/${TAG}_bench.err
 tail -c 900 gpurun_out/${TAG}_bench.json
+timeout 300 python __graft_entry__.py smoke 2>&1 | tail -1
