@@ -41,6 +41,24 @@ __device__ __forceinline__ double fast_rcp(double x)
     return y;
 }
 
+// One-Newton-step versions for the inside of the 50-sub-step loops of the isotropic modes: the hardware seed is good
+// to 2^-22, one step gives ~1e-13 relative -- the quantity only scales the plastic correction of a sub-step (itself
+// ~1e-2 of the stress), and the sub-step loop is bound by exactly this dependent FP64 chain.
+__device__ __forceinline__ double fast_rsqrt1(double x)
+{
+    double y;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+    const double e = fma(-0.5 * x * y, y, 0.5);
+    return fma(y, e, y);
+}
+__device__ __forceinline__ double fast_rcp1(double x)
+{
+    double y;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+    const double e = fma(-x, y, 1.);
+    return fma(y, e, y);
+}
+
 // o = CV v
 __device__ __forceinline__ void cv_mul(const DevMat &m, const double *v, double *o)
 {
@@ -442,6 +460,12 @@ __device__ __forceinline__ void seq_rs(double q, double &seq, double &rs)
     rs = fast_rsqrt(q + 1e-300);   // the addend vanishes in rounding for any q > 1e-284
     seq = q * rs;
 }
+// inside the sub-step loops: one Newton step (see fast_rsqrt1)
+__device__ __forceinline__ void seq_rs1(double q, double &seq, double &rs)
+{
+    rs = fast_rsqrt1(q + 1e-300);
+    seq = q * rs;
+}
 
 // ------------------------------------------------------------------------------------------------------------
 // FM 3: J2 yield function on isotropic elasticity (C11 - C12 = 2 C44 = 2G; BASELINE configs 2 and the 1024^2 target).
@@ -755,7 +779,7 @@ __device__ __forceinline__ int hill_passB_iso2d(const DevMat &m, double *s, doub
         n0 = fma(-beta, n0, n0 + dc0); n1 = fma(-beta, n1, n1 + dc1); n2 = fma(-beta, n2, n2 + dc2); n5 = fma(-beta, n5, n5 + dc5);
         p += pc;
         q2 = 1.5 * (n0 * n0 + n1 * n1 + n2 * n2) + 3. * (n5 * n5);
-        seq_rs(q2, seq, rs);
+        seq_rs1(q2, seq, rs);
         const double e2s = (2. / 3.) * ((f0 * f0 + f1e * f1e + f2 * f2) + 0.5 * (f5 * f5));
         const double lhs = seq - c0;
         if (lhs > 0. && lhs * lhs > K2 * e2s) {
@@ -771,6 +795,7 @@ __device__ __forceinline__ int hill_passB_iso2d(const DevMat &m, double *s, doub
         }
         e0 = f0; e1 = f1e; e2 = f2; e5 = f5;
     }
+    seq_rs(q2, seq, rs);   // full-precision seq for the returned yield-function value
     s[0] = n0 + p; s[1] = n1 + p; s[2] = n2 + p; s[3] = 0.; s[4] = 0.; s[5] = n5;
     epd[0] = e0; epd[1] = e1; epd[2] = e2; epd[5] = e5;   // epd[3], epd[4] stay zero
     fy = seq - (m.sy + (m.khard != 0. ? eps_eq6(epd) * m.khard : 0.));
@@ -917,7 +942,7 @@ __device__ __forceinline__ int hill_passB_hilliso2d(const DevMat &m, double *s, 
         const double Gam = fma(g5, gh5, fma(g2, g2, fma(g1, g1, g0 * g0)));
         const double gcd = fma(g5, c5k, fma(g2, c2k, fma(g1, c1k, g0 * c0k)));
         const bool yplus = (q + gcd) + qc > ythr2;
-        const double D = fast_rcp(fma(kap, q, Gam));
+        const double D = fast_rcp1(fma(kap, q, Gam));
         const double beta = gcd * D;
         const double gam = yplus ? beta * iG2 : 0.;
         const double w = G2 * D;
@@ -930,7 +955,7 @@ __device__ __forceinline__ int hill_passB_hilliso2d(const DevMat &m, double *s, 
         u0 = h0 * d01; u1 = h1 * d12; u2 = h2 * d20;
         g0 = u0 - u2; g1 = u1 - u0; g2 = u2 - u1; g5 = h5x6 * s5;
         q = 0.5 * fma(g5, s5, fma(u2, d20, fma(u1, d12, u0 * d01)));
-        seq = fast_sqrt(q);
+        seq = q * fast_rsqrt1(q + 1e-300);
         const double e2s = (2. / 3.) * ((f0 * f0 + f1e * f1e + f2 * f2) + 0.5 * (f5 * f5));
         const double lhs = seq - c0;
         if (lhs > 0. && lhs * lhs > K2 * e2s) {
@@ -946,6 +971,7 @@ __device__ __forceinline__ int hill_passB_hilliso2d(const DevMat &m, double *s, 
         }
         e0 = f0; e1 = f1e; e2 = f2; e5 = f5;
     }
+    seq = fast_sqrt(q);   // full-precision seq for the returned yield-function value
     s[0] = s0; s[1] = s1; s[2] = s2; s[3] = 0.; s[4] = 0.; s[5] = s5;
     epd[0] = e0; epd[1] = e1; epd[2] = e2; epd[5] = e5;   // epd[3], epd[4] stay zero
     fy = seq - (m.sy + (m.khard != 0. ? eps_eq6(epd) * m.khard : 0.));

@@ -327,6 +327,9 @@ __global__ void __launch_bounds__(RB, MINB) response_passB_kernel(const int32_t 
 {
     // count: [0] front class, [1] back class of the two-ended work list, [2] blocks that have finished
     __shared__ double s_xc[FM >= 3 ? 12 * RB : 1];   // radial-return correction sums + deps_r / 50 of the isotropic modes
+    // launched with programmatic stream serialization: the blocks are resident while pass A drains and wait here for
+    // its completion (and the visibility of its work list), which hides the launch latency between the two passes
+    cudaGridDependencySynchronize();
     const unsigned int n0 = count[0], n1 = count[1];
     for (unsigned int t = blockIdx.x * RB + threadIdx.x; t < n0; t += gridDim.x * RB) {
         const int64_t e = worklist[t];
@@ -694,9 +697,20 @@ cudaError_t launch_response(const LaunchCtx &lc, const DevMat *hmats, int nmat, 
                 return cudaGetLastError();
             }
             const int64_t bgrid = std::min<int64_t>((int64_t)lc.sm_count * 8, (int64_t)grid);
+            cudaLaunchAttribute pdl_attr;
+            pdl_attr.id = cudaLaunchAttributeProgrammaticStreamSerialization;
+            pdl_attr.val.programmaticStreamSerializationAllowed = 1;
+            cudaLaunchConfig_t pdl_cfg = {};
+            pdl_cfg.gridDim = dim3((unsigned)bgrid);
+            pdl_cfg.blockDim = dim3(RB);
+            pdl_cfg.dynamicSmemBytes = 0;
+            pdl_cfg.stream = lc.stream;
+            pdl_cfg.attrs = &pdl_attr;
+            pdl_cfg.numAttrs = 1;
+            const int32_t *wl_c = worklist;
 #define PASSB(M, S, F)                                                                                                     \
-    response_passB_kernel<M, S, F><<<(unsigned)bgrid, RB, 0, lc.stream>>>(mat_id, sig, epl, deps, fy, sig_out, depl, ctan, \
-                                                                          nsteps, worklist, n, work_count)
+    cudaLaunchKernelEx(&pdl_cfg, response_passB_kernel<M, S, F>, mat_id, sig, epl, deps, fy, sig_out, depl, ctan, nsteps, \
+                       wl_c, n, work_count)
             if (single) {
                 if (fm == 6) PASSB(3, true, 6);
                 else if (fm == 4) PASSB(3, true, 4);   // planar elements first, then whatever is not planar
