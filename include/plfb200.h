@@ -46,7 +46,8 @@ typedef enum plf_mat_kind {
     PLF_MAT_ELASTIC = 0, /* Material.sy is None                                                     */
     PLF_MAT_HILL = 1,    /* sdim=6 Hill-6p equivalent stress; J2 is hill = 1 (material.py:653-661)  */
     PLF_MAT_SVC = 2,     /* ML_yf: RBF support-vector yield function, sdim=6 (material.py:398-405)  */
-    PLF_MAT_BARLAT = 3   /* Yld2004-18p equivalent stress (material.py:678-702)                     */
+    PLF_MAT_BARLAT = 3,  /* Yld2004-18p equivalent stress (material.py:678-702)                     */
+    PLF_MAT_HILL3 = 4    /* sdim=3: 3-parameter Hill / J2 on ordered principal stresses (663-673)   */
 } plf_mat_kind;
 
 /* What Material.elasticity / Material.plasticity / train_SVC leave on a Material object
@@ -55,7 +56,8 @@ typedef struct plf_material {
     int32_t kind;     /* plf_mat_kind */
     int32_t nsv;      /* SVC: number of support vectors */
     int32_t dev_only; /* SVC: features use the deviatoric stress (material.py:2337-2338) */
-    int32_t tresca;   /* only the ML_full_yf start value depends on it (material.py:470-473) */
+    int32_t tresca;   /* Tresca equivalent stress max - min principal (material.py:630-632; no gradient, 824-825) and the
+                         ML_full_yf start value (470-473) */
     int32_t lhs;      /* d[] holds LHS parameters (material.py:646-647, 829-830) instead of drucker*[1,1,1] */
     int32_t pad_;
     double E, nu;     /* isotropic constants; used for the plane-stress CV and B row (model.py:274-283, 498-501) */

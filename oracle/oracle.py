@@ -12,7 +12,7 @@ import numpy as np
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB = os.path.join(HERE, 'libplf_oracle.so')
 
-ELASTIC, HILL, SVC, BARLAT = 0, 1, 2, 3
+ELASTIC, HILL, SVC, BARLAT, HILL3 = 0, 1, 2, 3, 4
 
 _dp = C.POINTER(C.c_double)
 _ip = C.POINTER(C.c_int32)
@@ -68,7 +68,7 @@ class Mat:
         m.kind = kind
         m.E, m.nu, m.sy, m.khard = E, nu, sy, khard
         hill = np.ones(6) if hill is None else np.asarray(hill, dtype=float)
-        m.hill[:] = list(hill)
+        m.hill[:] = (list(hill) + [1., 1., 1.])[:6]
         if lhs is not None:
             m.lhs = 1
             m.d[:] = list(lhs)

@@ -54,12 +54,16 @@ __device__ __forceinline__ void atomic_max_nonneg(double *addr, double v)
     atomicMax(reinterpret_cast<unsigned long long *>(addr), (unsigned long long)__double_as_longlong(v));
 }
 
-// analytic yield models that share the thread-per-element kernels: Hill-6p / J2 (HillModel) and Yld2004-18p (BarlatModel)
+// analytic yield models that share the thread-per-element kernels: Hill-6p / J2 (HillModel), Yld2004-18p (BarlatModel)
+// and the sdim = 3 principal-stress formulation (HillPrincModel)
 template <class F>
 __device__ __forceinline__ void with_model(const DevMat &m, F f)
 {
     if (m.kind == PLF_MAT_BARLAT) {
         BarlatModel ym(m);
+        f(ym);
+    } else if (m.kind == PLF_MAT_HILL3) {
+        HillPrincModel ym(m);
         f(ym);
     } else {
         HillModel ym(m);
@@ -229,9 +233,10 @@ __global__ void __launch_bounds__(128) sweep_hill_kernel(int64_t n, int NY, int 
     }
 }
 
-// sweep, thread per element, Yld2004-18p elements (unsplit response_core; FP64-bound: two 3x3 eigen-decompositions per
-// yield-function / gradient evaluation)
-__global__ void __launch_bounds__(128) sweep_barlat_kernel(int64_t n, int NY, int nit, const int32_t *__restrict__ desc,
+// sweep, thread per element, for the yield models with eigen-decompositions (Yld2004-18p, sdim = 3): unsplit
+// response_core, FP64-bound
+template <class Model, int KIND>
+__global__ void __launch_bounds__(128) sweep_model_kernel(int64_t n, int NY, int nit, const int32_t *__restrict__ desc,
                                                            const double *__restrict__ sig, const double *__restrict__ epl,
                                                            const double *__restrict__ du, double *__restrict__ elstiff,
                                                            double *__restrict__ res_sig, double *__restrict__ res_depl,
@@ -243,13 +248,13 @@ __global__ void __launch_bounds__(128) sweep_barlat_kernel(int64_t n, int NY, in
     if (e < n) {
         const int d = __ldg(desc + e);
         const DevMat &m = c_mat[d & 0xffff];
-        if (m.kind == PLF_MAT_BARLAT) {
+        if (m.kind == KIND) {
             double s[6], ep[6], de[6], dp[6], gs[21], fyv;
             int ns = 0;
 #pragma unroll
             for (int k = 0; k < 6; k++) { s[k] = __ldg(sig + e * 6 + k); ep[k] = __ldg(epl + e * 6 + k); }
             element_strain(c_geom[d >> 16], NY, e, du, de);
-            BarlatModel ym(m);
+            Model ym(m);
             const int br = response_core<0>(ym, m, s, ep, de, dp, gs, fyv, ns);
             es = sweep_finish(m, e, nit, s, dp, gs, fyv, ns, br, ep, elstiff, res_sig, res_depl, fyld, nsteps, has_res);
         }
@@ -323,11 +328,19 @@ cudaError_t launch_sweep(const LaunchCtx &lc, const DevMat *hmats, int nmat, int
             (*launches)++;
         }
     }
-    bool any_barlat = false;
-    for (int i = 0; i < nmat; i++) any_barlat |= (hmats[i].kind == PLF_MAT_BARLAT);
+    bool any_barlat = false, any_hill3 = false;
+    for (int i = 0; i < nmat; i++) {
+        any_barlat |= (hmats[i].kind == PLF_MAT_BARLAT);
+        any_hill3 |= (hmats[i].kind == PLF_MAT_HILL3);
+    }
     if (any_barlat) {
-        sweep_barlat_kernel<<<grid, 128, 0, lc.stream>>>(Nel, NY, nit, desc, sig, epl, du, elstiff, res_sig, res_depl, fyld, nsteps,
-                                                         has_res, st);
+        sweep_model_kernel<BarlatModel, PLF_MAT_BARLAT><<<grid, 128, 0, lc.stream>>>(Nel, NY, nit, desc, sig, epl, du, elstiff, res_sig,
+                                                                                     res_depl, fyld, nsteps, has_res, st);
+        (*launches)++;
+    }
+    if (any_hill3) {
+        sweep_model_kernel<HillPrincModel, PLF_MAT_HILL3><<<grid, 128, 0, lc.stream>>>(Nel, NY, nit, desc, sig, epl, du, elstiff,
+                                                                                       res_sig, res_depl, fyld, nsteps, has_res, st);
         (*launches)++;
     }
     for (int i = 0; i < nmat; i++) {
@@ -375,7 +388,7 @@ __global__ void __launch_bounds__(128) commit_elements_kernel(int64_t Nel, int N
         element_strain(gc, NY, e, du, de);
 #pragma unroll
         for (int k = 0; k < 36; k++) C[k] = elstiff[e * 36 + k];
-        if (m.kind == PLF_MAT_HILL || m.kind == PLF_MAT_BARLAT) {
+        if (m.kind == PLF_MAT_HILL || m.kind == PLF_MAT_BARLAT || m.kind == PLF_MAT_HILL3) {
             // Element.depl (model.py:424-437): Mat.epl_dot(sig, epl, CV, deps)
             with_model(m, [&](const auto &ym) {
                 double cd[6], st[6], a[6], ca[6];

@@ -233,7 +233,7 @@ extern "C" int plf_set_materials(plf_ctx *ctx, int nmat, const plf_material *mat
         const plf_material &m = mats[i];
         DevMat &d = ctx->hmats[i];
         memset(&d, 0, sizeof d);
-        if (m.kind < PLF_MAT_ELASTIC || m.kind > PLF_MAT_BARLAT) return fail(ctx, PLF_EINVAL, "plf_set_materials: unknown kind");
+        if (m.kind < PLF_MAT_ELASTIC || m.kind > PLF_MAT_HILL3) return fail(ctx, PLF_EINVAL, "plf_set_materials: unknown kind");
         d.kind = m.kind;
         d.tresca = m.tresca;
         d.lhs = m.lhs;
@@ -362,6 +362,10 @@ extern "C" int plf_batch_run(plf_ctx *ctx, plf_batch *b)
 {
     if (!ctx || !b) return PLF_EINVAL;
     if (ctx->nmat == 0) return fail(ctx, PLF_ESTATE, "plf_batch_run: no materials set");
+    for (int i = 0; i < ctx->nmat; i++)
+        if (ctx->hmats[i].tresca && (ctx->hmats[i].kind == PLF_MAT_HILL || ctx->hmats[i].kind == PLF_MAT_HILL3))
+            // material.py:824-825: the first plastic step of a Tresca material raises in the reference
+            return fail(ctx, PLF_EUNSUPPORTED, "response: analytical gradient for Tresca not implemented");
     LaunchCtx lc{ctx->stream, ctx->sm_count, ctx->passa_direct, ctx->max_fm, ctx->k1_only};
     CK(launch_response(lc, ctx->hmats, ctx->nmat, b->n, b->mat_id, b->sig, b->epl, b->deps, b->fy, b->sig_out, b->depl,
                        b->ctan, b->nsteps, b->worklist, (unsigned int *)(ctx->d_scalars + 16),

@@ -99,6 +99,11 @@ __device__ inline void sym3_eig(const double *v, double *w)
 // ------------------------------------------------------------------------------------------------------------
 __device__ __forceinline__ double hill_seq(const DevMat &m, const double *s)
 {
+    if (m.tresca) {   // material.py:630-632: max - min principal stress, no hydrostatic term
+        double w[3];
+        sym3_eig(s, w);
+        return fmax(w[0], fmax(w[1], w[2])) - fmin(w[0], fmin(w[1], w[2]));
+    }
     double I1 = (s[0] * m.d[0] + s[1] * m.d[1] + s[2] * m.d[2]) / 3.;
     double d01 = s[0] - s[1], d12 = s[1] - s[2], d20 = s[2] - s[0];
     double I2 = m.hill[0] * (d01 * d01) + m.hill[1] * (d12 * d12) + m.hill[2] * (d20 * d20) +
@@ -240,6 +245,72 @@ struct HillModel {
     __device__ __forceinline__ double yf(const double *s, double sflow) const { return seq(s) - sflow; }
     __device__ __forceinline__ double full_yf(const double *s, double sflow) const { return seq(s) - sflow; }
     __device__ __forceinline__ void fgrad(const double *s, double *a) const { hill_fgrad(m, s, hill_seq(m, s), a); }
+};
+
+// sig_princ (basic.py:107-179) of a Voigt stress: principal values in the reference's order.  The reference sorts
+// the eigenvalues that numpy.linalg.eig returns by "major force axes": iev[i] = index of the eigenvector with the largest
+// component along coordinate axis i, then the AXIS indices i are listed by ascending iev and used to index the
+// eigenvalues (basic.py:156-170).  Here the eigen-decomposition is cyclic Jacobi, whose natural order keeps eigenvalue e
+// with diagonal entry e; for stresses whose principal axes are close to the coordinate axes (every state of the
+// reference's own sdim = 3 tests) both give sp = (s11, s22, s33)-like ordering.  For strongly rotated states the
+// reference's result depends on LAPACK's eigenvalue order and is not reproduced bit for bit.
+__device__ inline void princ_ordered(const double *s, double *sp)
+{
+    double w[3], V[3][3];
+    sym3_eigv(s, w, V);
+    int iev[3];
+    for (int i = 0; i < 3; i++) {
+        int best = 0;
+        double vb = fabs(V[i][0]);
+        for (int e = 1; e < 3; e++)
+            if (fabs(V[i][e]) > vb) { vb = fabs(V[i][e]); best = e; }
+        iev[i] = best;
+    }
+    int j[3] = {0, 1, 2}, n = 0;
+    for (int v = 0; v < 3; v++)
+        for (int i = 0; i < 3; i++)
+            if (iev[i] == v && n < 3) j[n++] = i;
+    sp[0] = w[j[0]]; sp[1] = w[j[1]]; sp[2] = w[j[2]];
+}
+
+// sdim = 3 formulation (material.py:663-673, 836-838, 1045-1048): 3-parameter Hill / J2 equivalent stress on the ordered
+// principal stresses; the flow direction is the gradient with respect to the principal stresses written into the
+// normal Voigt components (shear components zero), exactly as epl_dot / C_tan build it.
+struct HillPrincModel {
+    static constexpr bool is_ml = false;
+    const DevMat &m;
+    __device__ explicit HillPrincModel(const DevMat &mm) : m(mm) {}
+    __device__ __forceinline__ double khard() const { return m.khard; }
+    __device__ __forceinline__ double seq_sp(const double *sp, const double *nrm) const
+    {
+        if (m.tresca) return fmax(sp[0], fmax(sp[1], sp[2])) - fmin(sp[0], fmin(sp[1], sp[2]));
+        const double d12 = sp[0] - sp[1], d23 = sp[1] - sp[2], d31 = sp[2] - sp[0];
+        const double I2 = 0.5 * (m.hill[0] * (d12 * d12) + m.hill[1] * (d23 * d23) + m.hill[2] * (d31 * d31));
+        const double I1 = (nrm[0] * m.d[0] + nrm[1] * m.d[1] + nrm[2] * m.d[2]) / 3.;   // 650: Voigt normal components
+        return sqrt(I2) + I1;
+    }
+    __device__ __forceinline__ double seq(const double *s) const
+    {
+        double sp[3];
+        princ_ordered(s, sp);
+        return seq_sp(sp, s);
+    }
+    __device__ __forceinline__ double yf(const double *s, double sflow) const { return seq(s) - sflow; }
+    __device__ __forceinline__ double full_yf(const double *s, double sflow) const { return seq(s) - sflow; }
+    __device__ __forceinline__ void fgrad(const double *s, double *a) const
+    {
+        // calc_fgrad(sig_princ(sig)[0]): a (3,) principal stress vector, seq = calc_seq(sp) with I1 from sp (607-611)
+        double sp[3];
+        princ_ordered(s, sp);
+        const double sq = seq_sp(sp, sp);
+        const double p = (sp[0] + sp[1] + sp[2]) / 3.;
+        const double s0 = sp[0] - p, s1 = sp[1] - p, s2 = sp[2] - p;
+        const double h0 = m.hill[0], h1 = m.hill[1], h2 = m.hill[2];
+        a[0] = ((h0 + h2) * s0 - h0 * s1 - h2 * s2) / (2. * sq) + m.d3[0];
+        a[1] = ((h1 + h0) * s1 - h0 * s0 - h1 * s2) / (2. * sq) + m.d3[1];
+        a[2] = ((h2 + h1) * s2 - h2 * s0 - h1 * s1) / (2. * sq) + m.d3[2];
+        a[3] = a[4] = a[5] = 0.;
+    }
 };
 
 // Yld2004-18p yield model (thread per element): equivalent stress of the reference, analytic gradient from the chain

@@ -430,6 +430,10 @@ static inline unsigned int *counter_ptr(plf_ctx *ctx) { return (unsigned int *)(
 extern "C" int plf_sweep(plf_ctx *ctx, int nit, int32_t *change, int32_t *conv, double *max_hh, int64_t counts[4])
 {
     NEED_MESH("plf_sweep");
+    for (int i = 0; i < ctx->nmat; i++)
+        if (ctx->hmats[i].tresca && (ctx->hmats[i].kind == PLF_MAT_HILL || ctx->hmats[i].kind == PLF_MAT_HILL3))
+            // material.py:824-825: the first plastic step of a Tresca material raises in the reference
+            return fail(ctx, PLF_EUNSUPPORTED, "plf_sweep: analytical gradient for Tresca not implemented");
     LaunchCtx lc{ctx->stream, ctx->sm_count};
     CK(launch_sweep(lc, ctx->hmats, ctx->nmat, ctx->Nel, ctx->NY, nit, ctx->d_desc, ctx->d_sig, ctx->d_epl, ctx->d_du, ctx->d_elstiff,
                     ctx->d_res_sig, ctx->d_res_depl, ctx->d_fyld, ctx->d_nsteps, ctx->d_has_res, ctx->d_worklist, ctx->d_scalars,

@@ -527,9 +527,11 @@ __global__ void __launch_bounds__(128) prim_hill_kernel(int op, int mid, int64_t
     prim_eval(ym, m, op, s, ep, de, nullptr, out, true, e);
 }
 
-// Barlat Yld2004-18p: thread per element (two 3x3 eigen-decompositions per yield-function / gradient evaluation;
-// FP64-bound, not tuned: BASELINE config 5 only)
-__global__ void __launch_bounds__(128) prim_barlat_kernel(int op, int mid, int64_t n, const double *__restrict__ sig,
+// Yield models that need eigen-decompositions -- Barlat Yld2004-18p (BarlatModel, BASELINE config 5) and the sdim = 3
+// principal-stress formulation (HillPrincModel) -- run the unsplit response_core, thread per element (FP64-bound, not
+// tuned).
+template <class Model>
+__global__ void __launch_bounds__(128) prim_model_kernel(int op, int mid, int64_t n, const double *__restrict__ sig,
                                                           const double *__restrict__ epl, const double *__restrict__ deps,
                                                           double *__restrict__ out)
 {
@@ -543,11 +545,12 @@ __global__ void __launch_bounds__(128) prim_barlat_kernel(int op, int mid, int64
         if (epl) ep[k] = epl[e * 6 + k];
         if (deps) de[k] = deps[e * 6 + k];
     }
-    BarlatModel ym(m);
+    Model ym(m);
     prim_eval(ym, m, op, s, ep, de, nullptr, out, true, e);
 }
 
-__global__ void __launch_bounds__(128) response_barlat_kernel(int64_t n, int mid, const int32_t *__restrict__ mat_id,
+template <class Model>
+__global__ void __launch_bounds__(128) response_model_kernel(int64_t n, int mid, const int32_t *__restrict__ mat_id,
                                                               const double *__restrict__ sig, const double *__restrict__ epl,
                                                               const double *__restrict__ deps, double *__restrict__ fy,
                                                               double *__restrict__ sig_out, double *__restrict__ depl_out,
@@ -565,7 +568,7 @@ __global__ void __launch_bounds__(128) response_barlat_kernel(int64_t n, int mid
         ep[k] = __ldg(epl + e * 6 + k);
         de[k] = __ldg(deps + e * 6 + k);
     }
-    BarlatModel ym(m);
+    Model ym(m);
     response_core<0>(ym, m, s, ep, de, dp, gs, fyv, ns);
     if (fy) fy[e] = fyv;
     if (nsteps) nsteps[e] = ns;
@@ -729,9 +732,14 @@ cudaError_t launch_response(const LaunchCtx &lc, const DevMat *hmats, int nmat, 
         }
     }
     for (int i = 0; i < nmat; i++) {
-        if (hmats[i].kind != PLF_MAT_BARLAT) continue;
-        response_barlat_kernel<<<grid, RB, 0, lc.stream>>>(n, i, nmat > 1 ? mat_id : nullptr, sig, epl, deps, fy, sig_out, depl,
-                                                           ctan, nsteps);
+        if (hmats[i].kind == PLF_MAT_BARLAT)
+            response_model_kernel<BarlatModel><<<grid, RB, 0, lc.stream>>>(n, i, nmat > 1 ? mat_id : nullptr, sig, epl, deps, fy,
+                                                                           sig_out, depl, ctan, nsteps);
+        else if (hmats[i].kind == PLF_MAT_HILL3)
+            response_model_kernel<HillPrincModel><<<grid, RB, 0, lc.stream>>>(n, i, nmat > 1 ? mat_id : nullptr, sig, epl, deps, fy,
+                                                                              sig_out, depl, ctan, nsteps);
+        else
+            continue;
         (*launches)++;
     }
     for (int i = 0; i < nmat; i++) {
@@ -758,7 +766,9 @@ cudaError_t launch_prim(const LaunchCtx &lc, const DevMat *hmats, int op, int mi
         if (blocks > need) blocks = (int)need;
         prim_svc_kernel<<<blocks, SVC_WARPS * 32, svc_smem(hmats[mid]), lc.stream>>>(op, mid, n, sig, epl, deps, ld, out);
     } else if (hmats[mid].kind == PLF_MAT_BARLAT) {
-        prim_barlat_kernel<<<(unsigned)((n + 127) / 128), 128, 0, lc.stream>>>(op, mid, n, sig, epl, deps, out);
+        prim_model_kernel<BarlatModel><<<(unsigned)((n + 127) / 128), 128, 0, lc.stream>>>(op, mid, n, sig, epl, deps, out);
+    } else if (hmats[mid].kind == PLF_MAT_HILL3) {
+        prim_model_kernel<HillPrincModel><<<(unsigned)((n + 127) / 128), 128, 0, lc.stream>>>(op, mid, n, sig, epl, deps, out);
     } else {
         prim_hill_kernel<<<(unsigned)((n + 127) / 128), 128, 0, lc.stream>>>(op, mid, n, sig, epl, deps, out);
     }

@@ -7,7 +7,7 @@ C-ABI (include/plfb200.h).  There is no CPU path: without libplfb200.so and a CU
 Scope: sdim = 6 materials -- J2 / Hill-6p with linear isotropic hardening and Drucker / LHS
 terms, the RBF-SVC machine-learned yield function (parameters adopted from a trained scikit-learn SVC or from a
 reference Material object), Barlat Yld2004-18p equivalent stress.  Training (train_SVC and friends), plotting and
-the sdim = 3 principal-stress formulation stay with the reference package.
+the ML variant of the sdim = 3 principal-stress formulation stay with the reference package.
 """
 import warnings
 
@@ -294,11 +294,11 @@ class Material(object):
             d.kind = _lib.MAT_ELASTIC
             d.hill[:] = [1.] * 6
         else:
-            if self.sdim != 6:
-                raise NotImplementedError('Material %s: sdim = 3 (principal-stress formulation) is not supported on the '
-                                          'device path; use sdim = 6' % self.name)
+            if self.sdim != 6 and (self.ML_yf or self.barlat):
+                raise NotImplementedError('Material %s: sdim = 3 is supported for the analytic Hill-3p / J2 / Tresca '
+                                          'formulation only (no ML or Barlat yield function)' % self.name)
             d.sy, d.khard = float(self.sy), float(self.khard)
-            d.hill[:] = [float(x) for x in self.hill]
+            d.hill[:] = ([float(x) for x in self.hill] + [1., 1., 1.])[:6]
             d.tresca = int(bool(self.tresca))
             if self.lhs is not None:
                 d.lhs = 1
@@ -321,9 +321,9 @@ class Material(object):
                 d.barlat_m2[:] = list(np.asarray(self.Bar_m2, float).ravel())
                 d.barlat_exp = float(self.barlat_exp)
             else:
-                if self.tresca:
-                    raise NotImplementedError('Tresca equivalent stress is not supported on the device path')
-                d.kind = _lib.MAT_HILL
+                # Tresca: d.tresca switches calc_seq to max - min principal stress.  sdim = 3: equivalent stress and
+                # gradient on the ordered principal stresses (material.py:663-673, 1045-1048)
+                d.kind = _lib.MAT_HILL if self.sdim == 6 else _lib.MAT_HILL3
         d._keep = keep
         return d
 
@@ -332,13 +332,16 @@ class Material(object):
         ctx.set_materials([self._descriptor(CV)], planestress=False)
         return ctx
 
-    @staticmethod
-    def _as_rows(sig, what):
+    def _as_rows(self, sig, what):
         a = np.asarray(sig, dtype=float)
         if a.ndim == 1 and a.shape[0] == 6:
             return a[None, :], True
         if a.ndim == 2 and a.shape[1] == 6:
             return a, False
+        if self.sdim == 3 and a.shape[-1] == 3 and a.ndim in (1, 2):
+            # principal stresses (material.py:609-614): the Voigt vector [sp, 0, 0, 0]
+            rows = np.atleast_2d(a)
+            return np.ascontiguousarray(np.concatenate([rows, np.zeros_like(rows)], axis=1)), a.ndim == 1
         raise TypeError('Unknown format of stress in %s (device path needs (6,) or (N,6) Voigt stresses)' % what)
 
     def _epl_rows(self, epl, n):
@@ -348,6 +351,8 @@ class Material(object):
             # calc_yf: a PEEQ is converted into a plastic strain tensor (material.py:381-383)
             return np.broadcast_to(float(epl) * np.array([1., -0.5, -0.5, 0., 0., 0.]), (n, 6))
         e = np.asarray(epl, dtype=float)
+        if e.shape[-1] == 3:   # sdim = 3: principal plastic strains
+            e = np.concatenate([np.atleast_2d(e), np.zeros_like(np.atleast_2d(e))], axis=1)
         return np.broadcast_to(e, (n, 6))
 
     # ------------------------------------------------------------------------------------------------------
@@ -357,7 +362,8 @@ class Material(object):
         """Equivalent stress, (6,) -> float or (N,6) -> (N,) (material.py:576-676; Barlat 678-702)."""
         a, single = self._as_rows(sig, 'calc_seq')
         out = self._bind().calc_seq(0, a)
-        self.msg['equiv'] = 'Barlat Yld2004-18p' if self.barlat else '6-parameter Hill, full Voigt stress'
+        self.msg['equiv'] = ('Barlat Yld2004-18p' if self.barlat else
+                             '6-parameter Hill, full Voigt stress' if self.sdim == 6 else '3-parameter Hill')
         return float(out[0]) if single else out
 
     def get_sflow(self, epl):
@@ -397,7 +403,12 @@ class Material(object):
         a, single = self._as_rows(sig, 'calc_fgrad')
         if epl is not None and np.shape(epl) != np.shape(sig):
             raise ValueError('Parameter sig and epl must have the same shape.')
+        if self.sdim == 3 and np.shape(sig)[-1] != 3:
+            raise NotImplementedError('calc_fgrad of an sdim = 3 material takes principal stresses, shape (3,) or (N,3) '
+                                      '(what epl_dot / C_tan pass, material.py:1045-1048)')
         out = self._bind().calc_fgrad(0, a, self._epl_rows(epl, len(a)))
+        if self.sdim == 3:
+            out = out[:, 0:3]
         if self.ML_yf:
             self.khard = 0.
             self.msg['gradient'] = 'gradient to ML_yf'

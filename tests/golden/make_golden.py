@@ -595,10 +595,107 @@ def gen_mlparam():
     print(f'mlparam_hill-svm.csv / -svm_meta.json / mlparam_hill.npz  nsv={len(out["dual"])}  {time.time() - t0:.1f}s')
 
 
+def gen_tresca():
+    """Tresca equivalent stress / yield function of the reference (material.py:630-632) on random Voigt stresses."""
+    m = FE.Material('Tresca')
+    m.elasticity(E=200.e3, nu=0.3)
+    m.plasticity(sy=150., khard=200., tresca=True, sdim=6)
+    rng = np.random.default_rng(21)
+    sig = rng.standard_normal((300, 6)) * 90.
+    sig[::6, 3:6] = 0.
+    epl = np.zeros((300, 6))
+    epl[::2] = rng.uniform(0., 0.02, (150, 1)) * np.array([1., -.5, -.5, 0., 0., 0.])
+    seq = m.calc_seq(sig)
+    yf = np.array([m.calc_yf(sig[i], epl=epl[i]) for i in range(300)])
+    raised = False
+    try:
+        m.calc_fgrad(sig[0])
+    except ValueError:
+        raised = True
+    np.savez_compressed(os.path.join(HERE, 'tresca.npz'), sig=sig, epl=epl, seq=seq, yf=yf, sy=150., khard=200., E=200.e3, nu=0.3,
+                        CV=np.array(m.CV), fgrad_raises=raised)
+    print('tresca.npz', seq[:3], 'calc_fgrad raises:', raised)
+
+
+def gen_sdim3():
+    """sdim = 3 principal-stress formulation (material.py:663-673, 836-838, 1045-1048, 1078-1080): Material.response /
+    calc_seq / calc_yf / epl_dot / C_tan of the reference for J2 and 3-parameter Hill materials on states whose
+    principal axes are the coordinate axes (no shear: what the reference's own sdim = 3 tests produce), and the two
+    reference test models that use sdim = 3 (tests/test_basic.py:107-125)."""
+    t0 = time.time()
+    for name, hill, khard in (('j2s3', None, 500.), ('hill3', [0.7, 1., 1.4], 100.)):
+        m = FE.Material(name=name)
+        m.elasticity(E=200.e3, nu=0.3)
+        m.plasticity(sy=150., hill=hill, khard=khard, sdim=3)
+        out = dict(E=200.e3, nu=0.3, sy=150., khard=khard, hill=np.array(m.hill, dtype=float), drucker=0., mat_CV=np.array(m.CV))
+        for planar, tag in [(False, 'pe'), (True, 'ps')]:
+            rng = np.random.default_rng(77 + planar)
+            n = 160
+            CV = cv_plane_stress(m) if planar else np.array(m.CV)
+            sig = np.zeros((n, 6)); epl = np.zeros((n, 6)); deps = np.zeros((n, 6))
+            for i in range(n):
+                if i % 3 == 1:
+                    epl[i] = rng.uniform(0., 0.02) * np.array([1., -.5, -.5, 0., 0., 0.])
+                elif i % 3 == 2:
+                    e = rng.standard_normal(3) * 0.005
+                    epl[i, 0:3] = e - e.mean()
+                d = np.zeros(6)
+                d[0:3] = rng.standard_normal(3)
+                if planar:
+                    d[2] = 0.
+                sflow = m.get_sflow(epl[i])
+                u = rng.uniform()
+                r = rng.uniform(0., 0.9) if u < 0.35 else (rng.uniform(0.9, 1.0) if u < 0.7 else rng.uniform(0.996, 1.004))
+                sig[i] = d / m.calc_seq(d) * r * sflow
+                de = np.zeros(6)
+                de[0:3] = rng.standard_normal(3)
+                if planar:
+                    de[2] = 0.
+                if i % 7 == 0:
+                    de = np.linalg.lstsq(m.CV, sig[i] + 1e-3 * de, rcond=None)[0]
+                    de[3:6] = 0.
+                    if planar:
+                        de[2] = 0.
+                deps[i] = de / FE.eps_eq(de) * [5.e-4, 5.e-4, 2.e-3, 1.e-2, 1.e-4][i % 5]
+            fy = np.zeros(n); so = np.zeros((n, 6)); dp = np.zeros((n, 6)); ct = np.zeros((n, 6, 6)); ns = np.zeros(n, dtype=np.int32)
+            seq = np.zeros(n); yf = np.zeros(n); fg = np.zeros((n, 3)); ed = np.zeros((n, 6)); ctan = np.zeros((n, 6, 6))
+            for i in range(n):
+                m.msg['nsteps'] = -1
+                fy[i], so[i], dp[i], ct[i] = m.response(sig[i], epl[i], deps[i], CV)
+                ns[i] = m.msg['nsteps']
+                seq[i] = m.calc_seq(sig[i])
+                yf[i] = m.calc_yf(sig[i], epl=epl[i])
+                fg[i] = m.calc_fgrad(FE.sig_princ(sig[i])[0], epl=epl[i, 0:3])
+                ed[i] = m.epl_dot(sig[i], epl[i], CV, deps[i])
+                ctan[i] = m.C_tan(sig[i], CV, epl=epl[i])
+            out.update({f'{tag}_CV': CV, f'{tag}_sig': sig, f'{tag}_epl': epl, f'{tag}_deps': deps, f'{tag}_fy': fy,
+                        f'{tag}_sig_out': so, f'{tag}_depl': dp, f'{tag}_ctan': ct, f'{tag}_nsteps': ns, f'{tag}_seq': seq,
+                        f'{tag}_yf': yf, f'{tag}_fgrad3': fg, f'{tag}_epl_dot': ed, f'{tag}_C_tan': ctan})
+            el = np.sum((ns == 0) & (np.abs(ct - CV).max(axis=(1, 2)) == 0))
+            print(f'  {name}/{tag}: elastic {el}, 50-step {np.sum(ns == 49)}, other {n - el - np.sum(ns == 49)}')
+        np.savez_compressed(os.path.join(HERE, f'response_{name}.npz'), **out)
+    # tests/test_basic.py:107-121: two sections (elastic | J2 sdim = 3), 4 x 4 plane strain, 10 % strain
+    mat1 = FE.Material()
+    mat1.elasticity(E=100.e3, nu=0.35)
+    mat2 = FE.Material()
+    mat2.elasticity(E=300.e3, nu=0.3)
+    mat2.plasticity(sy=150., khard=500., sdim=3)
+    fem2 = FE.Model(dim=2, planestress=False)
+    fem2.geom([2, 2], LY=4.)
+    fem2.assign([mat1, mat2])
+    fem2.bcleft(0.)
+    fem2.bcbot(0.)
+    fem2.bcright(0., 'force')
+    fem2.bctop(0.1 * fem2.leny, 'disp')
+    fem2.mesh(NX=4, NY=4)
+    solve_case('fem2_sdim3', fem2)
+    print(f'sdim3 fixtures {time.time() - t0:.1f}s; fem2 glob epl[1] = {fem2.glob["epl"][1]} (tests/test_basic.py:17: 0.04966042764325635)')
+
+
 if __name__ == '__main__':
     what = sys.argv[1:] or ['all']
     if 'all' in what:
-        what = ['response', 'kmat', 'solve', 'svc', 'barlat', 'barlat_response', 'barlat_solve', 'mlparam']
+        what = ['response', 'kmat', 'solve', 'svc', 'barlat', 'barlat_response', 'barlat_solve', 'mlparam', 'tresca', 'sdim3']
     for w in what:
         print('==', w)
         globals()['gen_' + w]()

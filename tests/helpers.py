@@ -31,7 +31,7 @@ def plf_material_from_golden(g):
     if 'sy' in g:
         m.kind = _lib.MAT_HILL
         m.sy, m.khard = float(g['sy']), float(g['khard'])
-        m.hill[:] = list(np.asarray(g['hill'], float))
+        m.hill[:] = (list(np.asarray(g['hill'], float)) + [1., 1., 1.])[:6]   # sdim = 3 fixtures carry 3 parameters
         m.d[:] = [float(g['drucker'])] * 3
     else:
         m.kind = _lib.MAT_ELASTIC

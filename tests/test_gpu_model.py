@@ -362,3 +362,60 @@ def test_from_MLparam_yield_function_matches_reference(golden):
     m = FE.Material.from_MLparam('mlparam_hill', path=here + os.sep)
     yf = m.calc_yf(g['yf_sig'])
     assert np.max(np.abs(yf - g['yf'])) < 1e-10
+
+
+def test_tresca_seq_yf_and_missing_gradient(golden):
+    """Tresca material (material.py:630-632): calc_seq / calc_yf match the reference; calc_fgrad and response raise
+    ValueError like the reference does at 824-825."""
+    g = golden('tresca')
+    m = FE.Material('Tresca')
+    m.elasticity(E=float(g['E']), nu=float(g['nu']))
+    m.plasticity(sy=float(g['sy']), khard=float(g['khard']), tresca=True, sdim=6)
+    assert relmax(m.calc_seq(g['sig']), g['seq']) < 1e-12
+    yf = np.array([m.calc_yf(g['sig'][i], epl=g['epl'][i]) for i in range(0, 300, 7)])
+    assert np.max(np.abs(yf - g['yf'][::7])) < 1e-10
+    assert bool(g['fgrad_raises'])
+    with pytest.raises(ValueError):
+        m.calc_fgrad(g['sig'][0])
+    with pytest.raises(ValueError):
+        m.response(g['sig'][0], g['epl'][0], np.full(6, 1e-3), g['CV'])
+
+
+def test_reference_fem2_sdim3_golden(golden):
+    """/root/reference/tests/test_basic.py:107-121 + :17 (test_model, fem2): two sections (elastic | J2 with sdim = 3),
+    4 x 4 plane strain, 10 % strain.  Same increments and passes as the reference run; golden scalar of the reference test."""
+    g = golden('solve_fem2_sdim3')
+    mat1 = FE.Material()
+    mat1.elasticity(E=100.e3, nu=0.35)
+    mat2 = FE.Material()
+    mat2.elasticity(E=300.e3, nu=0.3)
+    mat2.plasticity(sy=150., khard=500., sdim=3)
+    fem2 = FE.Model(dim=2, planestress=False)
+    fem2.geom([2, 2], LY=4.)
+    fem2.assign([mat1, mat2])
+    fem2.bcleft(0.)
+    fem2.bcbot(0.)
+    fem2.bcright(0., 'force')
+    fem2.bctop(0.1 * fem2.leny, 'disp')
+    fem2.mesh(NX=4, NY=4)
+    fem2.solve()
+    fem2.calc_global()
+    assert fem2.nsteps == int(g['nsteps']) and list(fem2.niter) == list(g['niter'])
+    compare_solution(fem2, g, 1e-6, 1e-6)
+    assert abs(fem2.glob['sig'][1] - fem2.glob['sbc2']) < 1e-5
+    assert abs(fem2.glob['eps'][1] - fem2.glob['ebc2']) < 1e-5
+    assert abs(fem2.glob['epl'][1] - 0.04966042764325635) < 1e-5
+
+
+def test_calc_properties_hill3p_sdim3_golden():
+    """/root/reference/tests/test_basic.py:19-26, 124-125 (test_plasticity): 3-parameter Hill with sdim = 3."""
+    mat2 = FE.Material()
+    mat2.elasticity(E=300.e3, nu=0.3)
+    mat2.plasticity(sy=150., hill=[0.7, 1., 1.4], khard=100., sdim=3)
+    mat2.calc_properties(eps=0.05)
+    assert abs(mat2.propJ2['stx']['ys'] - 146.38501094227996) < 1e-5
+    assert abs(mat2.propJ2['sty']['seq'][-1] - 168.5141123395444) < 1e-5
+    assert abs(mat2.propJ2['sty']['peeq'][-1] - 0.04969421741530513) < 1e-5
+    assert abs(mat2.propJ2['et2']['ys'] - 136.93063937629154) < 1e-5
+    assert abs(mat2.propJ2['ect']['peeq'][-1] - 0.04570405456408677) < 1e-5
+    assert abs(mat2.propJ2['ect']['seq'][-1] - 168.3199594723871) < 1e-5

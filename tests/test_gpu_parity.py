@@ -426,3 +426,23 @@ def test_strip_sharded_K_rows_equal_global_K(ctx, golden, world):
                     assert np.array_equal(col_g[rp_g[rg]:rp_g[rg + 1]] - 2 * first * (NY + 1), col[rp[rl]:rp[rl + 1]])
                     seen += 1
     assert seen == 2 * (NX + 1) * (NY + 1)
+
+
+@pytest.mark.parametrize('tag', ['pe', 'ps'])
+@pytest.mark.parametrize('name', ['j2s3', 'hill3'])
+def test_sdim3_response_vs_reference_golden(ctx, golden, name, tag):
+    """sdim = 3 principal-stress formulation (HillPrincModel) against reference outputs on axis-aligned states."""
+    from pylabfea_b200 import _lib
+    g = golden('response_' + name)
+    m = plf_material_from_golden(g)
+    m.kind = _lib.MAT_HILL3
+    ctx.set_materials([m], planestress=(tag == 'ps'))
+    assert np.array_equal(ctx.element_CV(0), g[tag + '_CV'])
+    sig, epl, deps = g[tag + '_sig'], g[tag + '_epl'], g[tag + '_deps']
+    assert relmax(ctx.calc_seq(0, sig), g[tag + '_seq']) < 1e-12
+    assert np.max(np.abs(ctx.calc_yf(0, sig, epl) - g[tag + '_yf'])) < 1e-10
+    fg = ctx.calc_fgrad(0, sig, epl)
+    assert relmax(fg[:, 0:3], g[tag + '_fgrad3']) < 1e-11 and np.all(fg[:, 3:6] == 0.)
+    assert relmax(ctx.epl_dot(0, sig, epl, deps), g[tag + '_epl_dot']) < 1e-10
+    assert relmax(ctx.C_tan(0, sig, epl), g[tag + '_C_tan']) < 1e-11
+    check_response(ctx.response_batch(sig, epl, deps), g, tag, float(g['sy']))

@@ -78,8 +78,9 @@ def test_plasticity_setter_matches_reference(golden):
         m.plasticity(sy=1., sdim=4)
     m.plasticity(sy=100., hill=[0.7, 1., 1.4], sdim=3)
     assert m.hill_3p and not m.hill_6p
-    with pytest.raises(NotImplementedError):
-        m._descriptor()     # sdim = 3 is outside the device path
+    from pylabfea_b200 import _lib
+    d = m._descriptor()     # sdim = 3: the principal-stress formulation has its own material kind
+    assert d.kind == _lib.MAT_HILL3 and list(d.hill) == [0.7, 1., 1.4, 1., 1., 1.]
 
 
 def test_stiffness_csr_wrapper():
