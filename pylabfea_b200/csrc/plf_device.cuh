@@ -119,7 +119,7 @@ __device__ __forceinline__ double j2_seq(const double *s)
     return sqrt(0.5 * I2);
 }
 
-__device__ inline double barlat_seq(const DevMat &m, const double *sv)
+static __device__ __noinline__ double barlat_seq(const DevMat &m, const double *sv)
 {
     // material.py:678-702
     double p = (sv[0] + sv[1] + sv[2]) / 3.;
@@ -176,7 +176,7 @@ __device__ inline void sym3_eigv(const double *v, double *w, double V[3][3])
 // with d(lambda_e) / d(Voigt k) = (v1^2, v2^2, v3^2, 2 v2 v3, 2 v1 v3, 2 v1 v2) of eigenvector e (phi is a symmetric
 // function of the eigenvalues, so any orthonormal eigenbasis gives the gradient, also for repeated eigenvalues).
 // Returns seq.
-__device__ inline double barlat_seq_grad(const DevMat &m, const double *sv, double *g)
+static __device__ __noinline__ double barlat_seq_grad(const DevMat &m, const double *sv, double *g)
 {
     const double p = (sv[0] + sv[1] + sv[2]) / 3.;
     const double sd[6] = {sv[0] - p, sv[1] - p, sv[2] - p, sv[3], sv[4], sv[5]};
@@ -251,10 +251,10 @@ struct HillModel {
 // the eigenvalues that numpy.linalg.eig returns by "major force axes": iev[i] = index of the eigenvector with the largest
 // component along coordinate axis i, then the AXIS indices i are listed by ascending iev and used to index the
 // eigenvalues (basic.py:156-170).  Here the eigen-decomposition is cyclic Jacobi, whose natural order keeps eigenvalue e
-// with diagonal entry e; for stresses whose principal axes are close to the coordinate axes (every state of the
+// with diagonal entry e (out of line: response_core calls it from a dozen sites); for stresses whose principal axes are close to the coordinate axes (every state of the
 // reference's own sdim = 3 tests) both give sp = (s11, s22, s33)-like ordering.  For strongly rotated states the
 // reference's result depends on LAPACK's eigenvalue order and is not reproduced bit for bit.
-__device__ inline void princ_ordered(const double *s, double *sp)
+static __device__ __noinline__ void princ_ordered(const double *s, double *sp)
 {
     double w[3], V[3][3];
     sym3_eigv(s, w, V);

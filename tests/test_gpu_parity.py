@@ -446,3 +446,27 @@ def test_sdim3_response_vs_reference_golden(ctx, golden, name, tag):
     assert relmax(ctx.epl_dot(0, sig, epl, deps), g[tag + '_epl_dot']) < 1e-10
     assert relmax(ctx.C_tan(0, sig, epl), g[tag + '_C_tan']) < 1e-11
     check_response(ctx.response_batch(sig, epl, deps), g, tag, float(g['sy']))
+
+
+def test_sdim3_j2_equals_sdim6_j2_on_axis_aligned_states(ctx, golden):
+    """For J2 and stresses without shear the sdim = 3 formulation is mathematically the sdim = 6 one; 20 000 random
+    axis-aligned tuples through both kernel families must agree to rounding (also a guard for the code generation of
+    the large eigen-decomposition kernels)."""
+    from pylabfea_b200 import _lib
+    g = golden('response_j2s3')
+    rng = np.random.default_rng(99)
+    n = 20000
+    src = rng.integers(0, len(g['pe_sig']), n)
+    sig = g['pe_sig'][src] * rng.uniform(0.8, 1.05, (n, 1))
+    epl = g['pe_epl'][src]
+    deps = g['pe_deps'][rng.integers(0, len(g['pe_sig']), n)] * rng.uniform(0.2, 1.5, (n, 1))
+    outs = []
+    for kind in (_lib.MAT_HILL3, _lib.MAT_HILL):
+        m = plf_material_from_golden(g)
+        m.kind = kind
+        ctx.set_materials([m], planestress=False)
+        outs.append(ctx.response_batch(sig, epl, deps))
+    assert np.array_equal(outs[0][4], outs[1][4])
+    assert int(np.sum(outs[0][4] == 49)) > 2000
+    for a, b in zip(outs[0][:4], outs[1][:4]):
+        assert np.max(np.abs(a - b)) <= 1e-9 * np.max(np.abs(b))
