@@ -835,6 +835,42 @@ cudaError_t launch_scf(const LaunchCtx &lc, const DevMat *hmats, int nmat, int64
 // run for a few microseconds each) and replayed; the host only reads the residual after every chunk.  Iterations
 // after convergence inside a chunk are frozen on the device (alpha = beta = 0), so the result does not depend on
 // the chunk length.
+// warm start: x0 = previous solution on the free dofs (0 on the fixed ones)
+__global__ void __launch_bounds__(256) cg_mask_x_kernel(int64_t n, double *__restrict__ x, const unsigned char *__restrict__ fixed)
+{
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+        if (fixed[i] || !isfinite(x[i])) x[i] = 0.;
+}
+
+// warm start: r = b - A x0 (q holds the masked product A x0), z = r / diag, p = z; r.z -> rz[0], r.r -> rr;
+// the convergence target stays relative to |b|: target = rtol^2 b.b
+__global__ void __launch_bounds__(256) cg_init_warm_kernel(int64_t n, const double *__restrict__ b, const double *__restrict__ q,
+                                                           double *__restrict__ r, double *__restrict__ z, double *__restrict__ p,
+                                                           const double *__restrict__ diag, const unsigned char *__restrict__ fixed,
+                                                           CgScalars *sc, double rtol, double *partial, unsigned int *counter)
+{
+    double v[3] = {0., 0., 0.};
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const double bi = fixed[i] ? 0. : b[i];
+        const double ri = fixed[i] ? 0. : bi - q[i];
+        const double zi = fixed[i] ? 0. : ri / diag[i];
+        r[i] = ri; z[i] = zi; p[i] = zi;
+        v[0] += ri * zi;
+        v[1] += ri * ri;
+        v[2] += bi * bi;
+    }
+    __shared__ double s_out[3];
+    if (block_reduce_to_partials<3>(v, partial, counter, s_out, 0)) {
+        sc->rz[0] = s_out[0];
+        sc->rz[1] = 0.;
+        sc->rr = s_out[1];
+        sc->tmp[1] = s_out[2];   // b.b, read by the host as the reference norm
+        sc->target = rtol * rtol * s_out[2];
+        sc->iters = 0.;
+        sc->pq = 0.;
+    }
+}
+
 struct CgGraphCache {
     cudaGraphExec_t exec = nullptr;
     int64_t n = 0;
@@ -848,7 +884,7 @@ static CgGraphCache g_cg;
 cudaError_t launch_cg(const LaunchCtx &lc, int64_t n, const int32_t *rowptr, const int32_t *col, const double *val,
                       const unsigned char *fixed, const double *b, double *x, double *r, double *z, double *p, double *q,
                       double *diag, double *partial, unsigned int *counter, void *d_sc, void *h_sc, double rtol, int max_iter,
-                      int check_every, int *iters, double *relres, int64_t *launches, MgHierarchy *mg)
+                      int check_every, int *iters, double *relres, int64_t *launches, MgHierarchy *mg, int warm)
 {
     CgScalars *sc = (CgScalars *)d_sc;
     CgScalars *hs = (CgScalars *)h_sc;
@@ -857,8 +893,16 @@ cudaError_t launch_cg(const LaunchCtx &lc, int64_t n, const int32_t *rowptr, con
     cudaError_t e;
     check_every = std::max(2, check_every & ~1);   // even: the rz ping-pong returns to parity 0 at chunk end
     diag_kernel<<<(unsigned)((n + 255) / 256), 256, 0, lc.stream>>>(n, rowptr, col, val, diag);
-    cg_init_kernel<<<vg, 256, 0, lc.stream>>>(n, b, x, r, z, p, diag, fixed, sc, rtol, partial, counter);
-    *launches += 2;
+    if (warm) {
+        // x keeps the previous solution (the Newton-like passes of an increment solve nearly the same system again)
+        cg_mask_x_kernel<<<vg, 256, 0, lc.stream>>>(n, x, fixed);
+        spmv_kernel<<<sg, 256, 0, lc.stream>>>(n, rowptr, col, val, x, nullptr, q, fixed, 0, nullptr, nullptr, nullptr);
+        cg_init_warm_kernel<<<vg, 256, 0, lc.stream>>>(n, b, q, r, z, p, diag, fixed, sc, rtol, partial, counter);
+        *launches += 4;
+    } else {
+        cg_init_kernel<<<vg, 256, 0, lc.stream>>>(n, b, x, r, z, p, diag, fixed, sc, rtol, partial, counter);
+        *launches += 2;
+    }
     if (mg) {
         // z = V(r), r.z, p = z with the multigrid preconditioner (the Jacobi z / p / r.z of cg_init_kernel are replaced)
         if ((e = mg_setup(lc, *mg, val, fixed, launches)) != cudaSuccess) return e;
@@ -869,11 +913,18 @@ cudaError_t launch_cg(const LaunchCtx &lc, int64_t n, const int32_t *rowptr, con
     }
     if ((e = cudaMemcpyAsync(hs, sc, sizeof(CgScalars), cudaMemcpyDeviceToHost, lc.stream)) != cudaSuccess) return e;
     if ((e = cudaStreamSynchronize(lc.stream)) != cudaSuccess) return e;
-    const double bb = hs->rr;
+    const double bb = warm ? hs->tmp[1] : hs->rr;   // |b|^2: the residual norm is reported relative to it
     *iters = 0;
     *relres = 0.;
-    if (bb == 0.) return cudaSuccess;
+    if (bb == 0.) {
+        if (warm) cudaMemsetAsync(x, 0, (size_t)n * sizeof(double), lc.stream);   // b = 0: the solution is 0
+        return cudaSuccess;
+    }
     const double target = hs->target;
+    if (warm && !(hs->rr > target)) {   // the previous solution already satisfies the tolerance
+        *relres = sqrt(hs->rr / bb);
+        return cudaSuccess;
+    }
 
     int64_t chunk_launches = 0;
     auto enqueue_chunk = [&]() {

@@ -396,6 +396,7 @@ extern "C" int plf_set_option(plf_ctx *ctx, const char *key, int value)
     if (!strcmp(key, "max_fm")) { ctx->max_fm = value; return PLF_OK; }
     if (!strcmp(key, "k1_only")) { ctx->k1_only = value; return PLF_OK; }
     if (!strcmp(key, "solver_mg")) { ctx->solver_mg = value; return PLF_OK; }
+    if (!strcmp(key, "solver_warm")) { ctx->solver_warm = value; return PLF_OK; }
     if (!strcmp(key, "mg_nu") || !strcmp(key, "mg_coarse_sweeps") || !strcmp(key, "mg_omega_permille")) {
         // multigrid tuning knobs (take effect at the next plf_mesh_structured / solve; the CG graph is rebuilt)
         if (!strcmp(key, "mg_nu")) ctx->mg_nu = value & ~1;

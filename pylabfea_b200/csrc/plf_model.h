@@ -75,6 +75,7 @@ struct plf_ctx {
     unsigned char *d_fixed = nullptr;
     plf::MgHierarchy *mg = nullptr;   // multigrid preconditioner of plf_solve_linear (built with the mesh)
     int solver_mg = 1;                // 1: V-cycle preconditioner when the mesh coarsens at least once, 0: Jacobi
+    int solver_warm = 1;              // CG starts from the previous du (0: from zero)
     int mg_nu = 2, mg_coarse_sweeps = 10;   // smoothing sweeps per level (even) / on the coarsest level
     double mg_omega = 0.7;            // Jacobi damping
     double *d_partial = nullptr;   // block partial sums
