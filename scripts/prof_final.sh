@@ -9,3 +9,4 @@ timeout 600 python bench.py --steps 200 --warmup 5 > gpurun_out/${TAG}_bench.jso
 timeout 600 python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/${TAG}_bench_reference.json 2>> gpurun_out/${TAG}_bench.err
 tail -c 900 gpurun_out/${TAG}_bench.json
 timeout 300 python __graft_entry__.py smoke 2>&1 | tail -1
+PLF_MG=1 timeout 900 python scripts/solve_demo.py 1024 5 0.004 2>&1 | grep -E "^N=|linear solves|increments|global|launches" > gpurun_out/${TAG}_solve_demo_1024.txt; cat gpurun_out/${TAG}_solve_demo_1024.txt | head -3
