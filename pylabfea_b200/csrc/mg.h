@@ -8,7 +8,7 @@ namespace plf {
 struct MgLevel {
     int NX = 0, NY = 0;
     int64_t ndof = 0, nnz = 0;
-    double *val = nullptr;            // level matrix in the closed-form CSR layout (level 0: the model's K, not owned)
+    float *val = nullptr;             // level matrix, FP32, closed-form CSR layout (level 0: converted copy of the model's K)
     unsigned char *mask = nullptr;    // 1 = Dirichlet dof (level 0: the solver's mask, not owned)
     double *dinv = nullptr;           // 1 / diag, 0 on masked rows
     double *x = nullptr, *b = nullptr, *r = nullptr, *t = nullptr;   // level 0: x and b are the caller's z and r

@@ -13,7 +13,10 @@
 //     when the coincident fine dof is (boundary edges coincide on all levels);
 //   * the smoother is damped Jacobi (symmetric, so the V-cycle with equal pre- and post-smoothing is an SPD
 //     preconditioner), the coarsest level does a fixed number of the same sweeps.
-// All kernels are one thread per row / dof, FP64, no atomics: the V-cycle is deterministic.
+//   * the level matrices are stored in FP32 (the finest one is a converted copy of the model's FP64 K, refreshed at
+//     every solve): the cycle is a preconditioner, its matrix traffic is what it costs, and CG's own residuals and
+//     products stay FP64; vectors and accumulations are FP64.
+// All kernels are one thread per row / dof, no atomics: the V-cycle is deterministic.
 #include <algorithm>
 #include <vector>
 
@@ -43,7 +46,7 @@ __device__ __forceinline__ RowGeom row_geom(int NX, int NY, int64_t row)
 }
 
 // y_row = sum_j A[row][j] x[j] over the stencil of the row (x holds zeros at masked dofs)
-__device__ __forceinline__ double stencil_row_dot(int NX, int NY, const RowGeom &g, const double *__restrict__ val,
+__device__ __forceinline__ double stencil_row_dot(int NX, int NY, const RowGeom &g, const float *__restrict__ val,
                                                   const double *__restrict__ x)
 {
     const int NnY = NY + 1;
@@ -56,10 +59,10 @@ __device__ __forceinline__ double stencil_row_dot(int NX, int NY, const RowGeom 
         for (int dk = -1; dk <= 1; dk++) {
             if (g.k + dk < 0 || g.k + dk > NY) continue;
             const int64_t m = (int64_t)(g.j + dj) * NnY + (g.k + dk);
-            const double2 a = __ldg(reinterpret_cast<const double2 *>(val + pos));
+            const float2 a = __ldg(reinterpret_cast<const float2 *>(val + pos));
             const double2 xv = __ldg(reinterpret_cast<const double2 *>(x + 2 * m));
-            s = fma(a.x, xv.x, s);
-            s = fma(a.y, xv.y, s);
+            s = fma((double)a.x, xv.x, s);
+            s = fma((double)a.y, xv.y, s);
             pos += 2;
         }
     }
@@ -83,7 +86,13 @@ __global__ void __launch_bounds__(256) mg_mask_inject_kernel(int NXc, int NYc, i
 }
 
 // 1 / diag per row (0 on masked rows)
-__global__ void __launch_bounds__(256) mg_dinv_kernel(int NX, int NY, const double *__restrict__ val,
+// FP32 copy of the model's K for the finest level
+__global__ void __launch_bounds__(256) mg_to_float_kernel(int64_t n, const double *__restrict__ a, float *__restrict__ b)
+{
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) b[i] = (float)a[i];
+}
+
+__global__ void __launch_bounds__(256) mg_dinv_kernel(int NX, int NY, const float *__restrict__ val,
                                                       const unsigned char *__restrict__ mask, double *__restrict__ dinv)
 {
     const int64_t row = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -95,15 +104,15 @@ __global__ void __launch_bounds__(256) mg_dinv_kernel(int NX, int NY, const doub
     int before = 0;
     if (g.j > 0) before += 1 + (g.k > 0) + (g.k < NY);
     if (g.k > 0) before += 1;
-    const double d = val[g.pos + 2 * before + g.c];
+    const double d = (double)val[g.pos + 2 * before + g.c];
     dinv[row] = d != 0. ? 1. / d : 0.;
 }
 
 // Galerkin coarse operator A_c = P^T A_f P for one coarse row per thread.  (a, b): offset of the fine row's node from
 // the coincident fine node (2J, 2K); (dj, dk): stencil offset of the fine column; the fine column at offset
 // o = a + dj from 2J belongs to coarse column J + o/2 (o even) or to J + (o-1)/2 and J + (o+1)/2 with weight 1/2 each.
-__global__ void __launch_bounds__(128) mg_rap_kernel(int NXc, int NYc, const double *__restrict__ val_f,
-                                                     const unsigned char *__restrict__ mask_f, double *__restrict__ val_c)
+__global__ void __launch_bounds__(128) mg_rap_kernel(int NXc, int NYc, const float *__restrict__ val_f,
+                                                     const unsigned char *__restrict__ mask_f, float *__restrict__ val_c)
 {
     const int64_t row = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int64_t nc = 2ll * (NXc + 1) * (NYc + 1);
@@ -136,10 +145,10 @@ __global__ void __launch_bounds__(128) mg_rap_kernel(int NXc, int NYc, const dou
                 for (int dk = -1; dk <= 1; dk++) {
                     if (fk + dk < 0 || fk + dk > NYf) continue;
                     const int64_t m = (int64_t)(fj + dj) * NnYf + (fk + dk);
-                    const double2 v = __ldg(reinterpret_cast<const double2 *>(val_f + pos));
+                    const float2 v = __ldg(reinterpret_cast<const float2 *>(val_f + pos));
                     pos += 2;
-                    const double vx = mask_f[2 * m] ? 0. : wi * v.x;
-                    const double vy = mask_f[2 * m + 1] ? 0. : wi * v.y;
+                    const double vx = mask_f[2 * m] ? 0. : wi * (double)v.x;
+                    const double vy = mask_f[2 * m + 1] ? 0. : wi * (double)v.y;
                     const int ox = a + dj, oy = b + dk;   // compile-time after unrolling: -2 .. 2
                     // x targets
                     const int x0 = (ox >= 0 ? ox : ox - 1) / 2;          // floor(ox / 2)
@@ -167,7 +176,7 @@ __global__ void __launch_bounds__(128) mg_rap_kernel(int NXc, int NYc, const dou
 #pragma unroll
         for (int dk = -1; dk <= 1; dk++) {
             if (K + dk < 0 || K + dk > NYc) continue;
-            *reinterpret_cast<double2 *>(val_c + pos) = make_double2(acc[dj + 1][dk + 1][0], acc[dj + 1][dk + 1][1]);
+            *reinterpret_cast<float2 *>(val_c + pos) = make_float2((float)acc[dj + 1][dk + 1][0], (float)acc[dj + 1][dk + 1][1]);
             pos += 2;
         }
     }
@@ -177,7 +186,7 @@ __global__ void __launch_bounds__(128) mg_rap_kernel(int NXc, int NYc, const dou
 // cycle kernels
 // ---------------------------------------------------------------------------------------------------------------
 // damped Jacobi sweep: xout = xin + omega D^-1 (b - A xin)   (first = 1: xin = 0, no matrix product)
-__global__ void __launch_bounds__(256) mg_jacobi_kernel(int NX, int NY, const double *__restrict__ val,
+__global__ void __launch_bounds__(256) mg_jacobi_kernel(int NX, int NY, const float *__restrict__ val,
                                                         const double *__restrict__ dinv, const double *__restrict__ b,
                                                         const double *__restrict__ xin, double *__restrict__ xout, double omega,
                                                         int first)
@@ -193,7 +202,7 @@ __global__ void __launch_bounds__(256) mg_jacobi_kernel(int NX, int NY, const do
 }
 
 // r = b - A x (0 on masked rows)
-__global__ void __launch_bounds__(256) mg_residual_kernel(int NX, int NY, const double *__restrict__ val,
+__global__ void __launch_bounds__(256) mg_residual_kernel(int NX, int NY, const float *__restrict__ val,
                                                           const unsigned char *__restrict__ mask, const double *__restrict__ b,
                                                           const double *__restrict__ x, double *__restrict__ r)
 {
@@ -263,7 +272,8 @@ void mg_free(MgHierarchy &H)
 {
     for (size_t l = 0; l < H.lv.size(); l++) {
         MgLevel &L = H.lv[l];
-        if (l > 0) { cudaFree(L.val); cudaFree(L.mask); cudaFree(L.x); cudaFree(L.b); }
+        cudaFree(L.val);
+        if (l > 0) { cudaFree(L.mask); cudaFree(L.x); cudaFree(L.b); }
         cudaFree(L.dinv); cudaFree(L.r); cudaFree(L.t);
     }
     H.lv.clear();
@@ -286,8 +296,8 @@ cudaError_t mg_build(MgHierarchy &H, int NX, int NY)
         MgLevel &L = H.lv[l];
         cudaError_t e;
         const size_t nb = (size_t)L.ndof * sizeof(double);
+        if ((e = cudaMalloc((void **)&L.val, (size_t)L.nnz * sizeof(float))) != cudaSuccess) return e;
         if (l > 0) {
-            if ((e = cudaMalloc((void **)&L.val, (size_t)L.nnz * sizeof(double))) != cudaSuccess) return e;
             if ((e = cudaMalloc((void **)&L.mask, (size_t)L.ndof)) != cudaSuccess) return e;
             if ((e = cudaMalloc((void **)&L.x, nb)) != cudaSuccess) return e;
             if ((e = cudaMalloc((void **)&L.b, nb)) != cudaSuccess) return e;
@@ -303,7 +313,8 @@ cudaError_t mg_build(MgHierarchy &H, int NX, int NY)
 cudaError_t mg_setup(const LaunchCtx &lc, MgHierarchy &H, const double *val_fine, const unsigned char *mask_fine, int64_t *launches)
 {
     if (H.lv.empty()) return cudaErrorInvalidValue;
-    H.lv[0].val = const_cast<double *>(val_fine);
+    mg_to_float_kernel<<<std::min<unsigned>(grid_for(H.lv[0].nnz, 256), 148u * 16u), 256, 0, lc.stream>>>(H.lv[0].nnz, val_fine, H.lv[0].val);
+    (*launches)++;
     H.lv[0].mask = const_cast<unsigned char *>(mask_fine);
     for (size_t l = 0; l < H.lv.size(); l++) {
         MgLevel &L = H.lv[l];
