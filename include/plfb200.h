@@ -189,12 +189,14 @@ int plf_reduce_global(plf_ctx *ctx, double *sig6, double *eps6, double *epl6);
 int plf_calc_scf(plf_ctx *ctx, const double *sld, double *scf);
 
 /* ---- linear solve (model.py:1028-1033, 1070-1206, 1291, 1335) -------------------------------------------------- */
-/* Solve K[ind][:,ind] du[ind] = df[ind] on the device with Jacobi-preconditioned CG.
+/* Solve K[ind][:,ind] du[ind] = df[ind] on the device with preconditioned CG (geometric multigrid V-cycle; Jacobi for
+ * meshes that cannot be coarsened).
  *   fixed[Ndof]  : 1 where a displacement BC removed the dof from `ind`
  *   du_bc[Ndof]  : prescribed du on fixed dofs (0 elsewhere)                      -- calc_BC's du
  *   w[Ndof]      : sum of all BC values applied to a dof (what calc_BC multiplies K's columns with)
  *   f_ext[Ndof]  : force-type BC contributions (1145-1151, 1173-1179, 1203-1205)
- * df = f_ext - K w on the free dofs.  Result: Model.du on the device (PLF_DU).  rtol is on |r|/|b|. */
+ * df = f_ext - K w on the free dofs.  Result: Model.du on the device (PLF_DU).  rtol is on |r|/|b|.
+ * Passing NULL for all four vectors re-uses the ones of the previous call (same boundary conditions, new K). */
 int plf_solve_linear(plf_ctx *ctx, const uint8_t *fixed, const double *du_bc, const double *w, const double *f_ext,
                      double rtol, int max_iter, int *iters, double *relres);
 

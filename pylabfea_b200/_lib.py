@@ -355,8 +355,10 @@ class Context:
         return out.value
 
     def solve_linear(self, fixed, du_bc, w, f_ext, rtol=1e-12, max_iter=200000):
-        fixed = _arr(fixed, np.uint8)
-        du_bc, w, f_ext = _arr(du_bc), _arr(w), _arr(f_ext)
+        """fixed = du_bc = w = f_ext = None re-uses the boundary-condition vectors of the previous call."""
+        if fixed is not None:
+            fixed = _arr(fixed, np.uint8)
+            du_bc, w, f_ext = _arr(du_bc), _arr(w), _arr(f_ext)
         it, rr = C.c_int(), C.c_double()
         self._ck(self.L.plf_solve_linear(self.h, _ptr(fixed), _ptr(du_bc), _ptr(w), _ptr(f_ext), C.c_double(rtol),
                                          int(max_iter), C.byref(it), C.byref(rr)))

@@ -50,6 +50,8 @@ void model_free(plf_ctx *c)
     cudaFree(c->d_has_res); cudaFree(c->d_u); cudaFree(c->d_du); cudaFree(c->d_f); cudaFree(c->d_rowptr); cudaFree(c->d_col);
     cudaFree(c->d_val); cudaFree(c->d_worklist); cudaFree(c->d_r); cudaFree(c->d_z); cudaFree(c->d_p); cudaFree(c->d_q);
     cudaFree(c->d_b); cudaFree(c->d_diag); cudaFree(c->d_w); cudaFree(c->d_fixed); cudaFree(c->d_partial);
+    cudaFree(c->d_bc_du); cudaFree(c->d_bc_f);
+    c->d_bc_du = c->d_bc_f = nullptr; c->bc_valid = false;
     c->d_desc = nullptr; c->d_elstiff = c->d_sig = c->d_eps = c->d_epl = c->d_res_sig = c->d_res_depl = c->d_fyld = nullptr;
     c->d_nsteps = c->d_branch = nullptr; c->d_has_res = nullptr; c->d_u = c->d_du = c->d_f = nullptr;
     c->d_rowptr = c->d_col = nullptr; c->d_val = nullptr; c->d_worklist = nullptr;
@@ -507,7 +509,9 @@ extern "C" int plf_solve_linear(plf_ctx *ctx, const uint8_t *fixed, const double
                                 double rtol, int max_iter, int *iters, double *relres)
 {
     NEED_MESH("plf_solve_linear");
-    if (!fixed || !du_bc || !w || !f_ext) return fail(ctx, PLF_EINVAL, "plf_solve_linear: NULL argument");
+    const bool reuse = !fixed && !du_bc && !w && !f_ext;   // all NULL: the boundary-condition vectors of the previous call
+    if (!reuse && (!fixed || !du_bc || !w || !f_ext)) return fail(ctx, PLF_EINVAL, "plf_solve_linear: NULL argument");
+    if (reuse && !ctx->bc_valid) return fail(ctx, PLF_ESTATE, "plf_solve_linear: no boundary-condition vectors to re-use");
     if (!ctx->K_ready) return fail(ctx, PLF_ESTATE, "plf_solve_linear: call plf_setupK first");
     CK(cudaSetDevice(ctx->device));
     const size_t D = (size_t)ctx->Ndof;
@@ -515,19 +519,23 @@ extern "C" int plf_solve_linear(plf_ctx *ctx, const uint8_t *fixed, const double
     if (!ctx->d_r) {
         if ((rc = dalloc(ctx, &ctx->d_r, D)) || (rc = dalloc(ctx, &ctx->d_z, D)) || (rc = dalloc(ctx, &ctx->d_p, D)) ||
             (rc = dalloc(ctx, &ctx->d_q, D)) || (rc = dalloc(ctx, &ctx->d_b, D)) || (rc = dalloc(ctx, &ctx->d_diag, D)) ||
-            (rc = dalloc(ctx, &ctx->d_w, D)) || (rc = dalloc(ctx, &ctx->d_fixed, D)))
+            (rc = dalloc(ctx, &ctx->d_w, D)) || (rc = dalloc(ctx, &ctx->d_fixed, D)) || (rc = dalloc(ctx, &ctx->d_bc_du, D)) ||
+            (rc = dalloc(ctx, &ctx->d_bc_f, D)))
             return rc;
     }
     if ((rc = ensure_partials(ctx)) != PLF_OK) return rc;
     LaunchCtx lc{ctx->stream, ctx->sm_count};
-    CK(cudaMemcpyAsync(ctx->d_fixed, fixed, D, cudaMemcpyHostToDevice, ctx->stream));
-    CK(cudaMemcpyAsync(ctx->d_w, w, D * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
-    CK(cudaMemcpyAsync(ctx->d_q, f_ext, D * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
-    CK(cudaMemcpyAsync(ctx->d_z, du_bc, D * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    if (!reuse) {
+        // the BC vectors stay on the device (d_fixed, d_w, d_bc_f, d_bc_du): the Newton-like passes of an increment call
+        // again with the same boundary conditions and then skip these 4 host-to-device copies
+        CK(cudaMemcpyAsync(ctx->d_fixed, fixed, D, cudaMemcpyHostToDevice, ctx->stream));
+        CK(cudaMemcpyAsync(ctx->d_w, w, D * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+        CK(cudaMemcpyAsync(ctx->d_bc_f, f_ext, D * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+        CK(cudaMemcpyAsync(ctx->d_bc_du, du_bc, D * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+        ctx->bc_valid = true;
+    }
     // b = f_ext - K w on the free dofs (calc_BC, model.py:1099-1205)
-    CK(launch_spmv(lc, ctx->Ndof, ctx->d_rowptr, ctx->d_col, ctx->d_val, ctx->d_w, ctx->d_q, ctx->d_b, ctx->d_fixed, 2, &ctx->launches));
-    // du_bc is parked in d_w while CG runs (d_w is free after the rhs is built)
-    CK(cudaMemcpyAsync(ctx->d_w, ctx->d_z, D * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
+    CK(launch_spmv(lc, ctx->Ndof, ctx->d_rowptr, ctx->d_col, ctx->d_val, ctx->d_w, ctx->d_bc_f, ctx->d_b, ctx->d_fixed, 2, &ctx->launches));
     int it = 0;
     double rr = 0.;
     double *x = ctx->d_du;   // CG iterate lives in du; fixed dofs are merged at the end
@@ -536,7 +544,7 @@ extern "C" int plf_solve_linear(plf_ctx *ctx, const uint8_t *fixed, const double
     CK(launch_cg(lc, ctx->Ndof, ctx->d_rowptr, ctx->d_col, ctx->d_val, ctx->d_fixed, ctx->d_b, x, ctx->d_r, ctx->d_z, ctx->d_p, ctx->d_q,
                  ctx->d_diag, ctx->d_partial, counter_ptr(ctx), ctx->d_scalars + 256, ctx->h_scalars + 256, rtol, max_iter,
                  use_mg ? 4 : 50, &it, &rr, &ctx->launches, use_mg ? ctx->mg : nullptr, ctx->solver_warm));
-    CK(launch_merge_du(lc, ctx->Ndof, x, ctx->d_w, ctx->d_fixed, ctx->d_du, &ctx->launches));
+    CK(launch_merge_du(lc, ctx->Ndof, x, ctx->d_bc_du, ctx->d_fixed, ctx->d_du, &ctx->launches));
     CK(cudaStreamSynchronize(ctx->stream));
     if (iters) *iters = it;
     if (relres) *relres = rr;

@@ -73,6 +73,8 @@ struct plf_ctx {
     // solver work vectors
     double *d_r = nullptr, *d_z = nullptr, *d_p = nullptr, *d_q = nullptr, *d_b = nullptr, *d_diag = nullptr, *d_w = nullptr;
     unsigned char *d_fixed = nullptr;
+    double *d_bc_du = nullptr, *d_bc_f = nullptr;   // calc_BC's du and force vector of the last plf_solve_linear (d_w: its w)
+    bool bc_valid = false;
     plf::MgHierarchy *mg = nullptr;   // multigrid preconditioner of plf_solve_linear (built with the mesh)
     int solver_mg = 1;                // 1: V-cycle preconditioner when the mesh coarsens at least once, 0: Jacobi
     int solver_warm = 1;              // CG starts from the previous du (0: from zero)

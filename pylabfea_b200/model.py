@@ -165,6 +165,8 @@ class Model(object):
         self.solver_rtol = 1.e-13     # CG stops at |r| <= rtol |b|
         self.solver_maxit = 200000
         self.solver_stats = []        # (iterations, relative residual) of every linear solve
+        self._bc_key = None           # boundary values whose BC vectors are on the device (re-used by the next pass)
+        self._bc_epoch = 0
 
     # ------------------------------------------------------------------------------------------------------
     # pre-processing: geometry, materials, boundary conditions (host, O(1))
@@ -414,8 +416,16 @@ class Model(object):
         return fixed, du, w, fext
 
     def _solve_increment(self, bcl0, bcb0, dbcr, dbct, dbcn):
-        fixed, du, w, fext = self._calc_BC(bcl0, bcb0, dbcr, dbct, dbcn)
-        it, rr = self._dev().solve_linear(fixed, du, w, fext, rtol=self.solver_rtol, max_iter=self.solver_maxit)
+        # the inner passes of an increment usually repeat the boundary values of the previous pass: the BC vectors are
+        # then neither rebuilt on the host nor copied to the device again
+        key = (repr(np.asarray(bcl0).tolist()), repr(np.asarray(bcb0).tolist()), repr(np.asarray(dbcr).tolist()),
+               repr(np.asarray(dbct).tolist()), None if dbcn is None else repr(np.asarray(dbcn).tolist()), self._bc_epoch)
+        if key == self._bc_key:
+            it, rr = self._dev().solve_linear(None, None, None, None, rtol=self.solver_rtol, max_iter=self.solver_maxit)
+        else:
+            fixed, du, w, fext = self._calc_BC(bcl0, bcb0, dbcr, dbct, dbcn)
+            it, rr = self._dev().solve_linear(fixed, du, w, fext, rtol=self.solver_rtol, max_iter=self.solver_maxit)
+            self._bc_key = key
         self.solver_stats.append((it, rr))
 
     # ------------------------------------------------------------------------------------------------------
@@ -426,6 +436,7 @@ class Model(object):
             raise AttributeError('Attributes for mesh not set, but required by solver.')
         ctx = self._dev()
         dim = self.dim
+        self._bc_key = None                      # BC types / node sets may have changed since the last call
         if self.u is None:                       # first call: zero state, elstiff = CV (1214-1234)
             ctx.set_field(_lib.F_U, np.zeros(self.Ndof))
             ctx.set_field(_lib.F_F, np.zeros(self.Ndof))

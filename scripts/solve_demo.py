@@ -42,8 +42,26 @@ def main():
         if 'PLF_' + key.upper() in os.environ:
             fe._dev().set_option(key, int(os.environ['PLF_' + key.upper()]))
     t1 = time.time()
+    # wall-clock breakdown of the load sequence (PLF_BREAKDOWN=1): time spent inside the main device calls and in calc_BC
+    acc = {}
+    if os.environ.get('PLF_BREAKDOWN'):
+        def timed(obj, name):
+            f = getattr(obj, name)
+            def g(*a, **k):
+                t = time.perf_counter()
+                r = f(*a, **k)
+                acc[name] = acc.get(name, 0.) + time.perf_counter() - t
+                return r
+            setattr(obj, name, g)
+        dev = fe._dev()
+        for nm in ('solve_linear', 'sweep', 'setupK', 'commit', 'calc_scf', 'reduce_global', 'get_field', 'set_field'):
+            if hasattr(dev, nm):
+                timed(dev, nm)
+        timed(fe, '_calc_BC')
     fe.solve(min_step=min_step)
     t2 = time.time()
+    if acc:
+        print('breakdown [s]:', {k: round(v, 3) for k, v in sorted(acc.items(), key=lambda kv: -kv[1])})
     its = np.array([s[0] for s in fe.solver_stats])
     print('N=%d  Nel=%d  Ndof=%d  mesh %.2fs  solve %.2fs' % (N, fe.Nel, fe.Ndof, t1 - t0, t2 - t1))
     print('increments %d, inner passes per increment %s' % (fe.nsteps, fe.niter))
