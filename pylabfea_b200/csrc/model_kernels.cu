@@ -4,6 +4,7 @@
 //   commit  : state update (1383-1392), calc_global element sums (1500-1511), calc_scf (1036-1067)
 //   solver  : CSR SpMV + Jacobi-preconditioned CG on the BC-reduced system (1028-1033, 1291, 1335)
 // All reductions are deterministic (fixed-order partial sums, last-block-done final pass).
+#include "csr_stencil.cuh"
 #include "hill_fast.cuh"
 #include "plf_device.cuh"
 #include "plf_host.h"
@@ -642,6 +643,44 @@ __global__ void __launch_bounds__(256) spmv_kernel(int64_t nrows, const int32_t 
     }
 }
 
+// q = A p (masked) and p.q for the structured mesh: one thread per row on the closed-form CSR layout (csr_stencil.cuh),
+// matrix pairs and vector pairs as 128-bit loads, no rowptr / col traffic.  The CSR kernel above reads 12 B per
+// non-zero and was the slowest kernel of a multigrid-preconditioned iteration (129 us at 1024^2).
+__global__ void __launch_bounds__(256) stencil_spmv_dot_kernel(int NX, int NY, const double *__restrict__ val,
+                                                               const double *__restrict__ x, double *__restrict__ y,
+                                                               const unsigned char *__restrict__ masked, double *partial,
+                                                               unsigned int *counter, double *dot_out)
+{
+    const int NnY = NY + 1;
+    const int64_t nd = 2ll * (NX + 1) * NnY;
+    double xy = 0.;
+    for (int64_t row = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; row < nd; row += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t n = row >> 1;
+        const int j = (int)(n / NnY), k = (int)(n - (int64_t)j * NnY);
+        int64_t pos = csr_row_start(NX, NY, row);
+        double s = 0.;
+#pragma unroll
+        for (int dj = -1; dj <= 1; dj++) {
+            if (j + dj < 0 || j + dj > NX) continue;
+#pragma unroll
+            for (int dk = -1; dk <= 1; dk++) {
+                if (k + dk < 0 || k + dk > NY) continue;
+                const int64_t m = (int64_t)(j + dj) * NnY + (k + dk);
+                const double2 a = __ldg(reinterpret_cast<const double2 *>(val + pos));
+                const double2 xv = __ldg(reinterpret_cast<const double2 *>(x + 2 * m));
+                s = fma(a.x, xv.x, s);
+                s = fma(a.y, xv.y, s);
+                pos += 2;
+            }
+        }
+        const double out = masked[row] ? 0. : s;
+        y[row] = out;
+        xy += x[row] * out;
+    }
+    double v[1] = {xy};
+    block_reduce_to_partials<1>(v, partial, counter, dot_out, 0);
+}
+
 // CG scalars in device memory.  rz is double-buffered by iteration parity so that no kernel has to swap it:
 // step with parity P reads rz[P] (r.z before the step) and writes rz[1-P].
 struct CgScalars {
@@ -884,7 +923,8 @@ static CgGraphCache g_cg;
 cudaError_t launch_cg(const LaunchCtx &lc, int64_t n, const int32_t *rowptr, const int32_t *col, const double *val,
                       const unsigned char *fixed, const double *b, double *x, double *r, double *z, double *p, double *q,
                       double *diag, double *partial, unsigned int *counter, void *d_sc, void *h_sc, double rtol, int max_iter,
-                      int check_every, int *iters, double *relres, int64_t *launches, MgHierarchy *mg, int warm)
+                      int check_every, int *iters, double *relres, int64_t *launches, MgHierarchy *mg, int warm, int NX,
+                      int NY)
 {
     CgScalars *sc = (CgScalars *)d_sc;
     CgScalars *hs = (CgScalars *)h_sc;
@@ -929,7 +969,8 @@ cudaError_t launch_cg(const LaunchCtx &lc, int64_t n, const int32_t *rowptr, con
     int64_t chunk_launches = 0;
     auto enqueue_chunk = [&]() {
         for (int c = 0; c < check_every; c += 2) {
-            spmv_kernel<<<sg, 256, 0, lc.stream>>>(n, rowptr, col, val, p, nullptr, q, fixed, 0, partial, counter, &sc->pq);
+            if (NX > 0) stencil_spmv_dot_kernel<<<vg, 256, 0, lc.stream>>>(NX, NY, val, p, q, fixed, partial, counter, &sc->pq);
+            else spmv_kernel<<<sg, 256, 0, lc.stream>>>(n, rowptr, col, val, p, nullptr, q, fixed, 0, partial, counter, &sc->pq);
             if (mg) {
                 cg_update_kernel<0, true><<<vg, 256, 0, lc.stream>>>(n, x, r, z, p, q, diag, fixed, sc, partial, counter);
                 mg_vcycle(lc, *mg, r, z, &chunk_launches);
@@ -939,7 +980,8 @@ cudaError_t launch_cg(const LaunchCtx &lc, int64_t n, const int32_t *rowptr, con
                 cg_update_kernel<0, false><<<vg, 256, 0, lc.stream>>>(n, x, r, z, p, q, diag, fixed, sc, partial, counter);
             }
             cg_p_kernel<0><<<vg, 256, 0, lc.stream>>>(n, p, z, sc);
-            spmv_kernel<<<sg, 256, 0, lc.stream>>>(n, rowptr, col, val, p, nullptr, q, fixed, 0, partial, counter, &sc->pq);
+            if (NX > 0) stencil_spmv_dot_kernel<<<vg, 256, 0, lc.stream>>>(NX, NY, val, p, q, fixed, partial, counter, &sc->pq);
+            else spmv_kernel<<<sg, 256, 0, lc.stream>>>(n, rowptr, col, val, p, nullptr, q, fixed, 0, partial, counter, &sc->pq);
             if (mg) {
                 cg_update_kernel<1, true><<<vg, 256, 0, lc.stream>>>(n, x, r, z, p, q, diag, fixed, sc, partial, counter);
                 mg_vcycle(lc, *mg, r, z, &chunk_launches);
@@ -952,7 +994,8 @@ cudaError_t launch_cg(const LaunchCtx &lc, int64_t n, const int32_t *rowptr, con
             chunk_launches += 6;
         }
     };
-    const void *key[6] = {rowptr, val, x, fixed, d_sc, mg ? (const void *)mg : (const void *)partial};
+    const void *key[6] = {NX > 0 ? (const void *)val : (const void *)rowptr, val, x, fixed, d_sc,
+                          mg ? (const void *)mg : (const void *)partial};
     bool cached = g_cg.exec && g_cg.n == n && g_cg.chunk == check_every && g_cg.stream == lc.stream;
     for (int i = 0; i < 6 && cached; i++) cached = (g_cg.key[i] == key[i]);
     if (!cached) {

@@ -40,7 +40,8 @@ cudaError_t launch_cg(const LaunchCtx &lc, int64_t n, const int32_t *rowptr, con
                       const unsigned char *fixed, const double *b, double *x, double *r, double *z, double *p, double *q,
                       double *diag, double *partial, unsigned int *counter, void *d_sc, void *h_sc, double rtol, int max_iter,
                       int check_every, int *iters, double *relres, int64_t *launches, MgHierarchy *mg /* nullable: Jacobi */,
-                      int warm /* 1: start from the previous content of x */);
+                      int warm /* 1: start from the previous content of x */, int NX, int NY /* structured mesh: the
+                      matrix product uses the closed-form CSR layout; NX = 0: generic CSR kernel */);
 cudaError_t launch_spmv(const LaunchCtx &lc, int64_t n, const int32_t *rowptr, const int32_t *col, const double *val, const double *x,
                         const double *rhs, double *y, const unsigned char *masked, int mode, int64_t *launches);
 void cg_graph_reset();   // drops the cached CUDA graph of the CG iteration chunk (call before freeing its buffers)

@@ -543,7 +543,7 @@ extern "C" int plf_solve_linear(plf_ctx *ctx, const uint8_t *fixed, const double
     const bool use_mg = ctx->solver_mg && ctx->mg && ctx->mg->levels() >= 2;
     CK(launch_cg(lc, ctx->Ndof, ctx->d_rowptr, ctx->d_col, ctx->d_val, ctx->d_fixed, ctx->d_b, x, ctx->d_r, ctx->d_z, ctx->d_p, ctx->d_q,
                  ctx->d_diag, ctx->d_partial, counter_ptr(ctx), ctx->d_scalars + 256, ctx->h_scalars + 256, rtol, max_iter,
-                 use_mg ? 4 : 50, &it, &rr, &ctx->launches, use_mg ? ctx->mg : nullptr, ctx->solver_warm));
+                 use_mg ? 4 : 50, &it, &rr, &ctx->launches, use_mg ? ctx->mg : nullptr, ctx->solver_warm, ctx->NX, ctx->NY));
     CK(launch_merge_du(lc, ctx->Ndof, x, ctx->d_bc_du, ctx->d_fixed, ctx->d_du, &ctx->launches));
     CK(cudaStreamSynchronize(ctx->stream));
     if (iters) *iters = it;
