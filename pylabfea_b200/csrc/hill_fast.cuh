@@ -292,6 +292,8 @@ __device__ __forceinline__ int hill_passA(const DevMat &m, double *s, const doub
 //   FM 3 : FM 2 and isotropic elasticity (DevMat.cv_iso): iso_passA / hill_passB_iso below
 //   FM 4 : FM 3 with planar states sorted to hill_passB_iso2d (the non-planar rest runs the FM 3 loop)
 //   FM 6 : FM 1 and isotropic elasticity, planar states sorted to hill_passB_hilliso2d (rest: the FM 1 loop)
+//   FM 7 : FM 1 / 2 on a block-structured CV that is not isotropic (plane stress, cubic), planar states sorted to
+//          hill_passB_blk2d (rest: the FM 1 loop)
 template <int FM>
 __device__ __forceinline__ void cv_mul_t(const DevMat &m, const double *v, double *o)
 {
@@ -984,6 +986,155 @@ __device__ __forceinline__ int hill_passB_hilliso2d(const DevMat &m, double *s, 
     Wf[sym_idx(1, 2)] = -W01 - W11;
     Wf[sym_idx(2, 2)] = W00 + 2. * W01 + W11;
     Wf[sym_idx(2, 5)] = -W05 - W15;
+    if (corrected) {
+        Wf[sym_idx(0, 0)] += xc[0 * xstride];
+        Wf[sym_idx(0, 1)] += xc[5 * xstride];
+        Wf[sym_idx(0, 2)] += xc[4 * xstride];
+        Wf[sym_idx(1, 1)] += xc[1 * xstride];
+        Wf[sym_idx(1, 2)] += xc[3 * xstride];
+        Wf[sym_idx(2, 2)] += xc[2 * xstride];
+    }
+    const double f2s = st_scal * (1. / (double)PLF_MAXIT);
+#pragma unroll
+    for (int i = 0; i < 6; i++)
+#pragma unroll
+        for (int j = i; j < 6; j++) {
+            const double c = m.CV[6 * i + j];
+            gs[sym_idx(i, j)] = c * f1 + ((double)PLF_MAXIT * c - Wf[sym_idx(i, j)]) * f2s;
+        }
+    return 2 | (corrected ? 4 : 0);
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// FM 7: Hill-6p / J2 (no Drucker / LHS term) on any block-structured symmetric CV that is not isotropic in the 3-d sense
+// -- the plane-stress CV of Element.__init__ (model.py:274-283, zero third row and column: most 2-d examples of the
+// reference), cubic C11 / C12 / C44 -- with planar states sorted to their own loop.  The identities of FM 6 without the
+// isotropy:  a = g / (2 seq),  CV a = cg / (2 seq) with cg = CV g,
+//     hh = a.CV a + khard = (Gc + 4 khard q) / (4 q),   Gc = g.cg
+//     sig += CV deps_r - CV a (a.CV deps_r / hh)   <=>   s += cdr - beta cg,   beta = (g.cdr) D,  D = 1 / (Gc + 4 khard q)
+//     depl = beta g (when the elastic trial stress is outside the yield surface),   CV a (CV a)^T / hh = D cg cg^T
+// One reciprocal and one reciprocal square root per sub-step; the tangent sum lives on {0,1,2,5} (10 entries).
+// ------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ int hillblk_passA(const DevMat &m, double *s, const double *ep, const double *de, double *dp, double *ca,
+                                             double &tc, double &tw, double &fy)
+{
+    HillStep P;
+#pragma unroll
+    for (int k = 0; k < 6; k++) { dp[k] = 0.; ca[k] = 0.; }
+    tc = 1.; tw = 0.;
+    if (iso_prelude<1>(m, s, ep, de, P, fy)) return 0;
+    double g[6], cg[6];
+    hill_qgrad(m, s, g);
+    cv_mul_t<1>(m, g, cg);
+    const double q = hill_q(m, s), qc = hill_q(m, P.cdr);
+    double Gc = 0., gcd = 0.;
+#pragma unroll
+    for (int k = 0; k < 6; k++) { Gc = fma(g[k], cg[k], Gc); gcd = fma(g[k], P.cdr[k], gcd); }
+    const double D = fast_rcp(fma(4. * m.khard, q, Gc));
+    const double beta = gcd * D;
+    const double ythr = P.sflow0 + PLF_YF_TOLERANCE;
+    const bool yplus = (q + gcd) + qc > ythr * ythr;   // epl_dot 1031-1041 on the elastic trial stress
+    const double gam = yplus ? beta : 0.;
+    double eplt[6], st[6];
+#pragma unroll
+    for (int k = 0; k < 6; k++) {
+        dp[k] = gam * g[k];
+        eplt[k] = ep[k] + dp[k];
+        st[k] = fma(-beta, cg[k], s[k] + P.cdr[k]);
+    }
+    fy = fast_sqrt(hill_q(m, st)) - (m.sy + (m.khard != 0. ? eps_eq6_fast(eplt) * m.khard : 0.));
+    if (fy > P.toler) return -1;   // 288-291: subdivide
+#pragma unroll
+    for (int k = 0; k < 6; k++) { s[k] = st[k]; ca[k] = cg[k]; }
+    // grad_stiff = CV (1 - st_scal) [split] + (CV - D cg cg^T) st_scal   (269, 343 with nsteps = 1)
+    tc = (P.split ? (1. - P.st_scal) : 0.) + P.st_scal;
+    tw = D * P.st_scal;
+    return 1;
+}
+
+__device__ __forceinline__ int hill_passB_blk2d(const DevMat &m, double *s, double *epd, const double *de, double *xc, int xstride,
+                                                double *gs, double &fy)
+{
+    double st_scal, f1;
+    double c0k, c1k, c2k, c5k, qc, c0, ythr2;   // CV deps_r / 50 on {0,1,2,5}
+    {
+        HillStep P;
+        iso_prelude<1>(m, s, epd, de, P, fy);   // cannot be elastic: pass A deferred this element
+#pragma unroll
+        for (int k = 0; k < 6; k++) {
+            P.dr[k] *= 1. / (double)PLF_MAXIT;   // 290
+            xc[(6 + k) * xstride] = P.dr[k];
+            xc[k * xstride] = 0.;
+        }
+        cv_mul_t<1>(m, P.dr, P.cdr);
+        c0k = P.cdr[0]; c1k = P.cdr[1]; c2k = P.cdr[2]; c5k = P.cdr[5];
+        qc = hill_q(m, P.cdr);
+        c0 = m.sy + P.toler;
+        const double ythr = P.sflow0 + PLF_YF_TOLERANCE;
+        ythr2 = ythr * ythr;
+        st_scal = P.st_scal;
+        f1 = P.split ? (1. - P.st_scal) : 0.;
+    }
+    const double *C = m.CV;
+    const double C00 = C[0], C01 = C[1], C02 = C[2], C11 = C[7], C12 = C[8], C22 = C[14], C55 = C[35];
+    const double kh4 = 4. * m.khard, K2 = m.khard * m.khard;
+    const double h0 = m.hill[0], h1 = m.hill[1], h2 = m.hill[2], h5x6 = 6. * m.hill[5];
+    double s0 = s[0], s1 = s[1], s2 = s[2], s5 = s[5];
+    double e0 = epd[0], e1 = epd[1], e2 = epd[2], e5 = epd[5];
+    double u0 = h0 * (s0 - s1), u1 = h1 * (s1 - s2), u2 = h2 * (s2 - s0);
+    double g0 = u0 - u2, g1 = u1 - u0, g2 = u2 - u1, g5 = h5x6 * s5;
+    double q = 0.5 * (u0 * (s0 - s1) + u1 * (s1 - s2) + u2 * (s2 - s0) + g5 * s5);
+    double W00 = 0., W01 = 0., W02 = 0., W05 = 0., W11 = 0., W12 = 0., W15 = 0., W22 = 0., W25 = 0., W55 = 0.;
+    double seq = 0.;
+    bool corrected = false;
+#pragma unroll 1
+    for (int it = 0; it < PLF_MAXIT; it++) {
+        const double cg0 = fma(C02, g2, fma(C01, g1, C00 * g0));
+        const double cg1 = fma(C12, g2, fma(C11, g1, C01 * g0));
+        const double cg2 = fma(C22, g2, fma(C12, g1, C02 * g0));
+        const double cg5 = C55 * g5;
+        const double Gc = fma(g5, cg5, fma(g2, cg2, fma(g1, cg1, g0 * cg0)));
+        const double gcd = fma(g5, c5k, fma(g2, c2k, fma(g1, c1k, g0 * c0k)));
+        const bool yplus = (q + gcd) + qc > ythr2;
+        const double D = fast_rcp1(fma(kh4, q, Gc));
+        const double beta = gcd * D;
+        const double gam = yplus ? beta : 0.;
+        const double t0 = D * cg0, t1 = D * cg1, t2 = D * cg2, t5 = D * cg5;
+        W00 = fma(t0, cg0, W00); W01 = fma(t0, cg1, W01); W02 = fma(t0, cg2, W02); W05 = fma(t0, cg5, W05);
+        W11 = fma(t1, cg1, W11); W12 = fma(t1, cg2, W12); W15 = fma(t1, cg5, W15);
+        W22 = fma(t2, cg2, W22); W25 = fma(t2, cg5, W25); W55 = fma(t5, cg5, W55);
+        double f0 = fma(gam, g0, e0), f1e = fma(gam, g1, e1), f2 = fma(gam, g2, e2), f5 = fma(gam, g5, e5);
+        s0 = fma(-beta, cg0, s0 + c0k); s1 = fma(-beta, cg1, s1 + c1k); s2 = fma(-beta, cg2, s2 + c2k); s5 = fma(-beta, cg5, s5 + c5k);
+        const double d01 = s0 - s1, d12 = s1 - s2, d20 = s2 - s0;
+        u0 = h0 * d01; u1 = h1 * d12; u2 = h2 * d20;
+        g0 = u0 - u2; g1 = u1 - u0; g2 = u2 - u1; g5 = h5x6 * s5;
+        q = 0.5 * fma(g5, s5, fma(u2, d20, fma(u1, d12, u0 * d01)));
+        seq = q * fast_rsqrt1(q + 1e-300);
+        const double e2s = (2. / 3.) * ((f0 * f0 + f1e * f1e + f2 * f2) + 0.5 * (f5 * f5));
+        const double lhs = seq - c0;
+        if (lhs > 0. && lhs * lhs > K2 * e2s) {
+            corrected = true;
+            double st[9] = {s0, s1, s2, s5, f0, f1e, f2, f5, seq};
+            hilliso2d_correct(m, st, xc, xstride);
+            s0 = st[0]; s1 = st[1]; s2 = st[2]; s5 = st[3];
+            f0 = st[4]; f1e = st[5]; f2 = st[6]; f5 = st[7];
+            u0 = h0 * (s0 - s1); u1 = h1 * (s1 - s2); u2 = h2 * (s2 - s0);
+            g0 = u0 - u2; g1 = u1 - u0; g2 = u2 - u1; g5 = h5x6 * s5;
+            q = 0.5 * (u0 * (s0 - s1) + u1 * (s1 - s2) + u2 * (s2 - s0) + g5 * s5);
+            seq = fast_sqrt(q);
+        }
+        e0 = f0; e1 = f1e; e2 = f2; e5 = f5;
+    }
+    seq = fast_sqrt(q);   // full-precision seq for the returned yield-function value
+    s[0] = s0; s[1] = s1; s[2] = s2; s[3] = 0.; s[4] = 0.; s[5] = s5;
+    epd[0] = e0; epd[1] = e1; epd[2] = e2; epd[5] = e5;   // epd[3], epd[4] stay zero
+    fy = seq - (m.sy + (m.khard != 0. ? eps_eq6(epd) * m.khard : 0.));
+    double Wf[21];
+#pragma unroll
+    for (int k = 0; k < 21; k++) Wf[k] = 0.;
+    Wf[sym_idx(0, 0)] = W00; Wf[sym_idx(0, 1)] = W01; Wf[sym_idx(0, 2)] = W02; Wf[sym_idx(0, 5)] = W05;
+    Wf[sym_idx(1, 1)] = W11; Wf[sym_idx(1, 2)] = W12; Wf[sym_idx(1, 5)] = W15;
+    Wf[sym_idx(2, 2)] = W22; Wf[sym_idx(2, 5)] = W25; Wf[sym_idx(5, 5)] = W55;
     if (corrected) {
         Wf[sym_idx(0, 0)] += xc[0 * xstride];
         Wf[sym_idx(0, 1)] += xc[5 * xstride];

@@ -137,7 +137,7 @@ __device__ __forceinline__ void passA_tile(int64_t n, int64_t tile, double *s_in
                                            double *__restrict__ ctan, int32_t *__restrict__ nsteps, int32_t *worklist,
                                            unsigned int *work_count)
 {
-    constexpr int FA = FM == 6 ? 1 : (FM >= 3 ? 2 : FM);   // (the isotropic modes use iso_passA / hilliso_passA)
+    constexpr int FA = (FM == 6 || FM == 7) ? 1 : (FM >= 3 ? 2 : FM);   // (modes >= 3 have their own pass A functions)
     const int tid = threadIdx.x;
     double *s_sig = s_in, *s_epl = s_in + RB * 6, *s_dep = s_in + 2 * RB * 6;
     const int64_t base = tile * RB;
@@ -158,7 +158,7 @@ __device__ __forceinline__ void passA_tile(int64_t n, int64_t tile, double *s_in
     const int64_t e = base + tid;
     if (tid < cnt) {
         const DevMat &m = c_mat[SINGLE ? 0 : mat_id[e]];
-        if (FM == 4 || FM == 6) general = !planar_state(s, ep, de);   // planar states go to the front of the list
+        if (FM == 4 || FM == 6 || FM == 7) general = !planar_state(s, ep, de);   // planar states go to the front of the list
         if (m.kind == PLF_MAT_ELASTIC || m.kind == PLF_MAT_HILL) {
             double dp[6], ca[6], tc = 1., tw = 0., fyv = 0.;
             int br = 0;
@@ -175,7 +175,8 @@ __device__ __forceinline__ void passA_tile(int64_t n, int64_t tile, double *s_in
                     for (int k = 0; k < 6; k++) { dp[k] = ep[k]; ca[k] = de[k]; }
                     fyv = s[0];
                 } else
-                br = (FM == 6) ? hilliso_passA(m, s, ep, de, dp, ca, tc, tw, fyv)
+                br = (FM == 7) ? hillblk_passA(m, s, ep, de, dp, ca, tc, tw, fyv)
+                   : (FM == 6) ? hilliso_passA(m, s, ep, de, dp, ca, tc, tw, fyv)
                    : (FM >= 3) ? iso_passA(m, s, ep, de, dp, ca, tc, tw, fyv) : hill_passA<FA>(m, s, ep, de, dp, ca, tc, tw, fyv);
             }
             if (br < 0) {
@@ -250,7 +251,8 @@ __device__ __forceinline__ void passB_element(int64_t e, WAcc &W, double *xc, co
         ep[2 * k] = b.x; ep[2 * k + 1] = b.y;
         de[2 * k] = c.x; de[2 * k + 1] = c.y;
     }
-    if (FM == 6) hill_passB_hilliso2d(m, s, ep, de, xc, RB, gs, fyv);
+    if (FM == 7) hill_passB_blk2d(m, s, ep, de, xc, RB, gs, fyv);
+    else if (FM == 6) hill_passB_hilliso2d(m, s, ep, de, xc, RB, gs, fyv);
     else if (FM == 4) hill_passB_iso2d(m, s, ep, de, xc, RB, gs, fyv);
     else if (FM == 3) hill_passB_iso(m, s, ep, de, xc, RB, gs, fyv);
     else hill_passB<FM>(m, s, ep, de, W, gs, fyv);
@@ -336,7 +338,7 @@ __global__ void __launch_bounds__(RB, MINB) response_passB_kernel(const int32_t 
         WRegs W;
         passB_element<SINGLE, FM>(e, W, s_xc + threadIdx.x, mat_id, sig, epl, deps, fy, sig_out, depl_out, ctan, nsteps);
     }
-    if (FM == 4 || FM == 6) {
+    if (FM == 4 || FM == 6 || FM == 7) {
         // the non-planar elements (back of the list) with the general loop of the material class
         for (unsigned int t = blockIdx.x * RB + threadIdx.x; t < n1; t += gridDim.x * RB) {
             const int64_t e = worklist[nlist - 1 - (int64_t)t];
@@ -638,6 +640,7 @@ cudaError_t response_init()
     if ((e = big_smem(response_passA_kernel<true, 4, false>, k1a_smem(false))) != cudaSuccess) return e;
     if ((e = big_smem(response_passA_kernel<true, 5, false>, k1a_smem(false))) != cudaSuccess) return e;
     if ((e = big_smem(response_passA_kernel<true, 6, false>, k1a_smem(false))) != cudaSuccess) return e;
+    if ((e = big_smem(response_passA_kernel<true, 7, false>, k1a_smem(false))) != cudaSuccess) return e;
     if ((e = big_smem(response_generic_kernel, k1_smem())) != cudaSuccess) return e;
     if ((e = big_smem(response_svc_kernel, 227 * 1024)) != cudaSuccess) return e;
     return big_smem(prim_svc_kernel, 227 * 1024);
@@ -654,6 +657,7 @@ static int fast_mode(const DevMat *hmats, int nmat, int max_fm)
         if (hmats[0].hill[k] != 1.) fm = 1;
     if (fm == 2 && hmats[0].cv_iso) fm = 4;
     if (fm == 1 && hmats[0].cv_iso && max_fm >= 4) return 6;   // Hill on isotropic elasticity: its own planar mode
+    if (!hmats[0].cv_iso && max_fm >= 4) return 7;              // plane-stress / cubic CV: block-CV planar mode (J2 and Hill)
     return std::min(fm, max_fm);
 }
 
@@ -687,6 +691,7 @@ cudaError_t launch_response(const LaunchCtx &lc, const DevMat *hmats, int nmat, 
     } while (0)
             if (lc.k1_only == 2) PASSA(true, 5);
             else if (!single) PASSA(false, 0);
+            else if (fm == 7) PASSA(true, 7);
             else if (fm == 6) PASSA(true, 6);
             else if (fm == 4) PASSA(true, 4);
             else if (fm == 3) PASSA(true, 3);
@@ -715,7 +720,8 @@ cudaError_t launch_response(const LaunchCtx &lc, const DevMat *hmats, int nmat, 
     cudaLaunchKernelEx(&pdl_cfg, response_passB_kernel<M, S, F>, mat_id, sig, epl, deps, fy, sig_out, depl, ctan, nsteps, \
                        wl_c, n, work_count)
             if (single) {
-                if (fm == 6) PASSB(3, true, 6);
+                if (fm == 7) PASSB(3, true, 7);
+                else if (fm == 6) PASSB(3, true, 6);
                 else if (fm == 4) PASSB(3, true, 4);   // planar elements first, then whatever is not planar
                 else if (fm == 3) PASSB(3, true, 3);
                 else if (fm == 2) PASSB(3, true, 2);

@@ -1,7 +1,7 @@
 #!/usr/bin/env python3
 """Kernel throughput on the other BASELINE.json configurations (bench.py measures the headline 1024 x 1024 J2 case):
 
-    python scripts/config_bench.py j2_256 | hill_512 | svc_512 | barlat_2048 [n_elements]
+    python scripts/config_bench.py j2_256 | hill_512 | svc_512 | barlat_2048 | j2ps_1024 [n_elements]
 
 config 2: 256 x 256 J2; config 3: 512 x 512 Hill (sy=150, hill=[0.7,1,1.4,1,1.2,0.8], khard=100); config 4: 512 x 512
 with the RBF-SVC yield function of examples/train_hill.py (1 585 support vectors, the model the reference trained in
@@ -23,6 +23,7 @@ import pylabfea_b200 as FE  # noqa: E402
 def run(name, n_override=None):
     ctx = _lib.Context(0)
     reps = 20
+    planestress = False
     if name == 'j2_256':
         N = 256
         mat, _ = bench.j2_material()
@@ -34,6 +35,12 @@ def run(name, n_override=None):
         m.plasticity(sy=150., hill=[0.7, 1., 1.4, 1., 1.2, 0.8], khard=100., sdim=6)
         mat = m._descriptor()
         sig, epl, deps = bench.synth_states(N, 1234, khard=100.)
+    elif name == 'j2ps_1024':   # plane-stress variant of the target workload (not a BASELINE config): block-CV fast mode
+        N = 1024
+        mat, _ = bench.j2_material()
+        sig, epl, deps = bench.synth_states(N, 1234)
+        sig[:, 2] = 0.
+        planestress = True
     elif name == 'svc_512':
         N = 512
         g = dict(np.load(os.path.join(os.path.dirname(__file__), '..', 'tests', 'golden', 'svc_hill.npz')))
@@ -57,11 +64,13 @@ def run(name, n_override=None):
         raise SystemExit('unknown config ' + name)
     n = N * N if n_override is None else int(n_override)
     sig, epl, deps = sig[:n], epl[:n], deps[:n]
-    ctx.set_materials([mat], planestress=False)
+    ctx.set_materials([mat], planestress=planestress)
     lx = 4. / N
     b = ctx.batch_create(n)
     ctx.batch_upload(b, np.ascontiguousarray(sig), np.ascontiguousarray(epl), np.ascontiguousarray(deps))
     full_mesh = (n == N * N)
+    if os.environ.get('PLF_MAX_FM'):
+        ctx.set_option('max_fm', int(os.environ['PLF_MAX_FM']))
     if full_mesh:
         ctx.mesh_structured(N, N, np.full(N, lx), lx, 1., np.zeros(n, np.int32))
     ctx.batch_run(b)

@@ -470,3 +470,45 @@ def test_sdim3_j2_equals_sdim6_j2_on_axis_aligned_states(ctx, golden):
     assert int(np.sum(outs[0][4] == 49)) > 2000
     for a, b in zip(outs[0][:4], outs[1][:4]):
         assert np.max(np.abs(a - b)) <= 1e-9 * np.max(np.abs(b))
+
+
+@pytest.mark.parametrize('hill', [None, [0.7, 1., 1.4, 1., 1.2, 0.8]])
+def test_response_plane_stress_block_mode_vs_general_and_oracle(ctx, hill):
+    """Plane-stress CV (zero third row / column: not isotropic in the 3-d sense) with J2 and Hill-6p, 512 x 512 synthetic
+    planar field: the block-CV fast mode (hillblk_passA + planar loop, FM 7) against the general kernels on every element
+    and against the CPU oracle on a seeded sample."""
+    import bench
+    from oracle import oracle as orc
+    N = 512
+    mat, CV3 = bench.j2_material()
+    if hill is not None:
+        mat.hill[:] = hill
+    mat.khard = 200.
+    ctx.set_materials([mat], planestress=True)
+    CV = ctx.element_CV(0)
+    assert CV[2, 2] == 0. and CV[0, 0] > 0.
+    sig, epl, deps = bench.synth_states(N, 777, khard=200.)
+    sig[:, 2] = 0.                                   # plane stress
+    if hill is not None:
+        # synth_states sets the load level with the J2 equivalent stress; keep the same level in the Hill measure
+        def seq_of(h):
+            d01, d12, d20 = sig[:, 0] - sig[:, 1], sig[:, 1] - sig[:, 2], sig[:, 2] - sig[:, 0]
+            return np.sqrt(0.5 * (h[0] * d01 ** 2 + h[1] * d12 ** 2 + h[2] * d20 ** 2) + 3. * h[5] * sig[:, 5] ** 2)
+        sig *= (seq_of([1.] * 6) / np.maximum(seq_of(hill), 1e-300))[:, None]
+    try:
+        ctx.set_option('max_fm', 0)
+        ref = ctx.response_batch(sig, epl, deps)
+        ctx.set_option('max_fm', 4)
+        out = ctx.response_batch(sig, epl, deps)
+        assert int(np.sum(ref[4] == 49)) > 0.02 * N * N
+        assert np.array_equal(out[4], ref[4])
+        for a, b in zip(out[:4], ref[:4]):
+            assert np.max(np.abs(a - b)) <= 1e-10 * np.max(np.abs(b))
+        idx = np.random.default_rng(8).choice(N * N, 10000, replace=False)
+        mats = [orc.Mat(kind=orc.HILL, E=bench.E_MOD, nu=bench.NU, sy=bench.SY, khard=200., hill=hill)]
+        oref = orc.response_batch(mats, None, sig[idx], epl[idx], deps[idx], CV[None])
+        assert np.array_equal(out[4][idx], oref[4])
+        assert relmax(out[1][idx], oref[1]) < TOL and relmax(out[3][idx], oref[3]) < TOL
+        assert np.max(np.abs(out[2][idx] - oref[2])) < TOL * np.max(np.abs(oref[2]))
+    finally:
+        ctx.set_option('max_fm', 4)
