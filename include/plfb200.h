@@ -200,6 +200,25 @@ int plf_calc_scf(plf_ctx *ctx, const double *sld, double *scf);
 int plf_solve_linear(plf_ctx *ctx, const uint8_t *fixed, const double *du_bc, const double *w, const double *f_ext,
                      double rtol, int max_iter, int *iters, double *relres);
 
+/* ---- strip-partitioned solve over several GPUs (one process per GPU) -------------------------------------------- */
+/* The reference has no counterpart (it is a single-process NumPy code); SURVEY.md 8e: rank g holds the strip of
+ * element columns it owns plus one halo element column on its left (pylabfea_b200/shard.py), so the rows of K of its
+ * owned node columns are complete and bit-identical to the global K (model.py:954-977) without communication.  The
+ * solve is the one exchange step: plf_solve_linear on a context with a communicator runs Jacobi-preconditioned CG on
+ * the distributed system -- per iteration one halo node column (2 (NY+1) doubles) to and from each neighbour and two
+ * all-reduces of the dot products, all enqueued on the context's stream (NCCL, loaded with dlopen on first use).
+ * Every rank passes the boundary-condition vectors of ITS local node grid (slices of the global calc_BC vectors,
+ * ghost columns included) and gets du on its local node grid back (ghost columns filled from the neighbours). */
+#define PLF_COMM_ID_BYTES 128
+int plf_comm_unique_id(unsigned char *id);                 /* rank 0: ncclGetUniqueId; hand the bytes to every rank */
+int plf_comm_init(plf_ctx *ctx, const unsigned char *id, int rank, int world);   /* collective over all ranks */
+/* owned node columns [own_first, own_end) of the local mesh: own_first = 1 on ranks with a left neighbour (column 0 is
+ * the neighbour's), own_end = NX on ranks with a right neighbour (column NX is the neighbour's), else 0 / NX + 1 */
+int plf_comm_set_strip(plf_ctx *ctx, int own_first, int own_end);
+/* sum of n <= 64 host doubles over all ranks, in place (sweep flags, calc_global sums, calc_scf moments) */
+int plf_comm_allreduce(plf_ctx *ctx, double *vals, int n);
+int plf_comm_destroy(plf_ctx *ctx);
+
 #ifdef __cplusplus
 }
 #endif

@@ -363,3 +363,36 @@ class Context:
         self._ck(self.L.plf_solve_linear(self.h, _ptr(fixed), _ptr(du_bc), _ptr(w), _ptr(f_ext), C.c_double(rtol),
                                          int(max_iter), C.byref(it), C.byref(rr)))
         return it.value, rr.value
+
+    # ---- strip-partitioned solve over several GPUs (plf_comm_*) --------------------------------------------
+    def comm_init(self, unique_id, rank, world):
+        """Collective over all ranks: join the NCCL communicator identified by `unique_id` (comm_unique_id() of rank 0)."""
+        if len(unique_id) != COMM_ID_BYTES:
+            raise ValueError('unique_id must be the %d bytes of comm_unique_id()' % COMM_ID_BYTES)
+        buf = (C.c_ubyte * COMM_ID_BYTES).from_buffer_copy(bytes(unique_id))
+        self._ck(self.L.plf_comm_init(self.h, buf, int(rank), int(world)))
+
+    def comm_set_strip(self, own_first, own_end):
+        """Owned node columns [own_first, own_end) of the local mesh (shard.strip_shard: owned_node_cols_local)."""
+        self._ck(self.L.plf_comm_set_strip(self.h, int(own_first), int(own_end)))
+
+    def comm_allreduce(self, vals):
+        """Sum of a small float vector over all ranks."""
+        a = np.array(vals, dtype=np.float64).ravel()
+        self._ck(self.L.plf_comm_allreduce(self.h, _ptr(a), len(a)))
+        return a
+
+    def comm_destroy(self):
+        self._ck(self.L.plf_comm_destroy(self.h))
+
+
+COMM_ID_BYTES = 128
+
+
+def comm_unique_id():
+    """ncclGetUniqueId of the calling process (rank 0); hand the bytes to every rank by any side channel."""
+    L = load()
+    buf = (C.c_ubyte * COMM_ID_BYTES)()
+    if L.plf_comm_unique_id(buf) != PLF_OK:
+        raise PlfError('plf_comm_unique_id failed: NCCL (libnccl.so.2) could not be loaded')
+    return bytes(buf)

@@ -26,6 +26,7 @@ UNITS = {
     'assembly_kernels.cu': ['-fmad=false'],
     'plf_api.cu': [],
     'plf_model.cu': [],
+    'plf_comm.cu': [],
 }
 
 
@@ -56,7 +57,7 @@ def build(force=False, verbose=False):
 
     with ThreadPoolExecutor(len(UNITS)) as ex:
         objs = list(ex.map(cc, UNITS.items()))
-    cmd = [NVCC, '-shared', '-o', LIB] + objs + ['-gencode', 'arch=compute_100a,code=sm_100a']
+    cmd = [NVCC, '-shared', '-o', LIB] + objs + ['-gencode', 'arch=compute_100a,code=sm_100a', '-ldl']
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError('link failed:\n%s\n%s' % (r.stdout, r.stderr))

@@ -691,7 +691,8 @@ struct CgScalars {
 // x += alpha p ; r -= alpha q ; z = r / diag ; r.z and r.r   (alpha = rz / pq computed by every thread)
 // MG: the preconditioner is the multigrid V-cycle (mg_kernels.cu), applied between this kernel and cg_rz_kernel:
 // z and r.z are not touched here.
-template <int P, bool MG>
+// DIST: the sums of this rank stay in sc->tmp; they are all-reduced and published by cg_publish_kernel.
+template <int P, bool MG, bool DIST = false>
 __global__ void __launch_bounds__(256) cg_update_kernel(int64_t n, double *__restrict__ x, double *__restrict__ r,
                                                         double *__restrict__ z, const double *__restrict__ p,
                                                         const double *__restrict__ q, const double *__restrict__ diag,
@@ -714,10 +715,29 @@ __global__ void __launch_bounds__(256) cg_update_kernel(int64_t n, double *__res
         }
         v[1] += ri * ri;
     }
-    if (block_reduce_to_partials<2>(v, partial, counter, sc->tmp, 0)) {
+    if (block_reduce_to_partials<2>(v, partial, counter, sc->tmp, 0) && !DIST) {
         // the one finalising thread: publish r.z for the next step, r.r, and count the step if it was a real one
         if (!MG) sc->rz[1 - P] = sc->tmp[0];
         if (live) { sc->rr = sc->tmp[1]; sc->iters += 1.; }
+    }
+}
+
+// distributed CG: what the finalising thread of cg_update_kernel does, after sc->tmp has been summed over the ranks
+template <int P>
+__global__ void cg_publish_kernel(CgScalars *sc)
+{
+    const bool live = sc->rr > sc->target && sc->pq != 0.;
+    sc->rz[1 - P] = sc->tmp[0];
+    if (live) { sc->rr = sc->tmp[1]; sc->iters += 1.; }
+}
+
+// mask of the distributed CG: Dirichlet dofs and the dofs of node columns owned by a neighbour rank
+__global__ void __launch_bounds__(256) cg_ghost_mask_kernel(int64_t n, int NnY, int own_first, int own_end,
+                                                            const unsigned char *__restrict__ fixed, unsigned char *__restrict__ mask)
+{
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const int j = (int)((i >> 1) / NnY);
+        mask[i] = (fixed[i] || j < own_first || j >= own_end) ? 1 : 0;
     }
 }
 
@@ -1021,6 +1041,88 @@ cudaError_t launch_cg(const LaunchCtx &lc, int64_t n, const int32_t *rowptr, con
         if (!(hs->rr > target)) break;   // also stops on NaN
     }
     *iters = (int)hs->iters;
+    return cudaGetLastError();
+}
+
+// Strip-partitioned Jacobi-preconditioned CG.  Every rank runs the same kernel sequence on its local
+// node grid; `mask` hides the Dirichlet dofs and the ghost node columns, so all sums run over owned free dofs only.  Per
+// iteration: ghost columns of p from the neighbours, q = K p on the owned rows (complete rows, see shard.py), p.q summed
+// over the ranks, update, (r.z, r.r) summed over the ranks, direction.  All scalars stay on the device and are identical
+// on every rank after each all-reduce, so every rank takes the same convergence decisions.  Enqueued eagerly (NCCL calls
+// between the kernels); the host reads the residual every `check_every` iterations.
+cudaError_t launch_cg_dist(const LaunchCtx &lc, Comm &comm, int64_t n, const int32_t *rowptr, const int32_t *col, const double *val,
+                           const unsigned char *mask, const double *b, double *x, double *r, double *z, double *p, double *q,
+                           double *diag, double *partial, unsigned int *counter, void *d_sc, void *h_sc, double rtol,
+                           int max_iter, int check_every, int *iters, double *relres, int64_t *launches, int warm, int NX, int NY)
+{
+    CgScalars *sc = (CgScalars *)d_sc;
+    CgScalars *hs = (CgScalars *)h_sc;
+    const unsigned vg = vec_grid(n, lc.sm_count);
+    cudaError_t e;
+#define PLF_NC(call) do { if (call) return cudaErrorUnknown; } while (0)
+    check_every = std::max(2, check_every & ~1);
+    diag_kernel<<<(unsigned)((n + 255) / 256), 256, 0, lc.stream>>>(n, rowptr, col, val, diag);
+    if (warm) {
+        cg_mask_x_kernel<<<vg, 256, 0, lc.stream>>>(n, x, mask);
+        PLF_NC(comm_halo_exchange(comm, x, NX, NY, lc.stream));
+        spmv_kernel<<<spmv_grid(n, lc.sm_count), 256, 0, lc.stream>>>(n, rowptr, col, val, x, nullptr, q, mask, 0, nullptr, nullptr, nullptr);
+        cg_init_warm_kernel<<<vg, 256, 0, lc.stream>>>(n, b, q, r, z, p, diag, mask, sc, rtol, partial, counter);
+        *launches += 4;
+    } else {
+        cg_init_kernel<<<vg, 256, 0, lc.stream>>>(n, b, x, r, z, p, diag, mask, sc, rtol, partial, counter);
+        *launches += 2;
+    }
+    // pq (= 0), rz[2], tmp[2], rr, target: every one of them is a sum over dofs (target = rtol^2 b.b)
+    PLF_NC(comm_allreduce_sum(comm, reinterpret_cast<double *>(sc), 7, lc.stream));
+    if ((e = cudaMemcpyAsync(hs, sc, sizeof(CgScalars), cudaMemcpyDeviceToHost, lc.stream)) != cudaSuccess) return e;
+    if ((e = cudaStreamSynchronize(lc.stream)) != cudaSuccess) return e;
+    const double bb = warm ? hs->tmp[1] : hs->rr;
+    *iters = 0;
+    *relres = 0.;
+    if (bb == 0.) {
+        if (warm) cudaMemsetAsync(x, 0, (size_t)n * sizeof(double), lc.stream);
+        return cudaSuccess;
+    }
+    const double target = hs->target;
+    if (warm && !(hs->rr > target)) {
+        *relres = sqrt(hs->rr / bb);
+        return cudaSuccess;
+    }
+    int it = 0;
+    while (it < max_iter) {
+        for (int c = 0; c < check_every; c += 2) {
+            PLF_NC(comm_halo_exchange(comm, p, NX, NY, lc.stream));
+            stencil_spmv_dot_kernel<<<vg, 256, 0, lc.stream>>>(NX, NY, val, p, q, mask, partial, counter, &sc->pq);
+            PLF_NC(comm_allreduce_sum(comm, &sc->pq, 1, lc.stream));
+            cg_update_kernel<0, false, true><<<vg, 256, 0, lc.stream>>>(n, x, r, z, p, q, diag, mask, sc, partial, counter);
+            PLF_NC(comm_allreduce_sum(comm, sc->tmp, 2, lc.stream));
+            cg_publish_kernel<0><<<1, 1, 0, lc.stream>>>(sc);
+            cg_p_kernel<0><<<vg, 256, 0, lc.stream>>>(n, p, z, sc);
+            PLF_NC(comm_halo_exchange(comm, p, NX, NY, lc.stream));
+            stencil_spmv_dot_kernel<<<vg, 256, 0, lc.stream>>>(NX, NY, val, p, q, mask, partial, counter, &sc->pq);
+            PLF_NC(comm_allreduce_sum(comm, &sc->pq, 1, lc.stream));
+            cg_update_kernel<1, false, true><<<vg, 256, 0, lc.stream>>>(n, x, r, z, p, q, diag, mask, sc, partial, counter);
+            PLF_NC(comm_allreduce_sum(comm, sc->tmp, 2, lc.stream));
+            cg_publish_kernel<1><<<1, 1, 0, lc.stream>>>(sc);
+            cg_p_kernel<1><<<vg, 256, 0, lc.stream>>>(n, p, z, sc);
+            *launches += 8;
+        }
+        it += check_every;
+        if ((e = cudaMemcpyAsync(hs, sc, sizeof(CgScalars), cudaMemcpyDeviceToHost, lc.stream)) != cudaSuccess) return e;
+        if ((e = cudaStreamSynchronize(lc.stream)) != cudaSuccess) return e;
+        *relres = sqrt(hs->rr / bb);
+        if (!(hs->rr > target)) break;
+    }
+#undef PLF_NC
+    *iters = (int)hs->iters;
+    return cudaGetLastError();
+}
+
+cudaError_t launch_ghost_mask(const LaunchCtx &lc, int64_t n, int NY, int own_first, int own_end, const unsigned char *fixed,
+                              unsigned char *mask, int64_t *launches)
+{
+    cg_ghost_mask_kernel<<<vec_grid(n, lc.sm_count), 256, 0, lc.stream>>>(n, NY + 1, own_first, own_end, fixed, mask);
+    (*launches)++;
     return cudaGetLastError();
 }
 

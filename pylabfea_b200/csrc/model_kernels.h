@@ -2,6 +2,7 @@
 #pragma once
 #include <algorithm>
 #include "plf_host.h"
+#include "plf_comm.h"
 
 namespace plf {
 
@@ -45,6 +46,12 @@ cudaError_t launch_cg(const LaunchCtx &lc, int64_t n, const int32_t *rowptr, con
 cudaError_t launch_spmv(const LaunchCtx &lc, int64_t n, const int32_t *rowptr, const int32_t *col, const double *val, const double *x,
                         const double *rhs, double *y, const unsigned char *masked, int mode, int64_t *launches);
 void cg_graph_reset();   // drops the cached CUDA graph of the CG iteration chunk (call before freeing its buffers)
+cudaError_t launch_cg_dist(const LaunchCtx &lc, Comm &comm, int64_t n, const int32_t *rowptr, const int32_t *col, const double *val,
+                           const unsigned char *mask, const double *b, double *x, double *r, double *z, double *p, double *q,
+                           double *diag, double *partial, unsigned int *counter, void *d_sc, void *h_sc, double rtol,
+                           int max_iter, int check_every, int *iters, double *relres, int64_t *launches, int warm, int NX, int NY);
+cudaError_t launch_ghost_mask(const LaunchCtx &lc, int64_t n, int NY, int own_first, int own_end, const unsigned char *fixed,
+                              unsigned char *mask, int64_t *launches);
 cudaError_t launch_merge_du(const LaunchCtx &lc, int64_t n, const double *x, const double *du_bc, const unsigned char *fixed, double *du,
                             int64_t *launches);
 

@@ -95,6 +95,7 @@ extern "C" void plf_destroy(plf_ctx *ctx)
     for (int i = 0; i < PLF_MAX_MATERIALS; i++) { cudaFree(ctx->d_sv[i]); cudaFree(ctx->d_dual[i]); }
     free_batch_bufs(ctx->scratch);
     model_free(ctx);
+    plf_comm_destroy(ctx);
     cudaFree(ctx->d_flush);
     cudaFree(ctx->d_scalars);
     cudaFreeHost(ctx->h_scalars);

@@ -1,0 +1,187 @@
+// plf_comm.cu -- NCCL plumbing of the strip-partitioned solve and its C-ABI entry points (include/plfb200.h).
+#include <dlfcn.h>
+#include <nccl.h>
+
+#include <cstring>
+#include <string>
+
+#include "plf_comm.h"
+#include "plf_model.h"
+#include "plfb200.h"
+
+namespace plf {
+
+namespace {
+struct NcclApi {
+    void *lib = nullptr;
+    ncclResult_t (*GetUniqueId)(ncclUniqueId *) = nullptr;
+    ncclResult_t (*CommInitRank)(ncclComm_t *, int, ncclUniqueId, int) = nullptr;
+    ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+    ncclResult_t (*AllReduce)(const void *, void *, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*Send)(const void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*Recv)(void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*GroupStart)() = nullptr;
+    ncclResult_t (*GroupEnd)() = nullptr;
+    const char *(*GetErrorString)(ncclResult_t) = nullptr;
+};
+NcclApi g_nccl;
+std::string g_err;
+
+int nccl_fail(const char *what, ncclResult_t r)
+{
+    g_err = std::string(what) + ": " + (g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "NCCL error");
+    return 1;
+}
+#define NC(call, what)                                   \
+    do {                                                 \
+        ncclResult_t r_ = (call);                        \
+        if (r_ != ncclSuccess) return nccl_fail(what, r_); \
+    } while (0)
+}   // namespace
+
+const char *comm_error() { return g_err.c_str(); }
+
+int comm_load()
+{
+    if (g_nccl.lib) return 0;
+    void *h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+    if (!h) h = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+    if (!h) { g_err = std::string("cannot load libnccl.so.2: ") + dlerror(); return 1; }
+    NcclApi a;
+    a.lib = h;
+    bool ok = true;
+    auto sym = [&](const char *name) { void *p = dlsym(h, name); if (!p) { ok = false; g_err = std::string("libnccl lacks ") + name; } return p; };
+    a.GetUniqueId = (decltype(a.GetUniqueId))sym("ncclGetUniqueId");
+    a.CommInitRank = (decltype(a.CommInitRank))sym("ncclCommInitRank");
+    a.CommDestroy = (decltype(a.CommDestroy))sym("ncclCommDestroy");
+    a.AllReduce = (decltype(a.AllReduce))sym("ncclAllReduce");
+    a.Send = (decltype(a.Send))sym("ncclSend");
+    a.Recv = (decltype(a.Recv))sym("ncclRecv");
+    a.GroupStart = (decltype(a.GroupStart))sym("ncclGroupStart");
+    a.GroupEnd = (decltype(a.GroupEnd))sym("ncclGroupEnd");
+    a.GetErrorString = (decltype(a.GetErrorString))sym("ncclGetErrorString");
+    if (!ok) { dlclose(h); return 1; }
+    g_nccl = a;
+    return 0;
+}
+
+int comm_unique_id(unsigned char *id128)
+{
+    if (comm_load()) return 1;
+    static_assert(sizeof(ncclUniqueId) == PLF_COMM_ID_BYTES, "ncclUniqueId size");
+    ncclUniqueId id;
+    NC(g_nccl.GetUniqueId(&id), "ncclGetUniqueId");
+    memcpy(id128, &id, sizeof id);
+    return 0;
+}
+
+int comm_init(Comm &c, const unsigned char *id128, int rank, int world)
+{
+    if (comm_load()) return 1;
+    comm_destroy(c);
+    ncclUniqueId id;
+    memcpy(&id, id128, sizeof id);
+    ncclComm_t comm = nullptr;
+    NC(g_nccl.CommInitRank(&comm, world, id, rank), "ncclCommInitRank");
+    c.nccl = comm;
+    c.rank = rank;
+    c.world = world;
+    c.strip_set = false;
+    return 0;
+}
+
+void comm_destroy(Comm &c)
+{
+    if (c.nccl && g_nccl.CommDestroy) g_nccl.CommDestroy((ncclComm_t)c.nccl);
+    c = Comm();
+}
+
+int comm_allreduce_sum(Comm &c, double *dbuf, int count, cudaStream_t s)
+{
+    NC(g_nccl.AllReduce(dbuf, dbuf, (size_t)count, ncclDouble, ncclSum, (ncclComm_t)c.nccl, s), "ncclAllReduce");
+    return 0;
+}
+
+int comm_halo_exchange(Comm &c, double *vec, int NX, int NY, cudaStream_t s)
+{
+    const bool left = c.ghost_left() && c.rank > 0, right = c.ghost_right(NX) && c.rank + 1 < c.world;
+    if (!left && !right) return 0;
+    const size_t ncol = 2 * (size_t)(NY + 1);   // doubles per node column
+    ncclComm_t comm = (ncclComm_t)c.nccl;
+    NC(g_nccl.GroupStart(), "ncclGroupStart");
+    if (left) {
+        NC(g_nccl.Send(vec + ncol * (size_t)c.own_first, ncol, ncclDouble, c.rank - 1, comm, s), "ncclSend");
+        NC(g_nccl.Recv(vec + ncol * (size_t)(c.own_first - 1), ncol, ncclDouble, c.rank - 1, comm, s), "ncclRecv");
+    }
+    if (right) {
+        NC(g_nccl.Send(vec + ncol * (size_t)(c.own_end - 1), ncol, ncclDouble, c.rank + 1, comm, s), "ncclSend");
+        NC(g_nccl.Recv(vec + ncol * (size_t)c.own_end, ncol, ncclDouble, c.rank + 1, comm, s), "ncclRecv");
+    }
+    NC(g_nccl.GroupEnd(), "ncclGroupEnd");
+    return 0;
+}
+
+}   // namespace plf
+
+using namespace plf;
+
+#define CKC(call)                                                                    \
+    do {                                                                             \
+        cudaError_t e_ = (call);                                                     \
+        if (e_ != cudaSuccess) return fail(ctx, PLF_ECUDA, std::string(#call) + ": " + cudaGetErrorString(e_)); \
+    } while (0)
+
+extern "C" int plf_comm_unique_id(unsigned char *id)
+{
+    if (!id) return PLF_EINVAL;
+    return comm_unique_id(id) ? PLF_EUNSUPPORTED : PLF_OK;
+}
+
+extern "C" int plf_comm_init(plf_ctx *ctx, const unsigned char *id, int rank, int world)
+{
+    if (!ctx) return PLF_EINVAL;
+    if (!id || world < 1 || rank < 0 || rank >= world) return fail(ctx, PLF_EINVAL, "plf_comm_init: need 0 <= rank < world and an id");
+    CKC(cudaSetDevice(ctx->device));
+    if (!ctx->comm) ctx->comm = new Comm();
+    if (comm_init(*ctx->comm, id, rank, world)) return fail(ctx, PLF_EUNSUPPORTED, std::string("plf_comm_init: ") + comm_error());
+    return PLF_OK;
+}
+
+extern "C" int plf_comm_set_strip(plf_ctx *ctx, int own_first, int own_end)
+{
+    if (!ctx) return PLF_EINVAL;
+    if (!ctx->comm || !ctx->comm->active()) return fail(ctx, PLF_ESTATE, "plf_comm_set_strip: call plf_comm_init first");
+    if (!ctx->mesh_ready) return fail(ctx, PLF_ESTATE, "plf_comm_set_strip: call plf_mesh_structured first");
+    const Comm &c = *ctx->comm;
+    // one ghost node column at most on either side; the outer ranks own their outer boundary column
+    const bool ok = (own_first == 0 || own_first == 1) && (own_end == ctx->NX || own_end == ctx->NX + 1) && own_first < own_end &&
+                    (own_first == 1) == (c.rank > 0) && (own_end == ctx->NX) == (c.rank + 1 < c.world);
+    if (!ok)
+        return fail(ctx, PLF_EINVAL, "plf_comm_set_strip: owned node columns must be [halo, NX + last) with halo = (rank > 0), "
+                                     "last = (rank == world - 1)");
+    ctx->comm->own_first = own_first;
+    ctx->comm->own_end = own_end;
+    ctx->comm->strip_set = true;
+    return PLF_OK;
+}
+
+extern "C" int plf_comm_allreduce(plf_ctx *ctx, double *vals, int n)
+{
+    if (!ctx) return PLF_EINVAL;
+    if (!ctx->comm || !ctx->comm->active()) return fail(ctx, PLF_ESTATE, "plf_comm_allreduce: call plf_comm_init first");
+    if (!vals || n < 1 || n > 64) return fail(ctx, PLF_EINVAL, "plf_comm_allreduce: 1 <= n <= 64 values");
+    CKC(cudaSetDevice(ctx->device));
+    double *d = reinterpret_cast<double *>(ctx->d_scalars + 1024);   // scratch slot of the 4 KB scalar page
+    CKC(cudaMemcpyAsync(d, vals, n * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    if (comm_allreduce_sum(*ctx->comm, d, n, ctx->stream)) return fail(ctx, PLF_ECUDA, std::string("plf_comm_allreduce: ") + comm_error());
+    CKC(cudaMemcpyAsync(vals, d, n * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    CKC(cudaStreamSynchronize(ctx->stream));
+    return PLF_OK;
+}
+
+extern "C" int plf_comm_destroy(plf_ctx *ctx)
+{
+    if (!ctx) return PLF_EINVAL;
+    if (ctx->comm) { comm_destroy(*ctx->comm); delete ctx->comm; ctx->comm = nullptr; }
+    return PLF_OK;
+}

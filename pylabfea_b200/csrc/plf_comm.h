@@ -1,0 +1,31 @@
+// plf_comm.h -- the exchange step of the strip-partitioned solve: one NCCL communicator per context,
+// one halo node column per neighbour and CG iteration, scalar all-reduces for the dot products.  NCCL is loaded with
+// dlopen on first use so that the library itself has no link-time dependency on it (single-GPU users, CPU build check).
+#pragma once
+#include <cuda_runtime.h>
+
+namespace plf {
+
+struct Comm {
+    void *nccl = nullptr;   // ncclComm_t
+    int rank = 0, world = 1;
+    // owned node columns [own_first, own_end) of the local mesh; a ghost column is the one column outside on either side
+    int own_first = 0, own_end = 0;
+    bool strip_set = false;
+    bool active() const { return nccl != nullptr; }
+    bool ghost_left() const { return own_first > 0; }
+    bool ghost_right(int NX) const { return own_end < NX + 1; }
+};
+
+// all return 0 on success; the message of the last failure is in comm_error()
+int comm_load();                                            // dlopen libnccl.so.2 and resolve the entry points
+int comm_unique_id(unsigned char *id128);                   // ncclGetUniqueId (128 bytes)
+int comm_init(Comm &c, const unsigned char *id128, int rank, int world);
+void comm_destroy(Comm &c);
+int comm_allreduce_sum(Comm &c, double *dbuf, int count, cudaStream_t s);   // in place, device pointer
+// vec: nodal vector of the local (NX+1) x (NY+1) node grid, 2 dofs per node.  Sends the first / last owned node column to
+// the left / right neighbour and receives their last / first owned column into the ghost columns.
+int comm_halo_exchange(Comm &c, double *vec, int NX, int NY, cudaStream_t s);
+const char *comm_error();
+
+}   // namespace plf

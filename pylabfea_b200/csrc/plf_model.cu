@@ -10,6 +10,7 @@
 
 #include "model_kernels.h"
 #include "mg.h"
+#include "plf_comm.h"
 #include "plf_device.cuh"
 #include "plf_host.h"
 #include "plf_model.h"
@@ -50,7 +51,8 @@ void model_free(plf_ctx *c)
     cudaFree(c->d_has_res); cudaFree(c->d_u); cudaFree(c->d_du); cudaFree(c->d_f); cudaFree(c->d_rowptr); cudaFree(c->d_col);
     cudaFree(c->d_val); cudaFree(c->d_worklist); cudaFree(c->d_r); cudaFree(c->d_z); cudaFree(c->d_p); cudaFree(c->d_q);
     cudaFree(c->d_b); cudaFree(c->d_diag); cudaFree(c->d_w); cudaFree(c->d_fixed); cudaFree(c->d_partial);
-    cudaFree(c->d_bc_du); cudaFree(c->d_bc_f);
+    cudaFree(c->d_bc_du); cudaFree(c->d_bc_f); cudaFree(c->d_cgmask); c->d_cgmask = nullptr;
+    if (c->comm) c->comm->strip_set = false;   // a new mesh needs a new plf_comm_set_strip
     c->d_bc_du = c->d_bc_f = nullptr; c->bc_valid = false;
     c->d_desc = nullptr; c->d_elstiff = c->d_sig = c->d_eps = c->d_epl = c->d_res_sig = c->d_res_depl = c->d_fyld = nullptr;
     c->d_nsteps = c->d_branch = nullptr; c->d_has_res = nullptr; c->d_u = c->d_du = c->d_f = nullptr;
@@ -534,11 +536,39 @@ extern "C" int plf_solve_linear(plf_ctx *ctx, const uint8_t *fixed, const double
         CK(cudaMemcpyAsync(ctx->d_bc_du, du_bc, D * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
         ctx->bc_valid = true;
     }
+    const bool dist = ctx->comm && ctx->comm->active();
+    if (dist && !ctx->comm->strip_set) return fail(ctx, PLF_ESTATE, "plf_solve_linear: call plf_comm_set_strip after plf_mesh_structured");
+    const unsigned char *mask = ctx->d_fixed;
+    if (dist) {
+        // rows of node columns owned by a neighbour are not this rank's equations (and incomplete here): masked like fixed dofs
+        if (!ctx->d_cgmask && (rc = dalloc(ctx, &ctx->d_cgmask, D))) return rc;
+        CK(launch_ghost_mask(lc, ctx->Ndof, ctx->NY, ctx->comm->own_first, ctx->comm->own_end, ctx->d_fixed, ctx->d_cgmask, &ctx->launches));
+        mask = ctx->d_cgmask;
+    }
     // b = f_ext - K w on the free dofs (calc_BC, model.py:1099-1205)
-    CK(launch_spmv(lc, ctx->Ndof, ctx->d_rowptr, ctx->d_col, ctx->d_val, ctx->d_w, ctx->d_bc_f, ctx->d_b, ctx->d_fixed, 2, &ctx->launches));
+    CK(launch_spmv(lc, ctx->Ndof, ctx->d_rowptr, ctx->d_col, ctx->d_val, ctx->d_w, ctx->d_bc_f, ctx->d_b, mask, 2, &ctx->launches));
     int it = 0;
     double rr = 0.;
     double *x = ctx->d_du;   // CG iterate lives in du; fixed dofs are merged at the end
+    if (dist) {
+        cudaError_t ce = launch_cg_dist(lc, *ctx->comm, ctx->Ndof, ctx->d_rowptr, ctx->d_col, ctx->d_val, mask, ctx->d_b, x, ctx->d_r,
+                                        ctx->d_z, ctx->d_p, ctx->d_q, ctx->d_diag, ctx->d_partial, counter_ptr(ctx), ctx->d_scalars + 256,
+                                        ctx->h_scalars + 256, rtol, max_iter, 50, &it, &rr, &ctx->launches, ctx->solver_warm, ctx->NX,
+                                        ctx->NY);
+        if (ce != cudaSuccess)
+            return fail(ctx, PLF_ECUDA, std::string("plf_solve_linear (distributed): ") +
+                                            (ce == cudaErrorUnknown && comm_error()[0] ? comm_error() : cudaGetErrorString(ce)));
+        CK(launch_merge_du(lc, ctx->Ndof, x, ctx->d_bc_du, ctx->d_fixed, ctx->d_du, &ctx->launches));
+        if (comm_halo_exchange(*ctx->comm, ctx->d_du, ctx->NX, ctx->NY, ctx->stream))   // ghost columns of du from their owners
+            return fail(ctx, PLF_ECUDA, std::string("plf_solve_linear (distributed): ") + comm_error());
+        CK(cudaStreamSynchronize(ctx->stream));
+        if (iters) *iters = it;
+        if (relres) *relres = rr;
+        if (!(rr <= rtol))
+            return fail(ctx, PLF_ENOCONV, "plf_solve_linear: distributed CG stopped after " + std::to_string(it) +
+                                              " iterations with relative residual " + std::to_string(rr));
+        return PLF_OK;
+    }
     // multigrid V-cycle preconditioner when the mesh coarsens at least once (mesh-independent iteration counts), else Jacobi
     const bool use_mg = ctx->solver_mg && ctx->mg && ctx->mg->levels() >= 2;
     CK(launch_cg(lc, ctx->Ndof, ctx->d_rowptr, ctx->d_col, ctx->d_val, ctx->d_fixed, ctx->d_b, x, ctx->d_r, ctx->d_z, ctx->d_p, ctx->d_q,

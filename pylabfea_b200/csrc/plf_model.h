@@ -7,7 +7,7 @@
 #include "plf_host.h"
 
 // device buffers of one batch of independent stress updates (AoS records, see DESIGN.md "data layout")
-namespace plf { struct MgHierarchy; }
+namespace plf { struct MgHierarchy; struct Comm; }
 
 struct plf_batch {
     int64_t n = 0, cap = 0;
@@ -80,6 +80,8 @@ struct plf_ctx {
     int solver_warm = 1;              // CG starts from the previous du (0: from zero)
     int mg_nu = 2, mg_coarse_sweeps = 10;   // smoothing sweeps per level (even) / on the coarsest level
     double mg_omega = 0.7;            // Jacobi damping
+    plf::Comm *comm = nullptr;       // NCCL communicator + strip neighbourhood (plf_comm.cu); nullptr: single GPU
+    unsigned char *d_cgmask = nullptr;   // fixed | ghost-column mask of the distributed CG
     double *d_partial = nullptr;   // block partial sums
     int n_partial = 0;
 };

@@ -27,3 +27,40 @@ def local_element_ids(shard, NY):
     """Global element ids (e = j*NY + k) of the rank's local mesh, in local element order (halo column first)."""
     first, nx = shard['first_col_global'], shard['nx_local']
     return [j * NY + k for j in range(first, first + nx) for k in range(NY)]
+
+
+def slice_node_vector(vec, shard, NY, ncomp=2):
+    """Entries of a global nodal vector (node id j*(NY+1)+k, `ncomp` values per node: Model.u / f and the calc_BC vectors)
+    that belong to the rank's local node grid -- halo and ghost columns included, which is what plf_solve_linear wants on
+    a rank of a distributed solve.  Node columns are contiguous, so this is a view."""
+    first, nx = shard['first_col_global'], shard['nx_local']
+    w = ncomp * (NY + 1)
+    return vec[first * w:(first + nx + 1) * w]
+
+
+def owned_slice(shard, NY, ncomp=2):
+    """Index range, inside the rank's local nodal vector, of the node columns it owns."""
+    cols = shard['owned_node_cols_local']
+    w = ncomp * (NY + 1)
+    return slice(cols[0] * w, (cols[-1] + 1) * w)
+
+
+def share_bytes(path, rank, payload=None, timeout=120.):
+    """Side channel for the NCCL unique id when no launcher-provided store is at hand: rank 0 writes `payload` to `path`
+    (atomically, via rename), the other ranks wait for the file and read it.  All ranks of one job must use the same path
+    (e.g. derived from MASTER_PORT) on a file system they share."""
+    import os
+    import time
+    if rank == 0:
+        tmp = '%s.tmp.%d' % (path, os.getpid())
+        with open(tmp, 'wb') as f:
+            f.write(payload)
+        os.replace(tmp, path)
+        return payload
+    t0 = time.time()
+    while not os.path.exists(path):
+        if time.time() - t0 > timeout:
+            raise TimeoutError('share_bytes: %s did not appear within %g s' % (path, timeout))
+        time.sleep(0.02)
+    with open(path, 'rb') as f:
+        return f.read()

@@ -66,3 +66,45 @@ def test_strip_shards_partition_the_mesh_exactly():
         assert elem_cols == list(range(NX)) and node_cols == list(range(NX + 1))
     with pytest.raises(ValueError):
         strip_shard(4, 0, 5)
+
+
+def test_nodal_vector_slices_of_the_strips_reassemble_the_global_vector():
+    """What every rank of a distributed solve passes to plf_solve_linear: the slice of the global calc_BC vectors on its
+    local node grid (ghost columns included); the owned parts of all ranks tile the global vector exactly once."""
+    import numpy as np
+    sys.path.insert(0, ROOT)
+    from pylabfea_b200.shard import strip_shard, slice_node_vector, owned_slice
+    for NX, NY, world in ((12, 3, 4), (37, 5, 3), (8, 2, 1)):
+        v = np.arange(2 * (NX + 1) * (NY + 1), dtype=float)
+        parts = []
+        for r in range(world):
+            s = strip_shard(NX, r, world)
+            loc = slice_node_vector(v, s, NY)
+            assert len(loc) == 2 * (s['nx_local'] + 1) * (NY + 1)
+            assert loc[0] == v[2 * s['first_col_global'] * (NY + 1)]
+            parts.append(loc[owned_slice(s, NY)])
+            # ghost columns: column 0 on ranks with a left neighbour, the last column on ranks with a right neighbour
+            cols = s['owned_node_cols_local']
+            assert cols[0] == (1 if r > 0 else 0) and cols[-1] == s['nx_local'] - (1 if r < world - 1 else 0)
+        assert np.array_equal(np.concatenate(parts), v)
+
+
+def test_unique_id_side_channel(tmp_path):
+    """share_bytes: rank 0 publishes the NCCL unique id through a file, another process picks it up."""
+    sys.path.insert(0, ROOT)
+    from pylabfea_b200 import _lib
+    from pylabfea_b200.shard import share_bytes
+    try:
+        uid = _lib.comm_unique_id()
+    except _lib.PlfError as e:      # image without libnccl.so.2
+        pytest.skip(str(e))
+    assert len(uid) == _lib.COMM_ID_BYTES and uid != bytes(_lib.COMM_ID_BYTES)
+    path = str(tmp_path / 'id')
+    reader = subprocess.Popen([sys.executable, '-c', 'import sys; sys.path.insert(0, %r)\n'
+                               'from pylabfea_b200.shard import share_bytes\n'
+                               'sys.stdout.buffer.write(share_bytes(%r, 1, timeout=30.))' % (ROOT, path)], stdout=subprocess.PIPE)
+    assert share_bytes(path, 0, uid) == uid
+    out, _ = reader.communicate(timeout=60)
+    assert reader.returncode == 0 and out == uid
+    with pytest.raises(TimeoutError):
+        share_bytes(str(tmp_path / 'missing'), 1, timeout=0.1)

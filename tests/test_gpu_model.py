@@ -353,6 +353,38 @@ def test_multigrid_and_jacobi_cg_agree_and_mg_is_mesh_independent():
     assert its_mg.max() <= 60 and its_j.mean() > 4 * its_mg.mean()
 
 
+def test_distributed_cg_path_with_one_rank_equals_the_single_gpu_jacobi_cg():
+    """plf_solve_linear on a context with a communicator (plf_comm_*, NCCL) runs the strip-partitioned CG: halo exchange,
+    all-reduced dot products, ghost-column mask.  With one rank owning every node column it must reproduce the
+    single-GPU Jacobi-preconditioned CG step by step (same kernels, same summation order) through a whole plastic load
+    sequence.  The 2-GPU check against the global solve is scripts/dist_solve.py (profiles/r1_dist_solve_2gpu.json)."""
+    from pylabfea_b200 import _lib
+    runs = {}
+    for dist in (0, 1):
+        fe = inclusion(24, plastic=True, eps_tot=0.004)
+        ctx = fe._dev()
+        ctx.set_option('solver_mg', 0)
+        if dist:
+            with pytest.raises(AttributeError):
+                ctx.comm_set_strip(0, 25)                  # no communicator yet
+            ctx.comm_init(_lib.comm_unique_id(), 0, 1)
+            with pytest.raises(ValueError):
+                ctx.comm_set_strip(1, 25)                  # rank 0 has no left neighbour
+            ctx.setupK()
+            with pytest.raises(AttributeError):
+                ctx.solve_linear(np.zeros(fe.Ndof, np.uint8), np.zeros(fe.Ndof), np.zeros(fe.Ndof), np.zeros(fe.Ndof))
+            ctx.comm_set_strip(0, 25)
+            assert list(ctx.comm_allreduce([3., 4.5])) == [3., 4.5]
+        fe.solver_rtol = 1.e-12
+        fe.solve(min_step=4)
+        runs[dist] = fe
+    a, b = runs[1], runs[0]
+    assert a.nsteps == b.nsteps and list(a.niter) == list(b.niter)
+    assert [s[0] for s in a.solver_stats] == [s[0] for s in b.solver_stats]
+    assert relmax(a.u, b.u) < 1e-13
+    assert relmax(np.array([el.sig for el in a.element]), np.array([el.sig for el in b.element])) < 1e-12
+
+
 def test_from_MLparam_yield_function_matches_reference(golden):
     """A model exported by the reference (export_MLparam) and loaded with Material.from_MLparam evaluates the same
     yield function as the reference material it came from (calc_yf on 200 stresses)."""
