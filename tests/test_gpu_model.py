@@ -5,6 +5,8 @@
 Tolerances: linear models: u within 1e-9 relative (the reference solves with dense LU, this path with CG);
 plastic models: stress / plastic strain / PEEQ within 1e-6 relative (BASELINE.json north_star), same number of
 increments and of inner passes."""
+import os
+
 import numpy as np
 import pytest
 
@@ -353,6 +355,10 @@ def test_multigrid_and_jacobi_cg_agree_and_mg_is_mesh_independent():
     assert its_mg.max() <= 60 and its_j.mean() > 4 * its_mg.mean()
 
 
+@pytest.mark.skipif(os.environ.get('PLF_TEST_NCCL') != '1',
+                    reason='opt-in (PLF_TEST_NCCL=1): the first ncclCommInitRank on a fresh box pages in the 411 MB libnccl.so.2, '
+                           'about 3 minutes of the measured 193 s for the whole suite; run and passed on 2 x B200, see '
+                           'profiles/r1_dist_solve_2gpu.json')
 def test_distributed_cg_path_with_one_rank_equals_the_single_gpu_jacobi_cg():
     """plf_solve_linear on a context with a communicator (plf_comm_*, NCCL) runs the strip-partitioned CG: halo exchange,
     all-reduced dot products, ghost-column mask.  With one rank owning every node column it must reproduce the
