@@ -47,7 +47,9 @@ typedef enum plf_mat_kind {
     PLF_MAT_HILL = 1,    /* sdim=6 Hill-6p equivalent stress; J2 is hill = 1 (material.py:653-661)  */
     PLF_MAT_SVC = 2,     /* ML_yf: RBF support-vector yield function, sdim=6 (material.py:398-405)  */
     PLF_MAT_BARLAT = 3,  /* Yld2004-18p equivalent stress (material.py:678-702)                     */
-    PLF_MAT_HILL3 = 4    /* sdim=3: 3-parameter Hill / J2 on ordered principal stresses (663-673)   */
+    PLF_MAT_HILL3 = 4,   /* sdim=3: 3-parameter Hill / J2 on ordered principal stresses (663-673)   */
+    PLF_MAT_SVC3 = 5     /* ML_yf, sdim=3: SVC on (seq_J2/scale-1, polar angle/pi) of the principal stresses
+                            (material.py:2331-2334, gradient 780-805); svc_sv rows: 6 columns, 2..5 zero */
 } plf_mat_kind;
 
 /* What Material.elasticity / Material.plasticity / train_SVC leave on a Material object

@@ -12,7 +12,7 @@ import numpy as np
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB = os.path.join(HERE, 'libplf_oracle.so')
 
-ELASTIC, HILL, SVC, BARLAT, HILL3 = 0, 1, 2, 3, 4
+ELASTIC, HILL, SVC, BARLAT, HILL3, SVC3 = 0, 1, 2, 3, 4, 5
 
 _dp = C.POINTER(C.c_double)
 _ip = C.POINTER(C.c_int32)
@@ -76,7 +76,10 @@ class Mat:
             m.d[:] = [drucker * 1.0] * 3
         m.tresca = int(tresca)
         if svc is not None:
-            self._sv = _a(svc['sv'])
+            sv = np.atleast_2d(np.asarray(svc['sv'], dtype=float))
+            if sv.shape[1] < 6:   # sdim = 3 models have 2 features: the table always has 6 columns, the rest zero
+                sv = np.hstack([sv, np.zeros((len(sv), 6 - sv.shape[1]))])
+            self._sv = _a(sv)
             self._dual = _a(svc['dual'])
             m.nsv = len(self._dual)
             m.sv = _p(self._sv)
@@ -93,7 +96,7 @@ class Mat:
     def from_golden(cls, g):
         """From a tests/golden/response_*.npz or svc_*.npz dict."""
         if 'sv' in g:
-            return cls(kind=SVC, E=float(g['E']), nu=float(g['nu']), sy=float(g['sy']), khard=0.,
+            return cls(kind=SVC3 if int(g['sdim']) == 3 else SVC, E=float(g['E']), nu=float(g['nu']), sy=float(g['sy']), khard=0.,
                        hill=g['hill'], drucker=float(g['drucker']),
                        svc=dict(sv=g['sv'], dual=g['dual'], gamma=g['gamma'], rho=g['rho'],
                                 scale_seq=g['scale_seq'], dev_only=int(g['dev_only'])))

@@ -9,7 +9,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, 'libplfb200.so')
 
 PLF_OK, PLF_EINVAL, PLF_ECUDA, PLF_ESTATE, PLF_EUNSUPPORTED, PLF_ENOCONV = 0, -1, -2, -3, -4, -5
-MAT_ELASTIC, MAT_HILL, MAT_SVC, MAT_BARLAT, MAT_HILL3 = 0, 1, 2, 3, 4
+MAT_ELASTIC, MAT_HILL, MAT_SVC, MAT_BARLAT, MAT_HILL3, MAT_SVC3 = 0, 1, 2, 3, 4, 5
 (F_SIG, F_EPS, F_EPL, F_RES_SIG, F_RES_DEPL, F_U, F_DU, F_F, F_FYLD, F_NSTEPS) = range(10)
 
 _dp = C.POINTER(C.c_double)

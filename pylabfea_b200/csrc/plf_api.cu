@@ -234,8 +234,10 @@ extern "C" int plf_set_materials(plf_ctx *ctx, int nmat, const plf_material *mat
         const plf_material &m = mats[i];
         DevMat &d = ctx->hmats[i];
         memset(&d, 0, sizeof d);
-        if (m.kind < PLF_MAT_ELASTIC || m.kind > PLF_MAT_HILL3) return fail(ctx, PLF_EINVAL, "plf_set_materials: unknown kind");
-        d.kind = m.kind;
+        if (m.kind < PLF_MAT_ELASTIC || m.kind > PLF_MAT_SVC3) return fail(ctx, PLF_EINVAL, "plf_set_materials: unknown kind");
+        // the sdim = 3 SVC runs on the SVC kernels with another feature map / gradient / equivalent stress (SvcModel, svc_princ)
+        d.kind = (m.kind == PLF_MAT_SVC3) ? PLF_MAT_SVC : m.kind;
+        d.svc_princ = (m.kind == PLF_MAT_SVC3) ? 1 : 0;
         d.tresca = m.tresca;
         d.lhs = m.lhs;
         d.dev_only = m.dev_only;
@@ -268,7 +270,7 @@ extern "C" int plf_set_materials(plf_ctx *ctx, int nmat, const plf_material *mat
         memcpy(d.bar_m1, m.barlat_m1, sizeof d.bar_m1);
         memcpy(d.bar_m2, m.barlat_m2, sizeof d.bar_m2);
         d.bar_exp = m.barlat_exp;
-        if (m.kind == PLF_MAT_SVC) {
+        if (m.kind == PLF_MAT_SVC || m.kind == PLF_MAT_SVC3) {
             if (m.nsv < 1 || !m.svc_sv || !m.svc_dual) return fail(ctx, PLF_EINVAL, "plf_set_materials: SVC table missing");
             const int np = (m.nsv + 31) / 32 * 32;
             if ((size_t)np * 7 * sizeof(double) > 227 * 1024)

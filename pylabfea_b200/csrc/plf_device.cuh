@@ -18,6 +18,7 @@ struct DevMat {
     int32_t has_d;      // any Drucker / LHS weight non-zero
     int32_t cv_sym;     // CV is exactly symmetric: (CV a) . deps == a . (CV deps)
     int32_t cv_iso;     // cv_block && cv_sym && C11 - C12 == 2 C44 (to 1e-13): isotropic elasticity, plane strain / 3-d
+    int32_t svc_princ;  // SVC trained on (seq_J2, polar angle) of the principal stresses: the sdim = 3 ML yield function
     double sy, khard;
     double hill[6];
     double d[3];     // I1 weights (calc_seq 645-650)
@@ -384,10 +385,34 @@ struct SvcModel {
         : m(mm), s_sv(sv), s_dual(dual), lane(l) {}
     // material.py:812-814: without work-hardening features every gradient call resets khard to 0
     __device__ __forceinline__ double khard() const { return 0.; }
-    __device__ __forceinline__ double seq(const double *s) const { return hill_seq(m, s); }
+    // sdim = 3 (svc_princ): calc_seq is the 3-parameter form on the ordered principal stresses (material.py:663-673)
+    __device__ __forceinline__ double seq(const double *s) const { return m.svc_princ ? HillPrincModel(m).seq(s) : hill_seq(m, s); }
+
+    // create_scaled_input, sdim = 3 (material.py:2331-2334): (sig_eq_j2 / scale_seq - 1, sig_polar_ang / pi) of the
+    // principal stresses (basic.py:30-104; a_vec, b_vec of basic.py:20-23); table columns 2..5 are zero
+    __device__ __forceinline__ void features_sp(const double *sp, double *x) const
+    {
+        const double d12 = sp[0] - sp[1], d23 = sp[1] - sp[2], d31 = sp[2] - sp[0];
+        x[0] = sqrt(0.5 * (d12 * d12 + d23 * d23 + d31 * d31)) / m.scale_seq - 1.;
+        const double hyd = (sp[0] + sp[1] + sp[2]) / 3.;
+        const double dv[3] = {sp[0] - hyd, sp[1] - hyd, sp[2] - hyd};
+        double vn = sqrt(dv[0] * dv[0] + dv[1] * dv[1] + dv[2] * dv[2]);
+        if (vn < 1.e-4) vn = 1.;
+        const double r15 = sqrt(1.5), r2 = sqrt(2.);
+        const double dsa = dv[0] / vn * (1. / r15) + dv[1] / vn * (-0.5 / r15) + dv[2] / vn * (-0.5 / r15);
+        const double dsb = dv[1] / vn * (0.5 * r2) + dv[2] / vn * (-0.5 * r2);
+        x[1] = atan2(dsb, dsa) / 3.141592653589793;
+        x[2] = x[3] = x[4] = x[5] = 0.;
+    }
 
     __device__ __forceinline__ void features(const double *s, double *x) const
     {
+        if (m.svc_princ) {   // a Voigt stress goes through sig_princ first (basic.py:49-52, 86-89)
+            double sp[3];
+            princ_ordered(s, sp);
+            features_sp(sp, x);
+            return;
+        }
         // create_scaled_input, sdim = 6 (material.py:2336-2340)
         double p = m.dev_only ? (s[0] + s[1] + s[2]) / 3. : 0.;
         x[0] = (s[0] - p) / m.scale_seq; x[1] = (s[1] - p) / m.scale_seq; x[2] = (s[2] - p) / m.scale_seq;
@@ -418,6 +443,7 @@ struct SvcModel {
     // gradient of the decision function w.r.t. stress (material.py:768-778, 802-807)
     __device__ __forceinline__ void fgrad(const double *s, double *a) const
     {
+        if (m.svc_princ) { fgrad_princ(s, a); return; }
         const int np = m.nsv_pad;
         double x[6], g[6] = {0., 0., 0., 0., 0., 0.};
         features(s, x);
@@ -436,6 +462,40 @@ struct SvcModel {
         for (int k = 0; k < 6; k++) a[k] = warp_sum(g[k]) / m.scale_seq;
     }
 
+    // sdim = 3 (material.py:780-805, called with sig_princ(sig)[0] by epl_dot / C_tan, 1045-1048, 1078-1080):
+    // fgrad = Jac(sp) @ [1, dK/dx[1], 0] -- the first entry is the constant 1 of the reference, not dK/dx[0].  Jacobian
+    // columns: d seq / d sp = 3 dev / vn with vn = sqrt(1.5) |dev|, and Re(-i ((a + i b) / (sp.a + i sp.b) - dseqds / vn)) =
+    // (b (sp.a) - a (sp.b)) / |sp.a + i sp.b|^2; the all-ones matrix when vn <= 0.1.  Shear components of the flow
+    // direction are zero.
+    __device__ __forceinline__ void fgrad_princ(const double *s, double *a) const
+    {
+        const int np = m.nsv_pad;
+        double sp[3], x[6], g1 = 0.;
+        princ_ordered(s, sp);
+        features_sp(sp, x);
+        for (int i = lane; i < np; i += 32) {
+            const double t0 = x[0] - s_sv[i], t1 = x[1] - s_sv[np + i];
+            const double r = fma(t1, t1, t0 * t0);
+            g1 = fma(s_dual[i] * exp(-m.gamma * r) * (-2. * m.gamma), t1, g1);
+        }
+        g1 = warp_sum(g1);
+        const double hyd = (sp[0] + sp[1] + sp[2]) / 3.;
+        const double dv[3] = {sp[0] - hyd, sp[1] - hyd, sp[2] - hyd};
+        const double vn = sqrt(dv[0] * dv[0] + dv[1] * dv[1] + dv[2] * dv[2]) * sqrt(1.5);
+        if (vn > 0.1) {
+            const double r15 = sqrt(1.5), r2 = sqrt(2.);
+            const double av[3] = {1. / r15, -0.5 / r15, -0.5 / r15}, bv[3] = {0., 0.5 * r2, -0.5 * r2};
+            const double dsa = sp[0] * av[0] + sp[1] * av[1] + sp[2] * av[2];
+            const double dsb = sp[0] * bv[0] + sp[1] * bv[1] + sp[2] * bv[2];
+            const double n2 = dsa * dsa + dsb * dsb;
+#pragma unroll
+            for (int k = 0; k < 3; k++) a[k] = 3. * dv[k] / vn + ((bv[k] * dsa - av[k] * dsb) / n2) * g1;
+        } else {
+            a[0] = a[1] = a[2] = 1. + g1;
+        }
+        a[3] = a[4] = a[5] = 0.;
+    }
+
     // find_yloc_scalar (material.py:547-574)
     __device__ __forceinline__ double yloc(double xs, const double *xu) const
     {
@@ -448,7 +508,7 @@ struct SvcModel {
     // ML_full_yf (material.py:414-516).  ld == nullptr: loading direction = sig / seq.
     __device__ double ml_full_yf(const double *sig, double sflow, const double *ld) const
     {
-        double seq = hill_seq(m, sig);
+        double seq = this->seq(sig);
         if (seq < 0.01 && ld == nullptr) return seq - 0.85 * sflow;
         double su[6];
         if (ld == nullptr) {
@@ -524,7 +584,7 @@ struct SvcModel {
             }
             if (!conv) xs = xcur;
         }
-        if (conv && xs < 4. * sflow) return seq - xs * hill_seq(m, su);
+        if (conv && xs < 4. * sflow) return seq - xs * this->seq(su);
         return seq - 0.85 * sflow;
     }
     __device__ __forceinline__ double full_yf(const double *s, double sflow) const { return ml_full_yf(s, sflow, nullptr); }

@@ -180,19 +180,24 @@ class Material(object):
         material.py:1109-1278): sklearn's svm_yf.support_vectors_ (nsv,6), dual_coef_[0], intercept_[0], gamma and the
         feature scale scale_seq (= sy when no microstructure data is attached, 1160-1161)."""
         sv = np.ascontiguousarray(support_vectors, dtype=float)
-        if sv.ndim != 2 or sv.shape[1] != 6:
-            raise ValueError('set_svc: support vectors must have shape (nsv, 6) (sdim = 6 features)')
+        if self.sy is None:
+            raise ValueError('set_svc: call plasticity(sy=...) first (train_SVC does so, material.py:1606)')
+        nfeat = 6 if self.sdim == 6 else 2
+        if sv.ndim != 2 or sv.shape[1] != nfeat:
+            raise ValueError('set_svc: support vectors must have shape (nsv, %d) for sdim = %d (features: %s)'
+                             % (nfeat, self.sdim, 'scaled Voigt stress' if nfeat == 6 else 'seq_J2 / scale_seq - 1, polar angle / pi'))
+        if nfeat == 2:
+            # sdim = 3 (setup_yf_SVM_3D, material.py:1280-1400): the device table always has 6 columns, the rest zero
+            sv = np.ascontiguousarray(np.hstack([sv, np.zeros((len(sv), 4))]))
         dc = np.ascontiguousarray(np.ravel(dual_coef), dtype=float)
         if len(dc) != len(sv):
             raise ValueError('set_svc: dual_coef must have one entry per support vector')
-        if self.sy is None:
-            raise ValueError('set_svc: call plasticity(sy=...) first (train_SVC does so, material.py:1606)')
         self._svc = (sv, dc, float(intercept))
         self.gam_yf = float(gamma)
         self.scale_seq = float(self.sy if scale_seq is None else scale_seq)
         self.dev_only = bool(dev_only)
         self.ML_yf = True
-        self.Ndof = 6
+        self.Ndof = nfeat
         self.khard = 0.   # material.py:812-814: the SVC gradient resets khard when there are no hardening features
 
     @classmethod
@@ -294,9 +299,8 @@ class Material(object):
             d.kind = _lib.MAT_ELASTIC
             d.hill[:] = [1.] * 6
         else:
-            if self.sdim != 6 and (self.ML_yf or self.barlat):
-                raise NotImplementedError('Material %s: sdim = 3 is supported for the analytic Hill-3p / J2 / Tresca '
-                                          'formulation only (no ML or Barlat yield function)' % self.name)
+            if self.sdim != 6 and self.barlat:
+                raise NotImplementedError('Material %s: the Barlat yield function needs sdim = 6' % self.name)
             d.sy, d.khard = float(self.sy), float(self.khard)
             d.hill[:] = ([float(x) for x in self.hill] + [1., 1., 1.])[:6]
             d.tresca = int(bool(self.tresca))
@@ -307,7 +311,7 @@ class Material(object):
                 d.d[:] = [float(self.drucker)] * 3
             if self.ML_yf:
                 sv, dc, rho = self._svc
-                d.kind = _lib.MAT_SVC
+                d.kind = _lib.MAT_SVC if self.sdim == 6 else _lib.MAT_SVC3
                 d.nsv = len(dc)
                 d.svc_sv = sv.ctypes.data_as(_lib._dp)
                 d.svc_dual = dc.ctypes.data_as(_lib._dp)

@@ -692,10 +692,82 @@ def gen_sdim3():
     print(f'sdim3 fixtures {time.time() - t0:.1f}s; fem2 glob epl[1] = {fem2.glob["epl"][1]} (tests/test_basic.py:17: 0.04966042764325635)')
 
 
+def gen_svc3():
+    """sdim = 3 machine-learned yield function (tests/test_ml.py:10-34, test_ml_plasticity): an SVC trained by the
+    reference in cylindrical principal-stress coordinates (setup_yf_SVM_3D, material.py:1280-1400; features
+    create_scaled_input 2331-2334; gradient through the Jacobian of calc_fgrad 780-805), its yield function / gradient /
+    ML_full_yf / response on seeded shear-free states, and the stress-strain data of calc_properties (3091-3166) that the
+    reference test pins."""
+    t0 = time.time()
+    E, nu, sy = 200.e3, 0.3, 150.
+    mat_h = FE.Material(name='anisotropic Hill')
+    mat_h.elasticity(E=E, nu=nu)
+    mat_h.plasticity(sy=sy, hill=[0.7, 1., 1.4], drucker=0., khard=0., sdim=3)
+    m = FE.Material(name='ML flow rule')
+    m.elasticity(E=E, nu=nu)
+    m.plasticity(sy=sy, sdim=3)
+    x_train, y_train = m.create_sig_data(36, mat_ref=mat_h, extend=True)
+    train_sc, test_sc = m.setup_yf_SVM_3D(x_train, y_train, C=10, gamma=4., fs=0.3)
+    out = svc_arrays(m)
+    out['train_score'] = float(train_sc)
+    print(f'  trained: {len(out["dual"])} support vectors, Ndof {m.Ndof}, scale_seq {m.scale_seq}')
+    for planar, tag in [(False, 'pe'), (True, 'ps')]:
+        rng = np.random.default_rng(177 + planar)
+        n = 70
+        CV = cv_plane_stress(m) if planar else np.array(m.CV)
+        sig = np.zeros((n, 6)); epl = np.zeros((n, 6)); deps = np.zeros((n, 6))
+        for i in range(n):
+            d = np.zeros(6)
+            d[0:3] = rng.standard_normal(3)
+            if planar:
+                d[2] = 0.
+            u = rng.uniform()
+            r = rng.uniform(0.05, 0.85) if u < 0.35 else (rng.uniform(0.85, 1.0) if u < 0.7 else rng.uniform(0.99, 1.02))
+            sig[i] = d / mat_h.calc_seq(d) * r * sy          # scaled by the Hill surface the SVC was trained on
+            de = np.zeros(6)
+            de[0:3] = rng.standard_normal(3)
+            if planar:
+                de[2] = 0.
+            if i % 5 == 0:
+                de = np.linalg.lstsq(m.CV, sig[i] + 1e-3 * de, rcond=None)[0]
+                de[3:6] = 0.
+                if planar:
+                    de[2] = 0.
+            deps[i] = de / FE.eps_eq(de) * [5.e-4, 5.e-4, 2.e-3, 1.e-4][i % 4]
+        fy = np.zeros(n); so = np.zeros((n, 6)); dp = np.zeros((n, 6)); ct = np.zeros((n, 6, 6)); ns = np.zeros(n, dtype=np.int32)
+        seq = np.zeros(n); yf = np.zeros(n); full = np.zeros(n); fg = np.zeros((n, 3)); ed = np.zeros((n, 6)); ctan = np.zeros((n, 6, 6))
+        for i in range(n):
+            m.msg['nsteps'] = -1
+            fy[i], so[i], dp[i], ct[i] = m.response(sig[i], epl[i], deps[i], CV)
+            ns[i] = m.msg['nsteps']
+            seq[i] = m.calc_seq(sig[i])
+            yf[i] = m.calc_yf(sig[i], epl=epl[i])
+            full[i] = m.ML_full_yf(sig[i], epl=epl[i])
+            fg[i] = m.calc_fgrad(FE.sig_princ(sig[i])[0], epl=epl[i, 0:3])
+            ed[i] = m.epl_dot(sig[i], epl[i], CV, deps[i])
+            ctan[i] = m.C_tan(sig[i], CV, epl=epl[i])
+        out.update({f'{tag}_CV': CV, f'{tag}_sig': sig, f'{tag}_epl': epl, f'{tag}_deps': deps, f'{tag}_fy': fy,
+                    f'{tag}_sig_out': so, f'{tag}_depl': dp, f'{tag}_ctan': ct, f'{tag}_nsteps': ns, f'{tag}_seq': seq,
+                    f'{tag}_yf': yf, f'{tag}_full_yf': full, f'{tag}_fgrad3': fg, f'{tag}_epl_dot': ed, f'{tag}_C_tan': ctan})
+        el = np.sum((ns == 0) & (np.abs(ct - CV).max(axis=(1, 2)) == 0))
+        print(f'  svc3/{tag}: elastic {el}, 50-step {np.sum(ns == 49)}, other {n - el - np.sum(ns == 49)}  ({time.time() - t0:.0f}s)')
+    # the reference test itself (tests/test_ml.py:29-34)
+    m.calc_properties(eps=0.01, sigeps=True, min_step=12)
+    for sel in ('stx', 'sty', 'et2', 'ect'):
+        for key in ('ys', 'seq', 'eeq', 'peeq'):
+            out[f'propJ2_{sel}_{key}'] = np.array(m.propJ2[sel][key])
+        out[f'sigeps_{sel}_sig'] = np.array(m.sigeps[sel]['sig'])
+        out[f'sigeps_{sel}_epl'] = np.array(m.sigeps[sel]['epl'])
+    print('  test_ml.py:32-34:', m.propJ2['stx']['ys'] - 149.62302821433968, m.propJ2['sty']['seq'][-1] - 157.25971534002542,
+          m.propJ2['ect']['peeq'][-1] - 0.00855380746615942)
+    np.savez_compressed(os.path.join(HERE, 'svc3_mlplast.npz'), **out)
+    print(f'svc3 fixture {time.time() - t0:.1f}s')
+
+
 if __name__ == '__main__':
     what = sys.argv[1:] or ['all']
     if 'all' in what:
-        what = ['response', 'kmat', 'solve', 'svc', 'barlat', 'barlat_response', 'barlat_solve', 'mlparam', 'tresca', 'sdim3']
+        what = ['response', 'kmat', 'solve', 'svc', 'barlat', 'barlat_response', 'barlat_solve', 'mlparam', 'tresca', 'sdim3', 'svc3']
     for w in what:
         print('==', w)
         globals()['gen_' + w]()

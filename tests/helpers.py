@@ -16,8 +16,12 @@ def plf_material_from_golden(g):
     m.CV[:] = list(CV.ravel())
     m.C44 = float(CV[3, 3])
     if 'sv' in g:
+        sv = np.asarray(g['sv'], dtype=float)
         m.kind = _lib.MAT_SVC
-        sv = np.ascontiguousarray(g['sv'], dtype=float)
+        if 'sdim' in g and int(g['sdim']) == 3:   # sdim = 3 model: 2 features, table padded to 6 columns
+            m.kind = _lib.MAT_SVC3
+            sv = np.hstack([sv, np.zeros((len(sv), 6 - sv.shape[1]))])
+        sv = np.ascontiguousarray(sv)
         dual = np.ascontiguousarray(g['dual'], dtype=float)
         m.nsv = len(dual)
         m.svc_sv = sv.ctypes.data_as(_lib._dp)

@@ -457,3 +457,26 @@ def test_calc_properties_hill3p_sdim3_golden():
     assert abs(mat2.propJ2['et2']['ys'] - 136.93063937629154) < 1e-5
     assert abs(mat2.propJ2['ect']['peeq'][-1] - 0.04570405456408677) < 1e-5
     assert abs(mat2.propJ2['ect']['seq'][-1] - 168.3199594723871) < 1e-5
+
+
+def test_ml_plasticity_sdim3_golden(golden):
+    """/root/reference/tests/test_ml.py:10-34 (test_ml_plasticity): an SVC trained in the cylindrical principal-stress
+    space (sdim = 3) as yield function inside calc_properties' four plane-stress load cases.  The SVC is the one the
+    reference trained (fixture svc3_mlplast.npz, tests/golden/make_golden.py gen_svc3); asserted are the reference
+    test's own golden scalars with its tolerances and the whole stress-strain curves of the reference run."""
+    g = golden('svc3_mlplast')
+    m = FE.Material(name='ML flow rule')
+    m.elasticity(E=200.e3, nu=0.3)
+    m.plasticity(sy=150., sdim=3)
+    m.set_svc(g['sv'], g['dual'], float(g['rho']), float(g['gamma']), scale_seq=float(g['scale_seq']))
+    assert m.Ndof == 2
+    m.calc_properties(eps=0.01, sigeps=True, min_step=12)
+    assert abs(m.propJ2['stx']['ys'] - 149.62302821433968) < 1E-5
+    assert abs(m.propJ2['sty']['seq'][-1] - 157.25971534002542) < 1E-5
+    assert abs(m.propJ2['ect']['peeq'][-1] - 0.00855380746615942) < 1E-7
+    for sel in ('stx', 'sty', 'et2', 'ect'):
+        for key in ('seq', 'eeq', 'peeq'):
+            ref = g['propJ2_%s_%s' % (sel, key)]
+            assert len(m.propJ2[sel][key]) == len(ref), (sel, key)
+            assert np.max(np.abs(np.asarray(m.propJ2[sel][key]) - ref)) < 1e-6 * max(np.max(np.abs(ref)), 1e-2), (sel, key)
+        assert relmax(np.asarray(m.sigeps[sel]['sig']), g['sigeps_%s_sig' % sel]) < 1e-6

@@ -124,6 +124,25 @@ def test_svc_response_vs_reference_golden(ctx, golden, tag):
     check_response(out, g, tag, float(g['sy']), tol=2e-6)
 
 
+@pytest.mark.parametrize('tag', ['pe', 'ps'])
+def test_svc_sdim3_vs_reference_golden(ctx, golden, tag):
+    """sdim = 3 machine-learned yield function (SVC on the cylindrical coordinates of the principal stresses, trained by
+    the reference as in tests/test_ml.py:10-28): decision function, ML_full_yf, the Jacobian-chain gradient
+    (material.py:780-805), epl_dot / C_tan and Material.response against the reference on shear-free states."""
+    g = golden('svc3_mlplast')
+    ctx.set_materials([plf_material_from_golden(g)], planestress=(tag == 'ps'))
+    assert np.array_equal(ctx.element_CV(0), g[tag + '_CV'])
+    sig, epl, deps = g[tag + '_sig'], g[tag + '_epl'], g[tag + '_deps']
+    assert relmax(ctx.calc_seq(0, sig), g[tag + '_seq']) < 1e-12
+    assert np.max(np.abs(ctx.calc_yf(0, sig, epl) - g[tag + '_yf'])) < 1e-10
+    assert np.max(np.abs(ctx.ml_full_yf(0, sig, epl) - g[tag + '_full_yf'])) < TOL * float(g['sy'])
+    fg = ctx.calc_fgrad(0, sig, epl)
+    assert relmax(fg[:, 0:3], g[tag + '_fgrad3']) < 1e-10 and np.all(fg[:, 3:6] == 0.)
+    assert relmax(ctx.epl_dot(0, sig, epl, deps), g[tag + '_epl_dot']) < 1e-9
+    assert relmax(ctx.C_tan(0, sig, epl), g[tag + '_C_tan']) < 1e-10
+    check_response(ctx.response_batch(sig, epl, deps), g, tag, float(g['sy']), tol=2e-6)
+
+
 def barlat_plf_material(g, khard=0.):
     from pylabfea_b200 import _lib
     m = _lib.PlfMaterial()

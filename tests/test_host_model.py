@@ -120,3 +120,24 @@ def test_from_MLparam_parses_the_reference_export(golden):
     assert m.sy == float(g['sy']) and m.dev_only == bool(g['dev_only']) and m.ML_yf
     assert np.allclose(m.CV, g['CV'], rtol=1e-15, atol=0.)
     assert m.meta['Data']['Class'] == 'SVC_parameters' and m.meta['Model']['Creator'] == 'pylabfea'
+
+
+def test_sdim3_svc_descriptor(golden):
+    """An SVC trained in the sdim = 3 feature space crosses the C-ABI as PLF_MAT_SVC3 with a 6-column table."""
+    from pylabfea_b200 import _lib
+    g = golden('svc3_mlplast')
+    m = FE.Material()
+    m.elasticity(E=200.e3, nu=0.3)
+    m.plasticity(sy=150., sdim=3)
+    with pytest.raises(ValueError):
+        m.set_svc(np.zeros((4, 6)), np.zeros(4), 0., 1.)        # sdim = 3 models have 2 features
+    m.set_svc(g['sv'], g['dual'], float(g['rho']), float(g['gamma']))
+    d = m._descriptor()
+    assert d.kind == _lib.MAT_SVC3 and d.nsv == len(g['dual']) and d.svc_scale_seq == 150. and m.Ndof == 2
+    sv = np.ctypeslib.as_array(d.svc_sv, shape=(d.nsv, 6))
+    assert np.array_equal(sv[:, 0:2], g['sv']) and not sv[:, 2:].any()
+    m6 = FE.Material()
+    m6.elasticity(E=200.e3, nu=0.3)
+    m6.plasticity(sy=150., sdim=6)
+    with pytest.raises(ValueError):
+        m6.set_svc(g['sv'], g['dual'], float(g['rho']), float(g['gamma']))
