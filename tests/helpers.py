@@ -29,7 +29,7 @@ def plf_material_from_golden(g):
         m.svc_gamma, m.svc_rho, m.svc_scale_seq = float(g['gamma']), float(g['rho']), float(g['scale_seq'])
         m.dev_only = int(g['dev_only'])
         m.sy, m.khard = float(g['sy']), 0.
-        m.hill[:] = list(np.asarray(g['hill'], float))
+        m.hill[:] = (list(np.asarray(g['hill'], float)) + [1., 1., 1.])[:6]   # sdim = 3 fixtures carry 3 parameters
         m.d[:] = [float(g['drucker'])] * 3
         return _keep(m, sv, dual)
     if 'sy' in g:
