@@ -729,6 +729,13 @@ static __device__ __noinline__ void iso2d_correct(const DevMat &m, double *st, d
     st[5] = eplt[0] + t[0]; st[6] = eplt[1] + t[1]; st[7] = eplt[2] + t[2]; st[8] = eplt[5] + t[5];
 }
 
+// RC (fast mode 8, option passb_recur): because n' = (1 - beta) n + dc, the two scalars a sub-step needs follow exact
+// recurrences -- n'.dc = (1 - beta) n.dc + dc.dc and q' = (1 - beta)((1 - beta) q + 2 n.dc) + dc.dc (weighted products
+// as in q) -- so the loop-carried dependency shrinks from  n -> q (4 ops) -> rsqrt -> r^2 -> g -> beta -> n  to
+// q -> rcp -> beta -> q'; the reciprocal for the next sub-step is issued before the yield check of this one.  The vector
+// update, the tangent sums and the check hang off that chain.  q and n.dc are re-derived from n after a radial-return
+// correction and at the end; they differ from the direct evaluation by ~1e-14 relative after 50 steps.
+template <bool RC = false>
 __device__ __forceinline__ int hill_passB_iso2d(const DevMat &m, double *s, double *epd, const double *de, double *xc, int xstride,
                                                 double *gs, double &fy)
 {
@@ -764,11 +771,15 @@ __device__ __forceinline__ int hill_passB_iso2d(const DevMat &m, double *s, doub
     seq_rs(q2, seq, rs);
     double W00 = 0., W01 = 0., W05 = 0., W11 = 0., W15 = 0., W55 = 0.;
     bool corrected = false;
+    double ncd = fma(1.5, fma(n2, dc2, fma(n1, dc1, n0 * dc0)), 3. * (n5 * dc5));
+    double r2 = rs * rs;
 #pragma unroll 1
     for (int it = 0; it < PLF_MAXIT; it++) {
-        const double ncd = fma(1.5, fma(n2, dc2, fma(n1, dc1, n0 * dc0)), 3. * (n5 * dc5));
+        if (!RC) {
+            ncd = fma(1.5, fma(n2, dc2, fma(n1, dc1, n0 * dc0)), 3. * (n5 * dc5));
+            r2 = rs * rs;
+        }
         const bool yplus = fma(2., ncd, q2 + qc) > ythr2;
-        const double r2 = rs * rs;
         const double g = ncd * r2;
         const double beta = g * bfac;
         const double gam = yplus ? g * gfac : 0.;
@@ -780,8 +791,16 @@ __device__ __forceinline__ int hill_passB_iso2d(const DevMat &m, double *s, doub
         double f0 = fma(gam, n0, e0), f1e = fma(gam, n1, e1), f2 = fma(gam, n2, e2), f5 = fma(gam2, n5, e5);
         n0 = fma(-beta, n0, n0 + dc0); n1 = fma(-beta, n1, n1 + dc1); n2 = fma(-beta, n2, n2 + dc2); n5 = fma(-beta, n5, n5 + dc5);
         p += pc;
-        q2 = 1.5 * (n0 * n0 + n1 * n1 + n2 * n2) + 3. * (n5 * n5);
-        seq_rs1(q2, seq, rs);
+        if (RC) {
+            const double omb = 1. - beta;
+            q2 = fma(omb, fma(omb, q2, ncd + ncd), qc);
+            ncd = fma(omb, ncd, qc);
+            r2 = fast_rcp1(q2);   // for the next sub-step: issued ahead of the yield check below
+            seq = q2 * fast_rsqrt1(q2 + 1e-300);
+        } else {
+            q2 = 1.5 * (n0 * n0 + n1 * n1 + n2 * n2) + 3. * (n5 * n5);
+            seq_rs1(q2, seq, rs);
+        }
         const double e2s = (2. / 3.) * ((f0 * f0 + f1e * f1e + f2 * f2) + 0.5 * (f5 * f5));
         const double lhs = seq - c0;
         if (lhs > 0. && lhs * lhs > K2 * e2s) {
@@ -794,9 +813,14 @@ __device__ __forceinline__ int hill_passB_iso2d(const DevMat &m, double *s, doub
             f0 = st[5]; f1e = st[6]; f2 = st[7]; f5 = st[8];
             q2 = 1.5 * (n0 * n0 + n1 * n1 + n2 * n2) + 3. * (n5 * n5);
             seq_rs(q2, seq, rs);
+            if (RC) {
+                ncd = fma(1.5, fma(n2, dc2, fma(n1, dc1, n0 * dc0)), 3. * (n5 * dc5));
+                r2 = rs * rs;
+            }
         }
         e0 = f0; e1 = f1e; e2 = f2; e5 = f5;
     }
+    if (RC) q2 = 1.5 * (n0 * n0 + n1 * n1 + n2 * n2) + 3. * (n5 * n5);
     seq_rs(q2, seq, rs);   // full-precision seq for the returned yield-function value
     s[0] = n0 + p; s[1] = n1 + p; s[2] = n2 + p; s[3] = 0.; s[4] = 0.; s[5] = n5;
     epd[0] = e0; epd[1] = e1; epd[2] = e2; epd[5] = e5;   // epd[3], epd[4] stay zero

@@ -5,6 +5,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -58,6 +59,7 @@ extern "C" int plf_create(int device, plf_ctx **out)
     CK(cudaSetDevice(device));
     ctx = new plf_ctx();
     ctx->device = device;
+    if (const char *ev = getenv("PLF_PASSB_RECUR")) ctx->passb_recur = atoi(ev);   // A/B default of the option of the same name
     cudaDeviceProp prop;
     e = cudaGetDeviceProperties(&prop, device);
     if (e != cudaSuccess) { delete ctx; return fail(nullptr, PLF_ECUDA, cudaGetErrorString(e)); }
@@ -369,7 +371,7 @@ extern "C" int plf_batch_run(plf_ctx *ctx, plf_batch *b)
         if (ctx->hmats[i].tresca && (ctx->hmats[i].kind == PLF_MAT_HILL || ctx->hmats[i].kind == PLF_MAT_HILL3))
             // material.py:824-825: the first plastic step of a Tresca material raises in the reference
             return fail(ctx, PLF_EUNSUPPORTED, "response: analytical gradient for Tresca not implemented");
-    LaunchCtx lc{ctx->stream, ctx->sm_count, ctx->passa_direct, ctx->max_fm, ctx->k1_only};
+    LaunchCtx lc{ctx->stream, ctx->sm_count, ctx->passa_direct, ctx->max_fm, ctx->k1_only, ctx->passb_recur};
     CK(launch_response(lc, ctx->hmats, ctx->nmat, b->n, b->mat_id, b->sig, b->epl, b->deps, b->fy, b->sig_out, b->depl,
                        b->ctan, b->nsteps, b->worklist, (unsigned int *)(ctx->d_scalars + 16),
                        (unsigned long long *)(ctx->d_scalars + 8), ctx->compact, &ctx->launches));
@@ -398,6 +400,7 @@ extern "C" int plf_set_option(plf_ctx *ctx, const char *key, int value)
     if (!strcmp(key, "passa_direct")) { ctx->passa_direct = value; return PLF_OK; }
     if (!strcmp(key, "max_fm")) { ctx->max_fm = value; return PLF_OK; }
     if (!strcmp(key, "k1_only")) { ctx->k1_only = value; return PLF_OK; }
+    if (!strcmp(key, "passb_recur")) { ctx->passb_recur = value; return PLF_OK; }
     if (!strcmp(key, "solver_mg")) { ctx->solver_mg = value; return PLF_OK; }
     if (!strcmp(key, "solver_warm")) { ctx->solver_warm = value; return PLF_OK; }
     if (!strcmp(key, "mg_nu") || !strcmp(key, "mg_coarse_sweeps") || !strcmp(key, "mg_omega_permille")) {

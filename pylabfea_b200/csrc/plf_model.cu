@@ -317,7 +317,7 @@ extern "C" int plf_step_host(plf_ctx *ctx, plf_batch *b, const double *sig, cons
     CK(cudaMemsetAsync(b->mat_id, 0, (size_t)b->n * sizeof(int32_t), ctx->stream));
     if (ctx->nmat > 1)   // material ids of the mesh elements (descriptor low half)
         return fail(ctx, PLF_EUNSUPPORTED, "plf_step_host: single-material meshes only (use plf_sweep for mixed meshes)");
-    LaunchCtx lc{ctx->stream, ctx->sm_count, ctx->passa_direct, ctx->max_fm, ctx->k1_only};
+    LaunchCtx lc{ctx->stream, ctx->sm_count, ctx->passa_direct, ctx->max_fm, ctx->k1_only, ctx->passb_recur};
     for (int c = 0; c < nchunk; c++) {
         const int ja = (int)((int64_t)NX * c / nchunk), jb = (int)((int64_t)NX * (c + 1) / nchunk);   // element columns
         const int64_t e0 = (int64_t)ja * NY, ne = (int64_t)(jb - ja) * NY;

@@ -9,7 +9,7 @@ ctx = _lib.Context(0)
 mat, CV = bench.j2_material()
 ctx.set_materials([mat], planestress=False)
 def run(sig, epl, deps, **opts):
-    base = dict(compact=1, passa_direct=0, max_fm=2)
+    base = dict(compact=1, passa_direct=0, max_fm=2, passb_recur=0)
     base.update(opts)
     for k, v in base.items():
         ctx.set_option(k, v)
@@ -23,7 +23,7 @@ deps3[odd, 3] = 1e-4 * rng.standard_normal(odd.sum())
 for name, (a, b, c) in (('planar', (sig, epl, deps)), ('mixed', (sig3, epl3, deps3))):
     ref = run(a, b, c)
     print(name, 'n50 =', int(np.sum(ref[4] == 49)))
-    for opts in (dict(passa_direct=1), dict(max_fm=3), dict(max_fm=4), dict(max_fm=4, passa_direct=1), dict(max_fm=4)):
+    for opts in (dict(passa_direct=1), dict(max_fm=3), dict(max_fm=4), dict(max_fm=4, passa_direct=1), dict(max_fm=4), dict(max_fm=4, passb_recur=1)):
         out = run(a, b, c, **opts)
         ok = np.array_equal(out[4], ref[4])
         err = max(float(np.max(np.abs(x - y)) / np.max(np.abs(y))) for x, y in zip(out[:4], ref[:4]))

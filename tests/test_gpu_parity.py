@@ -12,6 +12,7 @@ pytestmark = pytest.mark.gpu
 
 RESP_MATS = ['j2', 'j2pp', 'hill', 'hillrv', 'drucker', 'cubic']
 TOL = 1e-6
+PASSB_RECUR_DEFAULT = int(__import__('os').environ.get('PLF_PASSB_RECUR', '0'))   # library default of the option
 
 
 @pytest.fixture(scope='module')
@@ -304,7 +305,7 @@ def test_response_full_size_fast_modes_vs_oracle(ctx):
     mats = [orc.Mat(kind=orc.HILL, E=bench.E_MOD, nu=bench.NU, sy=bench.SY, khard=bench.KHARD)]
 
     def run(a, b, c, **opts):
-        o = dict(compact=1, max_fm=4, passa_direct=0)
+        o = dict(compact=1, max_fm=4, passa_direct=0, passb_recur=0)
         o.update(opts)
         for k, v in o.items():
             ctx.set_option(k, v)
@@ -314,7 +315,9 @@ def test_response_full_size_fast_modes_vs_oracle(ctx):
         ref = run(sig, epl, deps, max_fm=0)                      # general Hill path (any CV, any Hill parameters)
         n50 = int(np.sum(ref[4] == 49))
         assert 0.05 * N * N < n50 < 0.5 * N * N                  # the 50-sub-step pass really ran
-        for opts in (dict(max_fm=2), dict(max_fm=3), dict(max_fm=4), dict(max_fm=4), dict(max_fm=4, passa_direct=1)):
+        # passb_recur: the planar isotropic sub-step loop with scalar recurrences on its carried chain (hill_fast.cuh)
+        for opts in (dict(max_fm=2), dict(max_fm=3), dict(max_fm=4), dict(max_fm=4), dict(max_fm=4, passa_direct=1),
+                     dict(max_fm=4, passb_recur=1), dict(max_fm=4, passb_recur=PASSB_RECUR_DEFAULT)):
             out = run(sig, epl, deps, **opts)
             assert np.array_equal(out[4], ref[4]), opts          # same branch per element
             for a, b in zip(out[:4], ref[:4]):
@@ -334,7 +337,7 @@ def test_response_full_size_fast_modes_vs_oracle(ctx):
         s3[odd, 3] = 20. * rng.standard_normal(odd.sum())
         s3[odd, 4] = 10. * rng.standard_normal(odd.sum())
         d3[odd, 3] = 1e-4 * rng.standard_normal(odd.sum())
-        out = run(s3, e3, d3)
+        out = run(s3, e3, d3, passb_recur=PASSB_RECUR_DEFAULT)
         sel = np.concatenate([np.nonzero(odd)[0][:3000], np.nonzero(~odd)[0][:3000]])
         oref = orc.response_batch(mats, None, s3[sel], e3[sel], d3[sel], CV[None])
         assert np.array_equal(out[4][sel], oref[4])
@@ -342,7 +345,7 @@ def test_response_full_size_fast_modes_vs_oracle(ctx):
         assert relmax(out[1][sel], oref[1]) < TOL and relmax(out[3][sel], oref[3]) < TOL
         assert np.max(np.abs(out[2][sel] - oref[2])) < TOL * np.max(np.abs(oref[2]))
     finally:
-        for k, v in dict(compact=1, max_fm=4, passa_direct=0).items():
+        for k, v in dict(compact=1, max_fm=4, passa_direct=0, passb_recur=PASSB_RECUR_DEFAULT).items():
             ctx.set_option(k, v)
 
 
