@@ -26,7 +26,7 @@ struct LaunchCtx {
     int passa_direct = 0;  // 1: pass A writes its records straight from registers (256-bit stores) instead of staging them
     int max_fm = 4;        // cap of the single-material fast mode (hill_fast.cuh)
     int k1_only = 0;       // diagnostics: 1 = launch pass A only
-    int passb_recur = 0;   // 1: planar isotropic J2 loop of pass B with scalar recurrences on the carried chain (hill_fast.cuh)
+    int passb_recur = 1;   // 1: planar isotropic J2 loop of pass B with scalar recurrences on the carried chain (hill_fast.cuh)
 };
 
 // response_kernels.cu

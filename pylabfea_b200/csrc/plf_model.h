@@ -38,7 +38,7 @@ struct plf_ctx {
     int passa_direct = 0;                 // pass A: shared-memory staged coalesced stores (0, fastest measured) or per-thread 256-bit stores (1)
     int max_fm = 4;                       // cap of the single-material fast mode (hill_fast.cuh)
     int k1_only = 0;                      // diagnostics: 1 = launch pass A only
-    int passb_recur = 0;                  // pass B, planar isotropic J2: recurrence form of the sub-step loop (env PLF_PASSB_RECUR)
+    int passb_recur = 1;                  // pass B, planar isotropic J2: recurrence form of the sub-step loop (0: direct form; env PLF_PASSB_RECUR)
 
     // materials
     int nmat = 0, planestress = 0;

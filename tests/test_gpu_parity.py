@@ -12,7 +12,7 @@ pytestmark = pytest.mark.gpu
 
 RESP_MATS = ['j2', 'j2pp', 'hill', 'hillrv', 'drucker', 'cubic']
 TOL = 1e-6
-PASSB_RECUR_DEFAULT = int(__import__('os').environ.get('PLF_PASSB_RECUR', '0'))   # library default of the option
+PASSB_RECUR_DEFAULT = int(__import__('os').environ.get('PLF_PASSB_RECUR', '1'))   # library default of the option
 
 
 @pytest.fixture(scope='module')
