@@ -735,12 +735,7 @@ static __device__ __noinline__ void iso2d_correct(const DevMat &m, double *st, d
 // q -> rcp -> beta -> q'; the reciprocal for the next sub-step is issued before the yield check of this one.  The vector
 // update, the tangent sums and the check hang off that chain.  q and n.dc are re-derived from n after a radial-return
 // correction and at the end; they differ from the direct evaluation by ~1e-14 relative after 50 steps.
-// RC == 2 (fast mode 9, passb_recur = 2) additionally takes the yield check off the in-order path: the correction needs
-// seq' - c0 > K peeq', and peeq' >= peeq - eps_eq(gam (n0, n1, n2, 2 n5)) = peeq - (2/3) |gam| seq (eps_eq is a norm), so
-// q' <= T^2 with T = c0 + K (peeq - (2/3) |gam| seq) (shrunk by 1e-11 against rounding) proves that no correction is due.
-// T only needs values of the previous sub-step, so the branch waits for one compare after q'; sqrt(q') and peeq' are
-// computed off the chain for the next sub-step, and the exact test of RC == 1 runs only when the filter does not decide.
-template <int RC = 0>
+template <bool RC = false>
 __device__ __forceinline__ int hill_passB_iso2d(const DevMat &m, double *s, double *epd, const double *de, double *xc, int xstride,
                                                 double *gs, double &fy)
 {
@@ -778,12 +773,6 @@ __device__ __forceinline__ int hill_passB_iso2d(const DevMat &m, double *s, doub
     bool corrected = false;
     double ncd = fma(1.5, fma(n2, dc2, fma(n1, dc1, n0 * dc0)), 3. * (n5 * dc5));
     double r2 = rs * rs;
-    const double K = m.khard;
-    double se = 0.;   // RC == 2: sqrt(e2s) of the committed plastic strain
-    if (RC == 2) {
-        const double ec = (2. / 3.) * ((e0 * e0 + e1 * e1 + e2 * e2) + 0.5 * (e5 * e5));
-        se = ec * fast_rsqrt(ec + 1e-300);
-    }
 #pragma unroll 1
     for (int it = 0; it < PLF_MAXIT; it++) {
         if (!RC) {
@@ -802,16 +791,9 @@ __device__ __forceinline__ int hill_passB_iso2d(const DevMat &m, double *s, doub
         double f0 = fma(gam, n0, e0), f1e = fma(gam, n1, e1), f2 = fma(gam, n2, e2), f5 = fma(gam2, n5, e5);
         n0 = fma(-beta, n0, n0 + dc0); n1 = fma(-beta, n1, n1 + dc1); n2 = fma(-beta, n2, n2 + dc2); n5 = fma(-beta, n5, n5 + dc5);
         p += pc;
-        bool maybe = true;
         if (RC) {
             const double omb = 1. - beta;
-            if (RC == 2) {
-                const double T = fma(K, se - (2. / 3.) * fabs(gam) * seq, c0) * (1. - 1.e-11);   // previous seq, peeq
-                q2 = fma(omb, fma(omb, q2, ncd + ncd), qc);
-                maybe = !(T > 0. && q2 <= T * T);
-            } else {
-                q2 = fma(omb, fma(omb, q2, ncd + ncd), qc);
-            }
+            q2 = fma(omb, fma(omb, q2, ncd + ncd), qc);
             ncd = fma(omb, ncd, qc);
             r2 = fast_rcp1(q2);   // for the next sub-step: issued ahead of the yield check below
             seq = q2 * fast_rsqrt1(q2 + 1e-300);
@@ -820,9 +802,8 @@ __device__ __forceinline__ int hill_passB_iso2d(const DevMat &m, double *s, doub
             seq_rs1(q2, seq, rs);
         }
         const double e2s = (2. / 3.) * ((f0 * f0 + f1e * f1e + f2 * f2) + 0.5 * (f5 * f5));
-        if (RC == 2) se = e2s * fast_rsqrt1(e2s + 1e-300);
         const double lhs = seq - c0;
-        if (maybe && lhs > 0. && lhs * lhs > K2 * e2s) {
+        if (lhs > 0. && lhs * lhs > K2 * e2s) {
             // radial-return correction (310-342), rare: out of line, state handed over through local memory so that
             // its temporaries do not take registers from the loop
             corrected = true;
@@ -835,10 +816,6 @@ __device__ __forceinline__ int hill_passB_iso2d(const DevMat &m, double *s, doub
             if (RC) {
                 ncd = fma(1.5, fma(n2, dc2, fma(n1, dc1, n0 * dc0)), 3. * (n5 * dc5));
                 r2 = rs * rs;
-            }
-            if (RC == 2) {
-                const double ec = (2. / 3.) * ((f0 * f0 + f1e * f1e + f2 * f2) + 0.5 * (f5 * f5));
-                se = ec * fast_rsqrt(ec + 1e-300);
             }
         }
         e0 = f0; e1 = f1e; e2 = f2; e5 = f5;

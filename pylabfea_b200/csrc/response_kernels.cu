@@ -253,9 +253,8 @@ __device__ __forceinline__ void passB_element(int64_t e, WAcc &W, double *xc, co
     }
     if (FM == 7) hill_passB_blk2d(m, s, ep, de, xc, RB, gs, fyv);
     else if (FM == 6) hill_passB_hilliso2d(m, s, ep, de, xc, RB, gs, fyv);
-    else if (FM == 4) hill_passB_iso2d<0>(m, s, ep, de, xc, RB, gs, fyv);
-    else if (FM == 8) hill_passB_iso2d<1>(m, s, ep, de, xc, RB, gs, fyv);   // scalar recurrences on the carried chain
-    else if (FM == 9) hill_passB_iso2d<2>(m, s, ep, de, xc, RB, gs, fyv);   // + yield check filtered off the in-order path
+    else if (FM == 4) hill_passB_iso2d<false>(m, s, ep, de, xc, RB, gs, fyv);
+    else if (FM == 8) hill_passB_iso2d<true>(m, s, ep, de, xc, RB, gs, fyv);   // scalar recurrences on the carried chain
     else if (FM == 3) hill_passB_iso(m, s, ep, de, xc, RB, gs, fyv);
     else hill_passB<FM>(m, s, ep, de, W, gs, fyv);
     // ep now holds epl + depl; the increment is recovered against the (L2-resident) input record
@@ -340,12 +339,12 @@ __global__ void __launch_bounds__(RB, MINB) response_passB_kernel(const int32_t 
         WRegs W;
         passB_element<SINGLE, FM>(e, W, s_xc + threadIdx.x, mat_id, sig, epl, deps, fy, sig_out, depl_out, ctan, nsteps);
     }
-    if (FM == 4 || FM == 6 || FM == 7 || FM == 8 || FM == 9) {
+    if (FM == 4 || FM == 6 || FM == 7 || FM == 8) {
         // the non-planar elements (back of the list) with the general loop of the material class
         for (unsigned int t = blockIdx.x * RB + threadIdx.x; t < n1; t += gridDim.x * RB) {
             const int64_t e = worklist[nlist - 1 - (int64_t)t];
             WRegs W;
-            passB_element<SINGLE, ((FM == 4 || FM == 8 || FM == 9) ? 3 : 1)>(e, W, s_xc + threadIdx.x, mat_id, sig, epl, deps, fy, sig_out, depl_out, ctan,
+            passB_element<SINGLE, ((FM == 4 || FM == 8) ? 3 : 1)>(e, W, s_xc + threadIdx.x, mat_id, sig, epl, deps, fy, sig_out, depl_out, ctan,
                                                      nsteps);
         }
     }
@@ -724,7 +723,6 @@ cudaError_t launch_response(const LaunchCtx &lc, const DevMat *hmats, int nmat, 
             if (single) {
                 if (fm == 7) PASSB(3, true, 7);
                 else if (fm == 6) PASSB(3, true, 6);
-                else if (fm == 4 && lc.passb_recur == 2) PASSB(3, true, 9);
                 else if (fm == 4 && lc.passb_recur) PASSB(3, true, 8);   // FM 4 with the recurrence form of the planar loop
                 else if (fm == 4) PASSB(3, true, 4);   // planar elements first, then whatever is not planar
                 else if (fm == 3) PASSB(3, true, 3);

@@ -23,7 +23,7 @@ deps3[odd, 3] = 1e-4 * rng.standard_normal(odd.sum())
 for name, (a, b, c) in (('planar', (sig, epl, deps)), ('mixed', (sig3, epl3, deps3))):
     ref = run(a, b, c)
     print(name, 'n50 =', int(np.sum(ref[4] == 49)))
-    for opts in (dict(passa_direct=1), dict(max_fm=3), dict(max_fm=4), dict(max_fm=4, passa_direct=1), dict(max_fm=4), dict(max_fm=4, passb_recur=1), dict(max_fm=4, passb_recur=2)):
+    for opts in (dict(passa_direct=1), dict(max_fm=3), dict(max_fm=4), dict(max_fm=4, passa_direct=1), dict(max_fm=4), dict(max_fm=4, passb_recur=1)):
         out = run(a, b, c, **opts)
         ok = np.array_equal(out[4], ref[4])
         err = max(float(np.max(np.abs(x - y)) / np.max(np.abs(y))) for x, y in zip(out[:4], ref[:4]))

@@ -317,8 +317,7 @@ def test_response_full_size_fast_modes_vs_oracle(ctx):
         assert 0.05 * N * N < n50 < 0.5 * N * N                  # the 50-sub-step pass really ran
         # passb_recur: the planar isotropic sub-step loop with scalar recurrences on its carried chain (hill_fast.cuh)
         for opts in (dict(max_fm=2), dict(max_fm=3), dict(max_fm=4), dict(max_fm=4), dict(max_fm=4, passa_direct=1),
-                     dict(max_fm=4, passb_recur=0), dict(max_fm=4, passb_recur=1), dict(max_fm=4, passb_recur=2),
-                     dict(max_fm=4, passb_recur=PASSB_RECUR_DEFAULT)):
+                     dict(max_fm=4, passb_recur=1), dict(max_fm=4, passb_recur=PASSB_RECUR_DEFAULT)):
             out = run(sig, epl, deps, **opts)
             assert np.array_equal(out[4], ref[4]), opts          # same branch per element
             for a, b in zip(out[:4], ref[:4]):
