@@ -291,6 +291,7 @@ __device__ __forceinline__ int hill_passA(const DevMat &m, double *s, const doub
 //   FM 2 : FM 1 and all Hill parameters equal 1 (J2): q = 1.5 |dev s|^2 + 3 |shear|^2, a = 1.5 dev(s) / seq
 //   FM 3 : FM 2 and isotropic elasticity (DevMat.cv_iso): iso_passA / hill_passB_iso below
 //   FM 4 : FM 3 with planar states sorted to hill_passB_iso2d (the non-planar rest runs the FM 3 loop)
+//   FM 8 : FM 4 with the recurrence form of the planar loop (hill_passB_iso2d<true>; pass B only, option passb_recur)
 //   FM 6 : FM 1 and isotropic elasticity, planar states sorted to hill_passB_hilliso2d (rest: the FM 1 loop)
 //   FM 7 : FM 1 / 2 on a block-structured CV that is not isotropic (plane stress, cubic), planar states sorted to
 //          hill_passB_blk2d (rest: the FM 1 loop)
