@@ -96,8 +96,17 @@ int64_t plf_launch_count(const plf_ctx *ctx); /* kernels launched by this contex
 /* page-locked host memory for callers that want asynchronous H2D/D2H copies of their numpy buffers */
 int plf_pinned_alloc(size_t bytes, void **out);
 int plf_pinned_free(void *p);
-/* tuning switches: "compact" (default 1) = two-pass return mapping, the 50-sub-step elements are compacted into a
- * dense second launch instead of diverging inside the first one */
+/* tuning / A-B switches; unknown keys return PLF_EINVAL:
+ *   "compact"      1 (default): two-pass return mapping, the 50-sub-step elements are compacted into a dense second
+ *                  launch instead of diverging inside the first one; 0: one unsplit kernel
+ *   "max_fm"       cap of the single-material fast mode (hill_fast.cuh; default 4, 0 = general Hill kernels)
+ *   "passb_recur"  1 (default): recurrence form of the planar isotropic sub-step loop of pass B; 0: direct form
+ *   "passa_direct" 1: pass A writes its records with per-thread 256-bit stores; 0 (default): staged coalesced stores
+ *   "assembly_tiled" 1 (default): staged coalesced CSR stores; 0: direct stores
+ *   "solver_mg"    1 (default): multigrid V-cycle preconditioner for plf_solve_linear; 0: Jacobi
+ *   "solver_warm"  1 (default): CG starts from the previous du; 0: from zero
+ *   "mg_nu", "mg_coarse_sweeps", "mg_omega_permille": smoothing sweeps per level / on the coarsest level / Jacobi damping
+ *   "k1_only"      diagnostics: 1 = launch pass A only, 2 = pass A without the constitutive math */
 int plf_set_option(plf_ctx *ctx, const char *key, int value);
 
 /* ---- materials ------------------------------------------------------------------------------------------- */
