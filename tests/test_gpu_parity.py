@@ -148,6 +148,31 @@ def test_svc_sdim3_vs_reference_golden(ctx, golden, tag):
     check_response(ctx.response_batch(sig, epl, deps), g, tag, float(g['sy']), tol=2e-6)
 
 
+@pytest.mark.parametrize('tag', ['pe', 'ps'])
+def test_lhs_asymmetry_device_vs_oracle(ctx, golden, tag):
+    """LHS yield asymmetry (d = lhs in calc_seq 646-650 and calc_fgrad 829-830).  The reference itself raises in calc_seq
+    for every LHS material (`if self.lhs:` on an array, material.py:646), so there is no fixture: the device is checked
+    against the oracle's restatement on the states of the Drucker fixture (same elastic and Hill parameters)."""
+    from pylabfea_b200 import _lib
+    from oracle import oracle as orc
+    g = golden('response_drucker')
+    lhs = [0.05, -0.03, 0.08]
+    m = plf_material_from_golden(g)
+    m.lhs = 1
+    m.d[:] = lhs
+    ctx.set_materials([m], planestress=(tag == 'ps'))
+    om = orc.Mat(kind=orc.HILL, E=float(g['E']), nu=float(g['nu']), sy=float(g['sy']), khard=float(g['khard']), hill=g['hill'], lhs=lhs)
+    sig, epl, deps, CV = g[tag + '_sig'], g[tag + '_epl'], g[tag + '_deps'], g[tag + '_CV']
+    assert relmax(ctx.calc_seq(0, sig), orc.calc_seq(om, sig)) < 1e-12
+    assert relmax(ctx.calc_fgrad(0, sig, epl), orc.calc_fgrad(om, sig, epl)) < 1e-11
+    fy, so, dp, ct, ns = ctx.response_batch(sig, epl, deps)
+    ofy, oso, odp, oct_, ons = orc.response_batch([om], None, sig, epl, deps, CV[None])
+    assert np.array_equal(ns, ons) and int(np.sum(ns == 49)) > 10
+    assert np.max(np.abs(fy - ofy)) < TOL * float(g['sy'])
+    assert relmax(so, oso) < TOL and relmax(ct, oct_) < TOL
+    assert np.max(np.abs(dp - odp)) < TOL * np.max(np.abs(odp))
+
+
 def barlat_plf_material(g, khard=0.):
     from pylabfea_b200 import _lib
     m = _lib.PlfMaterial()
