@@ -188,7 +188,11 @@ def run_reference(args, rank, world):
             'warmup': args.warmup, 'ms_per_step': dt * 1e3, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
             'dtype': 'f64', 'data': 'synthetic', 'config': workload_config(N),
             'cpu_baseline': {'value': val, 'unit': unit, 'cores': cores, 'kind': 'port',
-                             'sample': '%d elements sampled (seeded) from the %dx%d workload per step' % (sample, N, N)},
+                             'sample': '%d elements sampled (seeded) from the %dx%d workload per step' % (sample, N, N),
+                             'note': 'C port of the reference algorithm, all host threads; the unmodified Python reference '
+                                     'runs Material.response at 181 updates/s on one core (measured in the build container on a '
+                                     'sample of this workload, where the port returns identical results: '
+                                     'profiles/r1_reference_python_timing.json)'},
             'e2e': {'value': val, 'unit': unit, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}, 'gpu_launches': 0}
     print(json.dumps(line))
 
