@@ -266,9 +266,9 @@ class Material(object):
             m.E, m.nu, m.C11, m.C12, m.C44 = ref.E, ref.nu, ref.C11, ref.C12, ref.C44
             m.CV = np.array(ref.CV, dtype=float)
         if ref.sy is not None:
-            if ref.sdim != 6:
-                raise NotImplementedError('only sdim = 6 materials are supported on the device path')
-            m.sy0, m.sy, m.khard, m.sdim = ref.sy0, ref.sy, ref.khard, 6
+            if ref.sdim not in (3, 6):
+                raise ValueError('sdim must be either 3 or 6')
+            m.sy0, m.sy, m.khard, m.sdim = ref.sy0, ref.sy, ref.khard, int(ref.sdim)
             m.drucker = ref.drucker
             m.lhs = None if ref.lhs is None else np.array(ref.lhs, dtype=float)
             m.hill = np.array(ref.hill, dtype=float)

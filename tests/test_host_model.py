@@ -141,3 +141,24 @@ def test_sdim3_svc_descriptor(golden):
     m6.plasticity(sy=150., sdim=6)
     with pytest.raises(ValueError):
         m6.set_svc(g['sv'], g['dual'], float(g['rho']), float(g['gamma']))
+
+
+def test_from_reference_duck_typed_sdim3_ml_material(golden):
+    """Material.from_reference copies what a pyLabFEA Material carries (here a stand-in object with the attributes the
+    reference sets in plasticity() and setup_yf_SVM_3D()) -- sdim = 3 with a trained SVC included."""
+    from types import SimpleNamespace
+    from pylabfea_b200 import _lib
+    g = golden('svc3_mlplast')
+    svc = SimpleNamespace(support_vectors_=g['sv'], dual_coef_=g['dual'][None, :], intercept_=np.array([float(g['rho'])]),
+                          _gamma=float(g['gamma']), gamma=float(g['gamma']))
+    ref = SimpleNamespace(name='ML flow rule', num=1, E=200.e3, nu=0.3, C11=g['CV'][0, 0], C12=g['CV'][0, 1], C44=g['CV'][3, 3],
+                          CV=g['CV'], sy=150., sy0=150., khard=0., sdim=3, drucker=0., lhs=None, hill=np.ones(3), hill_6p=False,
+                          hill_3p=False, tresca=False, barlat=False, ML_yf=True, whdat=False, txdat=False, svm_yf=svc,
+                          scale_seq=float(g['scale_seq']), dev_only=False)
+    m = FE.Material.from_reference(ref)
+    d = m._descriptor()
+    assert d.kind == _lib.MAT_SVC3 and d.nsv == len(g['dual']) and m.sdim == 3 and m.Ndof == 2
+    assert d.svc_gamma == float(g['gamma']) and d.svc_rho == float(g['rho']) and np.array_equal(m.CV, g['CV'])
+    ref.sdim = 4
+    with pytest.raises(ValueError):
+        FE.Material.from_reference(ref)
