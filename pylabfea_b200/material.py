@@ -216,9 +216,10 @@ class Material(object):
         trunk = os.path.join(path, file)
         props = np.loadtxt(trunk + '-svm.csv', delimiter=',').ravel()
         nsv, ndof = int(round(props[0])), int(round(props[1]))
-        if ndof != 6:
-            raise NotImplementedError('from_MLparam: only sdim = 6 models without work-hardening / texture features '
-                                      '(Ndof = 6) are supported on the device path, file has Ndof = %d' % ndof)
+        if ndof not in (2, 6):
+            raise NotImplementedError('from_MLparam: models without work-hardening / texture features are supported on the '
+                                      'device path (Ndof = 6: sdim = 6, Ndof = 2: sdim = 3), file has Ndof = %d' % ndof)
+        sdim = 6 if ndof == 6 else 3
         if nsv < 1 or len(props) < 29 + nsv * (ndof + 1):
             raise ValueError('from_MLparam: file %s-svm.csv is truncated' % trunk)
         meta = None
@@ -242,7 +243,7 @@ class Material(object):
         else:
             m.elasticity(C11=props[2], C12=props[3], C44=props[4])
         scale_seq = float(props[8])
-        m.plasticity(sy=float(scale_seq if sy is None else sy), sdim=6)
+        m.plasticity(sy=float(scale_seq if sy is None else sy), sdim=sdim)
         dual = props[29:29 + nsv]
         sv = props[29 + nsv:29 + nsv + nsv * ndof].reshape(nsv, ndof)
         m.set_svc(sv, dual, float(props[5]), float(props[6]), scale_seq=scale_seq, dev_only=(props[16] < 0.))

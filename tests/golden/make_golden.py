@@ -595,6 +595,34 @@ def gen_mlparam():
     print(f'mlparam_hill-svm.csv / -svm_meta.json / mlparam_hill.npz  nsv={len(out["dual"])}  {time.time() - t0:.1f}s')
 
 
+def gen_mlparam3():
+    """export_MLparam of the sdim = 3 SVC of tests/test_ml.py:10-28 (Ndof = 2: cylindrical principal-stress features),
+    plus reference calc_yf values on principal stresses so that the loader can be checked end to end."""
+    t0 = time.time()
+    mat_h = FE.Material(name='anisotropic Hill')
+    mat_h.elasticity(E=200.e3, nu=0.3)
+    mat_h.plasticity(sy=150., hill=[0.7, 1., 1.4], drucker=0., khard=0., sdim=3)
+    m = FE.Material(name='ML flow rule')
+    m.elasticity(E=200.e3, nu=0.3)
+    m.plasticity(sy=150., sdim=3)
+    x_train, y_train = m.create_sig_data(36, mat_ref=mat_h, extend=True)
+    m.setup_yf_SVM_3D(x_train, y_train, C=10, gamma=4., fs=0.3)
+    cwd = os.getcwd()
+    os.chdir(HERE)
+    try:
+        m.export_MLparam(sname='tests/golden/make_golden.py', source='Hill-3p reference material', file='mlparam_svc3',
+                         path='./', descr=['sy', 'hill'], param=[150., [0.7, 1., 1.4]])
+    finally:
+        os.chdir(cwd)
+    rng = np.random.default_rng(19)
+    sp = rng.standard_normal((200, 3))
+    sp = sp / mat_h.calc_seq(sp)[:, None] * (rng.uniform(0.05, 1.6, 200) * m.sy)[:, None]
+    out = svc_arrays(m)
+    out.update(yf_sp=sp, yf=m.calc_yf(sp))
+    np.savez_compressed(os.path.join(HERE, 'mlparam_svc3.npz'), **out)
+    print(f'mlparam_svc3-svm.csv / -svm_meta.json / mlparam_svc3.npz  nsv={len(out["dual"])}  {time.time() - t0:.1f}s')
+
+
 def gen_tresca():
     """Tresca equivalent stress / yield function of the reference (material.py:630-632) on random Voigt stresses."""
     m = FE.Material('Tresca')
@@ -767,7 +795,7 @@ def gen_svc3():
 if __name__ == '__main__':
     what = sys.argv[1:] or ['all']
     if 'all' in what:
-        what = ['response', 'kmat', 'solve', 'svc', 'barlat', 'barlat_response', 'barlat_solve', 'mlparam', 'tresca', 'sdim3', 'svc3']
+        what = ['response', 'kmat', 'solve', 'svc', 'barlat', 'barlat_response', 'barlat_solve', 'mlparam', 'mlparam3', 'tresca', 'sdim3', 'svc3']
     for w in what:
         print('==', w)
         globals()['gen_' + w]()

@@ -162,3 +162,19 @@ def test_from_reference_duck_typed_sdim3_ml_material(golden):
     ref.sdim = 4
     with pytest.raises(ValueError):
         FE.Material.from_reference(ref)
+
+
+def test_from_MLparam_parses_an_sdim3_export(golden):
+    """export_MLparam of an sdim = 3 model (Ndof = 2, written by the reference: tests/golden/mlparam_svc3-svm.csv,
+    make_golden.py gen_mlparam3) loads as an sdim = 3 material with the same SVC."""
+    import os
+    from pylabfea_b200 import _lib
+    g = golden('mlparam_svc3')
+    here = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden')
+    m = FE.Material.from_MLparam('mlparam_svc3', path=here + os.sep)
+    sv, dc, rho = m._svc
+    assert m.sdim == 3 and m.Ndof == 2 and sv.shape == (len(g['dual']), 6)
+    assert np.array_equal(sv[:, 0:2], g['sv']) and not sv[:, 2:].any() and np.array_equal(dc, g['dual'])
+    assert rho == float(g['rho']) and m.gam_yf == float(g['gamma']) and m.scale_seq == float(g['scale_seq']) == m.sy
+    assert np.allclose(m.CV, g['CV'], rtol=1e-15, atol=0.)
+    assert m._descriptor().kind == _lib.MAT_SVC3
