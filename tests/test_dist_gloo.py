@@ -10,9 +10,9 @@ import pytest
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-def _torchrun(args, port, timeout=300):
-    cmd = [sys.executable, '-m', 'torch.distributed.run', '--nnodes=1', '--nproc-per-node', '2', '--master-addr', '127.0.0.1',
-           '--master-port', str(port), os.path.join(ROOT, 'bench.py')] + args
+def _torchrun(args, port, timeout=300, nproc=2, script='bench.py'):
+    cmd = [sys.executable, '-m', 'torch.distributed.run', '--nnodes=1', '--nproc-per-node', str(nproc), '--master-addr', '127.0.0.1',
+           '--master-port', str(port), os.path.join(ROOT, script)] + args
     env = dict(os.environ)
     env.setdefault('OMP_NUM_THREADS', '1')
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=timeout, cwd=ROOT, env=env)
@@ -108,3 +108,18 @@ def test_unique_id_side_channel(tmp_path):
     assert reader.returncode == 0 and out == uid
     with pytest.raises(TimeoutError):
         share_bytes(str(tmp_path / 'missing'), 1, timeout=0.1)
+
+
+@pytest.mark.parametrize('nproc,port', [(2, 29641), (3, 29642)])
+def test_strip_partitioned_cg_rehearsal_over_gloo(nproc, port):
+    """The exchange pattern of the distributed solve (launch_cg_dist: ghost | fixed mask, one halo node column per
+    neighbour and iteration, all-reduced dot products, final halo of du) rehearsed on the CPU with real ranks over gloo
+    and numpy arithmetic (tests/dist_cg_gloo.py): every rank ends with the dense global solution on its node grid, all
+    ranks stop at the same iteration, and the owned rows of every strip stiffness equal the global rows.  3 ranks give
+    the middle rank ghosts on both sides."""
+    out = _torchrun([], port, nproc=nproc, script=os.path.join('tests', 'dist_cg_gloo.py'))
+    assert len(out) == 1
+    d = out[0]
+    assert d['world'] == nproc and d['owned_rows_equal_global']
+    assert len(set(d['iters'])) == 1 and 10 < d['iters'][0] < 5000
+    assert d['max_rel_err'] < 1e-9
