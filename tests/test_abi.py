@@ -51,3 +51,17 @@ def test_product_never_imports_the_oracle():
             if f.endswith(('.py', '.cu', '.cuh', '.h')):
                 src = open(os.path.join(root, f)).read()
                 assert 'oracle' not in src.lower().replace('no cpu fallback', ''), os.path.join(root, f)
+
+
+def test_header_is_plain_c(tmp_path):
+    """include/plfb200.h is the whole boundary: it must compile as C99 on its own (no C++ or CUDA types leak through)."""
+    import shutil
+    import subprocess
+    gcc = shutil.which('gcc')
+    if gcc is None:
+        pytest.skip('no gcc')
+    src = tmp_path / 'use_header.c'
+    src.write_text('#include "plfb200.h"\nint main(void) { plf_material m; (void)m; return PLF_MAT_SVC3 == 5 ? 0 : 1; }\n')
+    r = subprocess.run([gcc, '-std=c99', '-Wall', '-Werror', '-pedantic', '-fsyntax-only', '-I', os.path.join(ROOT, 'include'), str(src)],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
