@@ -426,6 +426,26 @@ def main():
                                                   'd2h_bytes_per_step': int(Nel * (8 + 48 + 48 + 4)),
                                                   'note': 'informational: grad_stiff and CSR(K) not copied back (on-device solve)'}
 
+        # informational third figure: the stiffness stays in HBM for the on-device solve (plf_solve_linear), everything the
+        # reference keeps on its element objects (sig, depl, elstiff = grad_stiff) returns to the host.  Never fatal.
+        try:
+            def konly_step():
+                ctx.step_host(b, hs, he, hd, fy=o_fy, sig_out=o_sig, depl=o_dp, ctan=o_ct, nsteps=o_ns)
+            for _ in range(2):
+                konly_step()
+            ctx.synchronize()
+            t0 = time.perf_counter()
+            for _ in range(ke):
+                konly_step()
+            ctx.synchronize()
+            k_ms = (time.perf_counter() - t0) * 1e3 / ke   # rank-local (no collective inside the try block)
+            e2e['device_resident_K'] = {'value': world * owned / (k_ms * 1e-3), 'ms_per_step': k_ms,
+                                        'd2h_bytes_per_step': int(Nel * (8 + 48 + 48 + 288 + 4)),
+                                        'note': 'informational, timed on rank 0 only: CSR(K) not copied back (consumed by the on-device '
+                                                'solve), grad_stiff returned'}
+        except Exception as exc:   # pragma: no cover
+            e2e['device_resident_K'] = {'error': str(exc)}
+
     if rank != 0:
         group.close()
         return
