@@ -1,7 +1,7 @@
 #!/usr/bin/env python3
 """Time the UNMODIFIED Python reference on a sample of bench.py's workload (build container only: needs /root/reference).
 
-    python scripts/time_reference_python.py [n_sample = 1500] [mesh N = 1024]
+    python scripts/time_reference_python.py [n_sample = 1500] [mesh N = 1024] [j2 | hill]
 
 SURVEY.md 8d / BASELINE.md plan item 2: replay (sig, epl, deps, CV) tuples of the 1024 x 1024 J2 bench workload (the same
 seeded generator, bench.synth_states) through the reference's Material.response (material.py:207-346) and through
@@ -30,14 +30,16 @@ warnings.filterwarnings('ignore')
 def main():
     n = int(sys.argv[1]) if len(sys.argv) > 1 else 1500
     N = int(sys.argv[2]) if len(sys.argv) > 2 else 1024
+    cfg = sys.argv[3] if len(sys.argv) > 3 else 'j2'
+    hill, khard = (None, bench.KHARD) if cfg == 'j2' else ([0.7, 1., 1.4, 1., 1.2, 0.8], 100.)   # BASELINE config 3
     FE = import_reference()
-    sig, epl, deps = bench.synth_states(N, seed=1234)
+    sig, epl, deps = bench.synth_states(N, seed=1234, khard=khard)
     rng = np.random.default_rng(5)
     idx = np.sort(rng.choice(len(sig), n, replace=False))
     sig, epl, deps = sig[idx], epl[idx], deps[idx]
     m = FE.Material()
     m.elasticity(E=bench.E_MOD, nu=bench.NU)
-    m.plasticity(sy=bench.SY, khard=bench.KHARD, sdim=6)
+    m.plasticity(sy=bench.SY, khard=khard, hill=hill, sdim=6)
     CV = np.array(m.CV)
 
     fy = np.zeros(n); so = np.zeros((n, 6)); dp = np.zeros((n, 6)); ct = np.zeros((n, 6, 6)); ns = np.zeros(n, dtype=np.int32)
@@ -48,7 +50,7 @@ def main():
         ns[i] = m.msg['nsteps']
     t_ref = time.perf_counter() - t0
 
-    om = orc.Mat(kind=orc.HILL, E=bench.E_MOD, nu=bench.NU, sy=bench.SY, khard=bench.KHARD)
+    om = orc.Mat(kind=orc.HILL, E=bench.E_MOD, nu=bench.NU, sy=bench.SY, khard=khard, hill=hill)
     t0 = time.perf_counter()
     ofy, oso, odp, oct_, ons = orc.response_batch([om], None, sig, epl, deps, CV[None])
     t_orc = time.perf_counter() - t0
@@ -77,7 +79,7 @@ def main():
         'what': 'unmodified pyLabFEA reference (Python, single core) on a seeded sample of the bench workload',
         'host': {'cpu': open('/proc/cpuinfo').read().split('model name')[1].split('\n')[0].strip(': \t'), 'nproc': os.cpu_count(),
                  'where': 'build container (the reference cannot travel to the GPU box)'},
-        'workload': '%d elements sampled (seed 5) from bench.synth_states(%d, seed=1234), J2 sy=150 khard=500' % (n, N),
+        'workload': '%d elements sampled (seed 5) from bench.synth_states(%d, seed=1234), %s' % (n, N, 'J2 sy=150 khard=500' if cfg == 'j2' else 'Hill-6p [0.7,1,1.4,1,1.2,0.8] sy=150 khard=100 (BASELINE config 3)'),
         'branches': {'elastic': elastic, 'substep50': sub50, 'other': n - elastic - sub50},
         'reference_response_s': t_ref, 'reference_updates_per_s_1core': n / t_ref,
         'oracle_port_response_s': t_orc, 'oracle_port_updates_per_s_1core': n / t_orc,
@@ -86,7 +88,7 @@ def main():
                                                'sig_rel': rel(oso, so), 'depl_rel': rel(odp, dp), 'ctan_rel': rel(oct_, ct)},
         'reference_calc_Kel_plus_setupK_32x32_s_best_of_3': min(tk), 'reference_assembly_elements_per_s_1core': 1024 / min(tk),
     }
-    with open(os.path.join(ROOT, 'profiles', 'r1_reference_python_timing.json'), 'w') as f:
+    with open(os.path.join(ROOT, 'profiles', 'r1_reference_python_timing%s.json' % ('' if cfg == 'j2' else '_' + cfg)), 'w') as f:
         json.dump(out, f, indent=1)
     print(json.dumps(out, indent=1))
 
