@@ -256,6 +256,234 @@ class RankGroup:
             self.dist.destroy_process_group()
 
 
+# ---------------------------------------------------------------------------------------------------------------------
+# BASELINE.json configs 1-5 (the headline line is the 1024 x 1024 target; these ride along in its `configs` block, and
+# `--config cN` makes one of them the workload of the run, e.g. under ncu)
+# ---------------------------------------------------------------------------------------------------------------------
+FP64_PEAK_TFLOPS = 148 * 2 * 32 * 2 * 1.965e9 / 1e12   # 2 warp-DFMA / clk / SM (profiles/r1_microbench_dfma_lat.txt) at 1965 MHz
+GOLDEN = os.path.join(ROOT, 'tests', 'golden')
+
+
+def config_material(name):
+    """(plf_material descriptor, kernel label, synthetic-state keywords, mesh N) of a BASELINE config."""
+    import pylabfea_b200 as FE
+    if name in ('c2', 'target'):
+        mat, _ = j2_material()
+        return mat, 'response_passA_kernel + response_passB_kernel', dict(), 256 if name == 'c2' else 1024
+    if name == 'c3':
+        m = FE.Material()
+        m.elasticity(E=200.e3, nu=0.3)
+        m.plasticity(sy=150., hill=[0.7, 1., 1.4, 1., 1.2, 0.8], khard=100., sdim=6)
+        return m._descriptor(), 'response_passA_kernel + response_passB_kernel (Hill mode)', dict(khard=100.), 512
+    if name == 'c4':
+        g = dict(np.load(os.path.join(GOLDEN, 'svc_hill.npz')))
+        m = FE.Material('ML-Hill-p1')
+        m.elasticity(CV=g['CV'])
+        m.plasticity(sy=float(g['sy']), sdim=6)
+        m.set_svc(g['sv'], g['dual'], float(g['rho']), float(g['gamma']), scale_seq=float(g['scale_seq']))
+        return m._descriptor(), 'response_svc_kernel (1585 support vectors)', dict(sy=float(g['sy']), khard=0., deps_scale=1. / 3.), 512
+    if name == 'c5':
+        g = dict(np.load(os.path.join(GOLDEN, 'barlat_response.npz')))
+        m = FE.Material('Goss-Barlat')
+        m.elasticity(E=float(g['E']), nu=float(g['nu']))
+        m.plasticity(sy=float(g['sy']), khard=0., barlat=list(g['bp']), barlat_exp=int(g['barlat_exp']), sdim=6)
+        return m._descriptor(), 'response_barlat kernels', dict(sy=float(g['sy']), khard=0., deps_scale=1. / 3.), 2048
+    raise SystemExit('unknown config ' + name)
+
+
+def profile_json(name):
+    try:
+        return json.load(open(os.path.join(ROOT, 'profiles', name)))
+    except Exception:
+        return {}
+
+
+def run_kernel_config(name, device, reps, peak, opts=()):
+    """Return mapping + assembly of one BASELINE config on synthetic states: inputs resident in HBM, CUDA events on the
+    context's stream, L2 flushed before every repetition (the small meshes would otherwise sit in the 126 MB L2)."""
+    from pylabfea_b200 import _lib
+    mat, kernel, kw, N = config_material(name)
+    ctx = _lib.Context(device)
+    for kv in opts:
+        k, v = kv.split('=')
+        ctx.set_option(k, int(v))
+    n = N * N
+    sig, epl, deps = synth_states(N, 1234, **kw)
+    ctx.set_materials([mat], planestress=False)
+    lx = 4. / N
+    ctx.mesh_structured(N, N, np.full(N, lx), lx, 1., np.zeros(n, np.int32))
+    b = ctx.batch_create(n)
+    ctx.batch_upload(b, sig, epl, deps)
+    l0 = ctx.launch_count()
+    for _ in range(3 if name not in ('c4',) else 1):
+        ctx.batch_run(b)
+        ctx.setupK_from_batch(b)
+    ctx.synchronize()
+    t_resp, t_asm = [], []
+    for i in range(reps):
+        ctx.flush_l2()
+        ctx.event_record(0)
+        ctx.batch_run(b)
+        ctx.event_record(1)
+        ctx.setupK_from_batch(b)
+        ctx.event_record(2)
+        ctx.synchronize()
+        t_resp.append(ctx.event_elapsed(0, 1))
+        t_asm.append(ctx.event_elapsed(1, 2))
+    launches = ctx.launch_count() - l0
+    ns = np.empty(n, dtype=np.int32)
+    ct = np.empty((n, 6, 6))
+    ctx.batch_download(b, ctan=ct, nsteps=ns)
+    cv = ctx.element_CV(0)
+    n_el = int(np.sum(np.all(ct.reshape(n, 36) == cv.ravel()[None, :], axis=1)))
+    n50 = int(np.sum(ns == 49))
+    tr, ta = float(np.median(t_resp)), float(np.median(t_asm))
+    ach = BYTES_PER_UPDATE * n / (tr * 1e-3) / 1e9
+    ach_a = BYTES_PER_ASSEMBLED * n / (ta * 1e-3) / 1e9
+    fp = profile_json('fp64_ops.json').get(name)   # FP64 flop per update counted by ncu on this config (scripts/summarize_ncu.py)
+    out = {'workload': '%dx%d Q4 mesh, %s, synthetic correlated states (seed 1234), L2 flushed between repetitions' % (N, N, kernel),
+           'elements': n, 'reps': reps, 'response_ms': tr, 'updates_per_s': n / (tr * 1e-3), 'assembly_ms': ta,
+           'assembly_elems_per_s': n / (ta * 1e-3), 'ms_per_step': tr + ta, 'elements_per_s': n / ((tr + ta) * 1e-3),
+           'branch_mix': {'elastic': n_el / n, 'substep50': n50 / n, 'plastic_1step': 1. - (n_el + n50) / n},
+           'roofline': {'bound': 'hbm', 'achieved': ach, 'peak': peak, 'unit': 'GB/s', 'frac': ach / peak,
+                        'assembly': {'achieved': ach_a, 'frac': ach_a / peak}},
+           'gpu_launches': int(launches)}
+    if fp:
+        tf = fp['flop_per_update'] * n / (tr * 1e-3) / 1e12
+        out['roofline_fp64'] = {'bound': 'fp64', 'achieved': tf, 'peak': FP64_PEAK_TFLOPS, 'unit': 'TFLOP/s', 'frac': tf / FP64_PEAK_TFLOPS,
+                                'flop_per_update': fp['flop_per_update'], 'source': fp.get('source')}
+    ctx.batch_destroy(b)
+    ctx.close()
+    return out
+
+
+def inclusion_model(N, eps, device=0):
+    """examples/inclusion.py pattern: J2 matrix (sy=150, khard=500) with a soft elastic inclusion in the
+    middle third, uniaxial-y displacement control, corner pin."""
+    import pylabfea_b200 as FE
+    n1 = N // 3
+    el = np.ones((N, N))
+    el[n1:2 * n1, n1:2 * n1] = 2
+    mat1 = FE.Material(num=1)
+    mat1.elasticity(E=E_MOD, nu=NU)
+    mat1.plasticity(sy=SY, khard=KHARD, sdim=6)
+    mat2 = FE.Material(num=2)
+    mat2.elasticity(E=3.e3, nu=0.3)
+    fe = FE.Model(dim=2, planestress=False, device=device)
+    fe.geom(sect=2, LX=4., LY=4.)
+    fe.assign([mat1, mat2])
+    fe.bcbot(0.)
+    fe.bcright(0., 'force')
+    fe.bcleft(0., 'force')
+    fe.bctop(eps * fe.leny, 'disp')
+    fe.mesh(elmts=el, NX=N, NY=N)
+    fe.bcnode(0, 0., 'disp', 'x')
+    fe.solver_rtol = 1.e-10
+    return fe
+
+
+def run_load_sequence(N, min_step, eps, device=0):
+    """Model.solve through the public API: every increment runs on the device (plf_load_increment).  Wall clock around
+    solve() (host buffers: only the boundary description goes in and the increment reports come back)."""
+    fe = inclusion_model(N, eps, device)
+    ctx = fe._dev()
+    l0 = ctx.launch_count()
+    t0 = time.perf_counter()
+    fe.solve(min_step=min_step)
+    dt = time.perf_counter() - t0
+    its = np.array([s[0] for s in fe.solver_stats])
+    passes = int(sum(max(n, 0) for n in fe.niter)) + len(fe.niter)
+    out = {'workload': '%dx%d inclusion mesh (J2 sy=150 khard=500 + elastic inclusion), uniaxial eps=%g, Model.solve(min_step=%d)'
+                       % (N, N, eps, min_step),
+           'elements': N * N, 'dofs': int(fe.Ndof), 'increments': int(fe.nsteps), 'inner_passes': [int(x) for x in fe.niter],
+           'linear_solves': int(len(its)), 'cg_iterations': int(its.sum()), 'seconds': dt,
+           'ms_per_increment': dt * 1e3 / max(fe.nsteps, 1),
+           'element_updates_per_s': float(sum(sum(s[5][:3]) for s in fe.sweep_stats) / dt),
+           'gpu_launches': int(ctx.launch_count() - l0), 'launches_per_solve': float((ctx.launch_count() - l0) / max(len(its), 1)),
+           'global_stress_yy': float(fe.glob['sig'][1]), 'substep50_final': float(fe.sweep_stats[-1][5][2] / max(sum(fe.sweep_stats[-1][5][:3]), 1)) if fe.sweep_stats else 0.}
+    return out, fe
+
+
+def run_c1(device):
+    """BASELINE config 1: 10 x 10 linear-elastic cantilever (plane stress) through Model.setupK + Model.solve."""
+    import pylabfea_b200 as FE
+    mat = FE.Material()
+    mat.elasticity(E=200.e3, nu=0.3)
+    fe = FE.Model(dim=2, planestress=True, device=device)
+    fe.geom([10.], LY=1.)
+    fe.assign([mat])
+    fe.bcleft(0., 'disp', 'x')
+    fe.bcleft(0., 'disp', 'y')
+    fe.bcbot(0., 'force', 'y')
+    fe.bctop(0., 'force', 'y')
+    fe.bcright(-10., 'force', 'y')
+    fe.mesh(NX=10, NY=10)
+    fe.solve()            # warm-up (JIT-free, but first launches / graph capture)
+    reps = 20
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        fe.mesh(NX=10, NY=10)         # forget the solution: the next solve starts from the zero state again
+        fe.solve()
+    dt = (time.perf_counter() - t0) / reps
+    tip = float(fe.u[2 * fe.noright[-1] + 1])
+    return {'workload': '10x10 linear-elastic cantilever, plane stress, Model.solve (setupK + reduced CG solve), wall clock',
+            'elements': 100, 'ms_per_mesh_and_solve': dt * 1e3, 'elements_per_s': 100 / dt, 'tip_uy': tip,
+            'reference_tip_uy': -0.14455, 'note': 'latency-bound: ~40 kernel launches for 242 dofs'}
+
+
+def cpu_load_step_estimate(seq):
+    """What the same load sequence costs on the host, from measured pieces (labelled an estimate: the reference cannot
+    allocate its dense K beyond ~128 x 128): per inner pass one threaded oracle step over all plastic
+    elements (C port, all host threads) + one sparse direct solve (scipy SuperLU) of a 2-d elasticity system of the same
+    size class, measured here on a 256 x 256 mesh and scaled by dof^1.5 (nested-dissection flop count of a 2-d mesh)."""
+    from oracle import oracle as orc
+    import scipy.sparse as sp
+    import scipy.sparse.linalg as spla
+    cores = host_cores()
+    n = 200000
+    sig, epl, deps = synth_states(512, 1234)
+    _, CV = j2_material()
+    mats = [orc.Mat(kind=orc.HILL, E=E_MOD, nu=NU, sy=SY, khard=KHARD)]
+    lx = 4. / 512
+    B4 = orc.gauss_bmats(lx, lx, 0, CV, E_MOD, NU)
+    t0 = time.perf_counter()
+    oracle_step(orc, mats, CV, sig[:n], epl[:n], deps[:n], B4, lx * lx * 4., cores)
+    per_elem = (time.perf_counter() - t0) / n
+    m = 256   # 2-d vector Laplacian stand-in with the 9-point x 2-dof sparsity of the Q4 stiffness
+    I = sp.identity(m + 1, format='csr')
+    T = sp.diags([-1., 2.4, -1.], [-1, 0, 1], shape=(m + 1, m + 1), format='csr')
+    A = sp.kron(sp.kron(T, I) + sp.kron(I, T) + 0.25 * sp.kron(T, T), sp.csr_matrix(np.array([[1., .2], [.2, 1.]])), format='csc')
+    rhs = np.ones(A.shape[0])
+    t0 = time.perf_counter()
+    spla.spsolve(A, rhs)
+    t_solve_256 = time.perf_counter() - t0
+    scale = (seq['dofs'] / A.shape[0]) ** 1.5
+    passes = seq['linear_solves']
+    est = passes * (per_elem * seq['elements'] + t_solve_256 * scale)
+    return {'kind': 'estimate from measured pieces', 'cores': cores, 'seconds': est, 'ms_per_increment': est * 1e3 / max(seq['increments'], 1),
+            'oracle_step_s_per_element': per_elem, 'spsolve_256x256_s': t_solve_256, 'spsolve_scaling': 'dof^1.5 -> x%.1f' % scale,
+            'passes': passes}
+
+
+def configs_block(device, peak, quick=False):
+    out = {}
+    for name, fn in (('c1', lambda: run_c1(device)),
+                     ('c2', lambda: run_kernel_config('c2', device, 20, peak)),
+                     ('c3', lambda: run_kernel_config('c3', device, 20, peak)),
+                     ('c4', lambda: run_kernel_config('c4', device, 1 if quick else 2, peak)),
+                     ('c5', lambda: run_kernel_config('c5', device, 2 if quick else 3, peak))):
+        try:
+            out[name] = fn()
+        except Exception as exc:   # a config must never take the headline down with it
+            out[name] = {'error': '%s: %s' % (type(exc).__name__, exc)}
+    try:
+        seq, _ = run_load_sequence(256, 20, 0.01, device)
+        out['c2']['load_sequence'] = seq
+    except Exception as exc:
+        out['c2']['load_sequence'] = {'error': '%s: %s' % (type(exc).__name__, exc)}
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--dist-selftest', action='store_true')
@@ -270,6 +498,9 @@ def main():
     ap.add_argument('--compact', type=int, default=1)
     ap.add_argument('--assembly-tiled', type=int, default=2)
     ap.add_argument('--opt', action='append', default=[], help='extra plf_set_option key=value (A/B measurements)')
+    ap.add_argument('--config', default='target', help="target (default) | c2 | c3 | c4 | c5: workload of this run; the default run "
+                    "carries all BASELINE configs in its `configs` block")
+    ap.add_argument('--no-configs', action='store_true', help='skip the configs block and the load-sequence key')
     args = ap.parse_args()
 
     rank = int(os.environ.get('RANK', '0'))
@@ -277,6 +508,24 @@ def main():
     local = int(os.environ.get('LOCAL_RANK', '0'))
     if args.impl == 'reference':
         run_reference(args, rank, world)
+        return
+
+    if args.config != 'target':
+        # one BASELINE config as the workload of this run (single GPU; rank 0 only under torchrun)
+        if rank == 0:
+            peaks = profile_json('../MEASURED_PEAKS.json')
+            peak = float(peaks.get('hbm_gbs', 6650.))
+            sampler = ClockSampler(local)
+            sampler.start()
+            c = run_kernel_config(args.config, local, max(args.steps, 1), peak, args.opt)
+            line = {'metric': METRIC, 'value': c['elements_per_s'], 'unit': 'elements/s', 'n_gpus': 1, 'steps': c['reps'],
+                    'warmup': 3, 'ms_per_step': c['ms_per_step'], 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
+                    'dtype': 'f64', 'data': 'synthetic', 'config': {'workload': c['workload'], 'elements': c['elements'],
+                                                                   'l2': 'flushed before every repetition'},
+                    'roofline': c['roofline'], 'roofline_fp64': c.get('roofline_fp64'), 'branch_mix': c['branch_mix'],
+                    'updates_per_s': c['updates_per_s'], 'assembly_elems_per_s': c['assembly_elems_per_s'], 'cpu_baseline': None,
+                    'e2e': None, 'gpu_launches': c['gpu_launches'], 'clocks': sampler.stop()}
+            print(json.dumps(line))
         return
 
     plan = shard_plan(args.mesh, rank, world)
@@ -510,6 +759,17 @@ def main():
             'roofline': roofline, 'cpu_baseline': cpu, 'e2e': e2e, 'gpu_launches': int(gpu_launches),
             'launches_per_step': launches_per_step, 'clocks': clocks, 'wall_s_timed_region': t_wall,
             'device': ctx.device_info()['name']}
+    if world == 1 and not args.no_configs:
+        # every BASELINE config next to the headline, and a whole load sequence through Model.solve (the path that keeps
+        # an increment on the device: predictor + calc_scf + inner passes + commit per increment)
+        ctx.synchronize()
+        line['configs'] = configs_block(local, peak, quick=args.steps < 50)
+        try:
+            seq, _ = run_load_sequence(N, 5, 0.004, local)
+            line['e2e_load_step'] = dict(seq, unit='ms per load increment', value=seq['ms_per_increment'],
+                                         cpu_reference=cpu_load_step_estimate(seq) if not args.no_cpu else None)
+        except Exception as exc:
+            line['e2e_load_step'] = {'error': '%s: %s' % (type(exc).__name__, exc)}
     print(json.dumps(line))
     group.close()
 

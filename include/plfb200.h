@@ -211,6 +211,60 @@ int plf_calc_scf(plf_ctx *ctx, const double *sld, double *scf);
 int plf_solve_linear(plf_ctx *ctx, const uint8_t *fixed, const double *du_bc, const double *w, const double *f_ext,
                      double rtol, int max_iter, int *iters, double *relres);
 
+/* ---- load-increment controller (model.py:1208-1450) ------------------------------------------------------------- */
+/* Model.solve's loop over load increments on the library side of the boundary, so that an increment -- elastic
+ * predictor, calc_scf, the Newton-like passes (setupK, reduced solve, response sweep with tangent replacement),
+ * the commit and calc_global -- runs without per-pass host round trips through the binding.  The boundary-condition
+ * vectors of calc_BC (model.py:1070-1206) are built here from the plain description below (O(boundary) host work,
+ * scattered into device vectors).  Behaviour restated, not re-designed: same increment sizes, same halving rule for
+ * il < 6 and nit > 1 (1308-1330), same termination test (1395-1411), same nsteps / niter / co_nconv. */
+typedef struct plf_bc {
+    double left[2], bot[2];                 /* Model.bcl, bcb: static values                                   */
+    double right[2], top[2], node[2];       /* Model.bcr, bct, bcn: targets of the incremented conditions      */
+    int32_t left_disp[2], bot_disp[2], right_disp[2], top_disp[2], node_disp[2]; /* ubc*: 1 displacement, 0 force */
+    int32_t n_noset;                        /* Model.noset (bcnode): number of nodes, 0 = none                 */
+    int32_t pad_;
+    const int32_t *noset;                   /* node ids j*(NY+1)+k of the GLOBAL mesh                          */
+} plf_bc;
+
+typedef struct plf_load_state {
+    double reached_right[2], reached_top[2], reached_node[2];   /* bcr0, bct0, bcn0 (in/out: Model.bcr_mem ...) */
+    int32_t il;       /* increments completed in this Model.solve call                                          */
+    int32_t nconv;    /* passes without plastic convergence so far (co_nconv)                                   */
+    int32_t more;     /* out: 1 while a target is not reached (bc_inc, 1411)                                    */
+    int32_t pad_;
+} plf_load_state;
+
+#define PLF_MAX_PASSES 17   /* the inner loop runs while nit <= 15 (1305): at most 16 passes */
+typedef struct plf_increment_report {
+    int32_t passes;                 /* nit when the inner loop ended (niter gets passes - 1; linear models: 0)   */
+    int32_t solves;                 /* linear solves of this increment                                           */
+    int64_t cg_iterations;
+    double max_relres;              /* largest relative residual any of these solves stopped at                  */
+    double scale_bc;                /* calc_scf result (1296)                                                    */
+    double step_right[2], step_top[2], step_node[2];   /* increment finally applied: dbcr, dbct, dbcn           */
+    double glob_sig[6], glob_eps[6], glob_epl[6];      /* calc_global element part (1500-1511)                  */
+    double edge[4][4];              /* bcval of left, right, bottom, top nodes: mean ux, mean uy, sum fx, sum fy */
+    /* per pass (verbose output, statistics) */
+    int32_t pass_change[PLF_MAX_PASSES], pass_conv[PLF_MAX_PASSES];
+    double pass_max_hh[PLF_MAX_PASSES];
+    int64_t pass_counts[PLF_MAX_PASSES][4];   /* elastic, 1 step, 50 sub-steps, radial corrections              */
+    int32_t pass_cg_iters[PLF_MAX_PASSES + 1];/* [0] predictor solve, [1 + nit] the solve of pass nit          */
+    int32_t n_warnings;             /* inconsistent displacement BCs met while building the vectors             */
+    char warning[200];              /* text of the first one (the reference warns, model.py:1119, 1137, 1167)   */
+} plf_increment_report;
+
+/* First part of Model.solve (1214-1258): `reset` != 0 zeroes u, f and the element state and sets elstiff = CV (first
+ * call after meshing); assembles K (1242); stores the boundary description and the loading direction sld. */
+int plf_solve_begin(plf_ctx *ctx, const plf_bc *bc, int reset);
+/* One pass of the `while bc_inc` loop (1270-1418).  min_step <= 0: None.  rtol / max_iter: linear solver. */
+int plf_load_increment(plf_ctx *ctx, plf_load_state *st, int min_step, double rtol, int max_iter,
+                       plf_increment_report *rep);
+/* Model.bcval (1452-1471) for the four edges from the device-resident u and f: edge[left,right,bottom,top][mean ux,
+ * mean uy, sum fx, sum fy]. */
+int plf_boundary_values(plf_ctx *ctx, double edge[4][4]);
+size_t plf_sizeof_increment_report(void);
+
 /* ---- strip-partitioned solve over several GPUs (one process per GPU) -------------------------------------------- */
 /* The reference has no counterpart (it is a single-process NumPy code); SURVEY.md 8e: rank g holds the strip of
  * element columns it owns plus one halo element column on its left (pylabfea_b200/shard.py), so the rows of K of its

@@ -28,6 +28,34 @@ class PlfMaterial(C.Structure):
                 ('svc_sv', _dp), ('svc_dual', _dp)]
 
 
+MAX_PASSES = 17
+
+
+class PlfBC(C.Structure):
+    """struct plf_bc (include/plfb200.h): Model.bcl / bcb / bcr / bct / bcn and the ubc* flags as plain data"""
+    _fields_ = [('left', C.c_double * 2), ('bot', C.c_double * 2), ('right', C.c_double * 2), ('top', C.c_double * 2),
+                ('node', C.c_double * 2), ('left_disp', C.c_int32 * 2), ('bot_disp', C.c_int32 * 2),
+                ('right_disp', C.c_int32 * 2), ('top_disp', C.c_int32 * 2), ('node_disp', C.c_int32 * 2),
+                ('n_noset', C.c_int32), ('pad_', C.c_int32), ('noset', _ip)]
+
+
+class PlfLoadState(C.Structure):
+    """struct plf_load_state: boundary values reached so far, increment counter, continuation flag"""
+    _fields_ = [('reached_right', C.c_double * 2), ('reached_top', C.c_double * 2), ('reached_node', C.c_double * 2),
+                ('il', C.c_int32), ('nconv', C.c_int32), ('more', C.c_int32), ('pad_', C.c_int32)]
+
+
+class PlfIncrementReport(C.Structure):
+    """struct plf_increment_report: what one load increment did"""
+    _fields_ = [('passes', C.c_int32), ('solves', C.c_int32), ('cg_iterations', C.c_int64), ('max_relres', C.c_double),
+                ('scale_bc', C.c_double), ('step_right', C.c_double * 2), ('step_top', C.c_double * 2),
+                ('step_node', C.c_double * 2), ('glob_sig', C.c_double * 6), ('glob_eps', C.c_double * 6),
+                ('glob_epl', C.c_double * 6), ('edge', (C.c_double * 4) * 4),
+                ('pass_change', C.c_int32 * MAX_PASSES), ('pass_conv', C.c_int32 * MAX_PASSES),
+                ('pass_max_hh', C.c_double * MAX_PASSES), ('pass_counts', (C.c_int64 * 4) * MAX_PASSES),
+                ('pass_cg_iters', C.c_int32 * (MAX_PASSES + 1)), ('n_warnings', C.c_int32), ('warning', C.c_char * 200)]
+
+
 class PlfError(RuntimeError):
     pass
 
@@ -58,6 +86,9 @@ def load():
     L.plf_sizeof_material.restype = C.c_size_t
     if L.plf_sizeof_material() != C.sizeof(PlfMaterial):
         raise PlfError('plf_material layout mismatch between libplfb200.so and the ctypes binding')
+    L.plf_sizeof_increment_report.restype = C.c_size_t
+    if L.plf_sizeof_increment_report() != C.sizeof(PlfIncrementReport):
+        raise PlfError('plf_increment_report layout mismatch between libplfb200.so and the ctypes binding')
     _lib = L
     return L
 
@@ -363,6 +394,24 @@ class Context:
         self._ck(self.L.plf_solve_linear(self.h, _ptr(fixed), _ptr(du_bc), _ptr(w), _ptr(f_ext), C.c_double(rtol),
                                          int(max_iter), C.byref(it), C.byref(rr)))
         return it.value, rr.value
+
+    # ---- load-increment controller (plf_solve_begin / plf_load_increment) -----------------------------------
+    def solve_begin(self, bc, reset):
+        """bc: PlfBC.  reset: zero u, f and the element state (first Model.solve after meshing)."""
+        self._ck(self.L.plf_solve_begin(self.h, C.byref(bc), int(bool(reset))))
+
+    def load_increment(self, state, min_step, rtol, max_iter):
+        """One load increment (model.py:1270-1418); `state` (PlfLoadState) is updated in place."""
+        rep = PlfIncrementReport()
+        self._ck(self.L.plf_load_increment(self.h, C.byref(state), int(min_step or 0), C.c_double(rtol), int(max_iter),
+                                           C.byref(rep)))
+        return rep
+
+    def boundary_values(self):
+        """Model.bcval of the left, right, bottom and top nodes: rows (mean ux, mean uy, sum fx, sum fy)."""
+        e = ((C.c_double * 4) * 4)()
+        self._ck(self.L.plf_boundary_values(self.h, e))
+        return np.array([[e[i][j] for j in range(4)] for i in range(4)])
 
     # ---- strip-partitioned solve over several GPUs (plf_comm_*) --------------------------------------------
     def comm_init(self, unique_id, rank, world):

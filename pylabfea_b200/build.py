@@ -26,6 +26,7 @@ UNITS = {
     'assembly_kernels.cu': ['-fmad=false'],
     'plf_api.cu': [],
     'plf_model.cu': [],
+    'plf_solve.cu': [],
     'plf_comm.cu': [],
 }
 

@@ -268,7 +268,7 @@ __global__ void __launch_bounds__(2 * SN, MINB) assemble_rows_staged_kernel(int 
     for (int i = tid; i < n2; i += 2 * SN) dst[i] = s_out[i];
 }
 
-static int g_tiled = 2;   // 0: row per thread, direct stores; 2: row per thread, staged stores (production)
+// LaunchCtx::assembly_tiled -- 0: row per thread, direct stores; 2: row per thread, staged stores (production)
 // (a shared-memory tiled variant -- coalesced tile loads of the tangents, 3 barriers -- measured 0.27 ms against
 //  0.15 ms for the staged row kernel at 1024^2 and was removed)
 
@@ -322,7 +322,7 @@ cudaError_t launch_assemble_columns(const LaunchCtx &lc, int NX, int NY, int pla
 cudaError_t launch_assemble(const LaunchCtx &lc, int NX, int NY, int planestress, int ngeom, const int32_t *elem_desc,
                             const double *elstiff, const int32_t *rowptr, double *val, int64_t *launches)
 {
-    if (g_tiled != 0) {
+    if (lc.assembly_tiled != 0) {
         const dim3 grid((NY + 1 + SN - 1) / SN, NX + 1);
 #define ASM(PS, U, M) assemble_rows_staged_kernel<PS, U, M><<<grid, 2 * SN, 0, lc.stream>>>(NX, NY, 0, elem_desc, elstiff, val)
         const bool uni = (ngeom == 1);
@@ -340,8 +340,6 @@ cudaError_t launch_assemble(const LaunchCtx &lc, int NX, int NY, int planestress
     (*launches)++;
     return cudaGetLastError();
 }
-
-void assembly_set_tiled(int on) { g_tiled = on; }
 
 cudaError_t launch_kel(const LaunchCtx &lc, int64_t Nel, int planestress, const int32_t *elem_desc, const double *elstiff,
                        double *Kel, int64_t *launches)

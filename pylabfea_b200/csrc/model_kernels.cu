@@ -930,21 +930,12 @@ __global__ void __launch_bounds__(256) cg_init_warm_kernel(int64_t n, const doub
     }
 }
 
-struct CgGraphCache {
-    cudaGraphExec_t exec = nullptr;
-    int64_t n = 0;
-    const void *key[6] = {nullptr};
-    int chunk = 0;
-    cudaStream_t stream = nullptr;
-    int64_t launches_per_chunk = 0;
-};
-static CgGraphCache g_cg;
 
 cudaError_t launch_cg(const LaunchCtx &lc, int64_t n, const int32_t *rowptr, const int32_t *col, const double *val,
                       const unsigned char *fixed, const double *b, double *x, double *r, double *z, double *p, double *q,
                       double *diag, double *partial, unsigned int *counter, void *d_sc, void *h_sc, double rtol, int max_iter,
                       int check_every, int *iters, double *relres, int64_t *launches, MgHierarchy *mg, int warm, int NX,
-                      int NY)
+                      int NY, CgGraphCache &g_cg, int mg_setup_needed)
 {
     CgScalars *sc = (CgScalars *)d_sc;
     CgScalars *hs = (CgScalars *)h_sc;
@@ -965,7 +956,7 @@ cudaError_t launch_cg(const LaunchCtx &lc, int64_t n, const int32_t *rowptr, con
     }
     if (mg) {
         // z = V(r), r.z, p = z with the multigrid preconditioner (the Jacobi z / p / r.z of cg_init_kernel are replaced)
-        if ((e = mg_setup(lc, *mg, val, fixed, launches)) != cudaSuccess) return e;
+        if (mg_setup_needed && (e = mg_setup(lc, *mg, val, fixed, launches)) != cudaSuccess) return e;
         if ((e = mg_vcycle(lc, *mg, r, z, launches)) != cudaSuccess) return e;
         cg_rz_kernel<0><<<vg, 256, 0, lc.stream>>>(n, r, z, fixed, sc, partial, counter);
         (*launches)++;
@@ -1126,7 +1117,7 @@ cudaError_t launch_ghost_mask(const LaunchCtx &lc, int64_t n, int NY, int own_fi
     return cudaGetLastError();
 }
 
-void cg_graph_reset()
+void cg_graph_reset(CgGraphCache &g_cg)
 {
     if (g_cg.exec) cudaGraphExecDestroy(g_cg.exec);
     g_cg = CgGraphCache();
@@ -1145,6 +1136,78 @@ cudaError_t launch_merge_du(const LaunchCtx &lc, int64_t n, const double *x, con
                             int64_t *launches)
 {
     merge_du_kernel<<<vec_grid(n, lc.sm_count), 256, 0, lc.stream>>>(n, x, du_bc, fixed, du);
+    (*launches)++;
+    return cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// boundary-condition vectors and boundary sums of the load-increment controller (plf_solve.cu)
+// ---------------------------------------------------------------------------------------------------------------
+// calc_BC (model.py:1070-1206) touches boundary dofs only: the host builds the entries, this kernel scatters them
+// into the (zeroed) dense vectors the solver reads.
+__global__ void __launch_bounds__(256) bc_scatter_kernel(int n, const int32_t *__restrict__ dof, const unsigned char *__restrict__ fx,
+                                                         const double *__restrict__ vals /* [3][n]: du, w, fext */,
+                                                         unsigned char *__restrict__ fixed, double *__restrict__ du,
+                                                         double *__restrict__ w, double *__restrict__ fext)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int32_t d = dof[i];
+    fixed[d] = fx[i];
+    du[d] = vals[i];
+    w[d] = vals[n + i];
+    fext[d] = vals[2 * n + i];
+}
+
+// Model.bcval (model.py:1452-1471) sums for the four edges: block b = edge (left, right, bottom, top), out[4 b + {0..3}] =
+// sum ux, sum uy, sum fx, sum fy over the edge's nodes (bottom / top: node columns [c0, c1) only -- the columns a rank
+// owns).  Fixed summation order.
+__global__ void __launch_bounds__(256) edge_sums_kernel(int NX, int NY, int c0, int c1, const double *__restrict__ u,
+                                                        const double *__restrict__ f, double *__restrict__ out)
+{
+    __shared__ double sh[4][8];
+    const int edge = blockIdx.x, NnY = NY + 1;
+    const int cnt = edge < 2 ? NnY : (c1 - c0);
+    double v[4] = {0., 0., 0., 0.};
+    for (int i = threadIdx.x; i < cnt; i += blockDim.x) {
+        int64_t node;
+        if (edge == 0) node = i;
+        else if (edge == 1) node = (int64_t)NX * NnY + i;
+        else if (edge == 2) node = (int64_t)(c0 + i) * NnY;
+        else node = (int64_t)(c0 + i) * NnY + NY;
+        const double2 uu = *reinterpret_cast<const double2 *>(u + 2 * node);
+        const double2 ff = *reinterpret_cast<const double2 *>(f + 2 * node);
+        v[0] += uu.x; v[1] += uu.y; v[2] += ff.x; v[3] += ff.y;
+    }
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int q = 0; q < 4; q++) {
+        double x = v[q];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
+        if (lane == 0) sh[q][warp] = x;
+    }
+    __syncthreads();
+    if (threadIdx.x < 4) {
+        double x = 0.;
+        for (int w = 0; w < 8; w++) x += sh[threadIdx.x][w];
+        out[4 * edge + threadIdx.x] = x;
+    }
+}
+
+cudaError_t launch_bc_scatter(const LaunchCtx &lc, int n, const int32_t *dof, const unsigned char *fx, const double *vals,
+                              unsigned char *fixed, double *du, double *w, double *fext, int64_t *launches)
+{
+    if (n <= 0) return cudaSuccess;
+    bc_scatter_kernel<<<(n + 255) / 256, 256, 0, lc.stream>>>(n, dof, fx, vals, fixed, du, w, fext);
+    (*launches)++;
+    return cudaGetLastError();
+}
+
+cudaError_t launch_edge_sums(const LaunchCtx &lc, int NX, int NY, int c0, int c1, const double *u, const double *f, double *out,
+                             int64_t *launches)
+{
+    edge_sums_kernel<<<4, 256, 0, lc.stream>>>(NX, NY, c0, c1, u, f, out);
     (*launches)++;
     return cudaGetLastError();
 }

@@ -20,6 +20,16 @@ struct SweepStats {
     unsigned long long queue;       // SVC dynamic element queue
 };
 
+// CUDA graph of one chunk of CG iterations, owned by the context whose buffers it captured
+struct CgGraphCache {
+    cudaGraphExec_t exec = nullptr;
+    int64_t n = 0;
+    const void *key[6] = {nullptr};
+    int chunk = 0;
+    cudaStream_t stream = nullptr;
+    int64_t launches_per_chunk = 0;
+};
+
 cudaError_t modelk_init();
 cudaError_t modelk_upload_materials(const DevMat *h, int n, cudaStream_t st);
 cudaError_t modelk_upload_geom(const GeomClass *h, int n, cudaStream_t st);
@@ -42,10 +52,11 @@ cudaError_t launch_cg(const LaunchCtx &lc, int64_t n, const int32_t *rowptr, con
                       double *diag, double *partial, unsigned int *counter, void *d_sc, void *h_sc, double rtol, int max_iter,
                       int check_every, int *iters, double *relres, int64_t *launches, MgHierarchy *mg /* nullable: Jacobi */,
                       int warm /* 1: start from the previous content of x */, int NX, int NY /* structured mesh: the
-                      matrix product uses the closed-form CSR layout; NX = 0: generic CSR kernel */);
+                      matrix product uses the closed-form CSR layout; NX = 0: generic CSR kernel */, CgGraphCache &g_cg,
+                      int mg_setup_needed = 1 /* 0: the hierarchy was set up for this very K and mask */);
 cudaError_t launch_spmv(const LaunchCtx &lc, int64_t n, const int32_t *rowptr, const int32_t *col, const double *val, const double *x,
                         const double *rhs, double *y, const unsigned char *masked, int mode, int64_t *launches);
-void cg_graph_reset();   // drops the cached CUDA graph of the CG iteration chunk (call before freeing its buffers)
+void cg_graph_reset(CgGraphCache &g);   // drops the cached graph (call before freeing the buffers it captured)
 cudaError_t launch_cg_dist(const LaunchCtx &lc, Comm &comm, int64_t n, const int32_t *rowptr, const int32_t *col, const double *val,
                            const unsigned char *mask, const double *b, double *x, double *r, double *z, double *p, double *q,
                            double *diag, double *partial, unsigned int *counter, void *d_sc, void *h_sc, double rtol,
@@ -54,5 +65,9 @@ cudaError_t launch_ghost_mask(const LaunchCtx &lc, int64_t n, int NY, int own_fi
                               unsigned char *mask, int64_t *launches);
 cudaError_t launch_merge_du(const LaunchCtx &lc, int64_t n, const double *x, const double *du_bc, const unsigned char *fixed, double *du,
                             int64_t *launches);
+cudaError_t launch_bc_scatter(const LaunchCtx &lc, int n, const int32_t *dof, const unsigned char *fx, const double *vals,
+                              unsigned char *fixed, double *du, double *w, double *fext, int64_t *launches);
+cudaError_t launch_edge_sums(const LaunchCtx &lc, int NX, int NY, int c0, int c1, const double *u, const double *f, double *out,
+                             int64_t *launches);
 
 }  // namespace plf

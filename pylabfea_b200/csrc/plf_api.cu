@@ -7,9 +7,11 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <mutex>
 #include <string>
 #include <vector>
 
+#include "model_kernels.h"
 #include "plf_device.cuh"
 #include "plf_host.h"
 #include "plf_model.h"
@@ -22,6 +24,49 @@ int fail(plf_ctx *c, int code, const std::string &msg)
 {
     if (c) c->err = msg; else g_create_error = msg;
     return code;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// __constant__ bank ownership.  c_mat / c_geom (response_kernels.cu, model_kernels.cu, assembly_kernels.cu) exist once
+// per device; several contexts (a Model, the default context behind Material.calc_*, a second Model) share them.  The
+// context that launches next must find ITS tables there: plf_bind() is called at the head of every launch sequence.
+// ---------------------------------------------------------------------------------------------------------------
+static const int kMaxDevices = 64;
+static plf_ctx *g_bank_owner[kMaxDevices] = {nullptr};
+static std::mutex g_bank_mutex;
+
+int plf_bind(plf_ctx *ctx)
+{
+    if (!ctx) return PLF_EINVAL;
+    std::lock_guard<std::mutex> lock(g_bank_mutex);
+    const int dev = ctx->device;
+    cudaError_t e = cudaSetDevice(dev);
+    if (e != cudaSuccess) return fail(ctx, PLF_ECUDA, std::string("plf_bind: ") + cudaGetErrorString(e));
+    plf_ctx *prev = g_bank_owner[dev];
+    if (prev == ctx && !ctx->tables_dirty) return PLF_OK;
+    // kernels of the previous owner (asynchronous entry points: plf_batch_run, plf_setupK) may still read the banks
+    if (prev && prev != ctx) cudaStreamSynchronize(prev->stream);
+    if (prev == ctx) cudaStreamSynchronize(ctx->stream);
+    if (ctx->nmat > 0) {
+        if ((e = response_upload_materials(ctx->hmats, ctx->nmat, ctx->stream)) != cudaSuccess ||
+            (e = modelk_init()) != cudaSuccess ||
+            (e = modelk_upload_materials(ctx->hmats, ctx->nmat, ctx->stream)) != cudaSuccess)
+            return fail(ctx, PLF_ECUDA, std::string("plf_bind (materials): ") + cudaGetErrorString(e));
+    }
+    if (ctx->ngeom > 0) {
+        if ((e = assembly_upload_geom(ctx->geom, ctx->ngeom, ctx->stream)) != cudaSuccess ||
+            (e = modelk_upload_geom(ctx->geom, ctx->ngeom, ctx->stream)) != cudaSuccess)
+            return fail(ctx, PLF_ECUDA, std::string("plf_bind (geometry): ") + cudaGetErrorString(e));
+    }
+    g_bank_owner[dev] = ctx;
+    ctx->tables_dirty = false;
+    return PLF_OK;
+}
+
+static void bank_release(plf_ctx *ctx)
+{
+    std::lock_guard<std::mutex> lock(g_bank_mutex);
+    if (ctx->device >= 0 && ctx->device < kMaxDevices && g_bank_owner[ctx->device] == ctx) g_bank_owner[ctx->device] = nullptr;
 }
 
 #define CK(call)                                                                                        \
@@ -55,7 +100,7 @@ extern "C" int plf_create(int device, plf_ctx **out)
     if (e != cudaSuccess || ndev == 0)
         return fail(nullptr, PLF_ECUDA, std::string("plf_create: no CUDA device (") + cudaGetErrorString(e) +
                                             "); this library has no CPU fallback");
-    if (device < 0 || device >= ndev) return fail(nullptr, PLF_EINVAL, "plf_create: device index out of range");
+    if (device < 0 || device >= ndev || device >= kMaxDevices) return fail(nullptr, PLF_EINVAL, "plf_create: device index out of range");
     CK(cudaSetDevice(device));
     ctx = new plf_ctx();
     ctx->device = device;
@@ -94,6 +139,7 @@ extern "C" void plf_destroy(plf_ctx *ctx)
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
+    bank_release(ctx);
     for (int i = 0; i < PLF_MAX_MATERIALS; i++) { cudaFree(ctx->d_sv[i]); cudaFree(ctx->d_dual[i]); }
     free_batch_bufs(ctx->scratch);
     model_free(ctx);
@@ -298,9 +344,7 @@ extern "C" int plf_set_materials(plf_ctx *ctx, int nmat, const plf_material *mat
     ctx->nmat = nmat;
     ctx->planestress = planestress ? 1 : 0;
     ctx->mats.assign(mats, mats + nmat);
-    CK(response_upload_materials(ctx->hmats, nmat, ctx->stream));
-    CK(model_upload_materials(ctx));
-    CK(cudaStreamSynchronize(ctx->stream));
+    ctx->tables_dirty = true;   // uploaded to the __constant__ banks by the next plf_bind
     ctx->mesh_ready = false;   // geometry classes depend on the materials for plane stress
     return PLF_OK;
 }
@@ -371,7 +415,8 @@ extern "C" int plf_batch_run(plf_ctx *ctx, plf_batch *b)
         if (ctx->hmats[i].tresca && (ctx->hmats[i].kind == PLF_MAT_HILL || ctx->hmats[i].kind == PLF_MAT_HILL3))
             // material.py:824-825: the first plastic step of a Tresca material raises in the reference
             return fail(ctx, PLF_EUNSUPPORTED, "response: analytical gradient for Tresca not implemented");
-    LaunchCtx lc{ctx->stream, ctx->sm_count, ctx->passa_direct, ctx->max_fm, ctx->k1_only, ctx->passb_recur};
+    if (int brc = plf_bind(ctx)) return brc;
+    LaunchCtx lc = make_lc(ctx);
     CK(launch_response(lc, ctx->hmats, ctx->nmat, b->n, b->mat_id, b->sig, b->epl, b->deps, b->fy, b->sig_out, b->depl,
                        b->ctan, b->nsteps, b->worklist, (unsigned int *)(ctx->d_scalars + 16),
                        (unsigned long long *)(ctx->d_scalars + 8), ctx->compact, &ctx->launches));
@@ -396,13 +441,14 @@ extern "C" int plf_set_option(plf_ctx *ctx, const char *key, int value)
 {
     if (!ctx || !key) return PLF_EINVAL;
     if (!strcmp(key, "compact")) { ctx->compact = value; return PLF_OK; }
-    if (!strcmp(key, "assembly_tiled")) { assembly_set_tiled(value); return PLF_OK; }
+    if (!strcmp(key, "assembly_tiled")) { ctx->assembly_tiled = value; return PLF_OK; }
     if (!strcmp(key, "passa_direct")) { ctx->passa_direct = value; return PLF_OK; }
     if (!strcmp(key, "max_fm")) { ctx->max_fm = value; return PLF_OK; }
     if (!strcmp(key, "k1_only")) { ctx->k1_only = value; return PLF_OK; }
     if (!strcmp(key, "passb_recur")) { ctx->passb_recur = value; return PLF_OK; }
     if (!strcmp(key, "solver_mg")) { ctx->solver_mg = value; return PLF_OK; }
     if (!strcmp(key, "solver_warm")) { ctx->solver_warm = value; return PLF_OK; }
+    if (!strcmp(key, "skip_unchanged")) { ctx->skip_unchanged = value; return PLF_OK; }
     if (!strcmp(key, "mg_nu") || !strcmp(key, "mg_coarse_sweeps") || !strcmp(key, "mg_omega_permille")) {
         // multigrid tuning knobs (take effect at the next plf_mesh_structured / solve; the CG graph is rebuilt)
         if (!strcmp(key, "mg_nu")) ctx->mg_nu = value & ~1;
@@ -454,7 +500,8 @@ static int prim_call(plf_ctx *ctx, int op, int mat, int64_t n, const double *sig
         d_ld = (double *)(ctx->d_scalars + 64);
         CK(cudaMemcpyAsync(d_ld, ld, 6 * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
     }
-    LaunchCtx lc{ctx->stream, ctx->sm_count};
+    if (int brc = plf_bind(ctx)) return brc;
+    LaunchCtx lc = make_lc(ctx);
     CK(launch_prim(lc, ctx->hmats, op, mat, n, b.sig, epl ? b.epl : nullptr, deps ? b.deps : nullptr, d_ld, b.ctan,
                    &ctx->launches));
     CK(cudaMemcpyAsync(out, b.ctan, (size_t)out_w * N * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));

@@ -12,6 +12,11 @@ struct Comm {
     // owned node columns [own_first, own_end) of the local mesh; a ghost column is the one column outside on either side
     int own_first = 0, own_end = 0;
     bool strip_set = false;
+    // position of the strip in the global mesh (plf_comm_set_partition): needed by the load-increment controller for the
+    // boundary conditions (edges, force shares, node sets) and the global averages
+    bool global_set = false;
+    int first_col_global = 0, NX_global = 0;
+    double x_offset = 0., lenx_global = 0.;
     bool active() const { return nccl != nullptr; }
     bool ghost_left() const { return own_first > 0; }
     bool ghost_right(int NX) const { return own_end < NX + 1; }
@@ -23,6 +28,7 @@ int comm_unique_id(unsigned char *id128);                   // ncclGetUniqueId (
 int comm_init(Comm &c, const unsigned char *id128, int rank, int world);
 void comm_destroy(Comm &c);
 int comm_allreduce_sum(Comm &c, double *dbuf, int count, cudaStream_t s);   // in place, device pointer
+int comm_allreduce_op(Comm &c, double *dbuf, int count, int op /* 0 sum, 1 max, 2 min */, cudaStream_t s);
 // vec: nodal vector of the local (NX+1) x (NY+1) node grid, 2 dofs per node.  Sends the first / last owned node column to
 // the left / right neighbour and receives their last / first owned column into the ghost columns.
 int comm_halo_exchange(Comm &c, double *vec, int NX, int NY, cudaStream_t s);

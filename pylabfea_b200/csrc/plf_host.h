@@ -27,6 +27,7 @@ struct LaunchCtx {
     int max_fm = 4;        // cap of the single-material fast mode (hill_fast.cuh)
     int k1_only = 0;       // diagnostics: 1 = launch pass A only
     int passb_recur = 1;   // 1: planar isotropic J2 loop of pass B with scalar recurrences on the carried chain (hill_fast.cuh)
+    int assembly_tiled = 2;  // 2: row per thread with staged coalesced stores (production); 0: direct stores
 };
 
 // response_kernels.cu
@@ -41,7 +42,6 @@ cudaError_t launch_prim(const LaunchCtx &lc, const DevMat *hmats, int op, int mi
 
 // assembly_kernels.cu
 cudaError_t assembly_upload_geom(const GeomClass *h, int n, cudaStream_t st);
-void assembly_set_tiled(int on);   // 1 (default): shared-memory tiled assembly; 0: row-per-thread direct variant
 cudaError_t launch_csr_pattern(const LaunchCtx &lc, int NX, int NY, int32_t *rowptr, int32_t *col, int64_t *launches);
 cudaError_t launch_assemble(const LaunchCtx &lc, int NX, int NY, int planestress, int ngeom, const int32_t *elem_desc,
                             const double *elstiff, const int32_t *rowptr, double *val, int64_t *launches);

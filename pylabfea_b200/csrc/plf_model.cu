@@ -39,12 +39,12 @@ void model_apply_mg_options(plf_ctx *ctx)
     ctx->mg->nu = std::max(2, ctx->mg_nu);
     ctx->mg->coarse_sweeps = std::max(1, ctx->mg_coarse_sweeps);
     ctx->mg->omega = ctx->mg_omega;
-    cg_graph_reset();   // the captured V-cycle has the old sweep counts baked in
+    cg_graph_reset(ctx->cg_graph);   // the captured V-cycle has the old sweep counts baked in
 }
 
 void model_free(plf_ctx *c)
 {
-    cg_graph_reset();
+    cg_graph_reset(c->cg_graph);
     if (c->mg) { mg_free(*c->mg); delete c->mg; c->mg = nullptr; }
     cudaFree(c->d_desc); cudaFree(c->d_elstiff); cudaFree(c->d_sig); cudaFree(c->d_eps); cudaFree(c->d_epl);
     cudaFree(c->d_res_sig); cudaFree(c->d_res_depl); cudaFree(c->d_fyld); cudaFree(c->d_nsteps); cudaFree(c->d_branch);
@@ -52,20 +52,15 @@ void model_free(plf_ctx *c)
     cudaFree(c->d_val); cudaFree(c->d_worklist); cudaFree(c->d_r); cudaFree(c->d_z); cudaFree(c->d_p); cudaFree(c->d_q);
     cudaFree(c->d_b); cudaFree(c->d_diag); cudaFree(c->d_w); cudaFree(c->d_fixed); cudaFree(c->d_partial);
     cudaFree(c->d_bc_du); cudaFree(c->d_bc_f); cudaFree(c->d_cgmask); c->d_cgmask = nullptr;
-    if (c->comm) c->comm->strip_set = false;   // a new mesh needs a new plf_comm_set_strip
+    if (c->comm) { c->comm->strip_set = false; c->comm->global_set = false; }   // a new mesh needs a new plf_comm_set_strip
+    solve_state_free(c);
+    c->tangent_epoch++; c->K_tangent_epoch = 0; c->mg_K_serial = -1; c->mg_mask_epoch = -1;
     c->d_bc_du = c->d_bc_f = nullptr; c->bc_valid = false;
     c->d_desc = nullptr; c->d_elstiff = c->d_sig = c->d_eps = c->d_epl = c->d_res_sig = c->d_res_depl = c->d_fyld = nullptr;
     c->d_nsteps = c->d_branch = nullptr; c->d_has_res = nullptr; c->d_u = c->d_du = c->d_f = nullptr;
     c->d_rowptr = c->d_col = nullptr; c->d_val = nullptr; c->d_worklist = nullptr;
     c->d_r = c->d_z = c->d_p = c->d_q = c->d_b = c->d_diag = c->d_w = nullptr; c->d_fixed = nullptr; c->d_partial = nullptr;
     c->mesh_ready = c->K_ready = false;
-}
-
-cudaError_t model_upload_materials(plf_ctx *ctx)
-{
-    cudaError_t e = modelk_init();
-    if (e != cudaSuccess) return e;
-    return modelk_upload_materials(ctx->hmats, ctx->nmat, ctx->stream);
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -177,11 +172,22 @@ extern "C" int plf_mesh_structured(plf_ctx *ctx, int NX, int NY, const double *d
         (rc = dalloc(ctx, &ctx->d_col, (size_t)nnz)) || (rc = dalloc(ctx, &ctx->d_val, (size_t)nnz)))
         return rc;
     CK(cudaMemcpyAsync(ctx->d_desc, ctx->h_desc.data(), E * sizeof(int32_t), cudaMemcpyHostToDevice, ctx->stream));
-    CK(assembly_upload_geom(ctx->geom, ctx->ngeom, ctx->stream));
-    CK(modelk_upload_geom(ctx->geom, ctx->ngeom, ctx->stream));
-    LaunchCtx lc{ctx->stream, ctx->sm_count};
+    ctx->tables_dirty = true;   // new geometry classes: uploaded by the next plf_bind
+    LaunchCtx lc = make_lc(ctx);
     CK(launch_csr_pattern(lc, NX, NY, ctx->d_rowptr, ctx->d_col, &ctx->launches));
-    // first Model.solve (model.py:1214-1227): zero state, elstiff = CV
+    ctx->mg = new MgHierarchy();
+    CK(mg_build(*ctx->mg, NX, NY));
+    model_apply_mg_options(ctx);
+    ctx->mesh_ready = true;
+    ctx->K_ready = false;
+    return model_reset_state(ctx);
+}
+
+// first Model.solve (model.py:1214-1227): u = f = 0, zero element state, elstiff = CV
+int model_reset_state(plf_ctx *ctx)
+{
+    const size_t E = (size_t)ctx->Nel, D = (size_t)ctx->Ndof;
+    CK(cudaSetDevice(ctx->device));
     CK(cudaMemsetAsync(ctx->d_sig, 0, 6 * E * sizeof(double), ctx->stream));
     CK(cudaMemsetAsync(ctx->d_eps, 0, 6 * E * sizeof(double), ctx->stream));
     CK(cudaMemsetAsync(ctx->d_epl, 0, 6 * E * sizeof(double), ctx->stream));
@@ -193,20 +199,13 @@ extern "C" int plf_mesh_structured(plf_ctx *ctx, int NX, int NY, const double *d
     CK(cudaMemsetAsync(ctx->d_u, 0, D * sizeof(double), ctx->stream));
     CK(cudaMemsetAsync(ctx->d_du, 0, D * sizeof(double), ctx->stream));
     CK(cudaMemsetAsync(ctx->d_f, 0, D * sizeof(double), ctx->stream));
-    ctx->mg = new MgHierarchy();
-    CK(mg_build(*ctx->mg, NX, NY));
-    model_apply_mg_options(ctx);
-    ctx->mesh_ready = true;
-    ctx->K_ready = false;
-    rc = plf_set_tangent(ctx, nullptr);
-    if (rc != PLF_OK) return rc;
-    CK(cudaStreamSynchronize(ctx->stream));
-    return PLF_OK;
+    return plf_set_tangent(ctx, nullptr);
 }
 
 #define NEED_MESH(name) \
     if (!ctx) return PLF_EINVAL; \
-    if (!ctx->mesh_ready) return fail(ctx, PLF_ESTATE, std::string(name) + ": attributes for mesh not set (call plf_mesh_structured)")
+    if (!ctx->mesh_ready) return fail(ctx, PLF_ESTATE, std::string(name) + ": attributes for mesh not set (call plf_mesh_structured)"); \
+    if (int brc_ = plf_bind(ctx)) return brc_
 
 extern "C" int plf_mesh_sizes(const plf_ctx *ctx, int64_t *Nel, int64_t *Nnode, int64_t *Ndof, int64_t *nnz)
 {
@@ -239,6 +238,7 @@ extern "C" int plf_set_tangent(plf_ctx *ctx, const double *elstiff)
     }
     CK(cudaStreamSynchronize(ctx->stream));
     ctx->K_ready = false;
+    ctx->tangent_epoch++;
     return PLF_OK;
 }
 
@@ -258,7 +258,7 @@ extern "C" int plf_get_kel(plf_ctx *ctx, double *Kel)
     CK(cudaSetDevice(ctx->device));
     double *d = nullptr;
     CK(cudaMalloc((void **)&d, 64 * (size_t)ctx->Nel * sizeof(double)));
-    LaunchCtx lc{ctx->stream, ctx->sm_count};
+    LaunchCtx lc = make_lc(ctx);
     cudaError_t e = launch_kel(lc, ctx->Nel, ctx->planestress, ctx->d_desc, ctx->d_elstiff, d, &ctx->launches);
     if (e == cudaSuccess) e = cudaMemcpyAsync(Kel, d, 64 * (size_t)ctx->Nel * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
@@ -270,9 +270,13 @@ extern "C" int plf_get_kel(plf_ctx *ctx, double *Kel)
 extern "C" int plf_setupK(plf_ctx *ctx)
 {
     NEED_MESH("plf_setupK");
-    LaunchCtx lc{ctx->stream, ctx->sm_count};
+    // no element tangent changed since this K was assembled from them: the CSR values are already the result
+    if (ctx->K_ready && ctx->K_tangent_epoch == ctx->tangent_epoch && ctx->skip_unchanged) return PLF_OK;
+    LaunchCtx lc = make_lc(ctx);
     CK(launch_assemble(lc, ctx->NX, ctx->NY, ctx->planestress, ctx->ngeom, ctx->d_desc, ctx->d_elstiff, ctx->d_rowptr, ctx->d_val, &ctx->launches));
     ctx->K_ready = true;
+    ctx->K_tangent_epoch = ctx->tangent_epoch;
+    ctx->K_serial++;
     return PLF_OK;
 }
 
@@ -280,9 +284,11 @@ extern "C" int plf_setupK_from_batch(plf_ctx *ctx, const plf_batch *b)
 {
     NEED_MESH("plf_setupK_from_batch");
     if (!b || b->n != ctx->Nel) return fail(ctx, PLF_EINVAL, "plf_setupK_from_batch: batch must hold exactly Nel elements");
-    LaunchCtx lc{ctx->stream, ctx->sm_count};
+    LaunchCtx lc = make_lc(ctx);
     CK(launch_assemble(lc, ctx->NX, ctx->NY, ctx->planestress, ctx->ngeom, ctx->d_desc, b->ctan, ctx->d_rowptr, ctx->d_val, &ctx->launches));
     ctx->K_ready = true;
+    ctx->K_tangent_epoch = 0;   // not assembled from Element.elstiff
+    ctx->K_serial++;
     return PLF_OK;
 }
 
@@ -317,7 +323,7 @@ extern "C" int plf_step_host(plf_ctx *ctx, plf_batch *b, const double *sig, cons
     CK(cudaMemsetAsync(b->mat_id, 0, (size_t)b->n * sizeof(int32_t), ctx->stream));
     if (ctx->nmat > 1)   // material ids of the mesh elements (descriptor low half)
         return fail(ctx, PLF_EUNSUPPORTED, "plf_step_host: single-material meshes only (use plf_sweep for mixed meshes)");
-    LaunchCtx lc{ctx->stream, ctx->sm_count, ctx->passa_direct, ctx->max_fm, ctx->k1_only, ctx->passb_recur};
+    LaunchCtx lc = make_lc(ctx);
     for (int c = 0; c < nchunk; c++) {
         const int ja = (int)((int64_t)NX * c / nchunk), jb = (int)((int64_t)NX * (c + 1) / nchunk);   // element columns
         const int64_t e0 = (int64_t)ja * NY, ne = (int64_t)(jb - ja) * NY;
@@ -349,6 +355,8 @@ extern "C" int plf_step_host(plf_ctx *ctx, plf_batch *b, const double *sig, cons
         }
     }
     ctx->K_ready = true;
+    ctx->K_tangent_epoch = 0;
+    ctx->K_serial++;
     CK(cudaStreamSynchronize(ctx->s_out));
     CK(cudaStreamSynchronize(ctx->stream));
     return PLF_OK;
@@ -438,11 +446,12 @@ extern "C" int plf_sweep(plf_ctx *ctx, int nit, int32_t *change, int32_t *conv, 
         if (ctx->hmats[i].tresca && (ctx->hmats[i].kind == PLF_MAT_HILL || ctx->hmats[i].kind == PLF_MAT_HILL3))
             // material.py:824-825: the first plastic step of a Tresca material raises in the reference
             return fail(ctx, PLF_EUNSUPPORTED, "plf_sweep: analytical gradient for Tresca not implemented");
-    LaunchCtx lc{ctx->stream, ctx->sm_count};
+    LaunchCtx lc = make_lc(ctx);
     CK(launch_sweep(lc, ctx->hmats, ctx->nmat, ctx->Nel, ctx->NY, nit, ctx->d_desc, ctx->d_sig, ctx->d_epl, ctx->d_du, ctx->d_elstiff,
                     ctx->d_res_sig, ctx->d_res_depl, ctx->d_fyld, ctx->d_nsteps, ctx->d_has_res, ctx->d_worklist, ctx->d_scalars,
                     ctx->h_scalars, ctx->compact, &ctx->launches));
     const SweepStats *st = (const SweepStats *)ctx->h_scalars;
+    if (st->change) ctx->tangent_epoch++;
     if (change) *change = st->change ? 1 : 0;
     if (conv) *conv = st->nonconv == 0 ? 1 : 0;
     if (max_hh) *max_hh = st->max_hh;
@@ -456,7 +465,7 @@ extern "C" int plf_commit(plf_ctx *ctx)
 {
     NEED_MESH("plf_commit");
     if (!ctx->K_ready) return fail(ctx, PLF_ESTATE, "plf_commit: the stiffness the increment was solved with is not assembled");
-    LaunchCtx lc{ctx->stream, ctx->sm_count};
+    LaunchCtx lc = make_lc(ctx);
     CK(launch_commit(lc, ctx->Nel, ctx->Ndof, ctx->NY, ctx->d_desc, ctx->d_u, ctx->d_du, ctx->d_f, ctx->d_rowptr, ctx->d_col, ctx->d_val,
                      ctx->d_elstiff, ctx->d_sig, ctx->d_eps, ctx->d_epl, ctx->d_res_sig, ctx->d_res_depl, ctx->d_has_res,
                      &ctx->launches));
@@ -468,7 +477,7 @@ extern "C" int plf_reduce_global(plf_ctx *ctx, double *sig6, double *eps6, doubl
     NEED_MESH("plf_reduce_global");
     int rc = ensure_partials(ctx);
     if (rc != PLF_OK) return rc;
-    LaunchCtx lc{ctx->stream, ctx->sm_count};
+    LaunchCtx lc = make_lc(ctx);
     double *d_out = (double *)(ctx->d_scalars + 576);
     CK(launch_global_sums(lc, ctx->Nel, ctx->d_desc, ctx->d_sig, ctx->d_eps, ctx->d_epl, ctx->d_partial, counter_ptr(ctx), d_out,
                           &ctx->launches));
@@ -493,7 +502,7 @@ extern "C" int plf_calc_scf(plf_ctx *ctx, const double *sld, double *scf)
     if (!sld || !scf) return PLF_EINVAL;
     int rc = ensure_partials(ctx);
     if (rc != PLF_OK) return rc;
-    LaunchCtx lc{ctx->stream, ctx->sm_count};
+    LaunchCtx lc = make_lc(ctx);
     double *d_sld = (double *)(ctx->d_scalars + 576);
     double *d_out = (double *)(ctx->d_scalars + 640);
     CK(cudaMemcpyAsync(d_sld, sld, 6 * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
@@ -507,6 +516,20 @@ extern "C" int plf_calc_scf(plf_ctx *ctx, const double *sld, double *scf)
 // ---------------------------------------------------------------------------------------------------------------
 // linear solve
 // ---------------------------------------------------------------------------------------------------------------
+int model_solver_buffers(plf_ctx *ctx)
+{
+    const size_t D = (size_t)ctx->Ndof;
+    int rc;
+    if (!ctx->d_r) {
+        if ((rc = dalloc(ctx, &ctx->d_r, D)) || (rc = dalloc(ctx, &ctx->d_z, D)) || (rc = dalloc(ctx, &ctx->d_p, D)) ||
+            (rc = dalloc(ctx, &ctx->d_q, D)) || (rc = dalloc(ctx, &ctx->d_b, D)) || (rc = dalloc(ctx, &ctx->d_diag, D)) ||
+            (rc = dalloc(ctx, &ctx->d_w, D)) || (rc = dalloc(ctx, &ctx->d_fixed, D)) || (rc = dalloc(ctx, &ctx->d_bc_du, D)) ||
+            (rc = dalloc(ctx, &ctx->d_bc_f, D)))
+            return rc;
+    }
+    return ensure_partials(ctx);
+}
+
 extern "C" int plf_solve_linear(plf_ctx *ctx, const uint8_t *fixed, const double *du_bc, const double *w, const double *f_ext,
                                 double rtol, int max_iter, int *iters, double *relres)
 {
@@ -518,15 +541,7 @@ extern "C" int plf_solve_linear(plf_ctx *ctx, const uint8_t *fixed, const double
     CK(cudaSetDevice(ctx->device));
     const size_t D = (size_t)ctx->Ndof;
     int rc;
-    if (!ctx->d_r) {
-        if ((rc = dalloc(ctx, &ctx->d_r, D)) || (rc = dalloc(ctx, &ctx->d_z, D)) || (rc = dalloc(ctx, &ctx->d_p, D)) ||
-            (rc = dalloc(ctx, &ctx->d_q, D)) || (rc = dalloc(ctx, &ctx->d_b, D)) || (rc = dalloc(ctx, &ctx->d_diag, D)) ||
-            (rc = dalloc(ctx, &ctx->d_w, D)) || (rc = dalloc(ctx, &ctx->d_fixed, D)) || (rc = dalloc(ctx, &ctx->d_bc_du, D)) ||
-            (rc = dalloc(ctx, &ctx->d_bc_f, D)))
-            return rc;
-    }
-    if ((rc = ensure_partials(ctx)) != PLF_OK) return rc;
-    LaunchCtx lc{ctx->stream, ctx->sm_count};
+    if ((rc = model_solver_buffers(ctx)) != PLF_OK) return rc;
     if (!reuse) {
         // the BC vectors stay on the device (d_fixed, d_w, d_bc_f, d_bc_du): the Newton-like passes of an increment call
         // again with the same boundary conditions and then skip these 4 host-to-device copies
@@ -535,7 +550,21 @@ extern "C" int plf_solve_linear(plf_ctx *ctx, const uint8_t *fixed, const double
         CK(cudaMemcpyAsync(ctx->d_bc_f, f_ext, D * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
         CK(cudaMemcpyAsync(ctx->d_bc_du, du_bc, D * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
         ctx->bc_valid = true;
+        ctx->mask_epoch++;
+        solve_state_invalidate_bc(ctx);
     }
+    return model_solve_device_bc(ctx, rtol, max_iter, iters, relres);
+}
+
+int model_solve_device_bc(plf_ctx *ctx, double rtol, int max_iter, int *iters, double *relres)
+{
+    if (!ctx->K_ready) return fail(ctx, PLF_ESTATE, "plf_solve_linear: call plf_setupK first");
+    if (!ctx->bc_valid) return fail(ctx, PLF_ESTATE, "plf_solve_linear: no boundary-condition vectors on the device");
+    if (int brc = plf_bind(ctx)) return brc;
+    int rc;
+    if ((rc = model_solver_buffers(ctx)) != PLF_OK) return rc;
+    const size_t D = (size_t)ctx->Ndof;
+    LaunchCtx lc = make_lc(ctx);
     const bool dist = ctx->comm && ctx->comm->active();
     if (dist && !ctx->comm->strip_set) return fail(ctx, PLF_ESTATE, "plf_solve_linear: call plf_comm_set_strip after plf_mesh_structured");
     const unsigned char *mask = ctx->d_fixed;
@@ -571,9 +600,12 @@ extern "C" int plf_solve_linear(plf_ctx *ctx, const uint8_t *fixed, const double
     }
     // multigrid V-cycle preconditioner when the mesh coarsens at least once (mesh-independent iteration counts), else Jacobi
     const bool use_mg = ctx->solver_mg && ctx->mg && ctx->mg->levels() >= 2;
+    // same K and same Dirichlet mask as at the previous solve: the Galerkin hierarchy is still valid
+    const bool mg_fresh = use_mg && ctx->skip_unchanged && ctx->mg_K_serial == ctx->K_serial && ctx->mg_mask_epoch == ctx->mask_epoch;
+    if (use_mg) { ctx->mg_K_serial = ctx->K_serial; ctx->mg_mask_epoch = ctx->mask_epoch; }
     CK(launch_cg(lc, ctx->Ndof, ctx->d_rowptr, ctx->d_col, ctx->d_val, ctx->d_fixed, ctx->d_b, x, ctx->d_r, ctx->d_z, ctx->d_p, ctx->d_q,
                  ctx->d_diag, ctx->d_partial, counter_ptr(ctx), ctx->d_scalars + 256, ctx->h_scalars + 256, rtol, max_iter,
-                 use_mg ? 4 : 50, &it, &rr, &ctx->launches, use_mg ? ctx->mg : nullptr, ctx->solver_warm, ctx->NX, ctx->NY));
+                 use_mg ? 4 : 50, &it, &rr, &ctx->launches, use_mg ? ctx->mg : nullptr, ctx->solver_warm, ctx->NX, ctx->NY, ctx->cg_graph, mg_fresh ? 0 : 1));
     CK(launch_merge_du(lc, ctx->Ndof, x, ctx->d_bc_du, ctx->d_fixed, ctx->d_du, &ctx->launches));
     CK(cudaStreamSynchronize(ctx->stream));
     if (iters) *iters = it;

@@ -5,9 +5,12 @@
 
 #include "plf_device.cuh"
 #include "plf_host.h"
+#include "model_kernels.h"
 
 // device buffers of one batch of independent stress updates (AoS records, see DESIGN.md "data layout")
 namespace plf { struct MgHierarchy; struct Comm; }
+
+struct plf_solve_state;   // plf_solve.cu: boundary description and staging buffers of the load-increment controller
 
 struct plf_batch {
     int64_t n = 0, cap = 0;
@@ -85,10 +88,35 @@ struct plf_ctx {
     unsigned char *d_cgmask = nullptr;   // fixed | ghost-column mask of the distributed CG
     double *d_partial = nullptr;   // block partial sums
     int n_partial = 0;
+    plf::CgGraphCache cg_graph;    // captured chunk of CG iterations over this context's buffers
+    int assembly_tiled = 2;        // option "assembly_tiled"
+    // The kernels read materials and geometry classes from __constant__ banks, which are per device, not per context.
+    // tables_dirty: this context's host tables changed since it last uploaded them; plf_bind() (head of every launch
+    // sequence) re-uploads when the banks hold another context's tables or stale ones.
+    bool tables_dirty = true;
+    plf_solve_state *solve = nullptr;   // set by plf_solve_begin
+    // change tracking, so that an unchanged K is neither re-assembled nor re-coarsened: tangent_epoch moves whenever
+    // element tangents change (plf_set_tangent, a sweep that replaced one), K_serial with every assembly, mask_epoch
+    // with every new set of boundary-condition vectors
+    int skip_unchanged = 1;   // option: 0 re-assembles / re-coarsens even when nothing changed (A/B, tests)
+    int64_t tangent_epoch = 1, K_tangent_epoch = 0, K_serial = 0, mask_epoch = 0, mg_K_serial = -1, mg_mask_epoch = -1;
 };
 
 int fail(plf_ctx *c, int code, const std::string &msg);
+// Makes this context the owner of the device's __constant__ material / geometry banks (uploads its tables if another
+// context used the device in between or the tables changed).  Returns PLF_OK or PLF_ECUDA.
+int plf_bind(plf_ctx *ctx);
+void solve_state_free(plf_ctx *ctx);            // plf_solve.cu
+void solve_state_invalidate_bc(plf_ctx *ctx);   // plf_solve.cu: the device BC vectors were overwritten by the caller
+int model_reset_state(plf_ctx *ctx);            // zero u, f, element state; elstiff = CV (first Model.solve, model.py:1214-1227)
+int model_solver_buffers(plf_ctx *ctx);         // work vectors of plf_solve_linear
+// reduced solve with the boundary-condition vectors already on the device (d_fixed, d_bc_du, d_w, d_bc_f)
+int model_solve_device_bc(plf_ctx *ctx, double rtol, int max_iter, int *iters, double *relres);
+inline plf::LaunchCtx make_lc(const plf_ctx *c)
+{
+    plf::LaunchCtx lc{c->stream, c->sm_count, c->passa_direct, c->max_fm, c->k1_only, c->passb_recur, c->assembly_tiled};
+    return lc;
+}
 void model_free(plf_ctx *ctx);
-cudaError_t model_upload_materials(plf_ctx *ctx);
 
 void model_apply_mg_options(plf_ctx *ctx);   // copies mg_nu / mg_coarse_sweeps / mg_omega into the hierarchy

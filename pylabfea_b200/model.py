@@ -4,8 +4,9 @@ Keeps the reference's API (geom / assign / bcleft / bcright / bcbot / bctop / bc
 calc_global / bcval and the attributes notebooks read: u, f, glob, sgl, egl, epgl, element[i].sig/.eps/.epl/...,
 Nel, Ndof, npos, noleft/noright/nobot/notop, nsteps, niter, co_nconv), but every O(Nel) / O(Ndof) operation of
 Model.solve runs on the device through the C-ABI: K integration + CSR assembly, BC-reduced CG solve, the
-Material.response sweep with tangent replacement, calc_scf, the state commit and the volume averages.  Only
-scalars, the boundary-condition vectors and (once per increment) u and f cross PCIe.
+Material.response sweep with tangent replacement, calc_scf, the state commit and the volume averages; the loop over
+load increments itself is the library's (plf_load_increment).  Per increment one report struct crosses the boundary;
+u, f and the element fields are copied to the host only when they are read.
 
 File:line citations refer to /root/reference/src/pylabfea/model.py.
 """
@@ -14,7 +15,6 @@ import warnings
 import numpy as np
 
 from . import _lib
-from .basic import yf_tolerance
 
 
 class StiffnessCSR(object):
@@ -155,8 +155,7 @@ class Model(object):
         self.sgl = np.zeros((1, 6))
         self.egl = np.zeros((1, 6))
         self.epgl = np.zeros((1, 6))
-        self.u = None
-        self.f = None
+        self._solved = False          # u, f, du live on the device; the properties mirror them on demand
         self.Nnode = None
         self.glob = {'ebc1': None, 'ebc2': None, 'sbc1': None, 'sbc2': None,
                      'eps': np.zeros(6), 'sig': np.zeros(6), 'epl': np.zeros(6)}
@@ -165,8 +164,6 @@ class Model(object):
         self.solver_rtol = 1.e-13     # CG stops at |r| <= rtol |b|
         self.solver_maxit = 200000
         self.solver_stats = []        # (iterations, relative residual) of every linear solve
-        self._bc_key = None           # boundary values whose BC vectors are on the device (re-used by the next pass)
-        self._bc_epoch = 0
 
     # ------------------------------------------------------------------------------------------------------
     # pre-processing: geometry, materials, boundary conditions (host, O(1))
@@ -259,10 +256,9 @@ class Model(object):
             NX, NY = el.shape
         if NX < self.Nsec:
             raise TypeError('Error: Number of elements is smaller than number of sections')
-        if self.u is not None:
+        if self._solved:
             warnings.warn('Warning: Solution of previous steps is deleted')
-            self.u = None
-            self.f = None
+            self._solved = False
         self.NnodeX, self.NnodeY = NX + 1, NY + 1
         self.Nnode = self.NnodeX * self.NnodeY
         self.Ndof = 2 * self.Nnode
@@ -358,234 +354,188 @@ class Model(object):
         return StiffnessCSR(rowptr, col, val, self.Ndof)
 
     # ------------------------------------------------------------------------------------------------------
-    # boundary conditions -> vectors for the reduced solve (model.py:1070-1206)
+    # boundary conditions (model.py:1070-1206)
     # ------------------------------------------------------------------------------------------------------
+    def _bc_descriptor(self):
+        """The boundary conditions as the plain struct the library's load-increment controller reads (plf_bc)."""
+        bc = _lib.PlfBC()
+        for name, vals, flags in (('left', self.bcl, self.ubcleft), ('bot', self.bcb, self.ubcbot),
+                                  ('right', self.bcr, self.ubcright), ('top', self.bct, self.ubctop),
+                                  ('node', self.bcn, self.ubcn)):
+            getattr(bc, name)[:] = [float(v) for v in vals]
+            getattr(bc, name + '_disp')[:] = [int(bool(f)) for f in flags]
+        if self.noset is not None:
+            self._noset_arr = np.ascontiguousarray(self.noset, dtype=np.int32)
+            bc.n_noset = len(self._noset_arr)
+            bc.noset = _lib._ptr(self._noset_arr)
+        return bc
+
     def _calc_BC(self, bcl0, bcb0, dbcr, dbct, dbcn):
-        """Restates calc_BC: returns fixed (dofs removed from `ind`), du (prescribed increments), w (sum of every BC
-        value applied to a dof: what the reference multiplies K's columns with, including its double application at
-        shared corner dofs) and f_ext (force-type BC).  df[ind] = f_ext[ind] - (K w)[ind]."""
+        """Host-side statement of what calc_BC leaves behind, as four dense vectors: `fixed` (dofs taken out of `ind`),
+        `du` (their prescribed increments), `w` (the sum of ALL displacement values applied to a dof -- the reference
+        multiplies column i of K into df once per edge that lists the dof, also at shared corners) and `f_ext` (force
+        conditions), so that df[ind] = f_ext[ind] - (K w)[ind].  The device path builds the same vectors inside
+        plf_load_increment; this NumPy version serves the host-only checks and plf_solve_linear callers."""
         n = self.Ndof
         fixed = np.zeros(n, dtype=np.uint8)
-        du = np.zeros(n)
-        w = np.zeros(n)
-        fext = np.zeros(n)
-
-        def disp(nodes, k, val, who, first=False):
-            for j in nodes:
-                i = 2 * j + k
-                if not fixed[i]:
-                    fixed[i] = 1
-                    du[i] = val
-                elif first:
-                    raise ValueError('list.remove(x): x not in list')   # what the reference's ind.remove does
-                elif du[i] != val:
-                    warnings.warn('Inconsistent BC at %s node %d (%g vs %g).' % (who, j, du[i], val))
-                w[i] += val
-
-        for k in range(2):                       # left: static (1099-1105)
-            if self.ubcleft[k]:
-                disp(self.noleft, k, bcl0[k], 'left', first=True)
-        for k in range(2):                       # bottom: static (1111-1122)
-            if self.ubcbot[k]:
-                disp(self.nobot, k, bcb0[k], 'bottom')
-        for k in range(2):                       # right (1126-1151)
-            if self.ubcright[k]:
-                disp(self.noright, k, dbcr[k], 'right')
-            else:
-                share = 1. / (self.NnodeY - 1)
-                for j in self.noright:
-                    hy = self.npos[2 * j + 1]
-                    fext[2 * j + k] += dbcr[k] * (share * 0.5 if (hy < 1.e-3 or hy > self.leny - 1.e-3) else share)
-        for k in range(2):                       # top (1156-1179)
-            if self.ubctop[k]:
-                disp(self.notop, k, dbct[k], 'top')
-            else:
-                share = 1. / (self.NnodeX - 1)
-                for j in self.notop:
-                    hx = self.npos[2 * j]
-                    fext[2 * j + k] += dbct[k] * (share * 0.5 if (hx < 1.e-3 or hx > self.lenx - 1.e-3) else share)
-        if self.noset is not None:               # node set (1183-1205)
+        du, w, fext = np.zeros(n), np.zeros(n), np.zeros(n)
+        edges = [('left', self.noleft, self.ubcleft, bcl0), ('bottom', self.nobot, self.ubcbot, bcb0),
+                 ('right', self.noright, self.ubcright, dbcr), ('top', self.notop, self.ubctop, dbct)]
+        if self.noset is not None:
             if dbcn is None:
                 raise ValueError('No BC for selected node set given.')
+            edges.append(('node set', self.noset, self.ubcn, dbcn))
+        for who, nodes, flags, vals in edges:
+            nodes = np.asarray(nodes, dtype=np.int64)
             for k in range(2):
-                if self.ubcn[k]:
-                    disp(self.noset, k, dbcn[k], 'node set')
-                else:
-                    for j in self.noset:
-                        fext[2 * j + k] += dbcn[k]
+                dofs = 2 * nodes + k
+                if flags[k]:
+                    fresh = fixed[dofs] == 0
+                    clash = ~fresh & (du[dofs] != vals[k])
+                    if clash.any():
+                        j = int(nodes[np.argmax(clash)])
+                        warnings.warn('Inconsistent BC at %s node %d (%g vs %g).' % (who, j, du[2 * j + k], vals[k]))
+                    du[dofs[fresh]] = vals[k]
+                    fixed[dofs] = 1
+                    np.add.at(w, dofs, vals[k])
+                elif who == 'right' or who == 'top':
+                    # a force is shared evenly over the edge's nodes, the two corner nodes carry half a share
+                    along = self.npos[2 * nodes + (1 if who == 'right' else 0)]
+                    length, nseg = (self.leny, self.NnodeY - 1) if who == 'right' else (self.lenx, self.NnodeX - 1)
+                    share = np.where((along < 1.e-3) | (along > length - 1.e-3), 0.5, 1.) / nseg
+                    np.add.at(fext, dofs, vals[k] * share)
+                elif who == 'node set':
+                    np.add.at(fext, dofs, vals[k])
         return fixed, du, w, fext
 
-    def _solve_increment(self, bcl0, bcb0, dbcr, dbct, dbcn):
-        # the inner passes of an increment usually repeat the boundary values of the previous pass: the BC vectors are
-        # then neither rebuilt on the host nor copied to the device again
-        key = (repr(np.asarray(bcl0).tolist()), repr(np.asarray(bcb0).tolist()), repr(np.asarray(dbcr).tolist()),
-               repr(np.asarray(dbct).tolist()), None if dbcn is None else repr(np.asarray(dbcn).tolist()), self._bc_epoch)
-        if key == self._bc_key:
-            it, rr = self._dev().solve_linear(None, None, None, None, rtol=self.solver_rtol, max_iter=self.solver_maxit)
-        else:
-            fixed, du, w, fext = self._calc_BC(bcl0, bcb0, dbcr, dbct, dbcn)
-            it, rr = self._dev().solve_linear(fixed, du, w, fext, rtol=self.solver_rtol, max_iter=self.solver_maxit)
-            self._bc_key = key
-        self.solver_stats.append((it, rr))
+    # ------------------------------------------------------------------------------------------------------
+    # nodal solution vectors: device-resident, mirrored to the host when somebody looks at them
+    # ------------------------------------------------------------------------------------------------------
+    def _nodal(self, name, field):
+        if not self._solved:
+            return None
+        if name not in self._cache:
+            self._cache[name] = self._dev().get_field(field)
+        return self._cache[name]
+
+    @property
+    def u(self):
+        return self._nodal('u', _lib.F_U)
+
+    @u.setter
+    def u(self, val):
+        if val is not None:
+            raise AttributeError('Model.u is computed by solve(); only None (forget the solution) can be assigned')
+        self._solved = False
+
+    @property
+    def f(self):
+        return self._nodal('f', _lib.F_F)
+
+    @f.setter
+    def f(self, val):
+        if val is not None:
+            raise AttributeError('Model.f is computed by solve(); only None can be assigned')
+
+    @property
+    def du(self):
+        return self._nodal('du', _lib.F_DU)
 
     # ------------------------------------------------------------------------------------------------------
     # solve (model.py:979-1450)
     # ------------------------------------------------------------------------------------------------------
     def solve(self, min_step=None, verb=False):
+        """Load-controlled solution (reference: Model.solve).  The loop over load increments lives in the library
+        (plf_load_increment: predictor solve, calc_scf, the inner passes with tangent update, commit, calc_global);
+        this method hands over the boundary conditions, keeps the increment history the reference exposes (sgl / egl /
+        epgl, glob, nsteps, niter, co_nconv, bcr_mem / bct_mem) and prints the verbose log."""
         if self.Nnode is None:
             raise AttributeError('Attributes for mesh not set, but required by solver.')
         ctx = self._dev()
-        dim = self.dim
-        self._bc_key = None                      # BC types / node sets may have changed since the last call
-        if self.u is None:                       # first call: zero state, elstiff = CV (1214-1234)
-            ctx.set_field(_lib.F_U, np.zeros(self.Ndof))
-            ctx.set_field(_lib.F_F, np.zeros(self.Ndof))
-            z = np.zeros((self.Nel, 6))
-            for fld in (_lib.F_SIG, _lib.F_EPS, _lib.F_EPL):
-                ctx.set_field(fld, z)
-            ctx.set_tangent(None)
-            self.u = np.zeros(self.Ndof)
-            self.f = np.zeros(self.Ndof)
-            self.sgl = np.zeros((1, 6))
-            self.egl = np.zeros((1, 6))
-            self.epgl = np.zeros((1, 6))
-            bcr0 = np.zeros(dim)
-            bct0 = np.zeros(dim)
-            self.bct_mem = np.zeros(dim)
-            self.bcr_mem = np.zeros(dim)
+        first = not self._solved
+        state = _lib.PlfLoadState()
+        if first:
+            self.sgl, self.egl, self.epgl = np.zeros((1, 6)), np.zeros((1, 6)), np.zeros((1, 6))
+            self.bcr_mem, self.bct_mem = np.zeros(self.dim), np.zeros(self.dim)
             if self.noset is not None:
-                bcn0 = np.zeros(dim)
-                self.bcn_mem = np.zeros(dim)
-        else:
-            bcr0 = self.bcr_mem
-            bct0 = self.bct_mem
-            if self.noset is not None:
-                bcn0 = self.bcn_mem
-        bcl0, bcb0 = self.bcl, self.bcb
-        ctx.setupK()                             # 1242
-        # loading direction for the ML yield-point search in calc_scf (1245-1258)
+                self.bcn_mem = np.zeros(self.dim)
+        state.reached_right[:] = list(self.bcr_mem)
+        state.reached_top[:] = list(self.bct_mem)
+        # The reference starts the node-set history of the first call from a private zero vector and never stores it
+        # (model.py:1233-1234, 1446-1447), so the SECOND call starts from zero again; from then on bcn_mem accumulates.
+        carry_set = self.noset is not None and not first and hasattr(self, 'bcn_mem')
+        if carry_set:
+            state.reached_node[:] = list(self.bcn_mem)
         sld = np.zeros(6)
-        if np.abs(self.bcr[0]) > 1.e-6:
-            sld[0] = np.sign(self.bcr[0])
-        if np.abs(self.bct[1]) > 1.e-6:
-            sld[1] = np.sign(self.bct[1])
-        if np.abs(self.bcr[1]) > 1.e-6:
-            sld[5] = np.sign(self.bcr[1])
-        if np.abs(self.bct[0]) > 1.e-6:
-            sld[5] = np.sign(self.bct[0])
+        for val, idx in ((self.bcr[0], 0), (self.bct[1], 1), (self.bcr[1], 5), (self.bct[0], 5)):
+            if abs(val) > 1.e-6:
+                sld[idx] = np.sign(val)
         if np.linalg.norm(sld) < 1.e-3:
             warnings.warn('solve: inconsistent BC sld={}, bct={}, bcr={}'.format(sld, self.bct, self.bcr))
-            sld[0] = 1.
-
-        il = 0
-        nit = 0
-        niter = []
-        co_nconv = []
-        bc_inc = True
-        nconv = 0
+        ctx.solve_begin(self._bc_descriptor(), reset=first)
+        self._solved = True
+        self._cache = {}
+        niter, co_nconv = [], []
         self.sweep_stats = []
-        while bc_inc:                            # load increments (1270)
-            max_dbct = self.bct - bct0
-            max_dbcr = self.bcr - bcr0
-            if min_step is not None:
-                sc = np.maximum(1, min_step - il)
-                max_dbct = max_dbct / sc
-                max_dbcr = max_dbcr / sc
-            dbcr = max_dbcr
-            dbct = max_dbct
-            if self.noset is not None:
-                max_dbcn = self.bcn - bcn0
-                if min_step is not None:
-                    max_dbcn = max_dbcn / np.maximum(1, min_step - il)
-                dbcn = max_dbcn
-            else:
-                max_dbcn = None
-                dbcn = None
-            # elastic predictor: final solution of a linear model (1290-1291)
-            self._solve_increment(bcl0, bcb0, dbcr, dbct, dbcn)
-            if self.nonlin:
-                scale_bc = ctx.calc_scf(sld) if il < 10 else 1.          # 1296
-                dbcr = max_dbcr * scale_bc
-                dbct = max_dbct * scale_bc
-                nit = 0
-                change = True
-                conv = False
-                if verb:
-                    print('***Load step #', il)
-                    print('scaling factor', scale_bc)
-                while (change or not conv) and nit <= 15:                 # 1305
-                    if il < 6 and nit > 1:                                # halve the increment (1308-1330)
-                        hs = 0.5
-
-                        def shrink(tgt, reached, cur, mx):
-                            for k in range(dim):
-                                if mx[k] >= 0:
-                                    cur[k] = np.maximum(0.05 * mx[k], np.minimum(tgt[k] - reached[k], cur[k] * hs))
-                                else:
-                                    cur[k] = np.minimum(0.05 * mx[k], np.maximum(tgt[k] - reached[k], cur[k] * hs))
-                        shrink(self.bcr, bcr0, dbcr, max_dbcr)
-                        shrink(self.bct, bct0, dbct, max_dbct)
-                        if self.noset is not None:
-                            shrink(self.bcn, bcn0, dbcn, max_dbcn)
-                    ctx.setupK()                                          # 1333
-                    self._solve_increment(bcl0, bcb0, dbcr, dbct, dbcn)   # 1334-1335
-                    change, conv, max_hh, counts = ctx.sweep(nit)         # 1338-1361 on the device
-                    self.sweep_stats.append((il, nit, change, conv, max_hh, counts))
-                    if verb:
-                        if not conv:
-                            print('\n  ###  Warning: No convergence of plasticity algorithm in trial step #', nit)
-                        print('+++Inner trial step #', nit, 'branches [elastic, 1 step, 50 sub-steps, corrections]:', counts)
-                        print('load increment right:', dbcr)
-                        print('load increment top:', dbct)
-                        if self.noset is not None:
-                            print('load increment set:', dbcn)
-                    if not conv:
-                        nconv += 1
-                    nit += 1
-            # commit (1383-1392).  f += K du uses the matrix the increment was solved with: the last sweep may have
-            # replaced element tangents, but like in the reference K is the one assembled before that sweep -- it is
-            # still in the CSR memory of the device.
-            self._commit()
-            il += 1                                                       # 1395-1413
-            niter.append(nit - 1)
-            co_nconv.append(nconv)
-            bcr0 += dbcr
-            hl0 = np.abs(bcr0[0] - self.bcr[0]) > 1.e-6 and np.abs(self.bcr[0]) > 1.e-9
-            hl1 = np.abs(bcr0[1] - self.bcr[1]) > 1.e-6 and np.abs(self.bcr[1]) > 1.e-9
-            bct0 += dbct
-            hr0 = np.abs(bct0[0] - self.bct[0]) > 1.e-6 and np.abs(self.bct[0]) > 1.e-9
-            hr1 = np.abs(bct0[1] - self.bct[1]) > 1.e-6 and np.abs(self.bct[1]) > 1.e-9
-            if self.noset is not None:
-                bcn0 += dbcn
-                hr0 = hr0 or (np.abs(bcn0[0] - self.bcn[0]) > 1.e-6 and np.abs(self.bcn[0]) > 1.e-9)
-                hr1 = hr1 or (np.abs(bcn0[1] - self.bcn[1]) > 1.e-6 and np.abs(self.bcn[1]) > 1.e-9)
-            bc_inc = bool(hr0 or hr1 or hl0 or hl1)
-            self.calc_global()                                            # 1415-1418
-            self.sgl = np.append(self.sgl, [self.glob['sig']], axis=0)
-            self.egl = np.append(self.egl, [self.glob['eps']], axis=0)
-            self.epgl = np.append(self.epgl, [self.glob['epl']], axis=0)
+        state.more = 1
+        while state.more:
+            il = state.il
+            rep = ctx.load_increment(state, min_step, self.solver_rtol, self.solver_maxit)
+            self._cache = {}
+            if rep.n_warnings:
+                warnings.warn(rep.warning.decode())
+            self.solver_stats += [(int(rep.pass_cg_iters[i]), rep.max_relres) for i in range(rep.solves)]
+            for nit in range(rep.passes):
+                self.sweep_stats.append((il, nit, bool(rep.pass_change[nit]), bool(rep.pass_conv[nit]), rep.pass_max_hh[nit],
+                                         list(rep.pass_counts[nit])))
+            niter.append(rep.passes - 1)
+            co_nconv.append(int(state.nconv))
+            self._store_global(rep)
             if verb:
-                print('Load increment ', il, 'top ', bct0, '/', self.bct, '; rhs', bcr0, '/', self.bcr)
-                print('Global strain: ', np.around(self.glob['eps'], decimals=5))
-                print('Global stress: ', np.around(self.glob['sig'], decimals=3))
-                print('Global plastic strain: ', np.around(self.glob['epl'], decimals=6))
-                print('----------------------------')
-        self.bct_mem = bct0
-        self.bcr_mem = bcr0
-        if self.noset is not None:
-            self.bcn_mem = bcn0
-        self.nsteps = il
+                self._report_increment(il, rep, state)
+        self.bcr_mem = np.array(state.reached_right[:])
+        self.bct_mem = np.array(state.reached_top[:])
+        if carry_set:
+            self.bcn_mem = np.array(state.reached_node[:])
+        self.nsteps = int(state.il)
         self.niter = niter
         self.co_nconv = co_nconv
 
-    def _commit(self):
-        """u += du; f += K du; element state update (1383-1392) on the device; refresh the host copies of u, f."""
-        ctx = self._dev()
-        ctx.commit()
-        self.u = ctx.get_field(_lib.F_U)
-        self.f = ctx.get_field(_lib.F_F)
-        self.du = ctx.get_field(_lib.F_DU)
-        self._cache = {}
+    def _store_global(self, rep):
+        """calc_global (model.py:1473-1511) from the increment report, appended to the history (1415-1418)."""
+        self._set_boundary_globals(np.array([list(row) for row in rep.edge]))
+        g = self.glob
+        g['sig'], g['eps'], g['epl'] = (np.array(v[:]) for v in (rep.glob_sig, rep.glob_eps, rep.glob_epl))
+        self.sgl = np.append(self.sgl, [g['sig']], axis=0)
+        self.egl = np.append(self.egl, [g['eps']], axis=0)
+        self.epgl = np.append(self.epgl, [g['epl']], axis=0)
+
+    def _set_boundary_globals(self, edge):
+        """Boundary strains and stresses from the bcval rows of the left, right, bottom and top nodes (1491-1498)."""
+        (uxl, uyl, fxl, fyl), (uxr, uyr, fxr, fyr), (uxb, uyb, fxb, fyb), (uxt, uyt, fxt, fyt) = edge
+        g = self.glob
+        ax, ay = self.leny * self.thick, self.lenx * self.thick   # cross sections normal to x and to y
+        g['ebc1'], g['sbc1'] = (uxr - uxl) / self.lenx, 0.5 * (fxr - fxl) / ax
+        g['ebc21'], g['sbc21'] = (uyr - uyl) / self.lenx, 0.5 * (fyr - fyl) / ax
+        g['ebc2'], g['sbc2'] = (uyt - uyb) / self.leny, 0.5 * (fyt - fyb) / ay
+        g['ebc12'], g['sbc12'] = (uxt - uxb) / self.leny, 0.5 * (fxt - fxb) / ay
+
+    def _report_increment(self, il, rep, state):
+        print('***Load step #', il)
+        print('scaling factor', rep.scale_bc)
+        for nit in range(rep.passes):
+            if not rep.pass_conv[nit]:
+                print('\n  ###  Warning: No convergence of plasticity algorithm in trial step #', nit)
+            print('+++Inner trial step #', nit, 'branches [elastic, 1 step, 50 sub-steps, corrections]:',
+                  list(rep.pass_counts[nit]), 'CG iterations:', rep.pass_cg_iters[1 + nit])
+        print('load increment right:', list(rep.step_right), 'top:', list(rep.step_top),
+              *(('set:', list(rep.step_node)) if self.noset is not None else ()))
+        print('Load increment ', il + 1, 'top ', list(state.reached_top), '/', self.bct, '; rhs', list(state.reached_right),
+              '/', self.bcr)
+        print('Global strain: ', np.around(self.glob['eps'], decimals=5))
+        print('Global stress: ', np.around(self.glob['sig'], decimals=3))
+        print('Global plastic strain: ', np.around(self.glob['epl'], decimals=6))
+        print('----------------------------')
 
     # ------------------------------------------------------------------------------------------------------
     # post-processing (model.py:1452-1511)
@@ -600,20 +550,9 @@ class Model(object):
 
     def calc_global(self):
         """Global quantities from boundary nodes and from volume-averaged element solutions (model.py:1473-1511)."""
-        uxl, uyl, fxl, fyl = self.bcval(self.noleft)
-        uxr, uyr, fxr, fyr = self.bcval(self.noright)
-        g = self.glob
-        g['ebc1'] = (uxr - uxl) / self.lenx
-        g['sbc1'] = 0.5 * (fxr - fxl) / (self.leny * self.thick)
-        g['ebc21'] = (uyr - uyl) / self.lenx
-        g['sbc21'] = 0.5 * (fyr - fyl) / (self.leny * self.thick)
-        uxb, uyb, fxb, fyb = self.bcval(self.nobot)
-        uxt, uyt, fxt, fyt = self.bcval(self.notop)
-        g['ebc2'] = (uyt - uyb) / self.leny
-        g['sbc2'] = 0.5 * (fyt - fyb) / (self.lenx * self.thick)
-        g['ebc12'] = (uxt - uxb) / self.leny
-        g['sbc12'] = 0.5 * (fxt - fxb) / (self.lenx * self.thick)
-        g['sig'], g['eps'], g['epl'] = self._dev().reduce_global()
+        ctx = self._dev()
+        self._set_boundary_globals(ctx.boundary_values())
+        self.glob['sig'], self.glob['eps'], self.glob['epl'] = ctx.reduce_global()
 
     def plot(self, *a, **k):
         raise NotImplementedError('Model.plot needs matplotlib and is outside the accelerated path; use the element '

@@ -480,3 +480,33 @@ def test_ml_plasticity_sdim3_golden(golden):
             assert len(m.propJ2[sel][key]) == len(ref), (sel, key)
             assert np.max(np.abs(np.asarray(m.propJ2[sel][key]) - ref)) < 1e-6 * max(np.max(np.abs(ref)), 1e-2), (sel, key)
         assert relmax(np.asarray(m.sigeps[sel]['sig']), g['sigeps_%s_sig' % sel]) < 1e-6
+
+
+def test_interleaved_contexts_do_not_disturb_a_model(golden):
+    """The material / geometry tables live in per-device __constant__ banks shared by all contexts (plf_bind).  A Model
+    must get the same solution when Material calls on the default context (other CV: 3-d instead of plane stress,
+    other parameters) and a second Model with another mesh and material run between its own solve() calls."""
+    g = golden('solve_hill_4x4_ps')
+    fe = uniax('hill', N=4, planestress=True, eps=0.005)
+    fe.solve()
+    other = make_material('j2')
+    sig = np.array([[10., 200., 0., 0., 0., 30.]])
+    seq_before = other.calc_seq(sig)
+    fe2 = inclusion(N=6, plastic=True, eps_tot=0.004)
+    fe2.solve(min_step=3)
+    assert other.calc_seq(sig) == seq_before
+    fe.bctop(0.01 * fe.leny, 'disp')
+    other.calc_yf(sig)
+    fe.solve()
+    ref = uniax('hill', N=4, planestress=True, eps=0.005)
+    ref.solve()
+    ref.bctop(0.01 * ref.leny, 'disp')
+    ref.solve()
+    assert fe.nsteps == ref.nsteps and fe.niter == ref.niter
+    assert np.array_equal(fe.u, ref.u)
+    assert np.array_equal(np.array([el.sig for el in fe.element]), np.array([el.sig for el in ref.element]))
+    # and the second model is not disturbed by the first either
+    fe3 = inclusion(N=6, plastic=True, eps_tot=0.004)
+    fe3.solve(min_step=3)
+    assert np.array_equal(fe2.u, fe3.u)
+    del g
