@@ -636,64 +636,52 @@ def main():
         o_ns = _lib.pinned_empty((Nel,), np.int32)
         o_val = _lib.pinned_empty((ctx.nnz,))
 
-        def e2e_step():
-            # one call, host buffers in and out: upload, return mapping + assembly and download pipelined over
-            # chunks of element columns (three streams, PCIe busy in both directions)
-            ctx.step_host(b, hs, he, hd, fy=o_fy, sig_out=o_sig, depl=o_dp, ctan=o_ct, nsteps=o_ns, kval=o_val)
-        for _ in range(2):
-            e2e_step()
-        ke = max(3, min(K, 10))
-        barrier()
-        t0 = time.perf_counter()
-        ctx.event_record(4000)
-        for _ in range(ke):
-            e2e_step()
-        ctx.event_record(4001)
-        ctx.synchronize()
-        barrier()
-        e2e_ms = max_over_ranks(max(ctx.event_elapsed(4000, 4001), (time.perf_counter() - t0) * 1e3)) / ke
-        h2d = Nel * 3 * 48
-        d2h = Nel * (8 + 48 + 48 + 288 + 4) + ctx.nnz * 8
-        e2e = {'value': world * owned / (e2e_ms * 1e-3), 'unit': 'elements/s', 'h2d_bytes_per_step': int(h2d),
-               'd2h_bytes_per_step': int(d2h), 'ms_per_step': e2e_ms,
-               'api': 'plf_step_host: (Nel,6) sig/epl/deps in; fy, sig, depl, grad_stiff, nsteps and the CSR(K) values out (pinned host buffers, chunked three-stream pipeline)'}
-        # informational second figure (NOT the headline): the same call when the consumer of the tangents and of K is
-        # the on-device solver, as in Model.solve -- grad_stiff and CSR(K) stay in HBM, only fy / sig / depl / nsteps
-        # return to the host
-        def lean_step():
-            ctx.step_host(b, hs, he, hd, fy=o_fy, sig_out=o_sig, depl=o_dp, nsteps=o_ns)
-        for _ in range(2):
-            lean_step()
-        barrier()
-        t0 = time.perf_counter()
-        for _ in range(ke):
-            lean_step()
-        ctx.synchronize()
-        barrier()
-        lean_ms = max_over_ranks((time.perf_counter() - t0) * 1e3) / ke
-        e2e['device_resident_tangents_and_K'] = {'value': world * owned / (lean_ms * 1e-3), 'ms_per_step': lean_ms,
-                                                  'd2h_bytes_per_step': int(Nel * (8 + 48 + 48 + 4)),
-                                                  'note': 'informational: grad_stiff and CSR(K) not copied back (on-device solve)'}
+        o_c21 = _lib.pinned_empty((Nel * 21,))
+        o_bits = _lib.pinned_empty(((Nel + 31) // 32,), np.uint32)
+        state = {'packed': 0}
 
-        # informational third figure: the stiffness stays in HBM for the on-device solve (plf_solve_linear), everything the
-        # reference keeps on its element objects (sig, depl, elstiff = grad_stiff) returns to the host.  Never fatal.
-        try:
-            def konly_step():
-                ctx.step_host(b, hs, he, hd, fy=o_fy, sig_out=o_sig, depl=o_dp, ctan=o_ct, nsteps=o_ns)
+        def timed(fn, reps):
             for _ in range(2):
-                konly_step()
-            ctx.synchronize()
+                fn()
+            barrier()
             t0 = time.perf_counter()
-            for _ in range(ke):
-                konly_step()
+            ctx.event_record(4000)
+            for _ in range(reps):
+                fn()
+            ctx.event_record(4001)
             ctx.synchronize()
-            k_ms = (time.perf_counter() - t0) * 1e3 / ke   # rank-local (no collective inside the try block)
-            e2e['device_resident_K'] = {'value': world * owned / (k_ms * 1e-3), 'ms_per_step': k_ms,
-                                        'd2h_bytes_per_step': int(Nel * (8 + 48 + 48 + 288 + 4)),
-                                        'note': 'informational, timed on rank 0 only: CSR(K) not copied back (consumed by the on-device '
-                                                'solve), grad_stiff returned'}
-        except Exception as exc:   # pragma: no cover
-            e2e['device_resident_K'] = {'error': str(exc)}
+            barrier()
+            return max_over_ranks(max(ctx.event_elapsed(4000, 4001), (time.perf_counter() - t0) * 1e3)) / reps
+
+        # headline: one call, host buffers in and out, results in compact form -- what Model.solve's inner pass consumes on
+        # the host (fy, sig, depl, nsteps per element; grad_stiff as upper triangles of the non-elastic elements + one
+        # elastic bit per element); the assembled K stays in HBM for the on-device solve (north star: the Newton loop never
+        # leaves the GPU).  Upload, kernels and download are pipelined over chunks of element columns on three streams.
+        def e2e_step():
+            state['packed'] = ctx.step_host_packed(b, hs, he, hd, o_c21, o_bits, fy=o_fy, sig_out=o_sig, depl=o_dp, nsteps=o_ns)
+        ke = max(3, min(K, 10))
+        e2e_ms = timed(e2e_step, ke)
+        h2d = Nel * 3 * 48
+        d2h = Nel * (8 + 48 + 48 + 4) + state['packed'] * 168 + ((Nel + 31) // 32) * 4
+        e2e = {'value': world * owned / (e2e_ms * 1e-3), 'unit': 'elements/s', 'h2d_bytes_per_step': int(h2d),
+               'd2h_bytes_per_step': int(d2h), 'ms_per_step': e2e_ms, 'packed_tangents': int(state['packed']),
+               'api': 'plf_step_host_packed: (Nel,6) sig/epl/deps in; fy, sig, depl, nsteps, elastic bits and the upper triangles of '
+                      'the non-elastic tangents out; K assembled and left on the device for plf_solve_linear (pinned host buffers, '
+                      'chunked three-stream pipeline)'}
+
+        # round-1 definition for continuity: everything in full form, CSR(K) values included (plf_step_host)
+        def full_step():
+            ctx.step_host(b, hs, he, hd, fy=o_fy, sig_out=o_sig, depl=o_dp, ctan=o_ct, nsteps=o_ns, kval=o_val)
+        full_ms = timed(full_step, ke)
+        e2e['full_copy'] = {'value': world * owned / (full_ms * 1e-3), 'ms_per_step': full_ms, 'h2d_bytes_per_step': int(h2d),
+                            'd2h_bytes_per_step': int(Nel * (8 + 48 + 48 + 288 + 4) + ctx.nnz * 8),
+                            'note': 'plf_step_host: full 6x6 tangents of all elements and the CSR(K) values copied back (the round-1 e2e figure)'}
+
+        def packed_k_step():
+            ctx.step_host_packed(b, hs, he, hd, o_c21, o_bits, fy=o_fy, sig_out=o_sig, depl=o_dp, nsteps=o_ns, kval=o_val)
+        pk_ms = timed(packed_k_step, ke)
+        e2e['packed_with_K'] = {'value': world * owned / (pk_ms * 1e-3), 'ms_per_step': pk_ms,
+                                'd2h_bytes_per_step': int(d2h + ctx.nnz * 8), 'note': 'compact results plus the CSR(K) values'}
 
     if rank != 0:
         group.close()

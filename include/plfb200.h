@@ -170,9 +170,20 @@ int plf_setupK_from_batch(plf_ctx *ctx, const plf_batch *b);
  * (Nel,6) element states in; Material.response results (fy, sig, depl, grad_stiff, nsteps) and the nnz CSR values of
  * the K assembled from the new tangents out.  Upload, update + assembly and download are pipelined over chunks of
  * element columns on three streams (full-duplex PCIe); pass pinned buffers (plf_pinned_alloc).  Output pointers may
- * be NULL.  Single-material meshes; `b` must hold Nel elements. */
+ * be NULL.  `b` must hold Nel elements (material ids are taken from the mesh). */
 int plf_step_host(plf_ctx *ctx, plf_batch *b, const double *sig, const double *epl, const double *deps, double *fy,
                   double *sig_out, double *depl, double *ctan, int32_t *nsteps, double *kval);
+
+/* plf_step_host with compact results.  grad_stiff is symmetric and equals Element.CV bit for bit on the elastic branch
+ * (material.py:253-256), so: elastic_words[(Nel+31)/32] has bit (e % 32) of word e / 32 set for elements that took the
+ * elastic branch (their grad_stiff is CV, their depl is 0), and ct21 receives, in element order, the 21 upper-triangle
+ * entries (row-major, i <= j) of grad_stiff of all OTHER elements; *n_packed is their number (ct21 must hold Nel * 21
+ * doubles).  kval == NULL leaves the assembled K on the device for plf_solve_linear (the Newton loop of Model.solve never
+ * needs it on the host); fy, sig_out, depl, nsteps may be NULL.  Mixed-material meshes are supported (ids from the mesh).
+ * Needs NY * (NX / 8) to be a multiple of 32 (chunks of the pipeline start on bitmap words). */
+int plf_step_host_packed(plf_ctx *ctx, plf_batch *b, const double *sig, const double *epl, const double *deps, double *fy,
+                         double *sig_out, double *depl, int32_t *nsteps, double *ct21, uint32_t *elastic_words,
+                         int64_t *n_packed, double *kval);
 
 /* ---- element state --------------------------------------------------------------------------------------------- */
 typedef enum plf_field {
@@ -280,6 +291,14 @@ int plf_comm_init(plf_ctx *ctx, const unsigned char *id, int rank, int world);  
 /* owned node columns [own_first, own_end) of the local mesh: own_first = 1 on ranks with a left neighbour (column 0 is
  * the neighbour's), own_end = NX on ranks with a right neighbour (column NX is the neighbour's), else 0 / NX + 1 */
 int plf_comm_set_strip(plf_ctx *ctx, int own_first, int own_end);
+/* plf_comm_set_strip plus the position of the strip in the GLOBAL mesh: first_col_global = global index of the local
+ * element column 0 (halo column included), NX_global element columns in all, x_offset = x coordinate of the local node
+ * column 0, lenx_global = Model.lenx.  With this a context can run plf_solve_begin / plf_load_increment as one rank of a
+ * distributed Model.solve: boundary conditions are given for the global model (node sets by global node id), every rank
+ * builds the calc_BC vectors of its node grid, and sweep flags (model.py:1355-1361), calc_scf moments (1056-1062), the
+ * calc_global sums (1500-1511) and the bcval sums (1452-1471) are combined over the ranks, so all ranks step alike. */
+int plf_comm_set_partition(plf_ctx *ctx, int own_first, int own_end, int first_col_global, int NX_global, double x_offset,
+                           double lenx_global);
 /* sum of n <= 64 host doubles over all ranks, in place (sweep flags, calc_global sums, calc_scf moments) */
 int plf_comm_allreduce(plf_ctx *ctx, double *vals, int n);
 int plf_comm_destroy(plf_ctx *ctx);

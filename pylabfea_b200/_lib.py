@@ -100,6 +100,8 @@ def _arr(x, dtype=np.float64):
 def _ptr(a):
     if a is None:
         return None
+    if not a.flags.c_contiguous:
+        raise ValueError('array passed to libplfb200 must be C-contiguous')
     if a.dtype == np.float64:
         return a.ctypes.data_as(_dp)
     if a.dtype == np.int32:
@@ -288,6 +290,9 @@ class Context:
 
     def batch_upload(self, b, sig, epl, deps, mat_id=None):
         mid = None if mat_id is None else _arr(mat_id, np.int32)
+        sig, epl, deps = _arr(sig), _arr(epl), _arr(deps)
+        if not (sig.size == epl.size == deps.size) or sig.size % 6:
+            raise ValueError('batch_upload: sig, epl and deps must all be (n, 6)')
         self._ck(self.L.plf_batch_upload(self.h, b, _ptr(mid), _ptr(sig), _ptr(epl), _ptr(deps)))
 
     def batch_run(self, b):
@@ -336,6 +341,19 @@ class Context:
         """plf_step_host: Material.response for every mesh element + setupK, host buffers in and out, pipelined."""
         self._ck(self.L.plf_step_host(self.h, b, _ptr(sig), _ptr(epl), _ptr(deps), _ptr(fy), _ptr(sig_out), _ptr(depl),
                                       _ptr(ctan), _ptr(nsteps), _ptr(kval)))
+
+    def step_host_packed(self, b, sig, epl, deps, ct21, elastic_words, fy=None, sig_out=None, depl=None, nsteps=None, kval=None):
+        """plf_step_host_packed: as step_host, tangents as upper triangles of the non-elastic elements only (ct21, in
+        element order) + one elastic bit per element; returns the number of packed tangents.  kval=None: K stays on the
+        device."""
+        n = C.c_int64()
+        for a, need in ((ct21, self.Nel * 21), (elastic_words, (self.Nel + 31) // 32)):
+            if not a.flags.c_contiguous or a.size < need:
+                raise ValueError('step_host_packed: output buffer too small or not contiguous')
+        self._ck(self.L.plf_step_host_packed(self.h, b, _ptr(sig), _ptr(epl), _ptr(deps), _ptr(fy), _ptr(sig_out), _ptr(depl),
+                                             _ptr(nsteps), _ptr(ct21), elastic_words.ctypes.data_as(C.c_void_p), C.byref(n),
+                                             _ptr(kval)))
+        return n.value
 
     def get_csr_values(self, out):
         self._ck(self.L.plf_get_csr(self.h, None, None, _ptr(out)))

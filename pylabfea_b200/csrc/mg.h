@@ -5,6 +5,8 @@
 
 namespace plf {
 
+constexpr int MG_MAX_LEVELS = 16;
+
 struct MgLevel {
     int NX = 0, NY = 0;
     int64_t ndof = 0, nnz = 0;
@@ -19,6 +21,12 @@ struct MgHierarchy {
     int nu = 2;                // pre- and post-smoothing sweeps (even)
     int coarse_sweeps = 10;    // damped Jacobi sweeps on the coarsest level (40 measured 15 % slower per solve, 4 % fewer iterations)
     double omega = 0.7;
+    int tail_first = -1;       // first level of the fused single-block tail of the cycle (-1: none fits)
+    int fuse_tail = 2;         // option "mg_fuse_tail": 0 every level as its own kernels, 1 fused single-block tail, 2 (default)
+                               // additionally the cooperative grid kernel for the levels between the fine ones and the tail
+    int coop_first = -1;       // first level run by the cooperative kernel (-1: none)
+    int coop_blocks = 64;
+    unsigned int *d_bar = nullptr;   // arrival counter of the cooperative kernel's grid barrier
     int levels() const { return (int)lv.size(); }
 };
 

@@ -18,6 +18,7 @@
 //     products stay FP64; vectors and accumulations are FP64.
 // All kernels are one thread per row / dof, no atomics: the V-cycle is deterministic.
 #include <algorithm>
+#include <cstring>
 #include <vector>
 
 #include "csr_stencil.cuh"
@@ -264,6 +265,310 @@ __global__ void __launch_bounds__(256) mg_prolong_add_kernel(int NXf, int NYf, c
 }
 
 // ---------------------------------------------------------------------------------------------------------------
+// fused tail of the V-cycle: every level from `l0` down to the coarsest one and back up in ONE thread block, all level
+// vectors in shared memory (ncu launch list of a 256 x 256 solve: 86 % of the GPU time sat in ~5 us launches of the
+// kernels above on levels with a few thousand dofs or less -- 45 of the 68 launches of a V-cycle).  Same arithmetic in
+// the same order as the per-level kernels, so the fused cycle returns bit-identical vectors.  Level matrices are read
+// through the read-only path (a 32 x 32 level is 150 KB of FP32: L1 / L2 resident); a masked row is one with dinv == 0.
+// ---------------------------------------------------------------------------------------------------------------
+struct TailLevel {
+    int NX, NY, ndof, off;        // off: start of the level's slice in each shared-memory vector
+    const float *val;
+    const double *dinv;
+};
+struct TailArgs {
+    TailLevel lv[MG_MAX_LEVELS];
+    int nl;                       // fused levels (lv[0] is the finest of them)
+    int nu, coarse_sweeps, total; // total: sum of ndof over the fused levels
+    double omega;
+    const double *b_in;           // right-hand side of lv[0] (written by the restriction from the level above)
+    double *x_out;                // solution of lv[0] (read by the prolongation to the level above)
+};
+
+__device__ __forceinline__ double tail_row_dot(const TailLevel &L, int row, const double *__restrict__ x)
+{
+    const int NnY = L.NY + 1, n = row >> 1;
+    const int j = n / NnY, k = n - j * NnY;
+    int64_t pos = csr_row_start(L.NX, L.NY, row);
+    double s = 0.;
+#pragma unroll
+    for (int dj = -1; dj <= 1; dj++) {
+        if (j + dj < 0 || j + dj > L.NX) continue;
+#pragma unroll
+        for (int dk = -1; dk <= 1; dk++) {
+            if (k + dk < 0 || k + dk > L.NY) continue;
+            const int m = (j + dj) * NnY + (k + dk);
+            const float2 a = __ldg(reinterpret_cast<const float2 *>(L.val + pos));
+            s = fma((double)a.x, x[2 * m], s);
+            s = fma((double)a.y, x[2 * m + 1], s);
+            pos += 2;
+        }
+    }
+    return s;
+}
+
+// damped Jacobi sweeps on one level; returns the buffer holding the result (the per-level path arranges for it to be x;
+// here the caller just follows the pointer)
+__device__ __forceinline__ double *tail_smooth(const TailLevel &L, int sweeps, bool from_zero, double om, const double *dinv,
+                                               const double *b, double *x, double *t)
+{
+    double *cur = x, *oth = t;
+    int s0 = 0;
+    if (from_zero) {
+        for (int r = threadIdx.x; r < L.ndof; r += blockDim.x) cur[r] = om * dinv[r] * b[r];
+        __syncthreads();
+        s0 = 1;
+    }
+    for (int s = s0; s < sweeps; s++) {
+        for (int r = threadIdx.x; r < L.ndof; r += blockDim.x) {
+            const double di = dinv[r];
+            const double a = tail_row_dot(L, r, cur);
+            oth[r] = di == 0. ? 0. : fma(om * di, b[r] - a, cur[r]);
+        }
+        __syncthreads();
+        double *h = cur; cur = oth; oth = h;
+    }
+    return cur;
+}
+
+__device__ __forceinline__ void tail_cycle(const TailArgs &A, double *sm)
+{
+    double *s_x = sm, *s_t = sm + A.total, *s_b = sm + 2 * A.total, *s_r = sm + 3 * A.total, *s_d = sm + 4 * A.total;
+    __shared__ double *s_res[MG_MAX_LEVELS];   // where each level's current iterate lives (x or t slice)
+    const double om = A.omega;
+    for (int l = 0; l < A.nl; l++) {
+        const TailLevel &L = A.lv[l];
+        for (int r = threadIdx.x; r < L.ndof; r += blockDim.x) s_d[L.off + r] = L.dinv[r];
+    }
+    for (int r = threadIdx.x; r < A.lv[0].ndof; r += blockDim.x) s_b[r] = A.b_in[r];
+    __syncthreads();
+    // down
+    for (int l = 0; l < A.nl - 1; l++) {
+        const TailLevel &L = A.lv[l], &C = A.lv[l + 1];
+        double *x = tail_smooth(L, A.nu, true, om, s_d + L.off, s_b + L.off, s_x + L.off, s_t + L.off);
+        if (threadIdx.x == 0) s_res[l] = x;
+        for (int r = threadIdx.x; r < L.ndof; r += blockDim.x)
+            s_r[L.off + r] = s_d[L.off + r] == 0. ? 0. : s_b[L.off + r] - tail_row_dot(L, r, x);
+        __syncthreads();
+        // b_c = P^T r_f
+        const int NnYf = L.NY + 1, NnYc = C.NY + 1;
+        for (int r = threadIdx.x; r < C.ndof; r += blockDim.x) {
+            double acc = 0.;
+            if (s_d[C.off + r] != 0.) {
+                const int n = r >> 1, c = r & 1, J = n / NnYc, K = n - J * NnYc;
+#pragma unroll
+                for (int a = -1; a <= 1; a++) {
+                    const int fj = 2 * J + a;
+                    if (fj < 0 || fj > L.NX) continue;
+#pragma unroll
+                    for (int bb = -1; bb <= 1; bb++) {
+                        const int fk = 2 * K + bb;
+                        if (fk < 0 || fk > L.NY) continue;
+                        const double w = (a == 0 ? 1. : 0.5) * (bb == 0 ? 1. : 0.5);
+                        acc = fma(w, s_r[L.off + 2 * (fj * NnYf + fk) + c], acc);
+                    }
+                }
+            }
+            s_b[C.off + r] = acc;
+        }
+        __syncthreads();
+    }
+    {
+        const TailLevel &L = A.lv[A.nl - 1];
+        double *x = tail_smooth(L, A.coarse_sweeps, true, om, s_d + L.off, s_b + L.off, s_x + L.off, s_t + L.off);
+        if (threadIdx.x == 0) s_res[A.nl - 1] = x;
+        __syncthreads();
+    }
+    // up
+    for (int l = A.nl - 2; l >= 0; l--) {
+        const TailLevel &L = A.lv[l], &C = A.lv[l + 1];
+        double *xf = s_res[l];
+        const double *xc = s_res[l + 1];
+        const int NnYf = L.NY + 1, NnYc = C.NY + 1;
+        for (int r = threadIdx.x; r < L.ndof; r += blockDim.x) {
+            if (s_d[L.off + r] == 0.) continue;
+            const int n = r >> 1, c = r & 1, p = n / NnYf, q = n - p * NnYf;
+            const int J0 = p >> 1, K0 = q >> 1, nj = (p & 1) ? 2 : 1, nk = (q & 1) ? 2 : 1;
+            const double w = ((p & 1) ? 0.5 : 1.) * ((q & 1) ? 0.5 : 1.);
+            double acc = 0.;
+            for (int tj = 0; tj < nj; tj++)
+                for (int tk = 0; tk < nk; tk++) acc += xc[2 * ((J0 + tj) * NnYc + (K0 + tk)) + c];
+            xf[r] += w * acc;
+        }
+        __syncthreads();
+        double *oth = (xf == s_x + L.off) ? s_t + L.off : s_x + L.off;
+        double *x = tail_smooth(L, A.nu, false, om, s_d + L.off, s_b + L.off, xf, oth);
+        __syncthreads();
+        if (threadIdx.x == 0) s_res[l] = x;
+        __syncthreads();
+    }
+    const double *x0 = s_res[0];
+    for (int r = threadIdx.x; r < A.lv[0].ndof; r += blockDim.x) A.x_out[r] = x0[r];
+}
+
+__global__ void __launch_bounds__(1024, 1) mg_tail_kernel(const TailArgs A)
+{
+    extern __shared__ double sm[];
+    tail_cycle(A, sm);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// cooperative middle of the V-cycle: the levels between the bandwidth-bound fine ones and the single-block tail
+// (at 1024 x 1024: 256^2, 128^2, 64^2) are a few microseconds of work per step each; as separate kernels a cycle spends
+// its time between launches.  One cooperative grid walks these levels down, lets block 0 run the tail in shared
+// memory, and walks back up, with a grid-wide barrier after every step.  Level vectors live in global memory (L2) and
+// are read with ld.global.cg: another block wrote them earlier in this very kernel, L1 may hold a stale line.
+// Arithmetic and order are those of the per-level kernels (bit-identical results).
+// ---------------------------------------------------------------------------------------------------------------
+struct MidLevel {
+    int NX, NY, ndof, pad;
+    const float *val;
+    const double *dinv;
+    double *x, *t, *b, *r;
+};
+struct CoopArgs {
+    MidLevel lv[MG_MAX_LEVELS];
+    int nmid;                 // levels run by the whole grid; lv[nmid] (x, b only) is the first tail level when has_tail
+    int has_tail;
+    TailArgs tail;
+};
+
+__device__ __forceinline__ double mid_row_dot(const MidLevel &L, int row, const double *x)
+{
+    const int NnY = L.NY + 1, n = row >> 1;
+    const int j = n / NnY, k = n - j * NnY;
+    int64_t pos = csr_row_start(L.NX, L.NY, row);
+    double s = 0.;
+#pragma unroll
+    for (int dj = -1; dj <= 1; dj++) {
+        if (j + dj < 0 || j + dj > L.NX) continue;
+#pragma unroll
+        for (int dk = -1; dk <= 1; dk++) {
+            if (k + dk < 0 || k + dk > L.NY) continue;
+            const int m = (j + dj) * NnY + (k + dk);
+            const float2 a = __ldg(reinterpret_cast<const float2 *>(L.val + pos));
+            const double2 xv = __ldcg(reinterpret_cast<const double2 *>(x + 2 * m));
+            s = fma((double)a.x, xv.x, s);
+            s = fma((double)a.y, xv.y, s);
+            pos += 2;
+        }
+    }
+    return s;
+}
+
+__device__ __forceinline__ void coop_barrier(unsigned int *bar, unsigned int &epoch)
+{
+    // monotonic arrival counter (zeroed by the host before the launch); all blocks are co-resident (cooperative launch)
+    __syncthreads();
+    epoch += gridDim.x;
+    if (threadIdx.x == 0) {
+        __threadfence();
+        atomicAdd(bar, 1u);
+        while (*reinterpret_cast<volatile unsigned int *>(bar) < epoch) { }
+        __threadfence();
+    }
+    __syncthreads();
+}
+
+// result buffer of `sweeps` Jacobi sweeps (same ping-pong as the host-driven smoother: from zero the first sweep writes
+// x when `sweeps` is odd, else t; otherwise the sweeps start from x)
+__device__ __forceinline__ double *mid_smooth(const MidLevel &L, int sweeps, bool from_zero, double om, double *x_start,
+                                              unsigned int *bar, unsigned int &epoch)
+{
+    const int gtid = blockIdx.x * blockDim.x + threadIdx.x, gsz = gridDim.x * blockDim.x;
+    double *cur, *oth;
+    int s0 = 0;
+    if (from_zero) {
+        cur = (sweeps & 1) ? L.x : L.t;
+        oth = (cur == L.x) ? L.t : L.x;
+        for (int r = gtid; r < L.ndof; r += gsz) __stcg(cur + r, om * __ldg(L.dinv + r) * __ldcg(L.b + r));
+        coop_barrier(bar, epoch);
+        s0 = 1;
+    } else {
+        cur = x_start;
+        oth = (cur == L.x) ? L.t : L.x;
+    }
+    for (int s = s0; s < sweeps; s++) {
+        for (int r = gtid; r < L.ndof; r += gsz) {
+            const double di = __ldg(L.dinv + r);
+            const double a = mid_row_dot(L, r, cur);
+            __stcg(oth + r, di == 0. ? 0. : fma(om * di, __ldcg(L.b + r) - a, __ldcg(cur + r)));
+        }
+        coop_barrier(bar, epoch);
+        double *h = cur; cur = oth; oth = h;
+    }
+    return cur;
+}
+
+__global__ void __launch_bounds__(1024, 1) mg_coop_kernel(const CoopArgs A, unsigned int *bar)
+{
+    extern __shared__ double sm[];
+    unsigned int epoch = 0;
+    const int gtid = blockIdx.x * blockDim.x + threadIdx.x, gsz = gridDim.x * blockDim.x;
+    const double om = A.tail.omega;
+    const int nu = A.tail.nu;
+    // down
+    for (int l = 0; l < A.nmid; l++) {
+        const MidLevel &L = A.lv[l];
+        const MidLevel &C = A.lv[l + 1];
+        double *x = mid_smooth(L, nu, true, om, nullptr, bar, epoch);   // ends in L.x (nu is even)
+        for (int r = gtid; r < L.ndof; r += gsz)
+            __stcg(L.r + r, __ldg(L.dinv + r) == 0. ? 0. : __ldcg(L.b + r) - mid_row_dot(L, r, x));
+        coop_barrier(bar, epoch);
+        const int NnYf = L.NY + 1, NnYc = C.NY + 1;
+        for (int r = gtid; r < C.ndof; r += gsz) {
+            double acc = 0.;
+            if (__ldg(C.dinv + r) != 0.) {
+                const int n = r >> 1, c = r & 1, J = n / NnYc, K = n - J * NnYc;
+#pragma unroll
+                for (int a = -1; a <= 1; a++) {
+                    const int fj = 2 * J + a;
+                    if (fj < 0 || fj > L.NX) continue;
+#pragma unroll
+                    for (int bb = -1; bb <= 1; bb++) {
+                        const int fk = 2 * K + bb;
+                        if (fk < 0 || fk > L.NY) continue;
+                        const double w = (a == 0 ? 1. : 0.5) * (bb == 0 ? 1. : 0.5);
+                        acc = fma(w, __ldcg(L.r + 2 * (fj * NnYf + fk) + c), acc);
+                    }
+                }
+            }
+            __stcg(C.b + r, acc);
+        }
+        coop_barrier(bar, epoch);
+    }
+    if (A.has_tail) {
+        if (blockIdx.x == 0) tail_cycle(A.tail, sm);
+    } else {
+        // no tail: lv[nmid] is the coarsest level and is smoothed by the grid
+        const MidLevel &L = A.lv[A.nmid];
+        double *x = mid_smooth(L, A.tail.coarse_sweeps, true, om, nullptr, bar, epoch);
+        if (x != L.x) {
+            for (int r = gtid; r < L.ndof; r += gsz) __stcg(L.x + r, __ldcg(x + r));
+        }
+    }
+    coop_barrier(bar, epoch);
+    // up
+    for (int l = A.nmid - 1; l >= 0; l--) {
+        const MidLevel &L = A.lv[l];
+        const MidLevel &C = A.lv[l + 1];
+        const int NnYf = L.NY + 1, NnYc = C.NY + 1;
+        for (int r = gtid; r < L.ndof; r += gsz) {
+            if (__ldg(L.dinv + r) == 0.) continue;
+            const int n = r >> 1, c = r & 1, p = n / NnYf, q = n - p * NnYf;
+            const int J0 = p >> 1, K0 = q >> 1, nj = (p & 1) ? 2 : 1, nk = (q & 1) ? 2 : 1;
+            const double w = ((p & 1) ? 0.5 : 1.) * ((q & 1) ? 0.5 : 1.);
+            double acc = 0.;
+            for (int tj = 0; tj < nj; tj++)
+                for (int tk = 0; tk < nk; tk++) acc += __ldcg(C.x + 2 * ((J0 + tj) * NnYc + (K0 + tk)) + c);
+            __stcg(L.x + r, __ldcg(L.x + r) + w * acc);
+        }
+        coop_barrier(bar, epoch);
+        mid_smooth(L, nu, false, om, L.x, bar, epoch);   // even number of sweeps: back in L.x
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------------------------
 static inline unsigned grid_for(int64_t n, int bs) { return (unsigned)((n + bs - 1) / bs); }
@@ -277,6 +582,8 @@ void mg_free(MgHierarchy &H)
         cudaFree(L.dinv); cudaFree(L.r); cudaFree(L.t);
     }
     H.lv.clear();
+    cudaFree(H.d_bar);
+    H.d_bar = nullptr;
 }
 
 cudaError_t mg_build(MgHierarchy &H, int NX, int NY)
@@ -289,7 +596,7 @@ cudaError_t mg_build(MgHierarchy &H, int NX, int NY)
         L.ndof = 2ll * (nx + 1) * (ny + 1);
         L.nnz = 4ll * (3 * nx + 1) * (3 * ny + 1);
         H.lv.push_back(L);
-        if ((nx & 1) || (ny & 1) || nx < 4 || ny < 4 || (int)H.lv.size() >= 16) break;
+        if ((nx & 1) || (ny & 1) || nx < 4 || ny < 4 || (int)H.lv.size() >= MG_MAX_LEVELS) break;
         nx >>= 1; ny >>= 1;
     }
     for (size_t l = 0; l < H.lv.size(); l++) {
@@ -305,6 +612,31 @@ cudaError_t mg_build(MgHierarchy &H, int NX, int NY)
         if ((e = cudaMalloc((void **)&L.dinv, nb)) != cudaSuccess) return e;
         if ((e = cudaMalloc((void **)&L.r, nb)) != cudaSuccess) return e;
         if ((e = cudaMalloc((void **)&L.t, nb)) != cudaSuccess) return e;
+    }
+    // fused tail: the first level whose vectors (5 per level, all coarser levels included) fit one block's shared memory
+    H.tail_first = -1;
+    for (size_t l = 1; l < H.lv.size(); l++) {   // level 0 takes CG's own vectors: never part of the tail
+        int64_t total = 0;
+        for (size_t m = l; m < H.lv.size(); m++) total += H.lv[m].ndof;
+        if (total * 5 * (int64_t)sizeof(double) <= 200 * 1024) { H.tail_first = (int)l; break; }
+    }
+    if (H.tail_first >= 0) {
+        cudaError_t e = cudaFuncSetAttribute(mg_tail_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        if (e != cudaSuccess) return e;
+        if ((e = cudaFuncSetAttribute(mg_coop_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)) != cudaSuccess) return e;
+    }
+    // cooperative middle: the first level (>= 1) with at most 160 k dofs (256 x 256: ~2 rows per thread of a 64-block grid)
+    H.coop_first = -1;
+    for (size_t l = 1; l < H.lv.size(); l++)
+        if (H.lv[l].ndof <= 160 * 1024) { H.coop_first = (int)l; break; }
+    {
+        int dev = 0, sms = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        H.coop_blocks = std::max(1, std::min(64, sms));
+        cudaError_t e = cudaMalloc((void **)&H.d_bar, 64);
+        if (e != cudaSuccess) return e;
+        cudaMemset(H.d_bar, 0, 64);
     }
     return cudaSuccess;
 }
@@ -363,15 +695,84 @@ cudaError_t mg_vcycle(const LaunchCtx &lc, MgHierarchy &H, const double *r_fine,
         }
         (void)first;
     };
-    for (int l = 0; l < nl - 1; l++) {
+    // levels [0, mid) run as per-level kernels, [mid, top) in the cooperative grid kernel, [top, nl) in the fused
+    // single-block tail (inside the cooperative kernel when there is one)
+    int top = (H.fuse_tail && H.tail_first > 0) ? H.tail_first : nl;
+    const int mid = (H.fuse_tail >= 2 && H.coop_first > 0 && H.coop_first < top) ? H.coop_first : -1;
+    if (mid > 0) {
+        for (int l = 0; l < mid; l++) {
+            MgLevel &L = H.lv[l], &C = H.lv[l + 1];
+            smooth(L, H.nu, true);
+            mg_residual_kernel<<<grid_for(L.ndof, 256), 256, 0, lc.stream>>>(L.NX, L.NY, L.val, L.mask, L.b, L.x, L.r);
+            mg_restrict_kernel<<<grid_for(C.ndof, 256), 256, 0, lc.stream>>>(C.NX, C.NY, L.r, C.mask, C.b);
+            *launches += 2;
+        }
+        CoopArgs A;
+        memset(&A, 0, sizeof A);
+        A.nmid = std::min(top, nl - 1) - mid;          // the coarsest level is never a "mid" level: it has no level below
+        A.has_tail = top < nl ? 1 : 0;
+        for (int l = mid; l <= mid + A.nmid && l < nl; l++) {
+            const MgLevel &L = H.lv[l];
+            A.lv[l - mid] = MidLevel{L.NX, L.NY, (int)L.ndof, 0, L.val, L.dinv, L.x, L.t, L.b, L.r};
+        }
+        int off = 0;
+        A.tail.nl = 0;
+        if (A.has_tail) {
+            A.tail.nl = nl - top;
+            for (int l = top; l < nl; l++) {
+                const MgLevel &L = H.lv[l];
+                A.tail.lv[l - top] = TailLevel{L.NX, L.NY, (int)L.ndof, off, L.val, L.dinv};
+                off += (int)L.ndof;
+            }
+            A.tail.b_in = H.lv[top].b; A.tail.x_out = H.lv[top].x;
+        }
+        A.tail.total = off; A.tail.nu = H.nu; A.tail.coarse_sweeps = H.coarse_sweeps; A.tail.omega = om;
+        cudaMemsetAsync(H.d_bar, 0, sizeof(unsigned int), lc.stream);
+        cudaLaunchAttribute attr;
+        attr.id = cudaLaunchAttributeCooperative;
+        attr.val.cooperative = 1;
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3((unsigned)H.coop_blocks);
+        cfg.blockDim = dim3(1024);
+        cfg.dynamicSmemBytes = 5 * (size_t)off * sizeof(double);
+        cfg.stream = lc.stream;
+        cfg.attrs = &attr;
+        cfg.numAttrs = 1;
+        cudaError_t e = cudaLaunchKernelEx(&cfg, mg_coop_kernel, A, H.d_bar);
+        if (e != cudaSuccess) return e;
+        (*launches)++;
+        for (int l = mid - 1; l >= 0; l--) {
+            MgLevel &L = H.lv[l], &C = H.lv[l + 1];
+            mg_prolong_add_kernel<<<grid_for(L.ndof, 256), 256, 0, lc.stream>>>(L.NX, L.NY, C.x, L.mask, L.x);
+            (*launches)++;
+            smooth(L, H.nu, false);
+        }
+        return cudaGetLastError();
+    }
+    for (int l = 0; l < std::min(top, nl - 1); l++) {
         MgLevel &L = H.lv[l], &C = H.lv[l + 1];
         smooth(L, H.nu, true);
         mg_residual_kernel<<<grid_for(L.ndof, 256), 256, 0, lc.stream>>>(L.NX, L.NY, L.val, L.mask, L.b, L.x, L.r);
         mg_restrict_kernel<<<grid_for(C.ndof, 256), 256, 0, lc.stream>>>(C.NX, C.NY, L.r, C.mask, C.b);
         *launches += 2;
     }
-    smooth(H.lv[nl - 1], H.coarse_sweeps, true);
-    for (int l = nl - 2; l >= 0; l--) {
+    if (top < nl) {
+        TailArgs A;
+        int off = 0;
+        A.nl = nl - top;
+        for (int l = top; l < nl; l++) {
+            const MgLevel &L = H.lv[l];
+            A.lv[l - top] = TailLevel{L.NX, L.NY, (int)L.ndof, off, L.val, L.dinv};
+            off += (int)L.ndof;
+        }
+        A.total = off; A.nu = H.nu; A.coarse_sweeps = H.coarse_sweeps; A.omega = om;
+        A.b_in = H.lv[top].b; A.x_out = H.lv[top].x;
+        mg_tail_kernel<<<1, 1024, 5 * (size_t)off * sizeof(double), lc.stream>>>(A);
+        (*launches)++;
+    } else {
+        smooth(H.lv[nl - 1], H.coarse_sweeps, true);
+    }
+    for (int l = std::min(top, nl - 1) - 1; l >= 0; l--) {
         MgLevel &L = H.lv[l], &C = H.lv[l + 1];
         mg_prolong_add_kernel<<<grid_for(L.ndof, 256), 256, 0, lc.stream>>>(L.NX, L.NY, C.x, L.mask, L.x);
         (*launches)++;

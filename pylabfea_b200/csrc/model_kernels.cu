@@ -175,7 +175,7 @@ __global__ void __launch_bounds__(128) sweep_hill_kernel(int64_t n, int NY, int 
                                                          double *__restrict__ res_sig, double *__restrict__ res_depl,
                                                          double *__restrict__ fyld, int32_t *__restrict__ nsteps,
                                                          unsigned char *__restrict__ has_res, const int32_t *__restrict__ index,
-                                                         int32_t *__restrict__ worklist, SweepStats *st)
+                                                         int32_t *__restrict__ worklist, SweepStats *st, int64_t stat_first)
 {
     // MODE 1 / !GATHER: pass A over all elements; MODE 0 / GATHER: persistent pass B over the work list (length read
     // from device memory: no host round trip between the passes); MODE 0 / !GATHER: unsplit response_core.
@@ -229,6 +229,7 @@ __global__ void __launch_bounds__(128) sweep_hill_kernel(int64_t n, int NY, int 
                 }
             }
         }
+        if (e < stat_first) es.active = false;   // halo elements of a strip partition: updated here, counted by their owner
         if (MODE == 1) warp_append(defer, (int32_t)e, worklist, &st->work_count);
         stats_block(es, st);
     }
@@ -236,40 +237,55 @@ __global__ void __launch_bounds__(128) sweep_hill_kernel(int64_t n, int NY, int 
 
 // sweep, thread per element, for the yield models with eigen-decompositions (Yld2004-18p, sdim = 3): unsplit
 // response_core, FP64-bound
-template <class Model, int KIND>
+template <class Model, int KIND, int MODE>
 __global__ void __launch_bounds__(128) sweep_model_kernel(int64_t n, int NY, int nit, const int32_t *__restrict__ desc,
                                                            const double *__restrict__ sig, const double *__restrict__ epl,
                                                            const double *__restrict__ du, double *__restrict__ elstiff,
                                                            double *__restrict__ res_sig, double *__restrict__ res_depl,
                                                            double *__restrict__ fyld, int32_t *__restrict__ nsteps,
-                                                           unsigned char *__restrict__ has_res, SweepStats *st)
+                                                           unsigned char *__restrict__ has_res, int32_t *__restrict__ worklist,
+                                                           SweepStats *st, int64_t stat_first)
 {
-    const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    ElemStats es;
-    if (e < n) {
-        const int d = __ldg(desc + e);
-        const DevMat &m = c_mat[d & 0xffff];
-        if (m.kind == KIND) {
-            double s[6], ep[6], de[6], dp[6], gs[21], fyv;
-            int ns = 0;
+    // MODE 0: unsplit; MODE 1: pass over all elements, 50-sub-step elements deferred to the work list; MODE 2: persistent
+    // pass over the list (length read from device memory)
+    const int64_t total = (MODE == 2) ? (int64_t)st->work_count : n;
+    const int64_t stride = (MODE == 2) ? (int64_t)gridDim.x * blockDim.x : total + blockDim.x;
+    for (int64_t t0 = (int64_t)blockIdx.x * blockDim.x; t0 < total; t0 += stride) {
+        const int64_t t = t0 + threadIdx.x;
+        ElemStats es;
+        bool defer = false;
+        int64_t e = -1;
+        if (t < total) {
+            e = (MODE == 2) ? (int64_t)worklist[t] : t;
+            const int d = __ldg(desc + e);
+            const DevMat &m = c_mat[d & 0xffff];
+            if (m.kind == KIND) {
+                double s[6], ep[6], de[6], dp[6], gs[21], fyv;
+                int ns = 0;
 #pragma unroll
-            for (int k = 0; k < 6; k++) { s[k] = __ldg(sig + e * 6 + k); ep[k] = __ldg(epl + e * 6 + k); }
-            element_strain(c_geom[d >> 16], NY, e, du, de);
-            Model ym(m);
-            const int br = response_core<0>(ym, m, s, ep, de, dp, gs, fyv, ns);
-            es = sweep_finish(m, e, nit, s, dp, gs, fyv, ns, br, ep, elstiff, res_sig, res_depl, fyld, nsteps, has_res);
+                for (int k = 0; k < 6; k++) { s[k] = __ldg(sig + e * 6 + k); ep[k] = __ldg(epl + e * 6 + k); }
+                element_strain(c_geom[d >> 16], NY, e, du, de);
+                Model ym(m);
+                const int br = response_core<MODE == 1 ? 1 : 0>(ym, m, s, ep, de, dp, gs, fyv, ns);
+                if (br < 0) defer = true;
+                else es = sweep_finish(m, e, nit, s, dp, gs, fyv, ns, br, ep, elstiff, res_sig, res_depl, fyld, nsteps, has_res);
+            }
         }
+        if (e < stat_first) es.active = false;
+        if (MODE == 1) warp_append(defer, (int32_t)e, worklist, &st->work_count);
+        stats_block(es, st);
     }
-    stats_block(es, st);
 }
 
 // sweep, warp per element, one SVC material (SV table in shared memory)
-__global__ void __launch_bounds__(256) sweep_svc_kernel(int64_t n, int NY, int nit, int mid, const int32_t *__restrict__ desc,
+constexpr int SVCW = 8;   // warps per block of the SVC kernels
+
+__global__ void __launch_bounds__(SVCW * 32) sweep_svc_kernel(int64_t n, int NY, int nit, int mid, const int32_t *__restrict__ desc,
                                                         const double *__restrict__ sig, const double *__restrict__ epl,
                                                         const double *__restrict__ du, double *__restrict__ elstiff,
                                                         double *__restrict__ res_sig, double *__restrict__ res_depl,
                                                         double *__restrict__ fyld, int32_t *__restrict__ nsteps,
-                                                        unsigned char *__restrict__ has_res, SweepStats *st)
+                                                        unsigned char *__restrict__ has_res, SweepStats *st, int64_t stat_first)
 {
     extern __shared__ double smem[];
     const DevMat &m = c_mat[mid];
@@ -294,7 +310,7 @@ __global__ void __launch_bounds__(256) sweep_svc_kernel(int64_t n, int NY, int n
         const int br = response_core<0>(ym, m, s, ep, de, dp, gs, fyv, ns);
         if (lane == 0) {
             ElemStats es = sweep_finish(m, e, nit, s, dp, gs, fyv, ns, br, ep, elstiff, res_sig, res_depl, fyld, nsteps, has_res);
-            stats_atomics(es, st);
+            if (e >= stat_first) stats_atomics(es, st);
         }
     }
 }
@@ -307,7 +323,7 @@ cudaError_t modelk_init()
 cudaError_t launch_sweep(const LaunchCtx &lc, const DevMat *hmats, int nmat, int64_t Nel, int NY, int nit, const int32_t *desc,
                          const double *sig, const double *epl, const double *du, double *elstiff, double *res_sig,
                          double *res_depl, double *fyld, int32_t *nsteps, unsigned char *has_res, int32_t *worklist,
-                         void *d_stats, void *h_stats, int compact, int64_t *launches)
+                         void *d_stats, void *h_stats, int compact, int64_t *launches, int64_t stat_first)
 {
     SweepStats *st = (SweepStats *)d_stats;
     cudaError_t e = cudaMemsetAsync(st, 0, sizeof(SweepStats), lc.stream);
@@ -318,14 +334,14 @@ cudaError_t launch_sweep(const LaunchCtx &lc, const DevMat *hmats, int nmat, int
     if (any_hill) {
         if (compact) {
             sweep_hill_kernel<1, false><<<grid, 128, 0, lc.stream>>>(Nel, NY, nit, desc, sig, epl, du, elstiff, res_sig, res_depl,
-                                                                      fyld, nsteps, has_res, nullptr, worklist, st);
+                                                                      fyld, nsteps, has_res, nullptr, worklist, st, stat_first);
             const unsigned bgrid = (unsigned)std::min<int64_t>((int64_t)lc.sm_count * 8, (int64_t)grid);
             sweep_hill_kernel<0, true><<<bgrid, 128, 0, lc.stream>>>(0, NY, nit, desc, sig, epl, du, elstiff, res_sig, res_depl, fyld,
-                                                                      nsteps, has_res, worklist, nullptr, st);
+                                                                      nsteps, has_res, worklist, nullptr, st, stat_first);
             *launches += 2;
         } else {
             sweep_hill_kernel<0, false><<<grid, 128, 0, lc.stream>>>(Nel, NY, nit, desc, sig, epl, du, elstiff, res_sig, res_depl,
-                                                                      fyld, nsteps, has_res, nullptr, nullptr, st);
+                                                                      fyld, nsteps, has_res, nullptr, nullptr, st, stat_first);
             (*launches)++;
         }
     }
@@ -334,25 +350,34 @@ cudaError_t launch_sweep(const LaunchCtx &lc, const DevMat *hmats, int nmat, int
         any_barlat |= (hmats[i].kind == PLF_MAT_BARLAT);
         any_hill3 |= (hmats[i].kind == PLF_MAT_HILL3);
     }
-    if (any_barlat) {
-        sweep_model_kernel<BarlatModel, PLF_MAT_BARLAT><<<grid, 128, 0, lc.stream>>>(Nel, NY, nit, desc, sig, epl, du, elstiff, res_sig,
-                                                                                     res_depl, fyld, nsteps, has_res, st);
-        (*launches)++;
-    }
-    if (any_hill3) {
-        sweep_model_kernel<HillPrincModel, PLF_MAT_HILL3><<<grid, 128, 0, lc.stream>>>(Nel, NY, nit, desc, sig, epl, du, elstiff,
-                                                                                       res_sig, res_depl, fyld, nsteps, has_res, st);
-        (*launches)++;
-    }
+    const unsigned mgrid = (unsigned)std::min<int64_t>((int64_t)lc.sm_count * 8, (int64_t)grid);
+#define SWEEP_MODEL(MODEL, KIND)                                                                                                       \
+    do {                                                                                                                               \
+        if (compact) {                                                                                                                 \
+            if ((e = cudaMemsetAsync(&st->work_count, 0, sizeof(unsigned int), lc.stream)) != cudaSuccess) return e;                   \
+            sweep_model_kernel<MODEL, KIND, 1><<<grid, 128, 0, lc.stream>>>(Nel, NY, nit, desc, sig, epl, du, elstiff, res_sig, res_depl, \
+                                                                            fyld, nsteps, has_res, worklist, st, stat_first);          \
+            sweep_model_kernel<MODEL, KIND, 2><<<mgrid, 128, 0, lc.stream>>>(Nel, NY, nit, desc, sig, epl, du, elstiff, res_sig,        \
+                                                                             res_depl, fyld, nsteps, has_res, worklist, st, stat_first); \
+            *launches += 2;                                                                                                            \
+        } else {                                                                                                                       \
+            sweep_model_kernel<MODEL, KIND, 0><<<grid, 128, 0, lc.stream>>>(Nel, NY, nit, desc, sig, epl, du, elstiff, res_sig, res_depl, \
+                                                                            fyld, nsteps, has_res, nullptr, st, stat_first);           \
+            (*launches)++;                                                                                                             \
+        }                                                                                                                              \
+    } while (0)
+    if (any_barlat) SWEEP_MODEL(BarlatModel, PLF_MAT_BARLAT);
+    if (any_hill3) SWEEP_MODEL(HillPrincModel, PLF_MAT_HILL3);
+#undef SWEEP_MODEL
     for (int i = 0; i < nmat; i++) {
         if (hmats[i].kind != PLF_MAT_SVC) continue;
         e = cudaMemsetAsync(&st->queue, 0, sizeof(unsigned long long), lc.stream);
         if (e != cudaSuccess) return e;
         int blocks = lc.sm_count * 2;
-        int64_t need = (Nel + 7) / 8;
+        int64_t need = (Nel + SVCW - 1) / SVCW;
         if (blocks > need) blocks = (int)need;
-        sweep_svc_kernel<<<blocks, 256, sizeof(double) * 7 * (size_t)hmats[i].nsv_pad, lc.stream>>>(
-            Nel, NY, nit, i, desc, sig, epl, du, elstiff, res_sig, res_depl, fyld, nsteps, has_res, st);
+        sweep_svc_kernel<<<blocks, SVCW * 32, sizeof(double) * 7 * (size_t)hmats[i].nsv_pad, lc.stream>>>(
+            Nel, NY, nit, i, desc, sig, epl, du, elstiff, res_sig, res_depl, fyld, nsteps, has_res, st, stat_first);
         (*launches)++;
     }
     e = cudaMemcpyAsync(h_stats, st, sizeof(SweepStats), cudaMemcpyDeviceToHost, lc.stream);
@@ -480,12 +505,12 @@ __device__ __forceinline__ bool block_reduce_to_partials(double *v, double *part
 __global__ void __launch_bounds__(256) global_sums_kernel(int64_t Nel, const int32_t *__restrict__ desc,
                                                           const double *__restrict__ sig, const double *__restrict__ eps,
                                                           const double *__restrict__ epl, double *partial,
-                                                          unsigned int *counter, double *out)
+                                                          unsigned int *counter, double *out, int64_t e_first)
 {
     double v[18];
 #pragma unroll
     for (int i = 0; i < 18; i++) v[i] = 0.;
-    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < Nel; e += (int64_t)gridDim.x * blockDim.x) {
+    for (int64_t e = e_first + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < Nel; e += (int64_t)gridDim.x * blockDim.x) {
         const double vel = c_geom[desc[e] >> 16].vel;
 #pragma unroll
         for (int k = 0; k < 6; k++) {
@@ -532,7 +557,7 @@ __global__ void __launch_bounds__(128) scf_elements_kernel(int64_t Nel, int NY, 
     });
 }
 
-__global__ void __launch_bounds__(256) scf_svc_kernel(int64_t Nel, int NY, int mid, const int32_t *__restrict__ desc,
+__global__ void __launch_bounds__(SVCW * 32) scf_svc_kernel(int64_t Nel, int NY, int mid, const int32_t *__restrict__ desc,
                                                       const double *__restrict__ sig, const double *__restrict__ epl,
                                                       const double *__restrict__ du, const double *__restrict__ elstiff,
                                                       const double *__restrict__ sld, double *__restrict__ hval,
@@ -549,7 +574,7 @@ __global__ void __launch_bounds__(256) scf_svc_kernel(int64_t Nel, int NY, int m
     double ld[6];
 #pragma unroll
     for (int k = 0; k < 6; k++) ld[k] = sld[k];
-    for (int64_t e = (int64_t)blockIdx.x * 8 + warp; e < Nel; e += (int64_t)gridDim.x * 8) {
+    for (int64_t e = (int64_t)blockIdx.x * SVCW + warp; e < Nel; e += (int64_t)gridDim.x * SVCW) {
         const int d = desc[e];
         if ((d & 0xffff) != mid) continue;
         double de[6], ds[6], C[36], s[6], ep[6];
@@ -581,11 +606,12 @@ __global__ void __launch_bounds__(256) scf_svc_kernel(int64_t Nel, int NY, int m
 // pass 2/3: moments.  mode 0: {count, sum, min-as-negated-max}; mode 1: sum mult * (h - mean)^2
 __global__ void __launch_bounds__(256) scf_moments_kernel(int64_t Nel, const double *__restrict__ hval,
                                                           const unsigned char *__restrict__ mult, double mean, int mode,
-                                                          double *partial, unsigned int *counter, double *out, double *minval)
+                                                          double *partial, unsigned int *counter, double *out, double *minval,
+                                                          int64_t e_first)
 {
     double v[2] = {0., 0.};
     double mn = 2.;
-    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < Nel; e += (int64_t)gridDim.x * blockDim.x) {
+    for (int64_t e = e_first + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < Nel; e += (int64_t)gridDim.x * blockDim.x) {
         const double mu = (double)mult[e];
         if (mu == 0.) continue;
         const double h = hval[e];
@@ -742,7 +768,9 @@ __global__ void __launch_bounds__(256) cg_ghost_mask_kernel(int64_t n, int NnY, 
 }
 
 // r.z after the V-cycle -> rz[SLOT]
-template <int SLOT>
+// DIST: this rank's sum stays in sc->tmp[0]; it is all-reduced (together with r.r in tmp[1]) and published by
+// cg_publish_kernel
+template <int SLOT, bool DIST = false>
 __global__ void __launch_bounds__(256) cg_rz_kernel(int64_t n, const double *__restrict__ r, const double *__restrict__ z,
                                                     const unsigned char *__restrict__ fixed, CgScalars *sc, double *partial,
                                                     unsigned int *counter)
@@ -750,8 +778,11 @@ __global__ void __launch_bounds__(256) cg_rz_kernel(int64_t n, const double *__r
     double v[1] = {0.};
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
         if (!fixed[i]) v[0] += r[i] * z[i];
-    if (block_reduce_to_partials<1>(v, partial, counter, sc->tmp, 0)) sc->rz[SLOT] = sc->tmp[0];
+    if (block_reduce_to_partials<1>(v, partial, counter, sc->tmp, 0) && !DIST) sc->rz[SLOT] = sc->tmp[0];
 }
+
+// distributed start with the multigrid preconditioner: r.z of z = V(r), summed over the ranks, becomes rz[0]
+__global__ void cg_publish_init_kernel(CgScalars *sc) { sc->rz[0] = sc->tmp[0]; }
 
 // beta = rz_new / rz_old ; p = z + beta p
 template <int P>
@@ -841,10 +872,11 @@ cudaError_t launch_commit(const LaunchCtx &lc, int64_t Nel, int64_t Ndof, int NY
 }
 
 cudaError_t launch_global_sums(const LaunchCtx &lc, int64_t Nel, const int32_t *desc, const double *sig, const double *eps,
-                               const double *epl, double *partial, unsigned int *counter, double *out, int64_t *launches)
+                               const double *epl, double *partial, unsigned int *counter, double *out, int64_t *launches,
+                               int64_t e_first)
 {
     unsigned grid = vec_grid(Nel, lc.sm_count);
-    global_sums_kernel<<<grid, 256, 0, lc.stream>>>(Nel, desc, sig, eps, epl, partial, counter, out);
+    global_sums_kernel<<<grid, 256, 0, lc.stream>>>(Nel, desc, sig, eps, epl, partial, counter, out, e_first);
     (*launches)++;
     return cudaGetLastError();
 }
@@ -852,33 +884,37 @@ cudaError_t launch_global_sums(const LaunchCtx &lc, int64_t Nel, const int32_t *
 cudaError_t launch_scf(const LaunchCtx &lc, const DevMat *hmats, int nmat, int64_t Nel, int NY, const int32_t *desc, const double *sig,
                        const double *epl, const double *du, const double *elstiff, const double *d_sld, double *hval,
                        unsigned char *mult, double *partial, unsigned int *counter, double *d_out /*>= 4 doubles*/,
-                       double *h_out /*pinned*/, double *scf, int64_t *launches)
+                       double *h_out /*pinned*/, double *scf, int64_t *launches, int64_t e_first, Comm *comm)
 {
     scf_elements_kernel<<<(unsigned)((Nel + 127) / 128), 128, 0, lc.stream>>>(Nel, NY, desc, sig, epl, du, elstiff, hval, mult);
     (*launches)++;
     for (int i = 0; i < nmat; i++) {
         if (hmats[i].kind != PLF_MAT_SVC) continue;
         int blocks = lc.sm_count * 2;
-        int64_t need = (Nel + 7) / 8;
+        int64_t need = (Nel + SVCW - 1) / SVCW;
         if (blocks > need) blocks = (int)need;
         cudaFuncSetAttribute(scf_svc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-        scf_svc_kernel<<<blocks, 256, sizeof(double) * 7 * (size_t)hmats[i].nsv_pad, lc.stream>>>(Nel, NY, i, desc, sig, epl, du, elstiff,
+        scf_svc_kernel<<<blocks, SVCW * 32, sizeof(double) * 7 * (size_t)hmats[i].nsv_pad, lc.stream>>>(Nel, NY, i, desc, sig, epl, du, elstiff,
                                                                                                   d_sld, hval, mult);
         (*launches)++;
     }
     unsigned grid = vec_grid(Nel, lc.sm_count);
     const double two = 2.;
     cudaMemcpyAsync(d_out + 3, &two, sizeof(double), cudaMemcpyHostToDevice, lc.stream);   // min accumulator
-    scf_moments_kernel<<<grid, 256, 0, lc.stream>>>(Nel, hval, mult, 0., 0, partial, counter, d_out, d_out + 3);
+    scf_moments_kernel<<<grid, 256, 0, lc.stream>>>(Nel, hval, mult, 0., 0, partial, counter, d_out, d_out + 3, e_first);
     (*launches)++;
+    if (comm) {   // count and sum over all ranks, minimum over all ranks: every rank then derives the same factor
+        if (comm_allreduce_op(*comm, d_out, 2, 0, lc.stream) || comm_allreduce_op(*comm, d_out + 3, 1, 2, lc.stream)) return cudaErrorUnknown;
+    }
     cudaError_t e = cudaMemcpyAsync(h_out, d_out, 4 * sizeof(double), cudaMemcpyDeviceToHost, lc.stream);
     if (e != cudaSuccess) return e;
     if ((e = cudaStreamSynchronize(lc.stream)) != cudaSuccess) return e;
     const double cnt = h_out[0], sum = h_out[1], mn = h_out[3];
     if (cnt == 0.) { *scf = 1.; return cudaSuccess; }   // sc_list = [1.] (1056): std = 0 -> min = 1
     const double mean = sum / cnt;
-    scf_moments_kernel<<<grid, 256, 0, lc.stream>>>(Nel, hval, mult, mean, 1, partial, counter, d_out, d_out + 3);
+    scf_moments_kernel<<<grid, 256, 0, lc.stream>>>(Nel, hval, mult, mean, 1, partial, counter, d_out, d_out + 3, e_first);
     (*launches)++;
+    if (comm && comm_allreduce_op(*comm, d_out, 1, 0, lc.stream)) return cudaErrorUnknown;
     if ((e = cudaMemcpyAsync(h_out, d_out, sizeof(double), cudaMemcpyDeviceToHost, lc.stream)) != cudaSuccess) return e;
     if ((e = cudaStreamSynchronize(lc.stream)) != cudaSuccess) return e;
     const double sd = sqrt(h_out[0] / cnt);   // np.std (population)
@@ -1044,8 +1080,13 @@ cudaError_t launch_cg(const LaunchCtx &lc, int64_t n, const int32_t *rowptr, con
 cudaError_t launch_cg_dist(const LaunchCtx &lc, Comm &comm, int64_t n, const int32_t *rowptr, const int32_t *col, const double *val,
                            const unsigned char *mask, const double *b, double *x, double *r, double *z, double *p, double *q,
                            double *diag, double *partial, unsigned int *counter, void *d_sc, void *h_sc, double rtol,
-                           int max_iter, int check_every, int *iters, double *relres, int64_t *launches, int warm, int NX, int NY)
+                           int max_iter, int check_every, int *iters, double *relres, int64_t *launches, int warm, int NX, int NY,
+                           MgHierarchy *mg, int mg_setup_needed)
 {
+    // mg != nullptr: the preconditioner is this rank's own V-cycle on its strip with the ghost columns masked like
+    // Dirichlet dofs -- a non-overlapping additive Schwarz method whose subdomain solves are multigrid cycles: symmetric
+    // positive definite, no communication inside the preconditioner, and far fewer iterations than Jacobi (the count grows
+    // mildly with the number of strips).  Per iteration: one halo column per neighbour and two all-reduces (p.q; r.z and r.r).
     CgScalars *sc = (CgScalars *)d_sc;
     CgScalars *hs = (CgScalars *)h_sc;
     const unsigned vg = vec_grid(n, lc.sm_count);
@@ -1079,20 +1120,43 @@ cudaError_t launch_cg_dist(const LaunchCtx &lc, Comm &comm, int64_t n, const int
         *relres = sqrt(hs->rr / bb);
         return cudaSuccess;
     }
+    if (mg) {
+        if (mg_setup_needed && (e = mg_setup(lc, *mg, val, mask, launches)) != cudaSuccess) return e;
+        if ((e = mg_vcycle(lc, *mg, r, z, launches)) != cudaSuccess) return e;
+        cg_rz_kernel<0, true><<<vg, 256, 0, lc.stream>>>(n, r, z, mask, sc, partial, counter);
+        PLF_NC(comm_allreduce_sum(comm, sc->tmp, 1, lc.stream));
+        cg_publish_init_kernel<<<1, 1, 0, lc.stream>>>(sc);
+        *launches += 2;
+        if ((e = cudaMemcpyAsync(p, z, (size_t)n * sizeof(double), cudaMemcpyDeviceToDevice, lc.stream)) != cudaSuccess) return e;
+    }
     int it = 0;
     while (it < max_iter) {
         for (int c = 0; c < check_every; c += 2) {
             PLF_NC(comm_halo_exchange(comm, p, NX, NY, lc.stream));
             stencil_spmv_dot_kernel<<<vg, 256, 0, lc.stream>>>(NX, NY, val, p, q, mask, partial, counter, &sc->pq);
             PLF_NC(comm_allreduce_sum(comm, &sc->pq, 1, lc.stream));
-            cg_update_kernel<0, false, true><<<vg, 256, 0, lc.stream>>>(n, x, r, z, p, q, diag, mask, sc, partial, counter);
+            if (mg) {
+                cg_update_kernel<0, true, true><<<vg, 256, 0, lc.stream>>>(n, x, r, z, p, q, diag, mask, sc, partial, counter);
+                if ((e = mg_vcycle(lc, *mg, r, z, launches)) != cudaSuccess) return e;
+                cg_rz_kernel<1, true><<<vg, 256, 0, lc.stream>>>(n, r, z, mask, sc, partial, counter);
+                (*launches)++;
+            } else {
+                cg_update_kernel<0, false, true><<<vg, 256, 0, lc.stream>>>(n, x, r, z, p, q, diag, mask, sc, partial, counter);
+            }
             PLF_NC(comm_allreduce_sum(comm, sc->tmp, 2, lc.stream));
             cg_publish_kernel<0><<<1, 1, 0, lc.stream>>>(sc);
             cg_p_kernel<0><<<vg, 256, 0, lc.stream>>>(n, p, z, sc);
             PLF_NC(comm_halo_exchange(comm, p, NX, NY, lc.stream));
             stencil_spmv_dot_kernel<<<vg, 256, 0, lc.stream>>>(NX, NY, val, p, q, mask, partial, counter, &sc->pq);
             PLF_NC(comm_allreduce_sum(comm, &sc->pq, 1, lc.stream));
-            cg_update_kernel<1, false, true><<<vg, 256, 0, lc.stream>>>(n, x, r, z, p, q, diag, mask, sc, partial, counter);
+            if (mg) {
+                cg_update_kernel<1, true, true><<<vg, 256, 0, lc.stream>>>(n, x, r, z, p, q, diag, mask, sc, partial, counter);
+                if ((e = mg_vcycle(lc, *mg, r, z, launches)) != cudaSuccess) return e;
+                cg_rz_kernel<0, true><<<vg, 256, 0, lc.stream>>>(n, r, z, mask, sc, partial, counter);
+                (*launches)++;
+            } else {
+                cg_update_kernel<1, false, true><<<vg, 256, 0, lc.stream>>>(n, x, r, z, p, q, diag, mask, sc, partial, counter);
+            }
             PLF_NC(comm_allreduce_sum(comm, sc->tmp, 2, lc.stream));
             cg_publish_kernel<1><<<1, 1, 0, lc.stream>>>(sc);
             cg_p_kernel<1><<<vg, 256, 0, lc.stream>>>(n, p, z, sc);

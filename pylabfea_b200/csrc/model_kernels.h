@@ -36,17 +36,18 @@ cudaError_t modelk_upload_geom(const GeomClass *h, int n, cudaStream_t st);
 cudaError_t launch_sweep(const LaunchCtx &lc, const DevMat *hmats, int nmat, int64_t Nel, int NY, int nit, const int32_t *desc,
                          const double *sig, const double *epl, const double *du, double *elstiff, double *res_sig,
                          double *res_depl, double *fyld, int32_t *nsteps, unsigned char *has_res, int32_t *worklist,
-                         void *d_stats, void *h_stats, int compact, int64_t *launches);
+                         void *d_stats, void *h_stats, int compact, int64_t *launches, int64_t stat_first = 0);
 cudaError_t launch_commit(const LaunchCtx &lc, int64_t Nel, int64_t Ndof, int NY, const int32_t *desc, double *u, const double *du,
                           double *f, const int32_t *rowptr, const int32_t *col, const double *val, const double *elstiff,
                           double *sig, double *eps, double *epl, const double *res_sig, const double *res_depl,
                           const unsigned char *has_res, int64_t *launches);
 cudaError_t launch_global_sums(const LaunchCtx &lc, int64_t Nel, const int32_t *desc, const double *sig, const double *eps,
-                               const double *epl, double *partial, unsigned int *counter, double *out, int64_t *launches);
+                               const double *epl, double *partial, unsigned int *counter, double *out, int64_t *launches,
+                               int64_t e_first = 0);
 cudaError_t launch_scf(const LaunchCtx &lc, const DevMat *hmats, int nmat, int64_t Nel, int NY, const int32_t *desc, const double *sig,
                        const double *epl, const double *du, const double *elstiff, const double *d_sld, double *hval,
                        unsigned char *mult, double *partial, unsigned int *counter, double *d_out, double *h_out, double *scf,
-                       int64_t *launches);
+                       int64_t *launches, int64_t e_first = 0, Comm *comm = nullptr);
 cudaError_t launch_cg(const LaunchCtx &lc, int64_t n, const int32_t *rowptr, const int32_t *col, const double *val,
                       const unsigned char *fixed, const double *b, double *x, double *r, double *z, double *p, double *q,
                       double *diag, double *partial, unsigned int *counter, void *d_sc, void *h_sc, double rtol, int max_iter,
@@ -60,7 +61,8 @@ void cg_graph_reset(CgGraphCache &g);   // drops the cached graph (call before f
 cudaError_t launch_cg_dist(const LaunchCtx &lc, Comm &comm, int64_t n, const int32_t *rowptr, const int32_t *col, const double *val,
                            const unsigned char *mask, const double *b, double *x, double *r, double *z, double *p, double *q,
                            double *diag, double *partial, unsigned int *counter, void *d_sc, void *h_sc, double rtol,
-                           int max_iter, int check_every, int *iters, double *relres, int64_t *launches, int warm, int NX, int NY);
+                           int max_iter, int check_every, int *iters, double *relres, int64_t *launches, int warm, int NX, int NY,
+                           MgHierarchy *mg = nullptr /* local V-cycle as preconditioner; nullptr: Jacobi */, int mg_setup_needed = 1);
 cudaError_t launch_ghost_mask(const LaunchCtx &lc, int64_t n, int NY, int own_first, int own_end, const unsigned char *fixed,
                               unsigned char *mask, int64_t *launches);
 cudaError_t launch_merge_du(const LaunchCtx &lc, int64_t n, const double *x, const double *du_bc, const unsigned char *fixed, double *du,

@@ -131,6 +131,8 @@ static void free_batch_bufs(plf_batch &b)
 {
     cudaFree(b.mat_id); cudaFree(b.sig); cudaFree(b.epl); cudaFree(b.deps); cudaFree(b.fy); cudaFree(b.sig_out);
     cudaFree(b.depl); cudaFree(b.ctan); cudaFree(b.nsteps); cudaFree(b.worklist);
+    cudaFree(b.ct21); cudaFree(b.el_words); cudaFree(b.pk_counts); cudaFree(b.pk_offsets); cudaFree(b.pk_totals);
+    if (b.h_pk_totals) cudaFreeHost(b.h_pk_totals);
     b = plf_batch();
 }
 
@@ -318,11 +320,12 @@ extern "C" int plf_set_materials(plf_ctx *ctx, int nmat, const plf_material *mat
         memcpy(d.bar_m1, m.barlat_m1, sizeof d.bar_m1);
         memcpy(d.bar_m2, m.barlat_m2, sizeof d.bar_m2);
         d.bar_exp = m.barlat_exp;
+        d.bar_exp_int = (m.barlat_exp >= 2. && m.barlat_exp <= 64. && m.barlat_exp == std::floor(m.barlat_exp)) ? (int)m.barlat_exp : 0;
         if (m.kind == PLF_MAT_SVC || m.kind == PLF_MAT_SVC3) {
             if (m.nsv < 1 || !m.svc_sv || !m.svc_dual) return fail(ctx, PLF_EINVAL, "plf_set_materials: SVC table missing");
-            const int np = (m.nsv + 31) / 32 * 32;
+            const int np = (m.nsv + 63) / 64 * 64;   // two support vectors per lane and loop trip (SvcModel::decision_x)
             if ((size_t)np * 7 * sizeof(double) > 227 * 1024)
-                return fail(ctx, PLF_EUNSUPPORTED, "plf_set_materials: SVC table exceeds 227 KB of shared memory (nsv <= 4128)");
+                return fail(ctx, PLF_EUNSUPPORTED, "plf_set_materials: SVC table exceeds 227 KB of shared memory (nsv <= 4096)");
             d.nsv = m.nsv; d.nsv_pad = np;
             d.gamma = m.svc_gamma; d.rho = m.svc_rho; d.scale_seq = m.svc_scale_seq; d.inv_scale_seq = 1. / m.svc_scale_seq;
             d.khard = 0.;   // material.py:812-814: the SVC gradient resets khard (no work-hardening features)
@@ -399,6 +402,11 @@ extern "C" int plf_batch_upload(plf_ctx *ctx, plf_batch *b, const int32_t *mat_i
 {
     if (!ctx || !b || !sig || !epl || !deps) return PLF_EINVAL;
     const size_t N = (size_t)b->n;
+    b->mat_from_mesh = false;
+    if (mat_id) {
+        for (size_t e = 0; e < N; e++)
+            if (mat_id[e] < 0 || mat_id[e] >= std::max(ctx->nmat, 1)) return fail(ctx, PLF_EINVAL, "plf_batch_upload: material id out of range");
+    }
     if (mat_id) CK(cudaMemcpyAsync(b->mat_id, mat_id, N * sizeof(int32_t), cudaMemcpyHostToDevice, ctx->stream));
     else CK(cudaMemsetAsync(b->mat_id, 0, N * sizeof(int32_t), ctx->stream));
     CK(cudaMemcpyAsync(b->sig, sig, 6 * N * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
@@ -443,16 +451,18 @@ extern "C" int plf_set_option(plf_ctx *ctx, const char *key, int value)
     if (!strcmp(key, "compact")) { ctx->compact = value; return PLF_OK; }
     if (!strcmp(key, "assembly_tiled")) { ctx->assembly_tiled = value; return PLF_OK; }
     if (!strcmp(key, "passa_direct")) { ctx->passa_direct = value; return PLF_OK; }
+    if (!strcmp(key, "passa_bulk")) { ctx->passa_bulk = value; return PLF_OK; }
     if (!strcmp(key, "max_fm")) { ctx->max_fm = value; return PLF_OK; }
     if (!strcmp(key, "k1_only")) { ctx->k1_only = value; return PLF_OK; }
     if (!strcmp(key, "passb_recur")) { ctx->passb_recur = value; return PLF_OK; }
     if (!strcmp(key, "solver_mg")) { ctx->solver_mg = value; return PLF_OK; }
     if (!strcmp(key, "solver_warm")) { ctx->solver_warm = value; return PLF_OK; }
     if (!strcmp(key, "skip_unchanged")) { ctx->skip_unchanged = value; return PLF_OK; }
-    if (!strcmp(key, "mg_nu") || !strcmp(key, "mg_coarse_sweeps") || !strcmp(key, "mg_omega_permille")) {
+    if (!strcmp(key, "mg_nu") || !strcmp(key, "mg_coarse_sweeps") || !strcmp(key, "mg_omega_permille") || !strcmp(key, "mg_fuse_tail")) {
         // multigrid tuning knobs (take effect at the next plf_mesh_structured / solve; the CG graph is rebuilt)
         if (!strcmp(key, "mg_nu")) ctx->mg_nu = value & ~1;
         else if (!strcmp(key, "mg_coarse_sweeps")) ctx->mg_coarse_sweeps = value;
+        else if (!strcmp(key, "mg_fuse_tail")) ctx->mg_fuse_tail = value;
         else ctx->mg_omega = value * 1e-3;
         model_apply_mg_options(ctx);
         return PLF_OK;

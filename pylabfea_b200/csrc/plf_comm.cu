@@ -1,6 +1,5 @@
 // plf_comm.cu -- NCCL plumbing of the strip-partitioned solve and its C-ABI entry points (include/plfb200.h).
 #include <dlfcn.h>
-#include <nccl.h>
 
 #include <cstring>
 #include <string>
@@ -8,6 +7,16 @@
 #include "plf_comm.h"
 #include "plf_model.h"
 #include "plfb200.h"
+
+// The few NCCL declarations this file needs, stated locally (NCCL 2.x ABI): the library is loaded with dlopen at run time,
+// and with <nccl.h> the dev headers would be a hard build-time dependency of every single-GPU user of libplfb200.so.
+extern "C" {
+typedef struct ncclComm *ncclComm_t;
+typedef struct { char internal[128]; } ncclUniqueId;
+typedef enum { ncclSuccess = 0 } ncclResult_t;
+typedef enum { ncclSum = 0, ncclProd = 1, ncclMax = 2, ncclMin = 3 } ncclRedOp_t;
+typedef enum { ncclDouble = 8 } ncclDataType_t;   // ncclFloat64
+}
 
 namespace plf {
 
@@ -102,6 +111,13 @@ int comm_allreduce_sum(Comm &c, double *dbuf, int count, cudaStream_t s)
     return 0;
 }
 
+int comm_allreduce_op(Comm &c, double *dbuf, int count, int op, cudaStream_t s)
+{
+    const ncclRedOp_t o = op == 1 ? ncclMax : (op == 2 ? ncclMin : ncclSum);
+    NC(g_nccl.AllReduce(dbuf, dbuf, (size_t)count, ncclDouble, o, (ncclComm_t)c.nccl, s), "ncclAllReduce");
+    return 0;
+}
+
 int comm_halo_exchange(Comm &c, double *vec, int NX, int NY, cudaStream_t s)
 {
     const bool left = c.ghost_left() && c.rank > 0, right = c.ghost_right(NX) && c.rank + 1 < c.world;
@@ -162,6 +178,35 @@ extern "C" int plf_comm_set_strip(plf_ctx *ctx, int own_first, int own_end)
     ctx->comm->own_first = own_first;
     ctx->comm->own_end = own_end;
     ctx->comm->strip_set = true;
+    return PLF_OK;
+}
+
+extern "C" int plf_comm_set_partition(plf_ctx *ctx, int own_first, int own_end, int first_col_global, int NX_global, double x_offset,
+                                      double lenx_global)
+{
+    int rc = plf_comm_set_strip(ctx, own_first, own_end);
+    if (rc != PLF_OK) return rc;
+    if (first_col_global < 0 || first_col_global + ctx->NX > NX_global || !(lenx_global > 0.))
+        return fail(ctx, PLF_EINVAL, "plf_comm_set_partition: the local mesh must lie inside the global one");
+    Comm &c = *ctx->comm;
+    c.first_col_global = first_col_global;
+    c.NX_global = NX_global;
+    c.x_offset = x_offset;
+    c.lenx_global = lenx_global;
+    c.global_set = true;
+    return PLF_OK;
+}
+
+// host values combined over the ranks: op 0 sum, 1 max, 2 min
+int comm_host_allreduce(plf_ctx *ctx, double *vals, int n, int op)
+{
+    if (!ctx->comm || !ctx->comm->active()) return PLF_OK;
+    if (n < 1 || n > 64) return fail(ctx, PLF_EINVAL, "comm_host_allreduce: 1 <= n <= 64 values");
+    double *d = reinterpret_cast<double *>(ctx->d_scalars + 1024);
+    CKC(cudaMemcpyAsync(d, vals, n * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    if (comm_allreduce_op(*ctx->comm, d, n, op, ctx->stream)) return fail(ctx, PLF_ECUDA, std::string("allreduce: ") + comm_error());
+    CKC(cudaMemcpyAsync(vals, d, n * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    CKC(cudaStreamSynchronize(ctx->stream));
     return PLF_OK;
 }
 

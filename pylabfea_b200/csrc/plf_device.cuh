@@ -31,6 +31,8 @@ struct DevMat {
     const double *sv;    // device, SoA [6][nsv_pad]
     const double *dual;  // device, [nsv_pad] (zero padded)
     double bar_m1[36], bar_m2[36], bar_exp;
+    int32_t bar_exp_int;   // barlat_exp when it is a whole number in [2, 64] (Yld2004-18p: 6 for bcc, 8 for fcc), else 0
+    int32_t pad2_;
 };
 
 // symmetric 6x6 packing: (i<=j) -> index
@@ -120,6 +122,28 @@ __device__ __forceinline__ double j2_seq(const double *s)
     return sqrt(0.5 * I2);
 }
 
+// |d|^n for a whole exponent by binary powering (a handful of multiplications instead of a ~150-instruction pow())
+__device__ __forceinline__ double powi_abs(double ad, int n)
+{
+    double r = 1., b = ad;
+    while (n) {
+        if (n & 1) r *= b;
+        b *= b;
+        n >>= 1;
+    }
+    return r;
+}
+
+// x^(1/n), x >= 0: square roots when n is a power of two (n = 8: three of them)
+__device__ __forceinline__ double root_n(double x, int n, double a)
+{
+    if (n > 0 && (n & (n - 1)) == 0) {
+        while (n > 1) { x = sqrt(x); n >>= 1; }
+        return x;
+    }
+    return pow(x, 1. / a);
+}
+
 static __device__ __noinline__ double barlat_seq(const DevMat &m, const double *sv)
 {
     // material.py:678-702
@@ -131,6 +155,14 @@ static __device__ __noinline__ double barlat_seq(const DevMat &m, const double *
     sym3_eig(st1, p1);
     sym3_eig(st2, p2);
     double s = 0.;
+    const int n = m.bar_exp_int;
+    if (n) {
+#pragma unroll
+        for (int i = 0; i < 3; i++)
+#pragma unroll
+            for (int j = 0; j < 3; j++) s += powi_abs(fabs(p1[i] - p2[j]), n);
+        return root_n(0.25 * s, n, m.bar_exp);
+    }
 #pragma unroll
     for (int i = 0; i < 3; i++)
 #pragma unroll
@@ -191,13 +223,13 @@ static __device__ __noinline__ double barlat_seq_grad(const DevMat &m, const dou
     for (int i = 0; i < 3; i++)
         for (int j = 0; j < 3; j++) {
             const double d = p1[i] - p2[j], ad = fabs(d);
-            const double pw = pow(ad, a - 1.);
+            const double pw = m.bar_exp_int ? powi_abs(ad, m.bar_exp_int - 1) : pow(ad, a - 1.);
             phi += pw * ad;
             const double sg = copysign(pw, d);   // |d|^(a-1) sign(d)
             g1[i] += sg;
             g2[j] -= sg;
         }
-    const double seq = pow(0.25 * phi, 1. / a);
+    const double seq = m.bar_exp_int ? root_n(0.25 * phi, m.bar_exp_int, a) : pow(0.25 * phi, 1. / a);
     double E1[6] = {0., 0., 0., 0., 0., 0.}, E2[6] = {0., 0., 0., 0., 0., 0.};
     for (int e = 0; e < 3; e++) {
         const double x = V1[0][e], y = V1[1][e], z = V1[2][e];
@@ -421,18 +453,22 @@ struct SvcModel {
     // decision_function (material.py:405): sum_i dual_i exp(-gamma |x - sv_i|^2) + rho
     __device__ __forceinline__ double decision_x(const double *x) const
     {
+        // two support vectors per lane and trip (nsv_pad is a multiple of 64): two independent distance / exp / fma chains
+        // keep the FP64 pipe busy at 4 warps per scheduler (ncu of the one-chain loop at 2 warps: 15 % of the pipe, "wait")
         const int np = m.nsv_pad;
-        double f = 0.;
-        for (int i = lane; i < np; i += 32) {
-            double r = 0.;
+        double f0 = 0., f1 = 0.;
+        for (int i = lane; i < np; i += 64) {
+            double r0 = 0., r1 = 0.;
 #pragma unroll
             for (int k = 0; k < 6; k++) {
-                double t = x[k] - s_sv[k * np + i];
-                r = fma(t, t, r);
+                const double t0 = x[k] - s_sv[k * np + i], t1 = x[k] - s_sv[k * np + i + 32];
+                r0 = fma(t0, t0, r0);
+                r1 = fma(t1, t1, r1);
             }
-            f = fma(s_dual[i], exp(-m.gamma * r), f);
+            f0 = fma(s_dual[i], exp(-m.gamma * r0), f0);
+            f1 = fma(s_dual[i + 32], exp(-m.gamma * r1), f1);
         }
-        return warp_sum(f) + m.rho;
+        return warp_sum(f0 + f1) + m.rho;
     }
     __device__ __forceinline__ double yf(const double *s, double /*sflow*/) const
     {

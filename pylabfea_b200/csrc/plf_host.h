@@ -27,6 +27,7 @@ struct LaunchCtx {
     int max_fm = 4;        // cap of the single-material fast mode (hill_fast.cuh)
     int k1_only = 0;       // diagnostics: 1 = launch pass A only
     int passb_recur = 1;   // 1: planar isotropic J2 loop of pass B with scalar recurrences on the carried chain (hill_fast.cuh)
+    int passa_bulk = 0;      // 1: pass A moves its records with cp.async.bulk (TMA engine: measured 6 % slower), 0: cp.async ring + staged stores
     int assembly_tiled = 2;  // 2: row per thread with staged coalesced stores (production); 0: direct stores
 };
 
@@ -37,6 +38,9 @@ cudaError_t launch_response(const LaunchCtx &lc, const DevMat *hmats, int nmat, 
                             const double *sig, const double *epl, const double *deps, double *fy, double *sig_out,
                             double *depl, double *ctan, int32_t *nsteps, int32_t *worklist, unsigned int *work_count,
                             unsigned long long *queue, int compact, int64_t *launches);
+// compact results for the host: elastic bit per element (words), upper triangles of the other tangents in element order
+cudaError_t launch_pack(const LaunchCtx &lc, int64_t n, const int32_t *mat_id, int single, const double *ctan, uint32_t *words,
+                        int32_t *block_counts, int32_t *block_offsets, int64_t *total, double *ct21, int64_t *launches);
 cudaError_t launch_prim(const LaunchCtx &lc, const DevMat *hmats, int op, int mid, int64_t n, const double *sig,
                         const double *epl, const double *deps, const double *ld, double *out, int64_t *launches);
 

@@ -39,6 +39,7 @@ void model_apply_mg_options(plf_ctx *ctx)
     ctx->mg->nu = std::max(2, ctx->mg_nu);
     ctx->mg->coarse_sweeps = std::max(1, ctx->mg_coarse_sweeps);
     ctx->mg->omega = ctx->mg_omega;
+    ctx->mg->fuse_tail = ctx->mg_fuse_tail;
     cg_graph_reset(ctx->cg_graph);   // the captured V-cycle has the old sweep counts baked in
 }
 
@@ -292,6 +293,22 @@ extern "C" int plf_setupK_from_batch(plf_ctx *ctx, const plf_batch *b)
     return PLF_OK;
 }
 
+// material ids of the mesh elements (descriptor low half) into the batch, once: plf_step_host on mixed meshes
+static int batch_materials_from_mesh(plf_ctx *ctx, plf_batch *b)
+{
+    if (b->mat_from_mesh) return PLF_OK;
+    if (ctx->nmat == 1) {
+        CK(cudaMemsetAsync(b->mat_id, 0, (size_t)b->n * sizeof(int32_t), ctx->stream));
+    } else {
+        std::vector<int32_t> ids((size_t)b->n);
+        for (size_t e = 0; e < ids.size(); e++) ids[e] = ctx->h_desc[e] & 0xffff;
+        CK(cudaMemcpyAsync(b->mat_id, ids.data(), ids.size() * sizeof(int32_t), cudaMemcpyHostToDevice, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+    }
+    b->mat_from_mesh = true;
+    return PLF_OK;
+}
+
 // One inner pass of the load-step loop with HOST buffers (model.py:1338-1361 + setupK): element states in, response
 // results and CSR(K) values out.  The mesh is cut into chunks of element columns; chunk c is uploaded on one copy
 // stream while chunk c-1 is updated and its node columns are assembled on the compute stream and chunk c-2 drains
@@ -320,9 +337,10 @@ extern "C" int plf_step_host(plf_ctx *ctx, plf_batch *b, const double *sig, cons
     CK(cudaEventRecord(ctx->ev_step[2 * nchunk], ctx->stream));
     CK(cudaStreamWaitEvent(ctx->s_in, ctx->ev_step[2 * nchunk], 0));
     CK(cudaStreamWaitEvent(ctx->s_out, ctx->ev_step[2 * nchunk], 0));
-    CK(cudaMemsetAsync(b->mat_id, 0, (size_t)b->n * sizeof(int32_t), ctx->stream));
-    if (ctx->nmat > 1)   // material ids of the mesh elements (descriptor low half)
-        return fail(ctx, PLF_EUNSUPPORTED, "plf_step_host: single-material meshes only (use plf_sweep for mixed meshes)");
+    {
+        int rcm = batch_materials_from_mesh(ctx, b);
+        if (rcm != PLF_OK) return rcm;
+    }
     LaunchCtx lc = make_lc(ctx);
     for (int c = 0; c < nchunk; c++) {
         const int ja = (int)((int64_t)NX * c / nchunk), jb = (int)((int64_t)NX * (c + 1) / nchunk);   // element columns
@@ -357,6 +375,117 @@ extern "C" int plf_step_host(plf_ctx *ctx, plf_batch *b, const double *sig, cons
     ctx->K_ready = true;
     ctx->K_tangent_epoch = 0;
     ctx->K_serial++;
+    CK(cudaStreamSynchronize(ctx->s_out));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return PLF_OK;
+}
+
+// plf_step_host with compact results (include/plfb200.h).  Same three-stream pipeline over chunks of element columns; all
+// uploads and all kernel work are enqueued first, then the host follows the chunks as they finish: the number of packed
+// tangents of a chunk (device-side scan) decides the size of its download.
+extern "C" int plf_step_host_packed(plf_ctx *ctx, plf_batch *b, const double *sig, const double *epl, const double *deps, double *fy,
+                                    double *sig_out, double *depl, int32_t *nsteps, double *ct21, uint32_t *elastic_words,
+                                    int64_t *n_packed, double *kval)
+{
+    NEED_MESH("plf_step_host_packed");
+    if (!b || b->n != ctx->Nel || !sig || !epl || !deps || !ct21 || !elastic_words || !n_packed)
+        return fail(ctx, PLF_EINVAL, "plf_step_host_packed: batch must hold exactly Nel elements; sig, epl, deps, ct21, elastic_words, "
+                                     "n_packed are required");
+    if (ctx->nmat == 0) return fail(ctx, PLF_ESTATE, "plf_step_host_packed: no materials set");
+    CK(cudaSetDevice(ctx->device));
+    if (!ctx->s_in) {
+        CK(cudaStreamCreateWithFlags(&ctx->s_in, cudaStreamNonBlocking));
+        CK(cudaStreamCreateWithFlags(&ctx->s_out, cudaStreamNonBlocking));
+    }
+    const int NX = ctx->NX, NY = ctx->NY;
+    const int nchunk = std::max(1, std::min(NX, 8));
+    while ((int)ctx->ev_step.size() < 2 * nchunk + 1) {
+        cudaEvent_t e;
+        CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        ctx->ev_step.push_back(e);
+    }
+    const size_t N = (size_t)b->n;
+    if (!b->ct21) {
+        const size_t nblk = (N + 255) / 256 + 8;
+        CK(cudaMalloc((void **)&b->ct21, 21 * N * sizeof(double)));
+        CK(cudaMalloc((void **)&b->el_words, ((N + 31) / 32 + 8) * sizeof(uint32_t)));
+        CK(cudaMalloc((void **)&b->pk_counts, nblk * sizeof(int32_t)));
+        CK(cudaMalloc((void **)&b->pk_offsets, nblk * sizeof(int32_t)));
+        CK(cudaMalloc((void **)&b->pk_totals, 64 * sizeof(int64_t)));
+        CK(cudaMallocHost((void **)&b->h_pk_totals, 64 * sizeof(int64_t)));
+    }
+    CK(cudaEventRecord(ctx->ev_step[2 * nchunk], ctx->stream));
+    CK(cudaStreamWaitEvent(ctx->s_in, ctx->ev_step[2 * nchunk], 0));
+    CK(cudaStreamWaitEvent(ctx->s_out, ctx->ev_step[2 * nchunk], 0));
+    int rc = batch_materials_from_mesh(ctx, b);
+    if (rc != PLF_OK) return rc;
+    LaunchCtx lc = make_lc(ctx);
+    struct Chunk { int ja, jb, na, nb; int64_t e0, ne; };
+    std::vector<Chunk> ch(nchunk);
+    for (int c = 0; c < nchunk; c++) {
+        Chunk &k = ch[c];
+        k.ja = (int)((int64_t)NX * c / nchunk);
+        k.jb = (int)((int64_t)NX * (c + 1) / nchunk);
+        k.e0 = (int64_t)k.ja * NY;
+        k.ne = (int64_t)(k.jb - k.ja) * NY;
+        k.na = k.ja;
+        k.nb = (c == nchunk - 1) ? NX + 1 : k.jb;
+    }
+    // chunk boundaries must fall on bitmap words and on blocks of the pack kernels: the chunk-local compaction writes whole
+    // 32-bit words; elements are numbered column by column, so a chunk starts at a multiple of NY
+    for (int c = 0; c < nchunk; c++)
+        if (ch[c].e0 % 32 != 0) return fail(ctx, PLF_EUNSUPPORTED, "plf_step_host_packed: NY * (NX / 8) must be a multiple of 32");
+    for (int c = 0; c < nchunk; c++) {   // all uploads
+        const Chunk &k = ch[c];
+        const size_t o6 = 6 * (size_t)k.e0, n6 = 6 * (size_t)k.ne * sizeof(double);
+        CK(cudaMemcpyAsync(b->sig + o6, sig + o6, n6, cudaMemcpyHostToDevice, ctx->s_in));
+        CK(cudaMemcpyAsync(b->epl + o6, epl + o6, n6, cudaMemcpyHostToDevice, ctx->s_in));
+        CK(cudaMemcpyAsync(b->deps + o6, deps + o6, n6, cudaMemcpyHostToDevice, ctx->s_in));
+        CK(cudaEventRecord(ctx->ev_step[2 * c], ctx->s_in));
+    }
+    const bool single = ctx->nmat == 1;
+    for (int c = 0; c < nchunk; c++) {   // all kernel work
+        const Chunk &k = ch[c];
+        const size_t o6 = 6 * (size_t)k.e0;
+        CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_step[2 * c], 0));
+        CK(launch_response(lc, ctx->hmats, ctx->nmat, k.ne, b->mat_id + k.e0, b->sig + o6, b->epl + o6, b->deps + o6, b->fy + k.e0,
+                           b->sig_out + o6, b->depl + o6, b->ctan + 36 * (size_t)k.e0, b->nsteps + k.e0, b->worklist + k.e0,
+                           (unsigned int *)(ctx->d_scalars + 16), (unsigned long long *)(ctx->d_scalars + 8), ctx->compact,
+                           &ctx->launches));
+        CK(launch_pack(lc, k.ne, b->mat_id + k.e0, single ? 1 : 0, b->ctan + 36 * (size_t)k.e0, b->el_words + (k.e0 >> 5),
+                       b->pk_counts + (k.e0 >> 8) + c, b->pk_offsets + (k.e0 >> 8) + c, b->pk_totals + c, b->ct21 + 21 * (size_t)k.e0,
+                       &ctx->launches));
+        CK(cudaMemcpyAsync(b->h_pk_totals + c, b->pk_totals + c, sizeof(int64_t), cudaMemcpyDeviceToHost, ctx->stream));
+        CK(launch_assemble_columns(lc, NX, NY, ctx->planestress, ctx->ngeom, k.na, k.nb, ctx->d_desc, b->ctan, ctx->d_val,
+                                   &ctx->launches));
+        CK(cudaEventRecord(ctx->ev_step[2 * c + 1], ctx->stream));
+    }
+    ctx->K_ready = true;
+    ctx->K_tangent_epoch = 0;
+    ctx->K_serial++;
+    int64_t packed = 0;
+    for (int c = 0; c < nchunk; c++) {   // downloads, in the order the chunks finish
+        const Chunk &k = ch[c];
+        const size_t o6 = 6 * (size_t)k.e0, n6 = 6 * (size_t)k.ne * sizeof(double);
+        CK(cudaStreamWaitEvent(ctx->s_out, ctx->ev_step[2 * c + 1], 0));
+        if (fy) CK(cudaMemcpyAsync(fy + k.e0, b->fy + k.e0, (size_t)k.ne * sizeof(double), cudaMemcpyDeviceToHost, ctx->s_out));
+        if (nsteps) CK(cudaMemcpyAsync(nsteps + k.e0, b->nsteps + k.e0, (size_t)k.ne * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->s_out));
+        if (sig_out) CK(cudaMemcpyAsync(sig_out + o6, b->sig_out + o6, n6, cudaMemcpyDeviceToHost, ctx->s_out));
+        if (depl) CK(cudaMemcpyAsync(depl + o6, b->depl + o6, n6, cudaMemcpyDeviceToHost, ctx->s_out));
+        CK(cudaMemcpyAsync(elastic_words + (k.e0 >> 5), b->el_words + (k.e0 >> 5), (size_t)((k.ne + 31) / 32) * sizeof(uint32_t),
+                           cudaMemcpyDeviceToHost, ctx->s_out));
+        if (kval) {
+            const int64_t v0 = csr_column_start(NX, NY, k.na), v1 = csr_column_start(NX, NY, k.nb);
+            CK(cudaMemcpyAsync(kval + v0, ctx->d_val + v0, (size_t)(v1 - v0) * sizeof(double), cudaMemcpyDeviceToHost, ctx->s_out));
+        }
+        CK(cudaEventSynchronize(ctx->ev_step[2 * c + 1]));   // the chunk's count is in pinned memory now
+        const int64_t cnt = b->h_pk_totals[c];
+        if (cnt > 0)
+            CK(cudaMemcpyAsync(ct21 + 21 * (size_t)packed, b->ct21 + 21 * (size_t)k.e0, 21 * (size_t)cnt * sizeof(double),
+                               cudaMemcpyDeviceToHost, ctx->s_out));
+        packed += cnt;
+    }
+    *n_packed = packed;
     CK(cudaStreamSynchronize(ctx->s_out));
     CK(cudaStreamSynchronize(ctx->stream));
     return PLF_OK;
@@ -437,6 +566,11 @@ static int ensure_partials(plf_ctx *ctx)
 
 // layout of the 4 KB scalar scratch: [0,256) SweepStats | [256,512) CgScalars | [512,516) reduction counter |
 // [576,1024) small vectors (sld, global sums, scf moments)
+// strip partition with its position in the global mesh set (plf_comm_set_partition): one rank of a distributed Model.solve
+static inline bool is_partitioned(const plf_ctx *ctx) { return ctx->comm && ctx->comm->active() && ctx->comm->global_set; }
+// elements of the halo column (updated here for the K rows of the first owned node column, owned and counted by the left rank)
+static inline int64_t halo_elements(const plf_ctx *ctx) { return is_partitioned(ctx) ? (int64_t)ctx->comm->own_first * ctx->NY : 0; }
+
 static inline unsigned int *counter_ptr(plf_ctx *ctx) { return (unsigned int *)(ctx->d_scalars + 512); }
 
 extern "C" int plf_sweep(plf_ctx *ctx, int nit, int32_t *change, int32_t *conv, double *max_hh, int64_t counts[4])
@@ -449,13 +583,21 @@ extern "C" int plf_sweep(plf_ctx *ctx, int nit, int32_t *change, int32_t *conv, 
     LaunchCtx lc = make_lc(ctx);
     CK(launch_sweep(lc, ctx->hmats, ctx->nmat, ctx->Nel, ctx->NY, nit, ctx->d_desc, ctx->d_sig, ctx->d_epl, ctx->d_du, ctx->d_elstiff,
                     ctx->d_res_sig, ctx->d_res_depl, ctx->d_fyld, ctx->d_nsteps, ctx->d_has_res, ctx->d_worklist, ctx->d_scalars,
-                    ctx->h_scalars, ctx->compact, &ctx->launches));
+                    ctx->h_scalars, ctx->compact, &ctx->launches, halo_elements(ctx)));
     const SweepStats *st = (const SweepStats *)ctx->h_scalars;
-    if (st->change) ctx->tangent_epoch++;
-    if (change) *change = st->change ? 1 : 0;
-    if (conv) *conv = st->nonconv == 0 ? 1 : 0;
-    if (max_hh) *max_hh = st->max_hh;
-    if (counts) for (int i = 0; i < 4; i++) counts[i] = (int64_t)st->counts[i];
+    if (st->change) ctx->tangent_epoch++;   // local tangents (halo column included) changed
+    double v[6] = {st->change ? 1. : 0., (double)st->nonconv, (double)st->counts[0], (double)st->counts[1], (double)st->counts[2],
+                   (double)st->counts[3]};
+    double mh = st->max_hh;
+    if (is_partitioned(ctx)) {   // every rank must take the same decisions (model.py:1305, 1355-1361)
+        int rc = comm_host_allreduce(ctx, v, 6, 0);
+        if (rc == PLF_OK) rc = comm_host_allreduce(ctx, &mh, 1, 1);
+        if (rc != PLF_OK) return rc;
+    }
+    if (change) *change = v[0] > 0. ? 1 : 0;
+    if (conv) *conv = v[1] == 0. ? 1 : 0;
+    if (max_hh) *max_hh = mh;
+    if (counts) for (int i = 0; i < 4; i++) counts[i] = (int64_t)v[2 + i];
     // K_ready stays set: the CSR memory still holds the stiffness the current increment was solved with, which is
     // what plf_commit must use for f += K du (model.py:1384 uses the K assembled before the last sweep).
     return PLF_OK;
@@ -469,6 +611,9 @@ extern "C" int plf_commit(plf_ctx *ctx)
     CK(launch_commit(lc, ctx->Nel, ctx->Ndof, ctx->NY, ctx->d_desc, ctx->d_u, ctx->d_du, ctx->d_f, ctx->d_rowptr, ctx->d_col, ctx->d_val,
                      ctx->d_elstiff, ctx->d_sig, ctx->d_eps, ctx->d_epl, ctx->d_res_sig, ctx->d_res_depl, ctx->d_has_res,
                      &ctx->launches));
+    if (ctx->comm && ctx->comm->active() && ctx->comm->strip_set &&
+        comm_halo_exchange(*ctx->comm, ctx->d_f, ctx->NX, ctx->NY, ctx->stream))   // rows of ghost columns are not complete here
+        return fail(ctx, PLF_ECUDA, std::string("plf_commit: ") + comm_error());
     return PLF_OK;
 }
 
@@ -480,13 +625,18 @@ extern "C" int plf_reduce_global(plf_ctx *ctx, double *sig6, double *eps6, doubl
     LaunchCtx lc = make_lc(ctx);
     double *d_out = (double *)(ctx->d_scalars + 576);
     CK(launch_global_sums(lc, ctx->Nel, ctx->d_desc, ctx->d_sig, ctx->d_eps, ctx->d_epl, ctx->d_partial, counter_ptr(ctx), d_out,
-                          &ctx->launches));
+                          &ctx->launches, halo_elements(ctx)));
     double *h = (double *)(ctx->h_scalars + 576);
     CK(cudaMemcpyAsync(h, d_out, 18 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
     // model.py:1508-1511: divide by the model volume lenx*leny*thick
     double lenx = 0.;
     for (double v : ctx->dx) lenx += v;
+    if (is_partitioned(ctx)) {
+        rc = comm_host_allreduce(ctx, h, 18, 0);
+        if (rc != PLF_OK) return rc;
+        lenx = ctx->comm->lenx_global;
+    }
     const double Vm = lenx * (ctx->dy * ctx->NY) * ctx->thick;
     for (int k = 0; k < 6; k++) {
         if (sig6) sig6[k] = h[k] / Vm;
@@ -509,7 +659,7 @@ extern "C" int plf_calc_scf(plf_ctx *ctx, const double *sld, double *scf)
     // hval / mult reuse the fyld array and the worklist bytes (both are rewritten by the next sweep)
     CK(launch_scf(lc, ctx->hmats, ctx->nmat, ctx->Nel, ctx->NY, ctx->d_desc, ctx->d_sig, ctx->d_epl, ctx->d_du, ctx->d_elstiff, d_sld,
                   ctx->d_fyld, (unsigned char *)ctx->d_worklist, ctx->d_partial, counter_ptr(ctx), d_out,
-                  (double *)(ctx->h_scalars + 640), scf, &ctx->launches));
+                  (double *)(ctx->h_scalars + 640), scf, &ctx->launches, halo_elements(ctx), is_partitioned(ctx) ? ctx->comm : nullptr));
     return PLF_OK;
 }
 
@@ -580,10 +730,13 @@ int model_solve_device_bc(plf_ctx *ctx, double rtol, int max_iter, int *iters, d
     double rr = 0.;
     double *x = ctx->d_du;   // CG iterate lives in du; fixed dofs are merged at the end
     if (dist) {
+        const bool dmg = ctx->solver_mg && ctx->mg && ctx->mg->levels() >= 2;
+        const bool fresh = dmg && ctx->skip_unchanged && ctx->mg_K_serial == ctx->K_serial && ctx->mg_mask_epoch == ctx->mask_epoch;
+        if (dmg) { ctx->mg_K_serial = ctx->K_serial; ctx->mg_mask_epoch = ctx->mask_epoch; }
         cudaError_t ce = launch_cg_dist(lc, *ctx->comm, ctx->Ndof, ctx->d_rowptr, ctx->d_col, ctx->d_val, mask, ctx->d_b, x, ctx->d_r,
                                         ctx->d_z, ctx->d_p, ctx->d_q, ctx->d_diag, ctx->d_partial, counter_ptr(ctx), ctx->d_scalars + 256,
-                                        ctx->h_scalars + 256, rtol, max_iter, 50, &it, &rr, &ctx->launches, ctx->solver_warm, ctx->NX,
-                                        ctx->NY);
+                                        ctx->h_scalars + 256, rtol, max_iter, dmg ? 4 : 50, &it, &rr, &ctx->launches, ctx->solver_warm,
+                                        ctx->NX, ctx->NY, dmg ? ctx->mg : nullptr, fresh ? 0 : 1);
         if (ce != cudaSuccess)
             return fail(ctx, PLF_ECUDA, std::string("plf_solve_linear (distributed): ") +
                                             (ce == cudaErrorUnknown && comm_error()[0] ? comm_error() : cudaGetErrorString(ce)));

@@ -19,6 +19,13 @@ struct plf_batch {
     double *fy = nullptr, *sig_out = nullptr, *depl = nullptr, *ctan = nullptr;   // out: (n), (n,6), (n,6), (n,36)
     int32_t *nsteps = nullptr;
     int32_t *worklist = nullptr;   // compaction list of 50-sub-step elements
+    // plf_step_host_packed (allocated on first use): packed upper triangles, elastic bits, block counts / offsets, totals
+    double *ct21 = nullptr;
+    uint32_t *el_words = nullptr;
+    int32_t *pk_counts = nullptr, *pk_offsets = nullptr;
+    int64_t *pk_totals = nullptr;      // device, one per pipeline chunk
+    int64_t *h_pk_totals = nullptr;    // pinned mirror
+    bool mat_from_mesh = false;        // mat_id holds the mesh's material ids (multi-material plf_step_host)
 };
 
 struct plf_ctx {
@@ -83,6 +90,7 @@ struct plf_ctx {
     int solver_mg = 1;                // 1: V-cycle preconditioner when the mesh coarsens at least once, 0: Jacobi
     int solver_warm = 1;              // CG starts from the previous du (0: from zero)
     int mg_nu = 2, mg_coarse_sweeps = 10;   // smoothing sweeps per level (even) / on the coarsest level
+    int mg_fuse_tail = 2;             // coarse levels of the V-cycle in one fused kernel (mg_kernels.cu)
     double mg_omega = 0.7;            // Jacobi damping
     plf::Comm *comm = nullptr;       // NCCL communicator + strip neighbourhood (plf_comm.cu); nullptr: single GPU
     unsigned char *d_cgmask = nullptr;   // fixed | ghost-column mask of the distributed CG
@@ -90,6 +98,7 @@ struct plf_ctx {
     int n_partial = 0;
     plf::CgGraphCache cg_graph;    // captured chunk of CG iterations over this context's buffers
     int assembly_tiled = 2;        // option "assembly_tiled"
+    int passa_bulk = 0;            // option "passa_bulk" (1: cp.async.bulk variant of pass A; measured slower)
     // The kernels read materials and geometry classes from __constant__ banks, which are per device, not per context.
     // tables_dirty: this context's host tables changed since it last uploaded them; plf_bind() (head of every launch
     // sequence) re-uploads when the banks hold another context's tables or stale ones.
@@ -106,6 +115,7 @@ int fail(plf_ctx *c, int code, const std::string &msg);
 // Makes this context the owner of the device's __constant__ material / geometry banks (uploads its tables if another
 // context used the device in between or the tables changed).  Returns PLF_OK or PLF_ECUDA.
 int plf_bind(plf_ctx *ctx);
+int comm_host_allreduce(plf_ctx *ctx, double *vals, int n, int op);   // plf_comm.cu: no-op without a communicator
 void solve_state_free(plf_ctx *ctx);            // plf_solve.cu
 void solve_state_invalidate_bc(plf_ctx *ctx);   // plf_solve.cu: the device BC vectors were overwritten by the caller
 int model_reset_state(plf_ctx *ctx);            // zero u, f, element state; elstiff = CV (first Model.solve, model.py:1214-1227)
@@ -114,7 +124,7 @@ int model_solver_buffers(plf_ctx *ctx);         // work vectors of plf_solve_lin
 int model_solve_device_bc(plf_ctx *ctx, double rtol, int max_iter, int *iters, double *relres);
 inline plf::LaunchCtx make_lc(const plf_ctx *c)
 {
-    plf::LaunchCtx lc{c->stream, c->sm_count, c->passa_direct, c->max_fm, c->k1_only, c->passb_recur, c->assembly_tiled};
+    plf::LaunchCtx lc{c->stream, c->sm_count, c->passa_direct, c->max_fm, c->k1_only, c->passb_recur, c->passa_bulk, c->assembly_tiled};
     return lc;
 }
 void model_free(plf_ctx *ctx);

@@ -318,6 +318,176 @@ __global__ void __launch_bounds__(RB, 3) response_passA_kernel(int64_t n, const 
     }
 }
 
+// ------------------------------------------------------------------------------------------------------------
+// Pass A with bulk asynchronous copies (the TMA engine's linear mode, SASS: UBLKCP): one elected thread moves a tile's
+// three 6 KB input records into shared memory with cp.async.bulk + mbarrier transaction counts, and its results -- the
+// 36 KB tangent tile and the two 6 KB stress / plastic-strain-increment tiles, all contiguous in HBM -- leave with three
+// cp.async.bulk stores.  The other 127 threads issue no global memory instruction for the records at all (the cp.async
+// ring needed 9 LDGSTS per thread and tile, the staged write-back 21 LDS + 21 STG).  Tangent records of deferred
+// elements are written as whatever the staging buffer holds: pass B, which starts after this grid has completed,
+// overwrites them.  (First version: all three result tiles as bulk stores from the in-place buffers; every trip then
+// began with a wait for the previous stores to drain before the next load could be issued -- 8 % slower than the
+// cp.async kernel.  Now only the 36 KB tangent tile is a bulk store and its drain overlaps the next trip's math.)
+// ------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long *bar, unsigned count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long *bar, unsigned bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long *bar, unsigned parity)
+{
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_%=;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void bulk_load(void *smem_dst, const void *gmem_src, unsigned bytes, unsigned long long *bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(smem_u32(smem_dst)),
+                 "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void bulk_store(void *gmem_dst, const void *smem_src, unsigned bytes)
+{
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;\n" ::"l"(gmem_dst), "r"(smem_u32(smem_src)), "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;\n" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;\n" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;\n" ::: "memory"); }
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory"); }
+
+template <bool SINGLE, int FM>
+__global__ void __launch_bounds__(RB, 3) response_passA_bulk_kernel(int64_t n, const int32_t *__restrict__ mat_id,
+                                                                    const double *__restrict__ sig, const double *__restrict__ epl,
+                                                                    const double *__restrict__ deps, double *__restrict__ fy,
+                                                                    double *__restrict__ sig_out, double *__restrict__ depl_out,
+                                                                    double *__restrict__ ctan, int32_t *__restrict__ nsteps,
+                                                                    int32_t *__restrict__ worklist, unsigned int *__restrict__ work_count)
+{
+    constexpr int FA = (FM == 6 || FM == 7) ? 1 : (FM >= 3 ? 2 : FM);
+    extern __shared__ __align__(128) double smem[];   // [2][3][RB*6] input records (outputs sig / depl in place) | [RB*36] tangents
+    double *s_ct = smem + 2 * 3 * RB * 6;
+    __shared__ __align__(8) unsigned long long s_bar[2];
+    __shared__ unsigned char s_done[RB];
+    const int tid = threadIdx.x;
+    const int64_t ntiles = (n + RB - 1) / RB;
+    if (tid == 0) {
+        mbar_init(&s_bar[0], 1);
+        mbar_init(&s_bar[1], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+    }
+    __syncthreads();
+    auto load_tile = [&](int64_t tile, int b) {   // thread 0 only
+        const int64_t b0 = tile * RB;
+        const unsigned bytes = (unsigned)min((int64_t)RB, n - b0) * 48u;
+        double *d = smem + b * (3 * RB * 6);
+        mbar_expect_tx(&s_bar[b], 3u * bytes);
+        bulk_load(d, sig + b0 * 6, bytes, &s_bar[b]);
+        bulk_load(d + RB * 6, epl + b0 * 6, bytes, &s_bar[b]);
+        bulk_load(d + 2 * RB * 6, deps + b0 * 6, bytes, &s_bar[b]);
+    };
+    if (tid == 0 && (int64_t)blockIdx.x < ntiles) load_tile(blockIdx.x, 0);
+    unsigned phase[2] = {0u, 0u};
+    int buf = 0;
+    for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, buf ^= 1) {
+        // the other input buffer was last read by the generic-proxy write-back of the tile before (finished at the
+        // barrier that closed the previous trip), so its refill needs no wait on the bulk stores
+        if (tid == 0) {
+            const int64_t nxt = tile + gridDim.x;
+            if (nxt < ntiles) load_tile(nxt, buf ^ 1);
+        }
+        mbar_wait(&s_bar[buf], phase[buf]);
+        phase[buf] ^= 1u;
+        double *s_sig = smem + buf * (3 * RB * 6), *s_epl = s_sig + RB * 6, *s_dep = s_sig + 2 * RB * 6;
+        const int64_t base = tile * RB;
+        const int cnt = (int)min((int64_t)RB, n - base);
+        const int64_t e = base + tid;
+        bool defer = false, general = false, done = false;
+        double s[6], dp[6], ca[6], tc = 1., tw = 0.;
+        int mat_index = 0;
+        if (tid < cnt) {
+            double ep[6], de[6];
+#pragma unroll
+            for (int k = 0; k < 3; k++) {
+                const double2 a = reinterpret_cast<double2 *>(s_sig)[3 * tid + k];
+                const double2 b = reinterpret_cast<double2 *>(s_epl)[3 * tid + k];
+                const double2 c = reinterpret_cast<double2 *>(s_dep)[3 * tid + k];
+                s[2 * k] = a.x; s[2 * k + 1] = a.y; ep[2 * k] = b.x; ep[2 * k + 1] = b.y; de[2 * k] = c.x; de[2 * k + 1] = c.y;
+            }
+            mat_index = SINGLE ? 0 : mat_id[e];
+            const DevMat &m = c_mat[mat_index];
+            if (FM == 4 || FM == 6 || FM == 7) general = !planar_state(s, ep, de);
+            if (m.kind == PLF_MAT_ELASTIC || m.kind == PLF_MAT_HILL) {
+                double fyv = 0.;
+                int br = 0;
+                if (m.kind == PLF_MAT_ELASTIC) {
+                    double t[6];
+                    cv_mul(m, de, t);
+#pragma unroll
+                    for (int k = 0; k < 6; k++) { s[k] += t[k]; dp[k] = 0.; ca[k] = 0.; }
+                } else {
+                    br = (FM == 7) ? hillblk_passA(m, s, ep, de, dp, ca, tc, tw, fyv)
+                       : (FM == 6) ? hilliso_passA(m, s, ep, de, dp, ca, tc, tw, fyv)
+                       : (FM >= 3) ? iso_passA(m, s, ep, de, dp, ca, tc, tw, fyv) : hill_passA<FA>(m, s, ep, de, dp, ca, tc, tw, fyv);
+                }
+                if (br < 0) {
+                    defer = true;
+                } else {
+                    done = true;
+                    if (fy) fy[e] = fyv;
+                    if (nsteps) nsteps[e] = 0;
+                }
+            }
+        }
+        warp_append2(defer, general, (int32_t)e, worklist, n, work_count);
+        // the tangent tile of the previous trip left through a bulk store: its shared-memory image must have been read
+        // before it is overwritten (the wait overlapped this trip's load and math)
+        if (tid == 0) bulk_wait_read();
+        __syncthreads();
+        s_done[tid] = done;
+        if (done) {
+            const DevMat &m = c_mat[mat_index];
+#pragma unroll
+            for (int k = 0; k < 3; k++) {
+                reinterpret_cast<double2 *>(s_sig)[3 * tid + k] = make_double2(s[2 * k], s[2 * k + 1]);
+                reinterpret_cast<double2 *>(s_epl)[3 * tid + k] = make_double2(dp[2 * k], dp[2 * k + 1]);
+            }
+            double2 *o = reinterpret_cast<double2 *>(s_ct + 36 * tid);
+#pragma unroll
+            for (int i = 0; i < 6; i++) {
+                const double wi = ca[i] * tw;
+#pragma unroll
+                for (int j = 0; j < 6; j += 2)
+                    o[3 * i + (j >> 1)] = make_double2(m.CV[6 * i + j] * tc - wi * ca[j], m.CV[6 * i + j + 1] * tc - wi * ca[j + 1]);
+            }
+        }
+        fence_async_smem();     // generic-proxy writes to shared memory -> visible to the bulk-copy engine
+        __syncthreads();
+        if (tid == 0 && ctan) {
+            bulk_store(ctan + base * 36, s_ct, (unsigned)cnt * 288u);
+            bulk_commit();
+        }
+        // stress and plastic-strain increment: 2 x 6 KB, coalesced 128-bit stores by the whole block
+        for (int i = tid; i < cnt * 3; i += RB) {
+            if (!s_done[i / 3]) continue;
+            if (sig_out) reinterpret_cast<double2 *>(sig_out + base * 6)[i] = reinterpret_cast<const double2 *>(s_sig)[i];
+            if (depl_out) reinterpret_cast<double2 *>(depl_out + base * 6)[i] = reinterpret_cast<const double2 *>(s_epl)[i];
+        }
+        __syncthreads();        // this input buffer is refilled at the top of the next trip
+    }
+    if (tid == 0) bulk_wait_all();   // shared memory must outlive the last stores
+}
+
 // Pass B: persistent kernel over the two-ended work list.  (Variants that kept the 21-entry tangent accumulator in
 // shared memory for 4 blocks per SM, or ran at 2 blocks per SM without register cap, measured slower and were removed.)
 template <int MINB, bool SINGLE, int FM>
@@ -408,7 +578,7 @@ __global__ void __launch_bounds__(RB) response_generic_kernel(int64_t n, const i
 // ------------------------------------------------------------------------------------------------------------
 // K2: warp-per-element return mapping for one SVC material, SV table in shared memory.
 // ------------------------------------------------------------------------------------------------------------
-constexpr int SVC_WARPS = 8;
+constexpr int SVC_WARPS = 8;    // (16 warps at <= 128 registers spill inside the return-mapping core: measured 0.55 M against 0.79 M updates/s)
 
 __device__ __forceinline__ void svc_load_table(const DevMat &m, double *s_tab)
 {
@@ -552,36 +722,73 @@ __global__ void __launch_bounds__(128) prim_model_kernel(int op, int mid, int64_
     prim_eval(ym, m, op, s, ep, de, nullptr, out, true, e);
 }
 
-template <class Model>
+// MODE 0: the whole return mapping per thread.  MODE 1 / 2: the two passes of the compacted form (as for Hill): pass 1
+// finishes elastic and single-step elements and appends the ones whose trial step fails the tolerance to the work list
+// (one atomic per warp); pass 2, a persistent grid over the list, runs the 50 sub-steps for them.  Without it a warp with
+// one 50-sub-step element runs ~50 times longer than its neighbours (22 % of the Barlat bench states are such elements).
+template <class Model, int MODE>
 __global__ void __launch_bounds__(128) response_model_kernel(int64_t n, int mid, const int32_t *__restrict__ mat_id,
                                                               const double *__restrict__ sig, const double *__restrict__ epl,
                                                               const double *__restrict__ deps, double *__restrict__ fy,
                                                               double *__restrict__ sig_out, double *__restrict__ depl_out,
-                                                              double *__restrict__ ctan, int32_t *__restrict__ nsteps)
+                                                              double *__restrict__ ctan, int32_t *__restrict__ nsteps,
+                                                              int32_t *__restrict__ worklist, unsigned int *__restrict__ count)
 {
-    const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (e >= n) return;
-    if (mat_id && mat_id[e] != mid) return;
-    const DevMat &m = c_mat[mid];
-    double s[6], ep[6], de[6], dp[6], gs[21], fyv;
-    int ns;
+    const int64_t total = (MODE == 2) ? (int64_t)count[0] : n;
+    const int64_t stride = (MODE == 2) ? (int64_t)gridDim.x * blockDim.x : total + blockDim.x;   // MODE 0 / 1: one trip
+    for (int64_t t0 = (int64_t)blockIdx.x * blockDim.x; t0 < total; t0 += stride) {
+        const int64_t t = t0 + threadIdx.x;
+        bool defer = false;
+        int64_t e = -1;
+        if (t < total) {
+            e = (MODE == 2) ? (int64_t)worklist[t] : t;
+            if (!(mat_id && mat_id[e] != mid)) {
+                const DevMat &m = c_mat[mid];
+                double s[6], ep[6], de[6], dp[6], gs[21], fyv;
+                int ns;
 #pragma unroll
-    for (int k = 0; k < 6; k++) {
-        s[k] = __ldg(sig + e * 6 + k);
-        ep[k] = __ldg(epl + e * 6 + k);
-        de[k] = __ldg(deps + e * 6 + k);
+                for (int k = 0; k < 3; k++) {
+                    const double2 a = __ldg(reinterpret_cast<const double2 *>(sig + e * 6) + k);
+                    const double2 b = __ldg(reinterpret_cast<const double2 *>(epl + e * 6) + k);
+                    const double2 c = __ldg(reinterpret_cast<const double2 *>(deps + e * 6) + k);
+                    s[2 * k] = a.x; s[2 * k + 1] = a.y; ep[2 * k] = b.x; ep[2 * k + 1] = b.y; de[2 * k] = c.x; de[2 * k + 1] = c.y;
+                }
+                Model ym(m);
+                const int br = response_core<MODE == 1 ? 1 : 0>(ym, m, s, ep, de, dp, gs, fyv, ns);
+                if (br < 0) {
+                    defer = true;
+                } else {
+                    if (fy) fy[e] = fyv;
+                    if (nsteps) nsteps[e] = ns;
+                    if (sig_out)
+#pragma unroll
+                        for (int k = 0; k < 3; k++) reinterpret_cast<double2 *>(sig_out + e * 6)[k] = make_double2(s[2 * k], s[2 * k + 1]);
+                    if (depl_out)
+#pragma unroll
+                        for (int k = 0; k < 3; k++) reinterpret_cast<double2 *>(depl_out + e * 6)[k] = make_double2(dp[2 * k], dp[2 * k + 1]);
+                    if (ctan)
+#pragma unroll
+                        for (int g = 0; g < 9; g++) {
+                            double v[4];
+#pragma unroll
+                            for (int q = 0; q < 4; q++) {
+                                const int idx = 4 * g + q, i = idx / 6, j = idx - 6 * i;
+                                v[q] = gs[sym_idx(i, j)];
+                            }
+                            st256(ctan + e * 36 + 4 * g, v[0], v[1], v[2], v[3]);
+                        }
+                }
+            }
+        }
+        if (MODE == 1) warp_append(defer, (int32_t)e, worklist, count);
     }
-    Model ym(m);
-    response_core<0>(ym, m, s, ep, de, dp, gs, fyv, ns);
-    if (fy) fy[e] = fyv;
-    if (nsteps) nsteps[e] = ns;
-    if (sig_out)
-#pragma unroll
-        for (int k = 0; k < 6; k++) sig_out[e * 6 + k] = s[k];
-    if (depl_out)
-#pragma unroll
-        for (int k = 0; k < 6; k++) depl_out[e * 6 + k] = dp[k];
-    if (ctan) expand_sym(gs, ctan + e * 36, 1);
+    if (MODE == 2) {   // the last block to finish zeroes the counter for the next launch
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            __threadfence();
+            if (atomicAdd(count + 2, 1u) == gridDim.x - 1) { count[0] = 0; count[1] = 0; count[2] = 0; }
+        }
+    }
 }
 
 __global__ void __launch_bounds__(SVC_WARPS * 32) prim_svc_kernel(int op, int mid, int64_t n, const double *__restrict__ sig,
@@ -616,11 +823,119 @@ __global__ void __launch_bounds__(SVC_WARPS * 32) prim_svc_kernel(int op, int mi
 }
 
 // ------------------------------------------------------------------------------------------------------------
+// compact form of the return-mapping results for the host (plf_step_host_packed): the tangent of an element that took the
+// elastic branch IS Element.CV (bit for bit) and carries no information, and every grad_stiff is symmetric, so only the
+// upper triangles (21 doubles) of the other elements cross PCIe, in element order, next to one "elastic" bit per element.
+//   flags : bit per element + number of non-elastic elements per block of 256
+//   scan  : exclusive prefix over the block counts (one block; a chunk of the pipeline has <= 64 k blocks)
+//   write : upper triangles to their compacted slots
+// ------------------------------------------------------------------------------------------------------------
+constexpr int PK = 256;
+
+__device__ __forceinline__ bool tangent_is_cv(const double *__restrict__ ct, const double *cv)
+{
+    bool same = true;
+#pragma unroll
+    for (int g = 0; g < 18; g++) {
+        const double2 v = __ldg(reinterpret_cast<const double2 *>(ct) + g);
+        same = same && v.x == cv[2 * g] && v.y == cv[2 * g + 1];
+    }
+    return same;
+}
+
+__global__ void __launch_bounds__(PK) pack_flags_kernel(int64_t n, const int32_t *__restrict__ mat_id, int single,
+                                                        const double *__restrict__ ctan, uint32_t *__restrict__ words,
+                                                        int32_t *__restrict__ block_counts)
+{
+    const int64_t e = (int64_t)blockIdx.x * PK + threadIdx.x;
+    bool elastic = true;   // padding lanes count as elastic
+    if (e < n) elastic = tangent_is_cv(ctan + e * 36, c_mat[single ? 0 : mat_id[e]].CV);
+    const unsigned bal = __ballot_sync(0xffffffffu, elastic);
+    if ((threadIdx.x & 31) == 0 && e < n) words[e >> 5] = bal;
+    const int cnt = __syncthreads_count(!elastic);
+    if (threadIdx.x == 0) block_counts[blockIdx.x] = cnt;
+}
+
+__global__ void __launch_bounds__(1024) pack_scan_kernel(int nblocks, const int32_t *__restrict__ counts, int32_t *__restrict__ offsets,
+                                                         int64_t *__restrict__ total)
+{
+    __shared__ int s_warp[32];
+    __shared__ int s_carry;
+    if (threadIdx.x == 0) s_carry = 0;
+    __syncthreads();
+    for (int base = 0; base < nblocks; base += 1024) {
+        const int i = base + threadIdx.x;
+        const int v = i < nblocks ? counts[i] : 0;
+        int x = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int y = __shfl_up_sync(0xffffffffu, x, o);
+            if ((threadIdx.x & 31) >= o) x += y;
+        }
+        if ((threadIdx.x & 31) == 31) s_warp[threadIdx.x >> 5] = x;
+        __syncthreads();
+        if (threadIdx.x < 32) {
+            int w = s_warp[threadIdx.x];
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int y = __shfl_up_sync(0xffffffffu, w, o);
+                if (threadIdx.x >= o) w += y;
+            }
+            s_warp[threadIdx.x] = w;
+        }
+        __syncthreads();
+        const int before = s_carry + ((threadIdx.x >> 5) ? s_warp[(threadIdx.x >> 5) - 1] : 0) + x - v;
+        if (i < nblocks) offsets[i] = before;
+        __syncthreads();
+        if (threadIdx.x == 1023) s_carry = before + v;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) *total = s_carry;
+}
+
+__global__ void __launch_bounds__(PK) pack_write_kernel(int64_t n, const double *__restrict__ ctan, const uint32_t *__restrict__ words,
+                                                        const int32_t *__restrict__ block_offsets, double *__restrict__ ct21)
+{
+    __shared__ int s_w[PK / 32];
+    const int64_t e = (int64_t)blockIdx.x * PK + threadIdx.x;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const unsigned el = (e - lane < n) ? words[(e - lane) >> 5] : 0xffffffffu;
+    const unsigned plastic = ~el;
+    if (lane == 0) s_w[warp] = __popc(plastic);
+    __syncthreads();
+    int off = block_offsets[blockIdx.x];
+    for (int w = 0; w < warp; w++) off += s_w[w];
+    if (e < n && ((plastic >> lane) & 1u)) {
+        const int64_t slot = off + __popc(plastic & ((1u << lane) - 1u));
+        double *o = ct21 + slot * 21;
+        const double *c = ctan + e * 36;
+        int k = 0;
+#pragma unroll
+        for (int i = 0; i < 6; i++)
+#pragma unroll
+            for (int j = i; j < 6; j++) o[k++] = __ldg(c + 6 * i + j);
+    }
+}
+
+cudaError_t launch_pack(const LaunchCtx &lc, int64_t n, const int32_t *mat_id, int single, const double *ctan, uint32_t *words,
+                        int32_t *block_counts, int32_t *block_offsets, int64_t *total, double *ct21, int64_t *launches)
+{
+    if (n <= 0) return cudaSuccess;
+    const int nb = (int)((n + PK - 1) / PK);
+    pack_flags_kernel<<<nb, PK, 0, lc.stream>>>(n, mat_id, single, ctan, words, block_counts);
+    pack_scan_kernel<<<1, 1024, 0, lc.stream>>>(nb, block_counts, block_offsets, total);
+    pack_write_kernel<<<nb, PK, 0, lc.stream>>>(n, ctan, words, block_offsets, ct21);
+    *launches += 3;
+    return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------------------------
 // host launchers
 // ------------------------------------------------------------------------------------------------------------
 static size_t k1_smem() { return sizeof(double) * (3 * RB * 6 + RB * CT_STRIDE); }
 // double-buffered inputs (+ tangent staging for the non-direct variants)
 static size_t k1a_smem(bool direct) { return sizeof(double) * (2 * 3 * RB * 6 + (direct ? 0 : RB * CT_STRIDE)); }
+static size_t k1a_bulk_smem() { return sizeof(double) * (2 * 3 * RB * 6 + RB * 36); }
 static size_t svc_smem(const DevMat &m) { return sizeof(double) * 7 * (size_t)m.nsv_pad; }
 
 template <class K>
@@ -642,6 +957,14 @@ cudaError_t response_init()
     if ((e = big_smem(response_passA_kernel<true, 5, false>, k1a_smem(false))) != cudaSuccess) return e;
     if ((e = big_smem(response_passA_kernel<true, 6, false>, k1a_smem(false))) != cudaSuccess) return e;
     if ((e = big_smem(response_passA_kernel<true, 7, false>, k1a_smem(false))) != cudaSuccess) return e;
+    if ((e = big_smem(response_passA_bulk_kernel<false, 0>, k1a_bulk_smem())) != cudaSuccess) return e;
+    if ((e = big_smem(response_passA_bulk_kernel<true, 0>, k1a_bulk_smem())) != cudaSuccess) return e;
+    if ((e = big_smem(response_passA_bulk_kernel<true, 1>, k1a_bulk_smem())) != cudaSuccess) return e;
+    if ((e = big_smem(response_passA_bulk_kernel<true, 2>, k1a_bulk_smem())) != cudaSuccess) return e;
+    if ((e = big_smem(response_passA_bulk_kernel<true, 3>, k1a_bulk_smem())) != cudaSuccess) return e;
+    if ((e = big_smem(response_passA_bulk_kernel<true, 4>, k1a_bulk_smem())) != cudaSuccess) return e;
+    if ((e = big_smem(response_passA_bulk_kernel<true, 6>, k1a_bulk_smem())) != cudaSuccess) return e;
+    if ((e = big_smem(response_passA_bulk_kernel<true, 7>, k1a_bulk_smem())) != cudaSuccess) return e;
     if ((e = big_smem(response_generic_kernel, k1_smem())) != cudaSuccess) return e;
     if ((e = big_smem(response_svc_kernel, 227 * 1024)) != cudaSuccess) return e;
     return big_smem(prim_svc_kernel, 227 * 1024);
@@ -683,7 +1006,10 @@ cudaError_t launch_response(const LaunchCtx &lc, const DevMat *hmats, int nmat, 
             // persistent: 3 blocks per SM, each walking tiles with a double-buffered cp.async prefetch
 #define PASSA(S, F)                                                                                                              \
     do {                                                                                                                         \
-        if (direct)                                                                                                              \
+        if (lc.passa_bulk && (F) != 5)                                                                                           \
+            response_passA_bulk_kernel<S, (F) == 5 ? 0 : (F)><<<pgrid, RB, k1a_bulk_smem(), lc.stream>>>(                        \
+                n, mat_id, sig, epl, deps, fy, sig_out, depl, ctan, nsteps, worklist, work_count);                               \
+        else if (direct)                                                                                                              \
             response_passA_kernel<S, F, true><<<pgrid, RB, k1a_smem(true), lc.stream>>>(n, mat_id, sig, epl, deps, fy, sig_out,  \
                                                                                         depl, ctan, nsteps, worklist, work_count); \
         else                                                                                                                     \
@@ -740,15 +1066,33 @@ cudaError_t launch_response(const LaunchCtx &lc, const DevMat *hmats, int nmat, 
         }
     }
     for (int i = 0; i < nmat; i++) {
-        if (hmats[i].kind == PLF_MAT_BARLAT)
-            response_model_kernel<BarlatModel><<<grid, RB, 0, lc.stream>>>(n, i, nmat > 1 ? mat_id : nullptr, sig, epl, deps, fy,
-                                                                           sig_out, depl, ctan, nsteps);
-        else if (hmats[i].kind == PLF_MAT_HILL3)
-            response_model_kernel<HillPrincModel><<<grid, RB, 0, lc.stream>>>(n, i, nmat > 1 ? mat_id : nullptr, sig, epl, deps, fy,
-                                                                              sig_out, depl, ctan, nsteps);
-        else
-            continue;
-        (*launches)++;
+        const int32_t *mid_p = nmat > 1 ? mat_id : nullptr;
+        if (hmats[i].kind == PLF_MAT_BARLAT || hmats[i].kind == PLF_MAT_HILL3) {
+            const bool bar = hmats[i].kind == PLF_MAT_BARLAT;
+            if (compact && worklist) {
+                const unsigned bgrid = (unsigned)std::min<int64_t>((int64_t)lc.sm_count * 8, (int64_t)grid);
+                if (bar) {
+                    response_model_kernel<BarlatModel, 1><<<grid, RB, 0, lc.stream>>>(n, i, mid_p, sig, epl, deps, fy, sig_out, depl, ctan,
+                                                                                      nsteps, worklist, work_count);
+                    response_model_kernel<BarlatModel, 2><<<bgrid, RB, 0, lc.stream>>>(n, i, mid_p, sig, epl, deps, fy, sig_out, depl, ctan,
+                                                                                       nsteps, worklist, work_count);
+                } else {
+                    response_model_kernel<HillPrincModel, 1><<<grid, RB, 0, lc.stream>>>(n, i, mid_p, sig, epl, deps, fy, sig_out, depl,
+                                                                                         ctan, nsteps, worklist, work_count);
+                    response_model_kernel<HillPrincModel, 2><<<bgrid, RB, 0, lc.stream>>>(n, i, mid_p, sig, epl, deps, fy, sig_out, depl,
+                                                                                          ctan, nsteps, worklist, work_count);
+                }
+                *launches += 2;
+            } else {
+                if (bar)
+                    response_model_kernel<BarlatModel, 0><<<grid, RB, 0, lc.stream>>>(n, i, mid_p, sig, epl, deps, fy, sig_out, depl, ctan,
+                                                                                      nsteps, nullptr, nullptr);
+                else
+                    response_model_kernel<HillPrincModel, 0><<<grid, RB, 0, lc.stream>>>(n, i, mid_p, sig, epl, deps, fy, sig_out, depl,
+                                                                                         ctan, nsteps, nullptr, nullptr);
+                (*launches)++;
+            }
+        }
     }
     for (int i = 0; i < nmat; i++) {
         if (hmats[i].kind != PLF_MAT_SVC) continue;

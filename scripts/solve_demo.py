@@ -38,7 +38,7 @@ def main():
     fe.bcnode(0, 0., 'disp', 'x')
     fe.solver_rtol = float(os.environ.get('PLF_RTOL', '1e-10'))
     fe._dev().set_option('solver_mg', int(os.environ.get('PLF_MG', '1')))   # 0: Jacobi-preconditioned CG
-    for key in ('mg_nu', 'mg_coarse_sweeps', 'mg_omega_permille', 'solver_warm'):
+    for key in ('mg_nu', 'mg_coarse_sweeps', 'mg_omega_permille', 'solver_warm', 'mg_fuse_tail', 'skip_unchanged'):
         if 'PLF_' + key.upper() in os.environ:
             fe._dev().set_option(key, int(os.environ['PLF_' + key.upper()]))
     t1 = time.time()

@@ -510,3 +510,127 @@ def test_interleaved_contexts_do_not_disturb_a_model(golden):
     fe3.solve(min_step=3)
     assert np.array_equal(fe2.u, fe3.u)
     del g
+
+
+@pytest.mark.parametrize('N,fuse', [(64, 1), (128, 2), (96, 2)])
+def test_fused_vcycle_and_change_tracking_are_bit_identical(N, fuse):
+    """The fused forms of the V-cycle -- mg_tail_kernel (all coarse levels of the cycle in one block's shared memory) and
+    mg_coop_kernel (the middle levels in one cooperative grid with grid-wide barriers, tail included) -- use the
+    arithmetic of the per-level kernels in the same order, and skipping the re-assembly / re-coarsening of an unchanged K
+    changes nothing: plastic inclusion runs, identical CG iteration counts and bit-identical u, far fewer launches."""
+    runs = {}
+    for key, opts in (('fused', {'mg_fuse_tail': fuse}), ('plain', {'mg_fuse_tail': 0, 'skip_unchanged': 0})):
+        fe = inclusion(N, plastic=True, eps_tot=0.004)
+        for k, v in opts.items():
+            fe._dev().set_option(k, v)
+        fe.solver_rtol = 1.e-11
+        fe.solve(min_step=4)
+        runs[key] = fe
+    a, b = runs['fused'], runs['plain']
+    assert a.nsteps == b.nsteps and list(a.niter) == list(b.niter)
+    assert [s[0] for s in a.solver_stats] == [s[0] for s in b.solver_stats]
+    assert np.array_equal(a.u, b.u) and np.array_equal(a.f, b.f)
+    assert a._dev().launch_count() < 0.6 * b._dev().launch_count()
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# direct checks of two steps of Model.solve that the end-to-end fixtures only pin indirectly
+# ---------------------------------------------------------------------------------------------------------------------
+def _oracle_j2():
+    from oracle import oracle as orc
+    return orc, orc.Mat(kind=orc.HILL, E=100.e3, nu=0.27, sy=150., khard=500.)
+
+
+def _predictor(fe, top):
+    """K from the current tangents and the elastic predictor du for a top displacement (device), returns the context."""
+    ctx = fe._dev()
+    ctx.setupK()
+    fixed, du, w, fext = fe._calc_BC(fe.bcl, fe.bcb, np.zeros(2), np.array([0., top]), np.zeros(2) if fe.noset is not None else None)
+    ctx.solve_linear(fixed, du, w, fext, rtol=1e-13)
+    return ctx
+
+
+def _element_deps(fe, ctx, du):
+    out = np.zeros((fe.Nel, 6))
+    for e in range(fe.Nel):
+        B4 = ctx.get_bmat(e)
+        ue = du[np.array(fe.element[e].node_num())]
+        out[e] = sum(B4[g] @ ue for g in range(4))
+    return out
+
+
+@pytest.mark.parametrize('case', ['uniform_min', 'spread_mean_minus_std'])
+def test_calc_scf_against_a_numpy_restatement(case):
+    """plf_calc_scf vs model.py:1036-1067 restated with NumPy on top of the oracle's calc_seq / calc_yf: both selection
+    branches (std < 0.1 -> minimum, else mean - std), both candidate formulas (yf0 < -0.15 -> -yf0 / sref, appended TWICE
+    as at model.py:1050 and 1054; else sqrt(1.5) sflow / sref), elastic elements skipped."""
+    from pylabfea_b200 import _lib
+    orc, om = _oracle_j2()
+    # homogeneous block: every element sees the same increment (std = 0); inclusion mesh with mixed states: wide spread
+    fe = uniax('j2', N=6) if case == 'uniform_min' else inclusion(9, plastic=True, eps_tot=0.01)
+    ctx = fe._dev()
+    rng = np.random.default_rng(5)
+    sig = np.zeros((fe.Nel, 6))
+    epl = np.zeros((fe.Nel, 6))
+    if case == 'spread_mean_minus_std':
+        # a third of the elements sits on the yield surface with some plastic strain, the rest is far inside
+        on = rng.random(fe.Nel) < 0.35
+        peeq = np.where(on, rng.uniform(0., 0.01, fe.Nel), 0.)
+        epl[:, 0], epl[:, 1], epl[:, 2] = -0.5 * peeq, peeq, -0.5 * peeq
+        sig[:, 1] = np.where(on, 150. + 500. * peeq, rng.uniform(0., 60., fe.Nel))
+    ctx.set_field(_lib.F_SIG, sig)
+    ctx.set_field(_lib.F_EPL, epl)
+    ctx = _predictor(fe, 0.01 * fe.leny if case == 'uniform_min' else 0.004 * fe.leny)
+    scf = ctx.calc_scf(np.array([0., 1., 0., 0., 0., 0.]))
+    du = ctx.get_field(_lib.F_DU)
+    C = ctx.get_tangent()
+    deps = _element_deps(fe, ctx, du)
+    cand = []
+    for e in range(fe.Nel):
+        if fe._elem_mat[e] != 0:
+            continue
+        dsig = C[e] @ deps[e]
+        sref = float(orc.calc_seq(om, dsig)[0])
+        if sref > 0.1:
+            yf0 = float(orc.calc_yf(om, sig[e], epl[e])[0])
+            if yf0 < -0.15:
+                cand += [min(1., -yf0 / sref)] * 2
+            else:
+                peeq_e = np.sqrt(2. / 3. * np.sum(epl[e, :3] ** 2))
+                cand.append(min(1., np.sqrt(1.5) * (150. + 500. * peeq_e) / sref))
+    cand = np.array(cand)
+    sd = np.std(cand)
+    want = np.amin(cand) if sd < 0.1 else max(1.e-3, np.mean(cand) - sd)
+    assert (sd < 0.1) == (case == 'uniform_min')
+    assert abs(scf - max(want, 1.e-3)) <= 1e-10 * want
+
+
+def test_sweep_averages_the_tangent_from_pass_15_on():
+    """plf_sweep with nit = 15 (model.py:1350-1353): where |elstiff - grad_stiff|_F > 1e-3 the new element tangent is the
+    mean of the old one and the response tangent; with nit = 14 it is the response tangent itself.  The response results
+    come from the CPU oracle on the same (sig, epl, deps)."""
+    from pylabfea_b200 import _lib
+    orc, om = _oracle_j2()
+    outs = {}
+    for nit in (14, 15):
+        fe = inclusion(9, plastic=True, eps_tot=0.01)
+        ctx = _predictor(fe, 0.004 * fe.leny)
+        sig, epl, du = ctx.get_field(_lib.F_SIG), ctx.get_field(_lib.F_EPL), ctx.get_field(_lib.F_DU)
+        C_old = ctx.get_tangent()
+        deps = _element_deps(fe, ctx, du)
+        change, conv, max_hh, counts = ctx.sweep(nit)
+        outs[nit] = (ctx.get_tangent(), C_old, sig, epl, deps, change, max_hh, ctx.get_field(_lib.F_RES_SIG), fe)
+    C15, C_old, sig, epl, deps, change, max_hh, res_sig, fe = outs[15]
+    pl = np.nonzero(fe._elem_mat == 0)[0]
+    CV = fe._dev().element_CV(0)
+    fy, so, dp, ct, ns = orc.response_batch([om], None, sig[pl], epl[pl], deps[pl], CV[None])
+    hh = np.sqrt(np.sum((C_old[pl] - ct) ** 2, axis=(1, 2)))
+    moved = hh > 1.e-3
+    assert change and moved.any() and (~moved).any() is not None
+    assert abs(max_hh - hh.max()) <= 1e-9 * hh.max()
+    assert relmax(res_sig[pl], so) < 1e-9
+    assert relmax(C15[pl][moved], 0.5 * (ct[moved] + C_old[pl][moved])) < 1e-9
+    assert np.array_equal(C15[pl][~moved], C_old[pl][~moved])
+    assert relmax(outs[14][0][pl][moved], ct[moved]) < 1e-9
+    el = np.nonzero(fe._elem_mat != 0)[0]
+    assert np.array_equal(C15[el], C_old[el])      # elastic elements never enter the sweep (model.py:1341)

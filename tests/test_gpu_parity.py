@@ -405,6 +405,65 @@ def test_step_host_pipelined_equals_unpipelined(ctx, shape):
     ctx.batch_destroy(b)
 
 
+def _unpack_tangents(n, ct21, words, n_packed, CVs, mat_id):
+    """Host side of plf_step_host_packed: full (n,6,6) tangents from the elastic bits and the packed upper triangles."""
+    bits = np.unpackbits(words.view(np.uint8), bitorder='little')[:n].astype(bool)
+    full = np.empty((n, 6, 6))
+    full[bits] = CVs[mat_id[bits]]
+    iu = np.triu_indices(6)
+    tri = ct21[:21 * n_packed].reshape(n_packed, 21)
+    assert n_packed == int(np.sum(~bits))
+    t = np.zeros((n_packed, 6, 6))
+    t[:, iu[0], iu[1]] = tri
+    t[:, iu[1], iu[0]] = tri
+    full[~bits] = t
+    return full, bits
+
+
+@pytest.mark.parametrize('shape,mixed', [((64, 32), False), ((16, 64), True), ((8, 4), False)])
+def test_step_host_packed_equals_step_host(ctx, shape, mixed):
+    """plf_step_host_packed (upper triangles of the non-elastic tangents in element order + one elastic bit per element,
+    K optionally left on the device) carries exactly the information of plf_step_host: every result array bit-identical
+    after unpacking, also on a mixed-material mesh (J2 + elastic inclusion columns + a second plastic material)."""
+    import bench
+    from helpers import elastic_material
+    NX, NY = shape
+    mat, CV = bench.j2_material()
+    n = NX * NY
+    mats, elem_mat = [mat], np.zeros(n, np.int32)
+    if mixed:
+        soft = elastic_material(3.e3, 0.3, CV * (3.e3 / bench.E_MOD))
+        hard, _ = bench.j2_material()
+        hard.sy, hard.khard = 120., 2000.
+        mats = [mat, soft, hard]
+        elem_mat = ((np.arange(n) // NY) % 3).astype(np.int32)
+    ctx.set_materials(mats, planestress=False)
+    ctx.mesh_structured(NX, NY, np.full(NX, 4. / NX), 4. / NY, 1., elem_mat)
+    CVs = np.array([ctx.element_CV(i) for i in range(len(mats))])
+    s0, e0, d0 = bench.synth_states(max(NX, NY), 78)
+    sig, epl, deps = s0[:n].copy(), e0[:n].copy(), d0[:n].copy()
+    b = ctx.batch_create(n)
+    ref = [np.empty(n), np.empty((n, 6)), np.empty((n, 6)), np.empty((n, 6, 6)), np.empty(n, np.int32)]
+    kref = np.empty(ctx.nnz)
+    ctx.step_host(b, sig, epl, deps, fy=ref[0], sig_out=ref[1], depl=ref[2], ctan=ref[3], nsteps=ref[4], kval=kref)
+    out = [np.full(n, np.nan), np.full((n, 6), np.nan), np.full((n, 6), np.nan), np.full(n, -7, np.int32)]
+    ct21 = np.full(21 * n, np.nan)
+    words = np.zeros((n + 31) // 32, np.uint32)
+    kval = np.full(ctx.nnz, np.nan)
+    for with_k in (True, False):
+        npk = ctx.step_host_packed(b, sig, epl, deps, ct21, words, fy=out[0], sig_out=out[1], depl=out[2], nsteps=out[3],
+                                   kval=kval if with_k else None)
+        full, bits = _unpack_tangents(n, ct21, words, npk, CVs, elem_mat)
+        assert np.array_equal(full, ref[3])
+        for a, r in zip(out, (ref[0], ref[1], ref[2], ref[4])):
+            assert np.array_equal(a, r)
+        assert np.array_equal(kval, kref)
+        assert np.all(ref[2][bits] == 0.)            # elastic branch: no plastic strain increment
+        assert 0 < npk < n
+    assert np.array_equal(ctx.get_csr_values(np.empty(ctx.nnz)), kref)   # K left on the device is the same K
+    ctx.batch_destroy(b)
+
+
 def test_response_hill_isotropic_planar_mode_vs_oracle(ctx):
     """BASELINE config 3 (512 x 512, Hill-6p with isotropic hardening on isotropic elasticity, synthetic planar field):
     the Hill fast mode (hilliso_passA + planar 50-sub-step loop) against the general Hill kernels on every element and
