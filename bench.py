@@ -251,6 +251,16 @@ class RankGroup:
     def sum_over_ranks(self, v):
         return self._reduce(v, self.dist.ReduceOp.SUM if self.dist else None)
 
+    def broadcast_bytes(self, payload, n):
+        """n bytes from rank 0 to every rank (the NCCL unique id of the solver's own communicator)."""
+        if self.dist is None:
+            return payload
+        t = self.torch.zeros(n, dtype=self.torch.uint8, device=self.dev)
+        if payload is not None:
+            t = self.torch.tensor(list(payload), dtype=self.torch.uint8, device=self.dev)
+        self.dist.broadcast(t, src=0)
+        return bytes(t.cpu().tolist())
+
     def close(self):
         if self.dist is not None:
             self.dist.destroy_process_group()
@@ -402,6 +412,60 @@ def run_load_sequence(N, min_step, eps, device=0):
            'gpu_launches': int(ctx.launch_count() - l0), 'launches_per_solve': float((ctx.launch_count() - l0) / max(len(its), 1)),
            'global_stress_yy': float(fe.glob['sig'][1]), 'substep50_final': float(fe.sweep_stats[-1][5][2] / max(sum(fe.sweep_stats[-1][5][:3]), 1)) if fe.sweep_stats else 0.}
     return out, fe
+
+
+def run_coupled_solve(group, rank, world, local, N=512, min_step=3, eps=0.002):
+    """The part of the path WITH an exchange step: Model.solve of ONE model cut into strips over the ranks
+    (Model.distribute, one process per GPU).  Workload = BASELINE config 4: 512 x 512 mesh, RBF-SVC yield function of
+    examples/train_hill.py (1585 support vectors), elastic inclusion, uniaxial displacement control.  STRONG scaling: the
+    model is fixed; every rank updates the elements of its strip and assembles its K rows, the owned rows of all ranks are
+    gathered (NCCL broadcasts, one contiguous CSR range per rank) and every rank solves the complete system (replicated
+    multigrid-CG: du bit-identical to the single-GPU run); sweep flags, calc_scf moments, global averages and boundary sums
+    are all-reduced.  Wall clock between barriers around solve(), max over ranks."""
+    import pylabfea_b200 as FE
+    from pylabfea_b200 import _lib
+    g = dict(np.load(os.path.join(GOLDEN, 'svc_hill.npz')))
+    mat1 = FE.Material('ML-Hill-p1', num=1)
+    mat1.elasticity(CV=g['CV'])
+    mat1.plasticity(sy=float(g['sy']), sdim=6)
+    mat1.set_svc(g['sv'], g['dual'], float(g['rho']), float(g['gamma']), scale_seq=float(g['scale_seq']))
+    mat2 = FE.Material(num=2)
+    mat2.elasticity(E=3.e3, nu=0.3)
+    n1 = N // 3
+    el = np.ones((N, N))
+    el[n1:2 * n1, n1:2 * n1] = 2
+    fe = FE.Model(dim=2, planestress=False, device=local)
+    fe.geom(sect=2, LX=4., LY=4.)
+    fe.assign([mat1, mat2])
+    fe.bcbot(0.)
+    fe.bcright(0., 'force')
+    fe.bcleft(0., 'force')
+    fe.bctop(eps * fe.leny, 'disp')
+    fe.mesh(elmts=el, NX=N, NY=N)
+    fe.bcnode(0, 0., 'disp', 'x')
+    fe.solver_rtol = 1.e-10
+    if world > 1:
+        uid = group.broadcast_bytes(_lib.comm_unique_id() if rank == 0 else None, _lib.COMM_ID_BYTES)
+        fe.distribute(rank, world, uid, solver='replicated')
+    ctx = fe._dev()
+    ctx.synchronize()
+    group.barrier()
+    l0 = ctx.launch_count()
+    t0 = time.perf_counter()
+    fe.solve(min_step=min_step)
+    ctx.synchronize()
+    group.barrier()
+    dt = group.max_over_ranks(time.perf_counter() - t0)
+    its = int(sum(s[0] for s in fe.solver_stats))
+    updates = float(sum(sum(s[5][:3]) for s in fe.sweep_stats))
+    return {'workload': '%dx%d mesh, RBF-SVC yield function (1585 support vectors) + elastic inclusion, Model.solve(min_step=%d), '
+                        'eps=%g (BASELINE config 4)' % (N, N, min_step, eps),
+            'scaling': 'strong', 'solver': 'single GPU' if world == 1 else 'replicated (K rows gathered, every rank solves)',
+            'elements': N * N, 'dofs': int(fe.Ndof), 'seconds': dt, 'increments': int(fe.nsteps),
+            'inner_passes': [int(x) for x in fe.niter], 'linear_solves': len(fe.solver_stats), 'cg_iterations': its,
+            'element_updates': updates, 'element_updates_per_s': updates / dt,
+            'collectives_per_pass': 0 if world == 1 else 'K gather (%d broadcasts) + 2 all-reduces of sweep flags' % world,
+            'launches_rank0': int(ctx.launch_count() - l0), 'global_stress_yy': float(fe.glob['sig'][1])}
 
 
 def run_c1(device):
@@ -683,6 +747,13 @@ def main():
         e2e['packed_with_K'] = {'value': world * owned / (pk_ms * 1e-3), 'ms_per_step': pk_ms,
                                 'd2h_bytes_per_step': int(d2h + ctx.nnz * 8), 'note': 'compact results plus the CSR(K) values'}
 
+    coupled = None
+    if not args.no_configs:
+        try:
+            coupled = run_coupled_solve(group, rank, world, local)
+        except Exception as exc:
+            coupled = {'error': '%s: %s' % (type(exc).__name__, exc)}
+
     if rank != 0:
         group.close()
         return
@@ -747,6 +818,7 @@ def main():
             'roofline': roofline, 'cpu_baseline': cpu, 'e2e': e2e, 'gpu_launches': int(gpu_launches),
             'launches_per_step': launches_per_step, 'clocks': clocks, 'wall_s_timed_region': t_wall,
             'device': ctx.device_info()['name']}
+    line['coupled_solve'] = coupled
     if world == 1 and not args.no_configs:
         # every BASELINE config next to the headline, and a whole load sequence through Model.solve (the path that keeps
         # an increment on the device: predictor + calc_scf + inner passes + commit per increment)

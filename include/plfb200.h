@@ -70,8 +70,14 @@ typedef struct plf_material {
     double d[3];
     double barlat_m1[36], barlat_m2[36], barlat_exp; /* Material.Bar_m1 / Bar_m2 / barlat_exp */
     double svc_gamma, svc_rho, svc_scale_seq;        /* gam_yf, svm_yf.intercept_[0], scale_seq */
-    const double *svc_sv;   /* host, [nsv][6]: svm_yf.support_vectors_ */
+    const double *svc_sv;   /* host, [nsv][svc_nfeat]: svm_yf.support_vectors_ */
     const double *svc_dual; /* host, [nsv]:    svm_yf.dual_coef_[0]    */
+    /* work-hardening SVC (Material.whdat, material.py:2342-2346, 2667-2669): svc_nfeat = 15 = 6 stress + 6 plastic strain /
+     * scale_wh + accumulated strain + maximum stress + flag (the last three are 0 on this path, the defaults of calc_yf);
+     * 0 or 6: stress features only.  khard then is what calc_fgrad leaves on the material (808-814), per element. */
+    int32_t svc_nfeat;
+    int32_t pad2_;
+    double svc_scale_wh;
 } plf_material;
 
 typedef struct plf_ctx plf_ctx;
@@ -179,8 +185,7 @@ int plf_step_host(plf_ctx *ctx, plf_batch *b, const double *sig, const double *e
  * elastic branch (their grad_stiff is CV, their depl is 0), and ct21 receives, in element order, the 21 upper-triangle
  * entries (row-major, i <= j) of grad_stiff of all OTHER elements; *n_packed is their number (ct21 must hold Nel * 21
  * doubles).  kval == NULL leaves the assembled K on the device for plf_solve_linear (the Newton loop of Model.solve never
- * needs it on the host); fy, sig_out, depl, nsteps may be NULL.  Mixed-material meshes are supported (ids from the mesh).
- * Needs NY * (NX / 8) to be a multiple of 32 (chunks of the pipeline start on bitmap words). */
+ * needs it on the host); fy, sig_out, depl, nsteps may be NULL.  Mixed-material meshes are supported (ids from the mesh). */
 int plf_step_host_packed(plf_ctx *ctx, plf_batch *b, const double *sig, const double *epl, const double *deps, double *fy,
                          double *sig_out, double *depl, int32_t *nsteps, double *ct21, uint32_t *elastic_words,
                          int64_t *n_packed, double *kval);
@@ -299,6 +304,15 @@ int plf_comm_set_strip(plf_ctx *ctx, int own_first, int own_end);
  * calc_global sums (1500-1511) and the bcval sums (1452-1471) are combined over the ranks, so all ranks step alike. */
 int plf_comm_set_partition(plf_ctx *ctx, int own_first, int own_end, int first_col_global, int NX_global, double x_offset,
                            double lenx_global);
+/* Replicated solve.  The element work of a pass (stress updates, K rows) shards perfectly over the strips; the linear
+ * solve does not have to: `global_ctx` is a second context of the same process holding the GLOBAL mesh (plf_set_materials +
+ * plf_mesh_structured with the global NX).  With it, every solve of plf_load_increment gathers the owned CSR rows of all
+ * ranks into global_ctx (one NCCL broadcast per rank; the rows of a strip are one contiguous range of the global value
+ * array), solves the complete system there -- on every rank alike, with the single-GPU multigrid-preconditioned CG, so du
+ * is bit-identical to the single-GPU solve -- and copies the strip's node columns of du back.  This is the north star's
+ * "NCCL allreduce on the assembled system" variant: no communication inside the solve, the solve itself is not sharded.
+ * Pass NULL to return to the strip-partitioned CG. */
+int plf_comm_set_replica(plf_ctx *ctx, plf_ctx *global_ctx);
 /* sum of n <= 64 host doubles over all ranks, in place (sweep flags, calc_global sums, calc_scf moments) */
 int plf_comm_allreduce(plf_ctx *ctx, double *vals, int n);
 int plf_comm_destroy(plf_ctx *ctx);

@@ -25,7 +25,7 @@ class OrcMat(C.Structure):
                 ('hill', C.c_double * 6), ('d', C.c_double * 3),
                 ('bar_m1', C.c_double * 36), ('bar_m2', C.c_double * 36), ('bar_exp', C.c_double),
                 ('gamma', C.c_double), ('rho', C.c_double), ('scale_seq', C.c_double),
-                ('sv', _dp), ('dual', _dp)]
+                ('sv', _dp), ('dual', _dp), ('nfeat', C.c_int32), ('pad2_', C.c_int32), ('scale_wh', C.c_double)]
 
 
 def build(force=False):
@@ -79,6 +79,9 @@ class Mat:
             sv = np.atleast_2d(np.asarray(svc['sv'], dtype=float))
             if sv.shape[1] < 6:   # sdim = 3 models have 2 features: the table always has 6 columns, the rest zero
                 sv = np.hstack([sv, np.zeros((len(sv), 6 - sv.shape[1]))])
+            if sv.shape[1] == 15:   # work-hardening features (Material.whdat)
+                m.nfeat = 15
+                m.scale_wh = float(svc['scale_wh'])
             self._sv = _a(sv)
             self._dual = _a(svc['dual'])
             m.nsv = len(self._dual)

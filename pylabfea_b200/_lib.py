@@ -25,7 +25,7 @@ class PlfMaterial(C.Structure):
                 ('sy', C.c_double), ('khard', C.c_double), ('hill', C.c_double * 6), ('d', C.c_double * 3),
                 ('barlat_m1', C.c_double * 36), ('barlat_m2', C.c_double * 36), ('barlat_exp', C.c_double),
                 ('svc_gamma', C.c_double), ('svc_rho', C.c_double), ('svc_scale_seq', C.c_double),
-                ('svc_sv', _dp), ('svc_dual', _dp)]
+                ('svc_sv', _dp), ('svc_dual', _dp), ('svc_nfeat', C.c_int32), ('pad2_', C.c_int32), ('svc_scale_wh', C.c_double)]
 
 
 MAX_PASSES = 17
@@ -442,6 +442,17 @@ class Context:
     def comm_set_strip(self, own_first, own_end):
         """Owned node columns [own_first, own_end) of the local mesh (shard.strip_shard: owned_node_cols_local)."""
         self._ck(self.L.plf_comm_set_strip(self.h, int(own_first), int(own_end)))
+
+    def comm_set_partition(self, own_first, own_end, first_col_global, NX_global, x_offset, lenx_global):
+        """comm_set_strip plus the strip's position in the global mesh (needed by solve_begin / load_increment on a rank)."""
+        self._ck(self.L.plf_comm_set_partition(self.h, int(own_first), int(own_end), int(first_col_global), int(NX_global),
+                                               C.c_double(x_offset), C.c_double(lenx_global)))
+
+    def comm_set_replica(self, global_ctx):
+        """Replicated solve: `global_ctx` (a Context with the GLOBAL mesh on the same device, or None) solves the system
+        gathered from all ranks; see plf_comm_set_replica."""
+        self._replica = global_ctx
+        self._ck(self.L.plf_comm_set_replica(self.h, None if global_ctx is None else global_ctx.h))
 
     def comm_allreduce(self, vals):
         """Sum of a small float vector over all ranks."""

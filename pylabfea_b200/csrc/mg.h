@@ -21,6 +21,7 @@ struct MgHierarchy {
     int nu = 2;                // pre- and post-smoothing sweeps (even)
     int coarse_sweeps = 10;    // damped Jacobi sweeps on the coarsest level (40 measured 15 % slower per solve, 4 % fewer iterations)
     double omega = 0.7;
+    int j0 = 0;                // first node column of level 0 that belongs to the hierarchy (1: left halo column of a strip)
     int tail_first = -1;       // first level of the fused single-block tail of the cycle (-1: none fits)
     int fuse_tail = 2;         // option "mg_fuse_tail": 0 every level as its own kernels, 1 fused single-block tail, 2 (default)
                                // additionally the cooperative grid kernel for the levels between the fine ones and the tail
@@ -30,7 +31,7 @@ struct MgHierarchy {
     int levels() const { return (int)lv.size(); }
 };
 
-cudaError_t mg_build(MgHierarchy &H, int NX, int NY);
+cudaError_t mg_build(MgHierarchy &H, int NX, int NY, int j0 = 0);
 void mg_free(MgHierarchy &H);
 cudaError_t mg_setup(const LaunchCtx &lc, MgHierarchy &H, const double *val_fine, const unsigned char *mask_fine, int64_t *launches);
 cudaError_t mg_vcycle(const LaunchCtx &lc, MgHierarchy &H, const double *r_fine, double *z_fine, int64_t *launches);

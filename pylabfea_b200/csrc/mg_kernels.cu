@@ -73,8 +73,10 @@ __device__ __forceinline__ double stencil_row_dot(int NX, int NY, const RowGeom 
 // ---------------------------------------------------------------------------------------------------------------
 // setup kernels
 // ---------------------------------------------------------------------------------------------------------------
+// joff (all transfer kernels): the coarse grid starts at fine node column joff -- 0 everywhere except between levels 0 and
+// 1 of a strip with a left halo column (distributed solve): that column is a ghost, masked, and not part of the hierarchy
 __global__ void __launch_bounds__(256) mg_mask_inject_kernel(int NXc, int NYc, int NYf, const unsigned char *__restrict__ mask_f,
-                                                             unsigned char *__restrict__ mask_c)
+                                                             unsigned char *__restrict__ mask_c, int joff)
 {
     const int64_t row = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int64_t nc = 2ll * (NXc + 1) * (NYc + 1);
@@ -82,7 +84,7 @@ __global__ void __launch_bounds__(256) mg_mask_inject_kernel(int NXc, int NYc, i
     const int64_t n = row >> 1;
     const int c = (int)(row & 1);
     const int J = (int)(n / (NYc + 1)), K = (int)(n - (int64_t)J * (NYc + 1));
-    const int64_t nf = (int64_t)(2 * J) * (NYf + 1) + 2 * K;
+    const int64_t nf = (int64_t)(2 * J + joff) * (NYf + 1) + 2 * K;
     mask_c[row] = mask_f[2 * nf + c];
 }
 
@@ -113,12 +115,12 @@ __global__ void __launch_bounds__(256) mg_dinv_kernel(int NX, int NY, const floa
 // the coincident fine node (2J, 2K); (dj, dk): stencil offset of the fine column; the fine column at offset
 // o = a + dj from 2J belongs to coarse column J + o/2 (o even) or to J + (o-1)/2 and J + (o+1)/2 with weight 1/2 each.
 __global__ void __launch_bounds__(128) mg_rap_kernel(int NXc, int NYc, const float *__restrict__ val_f,
-                                                     const unsigned char *__restrict__ mask_f, float *__restrict__ val_c)
+                                                     const unsigned char *__restrict__ mask_f, float *__restrict__ val_c, int joff)
 {
     const int64_t row = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int64_t nc = 2ll * (NXc + 1) * (NYc + 1);
     if (row >= nc) return;
-    const int NXf = 2 * NXc, NYf = 2 * NYc, NnYf = NYf + 1;
+    const int NXf = 2 * NXc + joff, NYf = 2 * NYc, NnYf = NYf + 1;
     const int64_t n = row >> 1;
     const int c = (int)(row & 1);
     const int J = (int)(n / (NYc + 1)), K = (int)(n - (int64_t)J * (NYc + 1));
@@ -129,8 +131,8 @@ __global__ void __launch_bounds__(128) mg_rap_kernel(int NXc, int NYc, const flo
         for (int y = 0; y < 3; y++) acc[x][y][0] = acc[x][y][1] = 0.;
 #pragma unroll
     for (int a = -1; a <= 1; a++) {
-        const int fj = 2 * J + a;
-        if (fj < 0 || fj > NXf) continue;
+        const int fj = 2 * J + a + joff;
+        if (fj < joff || fj > NXf) continue;
 #pragma unroll
         for (int b = -1; b <= 1; b++) {
             const int fk = 2 * K + b;
@@ -217,21 +219,21 @@ __global__ void __launch_bounds__(256) mg_residual_kernel(int NX, int NY, const 
 
 // b_c = P^T r_f
 __global__ void __launch_bounds__(256) mg_restrict_kernel(int NXc, int NYc, const double *__restrict__ r_f,
-                                                          const unsigned char *__restrict__ mask_c, double *__restrict__ b_c)
+                                                          const unsigned char *__restrict__ mask_c, double *__restrict__ b_c, int joff)
 {
     const int64_t row = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int64_t nc = 2ll * (NXc + 1) * (NYc + 1);
     if (row >= nc) return;
     if (mask_c[row]) { b_c[row] = 0.; return; }
-    const int NXf = 2 * NXc, NYf = 2 * NYc, NnYf = NYf + 1;
+    const int NXf = 2 * NXc + joff, NYf = 2 * NYc, NnYf = NYf + 1;
     const int64_t n = row >> 1;
     const int c = (int)(row & 1);
     const int J = (int)(n / (NYc + 1)), K = (int)(n - (int64_t)J * (NYc + 1));
     double s = 0.;
 #pragma unroll
     for (int a = -1; a <= 1; a++) {
-        const int fj = 2 * J + a;
-        if (fj < 0 || fj > NXf) continue;
+        const int fj = 2 * J + a + joff;
+        if (fj < joff || fj > NXf) continue;
 #pragma unroll
         for (int b = -1; b <= 1; b++) {
             const int fk = 2 * K + b;
@@ -245,7 +247,7 @@ __global__ void __launch_bounds__(256) mg_restrict_kernel(int NXc, int NYc, cons
 
 // x_f += P x_c (masked fine dofs stay 0)
 __global__ void __launch_bounds__(256) mg_prolong_add_kernel(int NXf, int NYf, const double *__restrict__ x_c,
-                                                             const unsigned char *__restrict__ mask_f, double *__restrict__ x_f)
+                                                             const unsigned char *__restrict__ mask_f, double *__restrict__ x_f, int joff)
 {
     const int64_t row = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int64_t nf = 2ll * (NXf + 1) * (NYf + 1);
@@ -254,7 +256,8 @@ __global__ void __launch_bounds__(256) mg_prolong_add_kernel(int NXf, int NYf, c
     const int NYc = NYf / 2, NnYc = NYc + 1;
     const int64_t n = row >> 1;
     const int c = (int)(row & 1);
-    const int p = (int)(n / (NYf + 1)), q = (int)(n - (int64_t)p * (NYf + 1));
+    const int p = (int)(n / (NYf + 1)) - joff, q = (int)(n - (int64_t)(p + joff) * (NYf + 1));
+    if (p < 0) return;   // ghost column left of the hierarchy (masked anyway)
     const int J0 = p >> 1, K0 = q >> 1;
     const int nj = (p & 1) ? 2 : 1, nk = (q & 1) ? 2 : 1;
     const double w = ((p & 1) ? 0.5 : 1.) * ((q & 1) ? 0.5 : 1.);
@@ -586,9 +589,10 @@ void mg_free(MgHierarchy &H)
     H.d_bar = nullptr;
 }
 
-cudaError_t mg_build(MgHierarchy &H, int NX, int NY)
+cudaError_t mg_build(MgHierarchy &H, int NX, int NY, int j0)
 {
     mg_free(H);
+    H.j0 = j0;
     int nx = NX, ny = NY;
     for (;;) {
         MgLevel L;
@@ -596,8 +600,10 @@ cudaError_t mg_build(MgHierarchy &H, int NX, int NY)
         L.ndof = 2ll * (nx + 1) * (ny + 1);
         L.nnz = 4ll * (3 * nx + 1) * (3 * ny + 1);
         H.lv.push_back(L);
-        if ((nx & 1) || (ny & 1) || nx < 4 || ny < 4 || (int)H.lv.size() >= MG_MAX_LEVELS) break;
-        nx >>= 1; ny >>= 1;
+        // level 1 covers the node columns [j0, NX] of level 0 (j0 = 1: the left halo column of a strip stays outside)
+        const int nxe = H.lv.size() == 1 ? nx - j0 : nx;
+        if ((nxe & 1) || (ny & 1) || nxe < 4 || ny < 4 || (int)H.lv.size() >= MG_MAX_LEVELS) break;
+        nx = nxe >> 1; ny >>= 1;
     }
     for (size_t l = 0; l < H.lv.size(); l++) {
         MgLevel &L = H.lv[l];
@@ -652,8 +658,9 @@ cudaError_t mg_setup(const LaunchCtx &lc, MgHierarchy &H, const double *val_fine
         MgLevel &L = H.lv[l];
         if (l > 0) {
             const MgLevel &F = H.lv[l - 1];
-            mg_mask_inject_kernel<<<grid_for(L.ndof, 256), 256, 0, lc.stream>>>(L.NX, L.NY, F.NY, F.mask, L.mask);
-            mg_rap_kernel<<<grid_for(L.ndof, 128), 128, 0, lc.stream>>>(L.NX, L.NY, F.val, F.mask, L.val);
+            const int joff = l == 1 ? H.j0 : 0;
+            mg_mask_inject_kernel<<<grid_for(L.ndof, 256), 256, 0, lc.stream>>>(L.NX, L.NY, F.NY, F.mask, L.mask, joff);
+            mg_rap_kernel<<<grid_for(L.ndof, 128), 128, 0, lc.stream>>>(L.NX, L.NY, F.val, F.mask, L.val, joff);
             *launches += 2;
         }
         mg_dinv_kernel<<<grid_for(L.ndof, 256), 256, 0, lc.stream>>>(L.NX, L.NY, L.val, L.mask, L.dinv);
@@ -704,7 +711,7 @@ cudaError_t mg_vcycle(const LaunchCtx &lc, MgHierarchy &H, const double *r_fine,
             MgLevel &L = H.lv[l], &C = H.lv[l + 1];
             smooth(L, H.nu, true);
             mg_residual_kernel<<<grid_for(L.ndof, 256), 256, 0, lc.stream>>>(L.NX, L.NY, L.val, L.mask, L.b, L.x, L.r);
-            mg_restrict_kernel<<<grid_for(C.ndof, 256), 256, 0, lc.stream>>>(C.NX, C.NY, L.r, C.mask, C.b);
+            mg_restrict_kernel<<<grid_for(C.ndof, 256), 256, 0, lc.stream>>>(C.NX, C.NY, L.r, C.mask, C.b, l == 0 ? H.j0 : 0);
             *launches += 2;
         }
         CoopArgs A;
@@ -743,7 +750,7 @@ cudaError_t mg_vcycle(const LaunchCtx &lc, MgHierarchy &H, const double *r_fine,
         (*launches)++;
         for (int l = mid - 1; l >= 0; l--) {
             MgLevel &L = H.lv[l], &C = H.lv[l + 1];
-            mg_prolong_add_kernel<<<grid_for(L.ndof, 256), 256, 0, lc.stream>>>(L.NX, L.NY, C.x, L.mask, L.x);
+            mg_prolong_add_kernel<<<grid_for(L.ndof, 256), 256, 0, lc.stream>>>(L.NX, L.NY, C.x, L.mask, L.x, l == 0 ? H.j0 : 0);
             (*launches)++;
             smooth(L, H.nu, false);
         }
@@ -753,7 +760,7 @@ cudaError_t mg_vcycle(const LaunchCtx &lc, MgHierarchy &H, const double *r_fine,
         MgLevel &L = H.lv[l], &C = H.lv[l + 1];
         smooth(L, H.nu, true);
         mg_residual_kernel<<<grid_for(L.ndof, 256), 256, 0, lc.stream>>>(L.NX, L.NY, L.val, L.mask, L.b, L.x, L.r);
-        mg_restrict_kernel<<<grid_for(C.ndof, 256), 256, 0, lc.stream>>>(C.NX, C.NY, L.r, C.mask, C.b);
+        mg_restrict_kernel<<<grid_for(C.ndof, 256), 256, 0, lc.stream>>>(C.NX, C.NY, L.r, C.mask, C.b, l == 0 ? H.j0 : 0);
         *launches += 2;
     }
     if (top < nl) {
@@ -774,7 +781,7 @@ cudaError_t mg_vcycle(const LaunchCtx &lc, MgHierarchy &H, const double *r_fine,
     }
     for (int l = std::min(top, nl - 1) - 1; l >= 0; l--) {
         MgLevel &L = H.lv[l], &C = H.lv[l + 1];
-        mg_prolong_add_kernel<<<grid_for(L.ndof, 256), 256, 0, lc.stream>>>(L.NX, L.NY, C.x, L.mask, L.x);
+        mg_prolong_add_kernel<<<grid_for(L.ndof, 256), 256, 0, lc.stream>>>(L.NX, L.NY, C.x, L.mask, L.x, l == 0 ? H.j0 : 0);
         (*launches)++;
         smooth(L, H.nu, false);
     }

@@ -290,11 +290,12 @@ __global__ void __launch_bounds__(SVCW * 32) sweep_svc_kernel(int64_t n, int NY,
     extern __shared__ double smem[];
     const DevMat &m = c_mat[mid];
     const int np = m.nsv_pad;
-    for (int i = threadIdx.x; i < 6 * np; i += blockDim.x) smem[i] = m.sv[i];
-    for (int i = threadIdx.x; i < np; i += blockDim.x) smem[6 * np + i] = m.dual[i];
+    const int nf = m.svc_nf;
+    for (int i = threadIdx.x; i < nf * np; i += blockDim.x) smem[i] = m.sv[i];
+    for (int i = threadIdx.x; i < np; i += blockDim.x) smem[nf * np + i] = m.dual[i];
     __syncthreads();
     const int lane = threadIdx.x & 31;
-    SvcModel ym(m, smem, smem + 6 * np, lane);
+    SvcModel ym(m, smem, smem + nf * np, lane);
     for (;;) {
         unsigned long long e0 = 0;
         if (lane == 0) e0 = atomicAdd(&st->queue, 1ull);
@@ -376,7 +377,7 @@ cudaError_t launch_sweep(const LaunchCtx &lc, const DevMat *hmats, int nmat, int
         int blocks = lc.sm_count * 2;
         int64_t need = (Nel + SVCW - 1) / SVCW;
         if (blocks > need) blocks = (int)need;
-        sweep_svc_kernel<<<blocks, SVCW * 32, sizeof(double) * 7 * (size_t)hmats[i].nsv_pad, lc.stream>>>(
+        sweep_svc_kernel<<<blocks, SVCW * 32, sizeof(double) * (size_t)(hmats[i].svc_nf + 1) * (size_t)hmats[i].nsv_pad, lc.stream>>>(
             Nel, NY, nit, i, desc, sig, epl, du, elstiff, res_sig, res_depl, fyld, nsteps, has_res, st, stat_first);
         (*launches)++;
     }
@@ -566,11 +567,12 @@ __global__ void __launch_bounds__(SVCW * 32) scf_svc_kernel(int64_t Nel, int NY,
     extern __shared__ double smem[];
     const DevMat &m = c_mat[mid];
     const int np = m.nsv_pad;
-    for (int i = threadIdx.x; i < 6 * np; i += blockDim.x) smem[i] = m.sv[i];
-    for (int i = threadIdx.x; i < np; i += blockDim.x) smem[6 * np + i] = m.dual[i];
+    const int nf = m.svc_nf;
+    for (int i = threadIdx.x; i < nf * np; i += blockDim.x) smem[i] = m.sv[i];
+    for (int i = threadIdx.x; i < np; i += blockDim.x) smem[nf * np + i] = m.dual[i];
     __syncthreads();
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    SvcModel ym(m, smem, smem + 6 * np, lane);
+    SvcModel ym(m, smem, smem + nf * np, lane);
     double ld[6];
 #pragma unroll
     for (int k = 0; k < 6; k++) ld[k] = sld[k];
@@ -589,6 +591,7 @@ __global__ void __launch_bounds__(SVCW * 32) scf_svc_kernel(int64_t Nel, int NY,
 #pragma unroll
             for (int k = 0; k < 6; k++) { s[k] = sig[e * 6 + k]; ep[k] = epl[e * 6 + k]; }
             const double sflow = m.sy + eps_eq6(ep) * m.khard;
+            ym.set_epl(ep);
             double yf0 = ym.yf(s, sflow);
             if (yf0 < PLF_SPLIT_FY0) {
                 yf0 = ym.ml_full_yf(s, sflow, ld);   // 1045-1048
@@ -894,7 +897,7 @@ cudaError_t launch_scf(const LaunchCtx &lc, const DevMat *hmats, int nmat, int64
         int64_t need = (Nel + SVCW - 1) / SVCW;
         if (blocks > need) blocks = (int)need;
         cudaFuncSetAttribute(scf_svc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-        scf_svc_kernel<<<blocks, SVCW * 32, sizeof(double) * 7 * (size_t)hmats[i].nsv_pad, lc.stream>>>(Nel, NY, i, desc, sig, epl, du, elstiff,
+        scf_svc_kernel<<<blocks, SVCW * 32, sizeof(double) * (size_t)(hmats[i].svc_nf + 1) * (size_t)hmats[i].nsv_pad, lc.stream>>>(Nel, NY, i, desc, sig, epl, du, elstiff,
                                                                                                   d_sld, hval, mult);
         (*launches)++;
     }

@@ -288,6 +288,7 @@ extern "C" int plf_set_materials(plf_ctx *ctx, int nmat, const plf_material *mat
         // the sdim = 3 SVC runs on the SVC kernels with another feature map / gradient / equivalent stress (SvcModel, svc_princ)
         d.kind = (m.kind == PLF_MAT_SVC3) ? PLF_MAT_SVC : m.kind;
         d.svc_princ = (m.kind == PLF_MAT_SVC3) ? 1 : 0;
+        d.svc_nf = 6;
         d.tresca = m.tresca;
         d.lhs = m.lhs;
         d.dev_only = m.dev_only;
@@ -323,16 +324,37 @@ extern "C" int plf_set_materials(plf_ctx *ctx, int nmat, const plf_material *mat
         d.bar_exp_int = (m.barlat_exp >= 2. && m.barlat_exp <= 64. && m.barlat_exp == std::floor(m.barlat_exp)) ? (int)m.barlat_exp : 0;
         if (m.kind == PLF_MAT_SVC || m.kind == PLF_MAT_SVC3) {
             if (m.nsv < 1 || !m.svc_sv || !m.svc_dual) return fail(ctx, PLF_EINVAL, "plf_set_materials: SVC table missing");
-            const int np = (m.nsv + 63) / 64 * 64;   // two support vectors per lane and loop trip (SvcModel::decision_x)
-            if ((size_t)np * 7 * sizeof(double) > 227 * 1024)
-                return fail(ctx, PLF_EUNSUPPORTED, "plf_set_materials: SVC table exceeds 227 KB of shared memory (nsv <= 4096)");
-            d.nsv = m.nsv; d.nsv_pad = np;
+            const int np = (m.nsv + 127) / 128 * 128;   // four support vectors per lane and loop trip (svc_decision_lane)
+            const int nfeat = m.svc_nfeat == 0 ? 6 : m.svc_nfeat;
+            if (nfeat != 6 && !(nfeat == 15 && m.kind == PLF_MAT_SVC))
+                return fail(ctx, PLF_EUNSUPPORTED, "plf_set_materials: SVC feature vectors with 6 (stress) or 15 (stress + work "
+                                                   "hardening, sdim = 6) entries are supported; texture features are not");
+            if (nfeat == 15 && !(m.svc_scale_wh > 0.)) return fail(ctx, PLF_EINVAL, "plf_set_materials: svc_scale_wh must be positive");
+            const int nf = nfeat == 15 ? 12 : 6;
+            if ((size_t)np * (nf + 1) * sizeof(double) > 227 * 1024)
+                return fail(ctx, PLF_EUNSUPPORTED, "plf_set_materials: SVC table exceeds 227 KB of shared memory (" +
+                                                       std::to_string(227 * 1024 / (8 * (nf + 1)) / 128 * 128) + " support vectors at most)");
+            d.nsv = m.nsv; d.nsv_pad = np; d.svc_nf = nf;
             d.gamma = m.svc_gamma; d.rho = m.svc_rho; d.scale_seq = m.svc_scale_seq; d.inv_scale_seq = 1. / m.svc_scale_seq;
-            d.khard = 0.;   // material.py:812-814: the SVC gradient resets khard (no work-hardening features)
-            std::vector<double> soa(6 * (size_t)np, 0.), dual(np, 0.);
+            if (nf == 12) {
+                d.inv_scale_wh = 1. / m.svc_scale_wh;
+                d.khard_fac = m.svc_scale_seq / m.svc_scale_wh;
+                // khard stays as the host set it: the value Material.khard has before the first gradient evaluation
+            } else {
+                d.khard = 0.;   // material.py:812-814: the SVC gradient resets khard (no work-hardening features)
+            }
+            std::vector<double> soa((size_t)nf * np, 0.), dual(np, 0.);
             for (int s = 0; s < m.nsv; s++) {
-                for (int k = 0; k < 6; k++) soa[(size_t)k * np + s] = m.svc_sv[6 * (size_t)s + k];
-                dual[s] = m.svc_dual[s];
+                for (int k = 0; k < nf; k++) soa[(size_t)k * np + s] = m.svc_sv[(size_t)nfeat * s + k];
+                double fold = 1.;
+                if (nfeat == 15) {
+                    // features 12..14 (accumulated strain, maximum stress, flag) are always 0 here: their share of
+                    // exp(-gamma |x - sv|^2) is a constant factor of the support vector's weight
+                    double r = 0.;
+                    for (int k = 12; k < 15; k++) r += m.svc_sv[(size_t)nfeat * s + k] * m.svc_sv[(size_t)nfeat * s + k];
+                    fold = std::exp(-m.svc_gamma * r);
+                }
+                dual[s] = m.svc_dual[s] * fold;
             }
             // padded support vectors: dual = 0 so they add exactly 0 to every sum
             int rc;

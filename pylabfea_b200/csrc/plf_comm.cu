@@ -4,6 +4,7 @@
 #include <cstring>
 #include <string>
 
+#include "mg.h"
 #include "plf_comm.h"
 #include "plf_model.h"
 #include "plfb200.h"
@@ -29,6 +30,7 @@ struct NcclApi {
     ncclResult_t (*AllReduce)(const void *, void *, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
     ncclResult_t (*Send)(const void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
     ncclResult_t (*Recv)(void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*Broadcast)(const void *, void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
     ncclResult_t (*GroupStart)() = nullptr;
     ncclResult_t (*GroupEnd)() = nullptr;
     const char *(*GetErrorString)(ncclResult_t) = nullptr;
@@ -66,6 +68,7 @@ int comm_load()
     a.AllReduce = (decltype(a.AllReduce))sym("ncclAllReduce");
     a.Send = (decltype(a.Send))sym("ncclSend");
     a.Recv = (decltype(a.Recv))sym("ncclRecv");
+    a.Broadcast = (decltype(a.Broadcast))sym("ncclBroadcast");
     a.GroupStart = (decltype(a.GroupStart))sym("ncclGroupStart");
     a.GroupEnd = (decltype(a.GroupEnd))sym("ncclGroupEnd");
     a.GetErrorString = (decltype(a.GetErrorString))sym("ncclGetErrorString");
@@ -115,6 +118,19 @@ int comm_allreduce_op(Comm &c, double *dbuf, int count, int op, cudaStream_t s)
 {
     const ncclRedOp_t o = op == 1 ? ncclMax : (op == 2 ? ncclMin : ncclSum);
     NC(g_nccl.AllReduce(dbuf, dbuf, (size_t)count, ncclDouble, o, (ncclComm_t)c.nccl, s), "ncclAllReduce");
+    return 0;
+}
+
+// Every rank contributes one contiguous range of doubles to the same global array on all ranks: rank r's range is
+// [goff[r], goff[r] + cnt[r]) of `global`; its own data sits at `mine`.  One broadcast per rank, grouped.
+int comm_gather_ranges(Comm &c, const double *mine, double *global, const int64_t *goff, const int64_t *cnt, cudaStream_t s)
+{
+    ncclComm_t comm = (ncclComm_t)c.nccl;
+    NC(g_nccl.GroupStart(), "ncclGroupStart");
+    for (int r = 0; r < c.world; r++)
+        NC(g_nccl.Broadcast(r == c.rank ? (const void *)mine : (const void *)(global + goff[r]), global + goff[r], (size_t)cnt[r],
+                            ncclDouble, r, comm, s), "ncclBroadcast");
+    NC(g_nccl.GroupEnd(), "ncclGroupEnd");
     return 0;
 }
 
@@ -178,6 +194,20 @@ extern "C" int plf_comm_set_strip(plf_ctx *ctx, int own_first, int own_end)
     ctx->comm->own_first = own_first;
     ctx->comm->own_end = own_end;
     ctx->comm->strip_set = true;
+    // The preconditioner of the distributed CG is one V-cycle per strip on the node columns the rank owns (+ its right
+    // ghost column, masked): with a left halo column the hierarchy starts at node column 1, which keeps the number of
+    // element columns under it at N / world (coarsenable) instead of N / world + 1.  All ranks must take the same code
+    // path (the multigrid and the Jacobi variant issue different collectives): agree on it here.
+    if (ctx->mg) {
+        cudaError_t e = mg_build(*ctx->mg, ctx->NX, ctx->NY, own_first);
+        if (e != cudaSuccess) return fail(ctx, PLF_ECUDA, std::string("plf_comm_set_strip: ") + cudaGetErrorString(e));
+        model_apply_mg_options(ctx);
+        ctx->mg_K_serial = -1;
+    }
+    double have_mg = (ctx->mg && ctx->mg->levels() >= 2) ? 1. : 0.;
+    int rc = comm_host_allreduce(ctx, &have_mg, 1, 2);
+    if (rc != PLF_OK) return rc;
+    ctx->comm->mg_all = have_mg > 0.5;
     return PLF_OK;
 }
 
@@ -207,6 +237,19 @@ int comm_host_allreduce(plf_ctx *ctx, double *vals, int n, int op)
     if (comm_allreduce_op(*ctx->comm, d, n, op, ctx->stream)) return fail(ctx, PLF_ECUDA, std::string("allreduce: ") + comm_error());
     CKC(cudaMemcpyAsync(vals, d, n * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
     CKC(cudaStreamSynchronize(ctx->stream));
+    return PLF_OK;
+}
+
+extern "C" int plf_comm_set_replica(plf_ctx *ctx, plf_ctx *global_ctx)
+{
+    if (!ctx) return PLF_EINVAL;
+    if (!global_ctx) { ctx->replica = nullptr; return PLF_OK; }
+    if (!ctx->comm || !ctx->comm->active() || !ctx->comm->global_set)
+        return fail(ctx, PLF_ESTATE, "plf_comm_set_replica: call plf_comm_set_partition first");
+    if (!global_ctx->mesh_ready || global_ctx->NX != ctx->comm->NX_global || global_ctx->NY != ctx->NY || global_ctx->device != ctx->device ||
+        global_ctx->planestress != ctx->planestress)
+        return fail(ctx, PLF_EINVAL, "plf_comm_set_replica: the second context must hold the GLOBAL mesh on the same device");
+    ctx->replica = global_ctx;
     return PLF_OK;
 }
 

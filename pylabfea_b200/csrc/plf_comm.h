@@ -3,6 +3,7 @@
 // dlopen on first use so that the library itself has no link-time dependency on it (single-GPU users, CPU build check).
 #pragma once
 #include <cuda_runtime.h>
+#include <stdint.h>
 
 namespace plf {
 
@@ -12,6 +13,7 @@ struct Comm {
     // owned node columns [own_first, own_end) of the local mesh; a ghost column is the one column outside on either side
     int own_first = 0, own_end = 0;
     bool strip_set = false;
+    bool mg_all = false;   // every rank's strip has a multigrid hierarchy (decided together in plf_comm_set_strip)
     // position of the strip in the global mesh (plf_comm_set_partition): needed by the load-increment controller for the
     // boundary conditions (edges, force shares, node sets) and the global averages
     bool global_set = false;
@@ -32,6 +34,7 @@ int comm_allreduce_op(Comm &c, double *dbuf, int count, int op /* 0 sum, 1 max, 
 // vec: nodal vector of the local (NX+1) x (NY+1) node grid, 2 dofs per node.  Sends the first / last owned node column to
 // the left / right neighbour and receives their last / first owned column into the ghost columns.
 int comm_halo_exchange(Comm &c, double *vec, int NX, int NY, cudaStream_t s);
+int comm_gather_ranges(Comm &c, const double *mine, double *global, const int64_t *goff, const int64_t *cnt, cudaStream_t s);
 const char *comm_error();
 
 }   // namespace plf

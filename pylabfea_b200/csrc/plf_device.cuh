@@ -32,7 +32,9 @@ struct DevMat {
     const double *dual;  // device, [nsv_pad] (zero padded)
     double bar_m1[36], bar_m2[36], bar_exp;
     int32_t bar_exp_int;   // barlat_exp when it is a whole number in [2, 64] (Yld2004-18p: 6 for bcc, 8 for fcc), else 0
-    int32_t pad2_;
+    int32_t svc_nf;        // feature columns of the device SV table: 6 (stress), 12 (stress + plastic strain: work-hardening SVC)
+    double inv_scale_wh;   // 1 / scale_wh (material.py:2343)
+    double khard_fac;      // scale_seq / scale_wh: khard = max(0, -sum_k dK/dx[6 + k] * khard_fac) (material.py:808-814)
 };
 
 // symmetric 6x6 packing: (i<=j) -> index
@@ -270,6 +272,7 @@ struct HillModel {
     static constexpr bool is_ml = false;
     const DevMat &m;
     __device__ explicit HillModel(const DevMat &mm) : m(mm) {}
+    __device__ __forceinline__ void set_epl(const double *) const {}
     __device__ __forceinline__ double khard() const { return m.khard; }
     __device__ __forceinline__ double seq(const double *s) const
     {
@@ -313,6 +316,7 @@ struct HillPrincModel {
     static constexpr bool is_ml = false;
     const DevMat &m;
     __device__ explicit HillPrincModel(const DevMat &mm) : m(mm) {}
+    __device__ __forceinline__ void set_epl(const double *) const {}
     __device__ __forceinline__ double khard() const { return m.khard; }
     __device__ __forceinline__ double seq_sp(const double *sp, const double *nrm) const
     {
@@ -352,6 +356,7 @@ struct BarlatModel {
     static constexpr bool is_ml = false;
     const DevMat &m;
     __device__ explicit BarlatModel(const DevMat &mm) : m(mm) {}
+    __device__ __forceinline__ void set_epl(const double *) const {}
     __device__ __forceinline__ double khard() const { return m.khard; }
     __device__ __forceinline__ double seq(const double *s) const { return barlat_seq(m, s); }
     __device__ __forceinline__ double yf(const double *s, double sflow) const { return barlat_seq(m, s) - sflow; }
@@ -407,16 +412,104 @@ __device__ __forceinline__ void warp_append2(bool pred, bool back, int32_t item,
     }
 }
 
+// exp(x) for x <= 0 with an instruction-level-parallel evaluation: magic-number rounding of x log2(e), two-constant
+// Cody-Waite reduction, degree-13 Taylor polynomial in Estrin form (dependency depth 4 instead of the 11 of a Horner
+// chain), exponent add.  Relative error < 3e-16 on |f| <= ln(2)/2; arguments below -700 return 0 (true value < 1e-304).
+__device__ __forceinline__ double exp_neg(double x)
+{
+    const double t = fma(x, 1.4426950408889634, 6755399441055744.0);
+    const int n = __double2loint(t);
+    const double nd = t - 6755399441055744.0;
+    double f = fma(nd, -6.93147180369123816490e-01, x);
+    f = fma(nd, -1.90821492927058770002e-10, f);
+    const double f2 = f * f, f4 = f2 * f2, f8 = f4 * f4;
+    const double a0 = fma(f, 1., 1.);
+    const double a1 = fma(f, 1.6666666666666666e-01, 0.5);
+    const double a2 = fma(f, 8.3333333333333332e-03, 4.1666666666666664e-02);
+    const double a3 = fma(f, 1.9841269841269841e-04, 1.3888888888888889e-03);
+    const double a4 = fma(f, 2.7557319223985893e-06, 2.4801587301587302e-05);
+    const double a5 = fma(f, 2.5052108385441720e-08, 2.7557319223985888e-07);
+    const double a6 = fma(f, 1.6059043836821613e-10, 2.0876756987868100e-09);
+    const double b0 = fma(a1, f2, a0), b1 = fma(a3, f2, a2), b2 = fma(a5, f2, a4);
+    const double d0 = fma(b1, f4, b0), d1 = fma(a6, f4, b2);
+    const double p = fma(d1, f8, d0);
+    const double r = __longlong_as_double(__double_as_longlong(p) + ((long long)n << 52));
+    return x < -700. ? 0. : r;
+}
+
+// sum_i dual_i exp(-gamma |x - sv_i|^2) over the support vectors of this lane (i = lane, lane + 32, ...), four support
+// vectors per trip: four independent distance / exp chains in flight.  Out of line on purpose: inside the return-mapping
+// core the loop competed with ~200 live registers and was scheduled as one dependent chain (ncu: 15 % of the FP64 pipe,
+// stall reason "wait"); as a function of its own it gets its own register allocation.  np is a multiple of 128.
+template <int NF>
+static __device__ __noinline__ double svc_decision_lane(const double *__restrict__ s_sv, const double *__restrict__ s_dual, int np,
+                                                       double gamma, const double *__restrict__ xin, int lane)
+{
+    double x[NF];
+#pragma unroll
+    for (int c = 0; c < NF; c++) x[c] = xin[c];
+    double acc[4] = {0., 0., 0., 0.};
+    const double ng = -gamma;
+    for (int i = lane; i < np; i += 128) {
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            const int k = i + 32 * u;
+            double q0 = 0., q1 = 0., q2 = 0.;
+#pragma unroll
+            for (int c = 0; c < NF; c += 3) {
+                const double t0 = x[c] - s_sv[c * np + k], t1 = x[c + 1] - s_sv[(c + 1) * np + k], t2 = x[c + 2] - s_sv[(c + 2) * np + k];
+                q0 = fma(t0, t0, q0); q1 = fma(t1, t1, q1); q2 = fma(t2, t2, q2);
+            }
+            acc[u] = fma(s_dual[k], exp_neg(ng * ((q0 + q1) + q2)), acc[u]);
+        }
+    }
+    return (acc[0] + acc[1]) + (acc[2] + acc[3]);
+}
+
+// the same loop for the gradient: g_c = sum_i dual_i exp(-gamma r_i) (-2 gamma) (x_c - sv_ic), two support vectors per trip
+template <int NF>
+static __device__ __noinline__ void svc_gradient_lane(const double *__restrict__ s_sv, const double *__restrict__ s_dual, int np,
+                                                     double gamma, const double *__restrict__ xin, int lane, double *g)
+{
+    double x[NF], ga[NF], gb[NF];
+#pragma unroll
+    for (int c = 0; c < NF; c++) { x[c] = xin[c]; ga[c] = 0.; gb[c] = 0.; }
+    const double ng = -gamma, m2g = -2. * gamma;
+    for (int i = lane; i < np; i += 64) {
+        const int k = i + 32;
+        double a[NF], b[NF], ra0 = 0., ra1 = 0., rb0 = 0., rb1 = 0.;
+#pragma unroll
+        for (int c = 0; c < NF; c += 2) {
+            a[c] = x[c] - s_sv[c * np + i]; a[c + 1] = x[c + 1] - s_sv[(c + 1) * np + i];
+            b[c] = x[c] - s_sv[c * np + k]; b[c + 1] = x[c + 1] - s_sv[(c + 1) * np + k];
+            ra0 = fma(a[c], a[c], ra0); ra1 = fma(a[c + 1], a[c + 1], ra1);
+            rb0 = fma(b[c], b[c], rb0); rb1 = fma(b[c + 1], b[c + 1], rb1);
+        }
+        const double wa = s_dual[i] * exp_neg(ng * (ra0 + ra1)) * m2g, wb = s_dual[k] * exp_neg(ng * (rb0 + rb1)) * m2g;
+#pragma unroll
+        for (int c = 0; c < NF; c++) { ga[c] = fma(wa, a[c], ga[c]); gb[c] = fma(wb, b[c], gb[c]); }
+    }
+#pragma unroll
+    for (int c = 0; c < NF; c++) g[c] = ga[c] + gb[c];
+}
+
 struct SvcModel {
     static constexpr bool is_ml = true;
     const DevMat &m;
-    const double *s_sv;    // shared, [6][nsv_pad]
+    const double *s_sv;    // shared, [svc_nf][nsv_pad]
     const double *s_dual;  // shared, [nsv_pad]
     int lane;
+    // Work-hardening SVC (material.py:2342-2346, 808-814): the plastic strain is part of the feature vector, and every
+    // gradient evaluation sets Material.khard from the plastic-strain part of the gradient.  The reference keeps khard on the
+    // Material object (one value for all elements, left behind by whichever element was visited last); here every element
+    // starts from the khard the host set and carries its own value through its return mapping.
+    mutable const double *cur_epl;   // plastic strain the next yield-function / gradient evaluation refers to
+    mutable double kh;
     __device__ SvcModel(const DevMat &mm, const double *sv, const double *dual, int l)
-        : m(mm), s_sv(sv), s_dual(dual), lane(l) {}
+        : m(mm), s_sv(sv), s_dual(dual), lane(l), cur_epl(nullptr), kh(mm.svc_nf == 12 ? mm.khard : 0.) {}
+    __device__ __forceinline__ void set_epl(const double *e) const { cur_epl = e; }
     // material.py:812-814: without work-hardening features every gradient call resets khard to 0
-    __device__ __forceinline__ double khard() const { return 0.; }
+    __device__ __forceinline__ double khard() const { return kh; }
     // sdim = 3 (svc_princ): calc_seq is the 3-parameter form on the ordered principal stresses (material.py:663-673)
     __device__ __forceinline__ double seq(const double *s) const { return m.svc_princ ? HillPrincModel(m).seq(s) : hill_seq(m, s); }
 
@@ -449,30 +542,23 @@ struct SvcModel {
         double p = m.dev_only ? (s[0] + s[1] + s[2]) / 3. : 0.;
         x[0] = (s[0] - p) / m.scale_seq; x[1] = (s[1] - p) / m.scale_seq; x[2] = (s[2] - p) / m.scale_seq;
         x[3] = s[3] / m.scale_seq; x[4] = s[4] / m.scale_seq; x[5] = s[5] / m.scale_seq;
+        if (m.svc_nf == 12) {
+            // work-hardening features (2342-2346): epl / scale_wh; accumulated strain, maximum stress and the flag are 0 on
+            // this path (the defaults of calc_yf, 348-350) and are folded into the dual coefficients on the host
+#pragma unroll
+            for (int k = 0; k < 6; k++) x[6 + k] = cur_epl ? cur_epl[k] * m.inv_scale_wh : 0.;
+        }
     }
     // decision_function (material.py:405): sum_i dual_i exp(-gamma |x - sv_i|^2) + rho
     __device__ __forceinline__ double decision_x(const double *x) const
     {
-        // two support vectors per lane and trip (nsv_pad is a multiple of 64): two independent distance / exp / fma chains
-        // keep the FP64 pipe busy at 4 warps per scheduler (ncu of the one-chain loop at 2 warps: 15 % of the pipe, "wait")
-        const int np = m.nsv_pad;
-        double f0 = 0., f1 = 0.;
-        for (int i = lane; i < np; i += 64) {
-            double r0 = 0., r1 = 0.;
-#pragma unroll
-            for (int k = 0; k < 6; k++) {
-                const double t0 = x[k] - s_sv[k * np + i], t1 = x[k] - s_sv[k * np + i + 32];
-                r0 = fma(t0, t0, r0);
-                r1 = fma(t1, t1, r1);
-            }
-            f0 = fma(s_dual[i], exp(-m.gamma * r0), f0);
-            f1 = fma(s_dual[i + 32], exp(-m.gamma * r1), f1);
-        }
-        return warp_sum(f0 + f1) + m.rho;
+        const double part = (m.svc_nf == 12) ? svc_decision_lane<12>(s_sv, s_dual, m.nsv_pad, m.gamma, x, lane)
+                                             : svc_decision_lane<6>(s_sv, s_dual, m.nsv_pad, m.gamma, x, lane);
+        return warp_sum(part) + m.rho;
     }
     __device__ __forceinline__ double yf(const double *s, double /*sflow*/) const
     {
-        double x[6];
+        double x[12];
         features(s, x);
         return decision_x(x);
     }
@@ -480,19 +566,16 @@ struct SvcModel {
     __device__ __forceinline__ void fgrad(const double *s, double *a) const
     {
         if (m.svc_princ) { fgrad_princ(s, a); return; }
-        const int np = m.nsv_pad;
-        double x[6], g[6] = {0., 0., 0., 0., 0., 0.};
+        double x[12], g[12];
         features(s, x);
-        for (int i = lane; i < np; i += 32) {
-            double hv[6], r = 0.;
+        if (m.svc_nf == 12) {
+            svc_gradient_lane<12>(s_sv, s_dual, m.nsv_pad, m.gamma, x, lane, g);
+            double hk = 0.;
 #pragma unroll
-            for (int k = 0; k < 6; k++) {
-                hv[k] = x[k] - s_sv[k * np + i];
-                r = fma(hv[k], hv[k], r);
-            }
-            double w = s_dual[i] * exp(-m.gamma * r) * (-2. * m.gamma);
-#pragma unroll
-            for (int k = 0; k < 6; k++) g[k] = fma(w, hv[k], g[k]);
+            for (int k = 0; k < 6; k++) hk -= warp_sum(g[6 + k]) * m.khard_fac;   // 808-809
+            kh = fmax(hk, 0.);                                                    // 812-814: no strain softening
+        } else {
+            svc_gradient_lane<6>(s_sv, s_dual, m.nsv_pad, m.gamma, x, lane, g);
         }
 #pragma unroll
         for (int k = 0; k < 6; k++) a[k] = warp_sum(g[k]) / m.scale_seq;
@@ -535,9 +618,11 @@ struct SvcModel {
     // find_yloc_scalar (material.py:547-574)
     __device__ __forceinline__ double yloc(double xs, const double *xu) const
     {
-        double x[6];
+        double x[12];
 #pragma unroll
         for (int k = 0; k < 6; k++) x[k] = xs * xu[k];
+#pragma unroll
+        for (int k = 0; k < 6; k++) x[6 + k] = (m.svc_nf == 12 && cur_epl) ? cur_epl[k] * m.inv_scale_wh : 0.;
         return decision_x(x);
     }
 
@@ -705,6 +790,7 @@ __device__ __forceinline__ int response_core(const Model &ym, const DevMat &m, d
     matvec6(CV, deps, dsig);   // 244
 #pragma unroll
     for (int k = 0; k < 6; k++) st[k] = sig[k] + dsig[k];
+    ym.set_epl(epl);   // yield function and gradient refer to the plastic strain at the start of the step unless stated otherwise
     double fy1 = ym.full_yf(st, sflow0);   // 249-252
     nsteps_out = 0;
     if (fy1 < toler) {   // 253-256 purely elastic
@@ -724,7 +810,11 @@ __device__ __forceinline__ int response_core(const Model &ym, const DevMat &m, d
     if (fy0 < PLF_SPLIT_FY0) {         // 260-270
         split = true;
         // ML: distance to the yield surface, called without epl (263-265): sflow = sy
-        if (Model::is_ml) fy0 = ym.full_yf(sig, m.sy);
+        if (Model::is_ml) {
+            ym.set_epl(nullptr);   // 265: ML_full_yf(sig) without epl
+            fy0 = ym.full_yf(sig, m.sy);
+            ym.set_epl(epl);
+        }
         st_scal += fy0 / ym.seq(dsig);
         double del[6], t[6];
 #pragma unroll
@@ -746,7 +836,6 @@ __device__ __forceinline__ int response_core(const Model &ym, const DevMat &m, d
     for (int k = 0; k < 21; k++) W[k] = 0.;
     double ddepl[6];
     bool corrected = false;
-    const double kh = ym.khard();
 
     auto plastic_step = [&](double *s, const double *dr, bool commit) -> double {
         double cd[6], a[6], ca[6], eplt[6];
@@ -756,7 +845,7 @@ __device__ __forceinline__ int response_core(const Model &ym, const DevMat &m, d
         double yfun = ym.yf(st, sflow0);   // epl_dot 1031
         ym.fgrad(s, a);                    // calc_fgrad (shared by epl_dot 1050 and C_tan 1082)
         matvec6(CV, a, ca);
-        double hh = kh, acd = 0., cadr = 0.;
+        double hh = ym.khard(), acd = 0., cadr = 0.;   // the hardening rate in effect after this gradient evaluation
 #pragma unroll
         for (int k = 0; k < 6; k++) {
             hh += a[k] * ca[k];
@@ -773,7 +862,9 @@ __device__ __forceinline__ int response_core(const Model &ym, const DevMat &m, d
             st[k] = s[k] + (cd[k] - ca[k] * q);   // sig + t_stiff @ deps_r
         }
         double sfl = m.sy + eps_eq6(eplt) * ym.khard();
+        ym.set_epl(eplt);   // 283, 304: the yield function at the end of the step sees the updated plastic strain
         double fy = ym.full_yf(st, sfl);
+        ym.set_epl(epl);
         if (!commit) return fy;
 #pragma unroll
         for (int k = 0; k < 6; k++) s[k] = st[k];
@@ -798,7 +889,9 @@ __device__ __forceinline__ int response_core(const Model &ym, const DevMat &m, d
             W[sym_idx(0, 0)] += x[0]; W[sym_idx(0, 1)] += x[5]; W[sym_idx(0, 2)] += x[4];
             W[sym_idx(1, 1)] += x[1]; W[sym_idx(1, 2)] += x[3]; W[sym_idx(2, 2)] += x[2];
             sfl = m.sy + eps_eq6(eplt) * ym.khard();
+            ym.set_epl(eplt);
             fy = ym.full_yf(s, sfl);
+            ym.set_epl(epl);
         }
 #pragma unroll
         for (int i = 0; i < 6; i++)

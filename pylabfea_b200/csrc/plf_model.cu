@@ -398,7 +398,13 @@ extern "C" int plf_step_host_packed(plf_ctx *ctx, plf_batch *b, const double *si
         CK(cudaStreamCreateWithFlags(&ctx->s_out, cudaStreamNonBlocking));
     }
     const int NX = ctx->NX, NY = ctx->NY;
-    const int nchunk = std::max(1, std::min(NX, 8));
+    // chunks of element columns must start on a bitmap word (32 elements): the largest chunk count <= 8 that does, else one
+    int nchunk = 1;
+    for (int c = std::min(NX, 8); c > 1; c--) {
+        bool ok = true;
+        for (int q = 1; q < c && ok; q++) ok = (((int64_t)NX * q / c) * NY) % 32 == 0;
+        if (ok) { nchunk = c; break; }
+    }
     while ((int)ctx->ev_step.size() < 2 * nchunk + 1) {
         cudaEvent_t e;
         CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
@@ -431,10 +437,6 @@ extern "C" int plf_step_host_packed(plf_ctx *ctx, plf_batch *b, const double *si
         k.na = k.ja;
         k.nb = (c == nchunk - 1) ? NX + 1 : k.jb;
     }
-    // chunk boundaries must fall on bitmap words and on blocks of the pack kernels: the chunk-local compaction writes whole
-    // 32-bit words; elements are numbered column by column, so a chunk starts at a multiple of NY
-    for (int c = 0; c < nchunk; c++)
-        if (ch[c].e0 % 32 != 0) return fail(ctx, PLF_EUNSUPPORTED, "plf_step_host_packed: NY * (NX / 8) must be a multiple of 32");
     for (int c = 0; c < nchunk; c++) {   // all uploads
         const Chunk &k = ch[c];
         const size_t o6 = 6 * (size_t)k.e0, n6 = 6 * (size_t)k.ne * sizeof(double);
@@ -730,7 +732,7 @@ int model_solve_device_bc(plf_ctx *ctx, double rtol, int max_iter, int *iters, d
     double rr = 0.;
     double *x = ctx->d_du;   // CG iterate lives in du; fixed dofs are merged at the end
     if (dist) {
-        const bool dmg = ctx->solver_mg && ctx->mg && ctx->mg->levels() >= 2;
+        const bool dmg = ctx->solver_mg && ctx->comm->mg_all;   // the same on every rank
         const bool fresh = dmg && ctx->skip_unchanged && ctx->mg_K_serial == ctx->K_serial && ctx->mg_mask_epoch == ctx->mask_epoch;
         if (dmg) { ctx->mg_K_serial = ctx->K_serial; ctx->mg_mask_epoch = ctx->mask_epoch; }
         cudaError_t ce = launch_cg_dist(lc, *ctx->comm, ctx->Ndof, ctx->d_rowptr, ctx->d_col, ctx->d_val, mask, ctx->d_b, x, ctx->d_r,

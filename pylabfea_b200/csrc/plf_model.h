@@ -104,6 +104,7 @@ struct plf_ctx {
     // sequence) re-uploads when the banks hold another context's tables or stale ones.
     bool tables_dirty = true;
     plf_solve_state *solve = nullptr;   // set by plf_solve_begin
+    plf_ctx *replica = nullptr;         // plf_comm_set_replica: context holding the GLOBAL mesh, solves the gathered system (not owned)
     // change tracking, so that an unchanged K is neither re-assembled nor re-coarsened: tangent_epoch moves whenever
     // element tangents change (plf_set_tangent, a sweep that replaced one), K_serial with every assembly, mask_epoch
     // with every new set of boundary-condition vectors

@@ -307,7 +307,52 @@ extern "C" int plf_solve_begin(plf_ctx *ctx, const plf_bc *bc, int reset)
     if (std::sqrt(s[0] * s[0] + s[1] * s[1] + s[5] * s[5]) < 1.e-3) s[0] = 1.;   // the reference warns here (1255-1258)
     int rc;
     if (reset && (rc = model_reset_state(ctx)) != PLF_OK) return rc;
+    if (ctx->replica) {
+        // the global solver context gets the same boundary description (its vectors are built on the global node grid)
+        plf_ctx *g = ctx->replica;
+        if (!g->solve) g->solve = new plf_solve_state();
+        g->solve->bc = S.bc;
+        g->solve->noset = S.noset;
+        g->solve->bc_built = false;
+        g->solve->nonlin = S.nonlin;
+    }
     return plf_setupK(ctx);   // 1242
+}
+
+// replicated solve (plf_comm_set_replica): gather the owned K rows of every rank into the global context, solve there,
+// bring the strip's part of du back
+static int solve_replicated(plf_ctx *ctx, const double *dr, const double *dt, const double *dn, double rtol, int max_iter, int *it,
+                            double *rr, plf_increment_report *rep)
+{
+    plf_ctx *g = ctx->replica;
+    Comm &c = *ctx->comm;
+    const int NY = ctx->NY, NXg = c.NX_global;
+    int64_t goff[64], cnt[64];
+    if (c.world > 64) return fail(ctx, PLF_EUNSUPPORTED, "replicated solve: at most 64 ranks");
+    for (int r = 0; r < c.world; r++) {   // owned node columns of rank r: [NXg r / world, NXg (r+1) / world) (+ the last column)
+        const int a = (int)((int64_t)NXg * r / c.world), b = (int)((int64_t)NXg * (r + 1) / c.world) + (r == c.world - 1 ? 1 : 0);
+        goff[r] = csr_column_start(NXg, NY, a);
+        cnt[r] = csr_column_start(NXg, NY, b) - goff[r];
+    }
+    const int64_t lo = csr_column_start(ctx->NX, NY, c.own_first);
+    if (csr_column_start(ctx->NX, NY, c.own_end) - lo != cnt[c.rank])
+        return fail(ctx, PLF_ESTATE, "replicated solve: the strip does not match the global partition");
+    CK(cudaSetDevice(ctx->device));
+    // the global context works on its own stream: order it behind this context's assembly and ahead of what follows
+    CK(cudaStreamSynchronize(ctx->stream));
+    if (comm_gather_ranges(c, ctx->d_val + lo, g->d_val, goff, cnt, g->stream))
+        return fail(ctx, PLF_ECUDA, std::string("replicated solve: ") + comm_error());
+    g->K_ready = true;
+    g->K_tangent_epoch = 0;
+    g->K_serial++;
+    int rc = build_bc_vectors(g, dr, dt, dn, rep);
+    if (rc != PLF_OK) { ctx->err = g->err; return rc; }
+    rc = model_solve_device_bc(g, rtol, max_iter, it, rr);
+    if (rc != PLF_OK) { ctx->err = g->err; return rc; }
+    CK(cudaMemcpyAsync(ctx->d_du, g->d_du + 2 * (size_t)(NY + 1) * (size_t)c.first_col_global, (size_t)ctx->Ndof * sizeof(double),
+                       cudaMemcpyDeviceToDevice, g->stream));
+    CK(cudaStreamSynchronize(g->stream));
+    return PLF_OK;
 }
 
 // Model.bcval sums of the four edges, combined over the ranks of a partition
@@ -367,9 +412,14 @@ extern "C" int plf_load_increment(plf_ctx *ctx, plf_load_state *st, int min_step
     int rc, it = 0;
     double rr = 0.;
     auto solve = [&](int slot) -> int {
-        int r = build_bc_vectors(ctx, right.step, top.step, node.step, rep);
-        if (r != PLF_OK) return r;
-        r = model_solve_device_bc(ctx, rtol, max_iter, &it, &rr);
+        int r;
+        if (ctx->replica) {
+            r = solve_replicated(ctx, right.step, top.step, node.step, rtol, max_iter, &it, &rr, rep);
+        } else {
+            r = build_bc_vectors(ctx, right.step, top.step, node.step, rep);
+            if (r != PLF_OK) return r;
+            r = model_solve_device_bc(ctx, rtol, max_iter, &it, &rr);
+        }
         rep->solves++;
         rep->cg_iterations += it;
         rep->pass_cg_iters[slot] = it;

@@ -195,16 +195,13 @@ __device__ __forceinline__ void passA_tile(int64_t n, int64_t tile, double *s_in
                         for (int k = 0; k < 3; k++)
                             reinterpret_cast<double2 *>(depl_out + e * 6)[k] = make_double2(dp[2 * k], dp[2 * k + 1]);
                     if (ctan) {
-                        double w[6];
-#pragma unroll
-                        for (int i = 0; i < 6; i++) w[i] = ca[i] * tw;
 #pragma unroll
                         for (int g = 0; g < 9; g++) {
                             double v[4];
 #pragma unroll
                             for (int q = 0; q < 4; q++) {
                                 const int idx = 4 * g + q, i = idx / 6, j = idx - 6 * i;
-                                v[q] = m.CV[idx] * tc - w[i] * ca[j];
+                                v[q] = m.CV[idx] * tc - (ca[i] * ca[j]) * tw;   // (ca_i ca_j) commutes: exactly symmetric like the reference's kron
                             }
                             st256(ctan + e * 36 + 4 * g, v[0], v[1], v[2], v[3]);
                         }
@@ -214,11 +211,14 @@ __device__ __forceinline__ void passA_tile(int64_t n, int64_t tile, double *s_in
                     for (int k = 0; k < 6; k++) { s_sig[6 * tid + k] = s[k]; s_epl[6 * tid + k] = dp[k]; }
                     double *o = s_ct + CT_STRIDE * tid;
 #pragma unroll
-                    for (int i = 0; i < 6; i++) {
-                        const double wi = ca[i] * tw;
+                    for (int i = 0; i < 6; i++)
 #pragma unroll
-                        for (int j = 0; j < 6; j++) o[6 * i + j] = m.CV[6 * i + j] * tc - wi * ca[j];
-                    }
+                        for (int j = i; j < 6; j++) {
+                            // ca_i ca_j first: the dyad is exactly symmetric, as np.kron(ca, ca) is in C_tan (material.py:1083-1085)
+                            const double pw = (ca[i] * ca[j]) * tw;
+                            o[6 * i + j] = m.CV[6 * i + j] * tc - pw;
+                            if (j > i) o[6 * j + i] = m.CV[6 * j + i] * tc - pw;
+                        }
                 }
             }
         }
@@ -464,12 +464,11 @@ __global__ void __launch_bounds__(RB, 3) response_passA_bulk_kernel(int64_t n, c
             }
             double2 *o = reinterpret_cast<double2 *>(s_ct + 36 * tid);
 #pragma unroll
-            for (int i = 0; i < 6; i++) {
-                const double wi = ca[i] * tw;
+            for (int i = 0; i < 6; i++)
 #pragma unroll
                 for (int j = 0; j < 6; j += 2)
-                    o[3 * i + (j >> 1)] = make_double2(m.CV[6 * i + j] * tc - wi * ca[j], m.CV[6 * i + j + 1] * tc - wi * ca[j + 1]);
-            }
+                    o[3 * i + (j >> 1)] = make_double2(m.CV[6 * i + j] * tc - (ca[i] * ca[j]) * tw,
+                                                       m.CV[6 * i + j + 1] * tc - (ca[i] * ca[j + 1]) * tw);
         }
         fence_async_smem();     // generic-proxy writes to shared memory -> visible to the bulk-copy engine
         __syncthreads();
@@ -583,8 +582,9 @@ constexpr int SVC_WARPS = 8;    // (16 warps at <= 128 registers spill inside th
 __device__ __forceinline__ void svc_load_table(const DevMat &m, double *s_tab)
 {
     const int np = m.nsv_pad;
-    for (int i = threadIdx.x; i < 6 * np; i += blockDim.x) s_tab[i] = m.sv[i];
-    for (int i = threadIdx.x; i < np; i += blockDim.x) s_tab[6 * np + i] = m.dual[i];
+    const int nf = m.svc_nf;
+    for (int i = threadIdx.x; i < nf * np; i += blockDim.x) s_tab[i] = m.sv[i];
+    for (int i = threadIdx.x; i < np; i += blockDim.x) s_tab[nf * np + i] = m.dual[i];
     __syncthreads();
 }
 
@@ -599,7 +599,7 @@ __global__ void __launch_bounds__(SVC_WARPS * 32) response_svc_kernel(int64_t n,
     const DevMat &m = c_mat[mid];
     svc_load_table(m, smem);
     const int lane = threadIdx.x & 31;
-    SvcModel ym(m, smem, smem + 6 * m.nsv_pad, lane);
+    SvcModel ym(m, smem, smem + m.svc_nf * m.nsv_pad, lane);
     for (;;) {
         unsigned long long e0 = 0;
         if (lane == 0) e0 = atomicAdd(queue, 1ull);
@@ -638,6 +638,7 @@ template <class Model>
 __device__ __forceinline__ void prim_eval(const Model &ym, const DevMat &m, int op, const double *s, const double *ep,
                                           const double *de, const double *ld, double *out, bool writer, int64_t e)
 {
+    ym.set_epl(ep);   // ML yield functions with work-hardening features read the plastic strain (material.py:2342-2346)
     if (op == OP_SEQ) {
         double v = ym.seq(s);
         if (writer) out[e] = v;
@@ -799,7 +800,7 @@ __global__ void __launch_bounds__(SVC_WARPS * 32) prim_svc_kernel(int op, int mi
     const DevMat &m = c_mat[mid];
     svc_load_table(m, smem);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    SvcModel ym(m, smem, smem + 6 * m.nsv_pad, lane);
+    SvcModel ym(m, smem, smem + m.svc_nf * m.nsv_pad, lane);
     for (int64_t e = (int64_t)blockIdx.x * SVC_WARPS + warp; e < n; e += (int64_t)gridDim.x * SVC_WARPS) {
         double s[6], ep[6] = {0, 0, 0, 0, 0, 0}, de[6] = {0, 0, 0, 0, 0, 0};
 #pragma unroll
@@ -814,6 +815,7 @@ __global__ void __launch_bounds__(SVC_WARPS * 32) prim_svc_kernel(int op, int mi
 #pragma unroll
                 for (int k = 0; k < 6; k++) ldv[k] = ld[k];
             double sflow = m.sy + eps_eq6(ep) * m.khard;
+            ym.set_epl(ep);
             double v = ym.ml_full_yf(s, sflow, ld ? ldv : nullptr);
             if (lane == 0) out[e] = v;
         } else {
@@ -936,7 +938,7 @@ static size_t k1_smem() { return sizeof(double) * (3 * RB * 6 + RB * CT_STRIDE);
 // double-buffered inputs (+ tangent staging for the non-direct variants)
 static size_t k1a_smem(bool direct) { return sizeof(double) * (2 * 3 * RB * 6 + (direct ? 0 : RB * CT_STRIDE)); }
 static size_t k1a_bulk_smem() { return sizeof(double) * (2 * 3 * RB * 6 + RB * 36); }
-static size_t svc_smem(const DevMat &m) { return sizeof(double) * 7 * (size_t)m.nsv_pad; }
+static size_t svc_smem(const DevMat &m) { return sizeof(double) * (size_t)(m.svc_nf + 1) * (size_t)m.nsv_pad; }
 
 template <class K>
 static cudaError_t big_smem(K kernel, size_t bytes)

@@ -175,14 +175,22 @@ class Material(object):
         else:
             self.barlat = False
 
-    def set_svc(self, support_vectors, dual_coef, intercept, gamma, scale_seq=None, dev_only=False):
+    def set_svc(self, support_vectors, dual_coef, intercept, gamma, scale_seq=None, dev_only=False, scale_wh=None):
         """Adopt a trained RBF support-vector yield function (what setup_yf_SVM_6D leaves on the Material,
         material.py:1109-1278): sklearn's svm_yf.support_vectors_ (nsv,6), dual_coef_[0], intercept_[0], gamma and the
-        feature scale scale_seq (= sy when no microstructure data is attached, 1160-1161)."""
+        feature scale scale_seq (= sy when no microstructure data is attached, 1160-1161).  A flow rule trained on
+        work-hardening data (Material.whdat, train_hardening.py) has 15 features per support vector -- 6 stresses,
+        6 plastic strains / scale_wh, accumulated strain, maximum stress, flag (material.py:2342-2346, 2667-2669) -- and
+        needs scale_wh; its hardening rate khard follows from the gradient of the yield function (808-814)."""
         sv = np.ascontiguousarray(support_vectors, dtype=float)
         if self.sy is None:
             raise ValueError('set_svc: call plasticity(sy=...) first (train_SVC does so, material.py:1606)')
         nfeat = 6 if self.sdim == 6 else 2
+        wh = self.sdim == 6 and sv.ndim == 2 and sv.shape[1] == 15
+        if wh:
+            if scale_wh is None or not scale_wh > 0.:
+                raise ValueError('set_svc: support vectors with work-hardening features need scale_wh > 0')
+            nfeat = 15
         if sv.ndim != 2 or sv.shape[1] != nfeat:
             raise ValueError('set_svc: support vectors must have shape (nsv, %d) for sdim = %d (features: %s)'
                              % (nfeat, self.sdim, 'scaled Voigt stress' if nfeat == 6 else 'seq_J2 / scale_seq - 1, polar angle / pi'))
@@ -198,7 +206,11 @@ class Material(object):
         self.dev_only = bool(dev_only)
         self.ML_yf = True
         self.Ndof = nfeat
-        self.khard = 0.   # material.py:812-814: the SVC gradient resets khard when there are no hardening features
+        self.whdat = bool(wh)
+        self.scale_wh = float(scale_wh) if wh else 1.
+        self.ind_wh = 6 if wh else None
+        if not wh:
+            self.khard = 0.   # material.py:812-814: the SVC gradient resets khard when there are no hardening features
 
     @classmethod
     def from_MLparam(cls, file, path='', sy=None, name=None):
@@ -216,10 +228,10 @@ class Material(object):
         trunk = os.path.join(path, file)
         props = np.loadtxt(trunk + '-svm.csv', delimiter=',').ravel()
         nsv, ndof = int(round(props[0])), int(round(props[1]))
-        if ndof not in (2, 6):
-            raise NotImplementedError('from_MLparam: models without work-hardening / texture features are supported on the '
-                                      'device path (Ndof = 6: sdim = 6, Ndof = 2: sdim = 3), file has Ndof = %d' % ndof)
-        sdim = 6 if ndof == 6 else 3
+        if ndof not in (2, 6, 15):
+            raise NotImplementedError('from_MLparam: supported feature vectors are Ndof = 6 (sdim = 6), 15 (sdim = 6 with '
+                                      'work-hardening features) and 2 (sdim = 3); texture features are not; file has Ndof = %d' % ndof)
+        sdim = 3 if ndof == 2 else 6
         if nsv < 1 or len(props) < 29 + nsv * (ndof + 1):
             raise ValueError('from_MLparam: file %s-svm.csv is truncated' % trunk)
         meta = None
@@ -246,16 +258,17 @@ class Material(object):
         m.plasticity(sy=float(scale_seq if sy is None else sy), sdim=sdim)
         dual = props[29:29 + nsv]
         sv = props[29 + nsv:29 + nsv + nsv * ndof].reshape(nsv, ndof)
-        m.set_svc(sv, dual, float(props[5]), float(props[6]), scale_seq=scale_seq, dev_only=(props[16] < 0.))
+        m.set_svc(sv, dual, float(props[5]), float(props[6]), scale_seq=scale_seq, dev_only=(props[16] < 0.),
+                  scale_wh=float(props[9]) if ndof == 15 else None)
         m.epc, m.scale_wh = float(props[7]), float(props[9])
         m.meta = meta
         return m
 
-    def from_sklearn(self, svc, scale_seq=None, dev_only=False):
+    def from_sklearn(self, svc, scale_seq=None, dev_only=False, scale_wh=None):
         """Adopt a fitted sklearn.svm.SVC(kernel='rbf') (binary) as yield function."""
         self.svm_yf = svc
         self.set_svc(svc.support_vectors_, svc.dual_coef_[0], svc.intercept_[0], svc._gamma if hasattr(svc, '_gamma') else svc.gamma,
-                     scale_seq=scale_seq, dev_only=dev_only)
+                     scale_seq=scale_seq, dev_only=dev_only, scale_wh=scale_wh)
 
     @classmethod
     def from_reference(cls, ref):
@@ -277,9 +290,11 @@ class Material(object):
             if getattr(ref, 'barlat', False):
                 m.barlat, m.Bar_m1, m.Bar_m2, m.barlat_exp = True, np.array(ref.Bar_m1), np.array(ref.Bar_m2), ref.barlat_exp
             if getattr(ref, 'ML_yf', False):
-                if getattr(ref, 'whdat', False) or getattr(ref, 'txdat', False):
-                    raise NotImplementedError('SVC features for work hardening / texture are not supported on the device path')
-                m.from_sklearn(ref.svm_yf, scale_seq=ref.scale_seq, dev_only=ref.dev_only)
+                if getattr(ref, 'txdat', False):
+                    # the reference's own texture path divides by self.self.scale_seq (material.py:811) and cannot run
+                    raise NotImplementedError('SVC features for texture are not supported on the device path')
+                m.from_sklearn(ref.svm_yf, scale_seq=ref.scale_seq, dev_only=ref.dev_only,
+                               scale_wh=ref.scale_wh if getattr(ref, 'whdat', False) else None)
         return m
 
     # ------------------------------------------------------------------------------------------------------
@@ -318,7 +333,10 @@ class Material(object):
                 d.svc_dual = dc.ctypes.data_as(_lib._dp)
                 d.svc_gamma, d.svc_rho, d.svc_scale_seq = self.gam_yf, rho, self.scale_seq
                 d.dev_only = int(self.dev_only)
-                d.khard = 0.
+                if getattr(self, 'whdat', False):
+                    d.svc_nfeat, d.svc_scale_wh = 15, float(self.scale_wh)   # khard: the value the material carries now
+                else:
+                    d.khard = 0.
                 keep = [sv, dc]
             elif self.barlat:
                 d.kind = _lib.MAT_BARLAT
@@ -415,13 +433,33 @@ class Material(object):
         if self.sdim == 3:
             out = out[:, 0:3]
         if self.ML_yf:
-            self.khard = 0.
+            self.khard = self._svc_khard(a, self._epl_rows(epl, len(a))) if getattr(self, 'whdat', False) else 0.
             self.msg['gradient'] = 'gradient to ML_yf'
         elif self.barlat:
             self.msg['gradient'] = 'analytical, Barlat Yld2004-18p, full stress'
         else:
             self.msg['gradient'] = 'analytical, 6-parameter Hill, full stress'
         return out[0] if single else out
+
+    def _svc_khard(self, sig, epl):
+        """Material.khard as calc_fgrad leaves it for a work-hardening SVC (material.py:802-814): minus the plastic-strain
+        part of the decision function's gradient, scaled by scale_seq / scale_wh, summed over components and averaged over
+        the points; never negative.  Host-side NumPy on the support-vector table (the device evaluates the same per element
+        inside the return mapping)."""
+        sv, dc, _ = self._svc
+        x = np.zeros((len(sig), 15))
+        s = np.array(sig, dtype=float)
+        if self.dev_only:
+            s[:, 0:3] -= s[:, 0:3].mean(axis=1, keepdims=True)
+        x[:, 0:6] = s / self.scale_seq
+        x[:, 6:12] = np.asarray(epl, dtype=float) / self.scale_wh
+        hk = 0.
+        for xi in x:
+            hv = xi[None, :] - sv
+            k = np.exp(-self.gam_yf * np.sum(hv * hv, axis=1))
+            dKdx = np.sum((dc * k)[:, None] * (-2. * self.gam_yf * hv), axis=0)
+            hk -= np.sum(dKdx[6:12]) * self.scale_seq / self.scale_wh
+        return max(hk / len(x), 0.)
 
     def epl_dot(self, sig, epl, Cel, deps, **_ignored):
         """Plastic strain increment (material.py:1009-1055, Crisfield 6.4 / 6.8 / 6.17)."""

@@ -156,6 +156,7 @@ class Model(object):
         self.egl = np.zeros((1, 6))
         self.epgl = np.zeros((1, 6))
         self._solved = False          # u, f, du live on the device; the properties mirror them on demand
+        self._part = None             # (rank, world, NCCL unique id) of a strip-partitioned model, see distribute()
         self.Nnode = None
         self.glob = {'ebc1': None, 'ebc2': None, 'sbc1': None, 'sbc2': None,
                      'eps': np.zeros(6), 'sig': np.zeros(6), 'epl': np.zeros(6)}
@@ -311,6 +312,34 @@ class Model(object):
         self._cache = {}
         self._on_device = False
 
+    def distribute(self, rank, world, unique_id, solver='replicated'):
+        """Make this process one rank of a strip-partitioned solve (one process per GPU).  Every rank builds
+        the SAME global model (geom / assign / bc* / mesh with the global NX, NY) and calls distribute() before the first
+        device call; its context then holds only the rank's strip of element columns (+ one halo column on the left,
+        pylabfea_b200/shard.py), and solve() runs the load increments on all ranks in lockstep: the linear solves
+        exchange one halo node column per CG iteration and all-reduce the dot products (NCCL), sweep flags, calc_scf
+        and the global averages are combined over the ranks.  glob / sgl / egl / epgl / nsteps / niter are the global
+        model's on every rank; u, f and element[i] refer to the rank's LOCAL node grid and elements (local_info()).
+
+        solver = 'replicated' (default): the element work is sharded, the owned K rows of all ranks are gathered and every
+        rank solves the complete system with the single-GPU multigrid-CG (du bit-identical to the single-GPU run, no
+        communication inside the solve; each rank additionally holds the global K).  solver = 'distributed': the strips
+        solve together (halo exchange + all-reduces per CG iteration, one V-cycle per strip as preconditioner): nothing
+        global is stored, but the iteration count grows with the number of strips."""
+        if self._on_device:
+            raise AttributeError('distribute() must be called before the model is used on the device')
+        if solver not in ('replicated', 'distributed'):
+            raise ValueError("distribute: solver must be 'replicated' or 'distributed'")
+        self._part = (int(rank), int(world), bytes(unique_id))
+        self._dist_solver = solver
+
+    def local_info(self):
+        """Strip of a distributed model held by this rank (shard.strip_shard) or None."""
+        if self._part is None:
+            return None
+        from .shard import strip_shard
+        return strip_shard(self._NX, self._part[0], self._part[1])
+
     def _dev(self):
         """The device context with materials and mesh uploaded (created on first use: no CPU fallback exists, so this
         raises PlfError without libplfb200.so or a CUDA device)."""
@@ -318,7 +347,24 @@ class Model(object):
             if self._ctx is None:
                 self._ctx = _lib.Context(self._device)
             self._ctx.set_materials([m._descriptor() for m in self.mat], planestress=self.planestress)
-            self._ctx.mesh_structured(self._NX, self._NY, self._dx, self._dy, self.thick, self._elem_mat)
+            if self._part is None:
+                self._ctx.mesh_structured(self._NX, self._NY, self._dx, self._dy, self.thick, self._elem_mat)
+            else:
+                rank, world, uid = self._part
+                sh = self.local_info()
+                j0, nxl = sh['first_col_global'], sh['nx_local']
+                em = self._elem_mat.reshape(self._NX, self._NY)[j0:j0 + nxl]
+                self._ctx.mesh_structured(nxl, self._NY, self._dx[j0:j0 + nxl], self._dy, self.thick, np.ascontiguousarray(em).ravel())
+                if not getattr(self, '_comm_up', False):
+                    self._ctx.comm_init(uid, rank, world)
+                    self._comm_up = True
+                cols = sh['owned_node_cols_local']
+                self._ctx.comm_set_partition(cols[0], cols[-1] + 1, j0, self._NX, float(self.npos[2 * j0 * self.NnodeY]), self.lenx)
+                if self._dist_solver == 'replicated':
+                    self._gctx = _lib.Context(self._device)
+                    self._gctx.set_materials([m._descriptor() for m in self.mat], planestress=self.planestress)
+                    self._gctx.mesh_structured(self._NX, self._NY, self._dx, self._dy, self.thick, self._elem_mat)
+                    self._ctx.comm_set_replica(self._gctx)
             self._on_device = True
         return self._ctx
 

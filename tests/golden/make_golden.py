@@ -792,6 +792,222 @@ def gen_svc3():
     print(f'svc3 fixture {time.time() - t0:.1f}s')
 
 
+def gen_sdim3_shear():
+    """sdim = 3 materials on ROTATED planar states.  sig_princ orders the eigenvalues that LAPACK's dgeev returns by "major
+    force axes" (basic.py:155-170); for every stress with s13 = s23 = 0 -- all a 2-d model produces -- that order is the
+    eigenvalue of the eigenvector closest to each coordinate axis (checked on 20 000 random planar states against the
+    reference; for general 3-d states the reference's result depends on dgeev's internal order and differs from this in 45 %
+    of random cases).  Fixtures: Material.response of the reference on planar states with shear, and a sheared model."""
+    t0 = time.time()
+    m = FE.Material(name='hill3s')
+    m.elasticity(E=200.e3, nu=0.3)
+    m.plasticity(sy=150., hill=[0.7, 1., 1.4], khard=100., sdim=3)
+    out = dict(E=200.e3, nu=0.3, sy=150., khard=100., hill=np.array(m.hill, dtype=float), drucker=0., mat_CV=np.array(m.CV))
+    rng = np.random.default_rng(91)
+    n = 240
+    CV = np.array(m.CV)
+    sig = np.zeros((n, 6)); epl = np.zeros((n, 6)); deps = np.zeros((n, 6))
+    for i in range(n):
+        if i % 3:
+            e = rng.standard_normal(3) * 0.004
+            epl[i, 0:3] = e - e.mean()
+        d = np.zeros(6)
+        d[[0, 1, 2, 5]] = rng.standard_normal(4)          # planar, sheared: principal axes rotated about z by any angle
+        sflow = m.get_sflow(epl[i])
+        u = rng.uniform()
+        r = rng.uniform(0., 0.9) if u < 0.35 else (rng.uniform(0.9, 1.0) if u < 0.7 else rng.uniform(0.996, 1.004))
+        sig[i] = d / m.calc_seq(d) * r * sflow
+        de = np.zeros(6)
+        de[[0, 1, 5]] = rng.standard_normal(3)
+        deps[i] = de / FE.eps_eq(de) * [5.e-4, 5.e-4, 2.e-3, 1.e-2, 1.e-4][i % 5]
+    fy = np.zeros(n); so = np.zeros((n, 6)); dp = np.zeros((n, 6)); ct = np.zeros((n, 6, 6)); ns = np.zeros(n, dtype=np.int32)
+    seq = np.zeros(n); sp = np.zeros((n, 3))
+    for i in range(n):
+        m.msg['nsteps'] = -1
+        fy[i], so[i], dp[i], ct[i] = m.response(sig[i], epl[i], deps[i], CV)
+        ns[i] = m.msg['nsteps']
+        seq[i] = m.calc_seq(sig[i])
+        sp[i] = FE.sig_princ(sig[i])[0]
+    out.update(pe_CV=CV, pe_sig=sig, pe_epl=epl, pe_deps=deps, pe_fy=fy, pe_sig_out=so, pe_depl=dp, pe_ctan=ct, pe_nsteps=ns,
+               pe_seq=seq, pe_sig_princ=sp)
+    print(f'  hill3 sheared states: 50-step {np.sum(ns == 49)}, elastic {np.sum(np.abs(ct - CV).max(axis=(1, 2)) == 0)}')
+    np.savez_compressed(os.path.join(HERE, 'response_hill3_shear.npz'), **out)
+    # tension + shear of a 4 x 4 plane-strain block of the same material: principal axes rotated by 20-35 degrees.  (Pure
+    # simple shear puts them at exactly 45 degrees, where argmax |ev| of basic.py:156 is a tie decided by rounding noise of
+    # LAPACK's eigenvectors: the reference's own result is then not reproducible -- a first version of this fixture
+    # agreed with the device for 7 increments to 1e-12 and then flipped.)
+    fe = FE.Model(dim=2, planestress=False)
+    fe.geom([4.], LY=4.)
+    fe.assign([m])
+    fe.bcleft(0., 'force')
+    fe.bcright(0., 'force')
+    fe.bcbot(0., 'disp', 'x')
+    fe.bcbot(0., 'disp', 'y')
+    fe.bctop(0.006 * fe.leny, 'disp', 'x')
+    fe.bctop(0.008 * fe.leny, 'disp', 'y')
+    fe.mesh(NX=4, NY=4)
+    solve_case('shear_hill3_4x4', fe, min_step=4)
+    print(f'sdim3 shear fixtures {time.time() - t0:.1f}s')
+
+
+class _RbfSVC:
+    """Duck-typed stand-in for a fitted sklearn.svm.SVC(kernel='rbf') with GIVEN support vectors (sklearn cannot be
+    constructed from parameters): the attributes and the decision function the reference reads (material.py:401-405,
+    798-799), f(x) = sum_i dual_i exp(-gamma |x - sv_i|^2) + intercept (libsvm k_function)."""
+
+    def __init__(self, sv, dual, rho, gamma):
+        self.support_vectors_ = np.array(sv)
+        self.dual_coef_ = np.array(dual)[None, :]
+        self.intercept_ = np.array([rho])
+        self.gamma = gamma
+
+    def decision_function(self, x):
+        x = np.atleast_2d(x)
+        d2 = ((x[:, None, :] - self.support_vectors_[None, :, :]) ** 2).sum(axis=2)
+        return np.exp(-self.gamma * d2) @ self.dual_coef_[0] + self.intercept_[0]
+
+    def predict(self, x):
+        return np.sign(self.decision_function(x))
+
+
+def gen_umat_models():
+    """The three trained flow rules the reference ships for its Abaqus UMAT (examples/UMAT/models/*-svm.csv, written by
+    export_MLparam of pyLabFEA 4.0: Nset at index 16 where 4.4 writes the dev_only flag; ml_umat.f:129-153 reads them with
+    dev_only = false).  The reference has no loader (from_MLparam is a stub, material.py:2688-2703): the parameters are put
+    on a reference Material by hand and its own calc_yf / calc_fgrad / ML_full_yf / response are evaluated on them."""
+    import json
+    src = os.path.join(HERE, 'umat_models')
+    for nm in ('abq_ML-Hill-p1_C15_G25', 'abq_ML-J2_C15_G25', 'abq_ML-Goss-Barlat_C15_G25'):
+        t0 = time.time()
+        props = np.loadtxt(os.path.join(src, nm + '-svm.csv'), delimiter=',').ravel()
+        meta = json.load(open(os.path.join(src, nm + '-svm_meta.json')))
+        names = meta['Data']['Names']
+        assert names[16] == 'Nset'   # layout of pyLabFEA 4.0 - 4.3
+        nsv, nsd = int(props[0]), int(props[1])
+        C11, C12, C44, rho, gamma, epc, scale_seq, scale_wh = props[2:10]
+        dual = props[29:29 + nsv]
+        sv = props[29 + nsv:29 + nsv + nsv * nsd].reshape(nsv, nsd)
+        m = FE.Material(name=nm)
+        m.elasticity(C11=C11, C12=C12, C44=C44)
+        m.plasticity(sy=scale_seq, sdim=6)
+        m.svm_yf = _RbfSVC(sv, dual, rho, gamma)
+        m.ML_yf, m.ML_grad = True, False
+        m.gam_yf, m.scale_seq, m.scale_wh, m.Ndof, m.dev_only = gamma, scale_seq, scale_wh, nsd, False
+        rng = np.random.default_rng(17)
+        n = 120
+        d = rng.standard_normal((n, 6))
+        d[: n // 2, 3:5] = 0.                                   # half of them planar
+        seq = np.array([FE.sig_eq_j2(x) for x in d])
+        sig = d / seq[:, None] * (scale_seq * rng.uniform(0.2, 1.3, n))[:, None]
+        yf = np.array([m.calc_yf(s) for s in sig])
+        fg = np.array([m.calc_fgrad(s) for s in sig])
+        full = np.array([m.ML_full_yf(s) for s in sig[:40]])
+        nr = 24
+        CV = np.array(m.CV)
+        deps = rng.standard_normal((nr, 6))
+        deps = deps / np.array([FE.eps_eq(x) for x in deps])[:, None] * 4.e-4
+        rs = np.zeros((nr, 6)); rd = np.zeros((nr, 6)); rc = np.zeros((nr, 6, 6)); rf = np.zeros(nr); rn = np.zeros(nr, dtype=np.int32)
+        for i in range(nr):
+            m.msg['nsteps'] = -1
+            rf[i], rs[i], rd[i], rc[i] = m.response(sig[i], np.zeros(6), deps[i], CV)
+            rn[i] = m.msg['nsteps']
+        np.savez_compressed(os.path.join(HERE, 'umat_' + nm.split('_')[1] + '.npz'), model=nm, sig=sig, yf=yf, fgrad=fg, full_yf=full,
+                            deps=deps, r_fy=rf, r_sig=rs, r_depl=rd, r_ctan=rc, r_nsteps=rn, CV=CV, scale_seq=scale_seq, nsv=nsv)
+        print(f'  {nm}: nsv {nsv}, yf in [{yf.min():.3f}, {yf.max():.3f}], 50-step {np.sum(rn == 49)} of {nr}, {time.time() - t0:.0f}s')
+
+
+def gen_svc_wh():
+    """SVC flow rule WITH work-hardening features (Material.whdat): the recipe of examples/train_hardening.py on a reduced
+    data set (Hill reference material with linear hardening khard = 1000; 45 load cases, plastic strain up to 2 %), trained
+    by the reference's train_SVC.  Feature vector (material.py:2336-2346): 6 stresses / scale_seq, 6 plastic strains /
+    scale_wh, accumulated strain, maximum stress / scale_seq, flag -- the last three are 0 in every call of the FE path.
+    Outputs of the reference: calc_yf, calc_fgrad (with the khard it leaves on the material, 808-814), ML_full_yf and
+    Material.response, each called on a FRESH copy of khard (the reference keeps khard on the Material object, so the
+    result of a call depends on which gradient was evaluated last; the fixture pins the per-call behaviour)."""
+    from scipy.optimize import fsolve
+    t0 = time.time()
+    E, nu, sy, khard = 200.e3, 0.3, 50., 1000.
+    rv = [1.2, 1.0, 0.8, 1.0, 1.0, 1.0]
+    mat_h = FE.Material(name='Hill-reference', num=1)
+    mat_h.elasticity(E=E, nu=nu)
+    mat_h.plasticity(sy=sy, rv=rv, khard=khard, sdim=6)
+    Nlc, epl_max, depl = 45, 0.02, 2.e-3
+    nl3d = int(Nlc / 3)
+    sunit_all = FE.load_cases(number_3d=nl3d, number_6d=Nlc - nl3d)
+    x1 = fsolve(mat_h.find_yloc, np.ones(Nlc) * mat_h.sy, args=(sunit_all,), xtol=1.e-5)
+    sig_ideal = sunit_all * x1[:, None]
+    SV = np.linalg.inv(mat_h.CV)
+    lc = dict()
+    for i, st in enumerate(sig_ideal):          # create_data of train_hardening.py:24-82
+        epl = np.zeros(6)
+        peeq = 0.
+        sl, el, tl = [], [], []
+        seq = FE.sig_eq_j2(st)
+        su = st / seq
+        ind = np.where(su > 0., 1, np.where(su < 0., 2, 0))
+        key = f'Us_A{ind[0]}B{ind[1]}C{ind[2]}D{ind[3]}E{ind[4]}F{ind[5]}_HI{i:03d}_NNNNN_Tx_NN'
+        for j in range(6):
+            s_ = su * j * seq / 5
+            sl.append(s_); el.append(np.array(epl)); tl.append(SV @ s_)
+        while peeq < epl_max:
+            peeq = FE.eps_eq(epl) + depl
+            s_ = su * (seq + peeq * khard)
+            epl = epl + mat_h.calc_fgrad(sig=s_, epl=epl) * depl
+            sl.append(s_); el.append(np.array(epl)); tl.append(epl + SV @ s_)
+        sl, el, tl = np.array(sl), np.array(el), np.array(tl)
+        lc[key] = {'Stress': sl, 'Eq_Stress': FE.sig_eq_j2(sl), 'Strain_Plastic': el, 'Eq_Strain_Plastic': FE.eps_eq(el),
+                   'Shifted_Strain_Plastic': None, 'Strain_Total': tl, 'Eq_Strain_Total': FE.eps_eq(tl)}
+    data = FE.Data(lc, mat_name='ML_Hill_hardening', epl_start=0.0, epl_crit=0.0, epl_max=epl_max, depl=depl, wh_data=True)
+    m = FE.Material(name='ML_Hill_hardening', num=2)
+    m.from_data(data.mat_data)
+    m.train_SVC(C=2.0, gamma=1.5, Ce=0.99, Fe=0.1, Nseq=8, gridsearch=False)
+    assert m.whdat and m.Ndof == 15 and m.ind_wh == 6
+    sv = np.array(m.svm_yf.support_vectors_)
+    print(f'  trained: {len(sv)} support vectors, scale_seq {m.scale_seq:.3f}, scale_wh {m.scale_wh:.5f}, sy {m.sy:.3f}, {time.time() - t0:.0f}s')
+    rng = np.random.default_rng(23)
+    n = 150
+    d = rng.standard_normal((n, 6))
+    d[: n // 2, 3:5] = 0.
+    peeq = np.where(rng.uniform(size=n) < 0.3, 0., rng.uniform(0., 0.015, n))
+    sig = np.zeros((n, 6)); epl = np.zeros((n, 6))
+    for i in range(n):
+        su = d[i] / FE.sig_eq_j2(d[i])
+        g = mat_h.calc_fgrad(sig=su * sy)
+        epl[i] = g / FE.eps_eq(g) * peeq[i]
+        sig[i] = su * (sy + khard * peeq[i]) * rng.uniform(0.3, 1.25)
+    k0 = float(m.khard)
+    yf = np.array([m.calc_yf(sig[i], epl=epl[i]) for i in range(n)])
+    fg = np.zeros((n, 6)); kh = np.zeros(n)
+    for i in range(n):
+        m.khard = k0
+        fg[i] = m.calc_fgrad(sig[i], epl=epl[i])
+        kh[i] = m.khard
+    nf = 40
+    full = np.zeros(nf)
+    for i in range(nf):
+        m.khard = k0
+        full[i] = m.ML_full_yf(sig[i], epl[i])
+    nr = 36
+    CV = np.array(m.CV)
+    deps = rng.standard_normal((nr, 6))
+    deps = deps / np.array([FE.eps_eq(x) for x in deps])[:, None] * np.array([2.e-4, 5.e-4, 1.e-3])[np.arange(nr) % 3][:, None]
+    rs = np.zeros((nr, 6)); rd = np.zeros((nr, 6)); rc = np.zeros((nr, 6, 6)); rf = np.zeros(nr); rn = np.zeros(nr, dtype=np.int32)
+    rk = np.zeros(nr)
+    for i in range(nr):
+        m.khard = k0
+        m.msg['nsteps'] = -1
+        rf[i], rs[i], rd[i], rc[i] = m.response(sig[i], epl[i], deps[i], CV)
+        rn[i] = m.msg['nsteps']
+        rk[i] = m.khard
+    m.khard = k0
+    np.savez_compressed(os.path.join(HERE, 'svc_wh.npz'), sv=sv, dual=np.array(m.svm_yf.dual_coef_[0]), rho=float(m.svm_yf.intercept_[0]),
+                        gamma=float(m.gam_yf), scale_seq=float(m.scale_seq), scale_wh=float(m.scale_wh), sy=float(m.sy), khard0=k0,
+                        dev_only=int(m.dev_only), CV=CV, sig=sig, epl=epl, yf=yf, fgrad=fg, khard_after_fgrad=kh, full_yf=full,
+                        deps=deps, r_fy=rf, r_sig=rs, r_depl=rd, r_ctan=rc, r_nsteps=rn, r_khard_after=rk)
+    print(f'  yf in [{yf.min():.3f}, {yf.max():.3f}], khard after fgrad in [{kh.min():.1f}, {kh.max():.1f}], '
+          f'response: 50-step {np.sum(rn == 49)}, 1-step {np.sum(rn == 0)} of {nr}; {time.time() - t0:.0f}s')
+
+
 if __name__ == '__main__':
     what = sys.argv[1:] or ['all']
     if 'all' in what:

@@ -558,6 +558,20 @@ def test_sdim3_response_vs_reference_golden(ctx, golden, name, tag):
     check_response(ctx.response_batch(sig, epl, deps), g, tag, float(g['sy']))
 
 
+def test_sdim3_response_on_rotated_planar_states_vs_reference_golden(ctx, golden):
+    """sdim = 3 material on stresses with in-plane shear (principal axes rotated about z by any angle): the reference's
+    eigenvalue order (basic.py:155-170) is reproduced for every planar state -- all a 2-d model can produce; 240 reference
+    tuples, 134 of them 50-sub-step."""
+    from pylabfea_b200 import _lib
+    g = golden('response_hill3_shear')
+    m = plf_material_from_golden(g)
+    m.kind = _lib.MAT_HILL3
+    ctx.set_materials([m], planestress=False)
+    sig, epl, deps = g['pe_sig'], g['pe_epl'], g['pe_deps']
+    assert relmax(ctx.calc_seq(0, sig), g['pe_seq']) < 1e-12
+    check_response(ctx.response_batch(sig, epl, deps), g, 'pe', float(g['sy']))
+
+
 def test_sdim3_j2_equals_sdim6_j2_on_axis_aligned_states(ctx, golden):
     """For J2 and stresses without shear the sdim = 3 formulation is mathematically the sdim = 6 one; 20 000 random
     axis-aligned tuples through both kernel families must agree to rounding (also a guard for the code generation of
