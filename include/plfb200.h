@@ -99,6 +99,10 @@ int plf_event_elapsed(plf_ctx *ctx, int idx0, int idx1, float *ms); /* synchroni
 int plf_synchronize(plf_ctx *ctx);
 int plf_flush_l2(plf_ctx *ctx);              /* overwrites a 256 MiB scratch buffer (L2 is 126 MB) */
 int64_t plf_launch_count(const plf_ctx *ctx); /* kernels launched by this context so far */
+/* Names of the return-mapping / assembly kernel variants launched since the previous call, ';'-separated, spelled as ncu
+ * prints them ("response_passA_kernel<1, 4, 0>;..."); the first call only switches the recording on.  bench.py matches its
+ * roofline.traffic figures to exactly these names. */
+int plf_last_kernels(plf_ctx *ctx, char *buf, int len);
 /* page-locked host memory for callers that want asynchronous H2D/D2H copies of their numpy buffers */
 int plf_pinned_alloc(size_t bytes, void **out);
 int plf_pinned_free(void *p);

@@ -202,6 +202,12 @@ class Context:
     def launch_count(self):
         return int(self.L.plf_launch_count(self.h))
 
+    def last_kernels(self):
+        """Kernel variants (ncu spelling) of the return mapping / assembly launched since the previous call."""
+        buf = C.create_string_buffer(256)
+        self._ck(self.L.plf_last_kernels(self.h, buf, 256))
+        return [k for k in buf.value.decode().split(';') if k]
+
     def set_option(self, key, value):
         self._ck(self.L.plf_set_option(self.h, key.encode(), int(value)))
 

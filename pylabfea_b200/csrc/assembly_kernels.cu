@@ -324,7 +324,11 @@ cudaError_t launch_assemble(const LaunchCtx &lc, int NX, int NY, int planestress
 {
     if (lc.assembly_tiled != 0) {
         const dim3 grid((NY + 1 + SN - 1) / SN, NX + 1);
-#define ASM(PS, U, M) assemble_rows_staged_kernel<PS, U, M><<<grid, 2 * SN, 0, lc.stream>>>(NX, NY, 0, elem_desc, elstiff, val)
+#define ASM(PS, U, M)                                                      \
+    do {                                                                   \
+        trace_kernel(lc, "assemble_rows_staged_kernel", PS, U, M, 1);      \
+        assemble_rows_staged_kernel<PS, U, M><<<grid, 2 * SN, 0, lc.stream>>>(NX, NY, 0, elem_desc, elstiff, val); \
+    } while (0)
         const bool uni = (ngeom == 1);
         if (planestress) { if (uni) ASM(true, true, 4); else ASM(true, false, 4); }
         else { if (uni) ASM(false, true, 5); else ASM(false, false, 5); }

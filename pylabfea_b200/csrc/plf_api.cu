@@ -229,6 +229,15 @@ extern "C" int plf_flush_l2(plf_ctx *ctx)
 
 extern "C" int64_t plf_launch_count(const plf_ctx *ctx) { return ctx ? ctx->launches : 0; }
 
+extern "C" int plf_last_kernels(plf_ctx *ctx, char *buf, int len)
+{
+    if (!ctx || !buf || len < 1) return PLF_EINVAL;
+    snprintf(buf, (size_t)len, "%s", ctx->trace);
+    ctx->trace[0] = 0;
+    ctx->trace_on = 1;   // recording starts with the first query
+    return PLF_OK;
+}
+
 extern "C" int plf_pinned_alloc(size_t bytes, void **out)
 {
     if (!out) return PLF_EINVAL;

@@ -29,7 +29,11 @@ struct LaunchCtx {
     int passb_recur = 1;   // 1: planar isotropic J2 loop of pass B with scalar recurrences on the carried chain (hill_fast.cuh)
     int passa_bulk = 0;      // 1: pass A moves its records with cp.async.bulk (TMA engine: measured 6 % slower), 0: cp.async ring + staged stores
     int assembly_tiled = 2;  // 2: row per thread with staged coalesced stores (production); 0: direct stores
+    char *trace = nullptr;   // when set (256 bytes): the launchers append the names of the kernel variants they launch, ';'-separated
 };
+
+// appends "name<a, b, c>;" to lc.trace (the spelling ncu prints), used by plf_last_kernels
+void trace_kernel(const LaunchCtx &lc, const char *name, int a, int b, int c, int d = -1);
 
 // response_kernels.cu
 cudaError_t response_init();

@@ -108,6 +108,8 @@ struct plf_ctx {
     // change tracking, so that an unchanged K is neither re-assembled nor re-coarsened: tangent_epoch moves whenever
     // element tangents change (plf_set_tangent, a sweep that replaced one), K_serial with every assembly, mask_epoch
     // with every new set of boundary-condition vectors
+    char trace[256] = {0};    // kernel variants launched since the last plf_last_kernels (when trace_on)
+    int trace_on = 0;
     int skip_unchanged = 1;   // option: 0 re-assembles / re-coarsens even when nothing changed (A/B, tests)
     int64_t tangent_epoch = 1, K_tangent_epoch = 0, K_serial = 0, mask_epoch = 0, mg_K_serial = -1, mg_mask_epoch = -1;
 };
@@ -126,6 +128,7 @@ int model_solve_device_bc(plf_ctx *ctx, double rtol, int max_iter, int *iters, d
 inline plf::LaunchCtx make_lc(const plf_ctx *c)
 {
     plf::LaunchCtx lc{c->stream, c->sm_count, c->passa_direct, c->max_fm, c->k1_only, c->passb_recur, c->passa_bulk, c->assembly_tiled};
+    lc.trace = c->trace_on ? const_cast<char *>(c->trace) : nullptr;
     return lc;
 }
 void model_free(plf_ctx *ctx);

@@ -6,6 +6,8 @@
 //    transaction is a fully used 128 B line, and stages the 36-double tangent the same way on the way out.
 // K2 (SVC): one warp per element, support-vector table resident in shared memory (SoA), dynamic element queue.
 #include <algorithm>
+#include <cstdio>
+#include <cstring>
 
 #include "hill_fast.cuh"
 #include "plf_device.cuh"
@@ -934,6 +936,15 @@ cudaError_t launch_pack(const LaunchCtx &lc, int64_t n, const int32_t *mat_id, i
 // ------------------------------------------------------------------------------------------------------------
 // host launchers
 // ------------------------------------------------------------------------------------------------------------
+void trace_kernel(const LaunchCtx &lc, const char *name, int a, int b, int c, int d)
+{
+    if (!lc.trace) return;
+    const size_t used = strlen(lc.trace);
+    if (used > 200) return;
+    if (d >= 0) snprintf(lc.trace + used, 256 - used, "%s<%d, %d, %d, %d>;", name, a, b, c, d);
+    else snprintf(lc.trace + used, 256 - used, "%s<%d, %d, %d>;", name, a, b, c);
+}
+
 static size_t k1_smem() { return sizeof(double) * (3 * RB * 6 + RB * CT_STRIDE); }
 // double-buffered inputs (+ tangent staging for the non-direct variants)
 static size_t k1a_smem(bool direct) { return sizeof(double) * (2 * 3 * RB * 6 + (direct ? 0 : RB * CT_STRIDE)); }
@@ -1008,6 +1019,8 @@ cudaError_t launch_response(const LaunchCtx &lc, const DevMat *hmats, int nmat, 
             // persistent: 3 blocks per SM, each walking tiles with a double-buffered cp.async prefetch
 #define PASSA(S, F)                                                                                                              \
     do {                                                                                                                         \
+        if (lc.passa_bulk && (F) != 5) trace_kernel(lc, "response_passA_bulk_kernel", S, F, -1 + 1);                             \
+        else trace_kernel(lc, "response_passA_kernel", S, F, direct ? 1 : 0);                                                    \
         if (lc.passa_bulk && (F) != 5)                                                                                           \
             response_passA_bulk_kernel<S, (F) == 5 ? 0 : (F)><<<pgrid, RB, k1a_bulk_smem(), lc.stream>>>(                        \
                 n, mat_id, sig, epl, deps, fy, sig_out, depl, ctan, nsteps, worklist, work_count);                               \
@@ -1045,9 +1058,12 @@ cudaError_t launch_response(const LaunchCtx &lc, const DevMat *hmats, int nmat, 
             pdl_cfg.attrs = &pdl_attr;
             pdl_cfg.numAttrs = 1;
             const int32_t *wl_c = worklist;
-#define PASSB(M, S, F)                                                                                                     \
-    cudaLaunchKernelEx(&pdl_cfg, response_passB_kernel<M, S, F>, mat_id, sig, epl, deps, fy, sig_out, depl, ctan, nsteps, \
-                       wl_c, n, work_count)
+#define PASSB(M, S, F)                                                                                                         \
+    do {                                                                                                                       \
+        trace_kernel(lc, "response_passB_kernel", M, S, F);                                                                    \
+        cudaLaunchKernelEx(&pdl_cfg, response_passB_kernel<M, S, F>, mat_id, sig, epl, deps, fy, sig_out, depl, ctan, nsteps, \
+                           wl_c, n, work_count);                                                                               \
+    } while (0)
             if (single) {
                 if (fm == 7) PASSB(3, true, 7);
                 else if (fm == 6) PASSB(3, true, 6);

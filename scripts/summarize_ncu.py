@@ -30,6 +30,11 @@ def to_bytes(val, unit):
 
 def main():
     rep, out = sys.argv[1], sys.argv[2]
+    # optional: --fp64 <config name> <elements>  -> FP64 flop per element update of that BASELINE config into profiles/fp64_ops.json
+    fp64_cfg = None
+    if '--fp64' in sys.argv:
+        i = sys.argv.index('--fp64')
+        fp64_cfg = (sys.argv[i + 1], float(sys.argv[i + 2]))
     raw = subprocess.run(['ncu', '-i', rep, '--page', 'raw', '--csv'], capture_output=True, text=True).stdout
     rows = list(csv.reader(io.StringIO(raw)))
     h, units = rows[0], rows[1]
@@ -50,6 +55,25 @@ def main():
             ir, iw = h.index('dram__bytes_read.sum'), h.index('dram__bytes_write.sum')
             b = to_bytes(r[ir], units[ir]) + to_bytes(r[iw], units[iw])
             traffic.setdefault(short, []).append(b)
+    if fp64_cfg:
+        ops = {'dfma': 'smsp__sass_thread_inst_executed_op_dfma_pred_on.sum', 'dadd': 'smsp__sass_thread_inst_executed_op_dadd_pred_on.sum',
+               'dmul': 'smsp__sass_thread_inst_executed_op_dmul_pred_on.sum'}
+        flop, seen = 0., []
+        for r in rows[2:]:
+            name = r[h.index('Kernel Name')].split('(')[0].replace('void ', '')
+            if not name.startswith('response_') and not name.startswith('sweep_'):
+                continue
+            if name in seen:      # one launch per kernel variant
+                continue
+            seen.append(name)
+            for k, col in ops.items():
+                if col in h:
+                    flop += float(r[h.index(col)].replace(',', '')) * (2. if k == 'dfma' else 1.)
+        fj = os.path.join(os.path.dirname(out) or '.', 'fp64_ops.json')
+        cur = json.load(open(fj)) if os.path.exists(fj) else {}
+        cur[fp64_cfg[0]] = {'flop_per_update': flop / fp64_cfg[1], 'kernels': seen, 'elements': fp64_cfg[1],
+                            'source': 'ncu thread-level DFMA x 2 + DADD + DMUL of ' + os.path.basename(rep)}
+        json.dump(cur, open(fj, 'w'), indent=1, sort_keys=True)
     tj = os.path.join(os.path.dirname(out) or '.', 'traffic.json')
     cur = json.load(open(tj)) if os.path.exists(tj) else {}
     cur.update({k: {'dram_bytes_per_launch': sum(v) / len(v), 'launches_profiled': len(v), 'report': os.path.basename(rep)}

@@ -116,10 +116,13 @@ def test_strip_partitioned_cg_rehearsal_over_gloo(nproc, port):
     neighbour and iteration, all-reduced dot products, final halo of du) rehearsed on the CPU with real ranks over gloo
     and numpy arithmetic (tests/dist_cg_gloo.py): every rank ends with the dense global solution on its node grid, all
     ranks stop at the same iteration, and the owned rows of every strip stiffness equal the global rows.  3 ranks give
-    the middle rank ghosts on both sides."""
+    the middle rank ghosts on both sides.  The same ranks also rehearse the replicated solve (plf_comm_set_replica): owned
+    rows gathered from all ranks reproduce the global K bit for bit, and the solve on them is the global solve."""
     out = _torchrun([], port, nproc=nproc, script=os.path.join('tests', 'dist_cg_gloo.py'))
     assert len(out) == 1
     d = out[0]
     assert d['world'] == nproc and d['owned_rows_equal_global']
     assert len(set(d['iters'])) == 1 and 10 < d['iters'][0] < 5000
     assert d['max_rel_err'] < 1e-9
+    # the replicated solve: the owned row ranges of all ranks tile the global K exactly once, bit for bit
+    assert d['gathered_rows_equal_global'] and d['replicated_max_rel_err'] == 0.

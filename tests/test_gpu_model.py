@@ -243,8 +243,9 @@ def test_svc_simple_shear_in_fe(golden):
     assert abs(fem.element[3].sig[1] - 43.9060552472426) < 5e-3
     # and the full state of the reference run in this container
     assert fem.nsteps == int(g['nsteps']) and list(fem.niter) == list(g['niter'])
-    assert relmax(np.array([el.sig for el in fem.element]), g['sig']) < 1e-5
-    assert relmax(fem.u, g['u']) < 1e-5
+    dev_sig, dev_u = relmax(np.array([el.sig for el in fem.element]), g['sig']), relmax(fem.u, g['u'])
+    print('svc shear model: sig', dev_sig, 'u', dev_u)
+    assert dev_sig < 1e-6 and dev_u < 1e-6      # north-star tolerance for plasticity
 
 
 def test_large_plastic_solve_invariants():
