@@ -238,7 +238,7 @@ __global__ void __launch_bounds__(128) sweep_hill_kernel(int64_t n, int NY, int 
 // sweep, thread per element, for the yield models with eigen-decompositions (Yld2004-18p, sdim = 3): unsplit
 // response_core, FP64-bound
 template <class Model, int KIND, int MODE>
-__global__ void __launch_bounds__(128) sweep_model_kernel(int64_t n, int NY, int nit, const int32_t *__restrict__ desc,
+__global__ void __launch_bounds__(128, 4) sweep_model_kernel(int64_t n, int NY, int nit, const int32_t *__restrict__ desc,
                                                            const double *__restrict__ sig, const double *__restrict__ epl,
                                                            const double *__restrict__ du, double *__restrict__ elstiff,
                                                            double *__restrict__ res_sig, double *__restrict__ res_depl,
@@ -278,9 +278,9 @@ __global__ void __launch_bounds__(128) sweep_model_kernel(int64_t n, int NY, int
 }
 
 // sweep, warp per element, one SVC material (SV table in shared memory)
-constexpr int SVCW = 8;   // warps per block of the SVC kernels
+constexpr int SVCW = 16;   // warps per block of the SVC kernels (one block per SM, <= 128 registers)
 
-__global__ void __launch_bounds__(SVCW * 32) sweep_svc_kernel(int64_t n, int NY, int nit, int mid, const int32_t *__restrict__ desc,
+__global__ void __launch_bounds__(SVCW * 32, 1) sweep_svc_kernel(int64_t n, int NY, int nit, int mid, const int32_t *__restrict__ desc,
                                                         const double *__restrict__ sig, const double *__restrict__ epl,
                                                         const double *__restrict__ du, double *__restrict__ elstiff,
                                                         double *__restrict__ res_sig, double *__restrict__ res_depl,
@@ -374,7 +374,7 @@ cudaError_t launch_sweep(const LaunchCtx &lc, const DevMat *hmats, int nmat, int
         if (hmats[i].kind != PLF_MAT_SVC) continue;
         e = cudaMemsetAsync(&st->queue, 0, sizeof(unsigned long long), lc.stream);
         if (e != cudaSuccess) return e;
-        int blocks = lc.sm_count * 2;
+        int blocks = lc.sm_count;
         int64_t need = (Nel + SVCW - 1) / SVCW;
         if (blocks > need) blocks = (int)need;
         sweep_svc_kernel<<<blocks, SVCW * 32, sizeof(double) * (size_t)(hmats[i].svc_nf + 1) * (size_t)hmats[i].nsv_pad, lc.stream>>>(
@@ -558,7 +558,7 @@ __global__ void __launch_bounds__(128) scf_elements_kernel(int64_t Nel, int NY, 
     });
 }
 
-__global__ void __launch_bounds__(SVCW * 32) scf_svc_kernel(int64_t Nel, int NY, int mid, const int32_t *__restrict__ desc,
+__global__ void __launch_bounds__(SVCW * 32, 1) scf_svc_kernel(int64_t Nel, int NY, int mid, const int32_t *__restrict__ desc,
                                                       const double *__restrict__ sig, const double *__restrict__ epl,
                                                       const double *__restrict__ du, const double *__restrict__ elstiff,
                                                       const double *__restrict__ sld, double *__restrict__ hval,
@@ -893,7 +893,7 @@ cudaError_t launch_scf(const LaunchCtx &lc, const DevMat *hmats, int nmat, int64
     (*launches)++;
     for (int i = 0; i < nmat; i++) {
         if (hmats[i].kind != PLF_MAT_SVC) continue;
-        int blocks = lc.sm_count * 2;
+        int blocks = lc.sm_count;
         int64_t need = (Nel + SVCW - 1) / SVCW;
         if (blocks > need) blocks = (int)need;
         cudaFuncSetAttribute(scf_svc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);

@@ -127,6 +127,12 @@ __device__ __forceinline__ double j2_seq(const double *s)
 // |d|^n for a whole exponent by binary powering (a handful of multiplications instead of a ~150-instruction pow())
 __device__ __forceinline__ double powi_abs(double ad, int n)
 {
+    // the exponents of Yld2004-18p in practice (a = 8 for fcc, 6 for bcc) and a - 1 for the gradient: straight-line code
+    const double x2 = ad * ad, x4 = x2 * x2;
+    if (n == 8) return x4 * x4;
+    if (n == 7) return x4 * (x2 * ad);
+    if (n == 6) return x4 * x2;
+    if (n == 5) return x4 * ad;
     double r = 1., b = ad;
     while (n) {
         if (n & 1) r *= b;

@@ -579,7 +579,8 @@ __global__ void __launch_bounds__(RB) response_generic_kernel(int64_t n, const i
 // ------------------------------------------------------------------------------------------------------------
 // K2: warp-per-element return mapping for one SVC material, SV table in shared memory.
 // ------------------------------------------------------------------------------------------------------------
-constexpr int SVC_WARPS = 8;    // (16 warps at <= 128 registers spill inside the return-mapping core: measured 0.55 M against 0.79 M updates/s)
+constexpr int SVC_WARPS = 16;   // one block per SM (the SV table fills its shared memory).  With the decision / gradient loops out of line
+                                // 16 warps at <= 128 registers beat 8 at 255 by 6 % (before that: 0.55 M against 0.79 M updates/s)
 
 __device__ __forceinline__ void svc_load_table(const DevMat &m, double *s_tab)
 {
@@ -590,7 +591,7 @@ __device__ __forceinline__ void svc_load_table(const DevMat &m, double *s_tab)
     __syncthreads();
 }
 
-__global__ void __launch_bounds__(SVC_WARPS * 32) response_svc_kernel(int64_t n, int mid, const int32_t *__restrict__ mat_id,
+__global__ void __launch_bounds__(SVC_WARPS * 32, 1) response_svc_kernel(int64_t n, int mid, const int32_t *__restrict__ mat_id,
                                                                       const double *__restrict__ sig, const double *__restrict__ epl,
                                                                       const double *__restrict__ deps, double *__restrict__ fy,
                                                                       double *__restrict__ sig_out, double *__restrict__ depl_out,
@@ -730,7 +731,7 @@ __global__ void __launch_bounds__(128) prim_model_kernel(int op, int mid, int64_
 // (one atomic per warp); pass 2, a persistent grid over the list, runs the 50 sub-steps for them.  Without it a warp with
 // one 50-sub-step element runs ~50 times longer than its neighbours (22 % of the Barlat bench states are such elements).
 template <class Model, int MODE>
-__global__ void __launch_bounds__(128) response_model_kernel(int64_t n, int mid, const int32_t *__restrict__ mat_id,
+__global__ void __launch_bounds__(128, 4) response_model_kernel(int64_t n, int mid, const int32_t *__restrict__ mat_id,
                                                               const double *__restrict__ sig, const double *__restrict__ epl,
                                                               const double *__restrict__ deps, double *__restrict__ fy,
                                                               double *__restrict__ sig_out, double *__restrict__ depl_out,
@@ -794,7 +795,7 @@ __global__ void __launch_bounds__(128) response_model_kernel(int64_t n, int mid,
     }
 }
 
-__global__ void __launch_bounds__(SVC_WARPS * 32) prim_svc_kernel(int op, int mid, int64_t n, const double *__restrict__ sig,
+__global__ void __launch_bounds__(SVC_WARPS * 32, 1) prim_svc_kernel(int op, int mid, int64_t n, const double *__restrict__ sig,
                                                                   const double *__restrict__ epl, const double *__restrict__ deps,
                                                                   const double *__restrict__ ld, double *__restrict__ out)
 {
@@ -1115,7 +1116,7 @@ cudaError_t launch_response(const LaunchCtx &lc, const DevMat *hmats, int nmat, 
     for (int i = 0; i < nmat; i++) {
         if (hmats[i].kind != PLF_MAT_SVC) continue;
         cudaMemsetAsync(queue, 0, sizeof(unsigned long long), lc.stream);
-        int blocks = lc.sm_count * 2;
+        int blocks = lc.sm_count;
         int64_t need = (n + SVC_WARPS - 1) / SVC_WARPS;
         if (blocks > need) blocks = (int)need;
         response_svc_kernel<<<blocks, SVC_WARPS * 32, svc_smem(hmats[i]), lc.stream>>>(n, i, nmat > 1 ? mat_id : nullptr, sig,
@@ -1131,7 +1132,7 @@ cudaError_t launch_prim(const LaunchCtx &lc, const DevMat *hmats, int op, int mi
 {
     if (n <= 0) return cudaSuccess;
     if (hmats[mid].kind == PLF_MAT_SVC) {
-        int blocks = lc.sm_count * 2;
+        int blocks = lc.sm_count;
         int64_t need = (n + SVC_WARPS - 1) / SVC_WARPS;
         if (blocks > need) blocks = (int)need;
         prim_svc_kernel<<<blocks, SVC_WARPS * 32, svc_smem(hmats[mid]), lc.stream>>>(op, mid, n, sig, epl, deps, ld, out);

@@ -170,23 +170,20 @@ class Model(object):
     # pre-processing: geometry, materials, boundary conditions (host, O(1))
     # ------------------------------------------------------------------------------------------------------
     def geom(self, sect=1, LX=None, LY=1., LZ=1.):
-        """Model dimensions and sections (model.py:514-552)."""
-        if type(sect) == list:
-            self.Nsec = len(sect)
-            self.LS = np.array(sect)
-            self.lenx = sum(sect)
-        elif type(sect) == int:
+        """Model dimensions and sections (model.py:514-552): either the list of section lengths, or a number of equally
+        long sections that share LX."""
+        if type(sect) is list:
+            lengths, total = np.array(sect), sum(sect)
+        elif type(sect) is int:
             if sect < 1:
                 raise ValueError('At least one section must be defined.')
             if LX is None:
                 raise ValueError('LX must be given if sect is of type int')
-            self.lenx = LX
-            self.Nsec = sect
-            self.LS = np.ones(sect) * self.lenx / sect
+            lengths, total = np.ones(sect) * LX / sect, LX
         else:
             raise TypeError('Sect must be either list or int, not {}'.format(type(sect)))
-        self.leny = LY
-        self.thick = LZ
+        self.Nsec, self.LS, self.lenx = len(lengths), lengths, total
+        self.leny, self.thick = LY, LZ
 
     def assign(self, mats):
         """One Material per section (model.py:554-577)."""
@@ -567,21 +564,21 @@ class Model(object):
         g['ebc12'], g['sbc12'] = (uxt - uxb) / self.leny, 0.5 * (fxt - fxb) / ay
 
     def _report_increment(self, il, rep, state):
-        print('***Load step #', il)
-        print('scaling factor', rep.scale_bc)
+        print('== increment %d: predictor scaled by %.6g, %d inner passes, %d linear solves (%d CG iterations)'
+              % (il, rep.scale_bc, rep.passes, rep.solves, rep.cg_iterations))
         for nit in range(rep.passes):
-            if not rep.pass_conv[nit]:
-                print('\n  ###  Warning: No convergence of plasticity algorithm in trial step #', nit)
-            print('+++Inner trial step #', nit, 'branches [elastic, 1 step, 50 sub-steps, corrections]:',
-                  list(rep.pass_counts[nit]), 'CG iterations:', rep.pass_cg_iters[1 + nit])
-        print('load increment right:', list(rep.step_right), 'top:', list(rep.step_top),
-              *(('set:', list(rep.step_node)) if self.noset is not None else ()))
-        print('Load increment ', il + 1, 'top ', list(state.reached_top), '/', self.bct, '; rhs', list(state.reached_right),
-              '/', self.bcr)
-        print('Global strain: ', np.around(self.glob['eps'], decimals=5))
-        print('Global stress: ', np.around(self.glob['sig'], decimals=3))
-        print('Global plastic strain: ', np.around(self.glob['epl'], decimals=6))
-        print('----------------------------')
+            print('   pass %2d: %s, tangents %s, max |dC| %.3g, elements [elastic, 1 step, 50 sub-steps, corrected] = %s, CG %d'
+                  % (nit, 'yield condition met' if rep.pass_conv[nit] else 'NOT converged (f > 5e-3)',
+                     'changed' if rep.pass_change[nit] else 'unchanged', rep.pass_max_hh[nit], list(rep.pass_counts[nit]),
+                     rep.pass_cg_iters[1 + nit]))
+        steps = 'right %s, top %s' % (list(rep.step_right), list(rep.step_top))
+        if self.noset is not None:
+            steps += ', node set %s' % list(rep.step_node)
+        print('   applied: ' + steps)
+        print('   reached: top %s of %s, right %s of %s' % (list(state.reached_top), list(self.bct), list(state.reached_right),
+                                                          list(self.bcr)))
+        for label, key, nd in (('strain', 'eps', 5), ('stress', 'sig', 3), ('plastic strain', 'epl', 6)):
+            print('   mean %s: %s' % (label, np.around(self.glob[key], decimals=nd)))
 
     # ------------------------------------------------------------------------------------------------------
     # post-processing (model.py:1452-1511)

@@ -45,10 +45,12 @@ def owned_slice(shard, NY, ncomp=2):
     return slice(cols[0] * w, (cols[-1] + 1) * w)
 
 
-def share_bytes(path, rank, payload=None, timeout=120.):
+def share_bytes(path, rank, payload=None, timeout=120., max_age=300.):
     """Side channel for the NCCL unique id when no launcher-provided store is at hand: rank 0 writes `payload` to `path`
     (atomically, via rename), the other ranks wait for the file and read it.  All ranks of one job must use the same path
-    (e.g. derived from MASTER_PORT) on a file system they share."""
+    (e.g. derived from MASTER_PORT) on a file system they share.  A file older than `max_age` seconds is taken for the
+    left-over of a crashed job and ignored (a rank that read a stale id would hang in ncclCommInitRank); rank 0 replaces
+    whatever is there."""
     import os
     import time
     if rank == 0:
@@ -58,7 +60,13 @@ def share_bytes(path, rank, payload=None, timeout=120.):
         os.replace(tmp, path)
         return payload
     t0 = time.time()
-    while not os.path.exists(path):
+
+    def fresh():
+        try:
+            return time.time() - os.path.getmtime(path) <= max_age
+        except OSError:
+            return False
+    while not fresh():
         if time.time() - t0 > timeout:
             raise TimeoutError('share_bytes: %s did not appear within %g s' % (path, timeout))
         time.sleep(0.02)
