@@ -116,7 +116,11 @@ int plf_pinned_free(void *p);
  *   "solver_mg"    1 (default): multigrid V-cycle preconditioner for plf_solve_linear; 0: Jacobi
  *   "solver_warm"  1 (default): CG starts from the previous du; 0: from zero
  *   "mg_nu", "mg_coarse_sweeps", "mg_omega_permille": smoothing sweeps per level / on the coarsest level / Jacobi damping
- *   "k1_only"      diagnostics: 1 = launch pass A only, 2 = pass A without the constitutive math */
+ *   "k1_only"      diagnostics: 1 = launch pass A only, 2 = pass A without the constitutive math
+ *   "passa_bulk"   1: pass A with cp.async.bulk / mbarrier (TMA engine) instead of the cp.async ring (default 0: measured slower)
+ *   "mg_fuse_tail" 2 (default): coarse levels of the V-cycle in one cooperative kernel + one fused block; 1: fused block only; 0: per level
+ *   "skip_unchanged" 1 (default): an unchanged K is neither re-assembled nor re-coarsened
+ *   "solver_hybrid" replicated multi-GPU solve: 1 = CG vectors and level 0 of the V-cycle split over the ranks (default 0) */
 int plf_set_option(plf_ctx *ctx, const char *key, int value);
 
 /* ---- materials ------------------------------------------------------------------------------------------- */

@@ -34,6 +34,14 @@ struct MgHierarchy {
 cudaError_t mg_build(MgHierarchy &H, int NX, int NY, int j0 = 0);
 void mg_free(MgHierarchy &H);
 cudaError_t mg_setup(const LaunchCtx &lc, MgHierarchy &H, const double *val_fine, const unsigned char *mask_fine, int64_t *launches);
-cudaError_t mg_vcycle(const LaunchCtx &lc, MgHierarchy &H, const double *r_fine, double *z_fine, int64_t *launches);
+struct Comm;
+// level 0 of the hierarchy shared among the ranks of a replicated solve (mg_vcycle)
+struct MgDist {
+    Comm *comm = nullptr;
+    int a = 0, b = 0;                 // global node columns [a, b) this rank owns
+    int64_t goff1[64], cnt1[64];      // per rank: start and length (doubles) of its part of the level-1 right-hand side
+};
+cudaError_t mg_vcycle(const LaunchCtx &lc, MgHierarchy &H, const double *r_fine, double *z_fine, int64_t *launches,
+                      const MgDist *dist = nullptr);
 
 }  // namespace plf

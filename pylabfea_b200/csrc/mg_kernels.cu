@@ -23,6 +23,7 @@
 
 #include "csr_stencil.cuh"
 #include "mg.h"
+#include "plf_comm.h"
 
 namespace plf {
 
@@ -192,11 +193,11 @@ __global__ void __launch_bounds__(128) mg_rap_kernel(int NXc, int NYc, const flo
 __global__ void __launch_bounds__(256) mg_jacobi_kernel(int NX, int NY, const float *__restrict__ val,
                                                         const double *__restrict__ dinv, const double *__restrict__ b,
                                                         const double *__restrict__ xin, double *__restrict__ xout, double omega,
-                                                        int first)
+                                                        int first, int64_t row0, int64_t row1)
 {
-    const int64_t row = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const int64_t nd = 2ll * (NX + 1) * (NY + 1);
-    if (row >= nd) return;
+    // [row0, row1): the rows this launch updates (all of them, or the rows a rank owns when level 0 is shared among ranks)
+    const int64_t row = row0 + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (row >= row1) return;
     const double di = dinv[row];   // 0 on masked rows: they stay 0
     if (first) { xout[row] = omega * di * b[row]; return; }
     const RowGeom g = row_geom(NX, NY, row);
@@ -207,11 +208,11 @@ __global__ void __launch_bounds__(256) mg_jacobi_kernel(int NX, int NY, const fl
 // r = b - A x (0 on masked rows)
 __global__ void __launch_bounds__(256) mg_residual_kernel(int NX, int NY, const float *__restrict__ val,
                                                           const unsigned char *__restrict__ mask, const double *__restrict__ b,
-                                                          const double *__restrict__ x, double *__restrict__ r)
+                                                          const double *__restrict__ x, double *__restrict__ r, int64_t row0,
+                                                          int64_t row1)
 {
-    const int64_t row = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const int64_t nd = 2ll * (NX + 1) * (NY + 1);
-    if (row >= nd) return;
+    const int64_t row = row0 + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (row >= row1) return;
     if (mask[row]) { r[row] = 0.; return; }
     const RowGeom g = row_geom(NX, NY, row);
     r[row] = b[row] - stencil_row_dot(NX, NY, g, val, x);
@@ -219,11 +220,11 @@ __global__ void __launch_bounds__(256) mg_residual_kernel(int NX, int NY, const 
 
 // b_c = P^T r_f
 __global__ void __launch_bounds__(256) mg_restrict_kernel(int NXc, int NYc, const double *__restrict__ r_f,
-                                                          const unsigned char *__restrict__ mask_c, double *__restrict__ b_c, int joff)
+                                                          const unsigned char *__restrict__ mask_c, double *__restrict__ b_c, int joff,
+                                                          int64_t row0, int64_t row1)
 {
-    const int64_t row = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const int64_t nc = 2ll * (NXc + 1) * (NYc + 1);
-    if (row >= nc) return;
+    const int64_t row = row0 + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (row >= row1) return;
     if (mask_c[row]) { b_c[row] = 0.; return; }
     const int NXf = 2 * NXc + joff, NYf = 2 * NYc, NnYf = NYf + 1;
     const int64_t n = row >> 1;
@@ -247,11 +248,11 @@ __global__ void __launch_bounds__(256) mg_restrict_kernel(int NXc, int NYc, cons
 
 // x_f += P x_c (masked fine dofs stay 0)
 __global__ void __launch_bounds__(256) mg_prolong_add_kernel(int NXf, int NYf, const double *__restrict__ x_c,
-                                                             const unsigned char *__restrict__ mask_f, double *__restrict__ x_f, int joff)
+                                                             const unsigned char *__restrict__ mask_f, double *__restrict__ x_f, int joff,
+                                                             int64_t row0, int64_t row1)
 {
-    const int64_t row = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const int64_t nf = 2ll * (NXf + 1) * (NYf + 1);
-    if (row >= nf) return;
+    const int64_t row = row0 + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (row >= row1) return;
     if (mask_f[row]) return;
     const int NYc = NYf / 2, NnYc = NYc + 1;
     const int64_t n = row >> 1;
@@ -670,50 +671,80 @@ cudaError_t mg_setup(const LaunchCtx &lc, MgHierarchy &H, const double *val_fine
 }
 
 // z = V(r): one V(nu, nu) cycle from a zero initial guess.  r and z are fine-level vectors (z must not alias r).
-cudaError_t mg_vcycle(const LaunchCtx &lc, MgHierarchy &H, const double *r_fine, double *z_fine, int64_t *launches)
+// dist != nullptr: level 0 is SHARED among the ranks of a replicated solve -- every rank holds the global vectors and the
+// global hierarchy, but smooths / forms the residual / restricts / prolongs only the level-0 rows of the node columns it
+// owns and swaps one ghost column with each neighbour after every step whose output the next stencil reads; the
+// right-hand side of level 1 is gathered from all ranks and the levels below run on every rank alike.
+cudaError_t mg_vcycle(const LaunchCtx &lc, MgHierarchy &H, const double *r_fine, double *z_fine, int64_t *launches, const MgDist *dist)
 {
     const int nl = (int)H.lv.size();
     const double om = H.omega;
     H.lv[0].b = const_cast<double *>(r_fine);
     H.lv[0].x = z_fine;
-    auto smooth = [&](MgLevel &L, int sweeps, bool from_zero) {
-        // result must end in L.x; sweeps alternate between L.x and L.t
+    bool comm_failed = false;
+    auto rows = [&](const MgLevel &L, int l, int64_t &r0, int64_t &r1) {   // rows a launch on level l works on
+        r0 = 0; r1 = L.ndof;
+        if (dist && l == 0) { r0 = 2ll * dist->a * (L.NY + 1); r1 = 2ll * dist->b * (L.NY + 1); }
+    };
+    auto swap_ghosts = [&](const MgLevel &L, int l, double *v) {
+        if (dist && l == 0 && comm_halo_exchange_cols(*dist->comm, v, L.NY, dist->a, dist->b, L.NX, lc.stream)) comm_failed = true;
+    };
+    auto jacobi = [&](MgLevel &L, int l, const double *in, double *out, int first) {
+        int64_t r0, r1;
+        rows(L, l, r0, r1);
+        mg_jacobi_kernel<<<grid_for(r1 - r0, 256), 256, 0, lc.stream>>>(L.NX, L.NY, L.val, L.dinv, L.b, in, out, om, first, r0, r1);
+        (*launches)++;
+    };
+    auto smooth = [&](MgLevel &L, int l, int sweeps, bool from_zero, bool last_needs_ghosts) {
+        // the result ends in L.x; sweeps alternate between L.x and L.t (from zero the first sweep has no input and writes the
+        // buffer that makes the last one land in L.x; otherwise the input is L.x and the number of sweeps is even)
         double *cur = L.x, *oth = L.t;
-        int first = from_zero ? 1 : 0;
-        // choose the starting buffer so that the last sweep writes L.x
-        // (from zero: the first sweep has no input; otherwise the input is L.x)
+        int s0 = 0;
         if (from_zero) {
-            double *out = (sweeps & 1) ? L.x : L.t;
-            mg_jacobi_kernel<<<grid_for(L.ndof, 256), 256, 0, lc.stream>>>(L.NX, L.NY, L.val, L.dinv, L.b, nullptr, out, om, 1);
-            (*launches)++;
-            cur = out; oth = (out == L.x) ? L.t : L.x;
-            for (int s = 1; s < sweeps; s++) {
-                mg_jacobi_kernel<<<grid_for(L.ndof, 256), 256, 0, lc.stream>>>(L.NX, L.NY, L.val, L.dinv, L.b, cur, oth, om, 0);
-                (*launches)++;
-                std::swap(cur, oth);
-            }
-        } else {
-            // even number of sweeps keeps the result in L.x
-            for (int s = 0; s < sweeps; s++) {
-                mg_jacobi_kernel<<<grid_for(L.ndof, 256), 256, 0, lc.stream>>>(L.NX, L.NY, L.val, L.dinv, L.b, cur, oth, om, 0);
-                (*launches)++;
-                std::swap(cur, oth);
-            }
+            cur = (sweeps & 1) ? L.x : L.t;
+            oth = (cur == L.x) ? L.t : L.x;
+            jacobi(L, l, nullptr, cur, 1);
+            if (sweeps > 1 || last_needs_ghosts) swap_ghosts(L, l, cur);
+            s0 = 1;
         }
-        (void)first;
+        for (int s = s0; s < sweeps; s++) {
+            jacobi(L, l, cur, oth, 0);
+            std::swap(cur, oth);
+            if (s + 1 < sweeps || last_needs_ghosts) swap_ghosts(L, l, cur);
+        }
+    };
+    auto down = [&](int l) {
+        MgLevel &L = H.lv[l], &C = H.lv[l + 1];
+        smooth(L, l, H.nu, true, true);
+        int64_t r0, r1;
+        rows(L, l, r0, r1);
+        mg_residual_kernel<<<grid_for(r1 - r0, 256), 256, 0, lc.stream>>>(L.NX, L.NY, L.val, L.mask, L.b, L.x, L.r, r0, r1);
+        swap_ghosts(L, l, L.r);
+        int64_t c0 = 0, c1 = C.ndof;
+        if (dist && l == 0) { c0 = 2ll * ((dist->a + 1) / 2) * (C.NY + 1); c1 = 2ll * ((dist->b + 1) / 2) * (C.NY + 1); }
+        mg_restrict_kernel<<<grid_for(c1 - c0, 256), 256, 0, lc.stream>>>(C.NX, C.NY, L.r, C.mask, C.b, l == 0 ? H.j0 : 0, c0, c1);
+        *launches += 2;
+        if (dist && l == 0 && comm_gather_ranges(*dist->comm, C.b + dist->goff1[dist->comm->rank], C.b, dist->goff1, dist->cnt1, lc.stream))
+            comm_failed = true;
+    };
+    auto up = [&](int l) {
+        MgLevel &L = H.lv[l], &C = H.lv[l + 1];
+        int64_t r0, r1;
+        rows(L, l, r0, r1);
+        if (dist && l == 0) {   // the ghost columns too: the coarse solution is complete on every rank, no exchange needed
+            r0 = 2ll * std::max(dist->a - 1, 0) * (L.NY + 1);
+            r1 = 2ll * std::min(dist->b + 1, L.NX + 1) * (L.NY + 1);
+        }
+        mg_prolong_add_kernel<<<grid_for(r1 - r0, 256), 256, 0, lc.stream>>>(L.NX, L.NY, C.x, L.mask, L.x, l == 0 ? H.j0 : 0, r0, r1);
+        (*launches)++;
+        smooth(L, l, H.nu, false, false);
     };
     // levels [0, mid) run as per-level kernels, [mid, top) in the cooperative grid kernel, [top, nl) in the fused
     // single-block tail (inside the cooperative kernel when there is one)
     int top = (H.fuse_tail && H.tail_first > 0) ? H.tail_first : nl;
     const int mid = (H.fuse_tail >= 2 && H.coop_first > 0 && H.coop_first < top) ? H.coop_first : -1;
     if (mid > 0) {
-        for (int l = 0; l < mid; l++) {
-            MgLevel &L = H.lv[l], &C = H.lv[l + 1];
-            smooth(L, H.nu, true);
-            mg_residual_kernel<<<grid_for(L.ndof, 256), 256, 0, lc.stream>>>(L.NX, L.NY, L.val, L.mask, L.b, L.x, L.r);
-            mg_restrict_kernel<<<grid_for(C.ndof, 256), 256, 0, lc.stream>>>(C.NX, C.NY, L.r, C.mask, C.b, l == 0 ? H.j0 : 0);
-            *launches += 2;
-        }
+        for (int l = 0; l < mid; l++) down(l);
         CoopArgs A;
         memset(&A, 0, sizeof A);
         A.nmid = std::min(top, nl - 1) - mid;          // the coarsest level is never a "mid" level: it has no level below
@@ -748,21 +779,10 @@ cudaError_t mg_vcycle(const LaunchCtx &lc, MgHierarchy &H, const double *r_fine,
         cudaError_t e = cudaLaunchKernelEx(&cfg, mg_coop_kernel, A, H.d_bar);
         if (e != cudaSuccess) return e;
         (*launches)++;
-        for (int l = mid - 1; l >= 0; l--) {
-            MgLevel &L = H.lv[l], &C = H.lv[l + 1];
-            mg_prolong_add_kernel<<<grid_for(L.ndof, 256), 256, 0, lc.stream>>>(L.NX, L.NY, C.x, L.mask, L.x, l == 0 ? H.j0 : 0);
-            (*launches)++;
-            smooth(L, H.nu, false);
-        }
-        return cudaGetLastError();
+        for (int l = mid - 1; l >= 0; l--) up(l);
+        return comm_failed ? cudaErrorUnknown : cudaGetLastError();
     }
-    for (int l = 0; l < std::min(top, nl - 1); l++) {
-        MgLevel &L = H.lv[l], &C = H.lv[l + 1];
-        smooth(L, H.nu, true);
-        mg_residual_kernel<<<grid_for(L.ndof, 256), 256, 0, lc.stream>>>(L.NX, L.NY, L.val, L.mask, L.b, L.x, L.r);
-        mg_restrict_kernel<<<grid_for(C.ndof, 256), 256, 0, lc.stream>>>(C.NX, C.NY, L.r, C.mask, C.b, l == 0 ? H.j0 : 0);
-        *launches += 2;
-    }
+    for (int l = 0; l < std::min(top, nl - 1); l++) down(l);
     if (top < nl) {
         TailArgs A;
         int off = 0;
@@ -777,15 +797,10 @@ cudaError_t mg_vcycle(const LaunchCtx &lc, MgHierarchy &H, const double *r_fine,
         mg_tail_kernel<<<1, 1024, 5 * (size_t)off * sizeof(double), lc.stream>>>(A);
         (*launches)++;
     } else {
-        smooth(H.lv[nl - 1], H.coarse_sweeps, true);
+        smooth(H.lv[nl - 1], nl - 1, H.coarse_sweeps, true, false);
     }
-    for (int l = std::min(top, nl - 1) - 1; l >= 0; l--) {
-        MgLevel &L = H.lv[l], &C = H.lv[l + 1];
-        mg_prolong_add_kernel<<<grid_for(L.ndof, 256), 256, 0, lc.stream>>>(L.NX, L.NY, C.x, L.mask, L.x, l == 0 ? H.j0 : 0);
-        (*launches)++;
-        smooth(L, H.nu, false);
-    }
-    return cudaGetLastError();
+    for (int l = std::min(top, nl - 1) - 1; l >= 0; l--) up(l);
+    return comm_failed ? cudaErrorUnknown : cudaGetLastError();
 }
 
 }  // namespace plf

@@ -678,12 +678,12 @@ __global__ void __launch_bounds__(256) spmv_kernel(int64_t nrows, const int32_t 
 __global__ void __launch_bounds__(256) stencil_spmv_dot_kernel(int NX, int NY, const double *__restrict__ val,
                                                                const double *__restrict__ x, double *__restrict__ y,
                                                                const unsigned char *__restrict__ masked, double *partial,
-                                                               unsigned int *counter, double *dot_out)
+                                                               unsigned int *counter, double *dot_out, int64_t row0, int64_t row1)
 {
+    // [row0, row1): all rows, or the rows of the node columns a rank owns (replicated solve with a shared level 0)
     const int NnY = NY + 1;
-    const int64_t nd = 2ll * (NX + 1) * NnY;
     double xy = 0.;
-    for (int64_t row = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; row < nd; row += (int64_t)gridDim.x * blockDim.x) {
+    for (int64_t row = row0 + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; row < row1; row += (int64_t)gridDim.x * blockDim.x) {
         const int64_t n = row >> 1;
         const int j = (int)(n / NnY), k = (int)(n - (int64_t)j * NnY);
         int64_t pos = csr_row_start(NX, NY, row);
@@ -1019,7 +1019,7 @@ cudaError_t launch_cg(const LaunchCtx &lc, int64_t n, const int32_t *rowptr, con
     int64_t chunk_launches = 0;
     auto enqueue_chunk = [&]() {
         for (int c = 0; c < check_every; c += 2) {
-            if (NX > 0) stencil_spmv_dot_kernel<<<vg, 256, 0, lc.stream>>>(NX, NY, val, p, q, fixed, partial, counter, &sc->pq);
+            if (NX > 0) stencil_spmv_dot_kernel<<<vg, 256, 0, lc.stream>>>(NX, NY, val, p, q, fixed, partial, counter, &sc->pq, 0, n);
             else spmv_kernel<<<sg, 256, 0, lc.stream>>>(n, rowptr, col, val, p, nullptr, q, fixed, 0, partial, counter, &sc->pq);
             if (mg) {
                 cg_update_kernel<0, true><<<vg, 256, 0, lc.stream>>>(n, x, r, z, p, q, diag, fixed, sc, partial, counter);
@@ -1030,7 +1030,7 @@ cudaError_t launch_cg(const LaunchCtx &lc, int64_t n, const int32_t *rowptr, con
                 cg_update_kernel<0, false><<<vg, 256, 0, lc.stream>>>(n, x, r, z, p, q, diag, fixed, sc, partial, counter);
             }
             cg_p_kernel<0><<<vg, 256, 0, lc.stream>>>(n, p, z, sc);
-            if (NX > 0) stencil_spmv_dot_kernel<<<vg, 256, 0, lc.stream>>>(NX, NY, val, p, q, fixed, partial, counter, &sc->pq);
+            if (NX > 0) stencil_spmv_dot_kernel<<<vg, 256, 0, lc.stream>>>(NX, NY, val, p, q, fixed, partial, counter, &sc->pq, 0, n);
             else spmv_kernel<<<sg, 256, 0, lc.stream>>>(n, rowptr, col, val, p, nullptr, q, fixed, 0, partial, counter, &sc->pq);
             if (mg) {
                 cg_update_kernel<1, true><<<vg, 256, 0, lc.stream>>>(n, x, r, z, p, q, diag, fixed, sc, partial, counter);
@@ -1136,7 +1136,7 @@ cudaError_t launch_cg_dist(const LaunchCtx &lc, Comm &comm, int64_t n, const int
     while (it < max_iter) {
         for (int c = 0; c < check_every; c += 2) {
             PLF_NC(comm_halo_exchange(comm, p, NX, NY, lc.stream));
-            stencil_spmv_dot_kernel<<<vg, 256, 0, lc.stream>>>(NX, NY, val, p, q, mask, partial, counter, &sc->pq);
+            stencil_spmv_dot_kernel<<<vg, 256, 0, lc.stream>>>(NX, NY, val, p, q, mask, partial, counter, &sc->pq, 0, n);
             PLF_NC(comm_allreduce_sum(comm, &sc->pq, 1, lc.stream));
             if (mg) {
                 cg_update_kernel<0, true, true><<<vg, 256, 0, lc.stream>>>(n, x, r, z, p, q, diag, mask, sc, partial, counter);
@@ -1150,7 +1150,7 @@ cudaError_t launch_cg_dist(const LaunchCtx &lc, Comm &comm, int64_t n, const int
             cg_publish_kernel<0><<<1, 1, 0, lc.stream>>>(sc);
             cg_p_kernel<0><<<vg, 256, 0, lc.stream>>>(n, p, z, sc);
             PLF_NC(comm_halo_exchange(comm, p, NX, NY, lc.stream));
-            stencil_spmv_dot_kernel<<<vg, 256, 0, lc.stream>>>(NX, NY, val, p, q, mask, partial, counter, &sc->pq);
+            stencil_spmv_dot_kernel<<<vg, 256, 0, lc.stream>>>(NX, NY, val, p, q, mask, partial, counter, &sc->pq, 0, n);
             PLF_NC(comm_allreduce_sum(comm, &sc->pq, 1, lc.stream));
             if (mg) {
                 cg_update_kernel<1, true, true><<<vg, 256, 0, lc.stream>>>(n, x, r, z, p, q, diag, mask, sc, partial, counter);
@@ -1173,6 +1173,95 @@ cudaError_t launch_cg_dist(const LaunchCtx &lc, Comm &comm, int64_t n, const int
     }
 #undef PLF_NC
     *iters = (int)hs->iters;
+    return cudaGetLastError();
+}
+
+// CG of the replicated solve with level 0 shared among the ranks (plf_comm_set_replica, option solver_hybrid).  Every rank
+// holds the GLOBAL matrix, hierarchy and vectors, but updates only the rows of the node columns [a, b) it owns: per iteration
+// one ghost column of p per neighbour, q = K p and p.q on the owned rows, all-reduce, update of x and r on the owned rows,
+// the V-cycle (mg_vcycle with MgDist: its level 0 split the same way, the levels below on every rank alike), all-reduce of
+// (r.z, r.r), direction.  Same iterates as the single-GPU solver up to the summation order of the dot products.  `mask` =
+// fixed | not owned, so the vector kernels of the single-GPU solver apply unchanged to the owned range.
+cudaError_t launch_cg_hybrid(const LaunchCtx &lc, Comm &comm, int a_col, int b_col, int64_t n, const int32_t *rowptr, const int32_t *col,
+                             const double *val, const unsigned char *mask, const double *b, double *x, double *r, double *z,
+                             double *p, double *q, double *diag, double *partial, unsigned int *counter, void *d_sc, void *h_sc,
+                             double rtol, int max_iter, int *iters, double *relres, int64_t *launches, int warm, int NX, int NY,
+                             MgHierarchy &mg, const MgDist &md, int mg_setup_needed, const unsigned char *fixed)
+{
+    CgScalars *sc = (CgScalars *)d_sc;
+    CgScalars *hs = (CgScalars *)h_sc;
+    const int64_t r0 = 2ll * a_col * (NY + 1), r1 = 2ll * b_col * (NY + 1), m = r1 - r0;   // owned rows
+    const unsigned vg = vec_grid(m, lc.sm_count);
+    cudaError_t e;
+#define PLF_NC(call) do { if (call) return cudaErrorUnknown; } while (0)
+    diag_kernel<<<(unsigned)((n + 255) / 256), 256, 0, lc.stream>>>(n, rowptr, col, val, diag);
+    if (warm) {
+        cg_mask_x_kernel<<<vg, 256, 0, lc.stream>>>(m, x + r0, mask + r0);
+        PLF_NC(comm_halo_exchange_cols(comm, x, NY, a_col, b_col, NX, lc.stream));
+        stencil_spmv_dot_kernel<<<vg, 256, 0, lc.stream>>>(NX, NY, val, x, q, mask, partial, counter, &sc->pq, r0, r1);
+        cg_init_warm_kernel<<<vg, 256, 0, lc.stream>>>(m, b + r0, q + r0, r + r0, z + r0, p + r0, diag + r0, mask + r0, sc, rtol, partial, counter);
+        *launches += 4;
+    } else {
+        cg_init_kernel<<<vg, 256, 0, lc.stream>>>(m, b + r0, x + r0, r + r0, z + r0, p + r0, diag + r0, mask + r0, sc, rtol, partial, counter);
+        *launches += 2;
+    }
+    PLF_NC(comm_allreduce_sum(comm, reinterpret_cast<double *>(sc), 7, lc.stream));
+    if ((e = cudaMemcpyAsync(hs, sc, sizeof(CgScalars), cudaMemcpyDeviceToHost, lc.stream)) != cudaSuccess) return e;
+    if ((e = cudaStreamSynchronize(lc.stream)) != cudaSuccess) return e;
+    const double bb = warm ? hs->tmp[1] : hs->rr;
+    *iters = 0;
+    *relres = 0.;
+    if (bb == 0.) {
+        if (warm) cudaMemsetAsync(x, 0, (size_t)n * sizeof(double), lc.stream);
+        return cudaSuccess;
+    }
+    const double target = hs->target;
+    if (warm && !(hs->rr > target)) {
+        *relres = sqrt(hs->rr / bb);
+        return cudaSuccess;
+    }
+    // the hierarchy is the global one on every rank (masks, Galerkin products, inverse diagonals from the gathered K)
+    if (mg_setup_needed && (e = mg_setup(lc, mg, val, fixed, launches)) != cudaSuccess) return e;
+    if ((e = mg_vcycle(lc, mg, r, z, launches, &md)) != cudaSuccess) return e;
+    cg_rz_kernel<0, true><<<vg, 256, 0, lc.stream>>>(m, r + r0, z + r0, mask + r0, sc, partial, counter);
+    PLF_NC(comm_allreduce_sum(comm, sc->tmp, 1, lc.stream));
+    cg_publish_init_kernel<<<1, 1, 0, lc.stream>>>(sc);
+    *launches += 2;
+    if ((e = cudaMemcpyAsync(p + r0, z + r0, (size_t)m * sizeof(double), cudaMemcpyDeviceToDevice, lc.stream)) != cudaSuccess) return e;
+    int it = 0;
+    const int check_every = 4;
+    while (it < max_iter) {
+        for (int c = 0; c < check_every; c += 2) {
+            PLF_NC(comm_halo_exchange_cols(comm, p, NY, a_col, b_col, NX, lc.stream));
+            stencil_spmv_dot_kernel<<<vg, 256, 0, lc.stream>>>(NX, NY, val, p, q, mask, partial, counter, &sc->pq, r0, r1);
+            PLF_NC(comm_allreduce_sum(comm, &sc->pq, 1, lc.stream));
+            cg_update_kernel<0, true, true><<<vg, 256, 0, lc.stream>>>(m, x + r0, r + r0, z + r0, p + r0, q + r0, diag + r0, mask + r0, sc, partial, counter);
+            if ((e = mg_vcycle(lc, mg, r, z, launches, &md)) != cudaSuccess) return e;
+            cg_rz_kernel<1, true><<<vg, 256, 0, lc.stream>>>(m, r + r0, z + r0, mask + r0, sc, partial, counter);
+            PLF_NC(comm_allreduce_sum(comm, sc->tmp, 2, lc.stream));
+            cg_publish_kernel<0><<<1, 1, 0, lc.stream>>>(sc);
+            cg_p_kernel<0><<<vg, 256, 0, lc.stream>>>(m, p + r0, z + r0, sc);
+            PLF_NC(comm_halo_exchange_cols(comm, p, NY, a_col, b_col, NX, lc.stream));
+            stencil_spmv_dot_kernel<<<vg, 256, 0, lc.stream>>>(NX, NY, val, p, q, mask, partial, counter, &sc->pq, r0, r1);
+            PLF_NC(comm_allreduce_sum(comm, &sc->pq, 1, lc.stream));
+            cg_update_kernel<1, true, true><<<vg, 256, 0, lc.stream>>>(m, x + r0, r + r0, z + r0, p + r0, q + r0, diag + r0, mask + r0, sc, partial, counter);
+            if ((e = mg_vcycle(lc, mg, r, z, launches, &md)) != cudaSuccess) return e;
+            cg_rz_kernel<0, true><<<vg, 256, 0, lc.stream>>>(m, r + r0, z + r0, mask + r0, sc, partial, counter);
+            PLF_NC(comm_allreduce_sum(comm, sc->tmp, 2, lc.stream));
+            cg_publish_kernel<1><<<1, 1, 0, lc.stream>>>(sc);
+            cg_p_kernel<1><<<vg, 256, 0, lc.stream>>>(m, p + r0, z + r0, sc);
+            *launches += 10;
+        }
+        it += check_every;
+        if ((e = cudaMemcpyAsync(hs, sc, sizeof(CgScalars), cudaMemcpyDeviceToHost, lc.stream)) != cudaSuccess) return e;
+        if ((e = cudaStreamSynchronize(lc.stream)) != cudaSuccess) return e;
+        *relres = sqrt(hs->rr / bb);
+        if (!(hs->rr > target)) break;
+    }
+#undef PLF_NC
+    *iters = (int)hs->iters;
+    // ghost columns of the solution from their owners: the strip of du a rank copies out covers its halo / ghost columns
+    if (comm_halo_exchange_cols(comm, x, NY, a_col, b_col, NX, lc.stream)) return cudaErrorUnknown;
     return cudaGetLastError();
 }
 

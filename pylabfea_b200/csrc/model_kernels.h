@@ -63,6 +63,12 @@ cudaError_t launch_cg_dist(const LaunchCtx &lc, Comm &comm, int64_t n, const int
                            double *diag, double *partial, unsigned int *counter, void *d_sc, void *h_sc, double rtol,
                            int max_iter, int check_every, int *iters, double *relres, int64_t *launches, int warm, int NX, int NY,
                            MgHierarchy *mg = nullptr /* local V-cycle as preconditioner; nullptr: Jacobi */, int mg_setup_needed = 1);
+struct MgDist;
+cudaError_t launch_cg_hybrid(const LaunchCtx &lc, Comm &comm, int a_col, int b_col, int64_t n, const int32_t *rowptr, const int32_t *col,
+                             const double *val, const unsigned char *mask, const double *b, double *x, double *r, double *z,
+                             double *p, double *q, double *diag, double *partial, unsigned int *counter, void *d_sc, void *h_sc,
+                             double rtol, int max_iter, int *iters, double *relres, int64_t *launches, int warm, int NX, int NY,
+                             MgHierarchy &mg, const MgDist &md, int mg_setup_needed, const unsigned char *fixed);
 cudaError_t launch_ghost_mask(const LaunchCtx &lc, int64_t n, int NY, int own_first, int own_end, const unsigned char *fixed,
                               unsigned char *mask, int64_t *launches);
 cudaError_t launch_merge_du(const LaunchCtx &lc, int64_t n, const double *x, const double *du_bc, const unsigned char *fixed, double *du,

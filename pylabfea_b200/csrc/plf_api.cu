@@ -489,6 +489,7 @@ extern "C" int plf_set_option(plf_ctx *ctx, const char *key, int value)
     if (!strcmp(key, "solver_mg")) { ctx->solver_mg = value; return PLF_OK; }
     if (!strcmp(key, "solver_warm")) { ctx->solver_warm = value; return PLF_OK; }
     if (!strcmp(key, "skip_unchanged")) { ctx->skip_unchanged = value; return PLF_OK; }
+    if (!strcmp(key, "solver_hybrid")) { ctx->solver_hybrid = value; return PLF_OK; }
     if (!strcmp(key, "mg_nu") || !strcmp(key, "mg_coarse_sweeps") || !strcmp(key, "mg_omega_permille") || !strcmp(key, "mg_fuse_tail")) {
         // multigrid tuning knobs (take effect at the next plf_mesh_structured / solve; the CG graph is rebuilt)
         if (!strcmp(key, "mg_nu")) ctx->mg_nu = value & ~1;

@@ -121,6 +121,25 @@ int comm_allreduce_op(Comm &c, double *dbuf, int count, int op, cudaStream_t s)
     return 0;
 }
 
+int comm_halo_exchange_cols(Comm &c, double *vec, int NY, int a, int b, int NX, cudaStream_t s)
+{
+    const bool left = a > 0 && c.rank > 0, right = b <= NX && c.rank + 1 < c.world;
+    if (!left && !right) return 0;
+    const size_t ncol = 2 * (size_t)(NY + 1);
+    ncclComm_t comm = (ncclComm_t)c.nccl;
+    NC(g_nccl.GroupStart(), "ncclGroupStart");
+    if (left) {
+        NC(g_nccl.Send(vec + ncol * (size_t)a, ncol, ncclDouble, c.rank - 1, comm, s), "ncclSend");
+        NC(g_nccl.Recv(vec + ncol * (size_t)(a - 1), ncol, ncclDouble, c.rank - 1, comm, s), "ncclRecv");
+    }
+    if (right) {
+        NC(g_nccl.Send(vec + ncol * (size_t)(b - 1), ncol, ncclDouble, c.rank + 1, comm, s), "ncclSend");
+        NC(g_nccl.Recv(vec + ncol * (size_t)b, ncol, ncclDouble, c.rank + 1, comm, s), "ncclRecv");
+    }
+    NC(g_nccl.GroupEnd(), "ncclGroupEnd");
+    return 0;
+}
+
 // Every rank contributes one contiguous range of doubles to the same global array on all ranks: rank r's range is
 // [goff[r], goff[r] + cnt[r]) of `global`; its own data sits at `mine`.  One broadcast per rank, grouped.
 int comm_gather_ranges(Comm &c, const double *mine, double *global, const int64_t *goff, const int64_t *cnt, cudaStream_t s)

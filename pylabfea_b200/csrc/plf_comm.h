@@ -34,6 +34,9 @@ int comm_allreduce_op(Comm &c, double *dbuf, int count, int op /* 0 sum, 1 max, 
 // vec: nodal vector of the local (NX+1) x (NY+1) node grid, 2 dofs per node.  Sends the first / last owned node column to
 // the left / right neighbour and receives their last / first owned column into the ghost columns.
 int comm_halo_exchange(Comm &c, double *vec, int NX, int NY, cudaStream_t s);
+// the same exchange on a GLOBAL nodal vector (every rank holds all node columns 0 .. NX, owns [a, b)): column a goes to the
+// left neighbour and column a - 1 comes back, column b - 1 goes to the right neighbour and column b comes back
+int comm_halo_exchange_cols(Comm &c, double *vec, int NY, int a, int b, int NX, cudaStream_t s);
 int comm_gather_ranges(Comm &c, const double *mine, double *global, const int64_t *goff, const int64_t *cnt, cudaStream_t s);
 const char *comm_error();
 

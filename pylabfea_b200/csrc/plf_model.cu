@@ -755,6 +755,38 @@ int model_solve_device_bc(plf_ctx *ctx, double rtol, int max_iter, int *iters, d
     }
     // multigrid V-cycle preconditioner when the mesh coarsens at least once (mesh-independent iteration counts), else Jacobi
     const bool use_mg = ctx->solver_mg && ctx->mg && ctx->mg->levels() >= 2;
+    if (ctx->share_comm && use_mg) {
+        // replicated solve, level 0 and the CG vectors shared among the ranks (launch_cg_hybrid)
+        Comm &c = *ctx->share_comm;
+        const int a = ctx->share_a, bcol = ctx->share_b;
+        if (!ctx->d_cgmask && (rc = dalloc(ctx, &ctx->d_cgmask, D))) return rc;
+        CK(launch_ghost_mask(lc, ctx->Ndof, ctx->NY, a, bcol, ctx->d_fixed, ctx->d_cgmask, &ctx->launches));
+        MgDist md;
+        md.comm = &c; md.a = a; md.b = bcol;
+        const MgLevel &L1 = ctx->mg->lv[1];
+        for (int r = 0; r < c.world; r++) {
+            const int ar = (int)((int64_t)ctx->NX * r / c.world), br = (int)((int64_t)ctx->NX * (r + 1) / c.world) + (r == c.world - 1 ? 1 : 0);
+            md.goff1[r] = 2ll * ((ar + 1) / 2) * (L1.NY + 1);
+            md.cnt1[r] = 2ll * ((br + 1) / 2) * (L1.NY + 1) - md.goff1[r];
+        }
+        const bool fresh = ctx->skip_unchanged && ctx->mg_K_serial == ctx->K_serial && ctx->mg_mask_epoch == ctx->mask_epoch;
+        ctx->mg_K_serial = ctx->K_serial; ctx->mg_mask_epoch = ctx->mask_epoch;
+        cudaError_t ce = launch_cg_hybrid(lc, c, a, bcol, ctx->Ndof, ctx->d_rowptr, ctx->d_col, ctx->d_val, ctx->d_cgmask, ctx->d_b, x, ctx->d_r,
+                                          ctx->d_z, ctx->d_p, ctx->d_q, ctx->d_diag, ctx->d_partial, counter_ptr(ctx), ctx->d_scalars + 256,
+                                          ctx->h_scalars + 256, rtol, max_iter, &it, &rr, &ctx->launches, ctx->solver_warm, ctx->NX, ctx->NY,
+                                          *ctx->mg, md, fresh ? 0 : 1, ctx->d_fixed);
+        if (ce != cudaSuccess)
+            return fail(ctx, PLF_ECUDA, std::string("plf_solve_linear (shared level 0): ") +
+                                            (ce == cudaErrorUnknown && comm_error()[0] ? comm_error() : cudaGetErrorString(ce)));
+        CK(launch_merge_du(lc, ctx->Ndof, x, ctx->d_bc_du, ctx->d_fixed, ctx->d_du, &ctx->launches));
+        CK(cudaStreamSynchronize(ctx->stream));
+        if (iters) *iters = it;
+        if (relres) *relres = rr;
+        if (!(rr <= rtol))
+            return fail(ctx, PLF_ENOCONV, "plf_solve_linear: CG (shared level 0) stopped after " + std::to_string(it) +
+                                              " iterations with relative residual " + std::to_string(rr));
+        return PLF_OK;
+    }
     // same K and same Dirichlet mask as at the previous solve: the Galerkin hierarchy is still valid
     const bool mg_fresh = use_mg && ctx->skip_unchanged && ctx->mg_K_serial == ctx->K_serial && ctx->mg_mask_epoch == ctx->mask_epoch;
     if (use_mg) { ctx->mg_K_serial = ctx->K_serial; ctx->mg_mask_epoch = ctx->mask_epoch; }

@@ -104,6 +104,12 @@ struct plf_ctx {
     // sequence) re-uploads when the banks hold another context's tables or stale ones.
     bool tables_dirty = true;
     plf_solve_state *solve = nullptr;   // set by plf_solve_begin
+    // set on the GLOBAL context of a replicated solve while level 0 of its solver is shared among the ranks (solver_hybrid):
+    // the communicator of the strip context and the global node columns [share_a, share_b) this rank owns
+    plf::Comm *share_comm = nullptr;
+    int share_a = 0, share_b = 0;
+    int solver_hybrid = 0;              // option (on the strip context): 1 share level 0 + CG of the replicated solve among the ranks
+                                        // (same iterates; ~12 NCCL calls per iteration: pays only with low-latency exchanges)
     plf_ctx *replica = nullptr;         // plf_comm_set_replica: context holding the GLOBAL mesh, solves the gathered system (not owned)
     // change tracking, so that an unchanged K is neither re-assembled nor re-coarsened: tangent_epoch moves whenever
     // element tangents change (plf_set_tangent, a sweep that replaced one), K_serial with every assembly, mask_epoch

@@ -10,7 +10,9 @@
 // sweep flags, calc_scf moments, the calc_global sums and the boundary sums are combined over the ranks, so all ranks
 // take identical decisions.
 #include <algorithm>
+#include <chrono>
 #include <cmath>
+#include <cstdlib>
 #include <cstdio>
 #include <cstring>
 #include <string>
@@ -340,14 +342,34 @@ static int solve_replicated(plf_ctx *ctx, const double *dr, const double *dt, co
     CK(cudaSetDevice(ctx->device));
     // the global context works on its own stream: order it behind this context's assembly and ahead of what follows
     CK(cudaStreamSynchronize(ctx->stream));
+    static const bool timing = getenv("PLF_TIMING") != nullptr;   // diagnostics: where a replicated solve spends its time
+    static double t_gather = 0., t_solve = 0.;
+    static int n_calls = 0;
+    const auto t0 = std::chrono::steady_clock::now();
     if (comm_gather_ranges(c, ctx->d_val + lo, g->d_val, goff, cnt, g->stream))
         return fail(ctx, PLF_ECUDA, std::string("replicated solve: ") + comm_error());
+    if (timing) CK(cudaStreamSynchronize(g->stream));
+    const auto t1 = std::chrono::steady_clock::now();
     g->K_ready = true;
     g->K_tangent_epoch = 0;
     g->K_serial++;
     int rc = build_bc_vectors(g, dr, dt, dn, rep);
     if (rc != PLF_OK) { ctx->err = g->err; return rc; }
+    // every rank solves the gathered system; with solver_hybrid the CG vectors and level 0 of the V-cycle are split over the
+    // node columns the ranks own (the levels below stay replicated)
+    const bool share = ctx->solver_hybrid && c.world > 1;
+    g->share_comm = share ? &c : nullptr;
+    g->share_a = (int)((int64_t)NXg * c.rank / c.world);
+    g->share_b = (int)((int64_t)NXg * (c.rank + 1) / c.world) + (c.rank == c.world - 1 ? 1 : 0);
     rc = model_solve_device_bc(g, rtol, max_iter, it, rr);
+    g->share_comm = nullptr;
+    if (timing) {
+        const auto t2 = std::chrono::steady_clock::now();
+        t_gather += std::chrono::duration<double>(t1 - t0).count();
+        t_solve += std::chrono::duration<double>(t2 - t1).count();
+        if (++n_calls % 50 == 0 && c.rank == 0)
+            fprintf(stderr, "[plf timing] %d replicated solves: gather %.3f s, BC + solve %.3f s\n", n_calls, t_gather, t_solve);
+    }
     if (rc != PLF_OK) { ctx->err = g->err; return rc; }
     CK(cudaMemcpyAsync(ctx->d_du, g->d_du + 2 * (size_t)(NY + 1) * (size_t)c.first_col_global, (size_t)ctx->Ndof * sizeof(double),
                        cudaMemcpyDeviceToDevice, g->stream));
