@@ -120,7 +120,9 @@ int plf_pinned_free(void *p);
  *   "passa_bulk"   1: pass A with cp.async.bulk / mbarrier (TMA engine) instead of the cp.async ring (default 0: measured slower)
  *   "mg_fuse_tail" 2 (default): coarse levels of the V-cycle in one cooperative kernel + one fused block; 1: fused block only; 0: per level
  *   "skip_unchanged" 1 (default): an unchanged K is neither re-assembled nor re-coarsened
- *   "solver_hybrid" replicated multi-GPU solve: 1 = CG vectors and level 0 of the V-cycle split over the ranks (default 0) */
+ *   "solver_hybrid" replicated multi-GPU solve: the CG vectors and the finest levels of the V-cycle (level 0, and every further
+ *                   level of >= 1 M dofs) split over the ranks, one ghost column swapped per stencil step: 0 never, 1 always,
+ *                   2 (default) when the exchanges run through peer mailboxes (plf_comm_p2p) */
 int plf_set_option(plf_ctx *ctx, const char *key, int value);
 
 /* ---- materials ------------------------------------------------------------------------------------------- */
@@ -321,6 +323,11 @@ int plf_comm_set_partition(plf_ctx *ctx, int own_first, int own_end, int first_c
  * "NCCL allreduce on the assembled system" variant: no communication inside the solve, the solve itself is not sharded.
  * Pass NULL to return to the strip-partitioned CG. */
 int plf_comm_set_replica(plf_ctx *ctx, plf_ctx *global_ctx);
+/* 1 when the halo columns and all-reduce scalars of this context travel through peer mailboxes -- every rank maps one device
+ * buffer of every other rank with CUDA IPC at plf_comm_set_strip, and an exchange is ONE kernel that stores into the peers'
+ * HBM over NVLink, releases a flag and spins on its own -- 0 when they go through NCCL (no IPC between the ranks, or the
+ * environment variable PLF_P2P=0).  The results are the same bits either way (all-reduces sum in rank order). */
+int plf_comm_p2p(plf_ctx *ctx);
 /* sum of n <= 64 host doubles over all ranks, in place (sweep flags, calc_global sums, calc_scf moments) */
 int plf_comm_allreduce(plf_ctx *ctx, double *vals, int n);
 int plf_comm_destroy(plf_ctx *ctx);

@@ -460,6 +460,11 @@ class Context:
         self._replica = global_ctx
         self._ck(self.L.plf_comm_set_replica(self.h, None if global_ctx is None else global_ctx.h))
 
+    def comm_p2p(self):
+        """True when halo columns and all-reduce scalars travel through CUDA-IPC peer mailboxes (one kernel per exchange over
+        NVLink) rather than NCCL; decided collectively in comm_set_strip."""
+        return bool(self.L.plf_comm_p2p(self.h))
+
     def comm_allreduce(self, vals):
         """Sum of a small float vector over all ranks."""
         a = np.array(vals, dtype=np.float64).ravel()

@@ -35,12 +35,16 @@ cudaError_t mg_build(MgHierarchy &H, int NX, int NY, int j0 = 0);
 void mg_free(MgHierarchy &H);
 cudaError_t mg_setup(const LaunchCtx &lc, MgHierarchy &H, const double *val_fine, const unsigned char *mask_fine, int64_t *launches);
 struct Comm;
-// level 0 of the hierarchy shared among the ranks of a replicated solve (mg_vcycle)
+// the finest `nshared` levels of the hierarchy shared among the ranks of a replicated solve (mg_vcycle)
 struct MgDist {
     Comm *comm = nullptr;
-    int a = 0, b = 0;                 // global node columns [a, b) this rank owns
-    int64_t goff1[64], cnt1[64];      // per rank: start and length (doubles) of its part of the level-1 right-hand side
+    int nshared = 1;
+    int a[8] = {}, b[8] = {};         // node columns [a[l], b[l]) of level l this rank owns (a[l+1] = ceil(a[l] / 2), b alike)
+    int64_t goff[64], cnt[64];        // per rank: start and length (doubles) of its part of the right-hand side of level nshared
 };
+// how many levels to share: level 0, and every further level that is large enough to repay its ghost exchanges, runs as
+// per-level kernels and leaves every rank at least two node columns; fills md.nshared, md.a / md.b (from a[0], b[0]), goff, cnt
+void mg_plan_sharing(const MgHierarchy &H, int world, int rank, MgDist &md);
 cudaError_t mg_vcycle(const LaunchCtx &lc, MgHierarchy &H, const double *r_fine, double *z_fine, int64_t *launches,
                       const MgDist *dist = nullptr);
 

@@ -18,6 +18,7 @@
 //     products stay FP64; vectors and accumulations are FP64.
 // All kernels are one thread per row / dof, no atomics: the V-cycle is deterministic.
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 
@@ -670,11 +671,50 @@ cudaError_t mg_setup(const LaunchCtx &lc, MgHierarchy &H, const double *val_fine
     return cudaGetLastError();
 }
 
+// levels [0, n) of the V-cycle that run as one kernel launch per step (the rest: cooperative kernel / single-block tail)
+static int per_level_kernels(const MgHierarchy &H)
+{
+    const int nl = (int)H.lv.size();
+    const int top = (H.fuse_tail && H.tail_first > 0) ? H.tail_first : nl;
+    const int mid = (H.fuse_tail >= 2 && H.coop_first > 0 && H.coop_first < top) ? H.coop_first : -1;
+    return mid > 0 ? mid : std::min(top, nl - 1);
+}
+
+void mg_plan_sharing(const MgHierarchy &H, int world, int rank, MgDist &md)
+{
+    static const long long min_dofs = getenv("PLF_SHARE_DOFS") ? atoll(getenv("PLF_SHARE_DOFS")) : 1000000ll;
+    const int nper = per_level_kernels(H), NX = H.lv[0].NX;
+    auto col_a = [&](int r) { return (int)((int64_t)NX * r / world); };
+    auto col_b = [&](int r) { return (int)((int64_t)NX * (r + 1) / world) + (r == world - 1 ? 1 : 0); };
+    int S = 1;
+    while (S < nper && S < 8 && H.lv[S].ndof >= min_dofs) {
+        bool wide = true;   // every rank keeps >= 2 node columns on level S
+        for (int r = 0; r < world; r++) {
+            int a = col_a(r), b = col_b(r);
+            for (int l = 0; l < S; l++) { a = (a + 1) / 2; b = (b + 1) / 2; }
+            wide = wide && b - a >= 2;
+        }
+        if (!wide) break;
+        S++;
+    }
+    md.nshared = S;
+    md.a[0] = col_a(rank); md.b[0] = col_b(rank);
+    for (int l = 1; l < S; l++) { md.a[l] = (md.a[l - 1] + 1) / 2; md.b[l] = (md.b[l - 1] + 1) / 2; }
+    const MgLevel &G = H.lv[S];   // first replicated level: its right-hand side is gathered
+    for (int r = 0; r < world; r++) {
+        int a = col_a(r), b = col_b(r);
+        for (int l = 0; l < S; l++) { a = (a + 1) / 2; b = (b + 1) / 2; }
+        md.goff[r] = 2ll * a * (G.NY + 1);
+        md.cnt[r] = 2ll * b * (G.NY + 1) - md.goff[r];
+    }
+}
+
 // z = V(r): one V(nu, nu) cycle from a zero initial guess.  r and z are fine-level vectors (z must not alias r).
-// dist != nullptr: level 0 is SHARED among the ranks of a replicated solve -- every rank holds the global vectors and the
-// global hierarchy, but smooths / forms the residual / restricts / prolongs only the level-0 rows of the node columns it
-// owns and swaps one ghost column with each neighbour after every step whose output the next stencil reads; the
-// right-hand side of level 1 is gathered from all ranks and the levels below run on every rank alike.
+// dist != nullptr: the finest dist->nshared levels are SHARED among the ranks of a replicated solve -- every rank holds the
+// global vectors and the global hierarchy, but on a shared level it smooths / forms the residual / restricts / prolongs only
+// the rows of the node columns it owns and swaps one ghost column with each neighbour after every step whose output the
+// next stencil reads; the right-hand side of the first level below is gathered from all ranks and the rest runs on every
+// rank alike.  Every row sees the arithmetic of the single-GPU cycle in the same order: the cycle is bit-identical.
 cudaError_t mg_vcycle(const LaunchCtx &lc, MgHierarchy &H, const double *r_fine, double *z_fine, int64_t *launches, const MgDist *dist)
 {
     const int nl = (int)H.lv.size();
@@ -682,12 +722,13 @@ cudaError_t mg_vcycle(const LaunchCtx &lc, MgHierarchy &H, const double *r_fine,
     H.lv[0].b = const_cast<double *>(r_fine);
     H.lv[0].x = z_fine;
     bool comm_failed = false;
+    const int S = dist ? dist->nshared : 0;   // shared levels
     auto rows = [&](const MgLevel &L, int l, int64_t &r0, int64_t &r1) {   // rows a launch on level l works on
         r0 = 0; r1 = L.ndof;
-        if (dist && l == 0) { r0 = 2ll * dist->a * (L.NY + 1); r1 = 2ll * dist->b * (L.NY + 1); }
+        if (l < S) { r0 = 2ll * dist->a[l] * (L.NY + 1); r1 = 2ll * dist->b[l] * (L.NY + 1); }
     };
     auto swap_ghosts = [&](const MgLevel &L, int l, double *v) {
-        if (dist && l == 0 && comm_halo_exchange_cols(*dist->comm, v, L.NY, dist->a, dist->b, L.NX, lc.stream)) comm_failed = true;
+        if (l < S && comm_halo_exchange_cols(*dist->comm, v, L.NY, dist->a[l], dist->b[l], L.NX, lc.stream)) comm_failed = true;
     };
     auto jacobi = [&](MgLevel &L, int l, const double *in, double *out, int first) {
         int64_t r0, r1;
@@ -721,23 +762,23 @@ cudaError_t mg_vcycle(const LaunchCtx &lc, MgHierarchy &H, const double *r_fine,
         mg_residual_kernel<<<grid_for(r1 - r0, 256), 256, 0, lc.stream>>>(L.NX, L.NY, L.val, L.mask, L.b, L.x, L.r, r0, r1);
         swap_ghosts(L, l, L.r);
         int64_t c0 = 0, c1 = C.ndof;
-        if (dist && l == 0) { c0 = 2ll * ((dist->a + 1) / 2) * (C.NY + 1); c1 = 2ll * ((dist->b + 1) / 2) * (C.NY + 1); }
+        if (l < S) { c0 = 2ll * ((dist->a[l] + 1) / 2) * (C.NY + 1); c1 = 2ll * ((dist->b[l] + 1) / 2) * (C.NY + 1); }
         mg_restrict_kernel<<<grid_for(c1 - c0, 256), 256, 0, lc.stream>>>(C.NX, C.NY, L.r, C.mask, C.b, l == 0 ? H.j0 : 0, c0, c1);
         *launches += 2;
-        if (dist && l == 0 && comm_gather_ranges(*dist->comm, C.b + dist->goff1[dist->comm->rank], C.b, dist->goff1, dist->cnt1, lc.stream))
+        if (l == S - 1 && comm_gather_ranges(*dist->comm, C.b + dist->goff[dist->comm->rank], C.b, dist->goff, dist->cnt, lc.stream))
             comm_failed = true;
     };
     auto up = [&](int l) {
         MgLevel &L = H.lv[l], &C = H.lv[l + 1];
         int64_t r0, r1;
         rows(L, l, r0, r1);
-        if (dist && l == 0) {   // the ghost columns too: the coarse solution is complete on every rank, no exchange needed
-            r0 = 2ll * std::max(dist->a - 1, 0) * (L.NY + 1);
-            r1 = 2ll * std::min(dist->b + 1, L.NX + 1) * (L.NY + 1);
+        if (l < S) {   // the ghost columns too (the coarse solution is complete, or has its own ghosts): no exchange needed here
+            r0 = 2ll * std::max(dist->a[l] - 1, 0) * (L.NY + 1);
+            r1 = 2ll * std::min(dist->b[l] + 1, L.NX + 1) * (L.NY + 1);
         }
         mg_prolong_add_kernel<<<grid_for(r1 - r0, 256), 256, 0, lc.stream>>>(L.NX, L.NY, C.x, L.mask, L.x, l == 0 ? H.j0 : 0, r0, r1);
         (*launches)++;
-        smooth(L, l, H.nu, false, false);
+        smooth(L, l, H.nu, false, l >= 1 && l < S);   // a shared finer level prolongs from this level's ghost columns as well
     };
     // levels [0, mid) run as per-level kernels, [mid, top) in the cooperative grid kernel, [top, nl) in the fused
     // single-block tail (inside the cooperative kernel when there is one)

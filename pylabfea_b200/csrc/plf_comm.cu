@@ -1,6 +1,7 @@
 // plf_comm.cu -- NCCL plumbing of the strip-partitioned solve and its C-ABI entry points (include/plfb200.h).
 #include <dlfcn.h>
 
+#include <cstdlib>
 #include <cstring>
 #include <string>
 
@@ -37,6 +38,7 @@ struct NcclApi {
 };
 NcclApi g_nccl;
 std::string g_err;
+void p2p_release(Comm &c);
 
 int nccl_fail(const char *what, ncclResult_t r)
 {
@@ -104,18 +106,202 @@ int comm_init(Comm &c, const unsigned char *id128, int rank, int world)
 
 void comm_destroy(Comm &c)
 {
+    p2p_release(c);
     if (c.nccl && g_nccl.CommDestroy) g_nccl.CommDestroy((ncclComm_t)c.nccl);
     c = Comm();
 }
 
+
+// ---- peer mailboxes ---------------------------------------------------------------------------------------------------------
+// Layout of one rank's mailbox (device memory, mapped into every other rank's process through CUDA IPC):
+//   [0, 16)   two arrival flags of the halo exchange (0: written by the left neighbour, 1: by the right neighbour)
+//   [16, 24)  arrival counter of the all-reduce
+//   [RED_OFF, HALO_OFF)  all-reduce slots, double[2 parities][64 ranks][64 values]
+//   [HALO_OFF, ...)      halo slots, double[2 parities][2 sides][box_cols]
+// An exchange is ONE kernel: push the payload into the peers' mailboxes (stores over NVLink), release-store the epoch into
+// their flags, spin on the own flags, copy the own slots out.  Two parities are enough: a rank cannot run two exchanges ahead
+// of a neighbour, because finishing exchange k + 1 needs that neighbour's push of k + 1, which comes after its copy-out of k.
+// The exchanges of one communicator must not overlap in time (different streams of one rank): the callers order them with
+// stream synchronisation, as they had to for NCCL.
+namespace {
+constexpr size_t RED_OFF = 64, RED_SLOT = 64, HALO_OFF = RED_OFF + 2 * 64 * RED_SLOT * sizeof(double) + 192;
+static_assert(HALO_OFF % 256 == 0, "halo slots are 256-byte aligned");
+constexpr long long SPIN_LIMIT = 120000000000ll;   // about a minute of SM clocks: a peer that never arrives is a lost rank
+
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long *p)
+{
+    unsigned long long v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_sys(unsigned long long *p, unsigned long long v)
+{
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ void spin_until(const unsigned long long *flag, unsigned long long want)
+{
+    const long long t0 = clock64();
+    while (ld_acquire_sys(flag) < want)
+        if (clock64() - t0 > SPIN_LIMIT) __trap();   // surfaces as a launch failure at the next synchronisation
+}
+
+__global__ void __launch_bounds__(1024) p2p_halo_kernel(double *vec, int ncol, long long sendL, long long recvL, long long sendR,
+                                                        long long recvR, unsigned char *mine, unsigned char *left, unsigned char *right,
+                                                        int box_cols, unsigned long long epoch)
+{
+    const int par = (int)(epoch & 1ull), tid = threadIdx.x;
+    // the left boundary column lands in the left neighbour's "from the right" slot and vice versa
+    if (left) {
+        double *dst = reinterpret_cast<double *>(left + HALO_OFF) + (size_t)(par * 2 + 1) * box_cols;
+        for (int i = tid; i < ncol; i += blockDim.x) dst[i] = vec[sendL + i];
+    }
+    if (right) {
+        double *dst = reinterpret_cast<double *>(right + HALO_OFF) + (size_t)(par * 2 + 0) * box_cols;
+        for (int i = tid; i < ncol; i += blockDim.x) dst[i] = vec[sendR + i];
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (tid == 0) {
+        if (left) st_release_sys(reinterpret_cast<unsigned long long *>(left) + 1, epoch);
+        if (right) st_release_sys(reinterpret_cast<unsigned long long *>(right) + 0, epoch);
+        if (left) spin_until(reinterpret_cast<unsigned long long *>(mine) + 0, epoch);
+        if (right) spin_until(reinterpret_cast<unsigned long long *>(mine) + 1, epoch);
+    }
+    __syncthreads();
+    if (left) {
+        const double *src = reinterpret_cast<const double *>(mine + HALO_OFF) + (size_t)(par * 2 + 0) * box_cols;
+        for (int i = tid; i < ncol; i += blockDim.x) vec[recvL + i] = __ldcg(src + i);
+    }
+    if (right) {
+        const double *src = reinterpret_cast<const double *>(mine + HALO_OFF) + (size_t)(par * 2 + 1) * box_cols;
+        for (int i = tid; i < ncol; i += blockDim.x) vec[recvR + i] = __ldcg(src + i);
+    }
+}
+
+struct PeerBoxes { unsigned char *p[64]; };
+
+// vals[0 .. n) combined over the ranks in rank order (the same bits on every rank): op 0 sum, 1 max, 2 min
+__global__ void __launch_bounds__(512) p2p_allreduce_kernel(double *vals, int n, int op, PeerBoxes peers, int rank, int world,
+                                                           unsigned long long epoch)
+{
+    const int par = (int)(epoch & 1ull), tid = threadIdx.x;
+    for (int t = tid; t < n * world; t += blockDim.x) {
+        const int r = t / n, i = t - r * n;
+        reinterpret_cast<double *>(peers.p[r] + RED_OFF)[((size_t)par * 64 + rank) * RED_SLOT + i] = vals[i];
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (tid < world) atomicAdd_system(reinterpret_cast<unsigned long long *>(peers.p[tid] + 16), 1ull);
+    if (tid == 0) spin_until(reinterpret_cast<unsigned long long *>(peers.p[rank] + 16), epoch * (unsigned long long)world);
+    __syncthreads();
+    for (int i = tid; i < n; i += blockDim.x) {
+        const double *slot = reinterpret_cast<const double *>(peers.p[rank] + RED_OFF) + (size_t)par * 64 * RED_SLOT + i;
+        double acc = __ldcg(slot);
+        for (int r = 1; r < world; r++) {
+            const double v = __ldcg(slot + (size_t)r * RED_SLOT);
+            acc = op == 0 ? acc + v : (op == 1 ? fmax(acc, v) : fmin(acc, v));
+        }
+        vals[i] = acc;
+    }
+}
+
+int cuda_fail(const char *what, cudaError_t e)
+{
+    g_err = std::string(what) + ": " + cudaGetErrorString(e);
+    return 1;
+}
+
+void p2p_release(Comm &c)
+{
+    for (int r = 0; r < 64; r++)
+        if (c.peer_box[r] && c.peer_box[r] != c.box) cudaIpcCloseMemHandle(c.peer_box[r]);
+    if (c.box) cudaFree(c.box);
+    for (int r = 0; r < 64; r++) c.peer_box[r] = nullptr;
+    c.box = nullptr;
+    c.p2p = false;
+    c.box_cols = 0;
+    c.halo_epoch = c.red_epoch = 0;
+}
+
+int p2p_allreduce(Comm &c, double *dbuf, int count, int op, cudaStream_t s)
+{
+    PeerBoxes pb;
+    for (int r = 0; r < 64; r++) pb.p[r] = c.peer_box[r];
+    p2p_allreduce_kernel<<<1, 512, 0, s>>>(dbuf, count, op, pb, c.rank, c.world, ++c.red_epoch);
+    const cudaError_t e = cudaGetLastError();
+    return e == cudaSuccess ? 0 : cuda_fail("p2p all-reduce", e);
+}
+
+int p2p_halo(Comm &c, double *vec, size_t ncol, bool left, bool right, size_t sendL, size_t recvL, size_t sendR, size_t recvR,
+             cudaStream_t s)
+{
+    p2p_halo_kernel<<<1, 1024, 0, s>>>(vec, (int)ncol, (long long)sendL, (long long)recvL, (long long)sendR, (long long)recvR, c.box,
+                                       left ? c.peer_box[c.rank - 1] : nullptr, right ? c.peer_box[c.rank + 1] : nullptr, c.box_cols,
+                                       ++c.halo_epoch);
+    const cudaError_t e = cudaGetLastError();
+    return e == cudaSuccess ? 0 : cuda_fail("p2p halo exchange", e);
+}
+}   // namespace
+
+int comm_p2p_setup(Comm &c, int cols, cudaStream_t s)
+{
+    if (!c.active() || c.world < 2 || c.world > 64) return 0;
+    const char *env = getenv("PLF_P2P");
+    if (env && env[0] == '0') { p2p_release(c); return 0; }
+    if (c.p2p && c.box_cols >= cols) return 0;   // every rank sees the same NY, hence takes the same branch
+    p2p_release(c);
+    // every step below is attempted by all ranks, and the outcome is agreed on at the end: no rank may skip a collective
+    bool ok = true;
+    const size_t bytes = HALO_OFF + 4 * (size_t)cols * sizeof(double);
+    cudaIpcMemHandle_t mine_h;
+    memset(&mine_h, 0, sizeof mine_h);
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+    ok = ok && cudaMalloc(&c.box, bytes) == cudaSuccess;
+    ok = ok && cudaMemset(c.box, 0, bytes) == cudaSuccess;
+    ok = ok && cudaIpcGetMemHandle(&mine_h, c.box) == cudaSuccess;
+    double *d_h = nullptr;
+    cudaError_t e = cudaMalloc(&d_h, (size_t)c.world * 64 + 8);
+    if (e != cudaSuccess) return cuda_fail("comm_p2p_setup", e);
+    std::string all((size_t)c.world * 64, '\0');
+    int64_t goff[64], cnt[64];
+    for (int r = 0; r < c.world; r++) { goff[r] = 8 * r; cnt[r] = 8; }
+    e = cudaMemcpyAsync(d_h + 8 * c.rank, &mine_h, 64, cudaMemcpyHostToDevice, s);
+    if (e == cudaSuccess && comm_gather_ranges(c, d_h + 8 * c.rank, d_h, goff, cnt, s)) { cudaFree(d_h); return 1; }
+    if (e == cudaSuccess) e = cudaMemcpyAsync(&all[0], d_h, all.size(), cudaMemcpyDeviceToHost, s);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+    if (e != cudaSuccess) { cudaFree(d_h); return cuda_fail("comm_p2p_setup", e); }
+    for (int r = 0; r < c.world && ok; r++) {
+        if (r == c.rank) { c.peer_box[r] = c.box; continue; }
+        cudaIpcMemHandle_t h;
+        memcpy(&h, &all[(size_t)r * 64], 64);
+        void *ptr = nullptr;
+        ok = cudaIpcOpenMemHandle(&ptr, h, cudaIpcMemLazyEnablePeerAccess) == cudaSuccess;
+        c.peer_box[r] = (unsigned char *)ptr;
+    }
+    cudaGetLastError();   // a failed IPC call is not an error of the library: the exchanges stay on NCCL
+    // agreement (this all-reduce is also the barrier behind every rank's cudaMemset)
+    double flag = ok ? 1. : 0.;
+    e = cudaMemcpyAsync(d_h + 8 * c.world, &flag, sizeof flag, cudaMemcpyHostToDevice, s);
+    if (e == cudaSuccess && comm_allreduce_op(c, d_h + 8 * c.world, 1, 2, s)) { cudaFree(d_h); return 1; }
+    if (e == cudaSuccess) e = cudaMemcpyAsync(&flag, d_h + 8 * c.world, sizeof flag, cudaMemcpyDeviceToHost, s);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+    cudaFree(d_h);
+    if (e != cudaSuccess) return cuda_fail("comm_p2p_setup", e);
+    if (flag > 0.5) { c.p2p = true; c.box_cols = cols; }
+    else p2p_release(c);
+    return 0;
+}
+
 int comm_allreduce_sum(Comm &c, double *dbuf, int count, cudaStream_t s)
 {
+    if (c.p2p && count <= (int)RED_SLOT) return p2p_allreduce(c, dbuf, count, 0, s);
     NC(g_nccl.AllReduce(dbuf, dbuf, (size_t)count, ncclDouble, ncclSum, (ncclComm_t)c.nccl, s), "ncclAllReduce");
     return 0;
 }
 
 int comm_allreduce_op(Comm &c, double *dbuf, int count, int op, cudaStream_t s)
 {
+    if (c.p2p && count <= (int)RED_SLOT) return p2p_allreduce(c, dbuf, count, op, s);
     const ncclRedOp_t o = op == 1 ? ncclMax : (op == 2 ? ncclMin : ncclSum);
     NC(g_nccl.AllReduce(dbuf, dbuf, (size_t)count, ncclDouble, o, (ncclComm_t)c.nccl, s), "ncclAllReduce");
     return 0;
@@ -126,6 +312,8 @@ int comm_halo_exchange_cols(Comm &c, double *vec, int NY, int a, int b, int NX, 
     const bool left = a > 0 && c.rank > 0, right = b <= NX && c.rank + 1 < c.world;
     if (!left && !right) return 0;
     const size_t ncol = 2 * (size_t)(NY + 1);
+    if (c.p2p && (int)ncol <= c.box_cols)
+        return p2p_halo(c, vec, ncol, left, right, ncol * (size_t)a, ncol * (size_t)(a - 1), ncol * (size_t)(b - 1), ncol * (size_t)b, s);
     ncclComm_t comm = (ncclComm_t)c.nccl;
     NC(g_nccl.GroupStart(), "ncclGroupStart");
     if (left) {
@@ -158,6 +346,9 @@ int comm_halo_exchange(Comm &c, double *vec, int NX, int NY, cudaStream_t s)
     const bool left = c.ghost_left() && c.rank > 0, right = c.ghost_right(NX) && c.rank + 1 < c.world;
     if (!left && !right) return 0;
     const size_t ncol = 2 * (size_t)(NY + 1);   // doubles per node column
+    if (c.p2p && (int)ncol <= c.box_cols)
+        return p2p_halo(c, vec, ncol, left, right, ncol * (size_t)c.own_first, ncol * (size_t)(c.own_first - 1),
+                        ncol * (size_t)(c.own_end - 1), ncol * (size_t)c.own_end, s);
     ncclComm_t comm = (ncclComm_t)c.nccl;
     NC(g_nccl.GroupStart(), "ncclGroupStart");
     if (left) {
@@ -223,6 +414,8 @@ extern "C" int plf_comm_set_strip(plf_ctx *ctx, int own_first, int own_end)
         model_apply_mg_options(ctx);
         ctx->mg_K_serial = -1;
     }
+    if (comm_p2p_setup(*ctx->comm, 2 * (ctx->NY + 1), ctx->stream))
+        return fail(ctx, PLF_ECUDA, std::string("plf_comm_set_strip: ") + comm_error());
     double have_mg = (ctx->mg && ctx->mg->levels() >= 2) ? 1. : 0.;
     int rc = comm_host_allreduce(ctx, &have_mg, 1, 2);
     if (rc != PLF_OK) return rc;
@@ -271,6 +464,8 @@ extern "C" int plf_comm_set_replica(plf_ctx *ctx, plf_ctx *global_ctx)
     ctx->replica = global_ctx;
     return PLF_OK;
 }
+
+extern "C" int plf_comm_p2p(plf_ctx *ctx) { return ctx && ctx->comm && ctx->comm->p2p ? 1 : 0; }
 
 extern "C" int plf_comm_allreduce(plf_ctx *ctx, double *vals, int n)
 {

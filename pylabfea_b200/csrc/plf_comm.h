@@ -19,6 +19,13 @@ struct Comm {
     bool global_set = false;
     int first_col_global = 0, NX_global = 0;
     double x_offset = 0., lenx_global = 0.;
+    // peer mailboxes (comm_p2p_setup): every rank exposes one device buffer through CUDA IPC; halo columns and the scalars of
+    // the all-reduces are then written straight into the other ranks' HBM over NVLink, one kernel per exchange
+    bool p2p = false;
+    unsigned char *box = nullptr;        // this rank's mailbox
+    unsigned char *peer_box[64] = {};    // every rank's mailbox as mapped into this process ([rank] == box)
+    int box_cols = 0;                    // doubles one halo slot holds
+    unsigned long long halo_epoch = 0, red_epoch = 0;
     bool active() const { return nccl != nullptr; }
     bool ghost_left() const { return own_first > 0; }
     bool ghost_right(int NX) const { return own_end < NX + 1; }
@@ -37,6 +44,9 @@ int comm_halo_exchange(Comm &c, double *vec, int NX, int NY, cudaStream_t s);
 // the same exchange on a GLOBAL nodal vector (every rank holds all node columns 0 .. NX, owns [a, b)): column a goes to the
 // left neighbour and column a - 1 comes back, column b - 1 goes to the right neighbour and column b comes back
 int comm_halo_exchange_cols(Comm &c, double *vec, int NY, int a, int b, int NX, cudaStream_t s);
+// Maps the mailboxes of all ranks (collective; needs NCCL for the handle exchange).  Leaves c.p2p false, and the exchanges on
+// NCCL, when CUDA IPC is not available between the ranks or PLF_P2P=0 is set.  `cols`: doubles per node column.
+int comm_p2p_setup(Comm &c, int cols, cudaStream_t s);
 int comm_gather_ranges(Comm &c, const double *mine, double *global, const int64_t *goff, const int64_t *cnt, cudaStream_t s);
 const char *comm_error();
 

@@ -762,13 +762,9 @@ int model_solve_device_bc(plf_ctx *ctx, double rtol, int max_iter, int *iters, d
         if (!ctx->d_cgmask && (rc = dalloc(ctx, &ctx->d_cgmask, D))) return rc;
         CK(launch_ghost_mask(lc, ctx->Ndof, ctx->NY, a, bcol, ctx->d_fixed, ctx->d_cgmask, &ctx->launches));
         MgDist md;
-        md.comm = &c; md.a = a; md.b = bcol;
-        const MgLevel &L1 = ctx->mg->lv[1];
-        for (int r = 0; r < c.world; r++) {
-            const int ar = (int)((int64_t)ctx->NX * r / c.world), br = (int)((int64_t)ctx->NX * (r + 1) / c.world) + (r == c.world - 1 ? 1 : 0);
-            md.goff1[r] = 2ll * ((ar + 1) / 2) * (L1.NY + 1);
-            md.cnt1[r] = 2ll * ((br + 1) / 2) * (L1.NY + 1) - md.goff1[r];
-        }
+        md.comm = &c;
+        mg_plan_sharing(*ctx->mg, c.world, c.rank, md);
+        if (md.a[0] != a || md.b[0] != bcol) return fail(ctx, PLF_ESTATE, "plf_solve_linear (shared levels): column ranges disagree");
         const bool fresh = ctx->skip_unchanged && ctx->mg_K_serial == ctx->K_serial && ctx->mg_mask_epoch == ctx->mask_epoch;
         ctx->mg_K_serial = ctx->K_serial; ctx->mg_mask_epoch = ctx->mask_epoch;
         cudaError_t ce = launch_cg_hybrid(lc, c, a, bcol, ctx->Ndof, ctx->d_rowptr, ctx->d_col, ctx->d_val, ctx->d_cgmask, ctx->d_b, x, ctx->d_r,

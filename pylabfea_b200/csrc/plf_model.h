@@ -108,7 +108,8 @@ struct plf_ctx {
     // the communicator of the strip context and the global node columns [share_a, share_b) this rank owns
     plf::Comm *share_comm = nullptr;
     int share_a = 0, share_b = 0;
-    int solver_hybrid = 0;              // option (on the strip context): 1 share level 0 + CG of the replicated solve among the ranks
+    int solver_hybrid = 2;              // option (on the strip context): share the finest levels + CG of the replicated solve among
+                                        // the ranks: 0 never, 1 always, 2 when the exchanges run through peer mailboxes (Comm::p2p)
                                         // (same iterates; ~12 NCCL calls per iteration: pays only with low-latency exchanges)
     plf_ctx *replica = nullptr;         // plf_comm_set_replica: context holding the GLOBAL mesh, solves the gathered system (not owned)
     // change tracking, so that an unchanged K is neither re-assembled nor re-coarsened: tangent_epoch moves whenever

@@ -355,9 +355,10 @@ static int solve_replicated(plf_ctx *ctx, const double *dr, const double *dt, co
     g->K_serial++;
     int rc = build_bc_vectors(g, dr, dt, dn, rep);
     if (rc != PLF_OK) { ctx->err = g->err; return rc; }
-    // every rank solves the gathered system; with solver_hybrid the CG vectors and level 0 of the V-cycle are split over the
+    // every rank solves the gathered system; with solver_hybrid (2 = when the exchanges run through peer mailboxes: the
+    // ranks agreed on c.p2p, so all take the same branch) the CG vectors and the finest levels of the V-cycle are split over the
     // node columns the ranks own (the levels below stay replicated)
-    const bool share = ctx->solver_hybrid && c.world > 1;
+    const bool share = (ctx->solver_hybrid == 1 || (ctx->solver_hybrid == 2 && c.p2p)) && c.world > 1;
     g->share_comm = share ? &c : nullptr;
     g->share_a = (int)((int64_t)NXg * c.rank / c.world);
     g->share_b = (int)((int64_t)NXg * (c.rank + 1) / c.world) + (c.rank == c.world - 1 ? 1 : 0);

@@ -57,6 +57,8 @@ def main():
         dist.broadcast(t, src=0)
         fe.distribute(rank, world, bytes(t.cpu().tolist()))
     ctx = fe._dev()
+    if 'PLF_HYBRID' in os.environ:   # 1: level 0 of the V-cycle and the CG vectors shared among the ranks (option solver_hybrid)
+        ctx.set_option('solver_hybrid', int(os.environ['PLF_HYBRID']))
     ctx.synchronize()
     if dist:
         dist.barrier()
@@ -70,6 +72,7 @@ def main():
         its = int(sum(s[0] for s in fe.solver_stats))
         upd = float(sum(sum(s[5][:3]) for s in fe.sweep_stats))
         print(json.dumps({'config': 'c5', 'mesh': [N, N], 'material': 'Barlat Yld2004-18p a=8 + elastic inclusion', 'n_gpus': world,
+                          'solver_hybrid': os.environ.get('PLF_HYBRID', 'default (2: shared when p2p)'), 'p2p': bool(world > 1 and ctx.comm_p2p()),
                           'seconds': dt, 'increments': int(fe.nsteps), 'inner_passes': [int(x) for x in fe.niter],
                           'linear_solves': len(fe.solver_stats), 'cg_iterations': its, 'ms_per_cg_iteration': dt * 1e3 / max(its, 1),
                           'element_updates': upd, 'element_updates_per_s': upd / dt,

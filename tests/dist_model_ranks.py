@@ -53,11 +53,13 @@ def main():
     fe.distribute(rank, world, uid, solver=solver)
     if 'PLF_HYBRID' in os.environ:      # 0 (default): every rank solves the gathered system alone; 1: level 0 + CG shared among the ranks
         fe._dev().set_option('solver_hybrid', int(os.environ['PLF_HYBRID']))
+    fe._dev().synchronize()   # contexts, communicator and peer mailboxes are set up here, not inside the timed solve
     t0 = time.perf_counter()
     fe.solve(min_step=4)
     dt = time.perf_counter() - t0
     out = {'rank': rank, 'world': world, 'N': N, 'solver': solver, 'seconds': dt, 'nsteps': fe.nsteps, 'niter': list(fe.niter),
-           'cg_iterations': int(sum(s[0] for s in fe.solver_stats)), 'solves': len(fe.solver_stats)}
+           'cg_iterations': int(sum(s[0] for s in fe.solver_stats)), 'solves': len(fe.solver_stats),
+           'p2p': fe._dev().comm_p2p()}
     if rank == 0:
         ref = build(N, device)
         t0 = time.perf_counter()
