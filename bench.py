@@ -397,7 +397,10 @@ def run_load_sequence(N, min_step, eps, device=0):
     solve() (host buffers: only the boundary description goes in and the increment reports come back)."""
     fe = inclusion_model(N, eps, device)
     ctx = fe._dev()
-    l0 = ctx.launch_count()
+    def launches():   # the strip's context + the context that holds the replicated global system
+        rep = getattr(ctx, '_replica', None)
+        return ctx.launch_count() + (rep.launch_count() if rep is not None else 0)
+    l0 = launches()
     t0 = time.perf_counter()
     fe.solve(min_step=min_step)
     dt = time.perf_counter() - t0
@@ -414,6 +417,39 @@ def run_load_sequence(N, min_step, eps, device=0):
     return out, fe
 
 
+def harvested_step(fe, peak, steps=30):
+    """The hot path on a state HARVESTED from a real solve instead of the synthetic branch mix of the headline: after the load
+    sequence the context holds the converged stresses / plastic strains of the last increment and the last displacement
+    increment; one step = plf_sweep (strains from du, Material.response of every element, tangents) + plf_setupK on it.  The
+    sweep leaves the committed state alone, so the step repeats identically (skip_unchanged is switched off for it: an
+    unchanged tangent would otherwise not be re-assembled).  Wall clock around `steps` steps with a synchronize on both
+    sides; every step includes the sweep's 48-byte flag read-back."""
+    ctx = fe._dev()
+    ctx.set_option('skip_unchanged', 0)
+    try:
+        for _ in range(3):
+            ctx.sweep(1)
+            ctx.setupK()
+        ctx.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            _, _, _, counts = ctx.sweep(1)
+            ctx.setupK()
+        ctx.synchronize()
+        ms = (time.perf_counter() - t0) * 1e3 / steps
+    finally:
+        ctx.set_option('skip_unchanged', 1)
+    n = float(sum(counts[:3]))
+    gbs = (BYTES_PER_UPDATE + BYTES_PER_ASSEMBLED) * fe.Nel / (ms * 1e-3) / 1e9
+    return {'workload': 'state after the last increment of the load sequence above; step = plf_sweep(du of the last solve) + plf_setupK',
+            'branch_mix': {'elastic': counts[0] / n, 'plastic_1step': counts[1] / n, 'substep50': counts[2] / n,
+                           'radial_correction': counts[3] / n},
+            'ms_per_step': ms, 'elements_per_s': fe.Nel / (ms * 1e-3), 'steps': steps,
+            'roofline_step': {'bound': 'hbm', 'achieved': gbs, 'peak': peak, 'unit': 'GB/s', 'frac': gbs / peak,
+                              'algorithmic_bytes_per_element': BYTES_PER_UPDATE + BYTES_PER_ASSEMBLED,
+                              'note': 'whole step (update + strain kernel + assembly + flag read-back) against the HBM peak'}}
+
+
 def run_coupled_solve(group, rank, world, local, N=256, min_step=3, eps=0.002):
     """The part of the path WITH an exchange step: Model.solve of ONE model cut into strips over the ranks
     (Model.distribute, one process per GPU).  Workload = the material of BASELINE config 4 -- RBF-SVC yield function of
@@ -421,8 +457,9 @@ def run_coupled_solve(group, rank, world, local, N=256, min_step=3, eps=0.002):
     displacement control (the 512 x 512 run takes 100 s on one GPU: 165 passes at 0.36 M in-FE updates/s; the kernel-level
     config-4 numbers are in `configs.c4`).  STRONG scaling: the
     model is fixed; every rank updates the elements of its strip and assembles its K rows, the owned rows of all ranks are
-    gathered (NCCL broadcasts, one contiguous CSR range per rank) and every rank solves the complete system (replicated
-    multigrid-CG: du bit-identical to the single-GPU run); sweep flags, calc_scf moments, global averages and boundary sums
+    gathered (NCCL broadcasts, one contiguous CSR range per rank) into a replicated global matrix; the CG vectors and the
+    finest multigrid levels are shared among the ranks when the peer mailboxes are up (plf_comm_p2p; else every rank solves
+    the complete system alone); sweep flags, calc_scf moments, global averages and boundary sums
     are all-reduced.  Wall clock between barriers around solve(), max over ranks."""
     import pylabfea_b200 as FE
     from pylabfea_b200 import _lib
@@ -460,7 +497,10 @@ def run_coupled_solve(group, rank, world, local, N=256, min_step=3, eps=0.002):
     ctx = fe._dev()
     ctx.synchronize()
     group.barrier()
-    l0 = ctx.launch_count()
+    def launches():   # the strip's context + the context that holds the replicated global system
+        rep = getattr(ctx, '_replica', None)
+        return ctx.launch_count() + (rep.launch_count() if rep is not None else 0)
+    l0 = launches()
     t0 = time.perf_counter()
     fe.solve(min_step=min_step)
     ctx.synchronize()
@@ -470,12 +510,16 @@ def run_coupled_solve(group, rank, world, local, N=256, min_step=3, eps=0.002):
     updates = float(sum(sum(s[5][:3]) for s in fe.sweep_stats))
     return {'workload': '%dx%d mesh, RBF-SVC yield function (1585 support vectors) + elastic inclusion, Model.solve(min_step=%d), '
                         'eps=%g (material of BASELINE config 4)' % (N, N, min_step, eps),
-            'scaling': 'strong', 'solver': 'single GPU' if world == 1 else 'replicated (K rows gathered, every rank solves)',
+            'scaling': 'strong',
+            'solver': 'single GPU' if world == 1 else (
+                'replicated K (rows gathered); CG vectors + finest multigrid levels shared among the ranks, ghost columns and dot '
+                'products through CUDA-IPC peer mailboxes' if ctx.comm_p2p() else 'replicated (K rows gathered, every rank solves)'),
+            'peer_mailboxes': bool(world > 1 and ctx.comm_p2p()),
             'elements': N * N, 'dofs': int(fe.Ndof), 'seconds': dt, 'increments': int(fe.nsteps),
             'inner_passes': [int(x) for x in fe.niter], 'linear_solves': len(fe.solver_stats), 'cg_iterations': its,
             'element_updates': updates, 'element_updates_per_s': updates / dt,
             'collectives_per_pass': 0 if world == 1 else 'K gather (%d broadcasts) + 2 all-reduces of sweep flags' % world,
-            'launches_rank0': int(ctx.launch_count() - l0), 'global_stress_yy': float(fe.glob['sig'][1])}
+            'launches_rank0': int(launches() - l0), 'global_stress_yy': float(fe.glob['sig'][1])}
 
 
 def run_c1(device):
@@ -838,9 +882,10 @@ def main():
         ctx.synchronize()
         line['configs'] = configs_block(local, peak, quick=args.steps < 50)
         try:
-            seq, _ = run_load_sequence(N, 5, 0.004, local)
+            seq, fe_seq = run_load_sequence(N, 5, 0.004, local)
             line['e2e_load_step'] = dict(seq, unit='ms per load increment', value=seq['ms_per_increment'],
                                          cpu_reference=cpu_load_step_estimate(seq) if not args.no_cpu else None)
+            line['harvested_mix'] = harvested_step(fe_seq, peak)
         except Exception as exc:
             line['e2e_load_step'] = {'error': '%s: %s' % (type(exc).__name__, exc)}
     print(json.dumps(line))
