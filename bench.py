@@ -417,16 +417,39 @@ def run_load_sequence(N, min_step, eps, device=0):
     return out, fe
 
 
-def harvested_step(fe, peak, steps=30):
-    """The hot path on a state HARVESTED from a real solve instead of the synthetic branch mix of the headline: after the load
-    sequence the context holds the converged stresses / plastic strains of the last increment and the last displacement
-    increment; one step = plf_sweep (strains from du, Material.response of every element, tangents) + plf_setupK on it.  The
-    sweep leaves the committed state alone, so the step repeats identically (skip_unchanged is switched off for it: an
-    unchanged tangent would otherwise not be re-assembled).  Wall clock around `steps` steps with a synchronize on both
-    sides; every step includes the sweep's 48-byte flag read-back."""
+def harvested_step(N, min_step, eps, device, peak, steps=30):
+    """The hot path on a state HARVESTED from a real solve instead of the synthetic branch mix of the headline.  The load
+    sequence is run once more (untimed) with Model.increment_hook saving the committed element state (sig, eps, epl) at the
+    start of every increment; afterwards the state at the start of the LAST increment is put back, and one step = plf_sweep
+    (strains from the du of the last solve, Material.response of every element, tangents) + plf_setupK -- the work of the last
+    inner pass of the sequence, elements crossing the yield surface inside the increment included.  The sweep leaves the
+    committed state alone, so the step repeats identically (skip_unchanged is off for it: an unchanged tangent would otherwise
+    not be re-assembled).  Wall clock around `steps` steps with a synchronize on both sides; every step includes the sweep's
+    flag read-back."""
+    from pylabfea_b200 import _lib
+    fe = inclusion_model(N, eps, device)
     ctx = fe._dev()
+    snap = {}
+
+    def hook(model, il):
+        for f in (_lib.F_SIG, _lib.F_EPS, _lib.F_EPL):
+            snap[f] = ctx.get_field(f)
+    fe.increment_hook = hook
+    fe.solve(min_step=min_step)
+    last_pass = fe.sweep_stats[-1][5]
+
+    def restore():
+        for f, a in snap.items():
+            ctx.set_field(f, a)
+    # strain increments of that last pass: what plf_commit adds to Element.eps
+    restore()
+    ctx.sweep(1)
+    ctx.commit()
+    deps = ctx.get_field(_lib.F_EPS) - snap[_lib.F_EPS]
+    restore()
     ctx.set_option('skip_unchanged', 0)
     try:
+        # (1) the in-FE step: plf_sweep (strain kernel, update, tangent comparison, statistics, flag read-back) + plf_setupK
         for _ in range(3):
             ctx.sweep(1)
             ctx.setupK()
@@ -439,15 +462,54 @@ def harvested_step(fe, peak, steps=30):
         ms = (time.perf_counter() - t0) * 1e3 / steps
     finally:
         ctx.set_option('skip_unchanged', 1)
+    # (2) the headline kernels (plf_batch_run + plf_setupK_from_batch) on the same states, timed like the headline
+    n1 = N // 3
+    mid = np.zeros((N, N), np.int32)
+    mid[n1:2 * n1, n1:2 * n1] = 1
+    b = ctx.batch_create(fe.Nel)
+    ctx.batch_upload(b, snap[_lib.F_SIG], snap[_lib.F_EPL], deps, mat_id=mid.ravel())
+    ctx.last_kernels()
+    for _ in range(3):
+        ctx.batch_run(b)
+        ctx.setupK_from_batch(b)
+    kernels = ctx.last_kernels()
+    ctx.synchronize()
+    t_resp, t_asm = [], []
+    for _ in range(steps):
+        ctx.flush_l2()
+        ctx.event_record(0)
+        ctx.batch_run(b)
+        ctx.event_record(1)
+        ctx.setupK_from_batch(b)
+        ctx.event_record(2)
+        ctx.synchronize()
+        t_resp.append(ctx.event_elapsed(0, 1))
+        t_asm.append(ctx.event_elapsed(1, 2))
+    ns = np.empty(fe.Nel, dtype=np.int32)
+    ctx.batch_download(b, nsteps=ns)
+    ctx.batch_destroy(b)
+    tr, ta = float(np.median(t_resp)), float(np.median(t_asm))
     n = float(sum(counts[:3]))
     gbs = (BYTES_PER_UPDATE + BYTES_PER_ASSEMBLED) * fe.Nel / (ms * 1e-3) / 1e9
-    return {'workload': 'state after the last increment of the load sequence above; step = plf_sweep(du of the last solve) + plf_setupK',
+    ach = BYTES_PER_UPDATE * fe.Nel / (tr * 1e-3) / 1e9
+    return {'workload': '%dx%d inclusion load sequence (J2 matrix + elastic inclusion); element state at the start of its last '
+                        'increment + strain increments of its last pass' % (N, N),
             'branch_mix': {'elastic': counts[0] / n, 'plastic_1step': counts[1] / n, 'substep50': counts[2] / n,
-                           'radial_correction': counts[3] / n},
-            'ms_per_step': ms, 'elements_per_s': fe.Nel / (ms * 1e-3), 'steps': steps,
-            'roofline_step': {'bound': 'hbm', 'achieved': gbs, 'peak': peak, 'unit': 'GB/s', 'frac': gbs / peak,
-                              'algorithmic_bytes_per_element': BYTES_PER_UPDATE + BYTES_PER_ASSEMBLED,
-                              'note': 'whole step (update + strain kernel + assembly + flag read-back) against the HBM peak'}}
+                           'radial_correction': counts[3] / n,
+                           'note': 'of the elements of the plastic material; the %d inclusion elements are elastic' % int(mid.sum())},
+            'branch_counts_last_pass_of_the_sequence': [int(c) for c in last_pass],
+            'hot_path': {'api': 'plf_batch_run + plf_setupK_from_batch, inputs resident, CUDA events, L2 flushed (as the headline)',
+                         'kernels': kernels, 'response_ms': tr, 'assembly_ms': ta, 'ms_per_step': tr + ta,
+                         'elements_per_s': fe.Nel / ((tr + ta) * 1e-3), 'updates_per_s': fe.Nel / (tr * 1e-3),
+                         'substep50_elements': int(np.sum(ns == 49)),
+                         'roofline': {'bound': 'hbm', 'achieved': ach, 'peak': peak, 'unit': 'GB/s', 'frac': ach / peak,
+                                      'note': 'return mapping alone; with %.0f %% of the elements in the 50-sub-step loop the '
+                                              'kernel pair is FP64-bound, not HBM-bound' % (100. * np.mean(ns == 49))}},
+            'in_fe_step': {'api': 'plf_sweep (strains from du, update, tangent comparison, statistics, flag read-back) + plf_setupK, '
+                                  'wall clock with a synchronize on both sides',
+                           'ms_per_step': ms, 'elements_per_s': fe.Nel / (ms * 1e-3), 'steps': steps,
+                           'roofline_step': {'bound': 'hbm', 'achieved': gbs, 'peak': peak, 'unit': 'GB/s', 'frac': gbs / peak,
+                                             'algorithmic_bytes_per_element': BYTES_PER_UPDATE + BYTES_PER_ASSEMBLED}}}
 
 
 def run_coupled_solve(group, rank, world, local, N=256, min_step=3, eps=0.002):
@@ -885,7 +947,8 @@ def main():
             seq, fe_seq = run_load_sequence(N, 5, 0.004, local)
             line['e2e_load_step'] = dict(seq, unit='ms per load increment', value=seq['ms_per_increment'],
                                          cpu_reference=cpu_load_step_estimate(seq) if not args.no_cpu else None)
-            line['harvested_mix'] = harvested_step(fe_seq, peak)
+            del fe_seq
+            line['harvested_mix'] = harvested_step(N, 5, 0.004, local, peak)
         except Exception as exc:
             line['e2e_load_step'] = {'error': '%s: %s' % (type(exc).__name__, exc)}
     print(json.dumps(line))

@@ -168,7 +168,10 @@ __device__ __forceinline__ ElemStats sweep_finish(const DevMat &m, int64_t e, in
 // ---------------------------------------------------------------------------------------------------------------
 // sweep, thread per element (Hill / J2).  GATHER: compacted second pass over the deferred elements.
 // ---------------------------------------------------------------------------------------------------------------
-template <int MODE, bool GATHER>
+//   FM: fast mode of the model's Hill / J2 materials (response_fast_mode: 0 general form, 4 / 8 J2 on isotropic elasticity with
+//   the direct / recurrence form of the planar sub-step loop, 6 Hill on isotropic elasticity, 7 block-structured CV) -- the same
+//   device functions as the batch kernels of response_kernels.cu, so a sweep and plf_response_batch agree bit for bit
+template <int MODE, bool GATHER, int FM>
 __global__ void __launch_bounds__(128) sweep_hill_kernel(int64_t n, int NY, int nit, const int32_t *__restrict__ desc,
                                                          const double *__restrict__ sig, const double *__restrict__ epl,
                                                          const double *__restrict__ du, double *__restrict__ elstiff,
@@ -179,6 +182,7 @@ __global__ void __launch_bounds__(128) sweep_hill_kernel(int64_t n, int NY, int 
 {
     // MODE 1 / !GATHER: pass A over all elements; MODE 0 / GATHER: persistent pass B over the work list (length read
     // from device memory: no host round trip between the passes); MODE 0 / !GATHER: unsplit response_core.
+    __shared__ double s_xc[(GATHER && FM != 0) ? 12 * 128 : 1];   // correction sums + deps_r / 50 of the fast sub-step loops
     const int64_t total = GATHER ? (int64_t)st->work_count : n;
     const int64_t stride = GATHER ? (int64_t)gridDim.x * blockDim.x : total + blockDim.x;
     for (int64_t t0 = (int64_t)blockIdx.x * blockDim.x; t0 < total; t0 += stride) {
@@ -204,17 +208,33 @@ __global__ void __launch_bounds__(128) sweep_hill_kernel(int64_t n, int NY, int 
                 element_strain(c_geom[d >> 16], NY, e, du, de);
                 if (MODE == 1) {
                     double ca[6], tc, tw;
-                    br = hill_passA<0>(m, s, ep, de, dp, ca, tc, tw, fyv);
+                    br = (FM == 7) ? hillblk_passA(m, s, ep, de, dp, ca, tc, tw, fyv)
+                       : (FM == 6) ? hilliso_passA(m, s, ep, de, dp, ca, tc, tw, fyv)
+                       : (FM == 4 || FM == 8) ? iso_passA(m, s, ep, de, dp, ca, tc, tw, fyv)
+                                              : hill_passA<0>(m, s, ep, de, dp, ca, tc, tw, fyv);
 #pragma unroll
                     for (int i = 0; i < 6; i++)
 #pragma unroll
-                        for (int j = i; j < 6; j++) gs[sym_idx(i, j)] = m.CV[6 * i + j] * tc - (ca[i] * tw) * ca[j];
+                        for (int j = i; j < 6; j++) gs[sym_idx(i, j)] = m.CV[6 * i + j] * tc - (ca[i] * ca[j]) * tw;   // as pass A of the batch path
                 } else if (GATHER) {
                     double epd[6];
 #pragma unroll
                     for (int k = 0; k < 6; k++) epd[k] = ep[k];
-                    WRegs W;
-                    br = hill_passB<0>(m, s, epd, de, W, gs, fyv);
+                    if (FM == 0) {
+                        WRegs W;
+                        br = hill_passB<0>(m, s, epd, de, W, gs, fyv);
+                    } else if (planar_state(s, ep, de)) {   // every state of a 2-d model that started from planar fields
+                        double *xc = s_xc + threadIdx.x;
+                        br = (FM == 7) ? hill_passB_blk2d(m, s, epd, de, xc, 128, gs, fyv)
+                           : (FM == 6) ? hill_passB_hilliso2d(m, s, epd, de, xc, 128, gs, fyv)
+                           : (FM == 8) ? hill_passB_iso2d<true>(m, s, epd, de, xc, 128, gs, fyv)
+                                       : hill_passB_iso2d<false>(m, s, epd, de, xc, 128, gs, fyv);
+                    } else if (FM == 4 || FM == 8) {
+                        br = hill_passB_iso(m, s, epd, de, s_xc + threadIdx.x, 128, gs, fyv);
+                    } else {
+                        WRegs W;
+                        br = hill_passB<1>(m, s, epd, de, W, gs, fyv);
+                    }
 #pragma unroll
                     for (int k = 0; k < 6; k++) dp[k] = epd[k] - ep[k];
                     ns = PLF_MAXIT - 1;
@@ -334,14 +354,26 @@ cudaError_t launch_sweep(const LaunchCtx &lc, const DevMat *hmats, int nmat, int
     const unsigned grid = (unsigned)((Nel + 127) / 128);
     if (any_hill) {
         if (compact) {
-            sweep_hill_kernel<1, false><<<grid, 128, 0, lc.stream>>>(Nel, NY, nit, desc, sig, epl, du, elstiff, res_sig, res_depl,
-                                                                      fyld, nsteps, has_res, nullptr, worklist, st, stat_first);
+            int fm = response_fast_mode(hmats, nmat, lc.max_fm);
+            if (fm == 4 && lc.passb_recur) fm = 8;
+            if (fm != 4 && fm != 8 && fm != 6 && fm != 7) fm = 0;
             const unsigned bgrid = (unsigned)std::min<int64_t>((int64_t)lc.sm_count * 8, (int64_t)grid);
-            sweep_hill_kernel<0, true><<<bgrid, 128, 0, lc.stream>>>(0, NY, nit, desc, sig, epl, du, elstiff, res_sig, res_depl, fyld,
-                                                                      nsteps, has_res, worklist, nullptr, st, stat_first);
+#define SWEEP_HILL(F)                                                                                                                  \
+    do {                                                                                                                               \
+        sweep_hill_kernel<1, false, F><<<grid, 128, 0, lc.stream>>>(Nel, NY, nit, desc, sig, epl, du, elstiff, res_sig, res_depl,     \
+                                                                     fyld, nsteps, has_res, nullptr, worklist, st, stat_first);        \
+        sweep_hill_kernel<0, true, F><<<bgrid, 128, 0, lc.stream>>>(0, NY, nit, desc, sig, epl, du, elstiff, res_sig, res_depl, fyld, \
+                                                                     nsteps, has_res, worklist, nullptr, st, stat_first);              \
+    } while (0)
+            if (fm == 8) SWEEP_HILL(8);
+            else if (fm == 4) SWEEP_HILL(4);
+            else if (fm == 6) SWEEP_HILL(6);
+            else if (fm == 7) SWEEP_HILL(7);
+            else SWEEP_HILL(0);
+#undef SWEEP_HILL
             *launches += 2;
         } else {
-            sweep_hill_kernel<0, false><<<grid, 128, 0, lc.stream>>>(Nel, NY, nit, desc, sig, epl, du, elstiff, res_sig, res_depl,
+            sweep_hill_kernel<0, false, 0><<<grid, 128, 0, lc.stream>>>(Nel, NY, nit, desc, sig, epl, du, elstiff, res_sig, res_depl,
                                                                       fyld, nsteps, has_res, nullptr, nullptr, st, stat_first);
             (*launches)++;
         }

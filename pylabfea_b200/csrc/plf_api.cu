@@ -457,8 +457,8 @@ extern "C" int plf_batch_run(plf_ctx *ctx, plf_batch *b)
     if (int brc = plf_bind(ctx)) return brc;
     LaunchCtx lc = make_lc(ctx);
     CK(launch_response(lc, ctx->hmats, ctx->nmat, b->n, b->mat_id, b->sig, b->epl, b->deps, b->fy, b->sig_out, b->depl,
-                       b->ctan, b->nsteps, b->worklist, (unsigned int *)(ctx->d_scalars + 16),
-                       (unsigned long long *)(ctx->d_scalars + 8), ctx->compact, &ctx->launches));
+                       b->ctan, b->nsteps, b->worklist, batch_counters(ctx),
+                       batch_queue(ctx), ctx->compact, &ctx->launches));
     return PLF_OK;
 }
 

@@ -38,6 +38,8 @@ void trace_kernel(const LaunchCtx &lc, const char *name, int a, int b, int c, in
 // response_kernels.cu
 cudaError_t response_init();
 cudaError_t response_upload_materials(const DevMat *h, int n, cudaStream_t st);
+// fast mode the Hill / J2 materials of a material set share (hill_fast.cuh; 0: general form), capped by max_fm
+int response_fast_mode(const DevMat *hmats, int nmat, int max_fm);
 cudaError_t launch_response(const LaunchCtx &lc, const DevMat *hmats, int nmat, int64_t n, const int32_t *mat_id,
                             const double *sig, const double *epl, const double *deps, double *fy, double *sig_out,
                             double *depl, double *ctan, int32_t *nsteps, int32_t *worklist, unsigned int *work_count,

@@ -353,7 +353,7 @@ extern "C" int plf_step_host(plf_ctx *ctx, plf_batch *b, const double *sig, cons
         CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_step[2 * c], 0));
         CK(launch_response(lc, ctx->hmats, ctx->nmat, ne, b->mat_id + e0, b->sig + o6, b->epl + o6, b->deps + o6, b->fy + e0,
                            b->sig_out + o6, b->depl + o6, b->ctan + 36 * (size_t)e0, b->nsteps + e0, b->worklist + e0,
-                           (unsigned int *)(ctx->d_scalars + 16), (unsigned long long *)(ctx->d_scalars + 8), ctx->compact,
+                           batch_counters(ctx), batch_queue(ctx), ctx->compact,
                            &ctx->launches));
         // node columns whose elements are all updated now: ja .. jb-1 (column jb needs the next chunk), plus NX at the end
         const int na = ja, nb = (c == nchunk - 1) ? NX + 1 : jb;
@@ -452,7 +452,7 @@ extern "C" int plf_step_host_packed(plf_ctx *ctx, plf_batch *b, const double *si
         CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_step[2 * c], 0));
         CK(launch_response(lc, ctx->hmats, ctx->nmat, k.ne, b->mat_id + k.e0, b->sig + o6, b->epl + o6, b->deps + o6, b->fy + k.e0,
                            b->sig_out + o6, b->depl + o6, b->ctan + 36 * (size_t)k.e0, b->nsteps + k.e0, b->worklist + k.e0,
-                           (unsigned int *)(ctx->d_scalars + 16), (unsigned long long *)(ctx->d_scalars + 8), ctx->compact,
+                           batch_counters(ctx), batch_queue(ctx), ctx->compact,
                            &ctx->launches));
         CK(launch_pack(lc, k.ne, b->mat_id + k.e0, single ? 1 : 0, b->ctan + 36 * (size_t)k.e0, b->el_words + (k.e0 >> 5),
                        b->pk_counts + (k.e0 >> 8) + c, b->pk_offsets + (k.e0 >> 8) + c, b->pk_totals + c, b->ct21 + 21 * (size_t)k.e0,

@@ -132,6 +132,13 @@ int model_reset_state(plf_ctx *ctx);            // zero u, f, element state; els
 int model_solver_buffers(plf_ctx *ctx);         // work vectors of plf_solve_linear
 // reduced solve with the boundary-condition vectors already on the device (d_fixed, d_bc_du, d_w, d_bc_f)
 int model_solve_device_bc(plf_ctx *ctx, double rtol, int max_iter, int *iters, double *relres);
+// Counters of the batch return mapping (launch_response: two-ended work list + finished blocks, SVC element queue) inside the
+// context's 4 KB scalar page.  Their own slot: the page's first 256 bytes are the SweepStats of plf_sweep, and the counters
+// must read zero when a batch starts (zeroed at context creation, re-zeroed by the last block of every launch) -- a sweep
+// followed by a batch call on the same context used to find a branch count in them and overran the work list.
+inline unsigned int *batch_counters(plf_ctx *c) { return (unsigned int *)(c->d_scalars + 2048); }
+inline unsigned long long *batch_queue(plf_ctx *c) { return (unsigned long long *)(c->d_scalars + 2064); }
+
 inline plf::LaunchCtx make_lc(const plf_ctx *c)
 {
     plf::LaunchCtx lc{c->stream, c->sm_count, c->passa_direct, c->max_fm, c->k1_only, c->passb_recur, c->passa_bulk, c->assembly_tiled};

@@ -963,6 +963,9 @@ cudaError_t response_init()
     cudaError_t e;
     // only the staged (non-direct) variants need more than the default 48 KB of dynamic shared memory
     if ((e = big_smem(response_passA_kernel<false, 0, false>, k1a_smem(false))) != cudaSuccess) return e;
+    if ((e = big_smem(response_passA_kernel<false, 4, false>, k1a_smem(false))) != cudaSuccess) return e;
+    if ((e = big_smem(response_passA_kernel<false, 6, false>, k1a_smem(false))) != cudaSuccess) return e;
+    if ((e = big_smem(response_passA_kernel<false, 7, false>, k1a_smem(false))) != cudaSuccess) return e;
     if ((e = big_smem(response_passA_kernel<true, 0, false>, k1a_smem(false))) != cudaSuccess) return e;
     if ((e = big_smem(response_passA_kernel<true, 1, false>, k1a_smem(false))) != cudaSuccess) return e;
     if ((e = big_smem(response_passA_kernel<true, 2, false>, k1a_smem(false))) != cudaSuccess) return e;
@@ -987,17 +990,34 @@ cudaError_t response_init()
 // Fast mode of a single-material Hill batch (hill_fast.cuh): 1 = block-structured symmetric CV without hydrostatic
 // term, 2 = additionally J2, 3 = additionally isotropic elasticity, 4 = 3 with planar states sorted to their own
 // loop, 6 = Hill on isotropic elasticity with its planar loop.  max_fm caps it (A/B measurements, tests).
-static int fast_mode(const DevMat *hmats, int nmat, int max_fm)
+static int fast_mode_of(const DevMat &h, int max_fm)
 {
-    if (nmat != 1 || hmats[0].kind != PLF_MAT_HILL || !hmats[0].cv_block || !hmats[0].cv_sym || hmats[0].has_d) return 0;
+    if (h.kind != PLF_MAT_HILL || !h.cv_block || !h.cv_sym || h.has_d) return 0;
     int fm = 2;
     for (int k = 0; k < 6; k++)
-        if (hmats[0].hill[k] != 1.) fm = 1;
-    if (fm == 2 && hmats[0].cv_iso) fm = 4;
-    if (fm == 1 && hmats[0].cv_iso && max_fm >= 4) return 6;   // Hill on isotropic elasticity: its own planar mode
-    if (!hmats[0].cv_iso && max_fm >= 4) return 7;              // plane-stress / cubic CV: block-CV planar mode (J2 and Hill)
+        if (h.hill[k] != 1.) fm = 1;
+    if (fm == 2 && h.cv_iso) fm = 4;
+    if (fm == 1 && h.cv_iso && max_fm >= 4) return 6;   // Hill on isotropic elasticity: its own planar mode
+    if (!h.cv_iso && max_fm >= 4) return 7;              // plane-stress / cubic CV: block-CV planar mode (J2 and Hill)
     return std::min(fm, max_fm);
 }
+// Several materials (an FE model: plastic matrix + elastic inclusion, examples/inclusion.py): the elastic ones take pass A's
+// elastic branch whatever the mode, so the batch runs in a fast mode when all its Hill / J2 materials fall into the same
+// class; only the planar modes (4, 6, 7) are instantiated for that case.
+static int fast_mode(const DevMat *hmats, int nmat, int max_fm)
+{
+    if (nmat == 1) return fast_mode_of(hmats[0], max_fm);
+    int fm = -1;
+    for (int i = 0; i < nmat; i++) {
+        if (hmats[i].kind == PLF_MAT_ELASTIC) continue;
+        const int f = fast_mode_of(hmats[i], max_fm);
+        if (fm >= 0 && f != fm) return 0;
+        fm = f;
+    }
+    return (fm == 4 || fm == 6 || fm == 7) ? fm : 0;
+}
+
+int response_fast_mode(const DevMat *hmats, int nmat, int max_fm) { return fast_mode(hmats, nmat, max_fm); }
 
 // Launches the return mapping over n elements (device pointers).  scratch: worklist[n] int32 (all -1) + counters.
 cudaError_t launch_response(const LaunchCtx &lc, const DevMat *hmats, int nmat, int64_t n, const int32_t *mat_id,
@@ -1023,7 +1043,7 @@ cudaError_t launch_response(const LaunchCtx &lc, const DevMat *hmats, int nmat, 
         if (lc.passa_bulk && (F) != 5) trace_kernel(lc, "response_passA_bulk_kernel", S, F, -1 + 1);                             \
         else trace_kernel(lc, "response_passA_kernel", S, F, direct ? 1 : 0);                                                    \
         if (lc.passa_bulk && (F) != 5)                                                                                           \
-            response_passA_bulk_kernel<S, (F) == 5 ? 0 : (F)><<<pgrid, RB, k1a_bulk_smem(), lc.stream>>>(                        \
+            response_passA_bulk_kernel<S, ((F) == 5 || !(S)) ? 0 : (F)><<<pgrid, RB, k1a_bulk_smem(), lc.stream>>>(              \
                 n, mat_id, sig, epl, deps, fy, sig_out, depl, ctan, nsteps, worklist, work_count);                               \
         else if (direct)                                                                                                              \
             response_passA_kernel<S, F, true><<<pgrid, RB, k1a_smem(true), lc.stream>>>(n, mat_id, sig, epl, deps, fy, sig_out,  \
@@ -1033,6 +1053,9 @@ cudaError_t launch_response(const LaunchCtx &lc, const DevMat *hmats, int nmat, 
                                                                                           depl, ctan, nsteps, worklist, work_count); \
     } while (0)
             if (lc.k1_only == 2) PASSA(true, 5);
+            else if (!single && fm == 7) PASSA(false, 7);
+            else if (!single && fm == 6) PASSA(false, 6);
+            else if (!single && fm == 4) PASSA(false, 4);
             else if (!single) PASSA(false, 0);
             else if (fm == 7) PASSA(true, 7);
             else if (fm == 6) PASSA(true, 6);
@@ -1075,7 +1098,11 @@ cudaError_t launch_response(const LaunchCtx &lc, const DevMat *hmats, int nmat, 
                 else if (fm == 1) PASSB(3, true, 1);
                 else PASSB(3, true, 0);
             } else {
-                PASSB(2, false, 0);
+                if (fm == 7) PASSB(3, false, 7);
+                else if (fm == 6) PASSB(3, false, 6);
+                else if (fm == 4 && lc.passb_recur) PASSB(3, false, 8);
+                else if (fm == 4) PASSB(3, false, 4);
+                else PASSB(2, false, 0);
             }
 #undef PASSB
             *launches += 2;

@@ -521,8 +521,11 @@ class Model(object):
         niter, co_nconv = [], []
         self.sweep_stats = []
         state.more = 1
+        hook = getattr(self, 'increment_hook', None)   # optional callable(model, il), called before every load increment
         while state.more:
             il = state.il
+            if hook is not None:
+                hook(self, il)
             rep = ctx.load_increment(state, min_step, self.solver_rtol, self.solver_maxit)
             self._cache = {}
             if rep.n_warnings:

@@ -388,6 +388,73 @@ def test_distributed_cg_path_with_one_rank_equals_the_single_gpu_jacobi_cg():
     assert relmax(np.array([el.sig for el in a.element]), np.array([el.sig for el in b.element])) < 1e-12
 
 
+def test_batch_calls_after_a_sweep_on_the_same_context():
+    """plf_sweep and the batch return mapping share the context's scalar page; the batch counters used to overlap the sweep's
+    branch counts (a sweep followed by plf_batch_run overran the work list).  After a solve, the model's own context must
+    return for a batch what a fresh context returns."""
+    import bench
+    from pylabfea_b200 import _lib
+    fe = inclusion(N=30, plastic=True, eps_tot=0.006)
+    fe.solve(min_step=3)
+    ctx = fe._dev()
+    assert sum(s[5][2] for s in fe.sweep_stats) > 0 and fe.sweep_stats[-1][5][0] > 0
+    n = fe.Nel
+    s0, e0, d0 = bench.synth_states(32, 99)
+    sig, epl, deps = s0[:n].copy(), e0[:n].copy(), d0[:n].copy()
+    mid = np.zeros(n, np.int32)
+    out = ctx.response_batch(sig, epl, deps, mat_id=mid)
+    fresh = _lib.Context(0)
+    try:
+        fresh.set_materials([m._descriptor() for m in fe.mat], planestress=fe.planestress)
+        ref = fresh.response_batch(sig, epl, deps, mat_id=mid)
+    finally:
+        fresh.close()
+    assert int(np.sum(ref[4] == 49)) > 0
+    for a, b in zip(out, ref):
+        assert np.array_equal(a, b)
+
+
+def test_sweep_fast_modes_equal_the_general_form():
+    """The sweep of a J2 / Hill model runs the fast device functions of the batch kernels (isotropic / planar loops, chosen per
+    material set: the elastic inclusion does not switch them off).  Against the general form (option max_fm = 0): same
+    increments and passes, same branch census in every pass, u and the state within 1e-9."""
+    def run(max_fm, hill=False):
+        N = 24
+        n1 = N // 3
+        el = np.ones((N, N))
+        el[n1:2 * n1, n1:2 * n1] = 2
+        mat1 = FE.Material(num=1)
+        mat1.elasticity(E=100.e3, nu=0.27)
+        if hill:
+            mat1.plasticity(sy=150., khard=500., hill=[1.2, 1., 0.8, 1., 1., 1.1], sdim=6)
+        else:
+            mat1.plasticity(sy=150., khard=500., sdim=6)
+        mat2 = FE.Material(num=2)
+        mat2.elasticity(E=3.e3, nu=0.3)
+        fe = FE.Model(dim=2, planestress=False)
+        fe.geom(sect=2, LX=4., LY=4.)
+        fe.assign([mat1, mat2])
+        fe.bcbot(0.)
+        fe.bcright(0., 'force')
+        fe.bcleft(0., 'force')
+        fe.bctop(0.006 * fe.leny, 'disp')
+        fe.mesh(elmts=el, NX=N, NY=N)
+        fe.bcnode(0, 0., 'disp', 'x')
+        fe._dev().set_option('max_fm', max_fm)
+        fe.solve(min_step=4)
+        return fe
+    for hill in (False, True):
+        a, b = run(0, hill), run(4, hill)
+        assert a.nsteps == b.nsteps and list(a.niter) == list(b.niter)
+        assert [s[5] for s in a.sweep_stats] == [s[5] for s in b.sweep_stats]
+        assert any(s[5][2] > 0 for s in b.sweep_stats)          # sub-stepped elements occurred
+        assert relmax(b.u, a.u) < 1e-9
+        assert relmax(b.sgl, a.sgl) < 1e-9 and np.max(np.abs(b.epgl - a.epgl)) < 1e-9 * max(np.max(np.abs(a.epgl)), 1e-12)
+        sa, sb = a._dev().get_field(0), b._dev().get_field(0)
+        assert relmax(sb, sa) < 1e-9
+
+
+
 @pytest.mark.parametrize('solver', ['distributed', 'replicated'])
 def test_partitioned_model_solve_with_one_rank_equals_the_plain_solve(solver):
     """Model.distribute with world = 1: the whole distributed machinery (plf_comm_set_partition, the controller's combined

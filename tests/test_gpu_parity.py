@@ -444,6 +444,68 @@ def test_response_full_size_fast_modes_vs_oracle(ctx):
             ctx.set_option(k, v)
 
 
+def FE_elastic(E, nu):
+    """plf_material of an isotropic elastic material (3-d stiffness), as bench.j2_material builds its J2 one."""
+    from pylabfea_b200 import _lib
+    m = _lib.PlfMaterial()
+    m.kind = _lib.MAT_ELASTIC
+    m.E, m.nu = E, nu
+    hh = E / ((1. + nu) * (1. - 2. * nu))
+    C11, C12, C44 = (1. - nu) * hh, nu * hh, (0.5 - nu) * hh
+    CV = np.zeros((6, 6))
+    CV[:3, :3] = C12
+    CV[0, 0] = CV[1, 1] = CV[2, 2] = C11
+    CV[3, 3] = CV[4, 4] = CV[5, 5] = C44
+    m.CV[:] = list(CV.ravel())
+    m.C44 = C44
+    m.hill[:] = [1.] * 6
+    return m
+
+
+def test_fast_modes_with_an_elastic_second_material(ctx):
+    """An FE model's material set -- J2 matrix + elastic inclusion (examples/inclusion.py) -- runs in the J2 fast modes too: the
+    elastic elements take pass A's elastic branch, the plastic ones the planar isotropic loops.  Same branch per element and
+    results within 1e-10 of the general form (max_fm = 0), and equal to the oracle on a sample."""
+    import bench
+    from oracle import oracle as orc
+    N = 512
+    mat, CV = bench.j2_material()
+    soft = FE_elastic(3.e3, 0.3)
+    ctx.set_materials([mat, soft], planestress=False)
+    sig, epl, deps = bench.synth_states(N, 4321)
+    n = N * N
+    rng = np.random.default_rng(5)
+    mid = (rng.random(n) < 0.15).astype(np.int32)
+    epl[mid == 1] = 0.
+    ctx.last_kernels()
+    try:
+        ctx.set_option('max_fm', 0)
+        ref = ctx.response_batch(sig, epl, deps, mat_id=mid)
+        assert 'response_passA_kernel<0, 0, 0>' in ctx.last_kernels()
+        ctx.set_option('max_fm', 4)
+        out = ctx.response_batch(sig, epl, deps, mat_id=mid)
+        names = ctx.last_kernels()
+        assert 'response_passA_kernel<0, 4, 0>' in names and 'response_passB_kernel<3, 0, 8>' in names, names
+    finally:
+        ctx.set_option('max_fm', 4)
+    assert np.array_equal(out[4], ref[4])
+    assert int(np.sum(out[4] == 49)) > 0.05 * n
+    for a, b in zip(out[:4], ref[:4]):
+        assert np.max(np.abs(a - b)) <= 1e-10 * np.max(np.abs(b))
+    # elastic elements: stress from CV, no plastic strain, tangent = CV (Model.solve never calls response for them, model.py:1341)
+    el = mid == 1
+    CV1 = ctx.element_CV(1)
+    assert np.all(out[4][el] == 0) and np.all(out[2][el] == 0.) and np.array_equal(out[3][el], np.broadcast_to(CV1, (int(el.sum()), 6, 6)))
+    assert relmax(out[1][el], sig[el] + deps[el] @ CV1.T) < 1e-13
+    idx = rng.choice(np.nonzero(~el)[0], 20000, replace=False)
+    mats = [orc.Mat(kind=orc.HILL, E=bench.E_MOD, nu=bench.NU, sy=bench.SY, khard=bench.KHARD), orc.Mat(kind=orc.ELASTIC, E=3.e3, nu=0.3)]
+    CVs = np.array([CV, CV1])
+    oref = orc.response_batch(mats, mid[idx], sig[idx], epl[idx], deps[idx], CVs)
+    assert np.array_equal(out[4][idx], oref[4])
+    assert relmax(out[1][idx], oref[1]) < TOL and relmax(out[3][idx], oref[3]) < TOL
+    assert np.max(np.abs(out[2][idx] - oref[2])) < TOL * np.max(np.abs(oref[2]))
+
+
 @pytest.mark.parametrize('shape', [(40, 24), (3, 70), (1, 5)])
 def test_step_host_pipelined_equals_unpipelined(ctx, shape):
     """plf_step_host (chunked upload / update + column-range assembly / download on three streams) returns exactly
