@@ -10,10 +10,11 @@ import pytest
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-def _torchrun(args, port, timeout=300, nproc=2, script='bench.py'):
+def _torchrun(args, port, timeout=300, nproc=2, script='bench.py', extra_env=None):
     cmd = [sys.executable, '-m', 'torch.distributed.run', '--nnodes=1', '--nproc-per-node', str(nproc), '--master-addr', '127.0.0.1',
            '--master-port', str(port), os.path.join(ROOT, script)] + args
     env = dict(os.environ)
+    env.update(extra_env or {})
     env.setdefault('OMP_NUM_THREADS', '1')
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=timeout, cwd=ROOT, env=env)
     assert r.returncode == 0, r.stderr[-2000:]
@@ -126,3 +127,25 @@ def test_strip_partitioned_cg_rehearsal_over_gloo(nproc, port):
     assert d['max_rel_err'] < 1e-9
     # the replicated solve: the owned row ranges of all ranks tile the global K exactly once, bit for bit
     assert d['gathered_rows_equal_global'] and d['replicated_max_rel_err'] == 0.
+
+
+@pytest.mark.parametrize('nproc,port', [(2, 29651), (3, 29652)])
+def test_shared_multigrid_levels_rehearsal_over_gloo(nproc, port):
+    """The V-cycle with its finest levels shared among the ranks (mg_vcycle with MgDist / mg_plan_sharing: the default solver
+    of a distributed Model.solve) rehearsed with real ranks over gloo (tests/dist_shared_vcycle_gloo.py): row ranges per
+    level, one ghost column swapped after every step whose output the next stencil reads, gathered right-hand side of the
+    first replicated level.  Entries a rank neither owns nor received are NaN, so a missing swap or a wrong range poisons
+    the result.  1, 2 and 3 shared levels, even and odd column splits, 3 ranks for a rank with two neighbours: the cycle
+    equals the single-process cycle."""
+    out = _torchrun([], port, nproc=nproc, script=os.path.join('tests', 'dist_shared_vcycle_gloo.py'))
+    assert len(out) == 1 and out[0]['world'] == nproc
+    cases = out[0]['cases']
+    assert {c['shared'] for c in cases} == {1, 2, 3} and len(cases) >= 8
+    assert all(c['max_rel_err'] <= 1e-13 for c in cases), cases
+
+
+def test_shared_multigrid_rehearsal_detects_a_missing_swap():
+    """Self-check of the rehearsal: without the ghost swap of the residual the restriction reads columns nobody sent."""
+    out = _torchrun([], 29653, nproc=2, script=os.path.join('tests', 'dist_shared_vcycle_gloo.py'),
+                    extra_env={'PLF_REHEARSAL_SKIP_RESIDUAL_SWAP': '1'})
+    assert any(c['max_rel_err'] > 1. for c in out[0]['cases'])
