@@ -109,7 +109,8 @@ int plf_pinned_free(void *p);
 /* tuning / A-B switches; unknown keys return PLF_EINVAL:
  *   "compact"      1 (default): two-pass return mapping, the 50-sub-step elements are compacted into a dense second
  *                  launch instead of diverging inside the first one; 0: one unsplit kernel
- *   "max_fm"       cap of the single-material fast mode (hill_fast.cuh; default 4, 0 = general Hill kernels)
+ *   "max_fm"       cap of the fast mode of the Hill / J2 materials of the set (hill_fast.cuh; default 4, 0 = general Hill kernels;
+ *                  batch kernels and plf_sweep alike; elastic materials in the set do not switch it off)
  *   "passb_recur"  1 (default): recurrence form of the planar isotropic sub-step loop of pass B; 0: direct form
  *   "passa_direct" 1: pass A writes its records with per-thread 256-bit stores; 0 (default): staged coalesced stores
  *   "assembly_tiled" 1 (default): staged coalesced CSR stores; 0: direct stores
