@@ -1,6 +1,7 @@
 // plf_comm.cu -- NCCL plumbing of the strip-partitioned solve and its C-ABI entry points (include/plfb200.h).
 #include <dlfcn.h>
 
+#include <algorithm>
 #include <cstdlib>
 #include <cstring>
 #include <string>
@@ -249,7 +250,25 @@ int comm_p2p_setup(Comm &c, int cols, cudaStream_t s)
     const char *env = getenv("PLF_P2P");
     if (env && env[0] == '0') { p2p_release(c); return 0; }
     if (c.p2p && c.box_cols >= cols) return 0;   // every rank sees the same NY, hence takes the same branch
-    p2p_release(c);
+    double *d_h = nullptr;
+    cudaError_t e = cudaMalloc(&d_h, (size_t)c.world * 64 + 8);
+    if (e != cudaSuccess) return cuda_fail("comm_p2p_setup", e);
+    if (c.box) {
+        // A mesh with longer node columns than the mailbox holds (slots are sized for NY <= 8192 up front, so this is rare):
+        // unmap the peers' mailboxes, wait until every rank has done the same (an exported allocation must not be freed while
+        // another process still maps it), then free the own one.  The barrier runs on NCCL: p2p is off from here on.
+        c.p2p = false;
+        for (int r = 0; r < 64; r++) {
+            if (c.peer_box[r] && c.peer_box[r] != c.box) cudaIpcCloseMemHandle(c.peer_box[r]);
+            c.peer_box[r] = nullptr;
+        }
+        e = cudaMemsetAsync(d_h, 0, sizeof(double), s);
+        if (e == cudaSuccess && comm_allreduce_op(c, d_h, 1, 0, s)) { cudaFree(d_h); return 1; }
+        if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+        if (e != cudaSuccess) { cudaFree(d_h); return cuda_fail("comm_p2p_setup", e); }
+        p2p_release(c);
+    }
+    cols = std::max(cols, 2 * 8193);
     // every step below is attempted by all ranks, and the outcome is agreed on at the end: no rank may skip a collective
     bool ok = true;
     const size_t bytes = HALO_OFF + 4 * (size_t)cols * sizeof(double);
@@ -259,9 +278,6 @@ int comm_p2p_setup(Comm &c, int cols, cudaStream_t s)
     ok = ok && cudaMalloc(&c.box, bytes) == cudaSuccess;
     ok = ok && cudaMemset(c.box, 0, bytes) == cudaSuccess;
     ok = ok && cudaIpcGetMemHandle(&mine_h, c.box) == cudaSuccess;
-    double *d_h = nullptr;
-    cudaError_t e = cudaMalloc(&d_h, (size_t)c.world * 64 + 8);
-    if (e != cudaSuccess) return cuda_fail("comm_p2p_setup", e);
     std::string all((size_t)c.world * 64, '\0');
     int64_t goff[64], cnt[64];
     for (int r = 0; r < c.world; r++) { goff[r] = 8 * r; cnt[r] = 8; }
