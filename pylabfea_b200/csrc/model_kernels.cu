@@ -172,7 +172,7 @@ __device__ __forceinline__ ElemStats sweep_finish(const DevMat &m, int64_t e, in
 //   the direct / recurrence form of the planar sub-step loop, 6 Hill on isotropic elasticity, 7 block-structured CV) -- the same
 //   device functions as the batch kernels of response_kernels.cu, so a sweep and plf_response_batch agree bit for bit
 template <int MODE, bool GATHER, int FM>
-__global__ void __launch_bounds__(128) sweep_hill_kernel(int64_t n, int NY, int nit, const int32_t *__restrict__ desc,
+__global__ void __launch_bounds__(128, (GATHER && FM != 0) ? 3 : 1) sweep_hill_kernel(int64_t n, int NY, int nit, const int32_t *__restrict__ desc,
                                                          const double *__restrict__ sig, const double *__restrict__ epl,
                                                          const double *__restrict__ du, double *__restrict__ elstiff,
                                                          double *__restrict__ res_sig, double *__restrict__ res_depl,
