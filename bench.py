@@ -581,6 +581,10 @@ def run_coupled_solve(group, rank, world, local, N=256, min_step=3, eps=0.002):
             'inner_passes': [int(x) for x in fe.niter], 'linear_solves': len(fe.solver_stats), 'cg_iterations': its,
             'element_updates': updates, 'element_updates_per_s': updates / dt,
             'collectives_per_pass': 0 if world == 1 else 'K gather (%d broadcasts) + 2 all-reduces of sweep flags' % world,
+            'exchanges_per_cg_iteration': 0 if world == 1 else (
+                'shared levels: 1 ghost-column swap per smoothing / residual step of every shared level and 1 for p (5-6 per level), '
+                '2 scalar all-reduces, 1 gather of the first replicated level (%d broadcasts)' % world if ctx.comm_p2p()
+                else 'none (every rank solves the gathered system alone)'),
             'launches_rank0': int(launches() - l0), 'global_stress_yy': float(fe.glob['sig'][1])}
 
 
